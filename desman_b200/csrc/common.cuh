@@ -1,0 +1,78 @@
+// desman_b200/csrc/common.cuh -- shared device helpers (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define DESMAN_FULL_MASK 0xffffffffu
+
+// counter "stage" tags of the Philox contract; c3 = stage<<28 | ...
+enum { STAGE_TAU = 1, STAGE_MU = 2, STAGE_GAMMA = 3, STAGE_ETA = 4, STAGE_GAMMA_BOOST = 5, STAGE_ETA_BOOST = 6 };
+
+// Philox4x32-10 (Salmon, Moraes, Dror, Shaw 2011).  Counter-based: every draw of the chain is a
+// pure function of (seed, sweep, stage, site, sample, base, index), so results do not depend on
+// grid shape, warp scheduling or GPU count.
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0;
+        uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ double warp_sum(double x)
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) x += __shfl_xor_sync(DESMAN_FULL_MASK, x, m);
+    return x;  // xor butterfly: every lane ends with the bit-identical sum
+}
+
+__device__ __forceinline__ float warp_sum(float x)
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) x += __shfl_xor_sync(DESMAN_FULL_MASK, x, m);
+    return x;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long x)
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) x += __shfl_xor_sync(DESMAN_FULL_MASK, x, m);
+    return x;
+}
+
+__device__ __forceinline__ float warp_max(float x)
+{
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) x = fmaxf(x, __shfl_xor_sync(DESMAN_FULL_MASK, x, m));
+    return x;
+}
+
+// 2-bit-per-strain packed haplotype code of one site (G <= 32), built from the uint8 tau row.
+__device__ __forceinline__ uint64_t load_tau_code(const uint8_t *__restrict__ tau_row, int G, int lane)
+{
+    uint32_t t = (lane < G) ? (uint32_t)tau_row[lane] & 3u : 0u;
+    uint32_t lo = __reduce_or_sync(DESMAN_FULL_MASK, lane < 16 ? t << (2 * lane) : 0u);
+    uint32_t hi = __reduce_or_sync(DESMAN_FULL_MASK, lane >= 16 ? t << (2 * (lane - 16)) : 0u);
+    return ((uint64_t)hi << 32) | lo;
+}
+
+__device__ __forceinline__ int code_get(uint64_t code, int g) { return (int)((code >> (2 * g)) & 3ull); }
+__device__ __forceinline__ uint64_t code_set(uint64_t code, int g, int b)
+{
+    return (code & ~(3ull << (2 * g))) | ((uint64_t)b << (2 * g));
+}
+
+__device__ __forceinline__ int4 ld_counts(const int4 *p)
+{
+    int4 r;  // streaming 128-bit load: one (v,s) cell, read once per pass
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}

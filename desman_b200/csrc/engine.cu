@@ -1,0 +1,965 @@
+// desman_b200/csrc/engine.cu -- host side of libdesman_b200.so: contexts, device memory, streams,
+// the sweep drivers and the C-ABI declared in include/desman_b200.h.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/desman_b200.h"
+#include "common.cuh"
+#include "misc_kernels.cuh"
+#include "mu_kernel.cuh"
+#include "nmft_kernel.cuh"
+#include "tau_kernel.cuh"
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[1024] = "";
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(DESMAN_ECUDA, "%s failed at %s:%d: %s", #call, __FILE__, __LINE__,        \
+                        cudaGetErrorString(e_));                                                  \
+    } while (0)
+#define RET(call)                   \
+    do {                            \
+        int r_ = (call);            \
+        if (r_ != DESMAN_OK) return r_; \
+    } while (0)
+
+extern "C" const char *desman_last_error(void) { return g_err; }
+extern "C" const char *desman_build_info(void) { return "desman_b200 0.1 (sm_100a; kernels: tau_sample, mu_stats, draw_gamma_eta, finalize_sweep, mt19937, nmft)"; }
+extern "C" int desman_device_count(int *n)
+{
+    CU(cudaGetDeviceCount(n));
+    return DESMAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ NCCL (dlopen)
+// The per-sweep exchange is one small all-reduce.  NCCL is bound at run time so the single-GPU
+// library has no link-time dependency and shares whatever libnccl the process already loaded.
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef void *nccl_comm_t;
+struct NcclApi {
+    void *h = nullptr;
+    int (*GetUniqueId)(nccl_uid_t *) = nullptr;
+    int (*CommInitRank)(nccl_comm_t *, int, nccl_uid_t, int) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+};
+static NcclApi g_nccl;
+enum { NCCL_INT64 = 4, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+
+static int nccl_load()
+{
+    if (g_nccl.h) return DESMAN_OK;
+    const char *names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    void *h = nullptr;
+    for (int i = 0; names[i] && !h; i++) h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    const char *env = getenv("DESMAN_B200_NCCL");
+    if (!h && env) h = dlopen(env, RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return fail(DESMAN_ECOMM, "cannot dlopen libnccl.so.2 (set DESMAN_B200_NCCL=/path/to/libnccl.so.2): %s", dlerror());
+    g_nccl.GetUniqueId = (int (*)(nccl_uid_t *))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(nccl_comm_t *, int, nccl_uid_t, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.CommDestroy = (int (*)(nccl_comm_t))dlsym(h, "ncclCommDestroy");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+    g_nccl.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce || !g_nccl.CommDestroy)
+        return fail(DESMAN_ECOMM, "libnccl is missing required symbols");
+    g_nccl.h = h;
+    return DESMAN_OK;
+}
+#define NC(call)                                                                                         \
+    do {                                                                                                 \
+        int e_ = (call);                                                                                 \
+        if (e_ != 0)                                                                                     \
+            return fail(DESMAN_ECOMM, "%s failed: %s", #call, g_nccl.GetErrorString ? g_nccl.GetErrorString(e_) : "?"); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------ context
+struct desman_ctx {
+    int device = 0, sm_count = 148;
+    cudaStream_t stream = nullptr;
+    int rng_mode = DESMAN_RNG_PHILOX;
+    uint64_t seed = 0;
+    uint32_t sweep = 0;            // Philox sweep counter (persists across update() calls)
+    uint64_t mt_consumed = 0;      // MT19937 words consumed so far
+    int mt_pos = 624;              // position inside the current 624-word block
+    double alpha = 0.1, delta = 0.1, epsilon = 1e-6;
+
+    int64_t V = 0, v0 = 0, V_total = 0;
+    int S = 0, G = 0;
+    // device buffers
+    int4 *counts = nullptr;
+    uint8_t *tau = nullptr, *tau_star = nullptr;
+    double *gamma = nullptr, *eta = nullptr, *eta_new = nullptr, *gamma_star = nullptr, *eta_star = nullptr;
+    unsigned long long *stats = nullptr;     // [S*G + 16] sum_mu | esum
+    unsigned long long *nchange = nullptr;
+    double *ll_partial = nullptr;
+    int ll_partial_n = 0;
+    double *red = nullptr;                   // [2]
+    double *scal = nullptr;                  // [4] lp_star, iter_star, ll, lp
+    int *flag = nullptr;
+    uint32_t *tau_cnt = nullptr, *tau_last = nullptr;
+    uint32_t *mt_state = nullptr, *words = nullptr;
+    size_t words_cap = 0;
+    double ll_const = 0.0;
+    bool ll_const_valid = false;
+    size_t counts_cap = 0;
+    size_t cap_vg = 0, cap_sg = 0;
+    uint32_t last_n_iter = 0;
+    // scratch
+    void *scratch = nullptr;
+    size_t scratch_cap = 0;
+    // comm
+    nccl_comm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    // profiling
+    int prof_kernels = 0, prof_flush = 0;
+    uint4 *flush_buf = nullptr;
+    size_t flush_n = 0;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    struct Span { int kind; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> sweep_spans;
+    double elapsed_ms = 0.0, k_ms[DESMAN_K_COUNT] = {0};
+    int64_t k_launch[DESMAN_K_COUNT] = {0};
+};
+
+static int ensure_scratch(desman_ctx *c, size_t bytes)
+{
+    if (bytes <= c->scratch_cap) return DESMAN_OK;
+    if (c->scratch) cudaFree(c->scratch);
+    c->scratch = nullptr; c->scratch_cap = 0;
+    CU(cudaMalloc(&c->scratch, bytes));
+    c->scratch_cap = bytes;
+    return DESMAN_OK;
+}
+
+static cudaEvent_t get_event(desman_ctx *c)
+{
+    if (c->ev_used == c->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        c->ev_pool.push_back(e);
+    }
+    return c->ev_pool[c->ev_used++];
+}
+
+struct KSpan {  // brackets one kernel launch with events when per-kernel profiling is on
+    desman_ctx *c; int kind; cudaEvent_t a = nullptr;
+    KSpan(desman_ctx *c_, int kind_) : c(c_), kind(kind_)
+    {
+        c->k_launch[kind]++;
+        if (c->prof_kernels) { a = get_event(c); cudaEventRecord(a, c->stream); }
+    }
+    ~KSpan()
+    {
+        if (a) { cudaEvent_t b = get_event(c); cudaEventRecord(b, c->stream); c->spans.push_back({kind, a, b}); }
+    }
+};
+
+static void timing_reset(desman_ctx *c)
+{
+    c->ev_used = 0; c->spans.clear(); c->sweep_spans.clear();
+    c->elapsed_ms = 0.0;
+    for (int i = 0; i < DESMAN_K_COUNT; i++) { c->k_ms[i] = 0.0; c->k_launch[i] = 0; }
+}
+static void timing_collect(desman_ctx *c)
+{
+    for (auto &s : c->spans) { float ms = 0; cudaEventElapsedTime(&ms, s.a, s.b); c->k_ms[s.kind] += ms; }
+    for (auto &s : c->sweep_spans) { float ms = 0; cudaEventElapsedTime(&ms, s.first, s.second); c->elapsed_ms += ms; }
+}
+static void sweep_begin(desman_ctx *c)
+{
+    cudaEvent_t a = get_event(c);
+    cudaEventRecord(a, c->stream);
+    c->sweep_spans.push_back({a, nullptr});
+}
+static void sweep_end(desman_ctx *c)
+{
+    cudaEvent_t b = get_event(c);
+    cudaEventRecord(b, c->stream);
+    c->sweep_spans.back().second = b;
+    if (c->prof_flush && c->flush_buf) l2_flush_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(c->flush_buf, c->flush_n);
+}
+
+extern "C" int desman_ctx_create(desman_ctx **out, int device, uint64_t seed, int rng_mode)
+{
+    if (!out) return fail(DESMAN_EINVAL, "desman_ctx_create: out is NULL");
+    if (rng_mode != DESMAN_RNG_MT19937 && rng_mode != DESMAN_RNG_PHILOX) return fail(DESMAN_EINVAL, "bad rng_mode %d", rng_mode);
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) return fail(DESMAN_EINVAL, "device %d out of range (have %d)", device, n);
+    CU(cudaSetDevice(device));
+    desman_ctx *c = new desman_ctx();
+    c->device = device;
+    c->rng_mode = rng_mode;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&c->eta, 16 * sizeof(double)));
+    CU(cudaMalloc(&c->eta_new, 16 * sizeof(double)));
+    CU(cudaMalloc(&c->eta_star, 16 * sizeof(double)));
+    CU(cudaMalloc(&c->nchange, sizeof(unsigned long long)));
+    CU(cudaMalloc(&c->red, 2 * sizeof(double)));
+    CU(cudaMalloc(&c->scal, 4 * sizeof(double)));
+    CU(cudaMalloc(&c->flag, sizeof(int)));
+    CU(cudaMalloc(&c->mt_state, 624 * sizeof(uint32_t)));
+    CU(cudaMemset(c->scal, 0, 4 * sizeof(double)));
+    *out = c;
+    return desman_set_rng(c, seed, 0, 0);
+}
+
+extern "C" int desman_ctx_destroy(desman_ctx *c)
+{
+    if (!c) return DESMAN_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    void *ptrs[] = {c->counts, c->tau, c->tau_star, c->gamma, c->eta, c->eta_new, c->gamma_star, c->eta_star, c->stats,
+                    c->nchange, c->ll_partial, c->red, c->scal, c->flag, c->tau_cnt, c->tau_last, c->mt_state, c->words,
+                    c->scratch, c->flush_buf};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return DESMAN_OK;
+}
+
+extern "C" int desman_synchronize(desman_ctx *c)
+{
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return DESMAN_OK;
+}
+
+extern "C" int desman_set_hyper(desman_ctx *c, double alpha, double delta, double epsilon)
+{
+    if (!(alpha > 0) || !(delta > 0) || !(epsilon >= 0)) return fail(DESMAN_EINVAL, "alpha, delta must be > 0 and epsilon >= 0");
+    c->alpha = alpha; c->delta = delta; c->epsilon = epsilon;
+    return DESMAN_OK;
+}
+
+// GSL gsl_rng_set for gsl_rng_mt19937 (seed 0 -> 4357), then skip `consumed` words.
+static int mt_seed(desman_ctx *c, uint64_t seed, uint64_t consumed)
+{
+    uint32_t st[624];
+    uint32_t s = (uint32_t)(seed & 0xffffffffu);
+    if (s == 0) s = 4357u;
+    st[0] = s;
+    for (int i = 1; i < 624; i++) st[i] = 1812433253u * (st[i - 1] ^ (st[i - 1] >> 30)) + (uint32_t)i;
+    CU(cudaMemcpyAsync(c->mt_state, st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    c->mt_pos = 624;
+    c->mt_consumed = 0;
+    if (consumed) {  // advance without storing
+        mt19937_kernel<<<1, 256, 0, c->stream>>>(c->mt_state, c->mt_pos, (size_t)consumed, 0, 0, nullptr);
+        CU(cudaGetLastError());
+        c->mt_pos = (int)((consumed - 1) % 624) + 1;
+        c->mt_consumed = consumed;
+    }
+    return DESMAN_OK;
+}
+
+extern "C" int desman_set_rng(desman_ctx *c, uint64_t seed, uint32_t sweep, uint64_t mt_words_consumed)
+{
+    CU(cudaSetDevice(c->device));
+    c->seed = seed;
+    c->sweep = sweep;
+    return mt_seed(c, seed, mt_words_consumed);
+}
+
+extern "C" int desman_get_rng(desman_ctx *c, uint32_t *sweep, uint64_t *mt_words_consumed)
+{
+    if (sweep) *sweep = c->sweep;
+    if (mt_words_consumed) *mt_words_consumed = c->mt_consumed;
+    return DESMAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ data
+extern "C" int desman_set_counts(desman_ctx *c, const int64_t *variants, int64_t V, int S, int64_t v0, int64_t V_total)
+{
+    if (!variants || V <= 0 || S <= 0) return fail(DESMAN_EINVAL, "desman_set_counts: need V > 0, S > 0 and a counts pointer");
+    if (V > 0x7fffffff || S >= (1 << 26)) return fail(DESMAN_EINVAL, "V or S too large");
+    if (V_total <= 0) V_total = V;
+    if (v0 < 0 || v0 + V > V_total) return fail(DESMAN_EINVAL, "shard [v0, v0+V) outside [0, V_total)");
+    CU(cudaSetDevice(c->device));
+    const size_t ncell = (size_t)V * S;
+    if (ncell > c->counts_cap) {
+        if (c->counts) cudaFree(c->counts);
+        c->counts = nullptr; c->counts_cap = 0;
+        CU(cudaMalloc(&c->counts, ncell * sizeof(int4)));
+        c->counts_cap = ncell;
+    }
+    // stage the int64 tensor in bounded chunks and repack on device
+    const size_t chunk_cells = ncell < ((size_t)8 << 20) ? ncell : ((size_t)8 << 20);
+    RET(ensure_scratch(c, chunk_cells * 32 + 64));
+    int *err = (int *)((char *)c->scratch + chunk_cells * 32);
+    CU(cudaMemsetAsync(err, 0, sizeof(int), c->stream));
+    for (size_t off = 0; off < ncell; off += chunk_cells) {
+        const size_t n = (ncell - off < chunk_cells) ? ncell - off : chunk_cells;
+        CU(cudaMemcpyAsync(c->scratch, variants + off * 4, n * 32, cudaMemcpyHostToDevice, c->stream));
+        pack_counts_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>((const long long *)c->scratch, c->counts + off, n, err);
+        CU(cudaGetLastError());
+    }
+    int herr = 0;
+    CU(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (herr) { c->V = 0; return fail(DESMAN_EINVAL, "counts must be in [0, %d] per (v,s,base) cell", DESMAN_MAX_COUNT); }
+    if (V != c->V || S != c->S) c->G = 0;  // state must be (re)set for a new shape
+    c->V = V; c->S = S; c->v0 = v0; c->V_total = V_total;
+    c->ll_const_valid = false;
+    return DESMAN_OK;
+}
+
+// constant multinomial-coefficient part of the log-likelihood (Desman_Utils.py:28-33), computed on first use
+static int ensure_ll_const(desman_ctx *c)
+{
+    if (c->ll_const_valid) return DESMAN_OK;
+    const int nb = c->sm_count * 4;
+    double *dpart = nullptr;
+    CU(cudaMalloc(&dpart, nb * sizeof(double)));
+    lgamma_const_kernel<<<nb, 256, 0, c->stream>>>(c->counts, (size_t)c->V * c->S, dpart);
+    CU(cudaGetLastError());
+    std::vector<double> part(nb);
+    CU(cudaMemcpyAsync(part.data(), dpart, nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(dpart);
+    double t = 0.0;
+    for (double x : part) t += x;
+    c->ll_const = t;
+    c->ll_const_valid = true;
+    return DESMAN_OK;
+}
+
+static int ensure_state(desman_ctx *c, int G)
+{
+    if (c->V <= 0) return fail(DESMAN_ESTATE, "set counts before state");
+    if (G < 1 || G > DESMAN_MAX_G) return fail(DESMAN_EINVAL, "G must be in [1, %d]", DESMAN_MAX_G);
+    const size_t nvg = (size_t)c->V * G, nsg = (size_t)c->S * G;
+    if (nvg > c->cap_vg) {
+        for (void *p : {(void *)c->tau, (void *)c->tau_star, (void *)c->tau_cnt, (void *)c->tau_last}) if (p) cudaFree(p);
+        c->tau = c->tau_star = nullptr; c->tau_cnt = c->tau_last = nullptr; c->cap_vg = 0;
+        CU(cudaMalloc(&c->tau, nvg));
+        CU(cudaMalloc(&c->tau_star, nvg));
+        CU(cudaMalloc(&c->tau_cnt, nvg * 4 * sizeof(uint32_t)));
+        CU(cudaMalloc(&c->tau_last, nvg * sizeof(uint32_t)));
+        c->cap_vg = nvg;
+    }
+    if (nsg > c->cap_sg) {
+        for (void *p : {(void *)c->gamma, (void *)c->gamma_star, (void *)c->stats}) if (p) cudaFree(p);
+        c->gamma = c->gamma_star = nullptr; c->stats = nullptr; c->cap_sg = 0;
+        CU(cudaMalloc(&c->gamma, nsg * sizeof(double)));
+        CU(cudaMalloc(&c->gamma_star, nsg * sizeof(double)));
+        CU(cudaMalloc(&c->stats, (nsg + 16) * sizeof(unsigned long long)));
+        c->cap_sg = nsg;
+    }
+    if (G != c->G) {
+        CU(cudaMemsetAsync(c->tau_cnt, 0, nvg * 4 * sizeof(uint32_t), c->stream));
+        CU(cudaMemsetAsync(c->tau_last, 0, nvg * sizeof(uint32_t), c->stream));
+    }
+    c->G = G;
+    return DESMAN_OK;
+}
+
+// int64 one-hot [n,4] -> uint8 index; first b with tau == 1 (c_sample_tau.c:115-123); rows without a 1 are rejected
+static int onehot_to_index(const int64_t *tau, size_t n, uint8_t *idx)
+{
+    for (size_t i = 0; i < n; i++) {
+        const int64_t *t = tau + i * 4;
+        int b = t[0] == 1 ? 0 : t[1] == 1 ? 1 : t[2] == 1 ? 2 : t[3] == 1 ? 3 : -1;
+        if (b < 0) return fail(DESMAN_EINVAL, "tau row %zu is not one-hot (undefined behaviour in the reference, c_sample_tau.c:115-123)", i);
+        idx[i] = (uint8_t)b;
+    }
+    return DESMAN_OK;
+}
+
+extern "C" int desman_set_tau_index(desman_ctx *c, const uint8_t *tau_idx, int G)
+{
+    CU(cudaSetDevice(c->device));
+    RET(ensure_state(c, G));
+    const size_t nvg = (size_t)c->V * G;
+    for (size_t i = 0; i < nvg; i++) if (tau_idx[i] > 3) return fail(DESMAN_EINVAL, "tau index %zu out of range", i);
+    CU(cudaMemcpyAsync(c->tau, tau_idx, nvg, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return DESMAN_OK;
+}
+
+extern "C" int desman_get_tau_index(desman_ctx *c, uint8_t *tau_idx)
+{
+    if (!c->G) return fail(DESMAN_ESTATE, "no state");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(tau_idx, c->tau, (size_t)c->V * c->G, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return DESMAN_OK;
+}
+
+extern "C" int desman_set_state(desman_ctx *c, const int64_t *tau, const double *gamma, const double *eta, int G)
+{
+    CU(cudaSetDevice(c->device));
+    RET(ensure_state(c, G));
+    if (tau) {
+        std::vector<uint8_t> idx((size_t)c->V * G);
+        RET(onehot_to_index(tau, idx.size(), idx.data()));
+        CU(cudaMemcpyAsync(c->tau, idx.data(), idx.size(), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    if (gamma) {
+        for (size_t i = 0; i < (size_t)c->S * G; i++)
+            if (!(gamma[i] > 0.0)) return fail(DESMAN_EINVAL, "gamma[%zu] = %g must be > 0", i, gamma[i]);
+        CU(cudaMemcpyAsync(c->gamma, gamma, (size_t)c->S * G * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    if (eta) {
+        for (int i = 0; i < 16; i++) if (!(eta[i] > 0.0)) return fail(DESMAN_EINVAL, "eta[%d] = %g must be > 0", i, eta[i]);
+        CU(cudaMemcpyAsync(c->eta, eta, 16 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    return DESMAN_OK;
+}
+
+static void index_to_onehot(const uint8_t *idx, size_t n, int64_t *tau)
+{
+    for (size_t i = 0; i < n; i++) {
+        int64_t *t = tau + i * 4;
+        t[0] = t[1] = t[2] = t[3] = 0;
+        t[idx[i] & 3] = 1;
+    }
+}
+
+extern "C" int desman_get_state(desman_ctx *c, int64_t *tau, double *gamma, double *eta)
+{
+    if (!c->G) return fail(DESMAN_ESTATE, "no state");
+    CU(cudaSetDevice(c->device));
+    std::vector<uint8_t> idx;
+    if (tau) {
+        idx.resize((size_t)c->V * c->G);
+        CU(cudaMemcpyAsync(idx.data(), c->tau, idx.size(), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (gamma) CU(cudaMemcpyAsync(gamma, c->gamma, (size_t)c->S * c->G * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    if (eta) CU(cudaMemcpyAsync(eta, c->eta, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (tau) index_to_onehot(idx.data(), idx.size(), tau);
+    return DESMAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ launches
+static int tau_grid(desman_ctx *c)
+{
+    int64_t want = (c->V + TAU_WARPS - 1) / TAU_WARPS;
+    int64_t cap = (int64_t)c->sm_count * 4;
+    return (int)(want < cap ? want : cap);
+}
+
+static int ensure_ll_partial(desman_ctx *c, int n)
+{
+    if (n <= c->ll_partial_n) return DESMAN_OK;
+    if (c->ll_partial) cudaFree(c->ll_partial);
+    c->ll_partial = nullptr; c->ll_partial_n = 0;
+    CU(cudaMalloc(&c->ll_partial, n * sizeof(double)));
+    c->ll_partial_n = n;
+    return DESMAN_OK;
+}
+
+// Draw the V*G uniform words of one c_sample_tau call from the MT19937 stream (rank slice under sharding).
+static int gen_mt_words(desman_ctx *c)
+{
+    const size_t total = (size_t)c->V_total * c->G, lo = (size_t)c->v0 * c->G, n = (size_t)c->V * c->G;
+    if (n > c->words_cap) {
+        if (c->words) cudaFree(c->words);
+        c->words = nullptr; c->words_cap = 0;
+        CU(cudaMalloc(&c->words, n * sizeof(uint32_t)));
+        c->words_cap = n;
+    }
+    {
+        KSpan k(c, DESMAN_K_MT);
+        mt19937_kernel<<<1, 256, 0, c->stream>>>(c->mt_state, c->mt_pos, total, lo, lo + n, c->words);
+    }
+    CU(cudaGetLastError());
+    c->mt_consumed += total;
+    c->mt_pos = (int)((c->mt_consumed - 1) % 624) + 1;
+    return DESMAN_OK;
+}
+
+// One tau pass.  gamma/eta/eta_ll are device pointers.  with_ll: also produce the n*log p partials.
+static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, const double *eta_ll, bool draw, bool with_ll,
+                      bool count_occupancy, uint32_t iter)
+{
+    TauParams p;
+    p.counts = c->counts; p.tau = c->tau; p.gamma = gamma; p.eta = eta; p.eta_ll = with_ll ? eta_ll : nullptr;
+    p.words = nullptr;
+    if (draw && c->rng_mode == DESMAN_RNG_MT19937) { RET(gen_mt_words(c)); p.words = c->words; }
+    p.seed = c->seed; p.sweep = c->sweep; p.v0 = c->v0;
+    p.V = (int)c->V; p.S = c->S; p.G = c->G;
+    p.nchange = c->nchange;
+    const int grid = tau_grid(c);
+    RET(ensure_ll_partial(c, grid));
+    p.ll_partial = with_ll ? c->ll_partial : nullptr;
+    p.tau_cnt = count_occupancy ? c->tau_cnt : nullptr;
+    p.tau_last = c->tau_last;
+    p.iter = iter;
+    p.do_draw = draw ? 1 : 0;
+    const size_t smem = tau_smem_bytes(c->S, c->G);
+    if (smem > 227 * 1024) return fail(DESMAN_EINVAL, "S*G too large for the shared-memory tile (%zu bytes)", smem);
+    CU(cudaFuncSetAttribute(tau_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaMemsetAsync(c->nchange, 0, sizeof(unsigned long long), c->stream));
+    {
+        KSpan k(c, DESMAN_K_TAU);
+        tau_sample_kernel<<<grid, TAU_WARPS * 32, smem, c->stream>>>(p);
+    }
+    CU(cudaGetLastError());
+    return DESMAN_OK;
+}
+
+template <int GP>
+static void launch_mu_t(desman_ctx *c, const MuParams &p, int grid)
+{
+    mu_stats_kernel<GP><<<grid, MU_WARPS * 32, 0, c->stream>>>(p);
+}
+
+static int launch_mu(desman_ctx *c, const double *gamma, const double *eta)
+{
+    MuParams p;
+    p.counts = c->counts; p.tau = c->tau; p.gamma = gamma; p.eta = eta;
+    p.seed = c->seed; p.sweep = c->sweep; p.v0 = c->v0;
+    p.V = (int)c->V; p.S = c->S; p.G = c->G;
+    p.sum_mu = c->stats; p.esum = c->stats + (size_t)c->S * c->G;
+    const int nch = (c->S + 31) / 32;
+    // total warps must be a multiple of the number of 32-sample chunks
+    int64_t items = c->V * nch;
+    int64_t blocks = (items + MU_WARPS - 1) / MU_WARPS;
+    int64_t cap = (int64_t)c->sm_count * 6;
+    if (blocks > cap) blocks = cap;
+    blocks = ((blocks + nch - 1) / nch) * nch;
+    const int grid = (int)blocks;
+    CU(cudaMemsetAsync(c->stats, 0, ((size_t)c->S * c->G + 16) * sizeof(unsigned long long), c->stream));
+    {
+        KSpan k(c, DESMAN_K_MU);
+        const int G = c->G;
+        if (G <= 2) launch_mu_t<2>(c, p, grid);
+        else if (G <= 4) launch_mu_t<4>(c, p, grid);
+        else if (G <= 8) launch_mu_t<8>(c, p, grid);
+        else if (G <= 12) launch_mu_t<12>(c, p, grid);
+        else if (G <= 16) launch_mu_t<16>(c, p, grid);
+        else if (G <= 20) launch_mu_t<20>(c, p, grid);
+        else if (G <= 24) launch_mu_t<24>(c, p, grid);
+        else launch_mu_t<32>(c, p, grid);
+    }
+    CU(cudaGetLastError());
+    return DESMAN_OK;
+}
+
+static int allreduce_stats(desman_ctx *c)
+{
+    if (c->nranks <= 1) return DESMAN_OK;
+    KSpan k(c, DESMAN_K_OTHER);
+    NC(g_nccl.AllReduce(c->stats, c->stats, (size_t)c->S * c->G + 16, NCCL_UINT64, NCCL_SUM, c->comm, c->stream));
+    return DESMAN_OK;
+}
+static int allreduce_red(desman_ctx *c)
+{
+    if (c->nranks <= 1) return DESMAN_OK;
+    KSpan k(c, DESMAN_K_OTHER);
+    NC(g_nccl.AllReduce(c->red, c->red, 2, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
+    return DESMAN_OK;
+}
+
+static int launch_draw(desman_ctx *c, const unsigned long long *stats, double *gamma_out, double *eta_out)
+{
+    DrawParams p;
+    p.sum_mu = stats; p.esum = stats + (size_t)c->S * c->G;
+    p.S = c->S; p.G = c->G; p.alpha = c->alpha; p.delta = c->delta; p.epsilon = c->epsilon;
+    p.seed = c->seed; p.sweep = c->sweep; p.gamma_out = gamma_out; p.eta_out = eta_out;
+    const size_t smem = ((size_t)c->S * c->G + 16) * sizeof(double);
+    if (smem > 200 * 1024) return fail(DESMAN_EINVAL, "S*G too large for draw kernel");
+    CU(cudaFuncSetAttribute(draw_gamma_eta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    {
+        KSpan k(c, DESMAN_K_DRAW);
+        draw_gamma_eta_kernel<<<1, 256, smem, c->stream>>>(p);
+    }
+    CU(cudaGetLastError());
+    return DESMAN_OK;
+}
+
+struct StoreBufs { double *ll = nullptr, *lp = nullptr, *nch = nullptr, *gs = nullptr, *es = nullptr; };
+
+static int launch_finalize(desman_ctx *c, const double *gamma, const double *eta, double *eta_commit, int it, int star_mode,
+                           const StoreBufs &sb, bool store_ge)
+{
+    const int grid = tau_grid(c);
+    {
+        KSpan k(c, DESMAN_K_FINAL);
+        reduce_ll_kernel<<<1, 256, 0, c->stream>>>(c->ll_partial, grid, c->ll_const, c->nchange, c->red);
+    }
+    CU(cudaGetLastError());
+    RET(allreduce_red(c));
+    FinalParams p;
+    p.red = c->red; p.gamma = gamma; p.eta = eta; p.eta_commit = eta_commit;
+    p.S = c->S; p.G = c->G; p.V_total = (double)c->V_total; p.alpha = c->alpha; p.delta = c->delta;
+    p.lg_alphaG = lgamma(c->alpha * c->G); p.lg_alpha = lgamma(c->alpha);
+    p.lg_delta4 = lgamma(4.0 * c->delta); p.lg_delta = lgamma(c->delta);
+    p.it = it; p.star_mode = star_mode;
+    p.ll_store = sb.ll; p.lp_store = sb.lp; p.nchange_store = sb.nch;
+    p.gamma_store = store_ge ? sb.gs : nullptr; p.eta_store = store_ge ? sb.es : nullptr;
+    p.gamma_star = c->gamma_star; p.eta_star = c->eta_star; p.scal = c->scal; p.flag = c->flag;
+    {
+        KSpan k(c, DESMAN_K_FINAL);
+        finalize_sweep_kernel<<<1, 256, 0, c->stream>>>(p);
+        copy_tau_if_kernel<<<c->sm_count, 256, 0, c->stream>>>(c->tau, c->tau_star, (size_t)c->V * c->G, c->flag);
+    }
+    CU(cudaGetLastError());
+    return DESMAN_OK;
+}
+
+static int require_state(desman_ctx *c)
+{
+    if (!c || c->V <= 0) return fail(DESMAN_ESTATE, "no counts set");
+    if (c->G <= 0) return fail(DESMAN_ESTATE, "no state set");
+    CU(cudaSetDevice(c->device));
+    return DESMAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ single steps
+extern "C" int desman_sample_tau(desman_ctx *c, int64_t *nchange)
+{
+    RET(require_state(c));
+    RET(launch_tau(c, c->gamma, c->eta, nullptr, true, false, false, 0));
+    if (c->rng_mode == DESMAN_RNG_PHILOX) c->sweep++;
+    unsigned long long n = 0;
+    CU(cudaMemcpyAsync(&n, c->nchange, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->nranks > 1) return fail(DESMAN_ESTATE, "desman_sample_tau is a single-rank call");
+    if (nchange) *nchange = (int64_t)n;
+    return DESMAN_OK;
+}
+
+extern "C" int desman_mu_stats(desman_ctx *c, int64_t *sum_mu, int64_t *esum)
+{
+    RET(require_state(c));
+    RET(launch_mu(c, c->gamma, c->eta));
+    RET(allreduce_stats(c));
+    const size_t nsg = (size_t)c->S * c->G;
+    std::vector<unsigned long long> h(nsg + 16);
+    CU(cudaMemcpyAsync(h.data(), c->stats, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (sum_mu) for (size_t i = 0; i < nsg; i++) sum_mu[i] = (int64_t)h[i];
+    if (esum) for (int i = 0; i < 16; i++) esum[i] = (int64_t)h[nsg + i];
+    return DESMAN_OK;
+}
+
+extern "C" int desman_draw_gamma_eta(desman_ctx *c, const int64_t *sum_mu, const int64_t *esum, double *gamma, double *eta)
+{
+    RET(require_state(c));
+    const size_t nsg = (size_t)c->S * c->G;
+    RET(ensure_scratch(c, (nsg + 16) * 16 + 256));
+    unsigned long long *st = (unsigned long long *)c->scratch;
+    double *out = (double *)(st + nsg + 16);
+    std::vector<unsigned long long> h(nsg + 16);
+    for (size_t i = 0; i < nsg; i++) h[i] = (unsigned long long)sum_mu[i];
+    for (int i = 0; i < 16; i++) h[nsg + i] = (unsigned long long)esum[i];
+    CU(cudaMemcpyAsync(st, h.data(), h.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    RET(launch_draw(c, st, out, out + nsg));
+    if (gamma) CU(cudaMemcpyAsync(gamma, out, nsg * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (eta) CU(cudaMemcpyAsync(eta, out + nsg, 16 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return DESMAN_OK;
+}
+
+extern "C" int desman_loglik(desman_ctx *c, double *ll, double *lp)
+{
+    RET(require_state(c));
+    RET(ensure_ll_const(c));
+    RET(launch_tau(c, c->gamma, c->eta, c->eta, false, true, false, 0));
+    // finalize with a scratch star area so the real star state is untouched
+    const int grid = tau_grid(c);
+    reduce_ll_kernel<<<1, 256, 0, c->stream>>>(c->ll_partial, grid, c->ll_const, nullptr, c->red);
+    CU(cudaGetLastError());
+    RET(allreduce_red(c));
+    double h_ll = 0.0;
+    CU(cudaMemcpyAsync(&h_ll, c->red, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    std::vector<double> g((size_t)c->S * c->G), e(16);
+    CU(cudaMemcpyAsync(g.data(), c->gamma, g.size() * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(e.data(), c->eta, 16 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    // prior on host (tiny): Desman_Utils.py:35-44, HaploSNP_Sampler.py:448-459
+    double prior = 0.0;
+    for (int s = 0; s < c->S; s++) {
+        double r = lgamma(c->alpha * c->G);
+        for (int k = 0; k < c->G; k++) { r += (c->alpha - 1.0) * log(g[(size_t)s * c->G + k]); r -= lgamma(c->alpha); }
+        prior += r;
+    }
+    for (int a = 0; a < 4; a++) {
+        double r = lgamma(4.0 * c->delta);
+        for (int k = 0; k < 4; k++) { r += (c->delta - 1.0) * log(e[a * 4 + k]); r -= lgamma(c->delta); }
+        prior += r;
+    }
+    prior += (double)c->V_total * c->G * log(0.25);
+    if (ll) *ll = h_ll;
+    if (lp) *lp = h_ll + prior;
+    return DESMAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ chains
+static int alloc_stores(desman_ctx *c, int n_iter, bool with_ge, StoreBufs *sb, const double *h_gs, const double *h_es)
+{
+    const size_t nsg = (size_t)c->S * c->G;
+    size_t bytes = sizeof(double) * (3 * (size_t)n_iter + (with_ge || h_gs ? (size_t)n_iter * (nsg + 16) : 0)) + 256;
+    RET(ensure_scratch(c, bytes));
+    double *base = (double *)c->scratch;
+    sb->ll = base; sb->lp = base + n_iter; sb->nch = base + 2 * (size_t)n_iter;
+    if (with_ge || h_gs) { sb->gs = base + 3 * (size_t)n_iter; sb->es = sb->gs + (size_t)n_iter * nsg; }
+    if (h_gs) {
+        CU(cudaMemcpyAsync(sb->gs, h_gs, (size_t)n_iter * nsg * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(sb->es, h_es, (size_t)n_iter * 16 * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    return DESMAN_OK;
+}
+
+static int fetch_stores(desman_ctx *c, int n_iter, const StoreBufs &sb, double *gamma_store, double *eta_store,
+                        double *ll_store, double *lp_store, int64_t *nchange_store)
+{
+    const size_t nsg = (size_t)c->S * c->G;
+    std::vector<double> nch(n_iter);
+    if (ll_store) CU(cudaMemcpyAsync(ll_store, sb.ll, n_iter * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (lp_store) CU(cudaMemcpyAsync(lp_store, sb.lp, n_iter * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (nchange_store) CU(cudaMemcpyAsync(nch.data(), sb.nch, n_iter * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (gamma_store && sb.gs) CU(cudaMemcpyAsync(gamma_store, sb.gs, (size_t)n_iter * nsg * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (eta_store && sb.es) CU(cudaMemcpyAsync(eta_store, sb.es, (size_t)n_iter * 16 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (nchange_store) for (int i = 0; i < n_iter; i++) nchange_store[i] = (int64_t)llround(nch[i]);
+    return DESMAN_OK;
+}
+
+static int prepare_profiling(desman_ctx *c)
+{
+    timing_reset(c);
+    if (c->prof_flush && !c->flush_buf) {
+        c->flush_n = ((size_t)256 << 20) / sizeof(uint4);
+        CU(cudaMalloc(&c->flush_buf, c->flush_n * sizeof(uint4)));
+    }
+    return DESMAN_OK;
+}
+
+// update(), HaploSNP_Sampler.py:334-365
+extern "C" int desman_update(desman_ctx *c, int n_iter, double *gamma_store, double *eta_store, double *ll_store,
+                             double *lp_store, int64_t *nchange_store)
+{
+    RET(require_state(c));
+    if (n_iter < 0) return fail(DESMAN_EINVAL, "n_iter < 0");
+    if (c->rng_mode != DESMAN_RNG_PHILOX)
+        return fail(DESMAN_ESTATE, "desman_update needs DESMAN_RNG_PHILOX: the mu/gamma/eta draws of the reference follow numpy's "
+                                   "sequential legacy stream, which has no parallel form (DESIGN.md section 4)");
+    RET(ensure_ll_const(c));
+    StoreBufs sb;
+    RET(alloc_stores(c, n_iter > 0 ? n_iter : 1, true, &sb, nullptr, nullptr));
+    RET(prepare_profiling(c));
+    const size_t nvg = (size_t)c->V * c->G;
+    CU(cudaMemsetAsync(c->tau_cnt, 0, nvg * 4 * sizeof(uint32_t), c->stream));
+    CU(cudaMemsetAsync(c->tau_last, 0, nvg * sizeof(uint32_t), c->stream));
+    // pre-sweep ll/lp and star state (:336-338)
+    RET(launch_tau(c, c->gamma, c->eta, c->eta, false, true, false, 0));
+    RET(launch_finalize(c, c->gamma, c->eta, nullptr, -1, 0, sb, false));
+    for (int it = 0; it < n_iter; it++) {
+        sweep_begin(c);
+        RET(launch_mu(c, c->gamma, c->eta));                            // sampleMu   (:341)
+        RET(allreduce_stats(c));
+        RET(launch_draw(c, c->stats, c->gamma, c->eta_new));            // sampleGamma (:342) + sampleEta's draw (:347)
+        RET(launch_tau(c, c->gamma, c->eta, c->eta_new, true, true, true, (uint32_t)it));   // sample_tau (:345) + ll (:349)
+        RET(launch_finalize(c, c->gamma, c->eta_new, c->eta, it, 0, sb, true));             // lp, stores, star (:350-358)
+        sweep_end(c);
+        c->sweep++;
+    }
+    flush_tau_counts_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(c->tau, c->tau_cnt, c->tau_last, nvg, (uint32_t)n_iter);
+    CU(cudaGetLastError());
+    c->last_n_iter = (uint32_t)n_iter;
+    RET(fetch_stores(c, n_iter, sb, gamma_store, eta_store, ll_store, lp_store, nchange_store));
+    timing_collect(c);
+    return DESMAN_OK;
+}
+
+// updateTau(), HaploSNP_Sampler.py:383-407
+extern "C" int desman_update_tau(desman_ctx *c, int n_iter, const double *gamma_store, const double *eta_store,
+                                 double *ll_store, double *lp_store, int64_t *nchange_store)
+{
+    RET(require_state(c));
+    if (n_iter <= 0 || !gamma_store || !eta_store) return fail(DESMAN_EINVAL, "update_tau needs n_iter > 0 and the gamma/eta stores");
+    const size_t nsg = (size_t)c->S * c->G;
+    for (size_t i = 0; i < (size_t)n_iter * nsg; i++) if (!(gamma_store[i] > 0.0)) return fail(DESMAN_EINVAL, "gamma_store[%zu] must be > 0", i);
+    for (size_t i = 0; i < (size_t)n_iter * 16; i++) if (!(eta_store[i] > 0.0)) return fail(DESMAN_EINVAL, "eta_store[%zu] must be > 0", i);
+    RET(ensure_ll_const(c));
+    StoreBufs sb;
+    RET(alloc_stores(c, n_iter, false, &sb, gamma_store, eta_store));
+    RET(prepare_profiling(c));
+    const size_t nvg = (size_t)c->V * c->G;
+    CU(cudaMemsetAsync(c->tau_cnt, 0, nvg * 4 * sizeof(uint32_t), c->stream));
+    CU(cudaMemsetAsync(c->tau_last, 0, nvg * sizeof(uint32_t), c->stream));
+    // lp_star from (gamma_store[0], tau, eta_store[0]) (:386-388)
+    RET(launch_tau(c, sb.gs, sb.es, sb.es, false, true, false, 0));
+    RET(launch_finalize(c, sb.gs, sb.es, nullptr, -1, 1, sb, false));
+    for (int it = 0; it < n_iter; it++) {
+        const double *gm = sb.gs + (size_t)it * nsg, *et = sb.es + (size_t)it * 16;
+        sweep_begin(c);
+        RET(launch_tau(c, gm, et, et, true, true, true, (uint32_t)it));
+        RET(launch_finalize(c, gm, et, nullptr, it, 1, sb, false));
+        sweep_end(c);
+        if (c->rng_mode == DESMAN_RNG_PHILOX) c->sweep++;
+    }
+    flush_tau_counts_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(c->tau, c->tau_cnt, c->tau_last, nvg, (uint32_t)n_iter);
+    CU(cudaGetLastError());
+    c->last_n_iter = (uint32_t)n_iter;
+    RET(fetch_stores(c, n_iter, sb, nullptr, nullptr, ll_store, lp_store, nchange_store));
+    timing_collect(c);
+    return DESMAN_OK;
+}
+
+extern "C" int desman_get_star(desman_ctx *c, int64_t *tau_star, double *gamma_star, double *eta_star, double *lp_star,
+                               int *iter_star)
+{
+    RET(require_state(c));
+    std::vector<uint8_t> idx;
+    double sc[4];
+    if (tau_star) {
+        idx.resize((size_t)c->V * c->G);
+        CU(cudaMemcpyAsync(idx.data(), c->tau_star, idx.size(), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (gamma_star) CU(cudaMemcpyAsync(gamma_star, c->gamma_star, (size_t)c->S * c->G * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (eta_star) CU(cudaMemcpyAsync(eta_star, c->eta_star, 16 * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(sc, c->scal, sizeof(sc), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (tau_star) index_to_onehot(idx.data(), idx.size(), tau_star);
+    if (lp_star) *lp_star = sc[0];
+    if (iter_star) *iter_star = (int)sc[1];
+    return DESMAN_OK;
+}
+
+extern "C" int desman_get_tau_sum(desman_ctx *c, int64_t *tau_sum)
+{
+    RET(require_state(c));
+    const size_t n = (size_t)c->V * c->G * 4;
+    std::vector<uint32_t> h(n);
+    CU(cudaMemcpyAsync(h.data(), c->tau_cnt, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (size_t i = 0; i < n; i++) tau_sum[i] = (int64_t)h[i];
+    return DESMAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ NMFT
+extern "C" int desman_nmft_factorize(desman_ctx *c, const int64_t *snps, int64_t V, int S, int G, double *tau, double *gamma,
+                                     int max_iter, double min_change, int fix_gamma, int *n_iter_done, double *div_final,
+                                     double *div_trace)
+{
+    if (!c || !snps || !tau || !gamma || V <= 0 || S <= 0 || G < 1 || G > DESMAN_MAX_G)
+        return fail(DESMAN_EINVAL, "desman_nmft_factorize: bad arguments");
+    CU(cudaSetDevice(c->device));
+    return nmft_factorize_impl(c->stream, c->sm_count, snps, V, S, G, tau, gamma, max_iter, min_change, fix_gamma, n_iter_done,
+                               div_final, div_trace, g_err, sizeof(g_err));
+}
+
+// ------------------------------------------------------------------------------------------ comm
+extern "C" int desman_comm_unique_id(char id[128])
+{
+    RET(nccl_load());
+    nccl_uid_t u;
+    NC(g_nccl.GetUniqueId(&u));
+    memcpy(id, u.internal, 128);
+    return DESMAN_OK;
+}
+
+extern "C" int desman_comm_init(desman_ctx *c, const char id[128], int rank, int nranks)
+{
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(DESMAN_EINVAL, "bad rank/nranks");
+    if (nranks == 1) { c->rank = 0; c->nranks = 1; return DESMAN_OK; }
+    RET(nccl_load());
+    CU(cudaSetDevice(c->device));
+    nccl_uid_t u;
+    memcpy(u.internal, id, 128);
+    NC(g_nccl.CommInitRank(&c->comm, nranks, u, rank));
+    c->rank = rank; c->nranks = nranks;
+    return DESMAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ measurement
+extern "C" int desman_set_profiling(desman_ctx *c, int per_kernel_events, int flush_l2_between_sweeps)
+{
+    c->prof_kernels = per_kernel_events; c->prof_flush = flush_l2_between_sweeps;
+    return DESMAN_OK;
+}
+
+extern "C" int desman_get_timing(desman_ctx *c, double *elapsed_ms, double kernel_ms[DESMAN_K_COUNT],
+                                 int64_t kernel_launches[DESMAN_K_COUNT])
+{
+    if (elapsed_ms) *elapsed_ms = c->elapsed_ms;
+    for (int i = 0; i < DESMAN_K_COUNT; i++) {
+        if (kernel_ms) kernel_ms[i] = c->k_ms[i];
+        if (kernel_launches) kernel_launches[i] = c->k_launch[i];
+    }
+    return DESMAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ reference ABI
+// Process-global stream, like the file-static gsl_rng of c_sample_tau.c:24.
+static desman_ctx *g_legacy = nullptr;
+static unsigned long g_legacy_seed = 0;
+
+extern "C" void c_initRNG(void)
+{
+    if (g_legacy) return;
+    int dev = 0;
+    const char *env = getenv("DESMAN_B200_DEVICE");
+    if (env) dev = atoi(env);
+    if (desman_ctx_create(&g_legacy, dev, 0, DESMAN_RNG_MT19937) != DESMAN_OK) {
+        fprintf(stderr, "desman_b200: c_initRNG failed: %s\n", g_err);
+        g_legacy = nullptr;
+    }
+}
+
+extern "C" void c_setRNG(unsigned long int seed)
+{
+    if (!g_legacy) { fail(DESMAN_ESTATE, "c_setRNG before c_initRNG"); fprintf(stderr, "desman_b200: %s\n", g_err); return; }
+    g_legacy_seed = seed;
+    if (desman_set_rng(g_legacy, (uint64_t)seed, 0, 0) != DESMAN_OK) fprintf(stderr, "desman_b200: c_setRNG failed: %s\n", g_err);
+}
+
+extern "C" void c_freeRNG(void)
+{
+    if (g_legacy) desman_ctx_destroy(g_legacy);
+    g_legacy = nullptr;
+}
+
+extern "C" int c_sample_tau(long *anTau, double *adPi, double *adEta, long *anVariants, int nV, int nG, int nS)
+{
+    if (!g_legacy) { fail(DESMAN_ESTATE, "c_sample_tau before c_initRNG (NULL dereference in the reference, c_sample_tau.c:174)"); return -1; }
+    desman_ctx *c = g_legacy;
+    if (!anTau || !adPi || !adEta || !anVariants || nV <= 0 || nG <= 0 || nS <= 0) { fail(DESMAN_EINVAL, "c_sample_tau: bad arguments"); return -1; }
+    // the reference borrows all four arrays for the call and retains nothing (c_sample_tau.c:107-114,192-195)
+    if (desman_set_counts(c, (const int64_t *)anVariants, nV, nS, 0, nV) != DESMAN_OK) return -1;
+    if (desman_set_state(c, (const int64_t *)anTau, adPi, adEta, nG) != DESMAN_OK) return -1;
+    std::vector<uint8_t> before((size_t)nV * nG), after((size_t)nV * nG);
+    if (desman_get_tau_index(c, before.data()) != DESMAN_OK) return -1;
+    int64_t nchange = 0;
+    if (desman_sample_tau(c, &nchange) != DESMAN_OK) return -1;
+    if (desman_get_tau_index(c, after.data()) != DESMAN_OK) return -1;
+    for (size_t i = 0; i < after.size(); i++)
+        if (after[i] != before[i]) { anTau[i * 4 + before[i]] = 0; anTau[i * 4 + after[i]] = 1; }   // :178-184
+    return (int)nchange;
+}

@@ -1,0 +1,282 @@
+// desman_b200/csrc/misc_kernels.cuh -- small kernels around the two site passes:
+//   pack_counts        int64 [V,S,4] -> int32x4 cells, range check
+//   lgamma_const       sum_vs lgamma(N+1) - sum_b lgamma(n_b+1)    (Desman_Utils.py:28-33, constant in the chain)
+//   mt19937_kernel     K9: GSL-compatible MT19937 stream             (c_sample_tau.c:33-40,174)
+//   draw_gamma_eta     K3: Dirichlet draws of gamma and eta          (HaploSNP_Sampler.py:263-281)
+//   reduce_ll / finalize_sweep / copy_tau_if / flush_tau_counts     K4-K5 (:326-332,:349-358,:431-461)
+#pragma once
+#include "common.cuh"
+
+// ---------------------------------------------------------------------------------------------
+__global__ void pack_counts_kernel(const long long *__restrict__ src, int4 *__restrict__ dst, size_t ncell,
+                                   int *__restrict__ err)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < ncell; i += (size_t)gridDim.x * blockDim.x) {
+        const longlong2 a = reinterpret_cast<const longlong2 *>(src)[2 * i];
+        const longlong2 b = reinterpret_cast<const longlong2 *>(src)[2 * i + 1];
+        if (a.x < 0 || a.y < 0 || b.x < 0 || b.y < 0 || a.x > 16777216 || a.y > 16777216 || b.x > 16777216 ||
+            b.y > 16777216)
+            *err = 1;
+        dst[i] = make_int4((int)a.x, (int)a.y, (int)b.x, (int)b.y);
+    }
+}
+
+__global__ void lgamma_const_kernel(const int4 *__restrict__ counts, size_t ncell, double *__restrict__ partial)
+{
+    __shared__ double red[256];
+    double acc = 0.0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < ncell; i += (size_t)gridDim.x * blockDim.x) {
+        const int4 n = counts[i];
+        const double N = (double)n.x + (double)n.y + (double)n.z + (double)n.w;
+        acc += lgamma(N + 1.0) - (lgamma((double)n.x + 1.0) + lgamma((double)n.y + 1.0) + lgamma((double)n.z + 1.0) +
+                                  lgamma((double)n.w + 1.0));
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int m = 128; m > 0; m >>= 1) {
+        if (threadIdx.x < m) red[threadIdx.x] += red[threadIdx.x + m];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K9.  One block.  state[624] holds the current (already regenerated) block of the recurrence and
+// `pos` how many of its words were consumed (GSL: mti).  Emits `n` tempered words of the stream,
+// storing only those with index in [store_lo, store_hi) (a rank's slice under V-sharding) at
+// out[index - store_lo].  Three dependent phases of <= 227 independent words per regeneration.
+__device__ __forceinline__ uint32_t mt_twist(uint32_t a, uint32_t b)
+{
+    const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+    return (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+}
+
+__global__ void __launch_bounds__(256) mt19937_kernel(uint32_t *__restrict__ state, int pos, size_t n,
+                                                      size_t store_lo, size_t store_hi, uint32_t *__restrict__ out)
+{
+    __shared__ uint32_t bufA[624], bufB[624];
+    uint32_t *cur = bufA, *nxt = bufB;
+    const int t = threadIdx.x;
+    for (int i = t; i < 624; i += 256) cur[i] = state[i];
+    __syncthreads();
+    size_t done = 0;
+    while (done < n) {
+        if (pos == 624) {
+            if (t < 227) nxt[t] = cur[t + 397] ^ mt_twist(cur[t], cur[t + 1]);
+            __syncthreads();
+            if (t < 227) nxt[t + 227] = nxt[t] ^ mt_twist(cur[t + 227], cur[t + 228]);
+            __syncthreads();
+            if (t < 169) nxt[t + 454] = nxt[t + 227] ^ mt_twist(cur[t + 454], cur[t + 455]);
+            if (t == 255) nxt[623] = nxt[396] ^ mt_twist(cur[623], nxt[0]);
+            __syncthreads();
+            uint32_t *tmp = cur; cur = nxt; nxt = tmp;
+            pos = 0;
+        }
+        const size_t take = min((size_t)(624 - pos), n - done);
+        for (int i = t; i < (int)take; i += 256) {
+            const size_t idx = done + i;
+            if (idx >= store_lo && idx < store_hi) {
+                uint32_t y = cur[pos + i];
+                y ^= y >> 11;
+                y ^= (y << 7) & 0x9d2c5680u;
+                y ^= (y << 15) & 0xefc60000u;
+                y ^= y >> 18;
+                out[idx - store_lo] = y;
+            }
+        }
+        pos += (int)take;
+        done += take;
+    }
+    __syncthreads();
+    for (int i = t; i < 624; i += 256) state[i] = cur[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3.  Marsaglia-Tsang gamma variates under the Philox contract (see oracle_gamma_variate):
+// attempt t of variate idx owns block ctr=(idx, t, sweep, stage<<28): (w0,w1)->53-bit radius uniform,
+// w2 -> angle, w3 -> accept; shape < 1 boosts with U^(1/shape), U from ctr=(idx,0,sweep,boost<<28).
+__device__ __forceinline__ double u53(uint32_t hi, uint32_t lo)
+{
+    const unsigned long long m = ((unsigned long long)(hi >> 5) << 26) | (unsigned long long)(lo >> 6);
+    return ((double)m + 0.5) * (1.0 / 9007199254740992.0);
+}
+__device__ __forceinline__ double u32d(uint32_t w) { return ((double)w + 0.5) * (1.0 / 4294967296.0); }
+
+__device__ double gamma_variate(double shape, uint32_t k0, uint32_t k1, uint32_t sweep, uint32_t idx, int stage,
+                                int boost_stage)
+{
+    const double a1 = (shape < 1.0) ? shape + 1.0 : shape;
+    const double d = a1 - 1.0 / 3.0;
+    const double c = 1.0 / sqrt(9.0 * d);
+    double y = d;
+    for (uint32_t t = 0; t < (1u << 20); t++) {
+        const uint4 o = philox4x32_10(idx, t, sweep, (uint32_t)stage << 28, k0, k1);
+        const double r1 = u53(o.x, o.y);
+        const double r2 = u32d(o.z);
+        const double z = sqrt(-2.0 * log(r1)) * cos(6.283185307179586476925 * r2);
+        double vv = 1.0 + c * z;
+        if (vv <= 0.0) continue;
+        vv = vv * vv * vv;
+        const double r3 = u32d(o.w);
+        if (log(r3) < 0.5 * z * z + d - d * vv + d * log(vv)) { y = d * vv; break; }
+    }
+    if (shape < 1.0) {
+        const uint4 o = philox4x32_10(idx, 0u, sweep, (uint32_t)boost_stage << 28, k0, k1);
+        y *= exp(log(u53(o.x, o.y)) / shape);
+    }
+    return y;
+}
+
+struct DrawParams {
+    const unsigned long long *sum_mu;  // [S][G]
+    const unsigned long long *esum;    // [16] esum[a_obs*4+b_true]
+    int S, G;
+    double alpha, delta, epsilon;
+    uint64_t seed;
+    uint32_t sweep;
+    double *gamma_out;  // [S][G]
+    double *eta_out;    // [16]
+};
+
+__global__ void __launch_bounds__(256) draw_gamma_eta_kernel(DrawParams p)
+{
+    extern __shared__ double y[];  // [S*G + 16]
+    const int S = p.S, G = p.G, nG = S * G;
+    const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+    for (int i = threadIdx.x; i < nG + 16; i += blockDim.x) {
+        if (i < nG) {
+            y[i] = gamma_variate(p.alpha + (double)p.sum_mu[i], k0, k1, p.sweep, (uint32_t)i, STAGE_GAMMA,
+                                 STAGE_GAMMA_BOOST);
+        } else {
+            const int j = i - nG, t = j >> 2, o = j & 3;   // eta[t][o] ~ Gamma(delta + Esum[o][t])  (:276-281)
+            y[i] = gamma_variate(p.delta + (double)p.esum[o * 4 + t], k0, k1, p.sweep, (uint32_t)j, STAGE_ETA,
+                                 STAGE_ETA_BOOST);
+        }
+    }
+    __syncthreads();
+    for (int s = threadIdx.x; s < S + 4; s += blockDim.x) {
+        if (s < S) {
+            double tot = 0.0;
+            for (int g = 0; g < G; g++) tot += y[s * G + g];
+            double rs = 0.0;
+            for (int g = 0; g < G; g++) {
+                double x = (tot > 0.0) ? y[s * G + g] / tot : 1.0 / G;
+                if (x < p.epsilon) x = p.epsilon;             // :271
+                y[s * G + g] = x;
+                rs += x;
+            }
+            for (int g = 0; g < G; g++) p.gamma_out[s * G + g] = y[s * G + g] / rs;   // :272-273
+        } else {
+            const int t = s - S;
+            double tot = 0.0;
+            for (int o = 0; o < 4; o++) tot += y[nG + t * 4 + o];
+            for (int o = 0; o < 4; o++) p.eta_out[t * 4 + o] = y[nG + t * 4 + o] / tot;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// red[0] = ll_const + sum of the per-block n*log p partials (fixed order), red[1] = nchange
+__global__ void reduce_ll_kernel(const double *__restrict__ partial, int nblocks, double ll_const,
+                                 const unsigned long long *__restrict__ nchange, double *__restrict__ red)
+{
+    __shared__ double sh[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += 256) acc += partial[i];
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int m = 128; m > 0; m >>= 1) {
+        if (threadIdx.x < m) sh[threadIdx.x] += sh[threadIdx.x + m];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        red[0] = sh[0] + ll_const;
+        red[1] = nchange ? (double)(*nchange) : 0.0;
+    }
+}
+
+struct FinalParams {
+    const double *red;        // [2] ll, nchange (already all-reduced under sharding)
+    const double *gamma;      // [S][G] used for the prior
+    const double *eta;        // [16]   used for the prior (eta_new in update())
+    double *eta_commit;       // if non-null: eta_commit[0..15] = eta (the chain's eta <- eta_new)
+    int S, G;
+    double V_total;
+    double alpha, delta;
+    double lg_alphaG, lg_alpha, lg_delta4, lg_delta;   // lgamma(alpha*G), lgamma(alpha), lgamma(4 delta), lgamma(delta)
+    int it;                   // iteration index, or -1 for the pre-sweep state (:336-338)
+    int star_mode;            // 0: gamma/eta/tau star (update), 1: tau only (updateTau)
+    double *ll_store, *lp_store, *nchange_store;   // device [n_iter] or null
+    double *gamma_store, *eta_store;               // device [n_iter][S*G], [n_iter][16] or null
+    double *gamma_star, *eta_star;                 // device
+    double *scal;             // [0]=lp_star [1]=iter_star [2]=ll [3]=lp
+    int *flag;                // 1 when the star state must be replaced
+};
+
+// logPosterior (HaploSNP_Sampler.py:444-461) + star bookkeeping (:326-332, :351-358)
+__global__ void __launch_bounds__(256) finalize_sweep_kernel(FinalParams p)
+{
+    __shared__ double sh[256];
+    const int nG = p.S * p.G;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < nG; i += 256) acc += (p.alpha - 1.0) * log(p.gamma[i]);
+    for (int i = threadIdx.x; i < 16; i += 256) acc += (p.delta - 1.0) * log(p.eta[i]);
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (int m = 128; m > 0; m >>= 1) {
+        if (threadIdx.x < m) sh[threadIdx.x] += sh[threadIdx.x + m];
+        __syncthreads();
+    }
+    __shared__ int upd;
+    if (threadIdx.x == 0) {
+        const double prior = sh[0] + p.S * (p.lg_alphaG - p.G * p.lg_alpha) + 4.0 * (p.lg_delta4 - 4.0 * p.lg_delta) +
+                             p.V_total * (double)p.G * log(0.25);
+        const double ll = p.red[0], lp = ll + prior;
+        p.scal[2] = ll; p.scal[3] = lp;
+        if (p.it >= 0) {
+            if (p.ll_store) p.ll_store[p.it] = ll;
+            if (p.lp_store) p.lp_store[p.it] = lp;
+            if (p.nchange_store) p.nchange_store[p.it] = p.red[1];
+        }
+        upd = (p.it < 0) || (lp > p.scal[0]);
+        if (upd) { p.scal[0] = lp; p.scal[1] = (double)(p.it < 0 ? 0 : p.it); }
+        *p.flag = upd;
+    }
+    __syncthreads();
+    const bool u = upd != 0;
+    for (int i = threadIdx.x; i < nG; i += 256) {
+        const double x = p.gamma[i];
+        if (p.it >= 0 && p.gamma_store) p.gamma_store[(size_t)p.it * nG + i] = x;
+        if (u && p.star_mode == 0) p.gamma_star[i] = x;
+    }
+    if (threadIdx.x < 16) {
+        const double x = p.eta[threadIdx.x];
+        if (p.it >= 0 && p.eta_store) p.eta_store[(size_t)p.it * 16 + threadIdx.x] = x;
+        if (u && p.star_mode == 0) p.eta_star[threadIdx.x] = x;
+        if (p.eta_commit) p.eta_commit[threadIdx.x] = x;
+    }
+}
+
+__global__ void copy_tau_if_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t n,
+                                   const int *__restrict__ flag)
+{
+    if (*flag == 0) return;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+// close the lazy occupancy counters at the end of an update(): cnt[vg][tau_vg] += n_iter - last[vg]
+__global__ void flush_tau_counts_kernel(const uint8_t *__restrict__ tau, uint32_t *__restrict__ cnt,
+                                        uint32_t *__restrict__ last, size_t nvg, uint32_t n_iter)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvg; i += (size_t)gridDim.x * blockDim.x) {
+        cnt[i * 4 + (tau[i] & 3)] += n_iter - last[i];
+        last[i] = n_iter;
+    }
+}
+
+__global__ void l2_flush_kernel(uint4 *__restrict__ buf, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        buf[i] = make_uint4((uint32_t)i, 0u, 0u, 0u);
+}

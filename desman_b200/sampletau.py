@@ -1,0 +1,72 @@
+"""Drop-in for the reference's `sampletau` extension module (sampletau/sampletau.pyx:21-57).
+
+Same four functions, same argument checks, same in-place mutation of `tau`, same GSL-compatible
+MT19937 stream -- but `sample_tau` runs the sm_100a kernel of libdesman_b200.so.  Callers in the
+reference: bin/desman:131-132,242; HaploSNP_Sampler.py:345,392; Eta_Sampler.py:367.
+
+Argument errors mirror what Cython's buffer acquisition raises for the reference module
+(SURVEY.md section 8b): TypeError for None / non-arrays, ValueError for wrong dtype, rank or
+memory order, OverflowError for a seed that does not fit a C int.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+
+def initRNG():
+    """c_initRNG (c_sample_tau.c:26-34)"""
+    _lib.lib().c_initRNG()
+    msg = _lib.last_error()
+    if msg and "c_initRNG" in msg:
+        raise _lib.DesmanB200Error(msg)
+
+
+def setRNG(seed):
+    """c_setRNG (c_sample_tau.c:36-40); `seed` is a C int in the reference signature (sampletau.pyx:28)."""
+    seed = int(seed)
+    if seed > 2**31 - 1:
+        raise OverflowError("value too large to convert to int")
+    if seed < -2**31:
+        raise OverflowError("value too small to convert to int")
+    _lib.lib().c_setRNG(C.c_ulong(seed & 0xFFFFFFFFFFFFFFFF))  # int -> unsigned long wrap, as in C
+
+
+def freeRNG():
+    """c_freeRNG (c_sample_tau.c:42-45)"""
+    _lib.lib().c_freeRNG()
+
+
+def _check(arr, name, ndim, dtype, cname):
+    if arr is None or not isinstance(arr, np.ndarray):
+        raise TypeError("Argument '%s' has incorrect type (expected numpy.ndarray, got %s)"
+                        % (name, type(arr).__name__))
+    if arr.ndim != ndim:
+        raise ValueError("Buffer has wrong number of dimensions (expected %d, got %d)" % (ndim, arr.ndim))
+    if arr.dtype != dtype:
+        got = {"int32": "int", "float32": "float", "int64": "long", "float64": "double"}.get(arr.dtype.name,
+                                                                                             arr.dtype.name)
+        raise ValueError("Buffer dtype mismatch, expected '%s' but got '%s'" % (cname, got))
+    if not arr.flags.c_contiguous:
+        raise ValueError("ndarray is not C-contiguous")
+
+
+def sample_tau(tau, pi, eta, variants):
+    """sample_tau(tau, pi, eta, variants) -> nchange   (sampletau.pyx:38-57)
+
+    tau      int64  [V,G,4] one-hot, mutated in place
+    pi       float64 [S,G]  strain abundances gamma
+    eta      float64 [4,4]  error matrix, row = true base
+    variants int64  [V,S,4] base counts
+    """
+    _check(tau, "tau", 3, np.int64, "long")
+    _check(pi, "pi", 2, np.float64, "double")
+    _check(eta, "eta", 2, np.float64, "double")
+    _check(variants, "variants", 3, np.int64, "long")
+    nV, nG, nS = tau.shape[0], tau.shape[1], pi.shape[0]      # sampletau.pyx:51-53
+    n = _lib.lib().c_sample_tau(tau.ctypes.data_as(_lib._p64), pi.ctypes.data_as(_lib._pd),
+                                eta.ctypes.data_as(_lib._pd), variants.ctypes.data_as(_lib._p64), nV, nG, nS)
+    if n < 0:
+        raise _lib.DesmanB200Error("c_sample_tau failed: " + _lib.last_error())
+    return n

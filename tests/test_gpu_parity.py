@@ -1,0 +1,266 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI (ctypes), against the oracle and
+against golden vectors recorded from the unmodified reference.  Integer results (tau, nchange,
+sum_mu, Esum, tau sums) must be bit-exact; gamma/eta/ll/lp within the stated relative tolerance."""
+import numpy as np
+import pytest
+
+from conftest import golden, onehot, synth_problem
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-6          # north_star tolerance for gamma / eta / log-likelihood
+RTOL_TIGHT = 1e-10   # what we actually expect between CUDA and glibc double arithmetic
+
+
+@pytest.fixture(scope="module")
+def eng_mod():
+    from desman_b200 import _lib, engine
+    assert _lib.device_count() >= 1
+    return engine
+
+
+def rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+# ------------------------------------------------------------------ reference ABI (MT19937 stream)
+def test_dropin_sample_tau_matches_reference_C_kats():
+    from desman_b200 import sampletau
+    z = golden("sample_tau_kat.npz")
+    for ci in range(int(z["ncases"])):
+        V, G, S, ncalls, seed = [int(x) for x in z[f"c{ci}_meta"]]
+        counts = z[f"c{ci}_counts"].astype(np.int64)
+        tau = onehot(z[f"c{ci}_tau0"])
+        sampletau.initRNG()
+        sampletau.setRNG(seed)
+        for k in range(ncalls):
+            n = sampletau.sample_tau(tau, np.ascontiguousarray(z[f"c{ci}_gamma"][k]),
+                                     np.ascontiguousarray(z[f"c{ci}_eta"][k]), counts)
+            assert np.array_equal(np.argmax(tau, 2), z[f"c{ci}_tau"][k]), (ci, k)
+            assert n == int(z[f"c{ci}_nchange"][k]), (ci, k)
+            assert (tau.sum(2) == 1).all() and tau.min() == 0
+        sampletau.freeRNG()
+
+
+@pytest.mark.parametrize("tag", ["i3", "i50"])
+def test_dropin_sample_tau_replays_real_reference_chain(tag):
+    """Every sample_tau call the unmodified `desman -g 5 -i N` made on COG0015 (burn-in + sampling
+    phases share ONE MT19937 stream): same inputs -> identical tau and nchange."""
+    from desman_b200 import sampletau
+    z = golden(f"cog0015_{tag}.npz")
+    counts = golden("cog0015.npz")["snps"].astype(np.int64)
+    seed = int(z["meta"][4])
+    sampletau.initRNG()
+    sampletau.setRNG(seed)
+    k = 0
+    for phase in ("call", "call2"):
+        for i in range(z[f"{phase}_tau_in"].shape[0]):
+            tau = onehot(z[f"{phase}_tau_in"][i])
+            n = sampletau.sample_tau(tau, np.ascontiguousarray(z[f"{phase}_gamma"][i]),
+                                     np.ascontiguousarray(z[f"{phase}_eta"][i]), counts)
+            assert n == int(z["call_nchange"][k]), (phase, i)
+            assert np.array_equal(np.argmax(tau, 2), z[f"{phase}_tau_out"][i]), (phase, i)
+            k += 1
+    sampletau.freeRNG()
+
+
+def test_dropin_argument_errors_and_rejections():
+    from desman_b200 import _lib, sampletau
+    sampletau.initRNG()
+    sampletau.setRNG(1)
+    tau = onehot(np.zeros((4, 2), dtype=np.uint8))
+    pi = np.full((3, 2), 0.5)
+    eta = 0.96 * np.identity(4) + 0.01
+    var = np.ones((4, 3, 4), dtype=np.int64)
+    bad = tau.copy(); bad[1, 0, :] = 0
+    with pytest.raises(_lib.DesmanB200Error, match="one-hot"):
+        sampletau.sample_tau(bad, pi, eta, var)
+    big = var.copy(); big[0, 0, 0] = 2**24 + 1
+    with pytest.raises(_lib.DesmanB200Error, match="counts"):
+        sampletau.sample_tau(tau, pi, eta, big)
+    assert sampletau.sample_tau(tau, pi, eta, var) >= 0
+    sampletau.freeRNG()
+
+
+# ------------------------------------------------------------------ single kernels vs oracle
+SHAPES = [(37, 1, 1), (50, 3, 2), (64, 64, 5), (40, 64, 8), (33, 130, 12), (20, 256, 16), (17, 96, 20), (9, 40, 32)]
+
+
+@pytest.mark.parametrize("V,S,G", SHAPES)
+def test_tau_philox_bit_exact_vs_oracle(eng_mod, oracle_mod, V, S, G):
+    p = synth_problem(V, S, G, depth=6.0 if S > 8 else 30.0, seed=V * 1000 + G, ambiguous=True)
+    p["counts"][:2] = 0                                   # all-zero rows: uniform draw t = floor(4u)
+    e = eng_mod.Engine(0, seed=77, rng_mode=eng_mod.RNG_PHILOX)
+    e.set_counts(p["counts"])
+    tau_o = onehot(p["tau0"])
+    e.set_state(tau_o, p["gamma0"], p["eta0"])
+    rng = np.random.default_rng(G)
+    total_flips = 0
+    for k in range(4):
+        gamma = rng.dirichlet(np.full(G, 0.3 if k % 2 else 1.0), size=S)
+        gamma[gamma < 1e-6] = 1e-6
+        gamma /= gamma.sum(1)[:, None]
+        e.set_state(None, gamma, p["eta0"], G=G)
+        e.set_rng(77, sweep=k)
+        n_gpu = e.sample_tau()
+        n_cpu = oracle_mod.sample_tau_philox(tau_o, gamma, p["eta0"], p["counts"], 77, k)
+        assert n_gpu == n_cpu
+        assert np.array_equal(e.get_tau_index(), np.argmax(tau_o, 2).astype(np.uint8))
+        total_flips += n_cpu
+    assert total_flips > 0          # the vectors are not vacuous
+    e.close()
+
+
+@pytest.mark.parametrize("V,S,G", SHAPES)
+def test_mu_stats_bit_exact_vs_oracle(eng_mod, oracle_mod, V, S, G):
+    p = synth_problem(V, S, G, depth=40.0, seed=V + G)
+    p["counts"][0] = 0
+    p["counts"][1, :, 2] = 777
+    eta = 0.9 * np.identity(4) + 0.025
+    e = eng_mod.Engine(0, seed=2024, rng_mode=eng_mod.RNG_PHILOX)
+    e.set_counts(p["counts"])
+    e.set_state(onehot(p["tau0"]), p["gamma0"], eta)
+    for sweep in (0, 5):
+        e.set_rng(2024, sweep=sweep)
+        sm, es = e.mu_stats()
+        sm_o, es_o = oracle_mod.mu_stats(onehot(p["tau0"]), p["gamma0"], eta, p["counts"], 2024, sweep)
+        assert np.array_equal(sm, sm_o)
+        assert np.array_equal(es, es_o)
+        assert sm.sum() == p["counts"].sum()
+    e.close()
+
+
+def test_mu_stats_sharded_offsets_equal_whole(eng_mod, oracle_mod):
+    """Counter contract is keyed by the GLOBAL site index: two half-shards sum to the whole."""
+    p = synth_problem(90, 40, 6, depth=25.0, seed=3)
+    whole = oracle_mod.mu_stats(onehot(p["tau0"]), p["gamma0"], p["eta0"], p["counts"], 9, 4)
+    acc_sm, acc_es = 0, 0
+    for lo, hi in ((0, 41), (41, 90)):
+        e = eng_mod.Engine(0, seed=9)
+        e.set_counts(p["counts"][lo:hi], v0=lo, V_total=90)
+        e.set_state(onehot(p["tau0"][lo:hi]), p["gamma0"], p["eta0"])
+        e.set_rng(9, sweep=4)
+        sm, es = e.mu_stats()
+        acc_sm, acc_es = acc_sm + sm, acc_es + es
+        e.close()
+    assert np.array_equal(acc_sm, whole[0]) and np.array_equal(acc_es, whole[1])
+
+
+@pytest.mark.parametrize("S,G", [(1, 1), (5, 3), (64, 8), (256, 16), (128, 20)])
+def test_draw_gamma_eta_vs_oracle(eng_mod, oracle_mod, S, G):
+    rng = np.random.default_rng(S * 100 + G)
+    sm = rng.integers(0, 5000, size=(S, G)).astype(np.int64)
+    sm[rng.random((S, G)) < 0.3] = 0
+    es = np.diag(rng.integers(10**4, 10**6, 4)).astype(np.int64) + rng.integers(0, 50, size=(4, 4))
+    p = synth_problem(4, S, G, depth=5.0)
+    e = eng_mod.Engine(0, seed=31337)
+    e.set_counts(p["counts"])
+    e.set_state(onehot(p["tau0"]), p["gamma0"], p["eta0"])
+    e.set_rng(31337, sweep=12)
+    g, et = e.draw_gamma_eta(sm, es)
+    g_o = oracle_mod.draw_gamma(sm, 0.1, 1e-6, 31337, 12)
+    e_o = oracle_mod.draw_eta(es, 0.1, 31337, 12)
+    assert rel(g, g_o) < RTOL_TIGHT and rel(et, e_o) < RTOL_TIGHT
+    assert np.allclose(g.sum(1), 1.0, atol=1e-12) and np.allclose(et.sum(1), 1.0, atol=1e-12)
+    e.close()
+
+
+def test_loglik_vs_reference_python_golden(eng_mod, oracle_mod):
+    z = golden("loglik_kat.npz")
+    for ci in range(int(z["ncases"])):
+        counts = z[f"c{ci}_counts"].astype(np.int64)
+        tau = onehot(z[f"c{ci}_tau"])
+        e = eng_mod.Engine(0, seed=1)
+        e.set_counts(counts)
+        e.set_state(tau, z[f"c{ci}_gamma"], z[f"c{ci}_eta"])
+        ll, lp = e.loglik()
+        want_ll, want_lp = z[f"c{ci}_ll_lp"]
+        assert abs(ll - want_ll) <= RTOL_TIGHT * abs(want_ll), ci
+        assert abs(lp - want_lp) <= RTOL_TIGHT * abs(want_lp), ci
+        e.close()
+
+
+# ------------------------------------------------------------------ chains vs oracle
+@pytest.mark.parametrize("V,S,G,depth,n_iter", [(120, 16, 3, 30.0, 25), (300, 64, 8, 20.0, 12), (64, 130, 12, 8.0, 6)])
+def test_update_chain_vs_oracle(eng_mod, oracle_mod, V, S, G, depth, n_iter):
+    p = synth_problem(V, S, G, depth=depth, seed=11 + G, ambiguous=True)
+    seed = 23724839
+    want = oracle_mod.update(onehot(p["tau0"]), p["gamma0"], p["eta0"], p["counts"], n_iter, seed, sweep0=3)
+    e = eng_mod.Engine(0, seed=seed)
+    e.set_counts(p["counts"])
+    e.set_state(onehot(p["tau0"]), p["gamma0"], p["eta0"])
+    e.set_rng(seed, sweep=3)
+    got = e.update(n_iter)
+    tau, gamma, eta = e.get_state()
+    assert np.array_equal(got["nchange"], want["nchange"])
+    assert np.array_equal(tau, want["tau"])                                   # bit-exact integer tau
+    assert np.array_equal(e.get_tau_sum(), want["tau_sum"])
+    assert rel(got["gamma_store"], want["gamma_store"]) < RTOL_TIGHT
+    assert rel(got["eta_store"], want["eta_store"]) < RTOL_TIGHT
+    assert rel(got["ll_store"], want["ll_store"]) < RTOL_TIGHT
+    assert rel(got["lp_store"], want["lp_store"]) < RTOL_TIGHT
+    assert rel(gamma, want["gamma"]) < RTOL_TIGHT and rel(eta, want["eta"]) < RTOL_TIGHT
+    star = e.get_star()
+    assert star["iter"] == want["iter_star"]
+    assert abs(star["lp"] - want["lp_star"]) <= RTOL_TIGHT * abs(want["lp_star"])
+    assert np.array_equal(star["tau"], want["tau_star"])
+    assert rel(star["gamma"], want["gamma_star"]) < RTOL_TIGHT and rel(star["eta"], want["eta_star"]) < RTOL_TIGHT
+    assert want["nchange"].sum() > 0 and e.get_rng()[0] == 3 + n_iter
+    # second update() continues the stream exactly like one long chain split in two
+    want2 = oracle_mod.update(want["tau"], want["gamma"], want["eta"], p["counts"], 3, seed, sweep0=3 + n_iter)
+    got2 = e.update(3)
+    assert np.array_equal(got2["nchange"], want2["nchange"])
+    assert np.array_equal(e.get_state()[0], want2["tau"])
+    e.close()
+
+
+@pytest.mark.parametrize("use_mt", [True, False])
+def test_update_tau_replay_vs_oracle(eng_mod, oracle_mod, use_mt):
+    p = synth_problem(150, 24, 4, depth=10.0, seed=5, ambiguous=True)
+    rng = np.random.default_rng(0)
+    n_iter = 9
+    gs = rng.dirichlet(np.ones(4), size=(n_iter, 24))
+    gs[gs < 1e-6] = 1e-6
+    gs /= gs.sum(2)[:, :, None]
+    es = np.tile(p["eta0"], (n_iter, 1, 1)) * rng.uniform(0.9, 1.1, size=(n_iter, 4, 4))
+    es /= es.sum(2)[:, :, None]
+    want = oracle_mod.update_tau(onehot(p["tau0"]), gs, es, p["counts"], seed=4242, sweep0=0, use_mt=use_mt)
+    e = eng_mod.Engine(0, seed=4242, rng_mode=eng_mod.RNG_MT19937 if use_mt else eng_mod.RNG_PHILOX)
+    e.set_counts(p["counts"])
+    e.set_state(onehot(p["tau0"]), gs[0], es[0])
+    got = e.update_tau(gs, es)
+    assert np.array_equal(got["nchange"], want["nchange"])
+    assert np.array_equal(e.get_state()[0], want["tau"])
+    assert np.array_equal(e.get_tau_sum(), want["tau_sum"])
+    assert rel(got["ll_store"], want["ll_store"]) < RTOL_TIGHT and rel(got["lp_store"], want["lp_store"]) < RTOL_TIGHT
+    star = e.get_star()
+    assert np.array_equal(star["tau"], want["tau_star"])
+    assert abs(star["lp"] - want["lp_star"]) <= RTOL_TIGHT * abs(want["lp_star"])
+    e.close()
+
+
+# ------------------------------------------------------------------ size-independent properties at scale
+def test_properties_at_config_C2_size(eng_mod):
+    """V=10000 S=64 G=8 (BASELINE config C2): conservation laws and run-to-run determinism."""
+    p = synth_problem(10000, 64, 8, depth=100.0, seed=20240611)
+    outs = []
+    for rep in range(2):
+        e = eng_mod.Engine(0, seed=23724839)
+        e.set_counts(p["counts"])
+        e.set_state(onehot(p["tau0"]), p["gamma0"], p["eta0"])
+        sm, es = e.mu_stats()
+        assert sm.sum() == p["counts"].sum()
+        assert np.array_equal(es.sum(1), p["counts"].sum((0, 1)))       # Esum rows = observed-base totals
+        assert np.array_equal(sm.sum(1), p["counts"].sum((0, 2)))       # sum_mu rows = per-sample depth
+        out = e.update(6)
+        tau = e.get_tau_index()
+        ts = e.get_tau_sum()
+        assert (ts.sum(2) == 6).all()
+        assert np.allclose(out["gamma_store"].sum(2), 1.0, atol=1e-12)
+        assert np.allclose(out["eta_store"].sum(2), 1.0, atol=1e-12)
+        assert out["lp_store"][-1] > out["lp_store"][0]
+        outs.append((tau, out["gamma_store"], out["ll_store"], out["nchange"]))
+        e.close()
+    for a, b in zip(outs[0], outs[1]):
+        assert np.array_equal(a, b)                                     # bitwise reproducible

@@ -1,0 +1,74 @@
+"""CPU tests of the host logic and of the C-ABI surface (no compute calls: no GPU here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_library_is_built_and_exports_every_declared_symbol():
+    from desman_b200 import _lib, build
+    build.build()
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    header = open(os.path.join(ROOT, "include", "desman_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b((?:c_|desman_)\w+)\s*\(", header))
+    declared.discard("desman_ctx")
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert b"sm_100a" in _lib.lib().desman_build_info()
+
+
+def test_reference_abi_names_are_exact():
+    # sampletau.pyx:13-19 binds exactly these four C symbols
+    from desman_b200 import _lib
+    for name in ("c_sample_tau", "c_initRNG", "c_setRNG", "c_freeRNG"):
+        assert name in _lib.SYMBOLS
+
+
+def test_sampletau_argument_checks_mirror_cython():
+    from desman_b200 import sampletau
+    tau = np.zeros((3, 2, 4), dtype=np.int64)
+    pi = np.full((5, 2), 0.5)
+    eta = np.full((4, 4), 0.25)
+    var = np.zeros((3, 5, 4), dtype=np.int64)
+    with pytest.raises(TypeError, match="Argument 'tau' has incorrect type"):
+        sampletau.sample_tau(None, pi, eta, var)
+    with pytest.raises(TypeError):
+        sampletau.sample_tau(tau.tolist(), pi, eta, var)
+    with pytest.raises(ValueError, match="expected 'long' but got 'int'"):
+        sampletau.sample_tau(tau.astype(np.int32), pi, eta, var)
+    with pytest.raises(ValueError, match="expected 'double'"):
+        sampletau.sample_tau(tau, pi.astype(np.float32), eta, var)
+    with pytest.raises(ValueError, match="not C-contiguous"):
+        sampletau.sample_tau(np.asfortranarray(tau), pi, eta, var)
+    with pytest.raises(ValueError, match="wrong number of dimensions \\(expected 2, got 1\\)"):
+        sampletau.sample_tau(tau, pi[0], eta, var)
+    with pytest.raises(OverflowError):
+        sampletau.setRNG(2**31)
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a GPU the product must fail loudly, not compute on the host."""
+    from desman_b200 import _lib, engine
+    try:
+        n = _lib.device_count()
+    except _lib.DesmanB200Error:
+        n = 0
+    if n > 0:
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.DesmanB200Error):
+        engine.Engine(0, seed=1)
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "desman_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("oracle/desman_oracle.c)", "").replace("oracle_gamma_variate", ""), f
