@@ -1,0 +1,356 @@
+"""Mirror of the reference class desman/HaploSNP_Sampler.py (same constructor, attributes and
+method names) whose sweeps run on the GPU through libdesman_b200.so.
+
+What differs from the reference, and why:
+  * update()/updateTau() keep tau, gamma, eta and the count tensor resident on the device for the
+    whole call; the externally assignable attributes (tau, gamma, eta, gamma_store, eta_store,
+    bin/desman:140-146,194-199) are uploaded on entry and written back on exit.
+  * mu[V,S,4,G] / E[V,S,4,4] are never materialised -- only their sums are consumed
+    (HaploSNP_Sampler.py:266,276).  mu_store/E_store/tau_store/tauStates (0.8 TB / 0.4 TB / 13 GB /
+    2 TB at the BASELINE configs, :89-103) are not allocated; tauMean()/probabilisticTau() come
+    from per-site occupancy counters kept by the tau kernel.
+  * the mu/gamma/eta draws follow the Philox counter contract instead of numpy's sequential legacy
+    stream (which has no parallel form); tau draws use Philox too, or the GSL-compatible MT19937
+    stream when tau_rng="mt19937".
+"""
+import logging
+import sys
+
+import numpy as np
+
+from . import sampletau as _sampletau
+from ._lib import RNG_MT19937, RNG_PHILOX
+from .engine import Engine
+
+
+class Constants(object):
+    MAX_LOG_DIR_PROB = 100.0
+
+
+class HaploSNP_Sampler():
+
+    def __init__(self, snps, G, randomState, fixed_tau=None, burn_iter=None, max_iter=None, alpha_constant=0.1,
+                 delta_constant=0.1, epsilon=1.0e-6, device=0, seed=None, tau_rng="philox", shard=None, comm=None):
+        # reference defaults, HaploSNP_Sampler.py:33-43
+        self.burn_iter = 250 if burn_iter is None else burn_iter
+        self.max_iter = 250 if max_iter is None else max_iter
+        self.tau_comp_iter = 10
+
+        self.randomState = randomState
+        self.G = G
+        self.V = snps.shape[0]
+        self.S = snps.shape[1]
+        self.variants = np.copy(snps, order='C').astype(np.int64, copy=False)
+        self.epsilon = epsilon
+
+        self.delta = np.empty(4); self.delta.fill(delta_constant)
+        self.delta_constant = delta_constant
+        self.alpha = np.empty(self.G); self.alpha.fill(alpha_constant)
+        self.alpha_constant = alpha_constant
+
+        # the constructor consumes the caller's stream exactly like the reference (:63, :72)
+        self.gamma = self.randomState.dirichlet(self.alpha, size=self.S)
+        self.gamma_store = np.zeros((self.max_iter, self.S, self.G))
+        if fixed_tau is None:
+            tri = self.randomState.randint(0, 4, self.V * self.G)
+            self.tau = np.zeros((self.V, self.G, 4), dtype=np.int64)
+            np.put_along_axis(self.tau, np.reshape(tri, (self.V, self.G, 1)).astype(np.int64), 1, axis=2)
+        else:
+            self.tau = np.reshape(fixed_tau, (self.V, self.G, 4))
+        self.tauIndices = np.zeros((self.V), dtype=np.int64)
+
+        self.eta = 0.96 * np.identity((4)) + 0.01 * np.ones((4, 4))        # :84
+        self.eta_store = np.zeros((self.max_iter, 4, 4))
+
+        self.amatrix = np.identity(4, dtype=np.int64)
+        self.ll = 0.0
+        self.lp = 0.0
+        self.ll_store = np.zeros(self.max_iter)
+        self.lp_store = np.zeros(self.max_iter)
+        self.nchange_store = np.zeros(self.max_iter, dtype=np.int64)
+        self.nTauStates = 4 ** self.G
+        self._set_tau_map()
+
+        self._tau_sum = None          # tau_store.sum(axis=0) of the last update()/updateTau()
+        self._sum_mu = None           # mu.sum(axis=(0,2)) of the last sampleMu()
+        self._Esum = None             # E.sum(axis=(0,1))
+        self._timing = None
+
+        # device side
+        self._device = device
+        self._seed = _sampletau.current_seed() if seed is None else int(seed)
+        self._tau_rng = tau_rng
+        self._shard = shard           # (v0, V_total) when this object holds one V-shard of a larger chain
+        self._comm = comm             # (uid, rank, nranks)
+        self._eng = None
+        self._eng_mode = None
+
+    # ------------------------------------------------------------------ device plumbing
+    def _engine(self, mode=RNG_PHILOX):
+        if self._eng is None or self._eng_mode != mode:
+            sweep = _sampletau.global_sweep()
+            if self._eng is not None:
+                sweep = self._eng.get_rng()[0]
+                self._eng.close()
+            self._eng = Engine(self._device, self._seed, mode)
+            v0, vt = self._shard if self._shard is not None else (0, self.V)
+            self._eng.set_counts(self.variants, v0=v0, V_total=vt)
+            if self._comm is not None:
+                self._eng.comm_init(*self._comm)
+            self._eng.set_rng(self._seed, sweep=sweep)
+            self._eng_mode = mode
+        self._eng.set_hyper(self.alpha_constant, self.delta_constant, self.epsilon)
+        return self._eng
+
+    def _push(self, eng, gamma=None, tau=None, eta=None):
+        tau = self.tau if tau is None else tau
+        gamma = self.gamma if gamma is None else gamma
+        eta = self.eta if eta is None else eta
+        if tau.shape[1] != self.G or gamma.shape[1] != self.G:
+            raise ValueError("tau/gamma do not match G = %d" % self.G)
+        eng.set_state(np.ascontiguousarray(tau, dtype=np.int64), gamma, eta, G=self.G)
+
+    def _pull(self, eng):
+        self.tau, self.gamma, self.eta = eng.get_state()
+
+    def close(self):
+        if self._eng is not None:
+            _sampletau.advance_global_sweep(self._eng.get_rng()[0])
+            self._eng.close()
+            self._eng = None
+
+    def _set_tau_map(self):
+        self.tauMap = np.zeros((self.G, 4), dtype=object if self.G > 31 else np.int64)
+        for g in range(self.G):
+            for a in range(4):
+                self.tauMap[g, a] = a * (4 ** (self.G - g - 1))              # :115-117
+
+    # ------------------------------------------------------------------ small helpers of the reference
+    def calcK(self):
+        return self.V * self.G + self.S * (self.G - 1)
+
+    def mapTauState(self, tauState):
+        return np.einsum('ga,ga', self.tauMap, tauState)                     # :224-226
+
+    def updateTauIndices(self):
+        self.tauIndices = np.einsum('ga,vga->v', self.tauMap, self.tau)      # :228-231, vectorised
+
+    def tauDist(self, tau1, tau2):
+        return int((np.argmax(tau1, axis=1) != np.argmax(tau2, axis=1)).sum())
+
+    def baseProbabilityGivenTau(self, tauState, gamma, eta):
+        return np.einsum('jk,lj,km->lm', tauState, gamma, eta)               # :129-135
+
+    def storeStarState(self, iter):
+        self.gamma_star = np.copy(self.gamma)
+        self.tau_star = np.copy(self.tau)
+        self.tauIndices_star = np.copy(self.tauIndices)
+        self.eta_star = np.copy(self.eta)
+        self.iter_star = iter
+        self.lp_star = self.lp
+
+    # ------------------------------------------------------------------ single Gibbs steps
+    def sampleTau(self, gamma=None, eta=None):
+        """One tau update with (gamma, eta); returns the number of changed (v,g) entries (:148-184)."""
+        eng = self._engine(RNG_MT19937 if self._tau_rng == "mt19937" else RNG_PHILOX)
+        self._push(eng, gamma=gamma, eta=eta)
+        n = eng.sample_tau()
+        self.tau = eng.get_state()[0]
+        self.updateTauIndices()
+        return n
+
+    def sampleMu(self, tauC, gammaC, etaC):
+        """mu/E data augmentation (:284-309); only sum_mu[S,G] and Esum[4,4] are produced."""
+        eng = self._engine()
+        self._push(eng, gamma=gammaC, tau=tauC, eta=etaC)
+        self._sum_mu, self._Esum = eng.mu_stats()
+        return self._sum_mu, self._Esum
+
+    def sampleGamma(self):
+        """gamma[s,:] ~ Dir(alpha + sum_mu[s,:]), clip at epsilon, renormalise (:263-273)."""
+        eng = self._engine()
+        self._push(eng)
+        self.gamma, self._eta_draw = eng.draw_gamma_eta(self._sum_mu, self._Esum)
+
+    def sampleEta(self):
+        """eta[a,:] ~ Dir(delta + Esum[:,a]) (:275-281); drawn together with gamma from the same statistics."""
+        if getattr(self, "_eta_draw", None) is None:
+            eng = self._engine()
+            self._push(eng)
+            _, self._eta_draw = eng.draw_gamma_eta(self._sum_mu, self._Esum)
+        self.eta = self._eta_draw
+        self._eta_draw = None
+
+    def logLikelihood(self, cGamma, cTau, cEta):
+        """Data log likelihood (:431-442)."""
+        return self._ll_lp(cGamma, cTau, cEta)[0]
+
+    def logPosterior(self, cGamma, cTau, cEta):
+        """Log posterior (:444-461)."""
+        return self._ll_lp(cGamma, cTau, cEta)[1]
+
+    def _ll_lp(self, cGamma, cTau, cEta):
+        cTau = np.asarray(cTau)
+        if not (((cTau == 0) | (cTau == 1)).all() and (cTau.sum(axis=2) == 1).all()):
+            raise NotImplementedError("log-likelihood of a non-one-hot tau (DIC, :486-496) is outside the hot path")
+        eng = self._engine()
+        self._push(eng, gamma=np.asarray(cGamma), tau=cTau, eta=np.asarray(cEta))
+        return eng.loglik()
+
+    # ------------------------------------------------------------------ chain drivers
+    def _log_progress(self, res, what):
+        for it in range(0, len(res["nchange"]), 10):                           # :360-361, :402-403
+            logging.info('Gibbs Iter %d, no. changed = %d, %s = %f' % (it, res["nchange"][it], what, res["lp_store"][it]))
+
+    def _finish(self, eng, res, n_iter, full):
+        self._pull(eng) if full else setattr(self, "tau", eng.get_state()[0])
+        star = eng.get_star()
+        self.tau_star = star["tau"]
+        self.lp_star = star["lp"]
+        self.iter_star = star["iter"]
+        if full:
+            self.gamma_star, self.eta_star = star["gamma"], star["eta"]
+        self.ll_store = res["ll_store"]
+        self.lp_store = res["lp_store"]
+        self.nchange_store = res["nchange"]
+        if n_iter > 0:
+            self.ll, self.lp = float(res["ll_store"][-1]), float(res["lp_store"][-1])
+        self._tau_sum = eng.get_tau_sum()
+        self._timing = eng.get_timing()
+        self.updateTauIndices()
+        self.tauIndices_star = np.einsum('ga,vga->v', self.tauMap, self.tau_star)
+
+    def update(self):
+        """max_iter Gibbs sweeps mu/E -> gamma -> tau -> eta -> ll/lp with MAP tracking (:334-365)."""
+        eng = self._engine()
+        self._push(eng)
+        res = eng.update(self.max_iter)
+        self.gamma_store, self.eta_store = res["gamma_store"], res["eta_store"]
+        self._finish(eng, res, self.max_iter, True)
+        self._log_progress(res, "nlp")
+
+    def updateTau(self):
+        """tau-only replay against gamma_store/eta_store (:383-407)."""
+        if self.gamma_store.shape[0] < self.max_iter or self.eta_store.shape[0] < self.max_iter:
+            raise ValueError("gamma_store/eta_store hold fewer than max_iter iterations")
+        eng = self._engine(RNG_MT19937 if self._tau_rng == "mt19937" else RNG_PHILOX)
+        self._push(eng, gamma=self.gamma_store[0], eta=self.eta_store[0])
+        res = eng.update_tau(self.gamma_store[:self.max_iter], self.eta_store[:self.max_iter])
+        self._finish(eng, res, self.max_iter, False)
+        self._log_progress(res, "nll")
+        sys.stdout.flush()
+
+    def burn(self):
+        """burn_iter sweeps printing `iter ll lp` (:313-324)."""
+        eng = self._engine()
+        self._push(eng)
+        res = eng.update(self.burn_iter)
+        self._pull(eng)
+        for it in range(self.burn_iter):
+            print(str(it) + " " + str(res["ll_store"][it]) + " " + str(res["lp_store"][it]))
+        if self.burn_iter > 0:
+            self.ll, self.lp = float(res["ll_store"][-1]), float(res["lp_store"][-1])
+
+    def burnTau(self):
+        """burn_iter tau-only updates at (gamma_star, eta_star) (:367-380)."""
+        gs = np.tile(self.gamma_star, (self.burn_iter, 1, 1))
+        es = np.tile(self.eta_star, (self.burn_iter, 1, 1))
+        eng = self._engine(RNG_MT19937 if self._tau_rng == "mt19937" else RNG_PHILOX)
+        self._push(eng, gamma=self.gamma_star, eta=self.eta_star)
+        res = eng.update_tau(gs, es)
+        self.tau = eng.get_state()[0]
+        for it in range(self.burn_iter):
+            print(str(it) + "," + str(res["nchange"][it]) + "," + str(res["lp_store"][it]))
+            sys.stdout.flush()
+        if self.burn_iter > 0:
+            self.ll, self.lp = float(res["ll_store"][-1]), float(res["lp_store"][-1])
+
+    # ------------------------------------------------------------------ summaries
+    def meanDeviance(self):
+        return -2.0 * np.mean(self.ll_store)                                   # :463-465
+
+    def gammaMean(self):
+        return np.mean(self.gamma_store, axis=0)                               # :467-471
+
+    def etaMean(self):
+        return np.mean(self.eta_store, axis=0)                                 # :473-477
+
+    def tauMean(self):
+        """np.mean(tau_store, axis=0) (:479-483) from the kernel's occupancy counters."""
+        if self._tau_sum is None:
+            return np.zeros((self.V, self.G, 4))
+        return self._tau_sum / float(self.max_iter)
+
+    def probabilisticTau(self):
+        return self.tauMean()                                                  # :834-840
+
+    @property
+    def tau_store(self):
+        raise AttributeError("tau_store[max_iter,V,G,4] is not materialised by desman_b200 "
+                             "(use tauMean()/probabilisticTau(); see DESIGN.md)")
+
+    mu_store = E_store = tauStates = tau_store
+
+    # ------------------------------------------------------------------ host-side bookkeeping (V*G^2 integer work)
+    def calculateSND(self, tau):
+        """Pairwise single-nucleotide differences between strains (:712-730)."""
+        idx = np.argmax(np.asarray(tau), axis=2)
+        G = idx.shape[1]
+        snd = np.zeros((G, G), dtype=np.int64)
+        for g in range(G):
+            snd[g, :] = (idx != idx[:, g:g + 1]).sum(axis=0)
+        return snd
+
+    def compSND(self, tau1, tau2):
+        i1, i2 = np.argmax(np.asarray(tau1), axis=2), np.argmax(np.asarray(tau2), axis=2)
+        snd = np.zeros((i1.shape[1], i2.shape[1]), dtype=np.int64)
+        for g in range(i1.shape[1]):
+            snd[g, :] = (i2 != i1[:, g:g + 1]).sum(axis=0)
+        return snd
+
+    def variableTau(self, tau):
+        idx = np.argmax(np.asarray(tau), axis=2)
+        return (idx != idx[:, :1]).any(axis=1)
+
+    def removeDegenerate(self):
+        """Merge identical haplotypes (SND == 0), adding their gamma columns (:771-832)."""
+        snd = self.calculateSND(self.tau)
+        deleted = np.zeros(self.G, dtype=bool)
+        allmapped = []
+        for g in range(self.G):
+            gmap = []
+            for h in range(g + 1, self.G):
+                if not deleted[h] and snd[g, h] == 0:
+                    deleted[h] = True
+                    gmap.append(h)
+            allmapped.append(gmap)
+        NU = self.G - int(deleted.sum())
+        tau_new = np.zeros((self.V, NU, 4), dtype=np.int64)
+        gamma_new = np.zeros((self.S, NU))
+        k = 0
+        for g in range(self.G):
+            if not deleted[g]:
+                tau_new[:, k, :] = self.tau[:, g, :]
+                gamma_new[:, k] = self.gamma[:, g]
+                for h in allmapped[g]:
+                    gamma_new[:, k] += self.gamma[:, h]
+                k += 1
+        self.gamma = gamma_new
+        self.tau = tau_new
+        self.G = NU
+        self.alpha = np.empty(self.G); self.alpha.fill(self.alpha_constant)
+        self.gamma_store = np.zeros((self.max_iter, self.S, self.G))          # stores are re-allocated (:809-814)
+        self._tau_sum = None
+        self.nTauStates = 4 ** self.G
+        self._set_tau_map()
+        self.updateTauIndices()
+
+    # ------------------------------------------------------------------ outside the hot path
+    def _next(self, *a, **k):
+        raise NotImplementedError("4^G joint-state enumeration (assignTau/logTauProb/Chib) is not part of the "
+                                  "Gibbs hot path; see DESIGN.md 'out of scope'")
+
+    assignTau = logTauProb = chibMarginalLogLikelihood = chibMarginalLogLikelihood2 = sampleTauFixTau = _next
+
+    def DIC(self):
+        raise NotImplementedError("DIC needs the likelihood of the non-one-hot tauMean (:486-496); outside the hot path")

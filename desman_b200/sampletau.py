@@ -15,6 +15,23 @@ import numpy as np
 from . import _lib
 
 
+_seed = 0          # last seed given to setRNG: the device chains are keyed by it, like the GSL stream
+_sweep = 0         # process-global Philox sweep counter (the analogue of the single global GSL stream)
+
+
+def current_seed():
+    return _seed
+
+
+def global_sweep():
+    return _sweep
+
+
+def advance_global_sweep(sweep):
+    global _sweep
+    _sweep = max(_sweep, int(sweep))
+
+
 def initRNG():
     """c_initRNG (c_sample_tau.c:26-34)"""
     _lib.lib().c_initRNG()
@@ -30,6 +47,8 @@ def setRNG(seed):
         raise OverflowError("value too large to convert to int")
     if seed < -2**31:
         raise OverflowError("value too small to convert to int")
+    global _seed, _sweep
+    _seed, _sweep = seed & 0xFFFFFFFFFFFFFFFF, 0
     _lib.lib().c_setRNG(C.c_ulong(seed & 0xFFFFFFFFFFFFFFFF))  # int -> unsigned long wrap, as in C
 
 
