@@ -34,7 +34,11 @@ def test_nmft_matches_oracle(oracle_mod, V, S, G, fix):
     assert rel(gtrace, wtrace) < 1e-9 and abs(gdiv - wdiv) <= 1e-9 * abs(wdiv)
     assert rel(gg, wg) < 1e-6
     assert np.max(np.abs(gt - wt)) < 1e-9
-    assert np.array_equal(oracle_mod.nmft_get_tau(gt, V, G), oracle_mod.nmft_get_tau(wt, V, G))
+    # one-hot argmax must agree wherever the winner is not an exact floating-point tie
+    srt = np.sort(wt.reshape(4, V, G), axis=0)
+    clear = (srt[3] - srt[2]) > 1e-9
+    a, b = oracle_mod.nmft_get_tau(gt, V, G), oracle_mod.nmft_get_tau(wt, V, G)
+    assert np.array_equal(a[clear], b[clear]) and clear.mean() > 0.9
 
 
 def test_nmft_class_reproduces_reference_on_cog0015():
@@ -69,13 +73,13 @@ def _write_freq(path):
 
 
 def test_cli_config_C1_outputs(tmp_path):
-    """bin/desman on COG0015 (-g 5 -i 20): same files, same headers/shapes as the reference's run; the chain
+    """bin/desman on COG0015 (-g 5 -i 50): same files, same headers/shapes as the reference's run; the chain
     reaches the reference's posterior plateau (chains with different RNG streams agree statistically,
     not draw by draw: reference replicates differ by ~4000 deviance units across seeds)."""
     freq = tmp_path / "cog0015.freq"
     _write_freq(str(freq))
     out = tmp_path / "out"
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "desman"), str(freq), "-g", "5", "-i", "20",
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "desman"), str(freq), "-g", "5", "-i", "50",
                         "-o", str(out)], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     ref_dir = os.path.join(GOLDEN, "cog0015_i50")
@@ -91,8 +95,8 @@ def test_cli_config_C1_outputs(tmp_path):
     fit = open(out / "fit.txt").read().strip().split(",")
     ref_fit = open(os.path.join(ref_dir, "fit.txt")).read().strip().split(",")
     assert fit[0] == "Fit" and fit[1] == "5" and len(fit) == 5
-    assert abs(float(fit[3]) - float(ref_fit[3])) < 0.02 * abs(float(ref_fit[3]))     # lp_star on the same plateau
-    assert abs(float(fit[4]) - float(ref_fit[4])) < 0.02 * abs(float(ref_fit[4]))     # mean deviance
+    assert abs(float(fit[3]) - float(ref_fit[3])) < 5e-3 * abs(float(ref_fit[3]))     # lp_star on the same plateau
+    assert abs(float(fit[4]) - float(ref_fit[4])) < 5e-3 * abs(float(ref_fit[4]))     # mean deviance
     log = open(out / "log_file.txt").read()
     assert "NTF Iter 0, div = 87258.148805" in log                  # same NMFT start as the reference log
     assert "Gibbs Iter 0, no. changed =" in log and "Wrote fit stats" in log
