@@ -50,6 +50,8 @@ SYMBOLS = {
     "desman_get_tau_sum": (C.c_int, [_ctx, _p64]),
     "desman_nmft_factorize": (C.c_int, [_ctx, _p64, C.c_int64, C.c_int, C.c_int, _pd, _pd, C.c_int, C.c_double, C.c_int,
                                         C.POINTER(C.c_int), _pd, _pd]),
+    "desman_set_option": (C.c_int, [_ctx, C.c_char_p, C.c_int64]),
+    "desman_get_tier_counts": (C.c_int, [_ctx, _p64, C.c_int]),
     "desman_comm_unique_id": (C.c_int, [C.c_char_p]),
     "desman_comm_init": (C.c_int, [_ctx, C.c_char_p, C.c_int, C.c_int]),
     "desman_set_profiling": (C.c_int, [_ctx, C.c_int, C.c_int]),

@@ -126,6 +126,8 @@ struct desman_ctx {
     size_t counts_cap = 0;
     size_t cap_vg = 0, cap_sg = 0;
     uint32_t last_n_iter = 0;
+    int tau_exact = 0;                       // 1: FP64 reference-order path for every draw
+    unsigned long long *tiers = nullptr;     // [3] draws decided by tier 1/2/3
     // scratch
     void *scratch = nullptr;
     size_t scratch_cap = 0;
@@ -225,6 +227,9 @@ extern "C" int desman_ctx_create(desman_ctx **out, int device, uint64_t seed, in
     CU(cudaMalloc(&c->red, 2 * sizeof(double)));
     CU(cudaMalloc(&c->scal, 4 * sizeof(double)));
     CU(cudaMalloc(&c->flag, sizeof(int)));
+    CU(cudaMalloc(&c->tiers, 3 * sizeof(unsigned long long)));
+    CU(cudaMemset(c->tiers, 0, 3 * sizeof(unsigned long long)));
+    { const char *ex = getenv("DESMAN_B200_TAU_EXACT"); c->tau_exact = (ex && atoi(ex)) ? 1 : 0; }
     CU(cudaMalloc(&c->mt_state, 624 * sizeof(uint32_t)));
     CU(cudaMemset(c->scal, 0, 4 * sizeof(double)));
     *out = c;
@@ -239,7 +244,7 @@ extern "C" int desman_ctx_destroy(desman_ctx *c)
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     void *ptrs[] = {c->counts, c->tau, c->tau_star, c->gamma, c->eta, c->eta_new, c->gamma_star, c->eta_star, c->stats,
                     c->nchange, c->ll_partial, c->red, c->scal, c->flag, c->tau_cnt, c->tau_last, c->mt_state, c->words,
-                    c->scratch, c->flush_buf};
+                    c->scratch, c->flush_buf, c->tiers};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
@@ -519,6 +524,8 @@ static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, con
     p.tau_last = c->tau_last;
     p.iter = iter;
     p.do_draw = draw ? 1 : 0;
+    p.exact_only = c->tau_exact;
+    p.tier_counts = c->tiers;
     const size_t smem = tau_smem_bytes(c->S, c->G);
     if (smem > 227 * 1024) return fail(DESMAN_EINVAL, "S*G too large for the shared-memory tile (%zu bytes)", smem);
     CU(cudaFuncSetAttribute(tau_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -895,6 +902,25 @@ extern "C" int desman_comm_init(desman_ctx *c, const char id[128], int rank, int
     memcpy(u.internal, id, 128);
     NC(g_nccl.CommInitRank(&c->comm, nranks, u, rank));
     c->rank = rank; c->nranks = nranks;
+    return DESMAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ options
+extern "C" int desman_set_option(desman_ctx *c, const char *name, int64_t value)
+{
+    if (!c || !name) return fail(DESMAN_EINVAL, "desman_set_option: bad arguments");
+    if (!strcmp(name, "tau_exact")) { c->tau_exact = value ? 1 : 0; return DESMAN_OK; }
+    return fail(DESMAN_EINVAL, "unknown option '%s'", name);
+}
+
+extern "C" int desman_get_tier_counts(desman_ctx *c, int64_t out[3], int reset)
+{
+    CU(cudaSetDevice(c->device));
+    unsigned long long h[3];
+    CU(cudaMemcpyAsync(h, c->tiers, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    if (reset) CU(cudaMemsetAsync(c->tiers, 0, sizeof(h), c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 3; i++) out[i] = (int64_t)h[i];
     return DESMAN_OK;
 }
 

@@ -5,6 +5,21 @@
 // samples s, strains g strictly in order (each draw conditions on the tau just written, :133,:180).
 // The site's S count cells (one 128-bit int32x4 word per (v,s)) are staged once into the warp's
 // shared-memory tile and re-read for every strain.
+//
+// Arithmetic: "filtered exact".  The reference evaluates 16*S logs in FP64 per (v,g); under that
+// arithmetic the kernel is bound by the FP64/log rate, ~100x above its HBM floor.  What has to be
+// reproduced, though, is only the DRAW t = sample4(softmax(L), u).  So per (v,g):
+//   tier 1  log-likelihood differences D_a = L_a - L_cur in FP32 (MUFU lg2.approx) with a rigorous
+//           running error bound B_a.  If one candidate leads every other by more than 60 nats even
+//           after the bounds, its probability differs from 1 by < 3e-26 < 2^-32 <= u-grid spacing,
+//           so the draw is decided without evaluating a single exp.
+//   tier 2  otherwise the CDF boundaries are bracketed in FP64 from D_a +- B_a; if u lies outside
+//           every bracket (plus 1e-9 slack) the draw is decided.
+//   tier 3  otherwise (u within the bracket of a boundary, or u == 0) the (v,g) step is recomputed
+//           with the reference's FP64 arithmetic and operation order (tau_exact_logp below).
+// Cancellation-free by construction: the mixture P[s][b] = sum_h eta[tau_h][b]*gamma[s][h] is kept in
+// FP64 and base = P - eta[cur][b]*gamma[s][g] is formed in FP64 before rounding to FP32; every FP32
+// quantity that enters a log is then a sum of non-negative terms (relative error a few ulp).
 #pragma once
 #include "common.cuh"
 
@@ -25,65 +40,35 @@ struct TauParams {
     uint32_t *tau_last;      // [V][G] iteration at which the current base was adopted
     uint32_t iter;           // iteration index inside the current update() call
     int do_draw;             // 0: skip the Gibbs draw, only accumulate the log-likelihood term
+    int exact_only;          // 1: every (v,g) step takes the FP64 reference-order path (validation)
+    unsigned long long *tier_counts;  // [3] += draws decided by tier 1 / 2 / 3 (or nullptr)
 };
 
 #define TAU_WARPS 8
+#define TAU_GAP 60.0f            // nats; exp(-60) = 8.8e-27, 3*exp(-60) << 2^-32
+#define TAU_SLACK 1.0e-9         // absolute slack on CDF brackets (covers all FP64 rounding)
 
-// Reference arithmetic (c_sample_tau.c:136-176) in FP64: base over h ascending skipping g,
-// candidate term added last, count through float, softmax with max subtraction, strict '<' CDF.
-// Terms with n == 0 are skipped: 0*log(p) adds exactly -0.0 there (p > 0 because eta, gamma > 0).
-__global__ void __launch_bounds__(TAU_WARPS * 32) tau_sample_kernel(TauParams p)
+// ---------------------------------------------------------------------------------------------
+// Reference arithmetic (c_sample_tau.c:136-170) in FP64 for ONE (v,g): base over h ascending skipping
+// g from 0.0, candidate term added last, count through float.  Terms with n == 0 are skipped:
+// 0*log(p) adds exactly -0.0 there (p > 0 because eta, gamma > 0).  All lanes of the warp call this.
+__device__ __forceinline__ void tau_exact_logp(const int4 *tile, const double *gT, const double *eta_s, uint64_t code,
+                                               int g, int S, int Sp, int G, int lane, double L[4])
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int S = p.S, G = p.G;
-    const int Sp = (S + 31) & ~31;
-    double *gT = reinterpret_cast<double *>(smem_raw);           // [G][Sp] gamma transposed
-    double *eta_s = gT + (size_t)G * Sp;                         // [16]
-    double *etall_s = eta_s + 16;                                // [16]
-    int4 *tiles = reinterpret_cast<int4 *>(etall_s + 16);        // [TAU_WARPS][S]
-    __shared__ double ll_warp[TAU_WARPS];
-
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < G * Sp; i += blockDim.x) {
-        int g = i / Sp, s = i - g * Sp;
-        gT[i] = (s < S) ? p.gamma[(size_t)s * G + g] : 0.0;
-    }
-    if (threadIdx.x < 16) {
-        eta_s[threadIdx.x] = p.eta[threadIdx.x];
-        etall_s[threadIdx.x] = p.eta_ll ? p.eta_ll[threadIdx.x] : 0.0;
-    }
-    __syncthreads();
-
-    int4 *tile = tiles + (size_t)wib * S;
-    const int gw = blockIdx.x * TAU_WARPS + wib, nw = gridDim.x * TAU_WARPS;
-    const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
-    unsigned int flips = 0;
-    double ll_acc = 0.0;
-
-    for (int v = gw; v < p.V; v += nw) {
-        const int4 *src = p.counts + (size_t)v * S;
-        for (int s = lane; s < S; s += 32) tile[s] = ld_counts(src + s);
-        uint64_t code = load_tau_code(p.tau + (size_t)v * G, G, lane);
-        const uint64_t code_in = code;
-        __syncwarp();
-
-        for (int g = 0; g < (p.do_draw ? G : 0); g++) {
-            const int cur = code_get(code, g);
-            double L0 = 0.0, L1 = 0.0, L2 = 0.0, L3 = 0.0;
-            for (int s = lane; s < S; s += 32) {
-                const int4 n = tile[s];
-                if ((n.x | n.y | n.z | n.w) == 0) continue;
-                double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
-                for (int h = 0; h < G; h++) {
-                    if (h == g) continue;
-                    const double *e = eta_s + 4 * code_get(code, h);
-                    const double gm = gT[h * Sp + s];
-                    b0 = fma(e[0], gm, b0); b1 = fma(e[1], gm, b1);
-                    b2 = fma(e[2], gm, b2); b3 = fma(e[3], gm, b3);
-                }
-                const double gg = gT[g * Sp + s];
-                const double f0 = (double)(float)n.x, f1 = (double)(float)n.y,
-                             f2 = (double)(float)n.z, f3 = (double)(float)n.w;
+    double L0 = 0.0, L1 = 0.0, L2 = 0.0, L3 = 0.0;
+    for (int s = lane; s < S; s += 32) {
+        const int4 n = tile[s];
+        if ((n.x | n.y | n.z | n.w) == 0) continue;
+        double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+        for (int h = 0; h < G; h++) {
+            if (h == g) continue;
+            const double *e = eta_s + 4 * code_get(code, h);
+            const double gm = gT[h * Sp + s];
+            b0 = fma(e[0], gm, b0); b1 = fma(e[1], gm, b1);
+            b2 = fma(e[2], gm, b2); b3 = fma(e[3], gm, b3);
+        }
+        const double gg = gT[g * Sp + s];
+        const double f0 = (double)(float)n.x, f1 = (double)(float)n.y, f2 = (double)(float)n.z, f3 = (double)(float)n.w;
 #define TAU_CAND(a, L)                                                        \
     {                                                                         \
         const double *e = eta_s + 4 * (a);                                    \
@@ -92,26 +77,245 @@ __global__ void __launch_bounds__(TAU_WARPS * 32) tau_sample_kernel(TauParams p)
         if (n.z) L = fma(f2, log(fma(e[2], gg, b2)), L);                      \
         if (n.w) L = fma(f3, log(fma(e[3], gg, b3)), L);                      \
     }
-                TAU_CAND(0, L0) TAU_CAND(1, L1) TAU_CAND(2, L2) TAU_CAND(3, L3)
+        TAU_CAND(0, L0) TAU_CAND(1, L1) TAU_CAND(2, L2) TAU_CAND(3, L3)
 #undef TAU_CAND
+    }
+    L[0] = warp_sum(L0); L[1] = warp_sum(L1); L[2] = warp_sum(L2); L[3] = warp_sum(L3);
+}
+
+// normaliseLog4 + sample4 (c_sample_tau.c:48-91)
+__device__ __forceinline__ int tau_exact_pick(const double L[4], double u)
+{
+    double mx = L[0];
+    if (L[1] > mx) mx = L[1];
+    if (L[2] > mx) mx = L[2];
+    if (L[3] > mx) mx = L[3];
+    const double e0 = exp(L[0] - mx), e1 = exp(L[1] - mx), e2 = exp(L[2] - mx), e3 = exp(L[3] - mx);
+    const double sum = ((0.0 + e0) + e1) + e2 + e3;
+    const double p0 = e0 / sum, p1 = e1 / sum, p2 = e2 / sum;
+    const double c0 = p0, c1 = p1 + c0, c2 = p2 + c1;
+    return (u < c0) ? 0 : (u < c1) ? 1 : (u < c2) ? 2 : 3;
+}
+
+// Sum four per-lane floats over the warp with 10 shuffles instead of 20 (transpose-reduce), result in all lanes.
+__device__ __forceinline__ void warp_sum4(float &a, float &b, float &c, float &d, int lane)
+{
+    const bool up16 = lane & 16;
+    float s0 = up16 ? a : c, s1 = up16 ? b : d;          // what I send
+    float k0 = up16 ? c : a, k1 = up16 ? d : b;          // what I keep (lanes <16 keep a,b; >=16 keep c,d)
+    k0 += __shfl_xor_sync(DESMAN_FULL_MASK, s0, 16);
+    k1 += __shfl_xor_sync(DESMAN_FULL_MASK, s1, 16);
+    const bool up8 = lane & 8;
+    float s = up8 ? k0 : k1, k = up8 ? k1 : k0;          // lanes with bit3 clear keep k0, set keep k1
+    k += __shfl_xor_sync(DESMAN_FULL_MASK, s, 8);
+    k += __shfl_xor_sync(DESMAN_FULL_MASK, k, 4);
+    k += __shfl_xor_sync(DESMAN_FULL_MASK, k, 2);
+    k += __shfl_xor_sync(DESMAN_FULL_MASK, k, 1);
+    // value index held by lane: (lane>>4)*2 + ((lane>>3)&1)  -> a:0-7, b:8-15, c:16-23, d:24-31
+    a = __shfl_sync(DESMAN_FULL_MASK, k, 0);
+    b = __shfl_sync(DESMAN_FULL_MASK, k, 8);
+    c = __shfl_sync(DESMAN_FULL_MASK, k, 16);
+    d = __shfl_sync(DESMAN_FULL_MASK, k, 24);
+}
+
+// error-model constants (log2 units per read); u = 2^-24
+//   q = base32 + eta32*gamma32: base32 carries 1 rounding (from FP64), the product 3, the sum 1 -> <= 5u relative
+//   lg2.approx: abs error <= 2^-22 * max(1, |lg2 q|)   (CUDA math API, __log2f)
+//   lP = lg2((float)P64): 1u relative + the same lg2 bound
+#define TAU_C0 (6.0f * 5.9604645e-8f * 1.4426950f + 2.0f * 2.3841858e-7f)   // relative parts + the two max(1,.) floors
+#define TAU_C1 3.0e-7f    // 2^-22 per unit of |lg2| (lg2.approx) + 2^-24 per unit for the rounding of (lq - lP)
+// FP32 accumulation: (4*nch adds per lane + 5 reduction levels + the product rounding) * 2^-24, relative to sum |terms|
+#define TAU_ACC(nch) ((float)(4 * (nch) + 8) * 5.9604645e-8f)
+// FP64 mixture P carries <= (2G+2)*2^-53*P absolute error; relative to a candidate q that is amplified by P/q = 2^(lP-lq)
+#define TAU_CANCEL(G) ((float)(2 * (G) + 2) * 1.1102230e-16f * 1.4426950f)
+
+__global__ void __launch_bounds__(TAU_WARPS * 32) tau_sample_kernel(TauParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = p.S, G = p.G;
+    const int Sp = (S + 31) & ~31;
+    double *gT = reinterpret_cast<double *>(smem_raw);           // [G][Sp] gamma transposed (FP64)
+    double *eta_s = gT + (size_t)G * Sp;                         // [16]
+    double *etall_s = eta_s + 16;                                // [16]
+    double *P64 = etall_s + 16;                                  // [TAU_WARPS][Sp][4] mixture probabilities
+    float *gT32 = reinterpret_cast<float *>(P64 + (size_t)TAU_WARPS * Sp * 4);   // [G][Sp]
+    float *eta32 = gT32 + (size_t)G * Sp;                        // [16]
+    float4 *lP = reinterpret_cast<float4 *>(eta32 + 16);         // [TAU_WARPS][Sp] lg2 of P
+    int4 *tiles = reinterpret_cast<int4 *>(lP + (size_t)TAU_WARPS * Sp);         // [TAU_WARPS][Sp]
+    __shared__ double ll_warp[TAU_WARPS];
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < G * Sp; i += blockDim.x) {
+        const int g = i / Sp, s = i - g * Sp;
+        const double x = (s < S) ? p.gamma[(size_t)s * G + g] : 0.0;
+        gT[i] = x;
+        gT32[i] = (float)x;
+    }
+    if (threadIdx.x < 16) {
+        eta_s[threadIdx.x] = p.eta[threadIdx.x];
+        eta32[threadIdx.x] = (float)p.eta[threadIdx.x];
+        etall_s[threadIdx.x] = p.eta_ll ? p.eta_ll[threadIdx.x] : 0.0;
+    }
+    __syncthreads();
+
+    int4 *tile = tiles + (size_t)wib * Sp;
+    double *Pw = P64 + (size_t)wib * Sp * 4;
+    float4 *lPw = lP + (size_t)wib * Sp;
+    const int nch = Sp >> 5;
+    const int gw = blockIdx.x * TAU_WARPS + wib, nw = gridDim.x * TAU_WARPS;
+    const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+    unsigned int flips = 0, n1 = 0, n2 = 0, n3 = 0;
+    double ll_acc = 0.0;
+
+    for (int v = gw; v < p.V; v += nw) {
+        const int4 *src = p.counts + (size_t)v * S;
+        uint64_t code = load_tau_code(p.tau + (size_t)v * G, G, lane);
+        const uint64_t code_in = code;
+        // stage counts; mixture P (FP64, ascending h) and its lg2; per-lane read count for the error bound
+        float nlane = 0.0f, mlP = 1.0f;
+        for (int c = 0; c < nch; c++) {
+            const int s = c * 32 + lane;
+            int4 n = make_int4(0, 0, 0, 0);
+            if (s < S) n = ld_counts(src + s);
+            tile[s] = n;
+            double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+            for (int h = 0; h < G; h++) {
+                const double *e = eta_s + 4 * code_get(code, h);
+                const double gm = gT[h * Sp + s];
+                b0 = fma(e[0], gm, b0); b1 = fma(e[1], gm, b1);
+                b2 = fma(e[2], gm, b2); b3 = fma(e[3], gm, b3);
             }
-            L0 = warp_sum(L0); L1 = warp_sum(L1); L2 = warp_sum(L2); L3 = warp_sum(L3);
-            // normaliseLog4 (c_sample_tau.c:48-70)
-            double mx = L0;
-            if (L1 > mx) mx = L1;
-            if (L2 > mx) mx = L2;
-            if (L3 > mx) mx = L3;
-            const double e0 = exp(L0 - mx), e1 = exp(L1 - mx), e2 = exp(L2 - mx), e3 = exp(L3 - mx);
-            const double sum = ((0.0 + e0) + e1) + e2 + e3;
-            const double p0 = e0 / sum, p1 = e1 / sum, p2 = e2 / sum;
+            if (s >= S) { b0 = 1.0; b1 = 1.0; b2 = 1.0; b3 = 1.0; }   // padding lanes: finite logs, zero counts
+            Pw[s * 4 + 0] = b0; Pw[s * 4 + 1] = b1; Pw[s * 4 + 2] = b2; Pw[s * 4 + 3] = b3;
+            float4 l;
+            l.x = __log2f((float)b0); l.y = __log2f((float)b1); l.z = __log2f((float)b2); l.w = __log2f((float)b3);
+            lPw[s] = l;
+            if (s < S) {
+                nlane += (float)(n.x + n.y + n.z + n.w);
+                mlP = fmaxf(mlP, fmaxf(fmaxf(fabsf(l.x), fabsf(l.y)), fmaxf(fabsf(l.z), fabsf(l.w))));
+            }
+        }
+        __syncwarp();
+
+        for (int g = 0; g < (p.do_draw ? G : 0); g++) {
+            const int cur = code_get(code, g);
             uint32_t w;
             if (p.words) w = p.words[(size_t)v * G + g];
             else w = philox4x32_10((uint32_t)(p.v0 + v), (uint32_t)g, p.sweep, (uint32_t)STAGE_TAU << 28, k0, k1).x;
-            const double u = (double)w / 4294967296.0;              // gsl_rng_uniform, :174
-            // sample4 (c_sample_tau.c:72-91)
-            const double c0 = p0, c1 = p1 + c0, c2 = p2 + c1;
-            const int t = (u < c0) ? 0 : (u < c1) ? 1 : (u < c2) ? 2 : 3;
+            const double u = (double)w / 4294967296.0;              // gsl_rng_uniform, c_sample_tau.c:174
+            int t = -1;
+            if (!p.exact_only && w != 0u) {
+                // ---- tier 1: FP32 differences D_a = log2-likelihood(a) - log2-likelihood(cur), a != cur
+                float D0 = 0.f, D1 = 0.f, D2 = 0.f, D3 = 0.f;       // log2 units
+                float A = 0.f;                                      // sum |terms| (accumulation error)
+                float mq = 1.0f;                                    // max |lg2 q| over this lane's terms
+                const double *ec = eta_s + 4 * cur;
+                for (int c = 0; c < nch; c++) {
+                    const int s = c * 32 + lane;
+                    const int4 n = tile[s];
+                    const bool any0 = __any_sync(DESMAN_FULL_MASK, n.x != 0), any1 = __any_sync(DESMAN_FULL_MASK, n.y != 0),
+                               any2 = __any_sync(DESMAN_FULL_MASK, n.z != 0), any3 = __any_sync(DESMAN_FULL_MASK, n.w != 0);
+                    const double gg = gT[g * Sp + s];
+                    const float gf = gT32[g * Sp + s];
+                    const float4 l = lPw[s];
+                    // base = P - eta[cur][b]*gamma (FP64: no cancellation error), then one rounding to FP32
+                    const float q0 = fmaxf((float)fma(-ec[0], gg, Pw[s * 4 + 0]), 0.f), q1 = fmaxf((float)fma(-ec[1], gg, Pw[s * 4 + 1]), 0.f),
+                                q2 = fmaxf((float)fma(-ec[2], gg, Pw[s * 4 + 2]), 0.f), q3 = fmaxf((float)fma(-ec[3], gg, Pw[s * 4 + 3]), 0.f);
+                    const float f0 = (float)n.x, f1 = (float)n.y, f2 = (float)n.z, f3 = (float)n.w;
+#define TAU_TERM(anyb, fb, qb, lb, ea, D)                                  \
+    if (anyb) {                                                            \
+        float lq = __log2f(fmaf(ea, gf, qb));                              \
+        lq = (fb != 0.f) ? lq : lb;      /* n == 0: term is exactly 0 */   \
+        const float tm = fb * (lq - lb);                                   \
+        D += tm;                                                           \
+        A += fabsf(tm);                                                    \
+        mq = fmaxf(mq, fabsf(lq));                                         \
+    }
+#define TAU_FCAND(a, D)                                                    \
+    if (cur != (a)) {                                                      \
+        const float *e = eta32 + 4 * (a);                                  \
+        TAU_TERM(any0, f0, q0, l.x, e[0], D)                               \
+        TAU_TERM(any1, f1, q1, l.y, e[1], D)                               \
+        TAU_TERM(any2, f2, q2, l.z, e[2], D)                               \
+        TAU_TERM(any3, f3, q3, l.w, e[3], D)                               \
+    }
+                    TAU_FCAND(0, D0) TAU_FCAND(1, D1) TAU_FCAND(2, D2) TAU_FCAND(3, D3)
+#undef TAU_FCAND
+#undef TAU_TERM
+                }
+                // error bound of every D_a (log2 units): reads * (C0 + C1*(max|lg2 q| + max|lg2 P|)) + accumulation
+                float eb = nlane * (TAU_C0 + TAU_C1 * (mq + mlP) + TAU_CANCEL(G) * exp2f(fminf(mq + mlP, 120.f))) +
+                           TAU_ACC(nch) * A;
+                // pack the bound into the slot of the current base (its D is identically 0)
+                if (cur == 0) D0 = eb; else if (cur == 1) D1 = eb; else if (cur == 2) D2 = eb; else D3 = eb;
+                warp_sum4(D0, D1, D2, D3, lane);
+                const float LN2 = 0.69314718f;
+                float Bn = ((cur == 0) ? D0 : (cur == 1) ? D1 : (cur == 2) ? D2 : D3) * LN2 * 1.0001f + 1e-6f;   // nats
+                float d[4] = {D0 * LN2, D1 * LN2, D2 * LN2, D3 * LN2};
+                d[cur] = 0.f;
+                // leader and runner-up
+                int m = 0;
+                if (d[1] > d[m]) m = 1;
+                if (d[2] > d[m]) m = 2;
+                if (d[3] > d[m]) m = 3;
+                float second = -3.0e38f;
+#pragma unroll
+                for (int a = 0; a < 4; a++) if (a != m) second = fmaxf(second, d[a]);
+                const float bm = (m == cur) ? 0.f : Bn;             // cur's own value (0) is exact
+                if (isfinite(Bn) && (d[m] - bm) - (second + Bn) > TAU_GAP) {
+                    t = m; n1++;
+                } else if (isfinite(Bn)) {
+                    // ---- tier 2: FP64 brackets of the three CDF boundaries from D_a +- B
+                    const double B = (double)Bn;
+                    double hi[4], lo[4];
+                    double M = -1.0e300;
+#pragma unroll
+                    for (int a = 0; a < 4; a++) {
+                        const double x = (double)d[a], bb = (a == cur) ? 0.0 : B;
+                        hi[a] = x + bb; lo[a] = x - bb;
+                        M = fmax(M, hi[a]);
+                    }
+                    double eh[4], el[4];
+#pragma unroll
+                    for (int a = 0; a < 4; a++) { eh[a] = exp(hi[a] - M); el[a] = exp(lo[a] - M); }
+                    int below = 0, above = 0;     // number of boundaries certainly > u / certainly <= u
+                    double ah = 0.0, al = 0.0;
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        ah += eh[k]; al += el[k];
+                        double rh = 0.0, rl = 0.0;
+#pragma unroll
+                        for (int a = k + 1; a < 4; a++) { rh += eh[a]; rl += el[a]; }
+                        const double cplus = ah / (ah + rl), cminus = al / (al + rh);
+                        if (u < cminus - TAU_SLACK) below++;
+                        else if (u >= cplus + TAU_SLACK) above++;
+                    }
+                    if (below + above == 3) { t = above; n2++; }    // boundaries are ordered: t = #boundaries <= u
+                }
+            }
+            if (t < 0) {
+                // ---- tier 3: the reference's FP64 arithmetic and order
+                double L[4];
+                tau_exact_logp(tile, gT, eta_s, code, g, S, Sp, G, lane, L);
+                t = tau_exact_pick(L, u);
+                n3++;
+            }
             if (t != cur) {
+                // P += (eta[t][b] - eta[cur][b]) * gamma[s][g]; refresh lg2 P
+                const double *et = eta_s + 4 * t, *ec2 = eta_s + 4 * cur;
+                const double d0 = et[0] - ec2[0], d1 = et[1] - ec2[1], d2 = et[2] - ec2[2], d3 = et[3] - ec2[3];
+                mlP = 1.0f;
+                for (int c = 0; c < nch; c++) {
+                    const int s = c * 32 + lane;
+                    const double gg = gT[g * Sp + s];
+                    const double b0 = fma(d0, gg, Pw[s * 4 + 0]), b1 = fma(d1, gg, Pw[s * 4 + 1]),
+                                 b2 = fma(d2, gg, Pw[s * 4 + 2]), b3 = fma(d3, gg, Pw[s * 4 + 3]);
+                    Pw[s * 4 + 0] = b0; Pw[s * 4 + 1] = b1; Pw[s * 4 + 2] = b2; Pw[s * 4 + 3] = b3;
+                    float4 l;
+                    l.x = __log2f((float)b0); l.y = __log2f((float)b1); l.z = __log2f((float)b2); l.w = __log2f((float)b3);
+                    lPw[s] = l;
+                    if (s < S) mlP = fmaxf(mlP, fmaxf(fmaxf(fabsf(l.x), fabsf(l.y)), fmaxf(fabsf(l.z), fabsf(l.w))));
+                }
                 code = code_set(code, g, t);
                 flips++;
                 if (p.tau_cnt && lane == 0) {
@@ -147,6 +351,11 @@ __global__ void __launch_bounds__(TAU_WARPS * 32) tau_sample_kernel(TauParams p)
     }
 
     if (lane == 0 && flips) atomicAdd(p.nchange, (unsigned long long)flips);
+    if (lane == 0 && p.tier_counts) {
+        if (n1) atomicAdd(p.tier_counts + 0, (unsigned long long)n1);
+        if (n2) atomicAdd(p.tier_counts + 1, (unsigned long long)n2);
+        if (n3) atomicAdd(p.tier_counts + 2, (unsigned long long)n3);
+    }
     if (p.ll_partial) {
         if (lane == 0) ll_warp[wib] = ll_acc;
         __syncthreads();
@@ -160,6 +369,7 @@ __global__ void __launch_bounds__(TAU_WARPS * 32) tau_sample_kernel(TauParams p)
 
 static inline size_t tau_smem_bytes(int S, int G)
 {
-    size_t Sp = (size_t)((S + 31) & ~31);
-    return sizeof(double) * ((size_t)G * Sp + 32) + sizeof(int4) * (size_t)TAU_WARPS * S;
+    const size_t Sp = (size_t)((S + 31) & ~31);
+    return sizeof(double) * ((size_t)G * Sp + 32 + (size_t)TAU_WARPS * Sp * 4) + sizeof(float) * ((size_t)G * Sp + 16) +
+           (sizeof(float4) + sizeof(int4)) * (size_t)TAU_WARPS * Sp;
 }

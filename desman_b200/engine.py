@@ -175,6 +175,14 @@ class Engine:
     def comm_init(self, uid, rank, nranks):
         check(self._L.desman_comm_init(self._h, uid, rank, nranks), "desman_comm_init")
 
+    def set_option(self, name, value):
+        check(self._L.desman_set_option(self._h, name.encode(), int(value)), "desman_set_option")
+
+    def get_tier_counts(self, reset=True):
+        out = np.zeros(3, dtype=np.int64)
+        check(self._L.desman_get_tier_counts(self._h, _lib.ptr_i64(out), int(reset)), "desman_get_tier_counts")
+        return out
+
     def set_profiling(self, per_kernel_events=False, flush_l2=False):
         check(self._L.desman_set_profiling(self._h, int(per_kernel_events), int(flush_l2)), "desman_set_profiling")
 

@@ -105,6 +105,12 @@ int desman_nmft_factorize(desman_ctx *ctx, const int64_t *snps, int64_t V, int S
                           double *tau, double *gamma, int max_iter, double min_change, int fix_gamma,
                           int *n_iter_done, double *div_final, double *div_trace);
 
+/* Engine options.  "tau_exact" = 1 forces the FP64 reference-order arithmetic for every tau draw (validation;
+ * default 0 = filtered-exact FP32 fast path with FP64 fallback, same draws).  desman_get_tier_counts returns how
+ * many draws were decided by the FP32 gap test / the FP64 CDF brackets / the FP64 reference-order recompute. */
+int desman_set_option(desman_ctx *ctx, const char *name, int64_t value);
+int desman_get_tier_counts(desman_ctx *ctx, int64_t out[3], int reset);
+
 /* Multi-GPU: one context per process/GPU, sites sharded by desman_set_counts(v0, V_total).
  * desman_comm_unique_id fills a 128-byte NCCL id on rank 0; every rank calls desman_comm_init. */
 int desman_comm_unique_id(char id[128]);

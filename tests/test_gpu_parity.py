@@ -264,3 +264,73 @@ def test_properties_at_config_C2_size(eng_mod):
         e.close()
     for a, b in zip(outs[0], outs[1]):
         assert np.array_equal(a, b)                                     # bitwise reproducible
+
+
+# ------------------------------------------------------------------ filtered-exact fast path
+@pytest.mark.parametrize("V,S,G,depth", [(400, 64, 8, 100.0), (300, 64, 8, 3.0), (200, 130, 12, 10.0), (150, 7, 3, 8.0),
+                                          (64, 256, 16, 30.0)])
+def test_tau_fast_path_draws_equal_fp64_reference_order_path(eng_mod, oracle_mod, V, S, G, depth):
+    """tau_exact=1 evaluates every draw with the reference's FP64 arithmetic; the default filtered path must
+    produce the identical tau (and both equal the oracle).  Tier counters prove the vectors exercise the FP32
+    gap test AND the FP64 bracket test (ambiguous draws), not only deterministic ones."""
+    p = synth_problem(V, S, G, depth=depth, seed=7 * V + G, ambiguous=True)
+    rng = np.random.default_rng(V)
+    taus = {}
+    tiers = None
+    for mode in (0, 1):
+        e = eng_mod.Engine(0, seed=99)
+        e.set_option("tau_exact", mode)
+        e.set_counts(p["counts"])
+        e.set_state(onehot(p["tau0"]), p["gamma0"], p["eta0"])
+        rng = np.random.default_rng(V)
+        hist = []
+        e.get_tier_counts()
+        for k in range(6):
+            gamma = rng.dirichlet(np.full(G, 0.2 if k % 2 else 1.0), size=S)
+            gamma[gamma < 1e-6] = 1e-6
+            gamma /= gamma.sum(1)[:, None]
+            eta = rng.dirichlet(np.array([200.0, 0.3, 0.3, 0.3]), size=4)       # rough, tiny off-diagonals included
+            eta = np.array([np.roll(eta[a], a) for a in range(4)])
+            eta = np.maximum(eta, 1e-30); eta /= eta.sum(1)[:, None]
+            e.set_state(None, gamma, eta, G=G)
+            e.set_rng(99, sweep=k)
+            e.sample_tau()
+            hist.append(e.get_tau_index())
+        taus[mode] = hist
+        if mode == 0:
+            tiers = e.get_tier_counts()
+        e.close()
+    for a, b in zip(taus[0], taus[1]):
+        assert np.array_equal(a, b)
+    assert tiers.sum() == 6 * V * G
+    assert tiers[0] > 0 and tiers[1] > 0, tiers
+    # and the oracle agrees on the last state
+    tau_o = onehot(p["tau0"])
+    rng = np.random.default_rng(V)
+    for k in range(6):
+        gamma = rng.dirichlet(np.full(G, 0.2 if k % 2 else 1.0), size=S)
+        gamma[gamma < 1e-6] = 1e-6
+        gamma /= gamma.sum(1)[:, None]
+        eta = rng.dirichlet(np.array([200.0, 0.3, 0.3, 0.3]), size=4)
+        eta = np.array([np.roll(eta[a], a) for a in range(4)])
+        eta = np.maximum(eta, 1e-30); eta /= eta.sum(1)[:, None]
+        oracle_mod.sample_tau_philox(tau_o, gamma, eta, p["counts"], 99, k)
+    assert np.array_equal(np.argmax(tau_o, 2).astype(np.uint8), taus[0][-1])
+
+
+def test_tau_fast_path_long_chain_equals_exact_at_C2_size(eng_mod):
+    """V=10000 S=64 G=8: 30 full sweeps from a random start, filtered path vs FP64 path: same tau, same nchange trace."""
+    p = synth_problem(10000, 64, 8, depth=100.0, seed=20240611)
+    res = {}
+    for mode in (0, 1):
+        e = eng_mod.Engine(0, seed=23724839)
+        e.set_option("tau_exact", mode)
+        e.set_counts(p["counts"])
+        e.set_state(onehot(p["tau0"]), p["gamma0"], p["eta0"])
+        out = e.update(30)
+        res[mode] = (e.get_tau_index(), out["nchange"], out["ll_store"], e.get_tier_counts())
+        e.close()
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert np.array_equal(res[0][2], res[1][2])
+    t = res[0][3]
+    assert t[2] < 0.01 * t.sum()            # the FP64 recompute is the rare path
