@@ -469,10 +469,16 @@ extern "C" int desman_get_state(desman_ctx *c, int64_t *tau, double *gamma, doub
 }
 
 // ------------------------------------------------------------------------------------------ launches
+// One resident wave: sites are statically strided over the warps of the grid, so a partial second wave would
+// run at a fraction of the occupancy for as long as a full one.
 static int tau_grid(desman_ctx *c)
 {
+    int occ = 0;
+    const size_t smem = tau_smem_bytes(c->S, c->G);
+    cudaFuncSetAttribute(tau_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tau_sample_kernel, TAU_WARPS * 32, smem) != cudaSuccess || occ < 1) occ = 1;
     int64_t want = (c->V + TAU_WARPS - 1) / TAU_WARPS;
-    int64_t cap = (int64_t)c->sm_count * 4;
+    int64_t cap = (int64_t)c->sm_count * occ;
     return (int)(want < cap ? want : cap);
 }
 

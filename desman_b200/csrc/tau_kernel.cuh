@@ -123,13 +123,21 @@ __device__ __forceinline__ void warp_sum4(float &a, float &b, float &c, float &d
 //   lg2.approx: abs error <= 2^-22 * max(1, |lg2 q|)   (CUDA math API, __log2f)
 //   lP = lg2((float)P64): 1u relative + the same lg2 bound
 #define TAU_C0 (6.0f * 5.9604645e-8f * 1.4426950f + 2.0f * 2.3841858e-7f)   // relative parts + the two max(1,.) floors
-#define TAU_C1 3.0e-7f    // 2^-22 per unit of |lg2| (lg2.approx) + 2^-24 per unit for the rounding of (lq - lP)
-// FP32 accumulation: (4*nch adds per lane + 5 reduction levels + the product rounding) * 2^-24, relative to sum |terms|
-#define TAU_ACC(nch) ((float)(4 * (nch) + 8) * 5.9604645e-8f)
+// per unit of |lg2|: 2^-22 (lg2.approx) and, for the FP32 accumulation of sum n*lg2 q and sum n*lg2 P over
+// 4*nch terms per lane + 5 reduction levels, (4*nch+8)*2^-24  (every partial sum is <= reads * max|lg2|)
+#define TAU_C1(nch) (2.3841858e-7f + (float)(4 * (nch) + 8) * 5.9604645e-8f)
 // FP64 mixture P carries <= (2G+2)*2^-53*P absolute error; relative to a candidate q that is amplified by P/q = 2^(lP-lq)
 #define TAU_CANCEL(G) ((float)(2 * (G) + 2) * 1.1102230e-16f * 1.4426950f)
+#define TAU_QMIN 1.0e-37f   // candidates below this are clamped (finite logs) and force the FP64 path via the bound
 
-__global__ void __launch_bounds__(TAU_WARPS * 32) tau_sample_kernel(TauParams p)
+__device__ __forceinline__ float lg2_fast(float x)
+{
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // bare MUFU.LG2: no denormal rescaling code around it
+    return y;
+}
+
+__global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = p.S, G = p.G;
@@ -137,11 +145,12 @@ __global__ void __launch_bounds__(TAU_WARPS * 32) tau_sample_kernel(TauParams p)
     double *gT = reinterpret_cast<double *>(smem_raw);           // [G][Sp] gamma transposed (FP64)
     double *eta_s = gT + (size_t)G * Sp;                         // [16]
     double *etall_s = eta_s + 16;                                // [16]
-    double *P64 = etall_s + 16;                                  // [TAU_WARPS][Sp][4] mixture probabilities
-    float *gT32 = reinterpret_cast<float *>(P64 + (size_t)TAU_WARPS * Sp * 4);   // [G][Sp]
-    float *eta32 = gT32 + (size_t)G * Sp;                        // [16]
-    float4 *lP = reinterpret_cast<float4 *>(eta32 + 16);         // [TAU_WARPS][Sp] lg2 of P
-    int4 *tiles = reinterpret_cast<int4 *>(lP + (size_t)TAU_WARPS * Sp);         // [TAU_WARPS][Sp]
+    double2 *P64 = reinterpret_cast<double2 *>(etall_s + 16);    // [TAU_WARPS][Sp][2] mixture probabilities (b0,b1),(b2,b3)
+    float *gT32 = reinterpret_cast<float *>(P64 + (size_t)TAU_WARPS * Sp * 2);   // [G][Sp]
+    float4 *eta32 = reinterpret_cast<float4 *>(gT32 + (size_t)G * Sp);           // [4] rows
+    float *K = reinterpret_cast<float *>(eta32 + 4);             // [TAU_WARPS][Sp] sum_b n_b*lg2 P_b
+    int4 *tiles = reinterpret_cast<int4 *>(K + (size_t)TAU_WARPS * Sp);          // [TAU_WARPS][Sp]
+    uint32_t *wbuf = reinterpret_cast<uint32_t *>(tiles + (size_t)TAU_WARPS * Sp);   // [TAU_WARPS][32] uniform words
     __shared__ double ll_warp[TAU_WARPS];
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -153,17 +162,19 @@ __global__ void __launch_bounds__(TAU_WARPS * 32) tau_sample_kernel(TauParams p)
     }
     if (threadIdx.x < 16) {
         eta_s[threadIdx.x] = p.eta[threadIdx.x];
-        eta32[threadIdx.x] = (float)p.eta[threadIdx.x];
+        reinterpret_cast<float *>(eta32)[threadIdx.x] = (float)p.eta[threadIdx.x];
         etall_s[threadIdx.x] = p.eta_ll ? p.eta_ll[threadIdx.x] : 0.0;
     }
     __syncthreads();
 
     int4 *tile = tiles + (size_t)wib * Sp;
-    double *Pw = P64 + (size_t)wib * Sp * 4;
-    float4 *lPw = lP + (size_t)wib * Sp;
+    double2 *Pw = P64 + (size_t)wib * Sp * 2;
+    float *Kw = K + (size_t)wib * Sp;
+    uint32_t *ww = wbuf + wib * 32;
     const int nch = Sp >> 5;
     const int gw = blockIdx.x * TAU_WARPS + wib, nw = gridDim.x * TAU_WARPS;
     const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+    const float c1 = TAU_C1(nch), ccan = TAU_CANCEL(G);
     unsigned int flips = 0, n1 = 0, n2 = 0, n3 = 0;
     double ll_acc = 0.0;
 
@@ -171,8 +182,18 @@ __global__ void __launch_bounds__(TAU_WARPS * 32) tau_sample_kernel(TauParams p)
         const int4 *src = p.counts + (size_t)v * S;
         uint64_t code = load_tau_code(p.tau + (size_t)v * G, G, lane);
         const uint64_t code_in = code;
-        // stage counts; mixture P (FP64, ascending h) and its lg2; per-lane read count for the error bound
+        // the G uniform words of this site: lane g draws word g (one Philox call per site instead of G per lane)
+        if (p.do_draw) {
+            uint32_t w = 0;
+            if (lane < G) {
+                if (p.words) w = p.words[(size_t)v * G + lane];
+                else w = philox4x32_10((uint32_t)(p.v0 + v), (uint32_t)lane, p.sweep, (uint32_t)STAGE_TAU << 28, k0, k1).x;
+            }
+            ww[lane] = w;
+        }
+        // stage counts; mixture P (FP64, ascending h); K = sum_b n_b lg2 P_b; per-lane read count and max |lg2 P|
         float nlane = 0.0f, mlP = 1.0f;
+        uint32_t anymask = 0;      // bit 4c+b: some lane of chunk c has a non-zero count of base b (c < 8)
         for (int c = 0; c < nch; c++) {
             const int s = c * 32 + lane;
             int4 n = make_int4(0, 0, 0, 0);
@@ -180,104 +201,104 @@ __global__ void __launch_bounds__(TAU_WARPS * 32) tau_sample_kernel(TauParams p)
             tile[s] = n;
             double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
             for (int h = 0; h < G; h++) {
-                const double *e = eta_s + 4 * code_get(code, h);
+                const double2 *e = reinterpret_cast<const double2 *>(eta_s + 4 * code_get(code, h));
+                const double2 e01 = e[0], e23 = e[1];
                 const double gm = gT[h * Sp + s];
-                b0 = fma(e[0], gm, b0); b1 = fma(e[1], gm, b1);
-                b2 = fma(e[2], gm, b2); b3 = fma(e[3], gm, b3);
+                b0 = fma(e01.x, gm, b0); b1 = fma(e01.y, gm, b1);
+                b2 = fma(e23.x, gm, b2); b3 = fma(e23.y, gm, b3);
             }
             if (s >= S) { b0 = 1.0; b1 = 1.0; b2 = 1.0; b3 = 1.0; }   // padding lanes: finite logs, zero counts
-            Pw[s * 4 + 0] = b0; Pw[s * 4 + 1] = b1; Pw[s * 4 + 2] = b2; Pw[s * 4 + 3] = b3;
-            float4 l;
-            l.x = __log2f((float)b0); l.y = __log2f((float)b1); l.z = __log2f((float)b2); l.w = __log2f((float)b3);
-            lPw[s] = l;
-            if (s < S) {
-                nlane += (float)(n.x + n.y + n.z + n.w);
-                mlP = fmaxf(mlP, fmaxf(fmaxf(fabsf(l.x), fabsf(l.y)), fmaxf(fabsf(l.z), fabsf(l.w))));
+            Pw[s * 2] = make_double2(b0, b1); Pw[s * 2 + 1] = make_double2(b2, b3);
+            const float l0 = lg2_fast((float)b0), l1 = lg2_fast((float)b1), l2 = lg2_fast((float)b2), l3 = lg2_fast((float)b3);
+            Kw[s] = fmaf((float)n.x, l0, fmaf((float)n.y, l1, fmaf((float)n.z, l2, (float)n.w * l3)));
+            nlane += (float)(n.x + n.y + n.z + n.w);
+            mlP = fmaxf(mlP, fmaxf(fmaxf(fabsf(l0), fabsf(l1)), fmaxf(fabsf(l2), fabsf(l3))));
+            if (c < 8) {
+                const uint32_t m4 = (__any_sync(DESMAN_FULL_MASK, n.x != 0) ? 1u : 0u) | (__any_sync(DESMAN_FULL_MASK, n.y != 0) ? 2u : 0u) |
+                                    (__any_sync(DESMAN_FULL_MASK, n.z != 0) ? 4u : 0u) | (__any_sync(DESMAN_FULL_MASK, n.w != 0) ? 8u : 0u);
+                anymask |= m4 << (4 * c);
             }
         }
         __syncwarp();
 
         for (int g = 0; g < (p.do_draw ? G : 0); g++) {
             const int cur = code_get(code, g);
-            uint32_t w;
-            if (p.words) w = p.words[(size_t)v * G + g];
-            else w = philox4x32_10((uint32_t)(p.v0 + v), (uint32_t)g, p.sweep, (uint32_t)STAGE_TAU << 28, k0, k1).x;
+            const uint32_t w = ww[g];
             const double u = (double)w / 4294967296.0;              // gsl_rng_uniform, c_sample_tau.c:174
             int t = -1;
             if (!p.exact_only && w != 0u) {
-                // ---- tier 1: FP32 differences D_a = log2-likelihood(a) - log2-likelihood(cur), a != cur
-                float D0 = 0.f, D1 = 0.f, D2 = 0.f, D3 = 0.f;       // log2 units
-                float A = 0.f;                                      // sum |terms| (accumulation error)
+                // ---- tier 1: FP32  E_j = sum n*lg2 q_{a_j},  a_j = (cur+1+j)&3,  D_j = E_j - sum n*lg2 P   (log2 units)
+                float E0 = 0.f, E1 = 0.f, E2 = 0.f, KK = 0.f;
                 float mq = 1.0f;                                    // max |lg2 q| over this lane's terms
-                const double *ec = eta_s + 4 * cur;
+                const double2 *ecp = reinterpret_cast<const double2 *>(eta_s + 4 * cur);
+                const double2 ec01 = ecp[0], ec23 = ecp[1];
+                const float4 ea = eta32[(cur + 1) & 3], eb4 = eta32[(cur + 2) & 3], ecc = eta32[(cur + 3) & 3];
+                const double *gTg = gT + g * Sp;
+                const float *gT32g = gT32 + g * Sp;
                 for (int c = 0; c < nch; c++) {
                     const int s = c * 32 + lane;
                     const int4 n = tile[s];
-                    const bool any0 = __any_sync(DESMAN_FULL_MASK, n.x != 0), any1 = __any_sync(DESMAN_FULL_MASK, n.y != 0),
-                               any2 = __any_sync(DESMAN_FULL_MASK, n.z != 0), any3 = __any_sync(DESMAN_FULL_MASK, n.w != 0);
-                    const double gg = gT[g * Sp + s];
-                    const float gf = gT32[g * Sp + s];
-                    const float4 l = lPw[s];
+                    const uint32_t am = (c < 8) ? (anymask >> (4 * c)) & 15u : 15u;
+                    const double gg = gTg[s];
+                    const float gf = gT32g[s];
+                    const double2 P01 = Pw[s * 2], P23 = Pw[s * 2 + 1];
+                    KK += Kw[s];
                     // base = P - eta[cur][b]*gamma (FP64: no cancellation error), then one rounding to FP32
-                    const float q0 = fmaxf((float)fma(-ec[0], gg, Pw[s * 4 + 0]), 0.f), q1 = fmaxf((float)fma(-ec[1], gg, Pw[s * 4 + 1]), 0.f),
-                                q2 = fmaxf((float)fma(-ec[2], gg, Pw[s * 4 + 2]), 0.f), q3 = fmaxf((float)fma(-ec[3], gg, Pw[s * 4 + 3]), 0.f);
+                    const float q0 = fmaxf((float)fma(-ec01.x, gg, P01.x), 0.f), q1 = fmaxf((float)fma(-ec01.y, gg, P01.y), 0.f),
+                                q2 = fmaxf((float)fma(-ec23.x, gg, P23.x), 0.f), q3 = fmaxf((float)fma(-ec23.y, gg, P23.y), 0.f);
                     const float f0 = (float)n.x, f1 = (float)n.y, f2 = (float)n.z, f3 = (float)n.w;
-#define TAU_TERM(anyb, fb, qb, lb, ea, D)                                  \
-    if (anyb) {                                                            \
-        float lq = __log2f(fmaf(ea, gf, qb));                              \
-        lq = (fb != 0.f) ? lq : lb;      /* n == 0: term is exactly 0 */   \
-        const float tm = fb * (lq - lb);                                   \
-        D += tm;                                                           \
-        A += fabsf(tm);                                                    \
-        mq = fmaxf(mq, fabsf(lq));                                         \
+#define TAU_TERM(fb, qb, eab, E)                                               \
+    {                                                                          \
+        const float lq = lg2_fast(fmaxf(fmaf(eab, gf, qb), TAU_QMIN));         \
+        E = fmaf(fb, lq, E);                                                   \
+        mq = fmaxf(mq, fabsf(lq));                                             \
     }
-#define TAU_FCAND(a, D)                                                    \
-    if (cur != (a)) {                                                      \
-        const float *e = eta32 + 4 * (a);                                  \
-        TAU_TERM(any0, f0, q0, l.x, e[0], D)                               \
-        TAU_TERM(any1, f1, q1, l.y, e[1], D)                               \
-        TAU_TERM(any2, f2, q2, l.z, e[2], D)                               \
-        TAU_TERM(any3, f3, q3, l.w, e[3], D)                               \
-    }
-                    TAU_FCAND(0, D0) TAU_FCAND(1, D1) TAU_FCAND(2, D2) TAU_FCAND(3, D3)
-#undef TAU_FCAND
+                    if (am & 1u) { TAU_TERM(f0, q0, ea.x, E0) TAU_TERM(f0, q0, eb4.x, E1) TAU_TERM(f0, q0, ecc.x, E2) }
+                    if (am & 2u) { TAU_TERM(f1, q1, ea.y, E0) TAU_TERM(f1, q1, eb4.y, E1) TAU_TERM(f1, q1, ecc.y, E2) }
+                    if (am & 4u) { TAU_TERM(f2, q2, ea.z, E0) TAU_TERM(f2, q2, eb4.z, E1) TAU_TERM(f2, q2, ecc.z, E2) }
+                    if (am & 8u) { TAU_TERM(f3, q3, ea.w, E0) TAU_TERM(f3, q3, eb4.w, E1) TAU_TERM(f3, q3, ecc.w, E2) }
 #undef TAU_TERM
                 }
-                // error bound of every D_a (log2 units): reads * (C0 + C1*(max|lg2 q| + max|lg2 P|)) + accumulation
-                float eb = nlane * (TAU_C0 + TAU_C1 * (mq + mlP) + TAU_CANCEL(G) * exp2f(fminf(mq + mlP, 120.f))) +
-                           TAU_ACC(nch) * A;
-                // pack the bound into the slot of the current base (its D is identically 0)
-                if (cur == 0) D0 = eb; else if (cur == 1) D1 = eb; else if (cur == 2) D2 = eb; else D3 = eb;
-                warp_sum4(D0, D1, D2, D3, lane);
+                // error bound of every D_j (log2 units).  mq >= 122 means a clamped (q < 1e-37) candidate: not bounded -> inf
+                float eb = nlane * (TAU_C0 + c1 * (mq + mlP) + ccan * exp2f(fminf(mq + mlP, 120.f)));
+                if (mq >= 122.f) eb = __int_as_float(0x7f800000);
+                float D0 = E0 - KK, D1 = E1 - KK, D2 = E2 - KK;
+                warp_sum4(D0, D1, D2, eb, lane);
                 const float LN2 = 0.69314718f;
-                float Bn = ((cur == 0) ? D0 : (cur == 1) ? D1 : (cur == 2) ? D2 : D3) * LN2 * 1.0001f + 1e-6f;   // nats
-                float d[4] = {D0 * LN2, D1 * LN2, D2 * LN2, D3 * LN2};
-                d[cur] = 0.f;
+                const float Bn = eb * LN2 * 1.0001f + 1e-6f;        // nats
+                float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;       // nats, indexed by base; d[cur] = 0 exactly
+                {
+                    const float x0 = D0 * LN2, x1 = D1 * LN2, x2 = D2 * LN2;
+                    // a_j = (cur+1+j)&3  <=>  j = (a-cur-1)&3
+                    const int j0 = (0 - cur - 1) & 3, j1 = (1 - cur - 1) & 3, j2 = (2 - cur - 1) & 3, j3 = (3 - cur - 1) & 3;
+                    d0 = (j0 == 0) ? x0 : (j0 == 1) ? x1 : (j0 == 2) ? x2 : 0.f;
+                    d1 = (j1 == 0) ? x0 : (j1 == 1) ? x1 : (j1 == 2) ? x2 : 0.f;
+                    d2 = (j2 == 0) ? x0 : (j2 == 1) ? x1 : (j2 == 2) ? x2 : 0.f;
+                    d3 = (j3 == 0) ? x0 : (j3 == 1) ? x1 : (j3 == 2) ? x2 : 0.f;
+                }
                 // leader and runner-up
-                int m = 0;
-                if (d[1] > d[m]) m = 1;
-                if (d[2] > d[m]) m = 2;
-                if (d[3] > d[m]) m = 3;
-                float second = -3.0e38f;
-#pragma unroll
-                for (int a = 0; a < 4; a++) if (a != m) second = fmaxf(second, d[a]);
+                int m = 0; float dm = d0;
+                if (d1 > dm) { m = 1; dm = d1; }
+                if (d2 > dm) { m = 2; dm = d2; }
+                if (d3 > dm) { m = 3; dm = d3; }
+                const float second = fmaxf(fmaxf(m == 0 ? -3.0e38f : d0, m == 1 ? -3.0e38f : d1),
+                                           fmaxf(m == 2 ? -3.0e38f : d2, m == 3 ? -3.0e38f : d3));
                 const float bm = (m == cur) ? 0.f : Bn;             // cur's own value (0) is exact
-                if (isfinite(Bn) && (d[m] - bm) - (second + Bn) > TAU_GAP) {
+                if (Bn < 1.0e30f && (dm - bm) - (second + Bn) > TAU_GAP) {
                     t = m; n1++;
-                } else if (isfinite(Bn)) {
+                } else if (Bn < 1.0e30f) {
                     // ---- tier 2: FP64 brackets of the three CDF boundaries from D_a +- B
                     const double B = (double)Bn;
-                    double hi[4], lo[4];
+                    const double dd[4] = {(double)d0, (double)d1, (double)d2, (double)d3};
+                    double eh[4], el[4];
                     double M = -1.0e300;
 #pragma unroll
-                    for (int a = 0; a < 4; a++) {
-                        const double x = (double)d[a], bb = (a == cur) ? 0.0 : B;
-                        hi[a] = x + bb; lo[a] = x - bb;
-                        M = fmax(M, hi[a]);
-                    }
-                    double eh[4], el[4];
+                    for (int a = 0; a < 4; a++) M = fmax(M, dd[a] + ((a == cur) ? 0.0 : B));
 #pragma unroll
-                    for (int a = 0; a < 4; a++) { eh[a] = exp(hi[a] - M); el[a] = exp(lo[a] - M); }
+                    for (int a = 0; a < 4; a++) {
+                        const double bb = (a == cur) ? 0.0 : B;
+                        eh[a] = exp(dd[a] + bb - M); el[a] = exp(dd[a] - bb - M);
+                    }
                     int below = 0, above = 0;     // number of boundaries certainly > u / certainly <= u
                     double ah = 0.0, al = 0.0;
 #pragma unroll
@@ -301,20 +322,20 @@ __global__ void __launch_bounds__(TAU_WARPS * 32) tau_sample_kernel(TauParams p)
                 n3++;
             }
             if (t != cur) {
-                // P += (eta[t][b] - eta[cur][b]) * gamma[s][g]; refresh lg2 P
+                // P += (eta[t][b] - eta[cur][b]) * gamma[s][g]; refresh K = sum_b n_b lg2 P_b
                 const double *et = eta_s + 4 * t, *ec2 = eta_s + 4 * cur;
-                const double d0 = et[0] - ec2[0], d1 = et[1] - ec2[1], d2 = et[2] - ec2[2], d3 = et[3] - ec2[3];
+                const double e0 = et[0] - ec2[0], e1 = et[1] - ec2[1], e2 = et[2] - ec2[2], e3 = et[3] - ec2[3];
                 mlP = 1.0f;
                 for (int c = 0; c < nch; c++) {
                     const int s = c * 32 + lane;
                     const double gg = gT[g * Sp + s];
-                    const double b0 = fma(d0, gg, Pw[s * 4 + 0]), b1 = fma(d1, gg, Pw[s * 4 + 1]),
-                                 b2 = fma(d2, gg, Pw[s * 4 + 2]), b3 = fma(d3, gg, Pw[s * 4 + 3]);
-                    Pw[s * 4 + 0] = b0; Pw[s * 4 + 1] = b1; Pw[s * 4 + 2] = b2; Pw[s * 4 + 3] = b3;
-                    float4 l;
-                    l.x = __log2f((float)b0); l.y = __log2f((float)b1); l.z = __log2f((float)b2); l.w = __log2f((float)b3);
-                    lPw[s] = l;
-                    if (s < S) mlP = fmaxf(mlP, fmaxf(fmaxf(fabsf(l.x), fabsf(l.y)), fmaxf(fabsf(l.z), fabsf(l.w))));
+                    const double2 P01 = Pw[s * 2], P23 = Pw[s * 2 + 1];
+                    const double b0 = fma(e0, gg, P01.x), b1 = fma(e1, gg, P01.y), b2 = fma(e2, gg, P23.x), b3 = fma(e3, gg, P23.y);
+                    Pw[s * 2] = make_double2(b0, b1); Pw[s * 2 + 1] = make_double2(b2, b3);
+                    const int4 n = tile[s];
+                    const float l0 = lg2_fast((float)b0), l1 = lg2_fast((float)b1), l2 = lg2_fast((float)b2), l3 = lg2_fast((float)b3);
+                    Kw[s] = fmaf((float)n.x, l0, fmaf((float)n.y, l1, fmaf((float)n.z, l2, (float)n.w * l3)));
+                    mlP = fmaxf(mlP, fmaxf(fmaxf(fabsf(l0), fabsf(l1)), fmaxf(fabsf(l2), fabsf(l3))));
                 }
                 code = code_set(code, g, t);
                 flips++;
@@ -335,10 +356,11 @@ __global__ void __launch_bounds__(TAU_WARPS * 32) tau_sample_kernel(TauParams p)
                 if ((n.x | n.y | n.z | n.w) == 0) continue;
                 double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
                 for (int h = 0; h < G; h++) {
-                    const double *e = etall_s + 4 * code_get(code, h);
+                    const double2 *e = reinterpret_cast<const double2 *>(etall_s + 4 * code_get(code, h));
+                    const double2 e01 = e[0], e23 = e[1];
                     const double gm = gT[h * Sp + s];
-                    b0 = fma(e[0], gm, b0); b1 = fma(e[1], gm, b1);
-                    b2 = fma(e[2], gm, b2); b3 = fma(e[3], gm, b3);
+                    b0 = fma(e01.x, gm, b0); b1 = fma(e01.y, gm, b1);
+                    b2 = fma(e23.x, gm, b2); b3 = fma(e23.y, gm, b3);
                 }
                 if (n.x) acc = fma((double)n.x, log(b0), acc);
                 if (n.y) acc = fma((double)n.y, log(b1), acc);
@@ -371,5 +393,5 @@ static inline size_t tau_smem_bytes(int S, int G)
 {
     const size_t Sp = (size_t)((S + 31) & ~31);
     return sizeof(double) * ((size_t)G * Sp + 32 + (size_t)TAU_WARPS * Sp * 4) + sizeof(float) * ((size_t)G * Sp + 16) +
-           (sizeof(float4) + sizeof(int4)) * (size_t)TAU_WARPS * Sp;
+           (sizeof(float) + sizeof(int4)) * (size_t)TAU_WARPS * Sp + sizeof(uint32_t) * TAU_WARPS * 32;
 }

@@ -25,12 +25,14 @@ def main():
     e.set_tau_index(p["tau0"])
     t2 = time.time()
     e.update(3)
+    e.get_tier_counts()
     e.set_profiling(True, False)
     out = e.update(n_iter)
+    tiers = e.get_tier_counts().tolist()
     tm = e.get_timing()
     res = dict(V=V, S=S, G=G, n_iter=n_iter, gen_s=t1 - t0, upload_s=t2 - t1, ms_per_sweep=tm["elapsed_ms"] / n_iter,
                kernel_ms_per_sweep={k: v / n_iter for k, v in tm["kernel_ms"].items()},
-               launches=tm["kernel_launches"], nchange=out["nchange"].tolist()[:10], lp=out["lp_store"][[0, -1]].tolist())
+               launches=tm["kernel_launches"], tiers=tiers, nchange=out["nchange"].tolist()[:10], lp=out["lp_store"][[0, -1]].tolist())
     print(json.dumps(res))
 
 
