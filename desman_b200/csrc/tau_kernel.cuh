@@ -128,13 +128,56 @@ __device__ __forceinline__ void warp_sum4(float &a, float &b, float &c, float &d
 #define TAU_C1(nch) (2.3841858e-7f + (float)(4 * (nch) + 8) * 5.9604645e-8f)
 // FP64 mixture P carries <= (2G+2)*2^-53*P absolute error; relative to a candidate q that is amplified by P/q = 2^(lP-lq)
 #define TAU_CANCEL(G) ((float)(2 * (G) + 2) * 1.1102230e-16f * 1.4426950f)
-#define TAU_QMIN 1.0e-37f   // candidates below this are clamped (finite logs) and force the FP64 path via the bound
+// The FP32 path needs every candidate q = base + eta*gamma to be a NORMAL float with a finite log even where the
+// count is 0 (0*lg2 q must be 0).  q >= min(eta)*min(gamma) =: qmin, evaluated per launch; if qmin < TAU_QMIN every
+// draw of the launch takes the FP64 path.  qmin also gives the a-priori bounds |lg2 q| <= -lg2(qmin)+1 and
+// P/q <= 1/qmin used by the cheap first-tier error bound.
+#define TAU_QMIN 1.0e-36f
 
 __device__ __forceinline__ float lg2_fast(float x)
 {
     float y;
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));   // bare MUFU.LG2: no denormal rescaling code around it
     return y;
+}
+
+// FP32 evaluation of one (v,g) step for the three candidates a_j = (cur+1+j)&3:
+//   E_j = sum_s sum_b n_sb * lg2(base_sb + eta[a_j][b]*gamma[s][g]),   KK = sum_s sum_b n_sb * lg2 P_sb   (log2 units)
+// TRACK additionally returns max |lg2 q| over the lane's terms (tight error bound for the bracket test).
+template <bool TRACK>
+__device__ __forceinline__ void tau_fp32_terms(const int4 *tile, const double2 *Pw, const float *Kw, const double *gTg,
+                                               const float *gT32g, const double *eta_cur, const float4 *eta32, int cur,
+                                               int nch, uint32_t anymask, int lane, float &E0, float &E1, float &E2,
+                                               float &KK, float &mq)
+{
+    const double2 *ecp = reinterpret_cast<const double2 *>(eta_cur);
+    const double2 ec01 = ecp[0], ec23 = ecp[1];
+    const float4 ea = eta32[(cur + 1) & 3], eb4 = eta32[(cur + 2) & 3], ecc = eta32[(cur + 3) & 3];
+    E0 = 0.f; E1 = 0.f; E2 = 0.f; KK = 0.f; mq = 1.0f;
+    for (int c = 0; c < nch; c++) {
+        const int s = c * 32 + lane;
+        const int4 n = tile[s];
+        const uint32_t am = (c < 8) ? (anymask >> (4 * c)) & 15u : 15u;
+        const double gg = gTg[s];
+        const float gf = gT32g[s];
+        const double2 P01 = Pw[s * 2], P23 = Pw[s * 2 + 1];
+        KK += Kw[s];
+        // base = P - eta[cur][b]*gamma (FP64: no cancellation error), then one rounding to FP32
+        const float q0 = fmaxf((float)fma(-ec01.x, gg, P01.x), 0.f), q1 = fmaxf((float)fma(-ec01.y, gg, P01.y), 0.f),
+                    q2 = fmaxf((float)fma(-ec23.x, gg, P23.x), 0.f), q3 = fmaxf((float)fma(-ec23.y, gg, P23.y), 0.f);
+        const float f0 = (float)n.x, f1 = (float)n.y, f2 = (float)n.z, f3 = (float)n.w;
+#define TAU_TERM(fb, qb, eab, E)                                               \
+    {                                                                          \
+        const float lq = lg2_fast(fmaf(eab, gf, qb));                          \
+        E = fmaf(fb, lq, E);                                                   \
+        if (TRACK) mq = fmaxf(mq, fabsf(lq));                                  \
+    }
+        if (am & 1u) { TAU_TERM(f0, q0, ea.x, E0) TAU_TERM(f0, q0, eb4.x, E1) TAU_TERM(f0, q0, ecc.x, E2) }
+        if (am & 2u) { TAU_TERM(f1, q1, ea.y, E0) TAU_TERM(f1, q1, eb4.y, E1) TAU_TERM(f1, q1, ecc.y, E2) }
+        if (am & 4u) { TAU_TERM(f2, q2, ea.z, E0) TAU_TERM(f2, q2, eb4.z, E1) TAU_TERM(f2, q2, ecc.z, E2) }
+        if (am & 8u) { TAU_TERM(f3, q3, ea.w, E0) TAU_TERM(f3, q3, eb4.w, E1) TAU_TERM(f3, q3, ecc.w, E2) }
+#undef TAU_TERM
+    }
 }
 
 __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams p)
@@ -152,20 +195,30 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
     int4 *tiles = reinterpret_cast<int4 *>(K + (size_t)TAU_WARPS * Sp);          // [TAU_WARPS][Sp]
     uint32_t *wbuf = reinterpret_cast<uint32_t *>(tiles + (size_t)TAU_WARPS * Sp);   // [TAU_WARPS][32] uniform words
     __shared__ double ll_warp[TAU_WARPS];
+    __shared__ unsigned int gmin_bits, emin_bits;   // min gamma / min eta as float bit patterns (positive floats order like uints)
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { gmin_bits = 0x7f800000u; emin_bits = 0x7f800000u; }
+    __syncthreads();
+    float gmin_l = __int_as_float(0x7f800000);
     for (int i = threadIdx.x; i < G * Sp; i += blockDim.x) {
         const int g = i / Sp, s = i - g * Sp;
         const double x = (s < S) ? p.gamma[(size_t)s * G + g] : 0.0;
         gT[i] = x;
         gT32[i] = (float)x;
+        if (s < S) gmin_l = fminf(gmin_l, fmaxf((float)x, 0.f));
     }
+    atomicMin(&gmin_bits, __float_as_uint(gmin_l));
     if (threadIdx.x < 16) {
         eta_s[threadIdx.x] = p.eta[threadIdx.x];
         reinterpret_cast<float *>(eta32)[threadIdx.x] = (float)p.eta[threadIdx.x];
         etall_s[threadIdx.x] = p.eta_ll ? p.eta_ll[threadIdx.x] : 0.0;
+        atomicMin(&emin_bits, __float_as_uint(fmaxf((float)p.eta[threadIdx.x], 0.f)));
     }
     __syncthreads();
+    const float qmin = 0.99f * __uint_as_float(gmin_bits) * __uint_as_float(emin_bits);
+    const bool fast_ok = !p.exact_only && qmin >= TAU_QMIN;
+    const float mq0 = fmaxf(1.0f, 1.0f - log2f(fmaxf(qmin, TAU_QMIN)));      // a-priori max |lg2 q| (q <= 2)
 
     int4 *tile = tiles + (size_t)wib * Sp;
     double2 *Pw = P64 + (size_t)wib * Sp * 2;
@@ -175,6 +228,7 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
     const int gw = blockIdx.x * TAU_WARPS + wib, nw = gridDim.x * TAU_WARPS;
     const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
     const float c1 = TAU_C1(nch), ccan = TAU_CANCEL(G);
+    const float cancel0 = ccan / fmaxf(qmin, TAU_QMIN);                     // a-priori bound of the P/q amplification
     unsigned int flips = 0, n1 = 0, n2 = 0, n3 = 0;
     double ll_acc = 0.0;
 
@@ -226,70 +280,46 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
             const uint32_t w = ww[g];
             const double u = (double)w / 4294967296.0;              // gsl_rng_uniform, c_sample_tau.c:174
             int t = -1;
-            if (!p.exact_only && w != 0u) {
-                // ---- tier 1: FP32  E_j = sum n*lg2 q_{a_j},  a_j = (cur+1+j)&3,  D_j = E_j - sum n*lg2 P   (log2 units)
-                float E0 = 0.f, E1 = 0.f, E2 = 0.f, KK = 0.f;
-                float mq = 1.0f;                                    // max |lg2 q| over this lane's terms
-                const double2 *ecp = reinterpret_cast<const double2 *>(eta_s + 4 * cur);
-                const double2 ec01 = ecp[0], ec23 = ecp[1];
-                const float4 ea = eta32[(cur + 1) & 3], eb4 = eta32[(cur + 2) & 3], ecc = eta32[(cur + 3) & 3];
-                const double *gTg = gT + g * Sp;
-                const float *gT32g = gT32 + g * Sp;
-                for (int c = 0; c < nch; c++) {
-                    const int s = c * 32 + lane;
-                    const int4 n = tile[s];
-                    const uint32_t am = (c < 8) ? (anymask >> (4 * c)) & 15u : 15u;
-                    const double gg = gTg[s];
-                    const float gf = gT32g[s];
-                    const double2 P01 = Pw[s * 2], P23 = Pw[s * 2 + 1];
-                    KK += Kw[s];
-                    // base = P - eta[cur][b]*gamma (FP64: no cancellation error), then one rounding to FP32
-                    const float q0 = fmaxf((float)fma(-ec01.x, gg, P01.x), 0.f), q1 = fmaxf((float)fma(-ec01.y, gg, P01.y), 0.f),
-                                q2 = fmaxf((float)fma(-ec23.x, gg, P23.x), 0.f), q3 = fmaxf((float)fma(-ec23.y, gg, P23.y), 0.f);
-                    const float f0 = (float)n.x, f1 = (float)n.y, f2 = (float)n.z, f3 = (float)n.w;
-#define TAU_TERM(fb, qb, eab, E)                                               \
-    {                                                                          \
-        const float lq = lg2_fast(fmaxf(fmaf(eab, gf, qb), TAU_QMIN));         \
-        E = fmaf(fb, lq, E);                                                   \
-        mq = fmaxf(mq, fabsf(lq));                                             \
-    }
-                    if (am & 1u) { TAU_TERM(f0, q0, ea.x, E0) TAU_TERM(f0, q0, eb4.x, E1) TAU_TERM(f0, q0, ecc.x, E2) }
-                    if (am & 2u) { TAU_TERM(f1, q1, ea.y, E0) TAU_TERM(f1, q1, eb4.y, E1) TAU_TERM(f1, q1, ecc.y, E2) }
-                    if (am & 4u) { TAU_TERM(f2, q2, ea.z, E0) TAU_TERM(f2, q2, eb4.z, E1) TAU_TERM(f2, q2, ecc.z, E2) }
-                    if (am & 8u) { TAU_TERM(f3, q3, ea.w, E0) TAU_TERM(f3, q3, eb4.w, E1) TAU_TERM(f3, q3, ecc.w, E2) }
-#undef TAU_TERM
-                }
-                // error bound of every D_j (log2 units).  mq >= 122 means a clamped (q < 1e-37) candidate: not bounded -> inf
-                float eb = nlane * (TAU_C0 + c1 * (mq + mlP) + ccan * exp2f(fminf(mq + mlP, 120.f)));
-                if (mq >= 122.f) eb = __int_as_float(0x7f800000);
-                float D0 = E0 - KK, D1 = E1 - KK, D2 = E2 - KK;
-                warp_sum4(D0, D1, D2, eb, lane);
+            if (fast_ok && w != 0u) {
+                // ---- tier 1: D_j = (E_j - KK)*ln2 = L(a_j) - L(cur), j = 0..2, with the a-priori bounds from qmin
+                const double *eta_cur = eta_s + 4 * cur;
+                float E0, E1, E2, KK, mq;
+                tau_fp32_terms<false>(tile, Pw, Kw, gT + g * Sp, gT32 + g * Sp, eta_cur, eta32, cur, nch, anymask, lane, E0, E1,
+                                      E2, KK, mq);
                 const float LN2 = 0.69314718f;
-                const float Bn = eb * LN2 * 1.0001f + 1e-6f;        // nats
-                float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;       // nats, indexed by base; d[cur] = 0 exactly
-                {
-                    const float x0 = D0 * LN2, x1 = D1 * LN2, x2 = D2 * LN2;
-                    // a_j = (cur+1+j)&3  <=>  j = (a-cur-1)&3
-                    const int j0 = (0 - cur - 1) & 3, j1 = (1 - cur - 1) & 3, j2 = (2 - cur - 1) & 3, j3 = (3 - cur - 1) & 3;
-                    d0 = (j0 == 0) ? x0 : (j0 == 1) ? x1 : (j0 == 2) ? x2 : 0.f;
-                    d1 = (j1 == 0) ? x0 : (j1 == 1) ? x1 : (j1 == 2) ? x2 : 0.f;
-                    d2 = (j2 == 0) ? x0 : (j2 == 1) ? x1 : (j2 == 2) ? x2 : 0.f;
-                    d3 = (j3 == 0) ? x0 : (j3 == 1) ? x1 : (j3 == 2) ? x2 : 0.f;
+                float D0 = E0 - KK, D1 = E1 - KK, D2 = E2 - KK;
+                float eb = nlane * (TAU_C0 + c1 * (mq0 + mlP) + cancel0);
+                warp_sum4(D0, D1, D2, eb, lane);
+                float Bn = eb * LN2 * 1.0001f + 1e-6f;              // nats
+                float x0 = D0 * LN2, x1 = D1 * LN2, x2 = D2 * LN2;
+                // leader among {cur (exactly 0), x0, x1, x2} and the best of the rest
+                float top = fmaxf(fmaxf(x0, x1), x2);
+                int jm = (x0 == top) ? 0 : (x1 == top) ? 1 : 2;
+                const bool finite = (fabsf(x0) + fabsf(x1) + fabsf(x2) + Bn) < 1.0e30f;   // false for inf / NaN
+                if (finite) {
+                    if (top + Bn < -TAU_GAP) { t = cur; n1++; }     // cur leads everything by > 60 nats
+                    else {
+                        const float rest = fmaxf(fmaxf(jm == 0 ? 0.f : x0, jm == 1 ? 0.f : x1), fmaxf(jm == 2 ? 0.f : x2, 0.f));
+                        if ((top - Bn) - (rest + Bn) > TAU_GAP) { t = (cur + 1 + jm) & 3; n1++; }
+                    }
                 }
-                // leader and runner-up
-                int m = 0; float dm = d0;
-                if (d1 > dm) { m = 1; dm = d1; }
-                if (d2 > dm) { m = 2; dm = d2; }
-                if (d3 > dm) { m = 3; dm = d3; }
-                const float second = fmaxf(fmaxf(m == 0 ? -3.0e38f : d0, m == 1 ? -3.0e38f : d1),
-                                           fmaxf(m == 2 ? -3.0e38f : d2, m == 3 ? -3.0e38f : d3));
-                const float bm = (m == cur) ? 0.f : Bn;             // cur's own value (0) is exact
-                if (Bn < 1.0e30f && (dm - bm) - (second + Bn) > TAU_GAP) {
-                    t = m; n1++;
-                } else if (Bn < 1.0e30f) {
-                    // ---- tier 2: FP64 brackets of the three CDF boundaries from D_a +- B
+                if (t < 0 && finite) {
+                    // ---- tier 2: same sums with the measured max |lg2 q| (tight bound), then FP64 brackets of the CDF
+                    tau_fp32_terms<true>(tile, Pw, Kw, gT + g * Sp, gT32 + g * Sp, eta_cur, eta32, cur, nch, anymask, lane, E0,
+                                         E1, E2, KK, mq);
+                    D0 = E0 - KK; D1 = E1 - KK; D2 = E2 - KK;
+                    eb = nlane * (TAU_C0 + c1 * (mq + mlP) + ccan * exp2f(fminf(mq + mlP, 120.f)));
+                    warp_sum4(D0, D1, D2, eb, lane);
+                    Bn = eb * LN2 * 1.0001f + 1e-6f;
+                    x0 = D0 * LN2; x1 = D1 * LN2; x2 = D2 * LN2;
                     const double B = (double)Bn;
-                    const double dd[4] = {(double)d0, (double)d1, (double)d2, (double)d3};
+                    double dd[4];
+                    // a_j = (cur+1+j)&3  <=>  j = (a-cur-1)&3 ; j == 3 is cur itself (exactly 0)
+#pragma unroll
+                    for (int a = 0; a < 4; a++) {
+                        const int j = (a - cur - 1) & 3;
+                        dd[a] = (j == 0) ? (double)x0 : (j == 1) ? (double)x1 : (j == 2) ? (double)x2 : 0.0;
+                    }
                     double eh[4], el[4];
                     double M = -1.0e300;
 #pragma unroll
@@ -311,7 +341,7 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
                         if (u < cminus - TAU_SLACK) below++;
                         else if (u >= cplus + TAU_SLACK) above++;
                     }
-                    if (below + above == 3) { t = above; n2++; }    // boundaries are ordered: t = #boundaries <= u
+                    if (below + above == 3 && Bn < 1.0e30f) { t = above; n2++; }    // boundaries are ordered: t = #boundaries <= u
                 }
             }
             if (t < 0) {
