@@ -52,7 +52,7 @@ struct TauParams {
 // Reference arithmetic (c_sample_tau.c:136-170) in FP64 for ONE (v,g): base over h ascending skipping
 // g from 0.0, candidate term added last, count through float.  Terms with n == 0 are skipped:
 // 0*log(p) adds exactly -0.0 there (p > 0 because eta, gamma > 0).  All lanes of the warp call this.
-__device__ __forceinline__ void tau_exact_logp(const int4 *tile, const double *gT, const double *eta_s, uint64_t code,
+__device__ __noinline__ void tau_exact_logp(const int4 *tile, const double *gT, const double *eta_s, uint64_t code,
                                                int g, int S, int Sp, int G, int lane, double L[4])
 {
     double L0 = 0.0, L1 = 0.0, L2 = 0.0, L3 = 0.0;
@@ -83,8 +83,10 @@ __device__ __forceinline__ void tau_exact_logp(const int4 *tile, const double *g
     L[0] = warp_sum(L0); L[1] = warp_sum(L1); L[2] = warp_sum(L2); L[3] = warp_sum(L3);
 }
 
+__device__ __noinline__ double log_fp64(double x) { return log(x); }   // one copy of the FP64 log for the ll term
+
 // normaliseLog4 + sample4 (c_sample_tau.c:48-91)
-__device__ __forceinline__ int tau_exact_pick(const double L[4], double u)
+__device__ __noinline__ int tau_exact_pick(const double L[4], double u)
 {
     double mx = L[0];
     if (L[1] > mx) mx = L[1];
@@ -147,8 +149,7 @@ __device__ __forceinline__ float lg2_fast(float x)
 template <bool TRACK>
 __device__ __forceinline__ void tau_fp32_terms(const int4 *tile, const double2 *Pw, const float *Kw, const double *gTg,
                                                const float *gT32g, const double *eta_cur, const float4 *eta32, int cur,
-                                               int nch, uint32_t anymask, int lane, float &E0, float &E1, float &E2,
-                                               float &KK, float &mq)
+                                               int nch, int lane, float &E0, float &E1, float &E2, float &KK, float &mq)
 {
     const double2 *ecp = reinterpret_cast<const double2 *>(eta_cur);
     const double2 ec01 = ecp[0], ec23 = ecp[1];
@@ -157,7 +158,6 @@ __device__ __forceinline__ void tau_fp32_terms(const int4 *tile, const double2 *
     for (int c = 0; c < nch; c++) {
         const int s = c * 32 + lane;
         const int4 n = tile[s];
-        const uint32_t am = (c < 8) ? (anymask >> (4 * c)) & 15u : 15u;
         const double gg = gTg[s];
         const float gf = gT32g[s];
         const double2 P01 = Pw[s * 2], P23 = Pw[s * 2 + 1];
@@ -172,12 +172,55 @@ __device__ __forceinline__ void tau_fp32_terms(const int4 *tile, const double2 *
         E = fmaf(fb, lq, E);                                                   \
         if (TRACK) mq = fmaxf(mq, fabsf(lq));                                  \
     }
-        if (am & 1u) { TAU_TERM(f0, q0, ea.x, E0) TAU_TERM(f0, q0, eb4.x, E1) TAU_TERM(f0, q0, ecc.x, E2) }
-        if (am & 2u) { TAU_TERM(f1, q1, ea.y, E0) TAU_TERM(f1, q1, eb4.y, E1) TAU_TERM(f1, q1, ecc.y, E2) }
-        if (am & 4u) { TAU_TERM(f2, q2, ea.z, E0) TAU_TERM(f2, q2, eb4.z, E1) TAU_TERM(f2, q2, ecc.z, E2) }
-        if (am & 8u) { TAU_TERM(f3, q3, ea.w, E0) TAU_TERM(f3, q3, eb4.w, E1) TAU_TERM(f3, q3, ecc.w, E2) }
+        // 12 independent FFMA -> MUFU.LG2 -> FFMA chains per chunk (straight-line: the scheduler interleaves them)
+        TAU_TERM(f0, q0, ea.x, E0) TAU_TERM(f1, q1, ea.y, E0) TAU_TERM(f2, q2, ea.z, E0) TAU_TERM(f3, q3, ea.w, E0)
+        TAU_TERM(f0, q0, eb4.x, E1) TAU_TERM(f1, q1, eb4.y, E1) TAU_TERM(f2, q2, eb4.z, E1) TAU_TERM(f3, q3, eb4.w, E1)
+        TAU_TERM(f0, q0, ecc.x, E2) TAU_TERM(f1, q1, ecc.y, E2) TAU_TERM(f2, q2, ecc.z, E2) TAU_TERM(f3, q3, ecc.w, E2)
 #undef TAU_TERM
     }
+}
+
+// tier 2 (rare, kept out of line so the hot loop stays small in the instruction cache)
+__device__ __noinline__ int tau_bracket_decide(const int4 *tile, const double2 *Pw, const float *Kw, const double *gTg,
+                                               const float *gT32g, const double *eta_cur, const float4 *eta32, int cur,
+                                               int nch, int lane, float nlane, float mlP, float c1, float ccan, double u)
+{
+    float E0, E1, E2, KK, mq;
+    tau_fp32_terms<true>(tile, Pw, Kw, gTg, gT32g, eta_cur, eta32, cur, nch, lane, E0, E1, E2, KK, mq);
+    const float LN2 = 0.69314718f;
+    float D0 = E0 - KK, D1 = E1 - KK, D2 = E2 - KK;
+    float eb = nlane * (TAU_C0 + c1 * (mq + mlP) + ccan * exp2f(fminf(mq + mlP, 120.f)));
+    warp_sum4(D0, D1, D2, eb, lane);
+    const float Bn = eb * LN2 * 1.0001f + 1e-6f;
+    if (!(Bn < 1.0e30f)) return -1;
+    const double x0 = (double)(D0 * LN2), x1 = (double)(D1 * LN2), x2 = (double)(D2 * LN2);
+    const double B = (double)Bn;
+    double eh[4], el[4];
+    double M = -1.0e300;
+    // a_j = (cur+1+j)&3  <=>  j = (a-cur-1)&3 ; j == 3 is cur itself (exactly 0, no error)
+#pragma unroll 1
+    for (int a = 0; a < 4; a++) {
+        const int j = (a - cur - 1) & 3;
+        const double d = (j == 0) ? x0 : (j == 1) ? x1 : (j == 2) ? x2 : 0.0;
+        const double bb = (j == 3) ? 0.0 : B;
+        eh[a] = d + bb; el[a] = d - bb;
+        M = fmax(M, eh[a]);
+    }
+#pragma unroll 1
+    for (int a = 0; a < 4; a++) { eh[a] = exp(eh[a] - M); el[a] = exp(el[a] - M); }
+    int below = 0, above = 0;     // number of boundaries certainly > u / certainly <= u
+    double ah = 0.0, al = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        ah += eh[k]; al += el[k];
+        double rh = 0.0, rl = 0.0;
+#pragma unroll
+        for (int a = k + 1; a < 4; a++) { rh += eh[a]; rl += el[a]; }
+        const double cplus = ah / (ah + rl), cminus = al / (al + rh);
+        if (u < cminus - TAU_SLACK) below++;
+        else if (u >= cplus + TAU_SLACK) above++;
+    }
+    return (below + above == 3) ? above : -1;    // boundaries are ordered: t = #boundaries <= u
 }
 
 __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams p)
@@ -247,7 +290,6 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
         }
         // stage counts; mixture P (FP64, ascending h); K = sum_b n_b lg2 P_b; per-lane read count and max |lg2 P|
         float nlane = 0.0f, mlP = 1.0f;
-        uint32_t anymask = 0;      // bit 4c+b: some lane of chunk c has a non-zero count of base b (c < 8)
         for (int c = 0; c < nch; c++) {
             const int s = c * 32 + lane;
             int4 n = make_int4(0, 0, 0, 0);
@@ -267,11 +309,6 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
             Kw[s] = fmaf((float)n.x, l0, fmaf((float)n.y, l1, fmaf((float)n.z, l2, (float)n.w * l3)));
             nlane += (float)(n.x + n.y + n.z + n.w);
             mlP = fmaxf(mlP, fmaxf(fmaxf(fabsf(l0), fabsf(l1)), fmaxf(fabsf(l2), fabsf(l3))));
-            if (c < 8) {
-                const uint32_t m4 = (__any_sync(DESMAN_FULL_MASK, n.x != 0) ? 1u : 0u) | (__any_sync(DESMAN_FULL_MASK, n.y != 0) ? 2u : 0u) |
-                                    (__any_sync(DESMAN_FULL_MASK, n.z != 0) ? 4u : 0u) | (__any_sync(DESMAN_FULL_MASK, n.w != 0) ? 8u : 0u);
-                anymask |= m4 << (4 * c);
-            }
         }
         __syncwarp();
 
@@ -284,8 +321,7 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
                 // ---- tier 1: D_j = (E_j - KK)*ln2 = L(a_j) - L(cur), j = 0..2, with the a-priori bounds from qmin
                 const double *eta_cur = eta_s + 4 * cur;
                 float E0, E1, E2, KK, mq;
-                tau_fp32_terms<false>(tile, Pw, Kw, gT + g * Sp, gT32 + g * Sp, eta_cur, eta32, cur, nch, anymask, lane, E0, E1,
-                                      E2, KK, mq);
+                tau_fp32_terms<false>(tile, Pw, Kw, gT + g * Sp, gT32 + g * Sp, eta_cur, eta32, cur, nch, lane, E0, E1, E2, KK, mq);
                 const float LN2 = 0.69314718f;
                 float D0 = E0 - KK, D1 = E1 - KK, D2 = E2 - KK;
                 float eb = nlane * (TAU_C0 + c1 * (mq0 + mlP) + cancel0);
@@ -304,44 +340,10 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
                     }
                 }
                 if (t < 0 && finite) {
-                    // ---- tier 2: same sums with the measured max |lg2 q| (tight bound), then FP64 brackets of the CDF
-                    tau_fp32_terms<true>(tile, Pw, Kw, gT + g * Sp, gT32 + g * Sp, eta_cur, eta32, cur, nch, anymask, lane, E0,
-                                         E1, E2, KK, mq);
-                    D0 = E0 - KK; D1 = E1 - KK; D2 = E2 - KK;
-                    eb = nlane * (TAU_C0 + c1 * (mq + mlP) + ccan * exp2f(fminf(mq + mlP, 120.f)));
-                    warp_sum4(D0, D1, D2, eb, lane);
-                    Bn = eb * LN2 * 1.0001f + 1e-6f;
-                    x0 = D0 * LN2; x1 = D1 * LN2; x2 = D2 * LN2;
-                    const double B = (double)Bn;
-                    double dd[4];
-                    // a_j = (cur+1+j)&3  <=>  j = (a-cur-1)&3 ; j == 3 is cur itself (exactly 0)
-#pragma unroll
-                    for (int a = 0; a < 4; a++) {
-                        const int j = (a - cur - 1) & 3;
-                        dd[a] = (j == 0) ? (double)x0 : (j == 1) ? (double)x1 : (j == 2) ? (double)x2 : 0.0;
-                    }
-                    double eh[4], el[4];
-                    double M = -1.0e300;
-#pragma unroll
-                    for (int a = 0; a < 4; a++) M = fmax(M, dd[a] + ((a == cur) ? 0.0 : B));
-#pragma unroll
-                    for (int a = 0; a < 4; a++) {
-                        const double bb = (a == cur) ? 0.0 : B;
-                        eh[a] = exp(dd[a] + bb - M); el[a] = exp(dd[a] - bb - M);
-                    }
-                    int below = 0, above = 0;     // number of boundaries certainly > u / certainly <= u
-                    double ah = 0.0, al = 0.0;
-#pragma unroll
-                    for (int k = 0; k < 3; k++) {
-                        ah += eh[k]; al += el[k];
-                        double rh = 0.0, rl = 0.0;
-#pragma unroll
-                        for (int a = k + 1; a < 4; a++) { rh += eh[a]; rl += el[a]; }
-                        const double cplus = ah / (ah + rl), cminus = al / (al + rh);
-                        if (u < cminus - TAU_SLACK) below++;
-                        else if (u >= cplus + TAU_SLACK) above++;
-                    }
-                    if (below + above == 3 && Bn < 1.0e30f) { t = above; n2++; }    // boundaries are ordered: t = #boundaries <= u
+                    // ---- tier 2 (rare): tracked FP32 sums -> tight bound -> FP64 brackets of the CDF boundaries
+                    t = tau_bracket_decide(tile, Pw, Kw, gT + g * Sp, gT32 + g * Sp, eta_cur, eta32, cur, nch, lane, nlane, mlP,
+                                           c1, ccan, u);
+                    if (t >= 0) n2++;
                 }
             }
             if (t < 0) {
@@ -392,10 +394,10 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
                     b0 = fma(e01.x, gm, b0); b1 = fma(e01.y, gm, b1);
                     b2 = fma(e23.x, gm, b2); b3 = fma(e23.y, gm, b3);
                 }
-                if (n.x) acc = fma((double)n.x, log(b0), acc);
-                if (n.y) acc = fma((double)n.y, log(b1), acc);
-                if (n.z) acc = fma((double)n.z, log(b2), acc);
-                if (n.w) acc = fma((double)n.w, log(b3), acc);
+                if (n.x) acc = fma((double)n.x, log_fp64(b0), acc);
+                if (n.y) acc = fma((double)n.y, log_fp64(b1), acc);
+                if (n.z) acc = fma((double)n.z, log_fp64(b2), acc);
+                if (n.w) acc = fma((double)n.w, log_fp64(b3), acc);
             }
             ll_acc += warp_sum(acc);
         }
