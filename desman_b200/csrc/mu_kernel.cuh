@@ -88,15 +88,26 @@ __global__ void __launch_bounds__(MU_WARPS * 32) mu_stats_kernel(MuParams p)
                 cge[g] = 0;
             }
             const uint32_t c3 = ((uint32_t)STAGE_MU << 28) | ((uint32_t)a << 26) | (uint32_t)s;
-            for (int j0 = 0; j0 < na; j0 += 4) {
-                const uint4 o = philox4x32_10((uint32_t)(p.v0 + v), (uint32_t)(j0 >> 2), p.sweep, c3, k0, k1);
-                const int lim = na - j0;
+            // full blocks of 4 reads, then one guarded tail block
+            const int nfull = na >> 2;
+            for (int jb = 0; jb < nfull; jb++) {
+                const uint4 o = philox4x32_10((uint32_t)(p.v0 + v), (uint32_t)jb, p.sweep, c3, k0, k1);
 #pragma unroll
                 for (int g = 0; g < GP - 1; g++) {
                     cge[g] += (o.x >= thr[g]);
-                    cge[g] += (lim > 1) & (o.y >= thr[g]);
-                    cge[g] += (lim > 2) & (o.z >= thr[g]);
-                    cge[g] += (lim > 3) & (o.w >= thr[g]);
+                    cge[g] += (o.y >= thr[g]);
+                    cge[g] += (o.z >= thr[g]);
+                    cge[g] += (o.w >= thr[g]);
+                }
+            }
+            const int rem = na & 3;
+            if (rem) {
+                const uint4 o = philox4x32_10((uint32_t)(p.v0 + v), (uint32_t)nfull, p.sweep, c3, k0, k1);
+#pragma unroll
+                for (int g = 0; g < GP - 1; g++) {
+                    cge[g] += (o.x >= thr[g]);
+                    cge[g] += (rem > 1) & (o.y >= thr[g]);
+                    cge[g] += (rem > 2) & (o.z >= thr[g]);
                 }
             }
             // cge[k] = #reads with strain >= k+1 (only k < G-1 is meaningful)

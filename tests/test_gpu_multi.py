@@ -1,0 +1,63 @@
+"""2-GPU test of the sharded chain (NCCL all-reduce inside the engine): runs only where >= 2 devices are visible."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+SCRIPT = r'''
+import os, sys
+sys.path.insert(0, os.environ["DESMAN_ROOT"]); sys.path.insert(0, os.path.join(os.environ["DESMAN_ROOT"], "tests"))
+import numpy as np, torch, torch.distributed as dist
+from conftest import onehot, synth_problem
+from desman_b200 import engine
+from desman_b200.parallel import exchange_unique_id, shard_bounds
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(rank)
+dist.init_process_group("nccl")
+p = synth_problem(4001, 64, 8, depth=30.0, seed=9, ambiguous=True)
+lo, hi = shard_bounds(4001, rank, world)
+e = engine.Engine(rank, seed=4242)
+e.set_counts(p["counts"][lo:hi], v0=lo, V_total=4001)
+e.comm_init(exchange_unique_id(dist, engine.Engine.comm_unique_id), rank, world)
+e.set_state(onehot(p["tau0"][lo:hi]), p["gamma0"], p["eta0"])
+out = e.update(8)
+np.savez(os.path.join(os.environ["DESMAN_OUT"], "r%d.npz" % rank), tau=e.get_tau_index(), gamma=out["gamma_store"],
+         eta=out["eta_store"], ll=out["ll_store"], nchange=out["nchange"], star=e.get_star()["iter"])
+e.close()
+dist.destroy_process_group()
+'''
+
+
+def test_two_gpu_sharded_update_equals_one_gpu(tmp_path):
+    from conftest import onehot, synth_problem
+    from desman_b200 import _lib, engine
+    if _lib.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "w.py"
+    script.write_text(SCRIPT)
+    env = dict(os.environ, DESMAN_ROOT=ROOT, DESMAN_OUT=str(tmp_path))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    p = synth_problem(4001, 64, 8, depth=30.0, seed=9, ambiguous=True)
+    e = engine.Engine(0, seed=4242)
+    e.set_counts(p["counts"])
+    e.set_state(onehot(p["tau0"]), p["gamma0"], p["eta0"])
+    one = e.update(8)
+    tau1 = e.get_tau_index()
+    e.close()
+    r0, r1 = np.load(tmp_path / "r0.npz"), np.load(tmp_path / "r1.npz")
+    assert np.array_equal(np.concatenate([r0["tau"], r1["tau"]]), tau1)         # integer tau: independent of GPU count
+    assert np.array_equal(r0["gamma"], r1["gamma"]) and np.array_equal(r0["gamma"], one["gamma_store"])
+    assert np.array_equal(r0["eta"], one["eta_store"])
+    assert np.array_equal(r0["nchange"], one["nchange"]) and np.array_equal(r1["nchange"], one["nchange"])
+    assert np.allclose(r0["ll"], one["ll_store"], rtol=1e-12, atol=0) and np.array_equal(r0["ll"], r1["ll"])
