@@ -221,6 +221,9 @@ def run_b200(args):
     e2e_value = (V_total / UNIT_V) * K / t_e2e
     hs.close()
 
+    if td is not None:
+        td.barrier()
+        td.destroy_process_group()
     if rank != 0:
         return
     out = {
