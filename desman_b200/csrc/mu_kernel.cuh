@@ -31,8 +31,17 @@ struct MuParams {
 #define MU_WARPS 8
 #define MU_FLUSH_SITES 64   // 64 sites * 2^24 max count < 2^31
 
+// (x >= T) as the carry of x + (2^32 - T), evaluated by IMAD.WIDE on the FMA pipe: the kernel is bound by the
+// integer-ALU pipe (Philox xors/adds + threshold counting), so the compares are moved off it.
+__device__ __forceinline__ uint32_t ge_carry(uint32_t x, unsigned long long neg_t)
+{
+    unsigned long long r;
+    asm("mad.wide.u32 %0, %1, 1, %2;" : "=l"(r) : "r"(x), "l"(neg_t));
+    return (uint32_t)(r >> 32);
+}
+
 template <int GP>
-__global__ void __launch_bounds__(MU_WARPS * 32) mu_stats_kernel(MuParams p)
+__global__ void __launch_bounds__(MU_WARPS * 32, 2) mu_stats_kernel(MuParams p)
 {
     __shared__ double eta_s[16];
     const int S = p.S, G = p.G;
@@ -79,12 +88,13 @@ __global__ void __launch_bounds__(MU_WARPS * 32) mu_stats_kernel(MuParams p)
                 cums[g] = cum;
             }
             const double scale = __ddiv_rn(4294967296.0, cum);
-            uint32_t thr[GP - 1];
+            unsigned long long nthr[GP - 1];   // 2^32 - T_g
             uint32_t cge[GP - 1];
 #pragma unroll
             for (int g = 0; g < GP - 1; g++) {
                 const double t = floor(__dmul_rn(cums[g], scale));
-                thr[g] = (t >= 4294967295.0) ? 0xffffffffu : (uint32_t)t;
+                const uint32_t thr = (t >= 4294967295.0) ? 0xffffffffu : (uint32_t)t;
+                nthr[g] = 0x100000000ull - (unsigned long long)thr;
                 cge[g] = 0;
             }
             const uint32_t c3 = ((uint32_t)STAGE_MU << 28) | ((uint32_t)a << 26) | (uint32_t)s;
@@ -94,10 +104,8 @@ __global__ void __launch_bounds__(MU_WARPS * 32) mu_stats_kernel(MuParams p)
                 const uint4 o = philox4x32_10((uint32_t)(p.v0 + v), (uint32_t)jb, p.sweep, c3, k0, k1);
 #pragma unroll
                 for (int g = 0; g < GP - 1; g++) {
-                    cge[g] += (o.x >= thr[g]);
-                    cge[g] += (o.y >= thr[g]);
-                    cge[g] += (o.z >= thr[g]);
-                    cge[g] += (o.w >= thr[g]);
+                    cge[g] += ge_carry(o.x, nthr[g]) + ge_carry(o.y, nthr[g]);
+                    cge[g] += ge_carry(o.z, nthr[g]) + ge_carry(o.w, nthr[g]);
                 }
             }
             const int rem = na & 3;
@@ -105,9 +113,9 @@ __global__ void __launch_bounds__(MU_WARPS * 32) mu_stats_kernel(MuParams p)
                 const uint4 o = philox4x32_10((uint32_t)(p.v0 + v), (uint32_t)nfull, p.sweep, c3, k0, k1);
 #pragma unroll
                 for (int g = 0; g < GP - 1; g++) {
-                    cge[g] += (o.x >= thr[g]);
-                    cge[g] += (rem > 1) & (o.y >= thr[g]);
-                    cge[g] += (rem > 2) & (o.z >= thr[g]);
+                    cge[g] += ge_carry(o.x, nthr[g]);
+                    cge[g] += (rem > 1) ? ge_carry(o.y, nthr[g]) : 0u;
+                    cge[g] += (rem > 2) ? ge_carry(o.z, nthr[g]) : 0u;
                 }
             }
             // cge[k] = #reads with strain >= k+1 (only k < G-1 is meaningful)
