@@ -49,6 +49,7 @@ class HaploSNP_Sampler():
         self.alpha_constant = alpha_constant
 
         # the constructor consumes the caller's stream exactly like the reference (:63, :72)
+        self._tau_oh = self._tau_ix = self._tau_star_oh = self._tau_star_ix = None
         self.gamma = self.randomState.dirichlet(self.alpha, size=self.S)
         self.gamma_store = np.zeros((self.max_iter, self.S, self.G))
         if fixed_tau is None:
@@ -85,6 +86,43 @@ class HaploSNP_Sampler():
         self._eng = None
         self._eng_mode = None
 
+    # ------------------------------------------------------------------ tau / tau_star: one-hot views built on demand
+    # The engine keeps tau as uint8 base indices [V,G]; the reference's int64 one-hot [V,G,4] layout (32x larger) is
+    # materialised only when the attribute is read, and whatever the caller assigns is uploaded at the next driver.
+    @staticmethod
+    def _onehot(idx):
+        out = np.zeros(idx.shape + (4,), dtype=np.int64)
+        np.put_along_axis(out, idx[..., None].astype(np.int64), 1, axis=-1)
+        return out
+
+    @property
+    def tau(self):
+        if self._tau_oh is None:
+            self._tau_oh = self._onehot(self._tau_ix)
+        return self._tau_oh
+
+    @tau.setter
+    def tau(self, value):
+        self._tau_oh = value
+        self._tau_ix = None
+
+    @property
+    def tau_star(self):
+        if self._tau_star_oh is None:
+            self._tau_star_oh = self._onehot(self._tau_star_ix)
+        return self._tau_star_oh
+
+    @tau_star.setter
+    def tau_star(self, value):
+        self._tau_star_oh = value
+        self._tau_star_ix = None
+
+    def _tau_index(self, star=False):
+        ix, oh = (self._tau_star_ix, self._tau_star_oh) if star else (self._tau_ix, self._tau_oh)
+        if oh is not None:          # the caller may have assigned or modified the one-hot array
+            return np.argmax(np.asarray(oh), axis=2).astype(np.uint8)
+        return ix
+
     # ------------------------------------------------------------------ device plumbing
     def _engine(self, mode=RNG_PHILOX):
         if self._eng is None or self._eng_mode != mode:
@@ -103,15 +141,25 @@ class HaploSNP_Sampler():
         return self._eng
 
     def _push(self, eng, gamma=None, tau=None, eta=None):
-        tau = self.tau if tau is None else tau
         gamma = self.gamma if gamma is None else gamma
         eta = self.eta if eta is None else eta
-        if tau.shape[1] != self.G or gamma.shape[1] != self.G:
-            raise ValueError("tau/gamma do not match G = %d" % self.G)
+        if gamma.shape[1] != self.G:
+            raise ValueError("gamma does not match G = %d" % self.G)
+        if tau is None and self._tau_oh is None and self._tau_ix is not None:
+            if self._tau_ix.shape[1] != self.G:
+                raise ValueError("tau does not match G = %d" % self.G)
+            eng.set_state(None, gamma, eta, G=self.G)
+            eng.set_tau_index(self._tau_ix)                       # untouched since the last driver: upload the indices
+            return
+        tau = self.tau if tau is None else tau
+        if tau.shape[1] != self.G:
+            raise ValueError("tau does not match G = %d" % self.G)
         eng.set_state(np.ascontiguousarray(tau, dtype=np.int64), gamma, eta, G=self.G)
 
-    def _pull(self, eng):
-        self.tau, self.gamma, self.eta = eng.get_state()
+    def _pull(self, eng, full=True):
+        self._tau_ix, self._tau_oh = eng.get_tau_index(), None
+        if full:
+            _, self.gamma, self.eta = eng.get_state(want_tau=False)
 
     def close(self):
         if self._eng is not None:
@@ -133,7 +181,11 @@ class HaploSNP_Sampler():
         return np.einsum('ga,ga', self.tauMap, tauState)                     # :224-226
 
     def updateTauIndices(self):
-        self.tauIndices = np.einsum('ga,vga->v', self.tauMap, self.tau)      # :228-231, vectorised
+        self.tauIndices = self._site_codes(self._tau_index())               # :228-231, vectorised
+
+    def _site_codes(self, idx):
+        w = np.array([4 ** (self.G - g - 1) for g in range(self.G)], dtype=object if self.G > 31 else np.int64)
+        return idx.astype(w.dtype) @ w
 
     def tauDist(self, tau1, tau2):
         return int((np.argmax(tau1, axis=1) != np.argmax(tau2, axis=1)).sum())
@@ -155,7 +207,7 @@ class HaploSNP_Sampler():
         eng = self._engine(RNG_MT19937 if self._tau_rng == "mt19937" else RNG_PHILOX)
         self._push(eng, gamma=gamma, eta=eta)
         n = eng.sample_tau()
-        self.tau = eng.get_state()[0]
+        self._pull(eng, full=False)
         self.updateTauIndices()
         return n
 
@@ -203,9 +255,9 @@ class HaploSNP_Sampler():
             logging.info('Gibbs Iter %d, no. changed = %d, %s = %f' % (it, res["nchange"][it], what, res["lp_store"][it]))
 
     def _finish(self, eng, res, n_iter, full):
-        self._pull(eng) if full else setattr(self, "tau", eng.get_state()[0])
-        star = eng.get_star()
-        self.tau_star = star["tau"]
+        self._pull(eng, full)
+        star = eng.get_star(want_tau=False)
+        self._tau_star_ix, self._tau_star_oh = eng.get_star_index(), None
         self.lp_star = star["lp"]
         self.iter_star = star["iter"]
         if full:
@@ -218,7 +270,7 @@ class HaploSNP_Sampler():
         self._tau_sum = eng.get_tau_sum()
         self._timing = eng.get_timing()
         self.updateTauIndices()
-        self.tauIndices_star = np.einsum('ga,vga->v', self.tauMap, self.tau_star)
+        self.tauIndices_star = self._site_codes(self._tau_star_ix)
 
     def update(self):
         """max_iter Gibbs sweeps mu/E -> gamma -> tau -> eta -> ll/lp with MAP tracking (:334-365)."""
@@ -228,6 +280,18 @@ class HaploSNP_Sampler():
         self.gamma_store, self.eta_store = res["gamma_store"], res["eta_store"]
         self._finish(eng, res, self.max_iter, True)
         self._log_progress(res, "nlp")
+
+    def update_fixed_tau(self):
+        """max_iter sweeps of mu/E -> gamma -> eta with tau held fixed (:409-428)."""
+        eng = self._engine()
+        self._push(eng)
+        eng.set_option("fixed_tau", 1)
+        try:
+            res = eng.update(self.max_iter)
+        finally:
+            eng.set_option("fixed_tau", 0)
+        self.gamma_store, self.eta_store = res["gamma_store"], res["eta_store"]
+        self._finish(eng, res, self.max_iter, True)
 
     def updateTau(self):
         """tau-only replay against gamma_store/eta_store (:383-407)."""
@@ -258,7 +322,7 @@ class HaploSNP_Sampler():
         eng = self._engine(RNG_MT19937 if self._tau_rng == "mt19937" else RNG_PHILOX)
         self._push(eng, gamma=self.gamma_star, eta=self.eta_star)
         res = eng.update_tau(gs, es)
-        self.tau = eng.get_state()[0]
+        self._pull(eng, full=False)
         for it in range(self.burn_iter):
             print(str(it) + "," + str(res["nchange"][it]) + "," + str(res["lp_store"][it]))
             sys.stdout.flush()

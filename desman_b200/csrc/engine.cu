@@ -7,7 +7,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/desman_b200.h"
@@ -127,7 +129,10 @@ struct desman_ctx {
     size_t cap_vg = 0, cap_sg = 0;
     uint32_t last_n_iter = 0;
     int tau_exact = 0;                       // 1: FP64 reference-order path for every draw
+    int fixed_tau = 0;                       // 1: update() skips the tau draw (update_fixed_tau, HaploSNP_Sampler.py:409-428)
     unsigned long long *tiers = nullptr;     // [3] draws decided by tier 1/2/3
+    int4 *pin[2] = {nullptr, nullptr};        // pinned staging for the count upload
+    cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     // scratch
     void *scratch = nullptr;
     size_t scratch_cap = 0;
@@ -247,6 +252,7 @@ extern "C" int desman_ctx_destroy(desman_ctx *c)
                     c->scratch, c->flush_buf, c->tiers};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) { if (c->pin[i]) cudaFreeHost(c->pin[i]); if (c->pin_ev[i]) cudaEventDestroy(c->pin_ev[i]); }
     cudaStreamDestroy(c->stream);
     delete c;
     return DESMAN_OK;
@@ -317,21 +323,44 @@ extern "C" int desman_set_counts(desman_ctx *c, const int64_t *variants, int64_t
         CU(cudaMalloc(&c->counts, ncell * sizeof(int4)));
         c->counts_cap = ncell;
     }
-    // stage the int64 tensor in bounded chunks and repack on device
-    const size_t chunk_cells = ncell < ((size_t)8 << 20) ? ncell : ((size_t)8 << 20);
-    RET(ensure_scratch(c, chunk_cells * 32 + 64));
-    int *err = (int *)((char *)c->scratch + chunk_cells * 32);
-    CU(cudaMemsetAsync(err, 0, sizeof(int), c->stream));
-    for (size_t off = 0; off < ncell; off += chunk_cells) {
-        const size_t n = (ncell - off < chunk_cells) ? ncell - off : chunk_cells;
-        CU(cudaMemcpyAsync(c->scratch, variants + off * 4, n * 32, cudaMemcpyHostToDevice, c->stream));
-        pack_counts_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>((const long long *)c->scratch, c->counts + off, n, err);
-        CU(cudaGetLastError());
+    // Repack int64 -> int32x4 on the host with a few threads straight into pinned staging buffers and stream the
+    // packed cells (half the bytes of the int64 tensor) to the device, double-buffered.
+    const size_t chunk_cells = (size_t)2 << 20;                         // 32 MB of packed cells per buffer
+    if (!c->pin[0]) {
+        CU(cudaMallocHost(&c->pin[0], chunk_cells * sizeof(int4)));
+        CU(cudaMallocHost(&c->pin[1], chunk_cells * sizeof(int4)));
+        CU(cudaEventCreateWithFlags(&c->pin_ev[0], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->pin_ev[1], cudaEventDisableTiming));
     }
-    int herr = 0;
-    CU(cudaMemcpyAsync(&herr, err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    std::atomic<int> bad(0);
+    int buf = 0;
+    for (size_t off = 0; off < ncell; off += chunk_cells, buf ^= 1) {
+        const size_t n = (ncell - off < chunk_cells) ? ncell - off : chunk_cells;
+        CU(cudaEventSynchronize(c->pin_ev[buf]));                       // previous copy out of this buffer finished
+        int4 *dst = c->pin[buf];
+        const int64_t *src = variants + off * 4;
+        const int nt = (n >= ((size_t)1 << 16)) ? 8 : 1;
+        auto work = [&](int t) {
+            const size_t lo = n * t / nt, hi = n * (t + 1) / nt;
+            int64_t orv = 0;
+            for (size_t i = lo; i < hi; i++) {
+                const int64_t a = src[4 * i], b = src[4 * i + 1], d = src[4 * i + 2], e = src[4 * i + 3];
+                orv |= a | b | d | e | (DESMAN_MAX_COUNT - a) | (DESMAN_MAX_COUNT - b) | (DESMAN_MAX_COUNT - d) | (DESMAN_MAX_COUNT - e);
+                dst[i] = make_int4((int)a, (int)b, (int)d, (int)e);
+            }
+            if (orv < 0) bad = 1;                                       // a negative count or one above the limit
+        };
+        if (nt == 1) work(0);
+        else {
+            std::vector<std::thread> th;
+            for (int t = 0; t < nt; t++) th.emplace_back(work, t);
+            for (auto &x : th) x.join();
+        }
+        CU(cudaMemcpyAsync(c->counts + off, dst, n * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaEventRecord(c->pin_ev[buf], c->stream));
+    }
     CU(cudaStreamSynchronize(c->stream));
-    if (herr) { c->V = 0; return fail(DESMAN_EINVAL, "counts must be in [0, %d] per (v,s,base) cell", DESMAN_MAX_COUNT); }
+    if (bad) { c->V = 0; return fail(DESMAN_EINVAL, "counts must be in [0, %d] per (v,s,base) cell", DESMAN_MAX_COUNT); }
     if (V != c->V || S != c->S) c->G = 0;  // state must be (re)set for a new shape
     c->V = V; c->S = S; c->v0 = v0; c->V_total = V_total;
     c->ll_const_valid = false;
@@ -797,7 +826,7 @@ extern "C" int desman_update(desman_ctx *c, int n_iter, double *gamma_store, dou
         RET(launch_mu(c, c->gamma, c->eta));                            // sampleMu   (:341)
         RET(allreduce_stats(c));
         RET(launch_draw(c, c->stats, c->gamma, c->eta_new));            // sampleGamma (:342) + sampleEta's draw (:347)
-        RET(launch_tau(c, c->gamma, c->eta, c->eta_new, true, true, true, (uint32_t)it));   // sample_tau (:345) + ll (:349)
+        RET(launch_tau(c, c->gamma, c->eta, c->eta_new, !c->fixed_tau, true, true, (uint32_t)it));   // sample_tau (:345) + ll (:349)
         RET(launch_finalize(c, c->gamma, c->eta_new, c->eta, it, 0, sb, true));             // lp, stores, star (:350-358)
         sweep_end(c);
         c->sweep++;
@@ -865,6 +894,14 @@ extern "C" int desman_get_star(desman_ctx *c, int64_t *tau_star, double *gamma_s
     return DESMAN_OK;
 }
 
+extern "C" int desman_get_star_index(desman_ctx *c, uint8_t *tau_star_idx)
+{
+    RET(require_state(c));
+    CU(cudaMemcpyAsync(tau_star_idx, c->tau_star, (size_t)c->V * c->G, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return DESMAN_OK;
+}
+
 extern "C" int desman_get_tau_sum(desman_ctx *c, int64_t *tau_sum)
 {
     RET(require_state(c));
@@ -916,6 +953,7 @@ extern "C" int desman_set_option(desman_ctx *c, const char *name, int64_t value)
 {
     if (!c || !name) return fail(DESMAN_EINVAL, "desman_set_option: bad arguments");
     if (!strcmp(name, "tau_exact")) { c->tau_exact = value ? 1 : 0; return DESMAN_OK; }
+    if (!strcmp(name, "fixed_tau")) { c->fixed_tau = value ? 1 : 0; return DESMAN_OK; }
     return fail(DESMAN_EINVAL, "unknown option '%s'", name);
 }
 
@@ -951,7 +989,6 @@ extern "C" int desman_get_timing(desman_ctx *c, double *elapsed_ms, double kerne
 // ------------------------------------------------------------------------------------------ reference ABI
 // Process-global stream, like the file-static gsl_rng of c_sample_tau.c:24.
 static desman_ctx *g_legacy = nullptr;
-static unsigned long g_legacy_seed = 0;
 
 extern "C" void c_initRNG(void)
 {
@@ -968,7 +1005,6 @@ extern "C" void c_initRNG(void)
 extern "C" void c_setRNG(unsigned long int seed)
 {
     if (!g_legacy) { fail(DESMAN_ESTATE, "c_setRNG before c_initRNG"); fprintf(stderr, "desman_b200: %s\n", g_err); return; }
-    g_legacy_seed = seed;
     if (desman_set_rng(g_legacy, (uint64_t)seed, 0, 0) != DESMAN_OK) fprintf(stderr, "desman_b200: c_setRNG failed: %s\n", g_err);
 }
 

@@ -1,5 +1,4 @@
 // desman_b200/csrc/misc_kernels.cuh -- small kernels around the two site passes:
-//   pack_counts        int64 [V,S,4] -> int32x4 cells, range check
 //   lgamma_const       sum_vs lgamma(N+1) - sum_b lgamma(n_b+1)    (Desman_Utils.py:28-33, constant in the chain)
 //   mt19937_kernel     K9: GSL-compatible MT19937 stream             (c_sample_tau.c:33-40,174)
 //   draw_gamma_eta     K3: Dirichlet draws of gamma and eta          (HaploSNP_Sampler.py:263-281)
@@ -8,19 +7,6 @@
 #include "common.cuh"
 
 // ---------------------------------------------------------------------------------------------
-__global__ void pack_counts_kernel(const long long *__restrict__ src, int4 *__restrict__ dst, size_t ncell,
-                                   int *__restrict__ err)
-{
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < ncell; i += (size_t)gridDim.x * blockDim.x) {
-        const longlong2 a = reinterpret_cast<const longlong2 *>(src)[2 * i];
-        const longlong2 b = reinterpret_cast<const longlong2 *>(src)[2 * i + 1];
-        if (a.x < 0 || a.y < 0 || b.x < 0 || b.y < 0 || a.x > 16777216 || a.y > 16777216 || b.x > 16777216 ||
-            b.y > 16777216)
-            *err = 1;
-        dst[i] = make_int4((int)a.x, (int)a.y, (int)b.x, (int)b.y);
-    }
-}
-
 __global__ void lgamma_const_kernel(const int4 *__restrict__ counts, size_t ncell, double *__restrict__ partial)
 {
     __shared__ double red[256];

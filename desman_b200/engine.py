@@ -145,6 +145,11 @@ class Engine:
                                       C.byref(it)), "desman_get_star")
         return dict(tau=tau, gamma=gamma, eta=eta, lp=lp.value, iter=it.value)
 
+    def get_star_index(self):
+        out = np.empty((self.V, self.G), dtype=np.uint8)
+        check(self._L.desman_get_star_index(self._h, out.ctypes.data_as(_lib._pu8)), "desman_get_star_index")
+        return out
+
     def get_tau_sum(self):
         out = np.empty((self.V, self.G, 4), dtype=np.int64)
         check(self._L.desman_get_tau_sum(self._h, _lib.ptr_i64(out)), "desman_get_tau_sum")

@@ -94,6 +94,7 @@ int desman_update_tau(desman_ctx *ctx, int n_iter, const double *gamma_store, co
 /* MAP state tracked by the last update()/update_tau() (storeStarState, :326-332) */
 int desman_get_star(desman_ctx *ctx, int64_t *tau_star, double *gamma_star, double *eta_star,
                     double *lp_star, int *iter_star);
+int desman_get_star_index(desman_ctx *ctx, uint8_t *tau_star_idx /*V*G*/);   /* tau_star as base indices */
 /* sum over the sweeps of the last update()/update_tau() of one-hot tau: tau_store.sum(axis=0)
  * (tauMean :479-483, probabilisticTau :834-840) */
 int desman_get_tau_sum(desman_ctx *ctx, int64_t *tau_sum /*V*G*4*/);
@@ -105,7 +106,8 @@ int desman_nmft_factorize(desman_ctx *ctx, const int64_t *snps, int64_t V, int S
                           double *tau, double *gamma, int max_iter, double min_change, int fix_gamma,
                           int *n_iter_done, double *div_final, double *div_trace);
 
-/* Engine options.  "tau_exact" = 1 forces the FP64 reference-order arithmetic for every tau draw (validation;
+/* Engine options.  "fixed_tau" = 1 makes desman_update skip the tau draw (update_fixed_tau, HaploSNP_Sampler.py:409-428).
+ * "tau_exact" = 1 forces the FP64 reference-order arithmetic for every tau draw (validation;
  * default 0 = filtered-exact FP32 fast path with FP64 fallback, same draws).  desman_get_tier_counts returns how
  * many draws were decided by the FP32 gap test / the FP64 CDF brackets / the FP64 reference-order recompute. */
 int desman_set_option(desman_ctx *ctx, const char *name, int64_t value);

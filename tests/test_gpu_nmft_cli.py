@@ -121,3 +121,45 @@ def test_hybrid_reference_loop_with_gpu_sampletau():
         sampletau.sample_tau(tau, np.ascontiguousarray(z["call_gamma"][i]), np.ascontiguousarray(z["call_eta"][i]), counts)
         assert np.array_equal(np.argmax(tau, 2), z["call_tau_out"][i])
     sampletau.freeRNG()
+
+
+def test_sampler_class_surface_on_gpu(oracle_mod):
+    """HaploSNP_Sampler mirror: attribute sync (lazy one-hot tau), update(), removeDegenerate(), updateTau(),
+    update_fixed_tau(), summaries -- against the oracle where it applies."""
+    from numpy.random import RandomState
+    from conftest import synth_problem
+    from desman_b200 import sampletau
+    from desman_b200.HaploSNP_Sampler import HaploSNP_Sampler
+    p = synth_problem(200, 16, 4, depth=25.0, seed=8, ambiguous=True)
+    sampletau.initRNG(); sampletau.setRNG(4321)
+    hs = HaploSNP_Sampler(p["counts"], 4, RandomState(1), max_iter=7)
+    assert hs.tau.shape == (200, 4, 4) and (hs.tau.sum(2) == 1).all() and hs.gamma.shape == (16, 4)
+    hs.tau = onehot(p["tau0"]); hs.gamma = p["gamma0"].copy(); hs.eta = p["eta0"].copy()
+    ll, lp = hs.logLikelihood(hs.gamma, hs.tau, hs.eta), hs.logPosterior(hs.gamma, hs.tau, hs.eta)
+    assert abs(ll - oracle_mod.loglik(hs.tau, hs.gamma, hs.eta, p["counts"])) < 1e-9 * abs(ll)
+    hs.update()
+    want = oracle_mod.update(onehot(p["tau0"]), p["gamma0"], p["eta0"], p["counts"], 7, seed=4321)
+    assert np.array_equal(hs.tau, want["tau"]) and np.array_equal(hs.tau_star, want["tau_star"])
+    assert np.allclose(hs.gamma_store, want["gamma_store"], rtol=1e-9, atol=0)
+    assert np.allclose(hs.ll_store, want["ll_store"], rtol=1e-9, atol=0)
+    assert np.allclose(hs.tauMean(), want["tau_sum"] / 7.0) and abs(hs.lp_star - want["lp_star"]) < 1e-9 * abs(lp)
+    assert np.array_equal(hs.tauIndices, np.einsum('ga,vga->v', hs.tauMap, hs.tau))
+    assert abs(hs.meanDeviance() + 2 * want["ll_store"].mean()) < 1e-6 * abs(hs.meanDeviance())
+    # duplicate a strain by hand -> removeDegenerate merges it and adds the gamma columns
+    t = hs.tau.copy(); t[:, 3, :] = t[:, 1, :]; hs.tau = t
+    g_before = hs.gamma.copy()
+    hs.removeDegenerate()
+    assert hs.G == 3 and hs.tau.shape == (200, 3, 4) and np.allclose(hs.gamma[:, 1], g_before[:, 1] + g_before[:, 3])
+    hs.update()                                           # runs with the new G
+    assert hs.gamma_store.shape == (7, 16, 3) and np.isfinite(hs.lp_star)
+    gs, es = hs.gamma_store.copy(), hs.eta_store.copy()
+    tau_fixed = hs.tau.copy()
+    hs.update_fixed_tau()
+    assert np.array_equal(hs.tau, tau_fixed)
+    hs.gamma_store, hs.eta_store = gs, es
+    hs.updateTau()
+    assert hs.ll_store.shape == (7,) and (hs.tauMean().sum(2) > 0.999).all()
+    with pytest.raises(NotImplementedError):
+        hs.DIC()
+    hs.close()
+    sampletau.freeRNG()
