@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <atomic>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -131,7 +132,6 @@ struct desman_ctx {
     int tau_exact = 0;                       // 1: FP64 reference-order path for every draw
     int fixed_tau = 0;                       // 1: update() skips the tau draw (update_fixed_tau, HaploSNP_Sampler.py:409-428)
     unsigned long long *tiers = nullptr;     // [3] draws decided by tier 1/2/3
-    int4 *pin[2] = {nullptr, nullptr};        // pinned staging for the count upload
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     // scratch
     void *scratch = nullptr;
@@ -252,7 +252,7 @@ extern "C" int desman_ctx_destroy(desman_ctx *c)
                     c->scratch, c->flush_buf, c->tiers};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
-    for (int i = 0; i < 2; i++) { if (c->pin[i]) cudaFreeHost(c->pin[i]); if (c->pin_ev[i]) cudaEventDestroy(c->pin_ev[i]); }
+    for (int i = 0; i < 2; i++) if (c->pin_ev[i]) cudaEventDestroy(c->pin_ev[i]);
     cudaStreamDestroy(c->stream);
     delete c;
     return DESMAN_OK;
@@ -326,9 +326,14 @@ extern "C" int desman_set_counts(desman_ctx *c, const int64_t *variants, int64_t
     // Repack int64 -> int32x4 on the host with a few threads straight into pinned staging buffers and stream the
     // packed cells (half the bytes of the int64 tensor) to the device, double-buffered.
     const size_t chunk_cells = (size_t)2 << 20;                         // 32 MB of packed cells per buffer
-    if (!c->pin[0]) {
-        CU(cudaMallocHost(&c->pin[0], chunk_cells * sizeof(int4)));
-        CU(cudaMallocHost(&c->pin[1], chunk_cells * sizeof(int4)));
+    static int4 *g_pin[2] = {nullptr, nullptr};                          // process-wide pinned staging (pinning is slow)
+    static std::mutex g_pin_mu;
+    std::lock_guard<std::mutex> pin_lock(g_pin_mu);
+    if (!g_pin[0]) {
+        CU(cudaMallocHost(&g_pin[0], chunk_cells * sizeof(int4)));
+        CU(cudaMallocHost(&g_pin[1], chunk_cells * sizeof(int4)));
+    }
+    if (!c->pin_ev[0]) {
         CU(cudaEventCreateWithFlags(&c->pin_ev[0], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->pin_ev[1], cudaEventDisableTiming));
     }
@@ -337,7 +342,7 @@ extern "C" int desman_set_counts(desman_ctx *c, const int64_t *variants, int64_t
     for (size_t off = 0; off < ncell; off += chunk_cells, buf ^= 1) {
         const size_t n = (ncell - off < chunk_cells) ? ncell - off : chunk_cells;
         CU(cudaEventSynchronize(c->pin_ev[buf]));                       // previous copy out of this buffer finished
-        int4 *dst = c->pin[buf];
+        int4 *dst = g_pin[buf];
         const int64_t *src = variants + off * 4;
         const int nt = (n >= ((size_t)1 << 16)) ? 8 : 1;
         auto work = [&](int t) {

@@ -163,3 +163,30 @@ def test_sampler_class_surface_on_gpu(oracle_mod):
         hs.DIC()
     hs.close()
     sampletau.freeRNG()
+
+
+@pytest.mark.parametrize("tau_rng", ["philox", "mt19937"])
+def test_cli_random_select_branch(tmp_path, tau_rng):
+    """`-r 300`: Gibbs on 300 random positions, then factorize_tau + tau-only replay (updateTau) on the other 633
+    (bin/desman:181-206), collated outputs with the reference's layout."""
+    freq = tmp_path / "cog0015.freq"
+    _write_freq(str(freq))
+    out = tmp_path / "out"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "desman"), str(freq), "-g", "4", "-i", "15", "-r", "300",
+                        "-o", str(out), "--tau_rng", tau_rng], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    for name in ("fit.txt", "fitP.txt", "Collated_Tau_star.csv", "Collated_Tau_mean.csv", "Filtered_Tau_star.csv",
+                 "Gamma_star.csv", "Eta_star.csv", "Selected_variants.csv"):
+        assert (out / name).exists(), name
+    col = open(out / "Collated_Tau_star.csv").read().splitlines()
+    assert len(col) == 934 and col[0].startswith(",Position,0,1,2")
+    sel = open(out / "Filtered_Tau_star.csv").read().splitlines()
+    assert len(sel) == 301
+    tau = np.loadtxt(out / "Collated_Tau_star.csv", delimiter=",", skiprows=1, usecols=range(2, 2 + 16))
+    assert ((tau.reshape(933, 4, 4).sum(2)) == 1).all()                     # one-hot everywhere
+    mean = np.loadtxt(out / "Collated_Tau_mean.csv", delimiter=",", skiprows=1, usecols=range(2, 2 + 16))
+    assert np.allclose(mean.reshape(933, 4, 4).sum(2), 1.0, atol=1e-9)
+    fitp = open(out / "fitP.txt").read().strip().split(",")
+    assert fitp[0] == "Fit" and np.isfinite(float(fitp[3])) and float(fitp[4]) > 0
+    log = open(out / "log_file.txt").read()
+    assert "Perform NTF initialisation on not selected SNPs fixed gamma" in log and "nll =" in log
