@@ -194,10 +194,16 @@ def run_b200(args):
     peak, peak_src = measured_hbm_peak()
     dom = max(("tau_sample", "mu_stats"), key=lambda k: kms[k])
 
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if args.config == "c3" and os.path.exists(tpath):       # dram bytes per launch from the committed ncu --set full capture
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch", {})
+
     def roof(kernel):
         b = algorithmic_bytes(kernel, V, S, G)
         ach = b / (kms[kernel] * 1e-3) / 1e9
-        return dict(kernel=kernel, bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak, traffic=None,
+        return dict(kernel=kernel, bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
+                    traffic=traffic.get(kernel),
                     algorithmic_bytes=b, ms=kms[kernel], peak_source=peak_src)
     e.close()
 
