@@ -16,6 +16,7 @@
 #include "../../include/desman_b200.h"
 #include "common.cuh"
 #include "misc_kernels.cuh"
+#include "mu_agg_kernel.cuh"
 #include "mu_kernel.cuh"
 #include "nmft_kernel.cuh"
 #include "tau_kernel.cuh"
@@ -131,6 +132,11 @@ struct desman_ctx {
     uint32_t last_n_iter = 0;
     int tau_exact = 0;                       // 1: FP64 reference-order path for every draw
     int fixed_tau = 0;                       // 1: update() skips the tau draw (update_fixed_tau, HaploSNP_Sampler.py:409-428)
+    int mu_mode = 1;                         // 1: pattern-aggregated binomial statistics (K2b), 0: per-read categorical (K2)
+    unsigned long long *agg_keys = nullptr, *agg_code = nullptr, *agg_N = nullptr;
+    int *agg_ids = nullptr;
+    unsigned int *agg_nslots = nullptr;
+    size_t agg_H = 0, agg_cap_v = 0, agg_cap_cells = 0;
     unsigned long long *tiers = nullptr;     // [3] draws decided by tier 1/2/3
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     // scratch
@@ -235,6 +241,7 @@ extern "C" int desman_ctx_create(desman_ctx **out, int device, uint64_t seed, in
     CU(cudaMalloc(&c->tiers, 3 * sizeof(unsigned long long)));
     CU(cudaMemset(c->tiers, 0, 3 * sizeof(unsigned long long)));
     { const char *ex = getenv("DESMAN_B200_TAU_EXACT"); c->tau_exact = (ex && atoi(ex)) ? 1 : 0; }
+    { const char *mm = getenv("DESMAN_B200_MU_MODE"); if (mm) c->mu_mode = atoi(mm) ? 1 : 0; }
     CU(cudaMalloc(&c->mt_state, 624 * sizeof(uint32_t)));
     CU(cudaMemset(c->scal, 0, 4 * sizeof(double)));
     *out = c;
@@ -249,7 +256,7 @@ extern "C" int desman_ctx_destroy(desman_ctx *c)
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     void *ptrs[] = {c->counts, c->tau, c->tau_star, c->gamma, c->eta, c->eta_new, c->gamma_star, c->eta_star, c->stats,
                     c->nchange, c->ll_partial, c->red, c->scal, c->flag, c->tau_cnt, c->tau_last, c->mt_state, c->words,
-                    c->scratch, c->flush_buf, c->tiers};
+                    c->scratch, c->flush_buf, c->tiers, c->agg_keys, c->agg_code, c->agg_N, c->agg_ids, c->agg_nslots};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) if (c->pin_ev[i]) cudaEventDestroy(c->pin_ev[i]);
@@ -584,8 +591,56 @@ static void launch_mu_t(desman_ctx *c, const MuParams &p, int grid)
     mu_stats_kernel<GP><<<grid, MU_WARPS * 32, 0, c->stream>>>(p);
 }
 
+// K2b: aggregate the counts by haplotype pattern, then one conditional-binomial chain per (pattern, sample, base)
+static int launch_mu_agg(desman_ctx *c, const double *gamma, const double *eta)
+{
+    const size_t V = (size_t)c->V, cells = V * c->S * 4;
+    if (V > c->agg_cap_v || cells > c->agg_cap_cells) {
+        for (void *q : {(void *)c->agg_keys, (void *)c->agg_code, (void *)c->agg_N, (void *)c->agg_ids, (void *)c->agg_nslots}) if (q) cudaFree(q);
+        c->agg_keys = c->agg_code = c->agg_N = nullptr; c->agg_ids = nullptr; c->agg_nslots = nullptr;
+        c->agg_cap_v = c->agg_cap_cells = 0;
+        size_t H = 64;
+        while (H < 2 * V) H <<= 1;
+        CU(cudaMalloc(&c->agg_keys, H * sizeof(unsigned long long)));
+        CU(cudaMalloc(&c->agg_ids, H * sizeof(int)));
+        CU(cudaMalloc(&c->agg_code, V * sizeof(unsigned long long)));
+        CU(cudaMalloc(&c->agg_nslots, sizeof(unsigned int)));
+        CU(cudaMalloc(&c->agg_N, cells * sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(c->agg_N, 0, cells * sizeof(unsigned long long), c->stream));
+        c->agg_H = H; c->agg_cap_v = V; c->agg_cap_cells = cells;
+    }
+    MuAggParams p;
+    p.counts = c->counts; p.tau = c->tau; p.gamma = gamma; p.eta = eta;
+    p.seed = c->seed; p.sweep = c->sweep; p.shard = (uint32_t)c->v0;
+    p.V = (int)c->V; p.S = c->S; p.G = c->G;
+    p.keys = c->agg_keys; p.ids = c->agg_ids; p.hmask = (unsigned int)(c->agg_H - 1);
+    p.slot_code = c->agg_code; p.nslots = c->agg_nslots; p.N = c->agg_N;
+    p.sum_mu = c->stats; p.esum = c->stats + (size_t)c->S * c->G;
+    CU(cudaMemsetAsync(c->stats, 0, ((size_t)c->S * c->G + 16) * sizeof(unsigned long long), c->stream));
+    CU(cudaMemsetAsync(c->agg_keys, 0xff, c->agg_H * sizeof(unsigned long long), c->stream));
+    CU(cudaMemsetAsync(c->agg_ids, 0xff, c->agg_H * sizeof(int), c->stream));
+    CU(cudaMemsetAsync(c->agg_nslots, 0, sizeof(unsigned int), c->stream));
+    const int nch = (c->S + 31) / 32;
+    const size_t smem = mub_smem_bytes(c->G);
+    CU(cudaFuncSetAttribute(mu_binomial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mu_binomial_kernel, MUB_WARPS * 32, smem) != cudaSuccess || occ < 1) occ = 1;
+    int grid = c->sm_count * occ;
+    while ((grid * MUB_WARPS) % nch) grid++;
+    {
+        KSpan k(c, DESMAN_K_MU);
+        int64_t ablocks = (c->V + 7) / 8;
+        if (ablocks > (int64_t)c->sm_count * 8) ablocks = (int64_t)c->sm_count * 8;
+        mu_aggregate_kernel<<<(int)ablocks, 256, 0, c->stream>>>(p);
+        mu_binomial_kernel<<<grid, MUB_WARPS * 32, smem, c->stream>>>(p);
+    }
+    CU(cudaGetLastError());
+    return DESMAN_OK;
+}
+
 static int launch_mu(desman_ctx *c, const double *gamma, const double *eta)
 {
+    if (c->mu_mode == 1) return launch_mu_agg(c, gamma, eta);
     MuParams p;
     p.counts = c->counts; p.tau = c->tau; p.gamma = gamma; p.eta = eta;
     p.seed = c->seed; p.sweep = c->sweep; p.v0 = c->v0;
@@ -959,6 +1014,7 @@ extern "C" int desman_set_option(desman_ctx *c, const char *name, int64_t value)
     if (!c || !name) return fail(DESMAN_EINVAL, "desman_set_option: bad arguments");
     if (!strcmp(name, "tau_exact")) { c->tau_exact = value ? 1 : 0; return DESMAN_OK; }
     if (!strcmp(name, "fixed_tau")) { c->fixed_tau = value ? 1 : 0; return DESMAN_OK; }
+    if (!strcmp(name, "mu_mode")) { c->mu_mode = value ? 1 : 0; return DESMAN_OK; }
     return fail(DESMAN_EINVAL, "unknown option '%s'", name);
 }
 

@@ -1,0 +1,254 @@
+// desman_b200/csrc/mu_agg_kernel.cuh -- K2b: mu/E sufficient statistics, pattern-aggregated form
+// (replaces HaploSNP_Sampler.sampleMu, HaploSNP_Sampler.py:284-309, and the reductions at :266, :276).
+//
+// The per-read kernel (mu_kernel.cuh) spends one Philox word and G-1 compares on each of the ~V*S*depth reads
+// of a sweep (6.4e8 at BASELINE config C3) and is bound by integer issue.  But the category probabilities of a
+// read observed as base a in sample s depend on the site only through its haplotype pattern tau_v: reads of all
+// sites with the same pattern are exchangeable, and the sum of their multinomials is ONE multinomial with the summed
+// count.  So:
+//   mu_aggregate_kernel   one warp per site: hash the 2G-bit pattern code into a slot (open addressing, atomicCAS),
+//                         add the site's S count cells into N[slot][s][a] (64-bit reductions); one HBM pass
+//   mu_binomial_kernel    one warp per (slot, 32-sample chunk): per (s,a) a chain of conditional binomials over the
+//                         strains (what numpy's RandomState.multinomial does), each by inversion when
+//                         n*min(p,q) < 10 and by Hoermann's BTRS transformed rejection otherwise: O(1) per draw,
+//                         independent of the count
+// In a converged chain of biallelic sites the number of patterns is ~12*2^G (3e3 at G=8) << V, so the work drops
+// by the average number of sites per pattern; with all-distinct patterns it degrades to one chain per cell.
+// Draw contract: identical, operation for operation, to oracle_mu_stats_agg (oracle/desman_oracle.c); every
+// decision outside the three logs of the BTRS slow path is made with +,*,/,sqrt,floor in IEEE double without
+// contraction, so the integer statistics are reproducible between CPU and GPU.
+#pragma once
+#include "common.cuh"
+
+#define STAGE_MUB 7
+#define MUB_WARPS 8
+#define MUB_EMPTY 0xffffffffffffffffull
+
+struct MuAggParams {
+    const int4 *counts;          // [V][S]
+    const uint8_t *tau;          // [V][G]
+    const double *gamma;         // [S][G]
+    const double *eta;           // [16]
+    uint64_t seed;
+    uint32_t sweep;
+    uint32_t shard;              // global index of local site 0 (keys the streams of a rank's partial aggregates)
+    int V, S, G;
+    unsigned long long *keys;    // [H] pattern codes (MUB_EMPTY = free)
+    int *ids;                    // [H] slot id of the key (-1 until published)
+    unsigned int hmask;          // H - 1
+    unsigned long long *slot_code;   // [V]
+    unsigned int *nslots;        // number of slots in use
+    unsigned long long *N;       // [V slots][S][4] aggregated counts (left zeroed by the sampling kernel)
+    unsigned long long *sum_mu;  // [S][G] +=
+    unsigned long long *esum;    // [16]   += (esum[a_obs*4 + b_true])
+};
+
+__device__ __forceinline__ unsigned int mix_code(unsigned long long x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return (unsigned int)x;
+}
+
+__global__ void __launch_bounds__(256) mu_aggregate_kernel(MuAggParams p)
+{
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int v = gw; v < p.V; v += nw) {
+        const unsigned long long code = load_tau_code(p.tau + (size_t)v * p.G, p.G, lane);
+        int id = 0;
+        if (lane == 0) {
+            unsigned int h = mix_code(code) & p.hmask;
+            while (true) {
+                const unsigned long long prev = atomicCAS(p.keys + h, MUB_EMPTY, code);
+                if (prev == MUB_EMPTY) {                       // first site of this pattern: publish a new slot
+                    id = (int)atomicAdd(p.nslots, 1u);
+                    p.slot_code[id] = code;
+                    __threadfence();
+                    atomicExch(p.ids + h, id);
+                    break;
+                }
+                if (prev == code) {                            // known pattern: wait until its slot id is visible
+                    while ((id = *((volatile int *)(p.ids + h))) < 0) {}
+                    break;
+                }
+                h = (h + 1) & p.hmask;
+            }
+        }
+        id = __shfl_sync(DESMAN_FULL_MASK, id, 0);
+        unsigned long long *dst = p.N + (size_t)id * p.S * 4;
+        const int4 *src = p.counts + (size_t)v * p.S;
+        for (int s = lane; s < p.S; s += 32) {
+            const int4 n = ld_counts(src + s);
+            if (n.x) atomicAdd(dst + s * 4 + 0, (unsigned long long)n.x);
+            if (n.y) atomicAdd(dst + s * 4 + 1, (unsigned long long)n.y);
+            if (n.z) atomicAdd(dst + s * 4 + 2, (unsigned long long)n.z);
+            if (n.w) atomicAdd(dst + s * 4 + 3, (unsigned long long)n.w);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double mub_u53(uint32_t hi, uint32_t lo)
+{
+    const unsigned long long m = ((unsigned long long)(hi >> 5) << 26) | (unsigned long long)(lo >> 6);
+    return __dmul_rn(__dadd_rn((double)m, 0.5), 1.0 / 9007199254740992.0);
+}
+
+__device__ double stirling_tail_d(double k)
+{
+    if (k <= 9.0) {
+        const int i = (int)k;
+        return i == 0 ? 0.0810614667953272 : i == 1 ? 0.0413406959554092 : i == 2 ? 0.0276779256849983 :
+               i == 3 ? 0.02079067210376509 : i == 4 ? 0.0166446911898211 : i == 5 ? 0.0138761288230707 :
+               i == 6 ? 0.0118967099458917 : i == 7 ? 0.0104112652619720 : i == 8 ? 0.00925546218271273 :
+                        0.00833056343336287;
+    }
+    const double kp1 = __dadd_rn(k, 1.0), kp1sq = __dmul_rn(kp1, kp1);
+    return __ddiv_rn(__dadd_rn(1.0 / 12.0, -__ddiv_rn(__dadd_rn(1.0 / 360.0, -__ddiv_rn(1.0 / 1260.0, kp1sq)), kp1sq)), kp1);
+}
+
+struct BinStream { uint32_t c0, c1, c2, c3, k0, k1; };
+
+__device__ __forceinline__ void bin_uniforms_d(const BinStream &st, int g, uint32_t attempt, double &u1, double &u2)
+{
+    const uint4 o = philox4x32_10(st.c0, st.c1, st.c2, st.c3, st.k0 ^ (((uint32_t)(g + 1) << 20) | attempt), st.k1);
+    u1 = mub_u53(o.x, o.y);
+    u2 = mub_u53(o.z, o.w);
+}
+
+// Bin(n, p) with q = 1-p supplied separately.  Mirrors binomial_draw() of oracle/desman_oracle.c step for step.
+__device__ __noinline__ long long binomial_draw_d(long long n, double p, double q, const BinStream &st, int g)
+{
+    if (n <= 0 || !(p > 0.0)) return 0;
+    if (!(q > 0.0)) return n;
+    const bool flip = p > q;
+    const double pp = flip ? q : p, qq = flip ? p : q;
+    const double dn = (double)n;
+    long long x;
+    if (__dmul_rn(dn, pp) < 10.0) {
+        double r = 1.0, base = qq;
+        for (long long e = n; e; e >>= 1) { if (e & 1) r = __dmul_rn(r, base); base = __dmul_rn(base, base); }
+        const double s = __ddiv_rn(pp, qq);
+        double u, dummy;
+        bin_uniforms_d(st, g, 0u, u, dummy);
+        x = 0;
+        while (u >= r) {
+            u = __dadd_rn(u, -r);
+            x++;
+            if (x > n) { x = n; break; }
+            r = __ddiv_rn(__dmul_rn(r, __dmul_rn(s, (double)(n - x + 1))), (double)x);
+            if (x > 4096) break;
+        }
+    } else {
+        const double spq = __dsqrt_rn(__dmul_rn(__dmul_rn(dn, pp), qq));
+        const double b = __dadd_rn(1.15, __dmul_rn(2.53, spq));
+        const double a = __dadd_rn(__dadd_rn(-0.0873, __dmul_rn(0.0248, b)), __dmul_rn(0.01, pp));
+        const double c = __dadd_rn(__dmul_rn(dn, pp), 0.5);
+        const double vr = __dadd_rn(0.92, -__ddiv_rn(4.2, b));
+        const double r = __ddiv_rn(pp, qq);
+        const double alpha = __dmul_rn(__dadd_rn(2.83, __ddiv_rn(5.1, b)), spq);
+        const double m = floor(__dmul_rn(__dadd_rn(dn, 1.0), pp));
+        double k = m;
+        for (uint32_t t = 0; t < (1u << 20); t++) {
+            double u1, v;
+            bin_uniforms_d(st, g, t, u1, v);
+            const double u = __dadd_rn(u1, -0.5);
+            const double us = __dadd_rn(0.5, -fabs(u));
+            k = floor(__dadd_rn(__dmul_rn(__dadd_rn(__ddiv_rn(__dmul_rn(2.0, a), us), b), u), c));
+            if (us >= 0.07 && v <= vr) break;
+            if (k < 0.0 || k > dn) continue;
+            const double lv = log(__ddiv_rn(__dmul_rn(v, alpha), __dadd_rn(__ddiv_rn(a, __dmul_rn(us, us)), b)));
+            const double nm1 = __dadd_rn(__dadd_rn(dn, -m), 1.0), nk1 = __dadd_rn(__dadd_rn(dn, -k), 1.0);
+            double ub = __dmul_rn(__dadd_rn(m, 0.5), log(__ddiv_rn(__dadd_rn(m, 1.0), __dmul_rn(r, nm1))));
+            ub = __dadd_rn(ub, __dmul_rn(__dadd_rn(dn, 1.0), log(__ddiv_rn(nm1, nk1))));
+            ub = __dadd_rn(ub, __dmul_rn(__dadd_rn(k, 0.5), log(__ddiv_rn(__dmul_rn(r, nk1), __dadd_rn(k, 1.0)))));
+            ub = __dadd_rn(ub, stirling_tail_d(m));
+            ub = __dadd_rn(ub, stirling_tail_d(__dadd_rn(dn, -m)));
+            ub = __dadd_rn(ub, -stirling_tail_d(k));
+            ub = __dadd_rn(ub, -stirling_tail_d(__dadd_rn(dn, -k)));
+            if (lv <= ub) break;
+        }
+        if (k < 0.0) k = 0.0;
+        if (k > dn) k = dn;
+        x = (long long)k;
+    }
+    return flip ? n - x : x;
+}
+
+// shared memory per warp: w[G][32], suf[G+1][32] (double), acc[G][32], E[16][32] (unsigned long long)
+static inline size_t mub_smem_bytes(int G) { return (size_t)MUB_WARPS * 32 * 8 * (size_t)(3 * G + 1 + 16) + 16 * 8; }
+
+__global__ void __launch_bounds__(MUB_WARPS * 32) mu_binomial_kernel(MuAggParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = p.S, G = p.G;
+    double *eta_s = reinterpret_cast<double *>(smem_raw);                    // [16]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *wS = eta_s + 16 + (size_t)wib * 32 * (3 * G + 1 + 16);            // [G][32]
+    double *sufS = wS + G * 32;                                              // [G+1][32]
+    unsigned long long *accS = reinterpret_cast<unsigned long long *>(sufS + (G + 1) * 32);   // [G][32]
+    unsigned long long *eS = accS + G * 32;                                  // [16][32]
+    if (threadIdx.x < 16) eta_s[threadIdx.x] = p.eta[threadIdx.x];
+    for (int i = lane; i < (G + 16) * 32; i += 32) accS[i] = 0ull;
+    __syncthreads();
+
+    const int nch = (S + 31) >> 5;
+    const int gw = blockIdx.x * MUB_WARPS + wib, nw = gridDim.x * MUB_WARPS;      // nw % nch == 0 (host)
+    const int chunk = gw % nch, s = chunk * 32 + lane;
+    const bool valid = s < S;
+    const int P = (int)*p.nslots;
+    BinStream st;
+    st.c2 = p.sweep; st.k0 = (uint32_t)p.seed; st.k1 = (uint32_t)(p.seed >> 32) ^ p.shard;
+
+    for (int slot = gw / nch; slot < P; slot += nw / nch) {
+        const unsigned long long code = p.slot_code[slot];
+        st.c0 = (uint32_t)code; st.c1 = (uint32_t)(code >> 32);
+        unsigned long long n4[4] = {0ull, 0ull, 0ull, 0ull};
+        if (valid) {
+            ulonglong2 *src = reinterpret_cast<ulonglong2 *>(p.N + ((size_t)slot * S + s) * 4);
+            const ulonglong2 lo = src[0], hi = src[1];
+            n4[0] = lo.x; n4[1] = lo.y; n4[2] = hi.x; n4[3] = hi.y;
+            src[0] = make_ulonglong2(0ull, 0ull); src[1] = make_ulonglong2(0ull, 0ull);   // leave the table clean
+        }
+#pragma unroll 1
+        for (int a = 0; a < 4; a++) {
+            const long long n = (long long)(a == 0 ? n4[0] : a == 1 ? n4[1] : a == 2 ? n4[2] : n4[3]);
+            if (n <= 0) continue;
+            st.c3 = ((uint32_t)STAGE_MUB << 28) | ((uint32_t)a << 26) | (uint32_t)s;
+            // weights and suffix sums (descending, rounded adds)
+            double suf = 0.0;
+            sufS[G * 32 + lane] = 0.0;
+            for (int g = G - 1; g >= 0; g--) {
+                const double w = __dmul_rn(p.gamma[(size_t)s * G + g], eta_s[4 * code_get(code, g) + a]);
+                suf = __dadd_rn(w, suf);
+                wS[g * 32 + lane] = w;
+                sufS[g * 32 + lane] = suf;
+            }
+            long long rem = n;
+            for (int g = 0; g < G; g++) {
+                long long x;
+                if (g == G - 1) x = rem;
+                else if (rem == 0) x = 0;
+                else {
+                    const double sg = sufS[g * 32 + lane];
+                    x = binomial_draw_d(rem, __ddiv_rn(wS[g * 32 + lane], sg), __ddiv_rn(sufS[(g + 1) * 32 + lane], sg), st, g);
+                }
+                rem -= x;
+                if (x) {
+                    accS[g * 32 + lane] += (unsigned long long)x;
+                    eS[(a * 4 + code_get(code, g)) * 32 + lane] += (unsigned long long)x;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (valid)
+        for (int g = 0; g < G; g++) {
+            const unsigned long long x = accS[g * 32 + lane];
+            if (x) atomicAdd(p.sum_mu + (size_t)s * G + g, x);
+        }
+    for (int i = 0; i < 16; i++) {
+        const unsigned long long t = warp_sum_u64(eS[i * 32 + lane]);
+        if (lane == 0 && t) atomicAdd(p.esum + i, t);
+    }
+}

@@ -291,6 +291,181 @@ void oracle_mu_stats(const int64_t *tau, const double *gamma, const double *eta,
     }
 }
 
+/* ------------------------------------------------------------------------ */
+/* Aggregated form of the same statistics ("pattern" contract).
+ * Reads of cells (v,s,a) whose sites carry the SAME haplotype pattern tau_v have identical category
+ * probabilities and are exchangeable, so their multinomials add up to ONE multinomial with the summed
+ * count N[pattern][s][a].  That multinomial is drawn as a chain of conditional binomials in ascending g
+ * (the construction numpy's RandomState.multinomial itself uses), each binomial by inversion when
+ * n*min(p,q) < 10 and by Hoermann's BTRS transformed rejection otherwise.
+ *   weights   w_g = gamma[s,g]*eta[tau_g,a]; suffix sums suf_g = w_g + suf_{g+1} (descending, rounded adds)
+ *   draw g    X_g ~ Bin(n_rem, p = w_g/suf_g) with q = suf_{g+1}/suf_g;  X_{G-1} = n_rem
+ *   uniforms  attempt t of draw (pattern code, s, a, g): Philox(ctr = (code_lo, code_hi, sweep,
+ *             STAGE_MUB<<28 | a<<26 | s), key = (seed_lo ^ ((g+1)<<20 | t), seed_hi ^ shard)):
+ *             U1 = u53(w0,w1), U2 = u53(w2,w3)
+ * All arithmetic outside the three logs of the BTRS slow path is +,*,/,sqrt,floor in IEEE double without
+ * contraction, identical in the CUDA kernel. */
+#define ORACLE_STAGE_MUB 7
+
+static inline double u53w(uint32_t hi, uint32_t lo)
+{
+    uint64_t m = ((uint64_t)(hi >> 5) << 26) | (uint64_t)(lo >> 6);
+    return ((double)m + 0.5) * (1.0 / 9007199254740992.0);
+}
+
+static double stirling_tail(double k)
+{
+    static const double t[10] = {0.0810614667953272, 0.0413406959554092, 0.0276779256849983, 0.02079067210376509,
+                                 0.0166446911898211, 0.0138761288230707, 0.0118967099458917, 0.0104112652619720,
+                                 0.00925546218271273, 0.00833056343336287};
+    if (k <= 9.0) return t[(int)k];
+    double kp1 = k + 1.0, kp1sq = kp1 * kp1;
+    return (1.0 / 12.0 - (1.0 / 360.0 - 1.0 / 1260.0 / kp1sq) / kp1sq) / kp1;
+}
+
+typedef struct { uint32_t c0, c1, c2, c3; uint64_t seed; uint32_t shard; int g; } bin_stream;
+
+static void bin_uniforms(const bin_stream *st, uint32_t attempt, double *u1, double *u2)
+{
+    uint32_t ctr[4] = {st->c0, st->c1, st->c2, st->c3};
+    uint32_t key[2] = {(uint32_t)st->seed ^ (((uint32_t)(st->g + 1) << 20) | attempt), (uint32_t)(st->seed >> 32) ^ st->shard};
+    uint32_t o[4];
+    oracle_philox4x32_10(ctr, key, o);
+    *u1 = u53w(o[0], o[1]);
+    *u2 = u53w(o[2], o[3]);
+}
+
+/* Bin(n, p) with q = 1-p supplied separately (no cancellation).  n >= 0. */
+static int64_t binomial_draw(int64_t n, double p, double q, const bin_stream *st)
+{
+    if (n <= 0 || !(p > 0.0)) return 0;
+    if (!(q > 0.0)) return n;
+    const int flip = p > q;
+    const double pp = flip ? q : p, qq = flip ? p : q;
+    const double dn = (double)n;
+    int64_t x;
+    if (dn * pp < 10.0) {
+        /* inversion: r = qq^n by binary powering, then sequential search */
+        double r = 1.0, base = qq;
+        for (int64_t e = n; e; e >>= 1) { if (e & 1) r = r * base; base = base * base; }
+        const double s = pp / qq;
+        double u, dummy;
+        bin_uniforms(st, 0, &u, &dummy);
+        x = 0;
+        while (u >= r) {
+            u = u - r;
+            x++;
+            if (x > n) { x = n; break; }
+            r = (r * (s * (double)(n - x + 1))) / (double)x;
+            if (x > 4096) break;        /* numerical guard: mass beyond here is < 1e-300 */
+        }
+    } else {
+        /* BTRS (Hoermann 1993) */
+        const double spq = sqrt(dn * pp * qq);
+        const double b = 1.15 + 2.53 * spq;
+        const double a = -0.0873 + 0.0248 * b + 0.01 * pp;
+        const double c = dn * pp + 0.5;
+        const double vr = 0.92 - 4.2 / b;
+        const double r = pp / qq;
+        const double alpha = (2.83 + 5.1 / b) * spq;
+        const double m = floor((dn + 1.0) * pp);
+        double k = m;
+        for (uint32_t t = 0; t < (1u << 20); t++) {
+            double u1, v;
+            bin_uniforms(st, t, &u1, &v);
+            const double u = u1 - 0.5;
+            const double us = 0.5 - fabs(u);
+            k = floor((2.0 * a / us + b) * u + c);
+            if (us >= 0.07 && v <= vr) break;
+            if (k < 0.0 || k > dn) continue;
+            const double lv = log(v * alpha / (a / (us * us) + b));
+            const double ub = (m + 0.5) * log((m + 1.0) / (r * (dn - m + 1.0))) +
+                              (dn + 1.0) * log((dn - m + 1.0) / (dn - k + 1.0)) +
+                              (k + 0.5) * log(r * (dn - k + 1.0) / (k + 1.0)) +
+                              stirling_tail(m) + stirling_tail(dn - m) - stirling_tail(k) - stirling_tail(dn - k);
+            if (lv <= ub) break;
+        }
+        if (k < 0.0) k = 0.0;
+        if (k > dn) k = dn;
+        x = (int64_t)k;
+    }
+    return flip ? n - x : x;
+}
+
+static int cmp_u64(const void *a, const void *b)
+{
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return x < y ? -1 : x > y;
+}
+
+void oracle_mu_stats_agg(const int64_t *tau, const double *gamma, const double *eta,
+                         const int64_t *variants, int V, int G, int S,
+                         uint64_t seed, uint32_t sweep, int64_t v0,
+                         int64_t *sum_mu, int64_t *esum)
+{
+    /* pattern code of every site: 2 bits per strain */
+    uint64_t *code = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(V ? V : 1));
+    uint64_t *uniq = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)(V ? V : 1));
+    for (int v = 0; v < V; v++) {
+        uint64_t c = 0;
+        for (int g = 0; g < G; g++) {
+            int idx = 0;
+            for (int b = 0; b < 4; b++) if (tau[((size_t)v * G + g) * 4 + b] == 1) { idx = b; break; }
+            c |= (uint64_t)idx << (2 * g);
+        }
+        code[v] = c; uniq[v] = c;
+    }
+    qsort(uniq, (size_t)V, sizeof(uint64_t), cmp_u64);
+    int P = 0;
+    for (int v = 0; v < V; v++) if (v == 0 || uniq[v] != uniq[v - 1]) uniq[P++] = uniq[v];
+    int64_t *N = (int64_t *)calloc((size_t)(P ? P : 1) * S * 4, sizeof(int64_t));
+    for (int v = 0; v < V; v++) {
+        uint64_t *hit = (uint64_t *)bsearch(&code[v], uniq, (size_t)P, sizeof(uint64_t), cmp_u64);
+        int64_t *dst = N + (size_t)(hit - uniq) * S * 4;
+        const int64_t *src = variants + (size_t)v * S * 4;
+        for (int i = 0; i < S * 4; i++) dst[i] += src[i];
+    }
+#pragma omp parallel
+    {
+        int64_t *lmu = (int64_t *)calloc((size_t)S * G + 16, sizeof(int64_t));
+        int64_t *le = lmu + (size_t)S * G;
+        double w[64], suf[65];
+#pragma omp for schedule(dynamic, 8)
+        for (int pi = 0; pi < P; pi++) {
+            const uint64_t c = uniq[pi];
+            for (int s = 0; s < S; s++)
+                for (int a = 0; a < 4; a++) {
+                    int64_t n = N[((size_t)pi * S + s) * 4 + a];
+                    if (n <= 0) continue;
+                    for (int g = 0; g < G; g++) w[g] = gamma[s * G + g] * eta[((c >> (2 * g)) & 3) * 4 + a];
+                    suf[G] = 0.0;
+                    for (int g = G - 1; g >= 0; g--) suf[g] = w[g] + suf[g + 1];
+                    bin_stream st;
+                    st.c0 = (uint32_t)c; st.c1 = (uint32_t)(c >> 32); st.c2 = sweep;
+                    st.c3 = ((uint32_t)ORACLE_STAGE_MUB << 28) | ((uint32_t)a << 26) | (uint32_t)s;
+                    st.seed = seed; st.shard = (uint32_t)v0;
+                    int64_t rem = n;
+                    for (int g = 0; g < G; g++) {
+                        int64_t x;
+                        if (g == G - 1) x = rem;
+                        else if (rem == 0) x = 0;
+                        else { st.g = g; x = binomial_draw(rem, w[g] / suf[g], suf[g + 1] / suf[g], &st); }
+                        rem -= x;
+                        lmu[s * G + g] += x;
+                        le[a * 4 + (int)((c >> (2 * g)) & 3)] += x;
+                    }
+                }
+        }
+#pragma omp critical
+        {
+            for (size_t i = 0; i < (size_t)S * G; i++) sum_mu[i] += lmu[i];
+            for (int i = 0; i < 16; i++) esum[i] += le[i];
+        }
+        free(lmu);
+    }
+    free(code); free(uniq); free(N);
+}
+
 /* ======================================================================== */
 /* gamma / eta draws  (HaploSNP_Sampler.py:263-281)                          */
 /* ======================================================================== */
@@ -471,7 +646,8 @@ void oracle_update(const oracle_chain_cfg *cfg, int64_t *tau, double *gamma, dou
         uint32_t sweep = cfg->sweep0 + (uint32_t)it;
         memset(sum_mu, 0, sizeof(int64_t) * ng);
         memset(esum, 0, sizeof(esum));
-        oracle_mu_stats(tau, gamma, eta, variants, V, G, S, cfg->seed, sweep, 0, sum_mu, esum);
+        if (cfg->mu_mode == 1) oracle_mu_stats_agg(tau, gamma, eta, variants, V, G, S, cfg->seed, sweep, 0, sum_mu, esum);
+        else oracle_mu_stats(tau, gamma, eta, variants, V, G, S, cfg->seed, sweep, 0, sum_mu, esum);
         oracle_draw_gamma(sum_mu, S, G, cfg->alpha, cfg->epsilon, cfg->seed, sweep, gamma);
         int nchange = oracle_sample_tau_philox(tau, gamma, eta, variants, V, G, S, cfg->seed, sweep, 0);
         oracle_draw_eta(esum, cfg->delta, cfg->seed, sweep, eta);

@@ -60,6 +60,12 @@ void oracle_mu_stats(const int64_t *tau, const double *gamma, const double *eta,
                      uint64_t seed, uint32_t sweep, int64_t v0,
                      int64_t *sum_mu, int64_t *esum);
 
+/* same statistics under the pattern-aggregated conditional-binomial contract (see desman_oracle.c) */
+void oracle_mu_stats_agg(const int64_t *tau, const double *gamma, const double *eta,
+                         const int64_t *variants, int V, int G, int S,
+                         uint64_t seed, uint32_t sweep, int64_t v0,
+                         int64_t *sum_mu, int64_t *esum);
+
 /* ---- gamma / eta Dirichlet draws (HaploSNP_Sampler.py:263-281) ----------- */
 void oracle_draw_gamma(const int64_t *sum_mu, int S, int G, double alpha, double epsilon,
                        uint64_t seed, uint32_t sweep, double *gamma);
@@ -79,6 +85,7 @@ typedef struct {
     double alpha, delta, epsilon;
     uint64_t seed;
     uint32_t sweep0;
+    int mu_mode;   /* 0: per-read categorical contract, 1: pattern-aggregated binomial contract */
 } oracle_chain_cfg;
 /* Runs n_iter sweeps in place.  Outputs (any may be NULL): gamma_store[n_iter*S*G],
  * eta_store[n_iter*16], ll_store[n_iter], lp_store[n_iter], nchange_store[n_iter],

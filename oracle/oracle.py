@@ -45,7 +45,7 @@ class MT19937(C.Structure):
 class ChainCfg(C.Structure):
     _fields_ = [("V", C.c_int), ("G", C.c_int), ("S", C.c_int), ("n_iter", C.c_int),
                 ("alpha", C.c_double), ("delta", C.c_double), ("epsilon", C.c_double),
-                ("seed", C.c_uint64), ("sweep0", C.c_uint32)]
+                ("seed", C.c_uint64), ("sweep0", C.c_uint32), ("mu_mode", C.c_int)]
 
 
 def lib():
@@ -68,6 +68,7 @@ def lib():
         L.oracle_tau_step_probs.argtypes = [_p64, _pd, _pd, _p64, C.c_int, C.c_int, C.c_int, _pd, _pd]
         L.oracle_mu_stats.argtypes = [_p64, _pd, _pd, _p64, C.c_int, C.c_int, C.c_int,
                                       C.c_uint64, C.c_uint32, C.c_int64, _p64, _p64]
+        L.oracle_mu_stats_agg.argtypes = L.oracle_mu_stats.argtypes
         L.oracle_draw_gamma.argtypes = [_p64, C.c_int, C.c_int, C.c_double, C.c_double,
                                         C.c_uint64, C.c_uint32, _pd]
         L.oracle_draw_eta.argtypes = [_p64, C.c_double, C.c_uint64, C.c_uint32, _pd]
@@ -212,7 +213,7 @@ def tau_step_probs(tau_index_v, pi, eta, variants_v, g):
 
 
 # ---------------------------------------------------------------- sweep pieces
-def mu_stats(tau, gamma, eta, variants, seed, sweep, v0=0):
+def mu_stats(tau, gamma, eta, variants, seed, sweep, v0=0, mode=0):
     V, G = tau.shape[0], tau.shape[1]
     S = gamma.shape[0]
     tau, pt = _i64(tau)
@@ -221,8 +222,8 @@ def mu_stats(tau, gamma, eta, variants, seed, sweep, v0=0):
     variants, pv = _i64(variants)
     sum_mu = np.zeros((S, G), dtype=np.int64)
     esum = np.zeros((4, 4), dtype=np.int64)
-    lib().oracle_mu_stats(pt, pg, pe, pv, V, G, S, seed, sweep, v0,
-                          sum_mu.ctypes.data_as(_p64), esum.ctypes.data_as(_p64))
+    fn = lib().oracle_mu_stats_agg if mode == 1 else lib().oracle_mu_stats
+    fn(pt, pg, pe, pv, V, G, S, seed, sweep, v0, sum_mu.ctypes.data_as(_p64), esum.ctypes.data_as(_p64))
     return sum_mu, esum
 
 
@@ -266,7 +267,7 @@ def logpost(tau, gamma, eta, variants, alpha=0.1, delta=0.1):
     return loglik(tau, gamma, eta, variants) + logprior(gamma, eta, tau.shape[0], alpha, delta)
 
 
-def update(tau, gamma, eta, variants, n_iter, seed, sweep0=0, alpha=0.1, delta=0.1, epsilon=1e-6):
+def update(tau, gamma, eta, variants, n_iter, seed, sweep0=0, alpha=0.1, delta=0.1, epsilon=1e-6, mu_mode=0):
     """Runs the restated update() chain; returns a dict of outputs (inputs are copied)."""
     tau = np.array(tau, dtype=np.int64, order="C")
     gamma = np.array(gamma, dtype=np.float64, order="C")
@@ -274,7 +275,7 @@ def update(tau, gamma, eta, variants, n_iter, seed, sweep0=0, alpha=0.1, delta=0
     variants, pv = _i64(variants)
     V, G = tau.shape[0], tau.shape[1]
     S = gamma.shape[0]
-    cfg = ChainCfg(V, G, S, n_iter, alpha, delta, epsilon, seed, sweep0)
+    cfg = ChainCfg(V, G, S, n_iter, alpha, delta, epsilon, seed, sweep0, mu_mode)
     out = dict(
         gamma_store=np.zeros((n_iter, S, G)), eta_store=np.zeros((n_iter, 4, 4)),
         ll_store=np.zeros(n_iter), lp_store=np.zeros(n_iter), nchange=np.zeros(n_iter, dtype=np.int64),
@@ -303,7 +304,7 @@ def update_tau(tau, gamma_store, eta_store, variants, seed, sweep0=0, use_mt=Fal
     variants, pv = _i64(variants)
     n_iter, S, G = gamma_store.shape
     V = tau.shape[0]
-    cfg = ChainCfg(V, G, S, n_iter, alpha, delta, 1e-6, seed, sweep0)
+    cfg = ChainCfg(V, G, S, n_iter, alpha, delta, 1e-6, seed, sweep0, 0)
     out = dict(ll_store=np.zeros(n_iter), lp_store=np.zeros(n_iter), nchange=np.zeros(n_iter, dtype=np.int64),
                tau_sum=np.zeros((V, G, 4), dtype=np.int64), tau_star=np.zeros((V, G, 4), dtype=np.int64))
     lp_star = C.c_double(0.0)

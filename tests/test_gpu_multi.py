@@ -24,6 +24,7 @@ dist.init_process_group("nccl")
 p = synth_problem(4001, 64, 8, depth=30.0, seed=9, ambiguous=True)
 lo, hi = shard_bounds(4001, rank, world)
 e = engine.Engine(rank, seed=4242)
+e.set_option("mu_mode", 0)   # per-read contract: statistics independent of how the sites are sharded
 e.set_counts(p["counts"][lo:hi], v0=lo, V_total=4001)
 e.comm_init(exchange_unique_id(dist, engine.Engine.comm_unique_id), rank, world)
 e.set_state(onehot(p["tau0"][lo:hi]), p["gamma0"], p["eta0"])
@@ -50,6 +51,7 @@ def test_two_gpu_sharded_update_equals_one_gpu(tmp_path):
     assert r.returncode == 0, r.stderr[-3000:]
     p = synth_problem(4001, 64, 8, depth=30.0, seed=9, ambiguous=True)
     e = engine.Engine(0, seed=4242)
+    e.set_option("mu_mode", 0)
     e.set_counts(p["counts"])
     e.set_state(onehot(p["tau0"]), p["gamma0"], p["eta0"])
     one = e.update(8)

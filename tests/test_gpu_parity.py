@@ -112,19 +112,23 @@ def test_tau_philox_bit_exact_vs_oracle(eng_mod, oracle_mod, V, S, G):
     e.close()
 
 
+@pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("V,S,G", SHAPES)
-def test_mu_stats_bit_exact_vs_oracle(eng_mod, oracle_mod, V, S, G):
+def test_mu_stats_bit_exact_vs_oracle(eng_mod, oracle_mod, V, S, G, mode):
+    """mode 0: one categorical draw per read; mode 1 (default): pattern-aggregated conditional binomials."""
     p = synth_problem(V, S, G, depth=40.0, seed=V + G)
     p["counts"][0] = 0
     p["counts"][1, :, 2] = 777
+    p["tau0"][V // 2:] = p["tau0"][V // 2]                      # many sites share a pattern -> large aggregated counts
     eta = 0.9 * np.identity(4) + 0.025
     e = eng_mod.Engine(0, seed=2024, rng_mode=eng_mod.RNG_PHILOX)
+    e.set_option("mu_mode", mode)
     e.set_counts(p["counts"])
     e.set_state(onehot(p["tau0"]), p["gamma0"], eta)
     for sweep in (0, 5):
         e.set_rng(2024, sweep=sweep)
         sm, es = e.mu_stats()
-        sm_o, es_o = oracle_mod.mu_stats(onehot(p["tau0"]), p["gamma0"], eta, p["counts"], 2024, sweep)
+        sm_o, es_o = oracle_mod.mu_stats(onehot(p["tau0"]), p["gamma0"], eta, p["counts"], 2024, sweep, mode=mode)
         assert np.array_equal(sm, sm_o)
         assert np.array_equal(es, es_o)
         assert sm.sum() == p["counts"].sum()
@@ -138,6 +142,7 @@ def test_mu_stats_sharded_offsets_equal_whole(eng_mod, oracle_mod):
     acc_sm, acc_es = 0, 0
     for lo, hi in ((0, 41), (41, 90)):
         e = eng_mod.Engine(0, seed=9)
+        e.set_option("mu_mode", 0)
         e.set_counts(p["counts"][lo:hi], v0=lo, V_total=90)
         e.set_state(onehot(p["tau0"][lo:hi]), p["gamma0"], p["eta0"])
         e.set_rng(9, sweep=4)
@@ -145,6 +150,16 @@ def test_mu_stats_sharded_offsets_equal_whole(eng_mod, oracle_mod):
         acc_sm, acc_es = acc_sm + sm, acc_es + es
         e.close()
     assert np.array_equal(acc_sm, whole[0]) and np.array_equal(acc_es, whole[1])
+    # aggregated mode: a shard's streams are keyed by its first global site; each shard equals the oracle's shard
+    for lo, hi in ((0, 41), (41, 90)):
+        e = eng_mod.Engine(0, seed=9)
+        e.set_counts(p["counts"][lo:hi], v0=lo, V_total=90)
+        e.set_state(onehot(p["tau0"][lo:hi]), p["gamma0"], p["eta0"])
+        e.set_rng(9, sweep=4)
+        sm, es = e.mu_stats()
+        want = oracle_mod.mu_stats(onehot(p["tau0"][lo:hi]), p["gamma0"], p["eta0"], p["counts"][lo:hi], 9, 4, v0=lo, mode=1)
+        assert np.array_equal(sm, want[0]) and np.array_equal(es, want[1])
+        e.close()
 
 
 @pytest.mark.parametrize("S,G", [(1, 1), (5, 3), (64, 8), (256, 16), (128, 20)])
@@ -182,12 +197,15 @@ def test_loglik_vs_reference_python_golden(eng_mod, oracle_mod):
 
 
 # ------------------------------------------------------------------ chains vs oracle
-@pytest.mark.parametrize("V,S,G,depth,n_iter", [(120, 16, 3, 30.0, 25), (300, 64, 8, 20.0, 12), (64, 130, 12, 8.0, 6)])
-def test_update_chain_vs_oracle(eng_mod, oracle_mod, V, S, G, depth, n_iter):
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("V,S,G,depth,n_iter", [(120, 16, 3, 30.0, 25), (300, 64, 8, 20.0, 12), (64, 130, 12, 8.0, 6),
+                                                  (2000, 64, 5, 60.0, 10)])
+def test_update_chain_vs_oracle(eng_mod, oracle_mod, V, S, G, depth, n_iter, mode):
     p = synth_problem(V, S, G, depth=depth, seed=11 + G, ambiguous=True)
     seed = 23724839
-    want = oracle_mod.update(onehot(p["tau0"]), p["gamma0"], p["eta0"], p["counts"], n_iter, seed, sweep0=3)
+    want = oracle_mod.update(onehot(p["tau0"]), p["gamma0"], p["eta0"], p["counts"], n_iter, seed, sweep0=3, mu_mode=mode)
     e = eng_mod.Engine(0, seed=seed)
+    e.set_option("mu_mode", mode)
     e.set_counts(p["counts"])
     e.set_state(onehot(p["tau0"]), p["gamma0"], p["eta0"])
     e.set_rng(seed, sweep=3)
@@ -208,7 +226,7 @@ def test_update_chain_vs_oracle(eng_mod, oracle_mod, V, S, G, depth, n_iter):
     assert rel(star["gamma"], want["gamma_star"]) < RTOL_TIGHT and rel(star["eta"], want["eta_star"]) < RTOL_TIGHT
     assert want["nchange"].sum() > 0 and e.get_rng()[0] == 3 + n_iter
     # second update() continues the stream exactly like one long chain split in two
-    want2 = oracle_mod.update(want["tau"], want["gamma"], want["eta"], p["counts"], 3, seed, sweep0=3 + n_iter)
+    want2 = oracle_mod.update(want["tau"], want["gamma"], want["eta"], p["counts"], 3, seed, sweep0=3 + n_iter, mu_mode=mode)
     got2 = e.update(3)
     assert np.array_equal(got2["nchange"], want2["nchange"])
     assert np.array_equal(e.get_state()[0], want2["tau"])
