@@ -200,44 +200,42 @@ __global__ void __launch_bounds__(MUB_WARPS * 32) mu_binomial_kernel(MuAggParams
     BinStream st;
     st.c2 = p.sweep; st.k0 = (uint32_t)p.seed; st.k1 = (uint32_t)(p.seed >> 32) ^ p.shard;
 
-    for (int slot = gw / nch; slot < P; slot += nw / nch) {
+    // work item = (slot, base a) for this warp's sample chunk: 4x more, 4x smaller items than one per slot, which
+    // matters because the number of patterns P can be a few thousand only
+    for (int item = gw / nch; item < 4 * P; item += nw / nch) {
+        const int slot = item >> 2, a = item & 3;
         const unsigned long long code = p.slot_code[slot];
         st.c0 = (uint32_t)code; st.c1 = (uint32_t)(code >> 32);
-        unsigned long long n4[4] = {0ull, 0ull, 0ull, 0ull};
+        long long n = 0;
         if (valid) {
-            ulonglong2 *src = reinterpret_cast<ulonglong2 *>(p.N + ((size_t)slot * S + s) * 4);
-            const ulonglong2 lo = src[0], hi = src[1];
-            n4[0] = lo.x; n4[1] = lo.y; n4[2] = hi.x; n4[3] = hi.y;
-            src[0] = make_ulonglong2(0ull, 0ull); src[1] = make_ulonglong2(0ull, 0ull);   // leave the table clean
+            unsigned long long *src = p.N + ((size_t)slot * S + s) * 4 + a;
+            n = (long long)*src;
+            *src = 0ull;                                               // leave the table clean for the next sweep
         }
-#pragma unroll 1
-        for (int a = 0; a < 4; a++) {
-            const long long n = (long long)(a == 0 ? n4[0] : a == 1 ? n4[1] : a == 2 ? n4[2] : n4[3]);
-            if (n <= 0) continue;
-            st.c3 = ((uint32_t)STAGE_MUB << 28) | ((uint32_t)a << 26) | (uint32_t)s;
-            // weights and suffix sums (descending, rounded adds)
-            double suf = 0.0;
-            sufS[G * 32 + lane] = 0.0;
-            for (int g = G - 1; g >= 0; g--) {
-                const double w = __dmul_rn(p.gamma[(size_t)s * G + g], eta_s[4 * code_get(code, g) + a]);
-                suf = __dadd_rn(w, suf);
-                wS[g * 32 + lane] = w;
-                sufS[g * 32 + lane] = suf;
+        if (n <= 0) continue;
+        st.c3 = ((uint32_t)STAGE_MUB << 28) | ((uint32_t)a << 26) | (uint32_t)s;
+        // weights and suffix sums (descending, rounded adds)
+        double suf = 0.0;
+        sufS[G * 32 + lane] = 0.0;
+        for (int g = G - 1; g >= 0; g--) {
+            const double w = __dmul_rn(p.gamma[(size_t)s * G + g], eta_s[4 * code_get(code, g) + a]);
+            suf = __dadd_rn(w, suf);
+            wS[g * 32 + lane] = w;
+            sufS[g * 32 + lane] = suf;
+        }
+        long long rem = n;
+        for (int g = 0; g < G; g++) {
+            long long x;
+            if (g == G - 1) x = rem;
+            else if (rem == 0) x = 0;
+            else {
+                const double sg = sufS[g * 32 + lane];
+                x = binomial_draw_d(rem, __ddiv_rn(wS[g * 32 + lane], sg), __ddiv_rn(sufS[(g + 1) * 32 + lane], sg), st, g);
             }
-            long long rem = n;
-            for (int g = 0; g < G; g++) {
-                long long x;
-                if (g == G - 1) x = rem;
-                else if (rem == 0) x = 0;
-                else {
-                    const double sg = sufS[g * 32 + lane];
-                    x = binomial_draw_d(rem, __ddiv_rn(wS[g * 32 + lane], sg), __ddiv_rn(sufS[(g + 1) * 32 + lane], sg), st, g);
-                }
-                rem -= x;
-                if (x) {
-                    accS[g * 32 + lane] += (unsigned long long)x;
-                    eS[(a * 4 + code_get(code, g)) * 32 + lane] += (unsigned long long)x;
-                }
+            rem -= x;
+            if (x) {
+                accS[g * 32 + lane] += (unsigned long long)x;
+                eS[(a * 4 + code_get(code, g)) * 32 + lane] += (unsigned long long)x;
             }
         }
     }
