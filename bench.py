@@ -91,8 +91,8 @@ def algorithmic_bytes(kernel, V, S, G):
     """DESIGN.md section 5 / SURVEY.md 8d: bytes one launch must move under the canonical packed layout."""
     if kernel == "tau_sample":      # counts once, tau read+write, gamma, eta
         return 16 * V * S + 2 * V * G + 8 * S * G + 128
-    if kernel == "mu_stats":        # counts once, tau read, gamma, eta, statistics out
-        return 16 * V * S + V * G + 8 * S * G + 128 + 8 * (S * G + 16)
+    if kernel == "mu_stats":        # per-read form: counts once, tau read, gamma, eta, statistics out.  (The pattern-
+        return 16 * V * S + V * G + 8 * S * G + 128 + 8 * (S * G + 16)   # aggregated form reads the small table instead.)
     raise KeyError(kernel)
 
 
@@ -180,9 +180,10 @@ def run_b200(args):
     clk = clocks.stop()
     tm = e.get_timing()
     ms_total = max_over_ranks(td, tm["elapsed_ms"])
-    # per sweep: mu_stats, draw_gamma_eta, tau_sample, reduce_ll, finalize_sweep, copy_tau_if; +4 for the pre-sweep
-    # ll/lp/star pass and +1 for flush_tau_counts (the L2 flush writes sit outside the timed events)
-    launches = 6 * K + 5
+    # per sweep: agg_reset, agg_begin, mu_aggregate (the three exit at once unless a table rebuild is pending),
+    # mu_binomial, draw_gamma_eta, tau_sample, ll_table, finalize_sweep, copy_tau_if; +6 for the pre-sweep ll/lp/star
+    # pass and +1 for flush_tau_counts (the L2 flush writes sit outside the timed events)
+    launches = 9 * K + 7
     value = (V_total / UNIT_V) * K / (ms_total / 1e3)
 
     # ---- per-kernel pass (events around every launch) for the roofline object

@@ -116,10 +116,7 @@ struct desman_ctx {
     uint8_t *tau = nullptr, *tau_star = nullptr;
     double *gamma = nullptr, *eta = nullptr, *eta_new = nullptr, *gamma_star = nullptr, *eta_star = nullptr;
     unsigned long long *stats = nullptr;     // [S*G + 16] sum_mu | esum
-    unsigned long long *nchange = nullptr;
-    double *ll_partial = nullptr;
-    int ll_partial_n = 0;
-    double *red = nullptr;                   // [2]
+    unsigned long long *red_i = nullptr;     // [2] fixed-point sum n*log p | nchange  (one int64 all-reduce under sharding)
     double *scal = nullptr;                  // [4] lp_star, iter_star, ll, lp
     int *flag = nullptr;
     uint32_t *tau_cnt = nullptr, *tau_last = nullptr;
@@ -136,7 +133,11 @@ struct desman_ctx {
     unsigned long long *agg_keys = nullptr, *agg_code = nullptr, *agg_N = nullptr;
     int *agg_ids = nullptr;
     unsigned int *agg_nslots = nullptr;
-    size_t agg_H = 0, agg_cap_v = 0, agg_cap_cells = 0;
+    int *agg_ctl = nullptr;                  // [3] rebuild wanted | rebuild running | overflow
+    size_t agg_H = 0, agg_cap_slots = 0, agg_cap_cells = 0;
+    bool agg_valid = false;                  // device table reflects the current device tau and counts
+    double total_reads = 0.0, ll_scale = 1.0;
+    double ll_const_total = 0.0;
     unsigned long long *tiers = nullptr;     // [3] draws decided by tier 1/2/3
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     // scratch
@@ -234,8 +235,7 @@ extern "C" int desman_ctx_create(desman_ctx **out, int device, uint64_t seed, in
     CU(cudaMalloc(&c->eta, 16 * sizeof(double)));
     CU(cudaMalloc(&c->eta_new, 16 * sizeof(double)));
     CU(cudaMalloc(&c->eta_star, 16 * sizeof(double)));
-    CU(cudaMalloc(&c->nchange, sizeof(unsigned long long)));
-    CU(cudaMalloc(&c->red, 2 * sizeof(double)));
+    CU(cudaMalloc(&c->red_i, 2 * sizeof(unsigned long long)));
     CU(cudaMalloc(&c->scal, 4 * sizeof(double)));
     CU(cudaMalloc(&c->flag, sizeof(int)));
     CU(cudaMalloc(&c->tiers, 3 * sizeof(unsigned long long)));
@@ -255,7 +255,7 @@ extern "C" int desman_ctx_destroy(desman_ctx *c)
     cudaStreamSynchronize(c->stream);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     void *ptrs[] = {c->counts, c->tau, c->tau_star, c->gamma, c->eta, c->eta_new, c->gamma_star, c->eta_star, c->stats,
-                    c->nchange, c->ll_partial, c->red, c->scal, c->flag, c->tau_cnt, c->tau_last, c->mt_state, c->words,
+                    c->red_i, c->agg_ctl, c->scal, c->flag, c->tau_cnt, c->tau_last, c->mt_state, c->words,
                     c->scratch, c->flush_buf, c->tiers, c->agg_keys, c->agg_code, c->agg_N, c->agg_ids, c->agg_nslots};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
@@ -345,6 +345,7 @@ extern "C" int desman_set_counts(desman_ctx *c, const int64_t *variants, int64_t
         CU(cudaEventCreateWithFlags(&c->pin_ev[1], cudaEventDisableTiming));
     }
     std::atomic<int> bad(0);
+    std::atomic<long long> total(0);
     int buf = 0;
     for (size_t off = 0; off < ncell; off += chunk_cells, buf ^= 1) {
         const size_t n = (ncell - off < chunk_cells) ? ncell - off : chunk_cells;
@@ -354,12 +355,14 @@ extern "C" int desman_set_counts(desman_ctx *c, const int64_t *variants, int64_t
         const int nt = (n >= ((size_t)1 << 16)) ? 8 : 1;
         auto work = [&](int t) {
             const size_t lo = n * t / nt, hi = n * (t + 1) / nt;
-            int64_t orv = 0;
+            int64_t orv = 0, sum = 0;
             for (size_t i = lo; i < hi; i++) {
                 const int64_t a = src[4 * i], b = src[4 * i + 1], d = src[4 * i + 2], e = src[4 * i + 3];
                 orv |= a | b | d | e | (DESMAN_MAX_COUNT - a) | (DESMAN_MAX_COUNT - b) | (DESMAN_MAX_COUNT - d) | (DESMAN_MAX_COUNT - e);
+                sum += a + b + d + e;
                 dst[i] = make_int4((int)a, (int)b, (int)d, (int)e);
             }
+            total += sum;
             if (orv < 0) bad = 1;                                       // a negative count or one above the limit
         };
         if (nt == 1) work(0);
@@ -376,6 +379,8 @@ extern "C" int desman_set_counts(desman_ctx *c, const int64_t *variants, int64_t
     if (V != c->V || S != c->S) c->G = 0;  // state must be (re)set for a new shape
     c->V = V; c->S = S; c->v0 = v0; c->V_total = V_total;
     c->ll_const_valid = false;
+    c->agg_valid = false;
+    c->total_reads = (double)total.load();
     return DESMAN_OK;
 }
 
@@ -395,6 +400,16 @@ static int ensure_ll_const(desman_ctx *c)
     double t = 0.0;
     for (double x : part) t += x;
     c->ll_const = t;
+    c->ll_const_total = t;
+    if (c->nranks > 1) {   // one-time sum over the shards
+        double *d = nullptr;
+        CU(cudaMalloc(&d, sizeof(double)));
+        CU(cudaMemcpyAsync(d, &t, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        NC(g_nccl.AllReduce(d, d, 1, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
+        CU(cudaMemcpyAsync(&c->ll_const_total, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(d);
+    }
     c->ll_const_valid = true;
     return DESMAN_OK;
 }
@@ -425,6 +440,7 @@ static int ensure_state(desman_ctx *c, int G)
         CU(cudaMemsetAsync(c->tau_cnt, 0, nvg * 4 * sizeof(uint32_t), c->stream));
         CU(cudaMemsetAsync(c->tau_last, 0, nvg * sizeof(uint32_t), c->stream));
     }
+    if (G != c->G) c->agg_valid = false;
     c->G = G;
     return DESMAN_OK;
 }
@@ -449,6 +465,7 @@ extern "C" int desman_set_tau_index(desman_ctx *c, const uint8_t *tau_idx, int G
     for (size_t i = 0; i < nvg; i++) if (tau_idx[i] > 3) return fail(DESMAN_EINVAL, "tau index %zu out of range", i);
     CU(cudaMemcpyAsync(c->tau, tau_idx, nvg, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    c->agg_valid = false;
     return DESMAN_OK;
 }
 
@@ -470,6 +487,7 @@ extern "C" int desman_set_state(desman_ctx *c, const int64_t *tau, const double 
         RET(onehot_to_index(tau, idx.size(), idx.data()));
         CU(cudaMemcpyAsync(c->tau, idx.data(), idx.size(), cudaMemcpyHostToDevice, c->stream));
         CU(cudaStreamSynchronize(c->stream));
+        c->agg_valid = false;
     }
     if (gamma) {
         for (size_t i = 0; i < (size_t)c->S * G; i++)
@@ -523,13 +541,91 @@ static int tau_grid(desman_ctx *c)
     return (int)(want < cap ? want : cap);
 }
 
-static int ensure_ll_partial(desman_ctx *c, int n)
+// Persistent pattern table (mu_agg_kernel.cuh).  Capacity 2.5 V slots: finalize asks for a rebuild once more than
+// 1.25 V slots were handed out, and one tau pass can add at most V.
+static int ensure_agg(desman_ctx *c)
 {
-    if (n <= c->ll_partial_n) return DESMAN_OK;
-    if (c->ll_partial) cudaFree(c->ll_partial);
-    c->ll_partial = nullptr; c->ll_partial_n = 0;
-    CU(cudaMalloc(&c->ll_partial, n * sizeof(double)));
-    c->ll_partial_n = n;
+    const size_t V = (size_t)c->V, slots = V * 5 / 2 + 64, cells = slots * c->S * 4;
+    if (slots > c->agg_cap_slots || cells > c->agg_cap_cells) {
+        for (void *q : {(void *)c->agg_keys, (void *)c->agg_code, (void *)c->agg_N, (void *)c->agg_ids, (void *)c->agg_nslots}) if (q) cudaFree(q);
+        c->agg_keys = c->agg_code = c->agg_N = nullptr; c->agg_ids = nullptr; c->agg_nslots = nullptr;
+        c->agg_cap_slots = c->agg_cap_cells = 0;
+        size_t H = 64;
+        while (H < 4 * slots / 3) H <<= 1;
+        CU(cudaMalloc(&c->agg_keys, H * sizeof(unsigned long long)));
+        CU(cudaMalloc(&c->agg_ids, H * sizeof(int)));
+        CU(cudaMalloc(&c->agg_code, slots * sizeof(unsigned long long)));
+        CU(cudaMalloc(&c->agg_nslots, sizeof(unsigned int)));
+        CU(cudaMalloc(&c->agg_N, cells * sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(c->agg_N, 0, cells * sizeof(unsigned long long), c->stream));
+        CU(cudaMemsetAsync(c->agg_nslots, 0, sizeof(unsigned int), c->stream));
+        c->agg_H = H; c->agg_cap_slots = slots; c->agg_cap_cells = cells;
+        c->agg_valid = false;
+    }
+    if (!c->agg_ctl) {
+        CU(cudaMalloc(&c->agg_ctl, 3 * sizeof(int)));
+        CU(cudaMemsetAsync(c->agg_ctl, 0, 3 * sizeof(int), c->stream));
+    }
+    // fixed-point scale of the log-likelihood accumulator: |sum n log p| <= reads * 88 must stay below 2^62
+    const double reads = (c->total_reads > 1.0 ? c->total_reads : 1.0) * ((double)c->V_total / (double)c->V);
+    int k = (int)floor(log2(4.6e18 / (reads * 88.0)));
+    if (k > 40) k = 40;
+    if (k < 0) k = 0;
+    c->ll_scale = ldexp(1.0, k);
+    return DESMAN_OK;
+}
+
+static AggTable agg_table(desman_ctx *c)
+{
+    AggTable t;
+    t.keys = c->agg_keys; t.ids = c->agg_ids; t.hmask = (unsigned int)(c->agg_H - 1); t.slot_code = c->agg_code;
+    t.nslots = c->agg_nslots; t.N = c->agg_N; t.cap_slots = (unsigned int)c->agg_cap_slots; t.S = c->S; t.ctl = c->agg_ctl;
+    return t;
+}
+
+static MuAggParams agg_params(desman_ctx *c, const double *gamma, const double *eta)
+{
+    MuAggParams p;
+    p.counts = c->counts; p.tau = c->tau; p.gamma = gamma; p.eta = eta;
+    p.seed = c->seed; p.sweep = c->sweep; p.shard = (uint32_t)c->v0;
+    p.V = (int)c->V; p.S = c->S; p.G = c->G;
+    p.t = agg_table(c);
+    p.sum_mu = c->stats; p.esum = c->stats + (size_t)c->S * c->G;
+    p.ll_scale = c->ll_scale; p.ll_fx = c->red_i;
+    return p;
+}
+
+// Bring the table in line with the device tau: three launches that exit at once unless a rebuild is pending
+// (requested here after a state upload, or by finalize_sweep_kernel when stale slots piled up).
+static int sync_table(desman_ctx *c)
+{
+    RET(ensure_agg(c));
+    if (!c->agg_valid) {
+        const int one = 1;
+        CU(cudaMemcpyAsync(c->agg_ctl, &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        c->agg_valid = true;
+    }
+    MuAggParams p = agg_params(c, c->gamma, c->eta);
+    KSpan k(c, DESMAN_K_MU);
+    agg_reset_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(p.t);
+    agg_begin_kernel<<<1, 1, 0, c->stream>>>(p.t);
+    int64_t ablocks = (c->V + 7) / 8;
+    if (ablocks > (int64_t)c->sm_count * 8) ablocks = (int64_t)c->sm_count * 8;
+    mu_aggregate_kernel<<<(int)ablocks, 256, 0, c->stream>>>(p);
+    CU(cudaGetLastError());
+    return DESMAN_OK;
+}
+
+// sum n*log p of the current device tau under (gamma, eta) into red_i[0] (fixed point); the table must be in sync
+static int launch_ll(desman_ctx *c, const double *gamma, const double *eta)
+{
+    MuAggParams p = agg_params(c, gamma, eta);
+    CU(cudaMemsetAsync(c->red_i, 0, sizeof(unsigned long long), c->stream));
+    {
+        KSpan k(c, DESMAN_K_FINAL);
+        ll_table_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(p);
+    }
+    CU(cudaGetLastError());
     return DESMAN_OK;
 }
 
@@ -553,30 +649,29 @@ static int gen_mt_words(desman_ctx *c)
     return DESMAN_OK;
 }
 
-// One tau pass.  gamma/eta/eta_ll are device pointers.  with_ll: also produce the n*log p partials.
-static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, const double *eta_ll, bool draw, bool with_ll,
-                      bool count_occupancy, uint32_t iter)
+// One tau pass (gamma, eta: device pointers).  maintain: keep the pattern table current (it must be in sync).
+static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, bool maintain, bool count_occupancy, uint32_t iter)
 {
     TauParams p;
-    p.counts = c->counts; p.tau = c->tau; p.gamma = gamma; p.eta = eta; p.eta_ll = with_ll ? eta_ll : nullptr;
+    p.counts = c->counts; p.tau = c->tau; p.gamma = gamma; p.eta = eta;
     p.words = nullptr;
-    if (draw && c->rng_mode == DESMAN_RNG_MT19937) { RET(gen_mt_words(c)); p.words = c->words; }
+    if (c->rng_mode == DESMAN_RNG_MT19937) { RET(gen_mt_words(c)); p.words = c->words; }
     p.seed = c->seed; p.sweep = c->sweep; p.v0 = c->v0;
     p.V = (int)c->V; p.S = c->S; p.G = c->G;
-    p.nchange = c->nchange;
+    p.nchange = c->red_i + 1;
     const int grid = tau_grid(c);
-    RET(ensure_ll_partial(c, grid));
-    p.ll_partial = with_ll ? c->ll_partial : nullptr;
+    memset(&p.agg, 0, sizeof(p.agg));
+    if (maintain && c->agg_valid) p.agg = agg_table(c);
+    else c->agg_valid = false;
     p.tau_cnt = count_occupancy ? c->tau_cnt : nullptr;
     p.tau_last = c->tau_last;
     p.iter = iter;
-    p.do_draw = draw ? 1 : 0;
     p.exact_only = c->tau_exact;
     p.tier_counts = c->tiers;
     const size_t smem = tau_smem_bytes(c->S, c->G);
     if (smem > 227 * 1024) return fail(DESMAN_EINVAL, "S*G too large for the shared-memory tile (%zu bytes)", smem);
     CU(cudaFuncSetAttribute(tau_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaMemsetAsync(c->nchange, 0, sizeof(unsigned long long), c->stream));
+    CU(cudaMemsetAsync(c->red_i + 1, 0, sizeof(unsigned long long), c->stream));
     {
         KSpan k(c, DESMAN_K_TAU);
         tau_sample_kernel<<<grid, TAU_WARPS * 32, smem, c->stream>>>(p);
@@ -591,35 +686,11 @@ static void launch_mu_t(desman_ctx *c, const MuParams &p, int grid)
     mu_stats_kernel<GP><<<grid, MU_WARPS * 32, 0, c->stream>>>(p);
 }
 
-// K2b: aggregate the counts by haplotype pattern, then one conditional-binomial chain per (pattern, sample, base)
+// K2b: one conditional-binomial chain per (pattern, sample, base) of the (synchronised) pattern table
 static int launch_mu_agg(desman_ctx *c, const double *gamma, const double *eta)
 {
-    const size_t V = (size_t)c->V, cells = V * c->S * 4;
-    if (V > c->agg_cap_v || cells > c->agg_cap_cells) {
-        for (void *q : {(void *)c->agg_keys, (void *)c->agg_code, (void *)c->agg_N, (void *)c->agg_ids, (void *)c->agg_nslots}) if (q) cudaFree(q);
-        c->agg_keys = c->agg_code = c->agg_N = nullptr; c->agg_ids = nullptr; c->agg_nslots = nullptr;
-        c->agg_cap_v = c->agg_cap_cells = 0;
-        size_t H = 64;
-        while (H < 2 * V) H <<= 1;
-        CU(cudaMalloc(&c->agg_keys, H * sizeof(unsigned long long)));
-        CU(cudaMalloc(&c->agg_ids, H * sizeof(int)));
-        CU(cudaMalloc(&c->agg_code, V * sizeof(unsigned long long)));
-        CU(cudaMalloc(&c->agg_nslots, sizeof(unsigned int)));
-        CU(cudaMalloc(&c->agg_N, cells * sizeof(unsigned long long)));
-        CU(cudaMemsetAsync(c->agg_N, 0, cells * sizeof(unsigned long long), c->stream));
-        c->agg_H = H; c->agg_cap_v = V; c->agg_cap_cells = cells;
-    }
-    MuAggParams p;
-    p.counts = c->counts; p.tau = c->tau; p.gamma = gamma; p.eta = eta;
-    p.seed = c->seed; p.sweep = c->sweep; p.shard = (uint32_t)c->v0;
-    p.V = (int)c->V; p.S = c->S; p.G = c->G;
-    p.keys = c->agg_keys; p.ids = c->agg_ids; p.hmask = (unsigned int)(c->agg_H - 1);
-    p.slot_code = c->agg_code; p.nslots = c->agg_nslots; p.N = c->agg_N;
-    p.sum_mu = c->stats; p.esum = c->stats + (size_t)c->S * c->G;
+    MuAggParams p = agg_params(c, gamma, eta);
     CU(cudaMemsetAsync(c->stats, 0, ((size_t)c->S * c->G + 16) * sizeof(unsigned long long), c->stream));
-    CU(cudaMemsetAsync(c->agg_keys, 0xff, c->agg_H * sizeof(unsigned long long), c->stream));
-    CU(cudaMemsetAsync(c->agg_ids, 0xff, c->agg_H * sizeof(int), c->stream));
-    CU(cudaMemsetAsync(c->agg_nslots, 0, sizeof(unsigned int), c->stream));
     const int nch = (c->S + 31) / 32;
     const size_t smem = mub_smem_bytes(c->G);
     CU(cudaFuncSetAttribute(mu_binomial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -629,9 +700,6 @@ static int launch_mu_agg(desman_ctx *c, const double *gamma, const double *eta)
     while ((grid * MUB_WARPS) % nch) grid++;
     {
         KSpan k(c, DESMAN_K_MU);
-        int64_t ablocks = (c->V + 7) / 8;
-        if (ablocks > (int64_t)c->sm_count * 8) ablocks = (int64_t)c->sm_count * 8;
-        mu_aggregate_kernel<<<(int)ablocks, 256, 0, c->stream>>>(p);
         mu_binomial_kernel<<<grid, MUB_WARPS * 32, smem, c->stream>>>(p);
     }
     CU(cudaGetLastError());
@@ -682,7 +750,7 @@ static int allreduce_red(desman_ctx *c)
 {
     if (c->nranks <= 1) return DESMAN_OK;
     KSpan k(c, DESMAN_K_OTHER);
-    NC(g_nccl.AllReduce(c->red, c->red, 2, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
+    NC(g_nccl.AllReduce(c->red_i, c->red_i, 2, NCCL_INT64, NCCL_SUM, c->comm, c->stream));
     return DESMAN_OK;
 }
 
@@ -705,18 +773,15 @@ static int launch_draw(desman_ctx *c, const unsigned long long *stats, double *g
 
 struct StoreBufs { double *ll = nullptr, *lp = nullptr, *nch = nullptr, *gs = nullptr, *es = nullptr; };
 
-static int launch_finalize(desman_ctx *c, const double *gamma, const double *eta, double *eta_commit, int it, int star_mode,
-                           const StoreBufs &sb, bool store_ge)
+// ll (from the table) -> lp, stores, MAP bookkeeping.  gamma/eta: the state the likelihood is evaluated at.
+static int launch_finalize(desman_ctx *c, const double *gamma, const double *eta, int it, int star_mode, const StoreBufs &sb,
+                           bool store_ge)
 {
-    const int grid = tau_grid(c);
-    {
-        KSpan k(c, DESMAN_K_FINAL);
-        reduce_ll_kernel<<<1, 256, 0, c->stream>>>(c->ll_partial, grid, c->ll_const, c->nchange, c->red);
-    }
-    CU(cudaGetLastError());
+    RET(launch_ll(c, gamma, eta));
     RET(allreduce_red(c));
     FinalParams p;
-    p.red = c->red; p.gamma = gamma; p.eta = eta; p.eta_commit = eta_commit;
+    p.red_i = (const long long *)c->red_i; p.ll_const = c->ll_const_total; p.ll_inv_scale = 1.0 / c->ll_scale;
+    p.gamma = gamma; p.eta = eta; p.eta_commit = nullptr;
     p.S = c->S; p.G = c->G; p.V_total = (double)c->V_total; p.alpha = c->alpha; p.delta = c->delta;
     p.lg_alphaG = lgamma(c->alpha * c->G); p.lg_alpha = lgamma(c->alpha);
     p.lg_delta4 = lgamma(4.0 * c->delta); p.lg_delta = lgamma(c->delta);
@@ -724,6 +789,7 @@ static int launch_finalize(desman_ctx *c, const double *gamma, const double *eta
     p.ll_store = sb.ll; p.lp_store = sb.lp; p.nchange_store = sb.nch;
     p.gamma_store = store_ge ? sb.gs : nullptr; p.eta_store = store_ge ? sb.es : nullptr;
     p.gamma_star = c->gamma_star; p.eta_star = c->eta_star; p.scal = c->scal; p.flag = c->flag;
+    p.agg_nslots = c->agg_nslots; p.agg_ctl = c->agg_ctl; p.agg_limit = (unsigned int)(c->V + c->V / 4);
     {
         KSpan k(c, DESMAN_K_FINAL);
         finalize_sweep_kernel<<<1, 256, 0, c->stream>>>(p);
@@ -745,10 +811,10 @@ static int require_state(desman_ctx *c)
 extern "C" int desman_sample_tau(desman_ctx *c, int64_t *nchange)
 {
     RET(require_state(c));
-    RET(launch_tau(c, c->gamma, c->eta, nullptr, true, false, false, 0));
+    RET(launch_tau(c, c->gamma, c->eta, false, false, 0));
     if (c->rng_mode == DESMAN_RNG_PHILOX) c->sweep++;
     unsigned long long n = 0;
-    CU(cudaMemcpyAsync(&n, c->nchange, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&n, c->red_i + 1, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (c->nranks > 1) return fail(DESMAN_ESTATE, "desman_sample_tau is a single-rank call");
     if (nchange) *nchange = (int64_t)n;
@@ -758,6 +824,7 @@ extern "C" int desman_sample_tau(desman_ctx *c, int64_t *nchange)
 extern "C" int desman_mu_stats(desman_ctx *c, int64_t *sum_mu, int64_t *esum)
 {
     RET(require_state(c));
+    if (c->mu_mode == 1) RET(sync_table(c));
     RET(launch_mu(c, c->gamma, c->eta));
     RET(allreduce_stats(c));
     const size_t nsg = (size_t)c->S * c->G;
@@ -791,18 +858,16 @@ extern "C" int desman_loglik(desman_ctx *c, double *ll, double *lp)
 {
     RET(require_state(c));
     RET(ensure_ll_const(c));
-    RET(launch_tau(c, c->gamma, c->eta, c->eta, false, true, false, 0));
-    // finalize with a scratch star area so the real star state is untouched
-    const int grid = tau_grid(c);
-    reduce_ll_kernel<<<1, 256, 0, c->stream>>>(c->ll_partial, grid, c->ll_const, nullptr, c->red);
-    CU(cudaGetLastError());
+    RET(sync_table(c));
+    RET(launch_ll(c, c->gamma, c->eta));
     RET(allreduce_red(c));
-    double h_ll = 0.0;
-    CU(cudaMemcpyAsync(&h_ll, c->red, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    long long fx = 0;
+    CU(cudaMemcpyAsync(&fx, c->red_i, sizeof(fx), cudaMemcpyDeviceToHost, c->stream));
     std::vector<double> g((size_t)c->S * c->G), e(16);
     CU(cudaMemcpyAsync(g.data(), c->gamma, g.size() * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(e.data(), c->eta, 16 * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    const double h_ll = c->ll_const_total + (double)fx / c->ll_scale;
     // prior on host (tiny): Desman_Utils.py:35-44, HaploSNP_Sampler.py:448-459
     double prior = 0.0;
     for (int s = 0; s < c->S; s++) {
@@ -849,6 +914,12 @@ static int fetch_stores(desman_ctx *c, int n_iter, const StoreBufs &sb, double *
     if (eta_store && sb.es) CU(cudaMemcpyAsync(eta_store, sb.es, (size_t)n_iter * 16 * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (nchange_store) for (int i = 0; i < n_iter; i++) nchange_store[i] = (int64_t)llround(nch[i]);
+    if (c->agg_ctl) {
+        int ctl[3] = {0, 0, 0};
+        CU(cudaMemcpyAsync(ctl, c->agg_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (ctl[2]) { c->agg_valid = false; return fail(DESMAN_ESTATE, "pattern table overflow or inconsistency (internal error)"); }
+    }
     return DESMAN_OK;
 }
 
@@ -879,15 +950,18 @@ extern "C" int desman_update(desman_ctx *c, int n_iter, double *gamma_store, dou
     CU(cudaMemsetAsync(c->tau_cnt, 0, nvg * 4 * sizeof(uint32_t), c->stream));
     CU(cudaMemsetAsync(c->tau_last, 0, nvg * sizeof(uint32_t), c->stream));
     // pre-sweep ll/lp and star state (:336-338)
-    RET(launch_tau(c, c->gamma, c->eta, c->eta, false, true, false, 0));
-    RET(launch_finalize(c, c->gamma, c->eta, nullptr, -1, 0, sb, false));
+    RET(sync_table(c));
+    RET(launch_finalize(c, c->gamma, c->eta, -1, 0, sb, false));
     for (int it = 0; it < n_iter; it++) {
         sweep_begin(c);
+        RET(sync_table(c));                                             // no-op launches unless a rebuild is pending
         RET(launch_mu(c, c->gamma, c->eta));                            // sampleMu   (:341)
         RET(allreduce_stats(c));
         RET(launch_draw(c, c->stats, c->gamma, c->eta_new));            // sampleGamma (:342) + sampleEta's draw (:347)
-        RET(launch_tau(c, c->gamma, c->eta, c->eta_new, !c->fixed_tau, true, true, (uint32_t)it));   // sample_tau (:345) + ll (:349)
-        RET(launch_finalize(c, c->gamma, c->eta_new, c->eta, it, 0, sb, true));             // lp, stores, star (:350-358)
+        if (!c->fixed_tau) RET(launch_tau(c, c->gamma, c->eta, true, true, (uint32_t)it));       // sample_tau (:345), old eta
+        else CU(cudaMemsetAsync(c->red_i + 1, 0, sizeof(unsigned long long), c->stream));
+        CU(cudaMemcpyAsync(c->eta, c->eta_new, 16 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));   // eta <- new (:347)
+        RET(launch_finalize(c, c->gamma, c->eta, it, 0, sb, true));     // ll, lp, stores, star (:349-358)
         sweep_end(c);
         c->sweep++;
     }
@@ -916,13 +990,14 @@ extern "C" int desman_update_tau(desman_ctx *c, int n_iter, const double *gamma_
     CU(cudaMemsetAsync(c->tau_cnt, 0, nvg * 4 * sizeof(uint32_t), c->stream));
     CU(cudaMemsetAsync(c->tau_last, 0, nvg * sizeof(uint32_t), c->stream));
     // lp_star from (gamma_store[0], tau, eta_store[0]) (:386-388)
-    RET(launch_tau(c, sb.gs, sb.es, sb.es, false, true, false, 0));
-    RET(launch_finalize(c, sb.gs, sb.es, nullptr, -1, 1, sb, false));
+    RET(sync_table(c));
+    RET(launch_finalize(c, sb.gs, sb.es, -1, 1, sb, false));
     for (int it = 0; it < n_iter; it++) {
         const double *gm = sb.gs + (size_t)it * nsg, *et = sb.es + (size_t)it * 16;
         sweep_begin(c);
-        RET(launch_tau(c, gm, et, et, true, true, true, (uint32_t)it));
-        RET(launch_finalize(c, gm, et, nullptr, it, 1, sb, false));
+        RET(sync_table(c));
+        RET(launch_tau(c, gm, et, true, true, (uint32_t)it));
+        RET(launch_finalize(c, gm, et, it, 1, sb, false));
         sweep_end(c);
         if (c->rng_mode == DESMAN_RNG_PHILOX) c->sweep++;
     }

@@ -2,7 +2,7 @@
 //   lgamma_const       sum_vs lgamma(N+1) - sum_b lgamma(n_b+1)    (Desman_Utils.py:28-33, constant in the chain)
 //   mt19937_kernel     K9: GSL-compatible MT19937 stream             (c_sample_tau.c:33-40,174)
 //   draw_gamma_eta     K3: Dirichlet draws of gamma and eta          (HaploSNP_Sampler.py:263-281)
-//   reduce_ll / finalize_sweep / copy_tau_if / flush_tau_counts     K4-K5 (:326-332,:349-358,:431-461)
+//   finalize_sweep / copy_tau_if / flush_tau_counts                  K5 (:326-332,:349-358,:444-461)
 #pragma once
 #include "common.cuh"
 
@@ -162,27 +162,12 @@ __global__ void __launch_bounds__(256) draw_gamma_eta_kernel(DrawParams p)
 }
 
 // ---------------------------------------------------------------------------------------------
-// red[0] = ll_const + sum of the per-block n*log p partials (fixed order), red[1] = nchange
-__global__ void reduce_ll_kernel(const double *__restrict__ partial, int nblocks, double ll_const,
-                                 const unsigned long long *__restrict__ nchange, double *__restrict__ red)
-{
-    __shared__ double sh[256];
-    double acc = 0.0;
-    for (int i = threadIdx.x; i < nblocks; i += 256) acc += partial[i];
-    sh[threadIdx.x] = acc;
-    __syncthreads();
-    for (int m = 128; m > 0; m >>= 1) {
-        if (threadIdx.x < m) sh[threadIdx.x] += sh[threadIdx.x + m];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        red[0] = sh[0] + ll_const;
-        red[1] = nchange ? (double)(*nchange) : 0.0;
-    }
-}
-
 struct FinalParams {
-    const double *red;        // [2] ll, nchange (already all-reduced under sharding)
+    const long long *red_i;   // [2] fixed-point sum n*log p | nchange (already all-reduced under sharding)
+    double ll_const, ll_inv_scale;
+    const unsigned int *agg_nslots;   // pattern table bookkeeping: ask for a rebuild when too many slots were handed out
+    int *agg_ctl;
+    unsigned int agg_limit;
     const double *gamma;      // [S][G] used for the prior
     const double *eta;        // [16]   used for the prior (eta_new in update())
     double *eta_commit;       // if non-null: eta_commit[0..15] = eta (the chain's eta <- eta_new)
@@ -217,12 +202,13 @@ __global__ void __launch_bounds__(256) finalize_sweep_kernel(FinalParams p)
     if (threadIdx.x == 0) {
         const double prior = sh[0] + p.S * (p.lg_alphaG - p.G * p.lg_alpha) + 4.0 * (p.lg_delta4 - 4.0 * p.lg_delta) +
                              p.V_total * (double)p.G * log(0.25);
-        const double ll = p.red[0], lp = ll + prior;
+        const double ll = p.ll_const + (double)p.red_i[0] * p.ll_inv_scale, lp = ll + prior;
+        if (p.agg_ctl && *p.agg_nslots > p.agg_limit) p.agg_ctl[0] = 1;
         p.scal[2] = ll; p.scal[3] = lp;
         if (p.it >= 0) {
             if (p.ll_store) p.ll_store[p.it] = ll;
             if (p.lp_store) p.lp_store[p.it] = lp;
-            if (p.nchange_store) p.nchange_store[p.it] = p.red[1];
+            if (p.nchange_store) p.nchange_store[p.it] = (double)p.red_i[1];
         }
         upd = (p.it < 0) || (lp > p.scal[0]);
         if (upd) { p.scal[0] = lp; p.scal[1] = (double)(p.it < 0 ? 0 : p.it); }

@@ -7,7 +7,8 @@
 // sites with the same pattern are exchangeable, and the sum of their multinomials is ONE multinomial with the summed
 // count.  So:
 //   mu_aggregate_kernel   one warp per site: hash the 2G-bit pattern code into a slot (open addressing, atomicCAS),
-//                         add the site's S count cells into N[slot][s][a] (64-bit reductions); one HBM pass
+//                         add the site's S count cells into N[slot][s][a] (64-bit reductions); one HBM pass, needed only
+//                         after a state upload: afterwards the tau kernel moves the counts of the sites it flips
 //   mu_binomial_kernel    one warp per (slot, 32-sample chunk): per (s,a) a chain of conditional binomials over the
 //                         strains (what numpy's RandomState.multinomial does), each by inversion when
 //                         n*min(p,q) < 10 and by Hoermann's BTRS transformed rejection otherwise: O(1) per draw,
@@ -24,6 +25,22 @@
 #define MUB_WARPS 8
 #define MUB_EMPTY 0xffffffffffffffffull
 
+// Persistent pattern table.  N[slot][s][a] = sum of the counts of all sites whose haplotype pattern is slot_code[slot].
+// Built by mu_aggregate_kernel, then kept current by the tau kernel (a site that changes pattern moves its counts),
+// so that in steady state (a handful of flips per sweep) no aggregation pass is needed.  ctl[0] = rebuild wanted
+// (host on state upload; finalize_sweep when stale slots pile up), ctl[1] = rebuild in progress, ctl[2] = overflow.
+struct AggTable {
+    unsigned long long *keys;        // [H] pattern codes (MUB_EMPTY = free)
+    int *ids;                        // [H] slot id of the key (-1 until published)
+    unsigned int hmask;              // H - 1
+    unsigned long long *slot_code;   // [cap_slots]
+    unsigned int *nslots;            // slots handed out so far
+    unsigned long long *N;           // [cap_slots][S][4]
+    unsigned int cap_slots;
+    int S;
+    int *ctl;
+};
+
 struct MuAggParams {
     const int4 *counts;          // [V][S]
     const uint8_t *tau;          // [V][G]
@@ -33,14 +50,11 @@ struct MuAggParams {
     uint32_t sweep;
     uint32_t shard;              // global index of local site 0 (keys the streams of a rank's partial aggregates)
     int V, S, G;
-    unsigned long long *keys;    // [H] pattern codes (MUB_EMPTY = free)
-    int *ids;                    // [H] slot id of the key (-1 until published)
-    unsigned int hmask;          // H - 1
-    unsigned long long *slot_code;   // [V]
-    unsigned int *nslots;        // number of slots in use
-    unsigned long long *N;       // [V slots][S][4] aggregated counts (left zeroed by the sampling kernel)
+    AggTable t;
     unsigned long long *sum_mu;  // [S][G] +=
     unsigned long long *esum;    // [16]   += (esum[a_obs*4 + b_true])
+    double ll_scale;             // 2^k of the fixed-point log-likelihood accumulator
+    unsigned long long *ll_fx;   // += llrint(sum n*log p * 2^k)  (two's complement)
 };
 
 __device__ __forceinline__ unsigned int mix_code(unsigned long long x)
@@ -49,33 +63,79 @@ __device__ __forceinline__ unsigned int mix_code(unsigned long long x)
     return (unsigned int)x;
 }
 
+// Slot of a pattern code (one thread per call).  insert = false: the code is known to be present.
+__device__ __forceinline__ int agg_slot(const AggTable &t, unsigned long long code, bool insert)
+{
+    unsigned int h = mix_code(code) & t.hmask;
+    int id;
+    while (true) {
+        const unsigned long long prev = insert ? atomicCAS(t.keys + h, MUB_EMPTY, code) : *((volatile unsigned long long *)(t.keys + h));
+        if (insert && prev == MUB_EMPTY) {                  // first site of this pattern: publish a new slot
+            id = (int)atomicAdd(t.nslots, 1u);
+            if ((unsigned int)id >= t.cap_slots) { t.ctl[2] = 1; id = (int)t.cap_slots - 1; }
+            t.slot_code[id] = code;
+            __threadfence();
+            atomicExch(t.ids + h, id);
+            return id;
+        }
+        if (prev == code) {                                 // known pattern: wait until its slot id is visible
+            while ((id = *((volatile int *)(t.ids + h))) < 0) {}
+            return id;
+        }
+        if (!insert && prev == MUB_EMPTY) { t.ctl[2] = 1; return 0; }   // inconsistent table (never expected)
+        h = (h + 1) & t.hmask;
+    }
+}
+
+// Move one site's counts between patterns (called by all lanes of the warp that owns the site).
+__device__ __forceinline__ void agg_move_site(const AggTable &t, unsigned long long code_old, unsigned long long code_new,
+                                              const int4 *tile, int lane)
+{
+    int so = 0, sn = 0;
+    if (lane == 0) { so = agg_slot(t, code_old, false); sn = agg_slot(t, code_new, true); }
+    so = __shfl_sync(DESMAN_FULL_MASK, so, 0);
+    sn = __shfl_sync(DESMAN_FULL_MASK, sn, 0);
+    unsigned long long *po = t.N + (size_t)so * t.S * 4, *pn = t.N + (size_t)sn * t.S * 4;
+    for (int s = lane; s < t.S; s += 32) {
+        const int4 n = tile[s];
+        if (n.x) { atomicAdd(pn + s * 4 + 0, (unsigned long long)n.x); atomicAdd(po + s * 4 + 0, 0ull - (unsigned long long)n.x); }
+        if (n.y) { atomicAdd(pn + s * 4 + 1, (unsigned long long)n.y); atomicAdd(po + s * 4 + 1, 0ull - (unsigned long long)n.y); }
+        if (n.z) { atomicAdd(pn + s * 4 + 2, (unsigned long long)n.z); atomicAdd(po + s * 4 + 2, 0ull - (unsigned long long)n.z); }
+        if (n.w) { atomicAdd(pn + s * 4 + 3, (unsigned long long)n.w); atomicAdd(po + s * 4 + 3, 0ull - (unsigned long long)n.w); }
+    }
+}
+
+// Rebuild, step 1 (only when ctl[0]): free every key and zero the used part of N.
+__global__ void agg_reset_kernel(AggTable t)
+{
+    if (!t.ctl[0]) return;
+    const size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = i0; i <= t.hmask; i += st) { t.keys[i] = MUB_EMPTY; t.ids[i] = -1; }
+    unsigned int used = *t.nslots;
+    if (used > t.cap_slots) used = t.cap_slots;
+    const size_t n = (size_t)used * t.S * 4;
+    for (size_t i = i0; i < n; i += st) t.N[i] = 0ull;
+}
+// step 2 (one thread): hand the request over to the aggregation pass
+__global__ void agg_begin_kernel(AggTable t)
+{
+    t.ctl[1] = t.ctl[0];
+    if (t.ctl[0]) *t.nslots = 0u;
+    t.ctl[0] = 0;
+}
+
+// step 3 (only when ctl[1]): one warp per site
 __global__ void __launch_bounds__(256) mu_aggregate_kernel(MuAggParams p)
 {
+    if (!p.t.ctl[1]) return;
     const int lane = threadIdx.x & 31;
     const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
     for (int v = gw; v < p.V; v += nw) {
         const unsigned long long code = load_tau_code(p.tau + (size_t)v * p.G, p.G, lane);
         int id = 0;
-        if (lane == 0) {
-            unsigned int h = mix_code(code) & p.hmask;
-            while (true) {
-                const unsigned long long prev = atomicCAS(p.keys + h, MUB_EMPTY, code);
-                if (prev == MUB_EMPTY) {                       // first site of this pattern: publish a new slot
-                    id = (int)atomicAdd(p.nslots, 1u);
-                    p.slot_code[id] = code;
-                    __threadfence();
-                    atomicExch(p.ids + h, id);
-                    break;
-                }
-                if (prev == code) {                            // known pattern: wait until its slot id is visible
-                    while ((id = *((volatile int *)(p.ids + h))) < 0) {}
-                    break;
-                }
-                h = (h + 1) & p.hmask;
-            }
-        }
+        if (lane == 0) id = agg_slot(p.t, code, true);
         id = __shfl_sync(DESMAN_FULL_MASK, id, 0);
-        unsigned long long *dst = p.N + (size_t)id * p.S * 4;
+        unsigned long long *dst = p.t.N + (size_t)id * p.S * 4;
         const int4 *src = p.counts + (size_t)v * p.S;
         for (int s = lane; s < p.S; s += 32) {
             const int4 n = ld_counts(src + s);
@@ -85,6 +145,46 @@ __global__ void __launch_bounds__(256) mu_aggregate_kernel(MuAggParams p)
             if (n.w) atomicAdd(dst + s * 4 + 3, (unsigned long long)n.w);
         }
     }
+}
+
+// K4 on the table: sum_v sum_s sum_b n*log p = sum_slots sum_s sum_a N[slot][s][a]*log(sum_g gamma[s,g]*eta[tau_g,a])
+// (HaploSNP_Sampler.py:435,441).  Per (slot, chunk) the terms are summed in FP64 in a fixed order; the per-item sums are
+// accumulated in 64-bit fixed point, so the total does not depend on slot numbering or scheduling (bitwise reproducible).
+__global__ void __launch_bounds__(256) ll_table_kernel(MuAggParams p)
+{
+    __shared__ double eta_s[16];
+    if (threadIdx.x < 16) eta_s[threadIdx.x] = p.eta[threadIdx.x];
+    __syncthreads();
+    const int S = p.S, G = p.G, lane = threadIdx.x & 31;
+    const int nch = (S + 31) >> 5;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    unsigned int P = *p.t.nslots;
+    if (P > p.t.cap_slots) P = p.t.cap_slots;
+    long long fx = 0;
+    for (long long item = gw; item < (long long)P * nch; item += nw) {
+        const int slot = (int)(item / nch), s = (int)(item % nch) * 32 + lane;
+        const unsigned long long code = p.t.slot_code[slot];
+        double acc = 0.0;
+        if (s < S) {
+            const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(p.t.N + ((size_t)slot * S + s) * 4);
+            const ulonglong2 lo = src[0], hi = src[1];
+            if (lo.x | lo.y | hi.x | hi.y) {
+                double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+                for (int g = 0; g < G; g++) {
+                    const double *e = eta_s + 4 * code_get(code, g);
+                    const double gm = p.gamma[(size_t)s * G + g];
+                    b0 = fma(e[0], gm, b0); b1 = fma(e[1], gm, b1); b2 = fma(e[2], gm, b2); b3 = fma(e[3], gm, b3);
+                }
+                if (lo.x) acc = fma((double)lo.x, log(b0), acc);
+                if (lo.y) acc = fma((double)lo.y, log(b1), acc);
+                if (hi.x) acc = fma((double)hi.x, log(b2), acc);
+                if (hi.y) acc = fma((double)hi.y, log(b3), acc);
+            }
+        }
+        acc = warp_sum(acc);
+        fx += __double2ll_rn(acc * p.ll_scale);
+    }
+    if (lane == 0 && fx) atomicAdd(p.ll_fx, (unsigned long long)fx);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -196,7 +296,9 @@ __global__ void __launch_bounds__(MUB_WARPS * 32) mu_binomial_kernel(MuAggParams
     const int gw = blockIdx.x * MUB_WARPS + wib, nw = gridDim.x * MUB_WARPS;      // nw % nch == 0 (host)
     const int chunk = gw % nch, s = chunk * 32 + lane;
     const bool valid = s < S;
-    const int P = (int)*p.nslots;
+    unsigned int Pu = *p.t.nslots;
+    if (Pu > p.t.cap_slots) Pu = p.t.cap_slots;
+    const int P = (int)Pu;
     BinStream st;
     st.c2 = p.sweep; st.k0 = (uint32_t)p.seed; st.k1 = (uint32_t)(p.seed >> 32) ^ p.shard;
 
@@ -204,14 +306,10 @@ __global__ void __launch_bounds__(MUB_WARPS * 32) mu_binomial_kernel(MuAggParams
     // matters because the number of patterns P can be a few thousand only
     for (int item = gw / nch; item < 4 * P; item += nw / nch) {
         const int slot = item >> 2, a = item & 3;
-        const unsigned long long code = p.slot_code[slot];
+        const unsigned long long code = p.t.slot_code[slot];
         st.c0 = (uint32_t)code; st.c1 = (uint32_t)(code >> 32);
         long long n = 0;
-        if (valid) {
-            unsigned long long *src = p.N + ((size_t)slot * S + s) * 4 + a;
-            n = (long long)*src;
-            *src = 0ull;                                               // leave the table clean for the next sweep
-        }
+        if (valid) n = (long long)p.t.N[((size_t)slot * S + s) * 4 + a];
         if (n <= 0) continue;
         st.c3 = ((uint32_t)STAGE_MUB << 28) | ((uint32_t)a << 26) | (uint32_t)s;
         // weights and suffix sums (descending, rounded adds)

@@ -1,5 +1,6 @@
 // desman_b200/csrc/tau_kernel.cuh -- K1: the tau Gibbs update (replaces sampletau/c_sample_tau.c:95-204)
-// fused with K4, the sum_n n*log(p) part of logLikelihood (HaploSNP_Sampler.py:431-442).
+// It also keeps the persistent pattern table (mu_agg_kernel.cuh) current: a site whose pattern changed moves its
+// counts from the old slot to the new one, so K2b and the log-likelihood never need a fresh aggregation pass.
 //
 // Mapping: one warp per variant position v (sites are independent, c_sample_tau.c:130), lanes over
 // samples s, strains g strictly in order (each draw conditions on the tau just written, :133,:180).
@@ -22,24 +23,23 @@
 // quantity that enters a log is then a sum of non-negative terms (relative error a few ulp).
 #pragma once
 #include "common.cuh"
+#include "mu_agg_kernel.cuh"
 
 struct TauParams {
     const int4 *counts;      // [V][S] int32x4
     uint8_t *tau;            // [V][G] base index, updated in place
     const double *gamma;     // [S][G]
     const double *eta;       // [16] eta used for the draw (row = true base)
-    const double *eta_ll;    // [16] eta used for the log-likelihood term, or nullptr (no ll)
     const uint32_t *words;   // MT19937 words [V*G] (u = w/2^32), or nullptr -> Philox
     uint64_t seed;
     uint32_t sweep;
     int64_t v0;              // global index of local site 0 (Philox counter / sharding)
     int V, S, G;
     unsigned long long *nchange;  // += flips
-    double *ll_partial;      // [gridDim.x] per-block sum of n*log p, or nullptr
+    AggTable agg;            // persistent pattern table to keep current (agg.N == nullptr: none)
     uint32_t *tau_cnt;       // [V][G][4] lazy per-base occupancy counters, or nullptr
     uint32_t *tau_last;      // [V][G] iteration at which the current base was adopted
     uint32_t iter;           // iteration index inside the current update() call
-    int do_draw;             // 0: skip the Gibbs draw, only accumulate the log-likelihood term
     int exact_only;          // 1: every (v,g) step takes the FP64 reference-order path (validation)
     unsigned long long *tier_counts;  // [3] += draws decided by tier 1 / 2 / 3 (or nullptr)
 };
@@ -82,8 +82,6 @@ __device__ __noinline__ void tau_exact_logp(const int4 *tile, const double *gT, 
     }
     L[0] = warp_sum(L0); L[1] = warp_sum(L1); L[2] = warp_sum(L2); L[3] = warp_sum(L3);
 }
-
-__device__ __noinline__ double log_fp64(double x) { return log(x); }   // one copy of the FP64 log for the ll term
 
 // normaliseLog4 + sample4 (c_sample_tau.c:48-91)
 __device__ __noinline__ int tau_exact_pick(const double L[4], double u)
@@ -237,7 +235,6 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
     float *K = reinterpret_cast<float *>(eta32 + 4);             // [TAU_WARPS][Sp] sum_b n_b*lg2 P_b
     int4 *tiles = reinterpret_cast<int4 *>(K + (size_t)TAU_WARPS * Sp);          // [TAU_WARPS][Sp]
     uint32_t *wbuf = reinterpret_cast<uint32_t *>(tiles + (size_t)TAU_WARPS * Sp);   // [TAU_WARPS][32] uniform words
-    __shared__ double ll_warp[TAU_WARPS];
     __shared__ unsigned int gmin_bits, emin_bits;   // min gamma / min eta as float bit patterns (positive floats order like uints)
 
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -255,7 +252,7 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
     if (threadIdx.x < 16) {
         eta_s[threadIdx.x] = p.eta[threadIdx.x];
         reinterpret_cast<float *>(eta32)[threadIdx.x] = (float)p.eta[threadIdx.x];
-        etall_s[threadIdx.x] = p.eta_ll ? p.eta_ll[threadIdx.x] : 0.0;
+        etall_s[threadIdx.x] = 0.0;
         atomicMin(&emin_bits, __float_as_uint(fmaxf((float)p.eta[threadIdx.x], 0.f)));
     }
     __syncthreads();
@@ -273,14 +270,13 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
     const float c1 = TAU_C1(nch), ccan = TAU_CANCEL(G);
     const float cancel0 = ccan / fmaxf(qmin, TAU_QMIN);                     // a-priori bound of the P/q amplification
     unsigned int flips = 0, n1 = 0, n2 = 0, n3 = 0;
-    double ll_acc = 0.0;
 
     for (int v = gw; v < p.V; v += nw) {
         const int4 *src = p.counts + (size_t)v * S;
         uint64_t code = load_tau_code(p.tau + (size_t)v * G, G, lane);
         const uint64_t code_in = code;
         // the G uniform words of this site: lane g draws word g (one Philox call per site instead of G per lane)
-        if (p.do_draw) {
+        {
             uint32_t w = 0;
             if (lane < G) {
                 if (p.words) w = p.words[(size_t)v * G + lane];
@@ -312,7 +308,7 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
         }
         __syncwarp();
 
-        for (int g = 0; g < (p.do_draw ? G : 0); g++) {
+        for (int g = 0; g < G; g++) {
             const int cur = code_get(code, g);
             const uint32_t w = ww[g];
             const double u = (double)w / 4294967296.0;              // gsl_rng_uniform, c_sample_tau.c:174
@@ -378,29 +374,11 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
                 }
             }
         }
-        if (code != code_in && lane < G) p.tau[(size_t)v * G + lane] = (uint8_t)code_get(code, lane);
-
-        if (p.ll_partial) {
-            // sum_s sum_b n*log(p_vsb), p = sum_g gamma[s,g]*eta_ll[tau_vg,b]   (HaploSNP_Sampler.py:435,441)
-            double acc = 0.0;
-            for (int s = lane; s < S; s += 32) {
-                const int4 n = tile[s];
-                if ((n.x | n.y | n.z | n.w) == 0) continue;
-                double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
-                for (int h = 0; h < G; h++) {
-                    const double2 *e = reinterpret_cast<const double2 *>(etall_s + 4 * code_get(code, h));
-                    const double2 e01 = e[0], e23 = e[1];
-                    const double gm = gT[h * Sp + s];
-                    b0 = fma(e01.x, gm, b0); b1 = fma(e01.y, gm, b1);
-                    b2 = fma(e23.x, gm, b2); b3 = fma(e23.y, gm, b3);
-                }
-                if (n.x) acc = fma((double)n.x, log_fp64(b0), acc);
-                if (n.y) acc = fma((double)n.y, log_fp64(b1), acc);
-                if (n.z) acc = fma((double)n.z, log_fp64(b2), acc);
-                if (n.w) acc = fma((double)n.w, log_fp64(b3), acc);
-            }
-            ll_acc += warp_sum(acc);
+        if (code != code_in) {
+            if (lane < G) p.tau[(size_t)v * G + lane] = (uint8_t)code_get(code, lane);
+            if (p.agg.N) agg_move_site(p.agg, code_in, code, tile, lane);
         }
+
         __syncwarp();
     }
 
@@ -409,15 +387,6 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
         if (n1) atomicAdd(p.tier_counts + 0, (unsigned long long)n1);
         if (n2) atomicAdd(p.tier_counts + 1, (unsigned long long)n2);
         if (n3) atomicAdd(p.tier_counts + 2, (unsigned long long)n3);
-    }
-    if (p.ll_partial) {
-        if (lane == 0) ll_warp[wib] = ll_acc;
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double t = 0.0;
-            for (int i = 0; i < TAU_WARPS; i++) t += ll_warp[i];
-            p.ll_partial[blockIdx.x] = t;   // fixed site->warp->block order: deterministic
-        }
     }
 }
 

@@ -10,6 +10,7 @@ pytestmark = pytest.mark.gpu
 
 RTOL = 1e-6          # north_star tolerance for gamma / eta / log-likelihood
 RTOL_TIGHT = 1e-10   # what we actually expect between CUDA and glibc double arithmetic
+RTOL_LL = 1e-9       # ll/lp: summed over the pattern table in 64-bit fixed point (order-independent, 2^-k resolution)
 
 
 @pytest.fixture(scope="module")
@@ -191,8 +192,8 @@ def test_loglik_vs_reference_python_golden(eng_mod, oracle_mod):
         e.set_state(tau, z[f"c{ci}_gamma"], z[f"c{ci}_eta"])
         ll, lp = e.loglik()
         want_ll, want_lp = z[f"c{ci}_ll_lp"]
-        assert abs(ll - want_ll) <= RTOL_TIGHT * abs(want_ll), ci
-        assert abs(lp - want_lp) <= RTOL_TIGHT * abs(want_lp), ci
+        assert abs(ll - want_ll) <= RTOL_LL * abs(want_ll), ci
+        assert abs(lp - want_lp) <= RTOL_LL * abs(want_lp), ci
         e.close()
 
 
@@ -216,12 +217,12 @@ def test_update_chain_vs_oracle(eng_mod, oracle_mod, V, S, G, depth, n_iter, mod
     assert np.array_equal(e.get_tau_sum(), want["tau_sum"])
     assert rel(got["gamma_store"], want["gamma_store"]) < RTOL_TIGHT
     assert rel(got["eta_store"], want["eta_store"]) < RTOL_TIGHT
-    assert rel(got["ll_store"], want["ll_store"]) < RTOL_TIGHT
-    assert rel(got["lp_store"], want["lp_store"]) < RTOL_TIGHT
+    assert rel(got["ll_store"], want["ll_store"]) < RTOL_LL
+    assert rel(got["lp_store"], want["lp_store"]) < RTOL_LL
     assert rel(gamma, want["gamma"]) < RTOL_TIGHT and rel(eta, want["eta"]) < RTOL_TIGHT
     star = e.get_star()
     assert star["iter"] == want["iter_star"]
-    assert abs(star["lp"] - want["lp_star"]) <= RTOL_TIGHT * abs(want["lp_star"])
+    assert abs(star["lp"] - want["lp_star"]) <= RTOL_LL * abs(want["lp_star"])
     assert np.array_equal(star["tau"], want["tau_star"])
     assert rel(star["gamma"], want["gamma_star"]) < RTOL_TIGHT and rel(star["eta"], want["eta_star"]) < RTOL_TIGHT
     assert want["nchange"].sum() > 0 and e.get_rng()[0] == 3 + n_iter
@@ -251,10 +252,10 @@ def test_update_tau_replay_vs_oracle(eng_mod, oracle_mod, use_mt):
     assert np.array_equal(got["nchange"], want["nchange"])
     assert np.array_equal(e.get_state()[0], want["tau"])
     assert np.array_equal(e.get_tau_sum(), want["tau_sum"])
-    assert rel(got["ll_store"], want["ll_store"]) < RTOL_TIGHT and rel(got["lp_store"], want["lp_store"]) < RTOL_TIGHT
+    assert rel(got["ll_store"], want["ll_store"]) < RTOL_LL and rel(got["lp_store"], want["lp_store"]) < RTOL_LL
     star = e.get_star()
     assert np.array_equal(star["tau"], want["tau_star"])
-    assert abs(star["lp"] - want["lp_star"]) <= RTOL_TIGHT * abs(want["lp_star"])
+    assert abs(star["lp"] - want["lp_star"]) <= RTOL_LL * abs(want["lp_star"])
     e.close()
 
 
