@@ -133,7 +133,7 @@ struct desman_ctx {
     unsigned long long *agg_keys = nullptr, *agg_code = nullptr, *agg_N = nullptr;
     int *agg_ids = nullptr;
     unsigned int *agg_nslots = nullptr;
-    int *agg_ctl = nullptr;                  // [3] rebuild wanted | rebuild running | overflow
+    int *agg_ctl = nullptr;                  // [4] rebuild wanted | rebuild running | overflow | flips since rebuild
     size_t agg_H = 0, agg_cap_slots = 0, agg_cap_cells = 0;
     bool agg_valid = false;                  // device table reflects the current device tau and counts
     double total_reads = 0.0, ll_scale = 1.0;
@@ -563,8 +563,8 @@ static int ensure_agg(desman_ctx *c)
         c->agg_valid = false;
     }
     if (!c->agg_ctl) {
-        CU(cudaMalloc(&c->agg_ctl, 3 * sizeof(int)));
-        CU(cudaMemsetAsync(c->agg_ctl, 0, 3 * sizeof(int), c->stream));
+        CU(cudaMalloc(&c->agg_ctl, 4 * sizeof(int)));
+        CU(cudaMemsetAsync(c->agg_ctl, 0, 4 * sizeof(int), c->stream));
     }
     // fixed-point scale of the log-likelihood accumulator: |sum n log p| <= reads * 88 must stay below 2^62
     const double reads = (c->total_reads > 1.0 ? c->total_reads : 1.0) * ((double)c->V_total / (double)c->V);

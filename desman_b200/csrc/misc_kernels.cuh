@@ -203,7 +203,14 @@ __global__ void __launch_bounds__(256) finalize_sweep_kernel(FinalParams p)
         const double prior = sh[0] + p.S * (p.lg_alphaG - p.G * p.lg_alpha) + 4.0 * (p.lg_delta4 - 4.0 * p.lg_delta) +
                              p.V_total * (double)p.G * log(0.25);
         const double ll = p.ll_const + (double)p.red_i[0] * p.ll_inv_scale, lp = ll + prior;
-        if (p.agg_ctl && *p.agg_nslots > p.agg_limit) p.agg_ctl[0] = 1;
+        if (p.agg_ctl) {
+            // pattern table upkeep: every flipped (v,g) may have left a stale slot behind.  Ask for a rebuild when the
+            // stale slots could outnumber half the live ones, or when the slot array is close to its capacity bound.
+            const long long stale = (long long)p.agg_ctl[3] + (p.it >= 0 ? p.red_i[1] : 0);
+            const long long used = (long long)*p.agg_nslots, live = used > stale ? used - stale : 0;
+            p.agg_ctl[3] = (int)(stale > 0x3fffffff ? 0x3fffffff : stale);
+            if (stale > live / 2 + 512 || used > (long long)p.agg_limit) p.agg_ctl[0] = 1;
+        }
         p.scal[2] = ll; p.scal[3] = lp;
         if (p.it >= 0) {
             if (p.ll_store) p.ll_store[p.it] = ll;

@@ -28,7 +28,8 @@
 // Persistent pattern table.  N[slot][s][a] = sum of the counts of all sites whose haplotype pattern is slot_code[slot].
 // Built by mu_aggregate_kernel, then kept current by the tau kernel (a site that changes pattern moves its counts),
 // so that in steady state (a handful of flips per sweep) no aggregation pass is needed.  ctl[0] = rebuild wanted
-// (host on state upload; finalize_sweep when stale slots pile up), ctl[1] = rebuild in progress, ctl[2] = overflow.
+// (host on state upload; finalize_sweep when stale slots pile up), ctl[1] = rebuild in progress, ctl[2] = overflow,
+// ctl[3] = flips since the last rebuild (upper bound of the number of stale slots).
 struct AggTable {
     unsigned long long *keys;        // [H] pattern codes (MUB_EMPTY = free)
     int *ids;                        // [H] slot id of the key (-1 until published)
@@ -120,7 +121,7 @@ __global__ void agg_reset_kernel(AggTable t)
 __global__ void agg_begin_kernel(AggTable t)
 {
     t.ctl[1] = t.ctl[0];
-    if (t.ctl[0]) *t.nslots = 0u;
+    if (t.ctl[0]) { *t.nslots = 0u; t.ctl[3] = 0; }
     t.ctl[0] = 0;
 }
 
