@@ -129,7 +129,8 @@ struct desman_ctx {
     uint32_t last_n_iter = 0;
     int tau_exact = 0;                       // 1: FP64 reference-order path for every draw
     int fixed_tau = 0;                       // 1: update() skips the tau draw (update_fixed_tau, HaploSNP_Sampler.py:409-428)
-    int mu_mode = 1;                         // 1: pattern-aggregated binomial statistics (K2b), 0: per-read categorical (K2)
+    int mu_mode = 2;                         // 1: pattern-aggregated binomial statistics (K2b), 0: per-read categorical (K2),
+                                             // 2: choose from (V, G): aggregated iff the ~12*2^G possible biallelic patterns are <= V/2
     unsigned long long *agg_keys = nullptr, *agg_code = nullptr, *agg_N = nullptr;
     int *agg_ids = nullptr;
     unsigned int *agg_nslots = nullptr;
@@ -241,7 +242,7 @@ extern "C" int desman_ctx_create(desman_ctx **out, int device, uint64_t seed, in
     CU(cudaMalloc(&c->tiers, 3 * sizeof(unsigned long long)));
     CU(cudaMemset(c->tiers, 0, 3 * sizeof(unsigned long long)));
     { const char *ex = getenv("DESMAN_B200_TAU_EXACT"); c->tau_exact = (ex && atoi(ex)) ? 1 : 0; }
-    { const char *mm = getenv("DESMAN_B200_MU_MODE"); if (mm) c->mu_mode = atoi(mm) ? 1 : 0; }
+    { const char *mm = getenv("DESMAN_B200_MU_MODE"); if (mm) c->mu_mode = atoi(mm); if (c->mu_mode < 0 || c->mu_mode > 2) c->mu_mode = 2; }
     CU(cudaMalloc(&c->mt_state, 624 * sizeof(uint32_t)));
     CU(cudaMemset(c->scal, 0, 4 * sizeof(double)));
     *out = c;
@@ -706,9 +707,17 @@ static int launch_mu_agg(desman_ctx *c, const double *gamma, const double *eta)
     return DESMAN_OK;
 }
 
+// Which statistics kernel: the aggregated form pays off when sites share patterns.  A biallelic site has one of
+// ~12*2^G patterns; the rule depends on (V, G) only, so it is reproducible outside the engine (oracle, tests).
+static int resolved_mu_mode(const desman_ctx *c)
+{
+    if (c->mu_mode != 2) return c->mu_mode;
+    return (c->G <= 24 && 12.0 * ldexp(1.0, c->G) <= (double)c->V / 2.0) ? 1 : 0;
+}
+
 static int launch_mu(desman_ctx *c, const double *gamma, const double *eta)
 {
-    if (c->mu_mode == 1) return launch_mu_agg(c, gamma, eta);
+    if (resolved_mu_mode(c) == 1) return launch_mu_agg(c, gamma, eta);
     MuParams p;
     p.counts = c->counts; p.tau = c->tau; p.gamma = gamma; p.eta = eta;
     p.seed = c->seed; p.sweep = c->sweep; p.v0 = c->v0;
@@ -824,7 +833,7 @@ extern "C" int desman_sample_tau(desman_ctx *c, int64_t *nchange)
 extern "C" int desman_mu_stats(desman_ctx *c, int64_t *sum_mu, int64_t *esum)
 {
     RET(require_state(c));
-    if (c->mu_mode == 1) RET(sync_table(c));
+    if (resolved_mu_mode(c) == 1) RET(sync_table(c));
     RET(launch_mu(c, c->gamma, c->eta));
     RET(allreduce_stats(c));
     const size_t nsg = (size_t)c->S * c->G;
@@ -1089,7 +1098,7 @@ extern "C" int desman_set_option(desman_ctx *c, const char *name, int64_t value)
     if (!c || !name) return fail(DESMAN_EINVAL, "desman_set_option: bad arguments");
     if (!strcmp(name, "tau_exact")) { c->tau_exact = value ? 1 : 0; return DESMAN_OK; }
     if (!strcmp(name, "fixed_tau")) { c->fixed_tau = value ? 1 : 0; return DESMAN_OK; }
-    if (!strcmp(name, "mu_mode")) { c->mu_mode = value ? 1 : 0; return DESMAN_OK; }
+    if (!strcmp(name, "mu_mode")) { c->mu_mode = (value == 0 || value == 1) ? (int)value : 2; return DESMAN_OK; }
     return fail(DESMAN_EINVAL, "unknown option '%s'", name);
 }
 

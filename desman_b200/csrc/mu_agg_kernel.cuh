@@ -204,8 +204,8 @@ __device__ double stirling_tail_d(double k)
                i == 6 ? 0.0118967099458917 : i == 7 ? 0.0104112652619720 : i == 8 ? 0.00925546218271273 :
                         0.00833056343336287;
     }
-    const double kp1 = __dadd_rn(k, 1.0), kp1sq = __dmul_rn(kp1, kp1);
-    return __ddiv_rn(__dadd_rn(1.0 / 12.0, -__ddiv_rn(__dadd_rn(1.0 / 360.0, -__ddiv_rn(1.0 / 1260.0, kp1sq)), kp1sq)), kp1);
+    const double t = __ddiv_rn(1.0, __dadd_rn(k, 1.0)), t2 = __dmul_rn(t, t);
+    return __dmul_rn(__dadd_rn(1.0 / 12.0, -__dmul_rn(__dadd_rn(1.0 / 360.0, -__dmul_rn(1.0 / 1260.0, t2)), t2)), t);
 }
 
 struct BinStream { uint32_t c0, c1, c2, c3, k0, k1; };

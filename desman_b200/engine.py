@@ -10,6 +10,12 @@ from . import _lib
 from ._lib import RNG_MT19937, RNG_PHILOX, check
 
 
+def auto_mu_mode(V, G):
+    """The engine's default choice of the mu/E statistics contract (engine.cu resolved_mu_mode): pattern-aggregated
+    binomials (1) when the ~12*2^G biallelic patterns are at most V/2, else one categorical draw per read (0)."""
+    return 1 if (G <= 24 and 12.0 * 2.0 ** G <= V / 2.0) else 0
+
+
 class Engine:
     """One device-resident chain: counts, tau, gamma, eta and RNG position on one GPU."""
 

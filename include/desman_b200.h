@@ -106,8 +106,8 @@ int desman_nmft_factorize(desman_ctx *ctx, const int64_t *snps, int64_t V, int S
                           double *tau, double *gamma, int max_iter, double min_change, int fix_gamma,
                           int *n_iter_done, double *div_final, double *div_trace);
 
-/* Engine options.  "mu_mode" = 1 (default): mu/E statistics from pattern-aggregated conditional binomials; 0: one
- * categorical draw per read (both exact, different counter contracts).  "fixed_tau" = 1 makes desman_update skip the tau draw (update_fixed_tau, HaploSNP_Sampler.py:409-428).
+/* Engine options.  "mu_mode" = 1: mu/E statistics from pattern-aggregated conditional binomials; 0: one categorical
+ * draw per read (both exact, different counter contracts); 2 (default): 1 iff 12*2^G <= V/2.  "fixed_tau" = 1 makes desman_update skip the tau draw (update_fixed_tau, HaploSNP_Sampler.py:409-428).
  * "tau_exact" = 1 forces the FP64 reference-order arithmetic for every tau draw (validation;
  * default 0 = filtered-exact FP32 fast path with FP64 fallback, same draws).  desman_get_tier_counts returns how
  * many draws were decided by the FP32 gap test / the FP64 CDF brackets / the FP64 reference-order recompute. */

@@ -138,7 +138,8 @@ def test_sampler_class_surface_on_gpu(oracle_mod):
     ll, lp = hs.logLikelihood(hs.gamma, hs.tau, hs.eta), hs.logPosterior(hs.gamma, hs.tau, hs.eta)
     assert abs(ll - oracle_mod.loglik(hs.tau, hs.gamma, hs.eta, p["counts"])) < 1e-9 * abs(ll)
     hs.update()
-    want = oracle_mod.update(onehot(p["tau0"]), p["gamma0"], p["eta0"], p["counts"], 7, seed=4321, mu_mode=1)
+    from desman_b200.engine import auto_mu_mode
+    want = oracle_mod.update(onehot(p["tau0"]), p["gamma0"], p["eta0"], p["counts"], 7, seed=4321, mu_mode=auto_mu_mode(200, 4))
     assert np.array_equal(hs.tau, want["tau"]) and np.array_equal(hs.tau_star, want["tau_star"])
     assert np.allclose(hs.gamma_store, want["gamma_store"], rtol=1e-9, atol=0)
     assert np.allclose(hs.ll_store, want["ll_store"], rtol=1e-9, atol=0)
