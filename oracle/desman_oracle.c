@@ -319,8 +319,8 @@ static double stirling_tail(double k)
                                  0.0166446911898211, 0.0138761288230707, 0.0118967099458917, 0.0104112652619720,
                                  0.00925546218271273, 0.00833056343336287};
     if (k <= 9.0) return t[(int)k];
-    double t = 1.0 / (k + 1.0), t2 = t * t;      /* one division; Horner in 1/(k+1)^2 */
-    return (1.0 / 12.0 - (1.0 / 360.0 - (1.0 / 1260.0) * t2) * t2) * t;
+    double r1 = 1.0 / (k + 1.0), r2 = r1 * r1;   /* one division; Horner in 1/(k+1)^2 */
+    return (1.0 / 12.0 - (1.0 / 360.0 - (1.0 / 1260.0) * r2) * r2) * r1;
 }
 
 typedef struct { uint32_t c0, c1, c2, c3; uint64_t seed; uint32_t shard; int g; } bin_stream;
