@@ -154,6 +154,7 @@ def test_mu_stats_sharded_offsets_equal_whole(eng_mod, oracle_mod):
     # aggregated mode: a shard's streams are keyed by its first global site; each shard equals the oracle's shard
     for lo, hi in ((0, 41), (41, 90)):
         e = eng_mod.Engine(0, seed=9)
+        e.set_option("mu_mode", 1)
         e.set_counts(p["counts"][lo:hi], v0=lo, V_total=90)
         e.set_state(onehot(p["tau0"][lo:hi]), p["gamma0"], p["eta0"])
         e.set_rng(9, sweep=4)
