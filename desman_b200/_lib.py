@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libdesman_b200.so")
 
 RNG_MT19937, RNG_PHILOX = 0, 1
 MAX_G = 32
-K_NAMES = ("tau_sample", "mu_stats", "draw_gamma_eta", "finalize", "mt19937", "nmft", "other")
+K_NAMES = ("tau_sample", "mu_stats", "draw_gamma_eta", "finalize", "mt19937", "nmft", "other", "tau_group", "maintain")
 
 _p64 = C.POINTER(C.c_int64)
 _pd = C.POINTER(C.c_double)
@@ -53,6 +53,7 @@ SYMBOLS = {
                                         C.POINTER(C.c_int), _pd, _pd]),
     "desman_set_option": (C.c_int, [_ctx, C.c_char_p, C.c_int64]),
     "desman_get_tier_counts": (C.c_int, [_ctx, _p64, C.c_int]),
+    "desman_get_group_stats": (C.c_int, [_ctx, _p64]),
     "desman_comm_unique_id": (C.c_int, [C.c_char_p]),
     "desman_comm_init": (C.c_int, [_ctx, C.c_char_p, C.c_int, C.c_int]),
     "desman_set_profiling": (C.c_int, [_ctx, C.c_int, C.c_int]),

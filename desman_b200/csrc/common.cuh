@@ -76,3 +76,11 @@ __device__ __forceinline__ int4 ld_counts(const int4 *p)
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
+
+// Control words of the pattern groups (tau_group_kernel.cuh, table_maintain_kernel): requests and list lengths.
+enum { GC_REGROUP = 0,   // regroup wanted (finalize_sweep sets it when orphans pile up; a table rebuild implies one)
+       GC_HAVE = 1,      // the groups are valid for the current slot numbering
+       GC_CALM = 2,      // the previous sweep flipped few sites: the screening pass pays off
+       GC_NITEMS = 3, GC_NSINGLES = 4, GC_NWORK = 5, GC_CURSOR = 6,
+       GC_ORPHANS = 7,   // sites that changed pattern since the last regroup (screened out by their slot mismatch)
+       GC_COUNT = 8 };

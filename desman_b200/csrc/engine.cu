@@ -20,6 +20,8 @@
 #include "mu_kernel.cuh"
 #include "nmft_kernel.cuh"
 #include "tau_kernel.cuh"
+#include "tau_group_kernel.cuh"
+#include "maintain_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[1024] = "";
@@ -140,6 +142,20 @@ struct desman_ctx {
     double total_reads = 0.0, ll_scale = 1.0;
     double ll_const_total = 0.0;
     unsigned long long *tiers = nullptr;     // [3] draws decided by tier 1/2/3
+    // pattern groups for the screening pass of the tau update (tau_group_kernel.cuh)
+    int tau_group = 2;                       // 0: off, 1: on, 2: on iff the ~12*2^G biallelic patterns are <= V/2
+    int tau_group_mma = 1;                   // 1: tensor-core form of the screening pass where it applies; 0: FFMA form
+    bool counts_tf32_exact = false;
+    float4 *countsf = nullptr;               // [V][S] FP32 copy of the counts
+    float *nsite = nullptr;                  // [V]
+    bool countsf_valid = false;
+    size_t countsf_cap = 0;
+    int *grp_site_slot = nullptr, *grp_order = nullptr, *grp_singles = nullptr, *grp_slot4 = nullptr, *grp_gctl = nullptr,
+        *grp_blk = nullptr;
+    int4 *grp_items = nullptr;
+    uint2 *grp_work = nullptr;
+    size_t grp_cap_v = 0, grp_cap_slots = 0;
+    int maint_grid = 0;
     cudaEvent_t pin_ev[2] = {nullptr, nullptr};
     // scratch
     void *scratch = nullptr;
@@ -242,6 +258,7 @@ extern "C" int desman_ctx_create(desman_ctx **out, int device, uint64_t seed, in
     CU(cudaMalloc(&c->tiers, 3 * sizeof(unsigned long long)));
     CU(cudaMemset(c->tiers, 0, 3 * sizeof(unsigned long long)));
     { const char *ex = getenv("DESMAN_B200_TAU_EXACT"); c->tau_exact = (ex && atoi(ex)) ? 1 : 0; }
+    { const char *tg = getenv("DESMAN_B200_TAU_GROUP"); if (tg) c->tau_group = atoi(tg); if (c->tau_group < 0 || c->tau_group > 2) c->tau_group = 2; }
     { const char *mm = getenv("DESMAN_B200_MU_MODE"); if (mm) c->mu_mode = atoi(mm); if (c->mu_mode < 0 || c->mu_mode > 2) c->mu_mode = 2; }
     CU(cudaMalloc(&c->mt_state, 624 * sizeof(uint32_t)));
     CU(cudaMemset(c->scal, 0, 4 * sizeof(double)));
@@ -257,7 +274,9 @@ extern "C" int desman_ctx_destroy(desman_ctx *c)
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     void *ptrs[] = {c->counts, c->tau, c->tau_star, c->gamma, c->eta, c->eta_new, c->gamma_star, c->eta_star, c->stats,
                     c->red_i, c->agg_ctl, c->scal, c->flag, c->tau_cnt, c->tau_last, c->mt_state, c->words,
-                    c->scratch, c->flush_buf, c->tiers, c->agg_keys, c->agg_code, c->agg_N, c->agg_ids, c->agg_nslots};
+                    c->scratch, c->flush_buf, c->tiers, c->agg_keys, c->agg_code, c->agg_N, c->agg_ids, c->agg_nslots,
+                    c->countsf, c->nsite, c->grp_site_slot, c->grp_order, c->grp_singles, c->grp_slot4, c->grp_gctl, c->grp_blk,
+                    c->grp_items, c->grp_work};
     for (void *p : ptrs) if (p) cudaFree(p);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) if (c->pin_ev[i]) cudaEventDestroy(c->pin_ev[i]);
@@ -346,7 +365,7 @@ extern "C" int desman_set_counts(desman_ctx *c, const int64_t *variants, int64_t
         CU(cudaEventCreateWithFlags(&c->pin_ev[1], cudaEventDisableTiming));
     }
     std::atomic<int> bad(0);
-    std::atomic<long long> total(0);
+    std::atomic<long long> total(0), or_all(0);
     int buf = 0;
     for (size_t off = 0; off < ncell; off += chunk_cells, buf ^= 1) {
         const size_t n = (ncell - off < chunk_cells) ? ncell - off : chunk_cells;
@@ -356,14 +375,16 @@ extern "C" int desman_set_counts(desman_ctx *c, const int64_t *variants, int64_t
         const int nt = (n >= ((size_t)1 << 16)) ? 8 : 1;
         auto work = [&](int t) {
             const size_t lo = n * t / nt, hi = n * (t + 1) / nt;
-            int64_t orv = 0, sum = 0;
+            int64_t orv = 0, sum = 0, orc = 0;
             for (size_t i = lo; i < hi; i++) {
                 const int64_t a = src[4 * i], b = src[4 * i + 1], d = src[4 * i + 2], e = src[4 * i + 3];
+                orc |= a | b | d | e;
                 orv |= a | b | d | e | (DESMAN_MAX_COUNT - a) | (DESMAN_MAX_COUNT - b) | (DESMAN_MAX_COUNT - d) | (DESMAN_MAX_COUNT - e);
                 sum += a + b + d + e;
                 dst[i] = make_int4((int)a, (int)b, (int)d, (int)e);
             }
             total += sum;
+            or_all |= orc;
             if (orv < 0) bad = 1;                                       // a negative count or one above the limit
         };
         if (nt == 1) work(0);
@@ -381,7 +402,9 @@ extern "C" int desman_set_counts(desman_ctx *c, const int64_t *variants, int64_t
     c->V = V; c->S = S; c->v0 = v0; c->V_total = V_total;
     c->ll_const_valid = false;
     c->agg_valid = false;
+    c->countsf_valid = false;
     c->total_reads = (double)total.load();
+    c->counts_tf32_exact = or_all.load() < 2048;   // every count < 2^11: exact as a TF32 operand
     return DESMAN_OK;
 }
 
@@ -567,6 +590,26 @@ static int ensure_agg(desman_ctx *c)
         CU(cudaMalloc(&c->agg_ctl, 4 * sizeof(int)));
         CU(cudaMemsetAsync(c->agg_ctl, 0, 4 * sizeof(int), c->stream));
     }
+    // site groups of the screening pass
+    if (V > c->grp_cap_v || c->agg_cap_slots > c->grp_cap_slots) {
+        for (void *q : {(void *)c->grp_site_slot, (void *)c->grp_order, (void *)c->grp_singles, (void *)c->grp_slot4,
+                        (void *)c->grp_items, (void *)c->grp_work}) if (q) cudaFree(q);
+        c->grp_site_slot = c->grp_order = c->grp_singles = c->grp_slot4 = nullptr; c->grp_items = nullptr; c->grp_work = nullptr;
+        c->grp_cap_v = c->grp_cap_slots = 0;
+        CU(cudaMalloc(&c->grp_site_slot, V * sizeof(int)));
+        CU(cudaMalloc(&c->grp_order, V * sizeof(int)));
+        CU(cudaMalloc(&c->grp_singles, V * sizeof(int)));
+        CU(cudaMalloc(&c->grp_slot4, 4 * c->agg_cap_slots * sizeof(int)));
+        CU(cudaMalloc(&c->grp_items, (V / 2 + V / TG_ITEM_SITES + 64) * sizeof(int4)));
+        CU(cudaMalloc(&c->grp_work, V * sizeof(uint2)));
+        c->grp_cap_v = V; c->grp_cap_slots = c->agg_cap_slots;
+        c->agg_valid = false;
+    }
+    if (!c->grp_gctl) {
+        CU(cudaMalloc(&c->grp_gctl, GC_COUNT * sizeof(int)));
+        CU(cudaMemsetAsync(c->grp_gctl, 0, GC_COUNT * sizeof(int), c->stream));
+        CU(cudaMalloc(&c->grp_blk, 4 * 2048 * sizeof(int)));
+    }
     // fixed-point scale of the log-likelihood accumulator: |sum n log p| <= reads * 88 must stay below 2^62
     const double reads = (c->total_reads > 1.0 ? c->total_reads : 1.0) * ((double)c->V_total / (double)c->V);
     int k = (int)floor(log2(4.6e18 / (reads * 88.0)));
@@ -596,32 +639,103 @@ static MuAggParams agg_params(desman_ctx *c, const double *gamma, const double *
     return p;
 }
 
-// Bring the table in line with the device tau: three launches that exit at once unless a rebuild is pending
-// (requested here after a state upload, or by finalize_sweep_kernel when stale slots piled up).
-static int sync_table(desman_ctx *c)
+// Is the screening pass of the tau update (tau_group_kernel.cuh) worth keeping groups for?  Same rule as the statistics:
+// sites share patterns when the ~12*2^G biallelic patterns are few compared with V.  *gb / *warps: strain block and warps
+// per CTA of the kernel (each warp owns one table in shared memory).
+static bool group_use_mma(const desman_ctx *c)
 {
-    RET(ensure_agg(c));
-    if (!c->agg_valid) {
-        const int one = 1;
-        CU(cudaMemcpyAsync(c->agg_ctl, &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        c->agg_valid = true;
+    return c->tau_group_mma && c->counts_tf32_exact && tgm_tiles(c->G) <= 6 &&
+           tg_shared_bytes(c->S, c->G) + tgm_table_bytes(c->S, c->G) + 1024 <= 200 * 1024;
+}
+
+static bool group_config(const desman_ctx *c, int *gb, int *warps)
+{
+    if (c->tau_group == 0 || c->tau_exact) return false;
+    if (c->tau_group == 2 && !(c->G <= 24 && 12.0 * ldexp(1.0, c->G) <= (double)c->V / 2.0)) return false;
+    if (group_use_mma(c)) return true;
+    const int r = c->G % 8, GB = (r >= 1 && r <= 4) ? 4 : 8;
+    const size_t table = tg_table_bytes(c->S, c->G, GB), shared = tg_shared_bytes(c->S, c->G) + 1024;
+    int w = TG_MAX_WARPS;
+    if (shared + (size_t)w * table > 110 * 1024) {                 // one CTA per SM: as many warps as fit
+        w = (int)((220 * 1024 - shared) / table);
+        if (w > TG_MAX_WARPS) w = TG_MAX_WARPS;
     }
-    MuAggParams p = agg_params(c, c->gamma, c->eta);
-    KSpan k(c, DESMAN_K_MU);
-    agg_reset_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(p.t);
-    agg_begin_kernel<<<1, 1, 0, c->stream>>>(p.t);
-    int64_t ablocks = (c->V + 7) / 8;
-    if (ablocks > (int64_t)c->sm_count * 8) ablocks = (int64_t)c->sm_count * 8;
-    mu_aggregate_kernel<<<(int)ablocks, 256, 0, c->stream>>>(p);
+    if (w < 1) return false;
+    if (gb) *gb = GB;
+    if (warps) *warps = w;
+    return true;
+}
+
+static TauGroup group_ptrs(desman_ctx *c)
+{
+    TauGroup g;
+    g.site_slot = c->grp_site_slot; g.order = c->grp_order; g.singles = c->grp_singles; g.items = c->grp_items; g.work = c->grp_work;
+    g.slot_cnt = c->grp_slot4; g.slot_fill = c->grp_slot4 + c->grp_cap_slots; g.slot_start = c->grp_slot4 + 2 * c->grp_cap_slots;
+    g.slot_item = c->grp_slot4 + 3 * c->grp_cap_slots;
+    g.gctl = c->grp_gctl;
+    return g;
+}
+
+static int ensure_countsf(desman_ctx *c)
+{
+    if (c->countsf_valid) return DESMAN_OK;
+    const size_t ncell = (size_t)c->V * c->S;
+    if (ncell > c->countsf_cap) {
+        if (c->countsf) cudaFree(c->countsf);
+        if (c->nsite) cudaFree(c->nsite);
+        c->countsf = nullptr; c->nsite = nullptr; c->countsf_cap = 0;
+        CU(cudaMalloc(&c->countsf, ncell * sizeof(float4)));
+        CU(cudaMalloc(&c->nsite, (size_t)c->V * sizeof(float)));
+        c->countsf_cap = ncell;
+    }
+    counts_to_float_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->counts, c->countsf, c->nsite, (int)c->V, c->S);
     CU(cudaGetLastError());
+    c->countsf_valid = true;
     return DESMAN_OK;
 }
 
-// sum n*log p of the current device tau under (gamma, eta) into red_i[0] (fixed point); the table must be in sync
+// Start of a sweep: ONE cooperative launch that clears the per-sweep accumulators (statistics, fixed-point ll, nchange,
+// work-list length) and, only when a request is pending (host: state upload; device: finalize_sweep_kernel), rebuilds the
+// pattern table and regroups the sites (maintain_kernel.cuh).
+static int sync_table(desman_ctx *c)
+{
+    RET(ensure_agg(c));
+    const bool grouping = group_config(c, nullptr, nullptr);
+    if (grouping) RET(ensure_countsf(c));
+    if (!c->agg_valid) {
+        const int one = 1;
+        CU(cudaMemcpyAsync(c->agg_ctl, &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        // optimistic: a freshly uploaded state is screened on its first sweep (a converged state pays off at once; after a
+        // random one finalize_sweep_kernel turns the screening off until the chain has calmed down)
+        CU(cudaMemcpyAsync(c->grp_gctl + GC_CALM, &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        c->agg_valid = true;
+    }
+    if (!c->maint_grid) {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, table_maintain_kernel, MAINT_THREADS, 0) != cudaSuccess || occ < 1) occ = 1;
+        if (occ > 4) occ = 4;
+        c->maint_grid = c->sm_count * occ;
+        if (c->maint_grid > 2048) c->maint_grid = 2048;
+    }
+    MaintParams p;
+    p.a = agg_params(c, c->gamma, c->eta);
+    p.grp = group_ptrs(c);
+    if (!grouping) p.grp.gctl = nullptr;
+    p.blk = c->grp_blk;
+    p.zero64 = c->stats; p.nzero64 = (int)((size_t)c->S * c->G + 16);
+    p.red_i = c->red_i;
+    void *args[] = {&p};
+    {
+        KSpan k(c, DESMAN_K_MAINT);
+        CU(cudaLaunchCooperativeKernel((const void *)table_maintain_kernel, dim3(c->maint_grid), dim3(MAINT_THREADS), args, 0, c->stream));
+    }
+    return DESMAN_OK;
+}
+
+// sum n*log p of the current device tau under (gamma, eta) into red_i[0] (fixed point, cleared by sync_table)
 static int launch_ll(desman_ctx *c, const double *gamma, const double *eta)
 {
     MuAggParams p = agg_params(c, gamma, eta);
-    CU(cudaMemsetAsync(c->red_i, 0, sizeof(unsigned long long), c->stream));
     {
         KSpan k(c, DESMAN_K_FINAL);
         ll_table_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(p);
@@ -650,7 +764,33 @@ static int gen_mt_words(desman_ctx *c)
     return DESMAN_OK;
 }
 
-// One tau pass (gamma, eta: device pointers).  maintain: keep the pattern table current (it must be in sync).
+template <int NT>
+static int launch_tau_group_mma_t(desman_ctx *c, const TauGroupParams &p)
+{
+    const size_t smem = tg_shared_bytes(c->S, c->G) + tgm_table_bytes(c->S, c->G);
+    CU(cudaFuncSetAttribute(tau_group_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tau_group_mma_kernel<NT>, TGM_WARPS * 32, smem) != cudaSuccess || occ < 1) occ = 1;
+    tau_group_mma_kernel<NT><<<c->sm_count * occ, TGM_WARPS * 32, smem, c->stream>>>(p);
+    CU(cudaGetLastError());
+    return DESMAN_OK;
+}
+
+template <int GB>
+static int launch_tau_group_t(desman_ctx *c, const TauGroupParams &p, int warps)
+{
+    const size_t smem = tg_shared_bytes(c->S, c->G) + (size_t)warps * tg_table_bytes(c->S, c->G, GB);
+    CU(cudaFuncSetAttribute(tau_group_kernel<GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tau_group_kernel<GB>, warps * 32, smem) != cudaSuccess || occ < 1) occ = 1;
+    tau_group_kernel<GB><<<c->sm_count * occ, warps * 32, smem, c->stream>>>(p);
+    CU(cudaGetLastError());
+    return DESMAN_OK;
+}
+
+// One tau pass (gamma, eta: device pointers).  maintain: keep the pattern table current (it must be in sync); then the
+// screening pass runs first where groups are kept, and the per-site kernel walks its work list only.
+// red_i[1] (nchange) must be zero on entry (sync_table, or the caller's memset).
 static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, bool maintain, bool count_occupancy, uint32_t iter)
 {
     TauParams p;
@@ -669,10 +809,34 @@ static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, boo
     p.iter = iter;
     p.exact_only = c->tau_exact;
     p.tier_counts = c->tiers;
+    p.work = nullptr; p.singles = nullptr; p.gctl = nullptr; p.site_slot = nullptr;
+    int gb = 8, gwarps = 1;
+    if (p.agg.N && group_config(c, &gb, &gwarps)) {
+        TauGroupParams q;
+        q.countsf = c->countsf; q.nsite = c->nsite; q.gamma = gamma; q.eta = eta; q.words = p.words;
+        q.V = (int)c->V; q.S = c->S; q.G = c->G;
+        q.slot_code = c->agg_code;
+        q.grp = group_ptrs(c);
+        q.tier_counts = c->tiers;
+        {
+            KSpan k(c, DESMAN_K_TAU_GROUP);
+            if (group_use_mma(c)) {
+                switch (tgm_tiles(c->G)) {
+                case 1: RET(launch_tau_group_mma_t<1>(c, q)); break;
+                case 2: RET(launch_tau_group_mma_t<2>(c, q)); break;
+                case 3: RET(launch_tau_group_mma_t<3>(c, q)); break;
+                case 4: RET(launch_tau_group_mma_t<4>(c, q)); break;
+                case 5: RET(launch_tau_group_mma_t<5>(c, q)); break;
+                default: RET(launch_tau_group_mma_t<6>(c, q)); break;
+                }
+            } else if (gb == 4) RET(launch_tau_group_t<4>(c, q, gwarps));
+            else RET(launch_tau_group_t<8>(c, q, gwarps));
+        }
+        p.work = c->grp_work; p.singles = c->grp_singles; p.gctl = c->grp_gctl; p.site_slot = c->grp_site_slot;
+    }
     const size_t smem = tau_smem_bytes(c->S, c->G);
     if (smem > 227 * 1024) return fail(DESMAN_EINVAL, "S*G too large for the shared-memory tile (%zu bytes)", smem);
     CU(cudaFuncSetAttribute(tau_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CU(cudaMemsetAsync(c->red_i + 1, 0, sizeof(unsigned long long), c->stream));
     {
         KSpan k(c, DESMAN_K_TAU);
         tau_sample_kernel<<<grid, TAU_WARPS * 32, smem, c->stream>>>(p);
@@ -687,11 +851,11 @@ static void launch_mu_t(desman_ctx *c, const MuParams &p, int grid)
     mu_stats_kernel<GP><<<grid, MU_WARPS * 32, 0, c->stream>>>(p);
 }
 
-// K2b: one conditional-binomial chain per (pattern, sample, base) of the (synchronised) pattern table
+// K2b: one conditional-binomial chain per (pattern, sample, base) of the (synchronised) pattern table.
+// The statistics accumulators are cleared by sync_table at the start of the sweep.
 static int launch_mu_agg(desman_ctx *c, const double *gamma, const double *eta)
 {
     MuAggParams p = agg_params(c, gamma, eta);
-    CU(cudaMemsetAsync(c->stats, 0, ((size_t)c->S * c->G + 16) * sizeof(unsigned long long), c->stream));
     const int nch = (c->S + 31) / 32;
     const size_t smem = mub_smem_bytes(c->G);
     CU(cudaFuncSetAttribute(mu_binomial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -731,7 +895,6 @@ static int launch_mu(desman_ctx *c, const double *gamma, const double *eta)
     if (blocks > cap) blocks = cap;
     blocks = ((blocks + nch - 1) / nch) * nch;
     const int grid = (int)blocks;
-    CU(cudaMemsetAsync(c->stats, 0, ((size_t)c->S * c->G + 16) * sizeof(unsigned long long), c->stream));
     {
         KSpan k(c, DESMAN_K_MU);
         const int G = c->G;
@@ -799,6 +962,8 @@ static int launch_finalize(desman_ctx *c, const double *gamma, const double *eta
     p.gamma_store = store_ge ? sb.gs : nullptr; p.eta_store = store_ge ? sb.es : nullptr;
     p.gamma_star = c->gamma_star; p.eta_star = c->eta_star; p.scal = c->scal; p.flag = c->flag;
     p.agg_nslots = c->agg_nslots; p.agg_ctl = c->agg_ctl; p.agg_limit = (unsigned int)(c->V + c->V / 4);
+    p.gctl = group_config(c, nullptr, nullptr) ? c->grp_gctl : nullptr;
+    p.V_local = (long long)c->V;
     {
         KSpan k(c, DESMAN_K_FINAL);
         finalize_sweep_kernel<<<1, 256, 0, c->stream>>>(p);
@@ -820,6 +985,7 @@ static int require_state(desman_ctx *c)
 extern "C" int desman_sample_tau(desman_ctx *c, int64_t *nchange)
 {
     RET(require_state(c));
+    CU(cudaMemsetAsync(c->red_i + 1, 0, sizeof(unsigned long long), c->stream));
     RET(launch_tau(c, c->gamma, c->eta, false, false, 0));
     if (c->rng_mode == DESMAN_RNG_PHILOX) c->sweep++;
     unsigned long long n = 0;
@@ -833,7 +999,7 @@ extern "C" int desman_sample_tau(desman_ctx *c, int64_t *nchange)
 extern "C" int desman_mu_stats(desman_ctx *c, int64_t *sum_mu, int64_t *esum)
 {
     RET(require_state(c));
-    if (resolved_mu_mode(c) == 1) RET(sync_table(c));
+    RET(sync_table(c));
     RET(launch_mu(c, c->gamma, c->eta));
     RET(allreduce_stats(c));
     const size_t nsg = (size_t)c->S * c->G;
@@ -963,12 +1129,11 @@ extern "C" int desman_update(desman_ctx *c, int n_iter, double *gamma_store, dou
     RET(launch_finalize(c, c->gamma, c->eta, -1, 0, sb, false));
     for (int it = 0; it < n_iter; it++) {
         sweep_begin(c);
-        RET(sync_table(c));                                             // no-op launches unless a rebuild is pending
+        RET(sync_table(c));                                             // clears the accumulators; table upkeep when pending
         RET(launch_mu(c, c->gamma, c->eta));                            // sampleMu   (:341)
         RET(allreduce_stats(c));
         RET(launch_draw(c, c->stats, c->gamma, c->eta_new));            // sampleGamma (:342) + sampleEta's draw (:347)
-        if (!c->fixed_tau) RET(launch_tau(c, c->gamma, c->eta, true, true, (uint32_t)it));       // sample_tau (:345), old eta
-        else CU(cudaMemsetAsync(c->red_i + 1, 0, sizeof(unsigned long long), c->stream));
+        if (!c->fixed_tau) RET(launch_tau(c, c->gamma, c->eta, true, true, (uint32_t)it));       // sample_tau (:345), old eta (nchange cleared by sync_table)
         CU(cudaMemcpyAsync(c->eta, c->eta_new, 16 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));   // eta <- new (:347)
         RET(launch_finalize(c, c->gamma, c->eta, it, 0, sb, true));     // ll, lp, stores, star (:349-358)
         sweep_end(c);
@@ -1099,6 +1264,9 @@ extern "C" int desman_set_option(desman_ctx *c, const char *name, int64_t value)
     if (!strcmp(name, "tau_exact")) { c->tau_exact = value ? 1 : 0; return DESMAN_OK; }
     if (!strcmp(name, "fixed_tau")) { c->fixed_tau = value ? 1 : 0; return DESMAN_OK; }
     if (!strcmp(name, "mu_mode")) { c->mu_mode = (value == 0 || value == 1) ? (int)value : 2; return DESMAN_OK; }
+    if (!strcmp(name, "tau_group_mma")) { c->tau_group_mma = value ? 1 : 0; return DESMAN_OK; }
+    if (!strcmp(name, "tau_group_mma")) { c->tau_group_mma = value ? 1 : 0; return DESMAN_OK; }
+    if (!strcmp(name, "tau_group")) { c->tau_group = (value == 0 || value == 1) ? (int)value : 2; c->agg_valid = false; return DESMAN_OK; }
     return fail(DESMAN_EINVAL, "unknown option '%s'", name);
 }
 
@@ -1110,6 +1278,19 @@ extern "C" int desman_get_tier_counts(desman_ctx *c, int64_t out[3], int reset)
     if (reset) CU(cudaMemsetAsync(c->tiers, 0, sizeof(h), c->stream));
     CU(cudaStreamSynchronize(c->stream));
     for (int i = 0; i < 3; i++) out[i] = (int64_t)h[i];
+    return DESMAN_OK;
+}
+
+extern "C" int desman_get_group_stats(desman_ctx *c, int64_t out[8])
+{
+    CU(cudaSetDevice(c->device));
+    int h[GC_COUNT] = {0};
+    if (c->grp_gctl) CU(cudaMemcpyAsync(h, c->grp_gctl, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    unsigned int ns = 0;
+    if (c->agg_nslots) CU(cudaMemcpyAsync(&ns, c->agg_nslots, sizeof(ns), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    out[0] = h[GC_HAVE]; out[1] = h[GC_CALM]; out[2] = h[GC_NITEMS]; out[3] = h[GC_NSINGLES]; out[4] = h[GC_NWORK];
+    out[5] = h[GC_ORPHANS]; out[6] = (int64_t)ns; out[7] = group_config(c, nullptr, nullptr) ? 1 : 0;
     return DESMAN_OK;
 }
 

@@ -1,0 +1,187 @@
+// desman_b200/csrc/maintain_kernel.cuh -- one cooperative launch per sweep that (a) clears the per-sweep accumulators and
+// (b) only when asked to, rebuilds the persistent pattern table (mu_agg_kernel.cuh) and regroups the sites by pattern for the
+// screening pass of the tau update (tau_group_kernel.cuh).  In steady state (b) is a handful of flag reads: the launch
+// replaces three conditional no-op launches and three memsets of the first version.
+//
+// Requests: ctl[0] (table rebuild: host after a state upload, finalize_sweep when stale slots pile up) and gctl[GC_REGROUP]
+// (finalize_sweep when orphans pile up).  Both are read by every block BEFORE the first grid barrier and cleared after it,
+// so all blocks take the same path.
+#pragma once
+#include <cooperative_groups.h>
+#include "common.cuh"
+#include "mu_agg_kernel.cuh"
+#include "tau_group_kernel.cuh"
+
+namespace cg = cooperative_groups;
+
+struct MaintParams {
+    MuAggParams a;               // counts, tau, shape, table
+    TauGroup grp;                // grp.gctl == nullptr: no grouping
+    int *blk;                    // [4 * gridDim] block totals of the regroup scan
+    unsigned long long *zero64;  // per-sweep accumulators cleared here: the statistics ...
+    int nzero64;
+    unsigned long long *red_i;   // ... and [2] fixed-point ll | nchange
+};
+
+#define MAINT_THREADS 256
+
+// exclusive scan of four ints over the block (256 threads); returns the block totals in tot
+__device__ __forceinline__ int4 block_excl_scan4(int4 v, int4 &tot, int (*sh)[4])
+{
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int4 inc = v;
+#pragma unroll
+    for (int m = 1; m < 32; m <<= 1) {
+        const int x = __shfl_up_sync(DESMAN_FULL_MASK, inc.x, m), y = __shfl_up_sync(DESMAN_FULL_MASK, inc.y, m),
+                  z = __shfl_up_sync(DESMAN_FULL_MASK, inc.z, m), u = __shfl_up_sync(DESMAN_FULL_MASK, inc.w, m);
+        if (lane >= m) { inc.x += x; inc.y += y; inc.z += z; inc.w += u; }
+    }
+    __syncthreads();
+    if (lane == 31) { sh[w][0] = inc.x; sh[w][1] = inc.y; sh[w][2] = inc.z; sh[w][3] = inc.w; }
+    __syncthreads();
+    int4 off = make_int4(0, 0, 0, 0);
+    tot = make_int4(0, 0, 0, 0);
+    for (int i = 0; i < MAINT_THREADS / 32; i++) {
+        if (i < w) { off.x += sh[i][0]; off.y += sh[i][1]; off.z += sh[i][2]; off.w += sh[i][3]; }
+        tot.x += sh[i][0]; tot.y += sh[i][1]; tot.z += sh[i][2]; tot.w += sh[i][3];
+    }
+    return make_int4(off.x + inc.x - v.x, off.y + inc.y - v.y, off.z + inc.z - v.z, off.w + inc.w - v.w);
+}
+
+__global__ void __launch_bounds__(MAINT_THREADS) table_maintain_kernel(MaintParams p)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ int sh[MAINT_THREADS / 32][4];
+    const AggTable &t = p.a.t;
+    int *gctl = p.grp.gctl;
+    const size_t gtid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, gsz = (size_t)gridDim.x * blockDim.x;
+
+    const bool do_rebuild = t.ctl[0] != 0;
+    const bool do_regroup = gctl && gctl[GC_CALM] && (do_rebuild || gctl[GC_REGROUP] || !gctl[GC_HAVE]);
+    for (size_t i = gtid; i < (size_t)p.nzero64; i += gsz) p.zero64[i] = 0ull;
+    if (gtid < 2) p.red_i[gtid] = 0ull;
+    if (gtid == 0 && gctl) { gctl[GC_NWORK] = 0; gctl[GC_CURSOR] = 0; }
+    if (!do_rebuild && !do_regroup) return;
+
+    const int V = p.a.V, S = p.a.S, G = p.a.G;
+    const int lane = threadIdx.x & 31;
+    const int gw = (int)(gtid >> 5), nw = (int)(gsz >> 5);
+    if (do_rebuild) {
+        // ---- free every key, zero the used part of N
+        unsigned int used = *t.nslots;
+        if (used > t.cap_slots) used = t.cap_slots;
+        for (size_t i = gtid; i <= t.hmask; i += gsz) { t.keys[i] = MUB_EMPTY; t.ids[i] = -1; }
+        const size_t n = (size_t)used * S * 4;
+        for (size_t i = gtid; i < n; i += gsz) t.N[i] = 0ull;
+        grid.sync();
+        if (gtid == 0) { *t.nslots = 0u; t.ctl[3] = 0; t.ctl[0] = 0; if (gctl) gctl[GC_HAVE] = 0; }
+        grid.sync();
+        // ---- aggregation pass: one warp per site
+        for (int v = gw; v < V; v += nw) {
+            const unsigned long long code = load_tau_code(p.a.tau + (size_t)v * G, G, lane);
+            int id = 0;
+            if (lane == 0) id = agg_slot(t, code, true);
+            id = __shfl_sync(DESMAN_FULL_MASK, id, 0);
+            if (lane == 0 && p.grp.site_slot) p.grp.site_slot[v] = id;
+            unsigned long long *dst = t.N + (size_t)id * S * 4;
+            const int4 *src = p.a.counts + (size_t)v * S;
+            for (int s = lane; s < S; s += 32) {
+                const int4 n4 = ld_counts(src + s);
+                if (n4.x) atomicAdd(dst + s * 4 + 0, (unsigned long long)n4.x);
+                if (n4.y) atomicAdd(dst + s * 4 + 1, (unsigned long long)n4.y);
+                if (n4.z) atomicAdd(dst + s * 4 + 2, (unsigned long long)n4.z);
+                if (n4.w) atomicAdd(dst + s * 4 + 3, (unsigned long long)n4.w);
+            }
+        }
+    }
+    if (!do_regroup) return;
+    grid.sync();
+
+    // ---- regroup: counting sort of the sites by slot; slots with one site go to the singles list
+    unsigned int nslu = *t.nslots;
+    if (nslu > t.cap_slots) nslu = t.cap_slots;
+    const int nsl = (int)nslu;
+    for (size_t i = gtid; i < (size_t)nsl; i += gsz) p.grp.slot_cnt[i] = 0;
+    if (gtid == 0) { gctl[GC_ORPHANS] = 0; gctl[GC_REGROUP] = 0; }
+    grid.sync();
+    for (size_t v = gtid; v < (size_t)V; v += gsz) atomicAdd(p.grp.slot_cnt + p.grp.site_slot[v], 1);
+    grid.sync();
+    // scan, step 1: every block scans its segment of the slots: sites of multi-site patterns | full items | partial items |
+    // singles.  Full items (TG_ITEM_SITES sites) are numbered before all partial ones, so the dynamic schedule of the
+    // screening pass hands out the long items first and its tail is made of short ones.
+    const int seg = (nsl + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int lo = (int)blockIdx.x * seg, hi = min(nsl, lo + seg);
+    {
+        int4 carry = make_int4(0, 0, 0, 0);
+        for (int base = lo; base < hi; base += MAINT_THREADS) {
+            const int sl = base + (int)threadIdx.x;
+            const int c = (sl < hi) ? p.grp.slot_cnt[sl] : 0;
+            const int4 val = make_int4(c >= 2 ? c : 0, c >= 2 ? c / TG_ITEM_SITES : 0, (c >= 2 && c % TG_ITEM_SITES) ? 1 : 0, c == 1 ? 1 : 0);
+            int4 tot;
+            const int4 ex = block_excl_scan4(val, tot, sh);
+            if (sl < hi) {
+                p.grp.slot_start[sl] = (c == 1) ? carry.w + ex.w : carry.x + ex.x;
+                p.grp.slot_item[sl] = carry.y + ex.y;           // first full item (local numbering)
+                p.grp.slot_fill[sl] = carry.z + ex.z;           // partial item (local numbering); reset to 0 in step 3
+            }
+            carry.x += tot.x; carry.y += tot.y; carry.z += tot.z; carry.w += tot.w;
+        }
+        if (threadIdx.x == 0) {
+            p.blk[4 * blockIdx.x] = carry.x; p.blk[4 * blockIdx.x + 1] = carry.y; p.blk[4 * blockIdx.x + 2] = carry.z;
+            p.blk[4 * blockIdx.x + 3] = carry.w;
+        }
+    }
+    grid.sync();
+    // step 2: offsets of the blocks (a few hundred values: every thread of a block needs only its own block's offset)
+    int4 off, all;
+    {
+        int4 part = make_int4(0, 0, 0, 0), mine = make_int4(0, 0, 0, 0);
+        for (int b = (int)threadIdx.x; b < (int)gridDim.x; b += MAINT_THREADS) {
+            const int4 x = make_int4(p.blk[4 * b], p.blk[4 * b + 1], p.blk[4 * b + 2], p.blk[4 * b + 3]);
+            if (b < (int)blockIdx.x) { part.x += x.x; part.y += x.y; part.z += x.z; part.w += x.w; }
+            mine.x += x.x; mine.y += x.y; mine.z += x.z; mine.w += x.w;
+        }
+        block_excl_scan4(part, off, sh);
+        __syncthreads();
+        block_excl_scan4(mine, all, sh);
+        if (gtid == 0) { gctl[GC_NITEMS] = all.y + all.z; gctl[GC_NSINGLES] = all.w; gctl[GC_HAVE] = 1; }
+        __syncthreads();
+    }
+    // step 3: global positions and the items of this block's slots
+    for (int sl = lo + (int)threadIdx.x; sl < hi; sl += MAINT_THREADS) {
+        const int c = p.grp.slot_cnt[sl];
+        if (c == 1) p.grp.slot_start[sl] += off.w;
+        else if (c >= 2) {
+            const int st = p.grp.slot_start[sl] + off.x, it0 = p.grp.slot_item[sl] + off.y, itp = all.y + off.z + p.grp.slot_fill[sl];
+            p.grp.slot_start[sl] = st;
+            const int nfull = c / TG_ITEM_SITES;
+            for (int j = 0; j < nfull; j++) p.grp.items[it0 + j] = make_int4(sl, st + j * TG_ITEM_SITES, TG_ITEM_SITES, 0);
+            if (c % TG_ITEM_SITES) p.grp.items[itp] = make_int4(sl, st + nfull * TG_ITEM_SITES, c % TG_ITEM_SITES, 0);
+        }
+        p.grp.slot_fill[sl] = 0;
+    }
+    grid.sync();
+    for (size_t v = gtid; v < (size_t)V; v += gsz) {
+        const int sl = p.grp.site_slot[v];
+        if (p.grp.slot_cnt[sl] == 1) p.grp.singles[p.grp.slot_start[sl]] = (int)v;
+        else p.grp.order[p.grp.slot_start[sl] + atomicAdd(p.grp.slot_fill + sl, 1)] = (int)v;
+    }
+}
+
+// counts int32x4 -> FP32x4 copy for the screening pass (exact, counts <= 2^24) + per-site read totals rounded up
+__global__ void __launch_bounds__(256) counts_to_float_kernel(const int4 *__restrict__ counts, float4 *__restrict__ countsf,
+                                                              float *__restrict__ nsite, int V, int S)
+{
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (int v = gw; v < V; v += nw) {
+        long long tot = 0;
+        for (int s = lane; s < S; s += 32) {
+            const int4 n = counts[(size_t)v * S + s];
+            countsf[(size_t)v * S + s] = make_float4((float)n.x, (float)n.y, (float)n.z, (float)n.w);
+            tot += (long long)n.x + n.y + n.z + n.w;
+        }
+        tot = (long long)warp_sum_u64((unsigned long long)tot);
+        if (lane == 0) nsite[v] = __ll2float_ru(tot);
+    }
+}

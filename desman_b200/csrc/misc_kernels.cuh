@@ -168,6 +168,8 @@ struct FinalParams {
     const unsigned int *agg_nslots;   // pattern table bookkeeping: ask for a rebuild when too many slots were handed out
     int *agg_ctl;
     unsigned int agg_limit;
+    int *gctl;                // site-group control words (tau_group_kernel.cuh), or null
+    long long V_local;
     const double *gamma;      // [S][G] used for the prior
     const double *eta;        // [16]   used for the prior (eta_new in update())
     double *eta_commit;       // if non-null: eta_commit[0..15] = eta (the chain's eta <- eta_new)
@@ -210,6 +212,12 @@ __global__ void __launch_bounds__(256) finalize_sweep_kernel(FinalParams p)
             const long long used = (long long)*p.agg_nslots, live = used > stale ? used - stale : 0;
             p.agg_ctl[3] = (int)(stale > 0x3fffffff ? 0x3fffffff : stale);
             if (stale > live / 2 + 512 || used > (long long)p.agg_limit) p.agg_ctl[0] = 1;
+        }
+        if (p.gctl && p.it >= 0) {
+            // screening pass upkeep: it pays off while few sites flip; regroup when orphans (sites that left their group) pile up
+            p.gctl[GC_CALM] = (double)p.red_i[1] <= p.V_total / 16.0;
+            const long long lim = p.V_local / 128 > 64 ? p.V_local / 128 : 64;
+            if ((long long)p.gctl[GC_ORPHANS] > lim) p.gctl[GC_REGROUP] = 1;
         }
         p.scal[2] = ll; p.scal[3] = lp;
         if (p.it >= 0) {

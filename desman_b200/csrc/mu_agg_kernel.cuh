@@ -6,7 +6,7 @@
 // read observed as base a in sample s depend on the site only through its haplotype pattern tau_v: reads of all
 // sites with the same pattern are exchangeable, and the sum of their multinomials is ONE multinomial with the summed
 // count.  So:
-//   mu_aggregate_kernel   one warp per site: hash the 2G-bit pattern code into a slot (open addressing, atomicCAS),
+//   aggregation pass      (table_maintain_kernel) one warp per site: hash the 2G-bit pattern code into a slot (open addressing, atomicCAS),
 //                         add the site's S count cells into N[slot][s][a] (64-bit reductions); one HBM pass, needed only
 //                         after a state upload: afterwards the tau kernel moves the counts of the sites it flips
 //   mu_binomial_kernel    one warp per (slot, 32-sample chunk): per (s,a) a chain of conditional binomials over the
@@ -28,8 +28,9 @@
 // Persistent pattern table.  N[slot][s][a] = sum of the counts of all sites whose haplotype pattern is slot_code[slot].
 // Built by mu_aggregate_kernel, then kept current by the tau kernel (a site that changes pattern moves its counts),
 // so that in steady state (a handful of flips per sweep) no aggregation pass is needed.  ctl[0] = rebuild wanted
-// (host on state upload; finalize_sweep when stale slots pile up), ctl[1] = rebuild in progress, ctl[2] = overflow,
-// ctl[3] = flips since the last rebuild (upper bound of the number of stale slots).
+// (host on state upload; finalize_sweep when stale slots pile up; served and cleared by table_maintain_kernel,
+// maintain_kernel.cuh), ctl[1] unused, ctl[2] = overflow, ctl[3] = flips since the last rebuild (upper bound of the
+// number of stale slots).
 struct AggTable {
     unsigned long long *keys;        // [H] pattern codes (MUB_EMPTY = free)
     int *ids;                        // [H] slot id of the key (-1 until published)
@@ -89,8 +90,8 @@ __device__ __forceinline__ int agg_slot(const AggTable &t, unsigned long long co
 }
 
 // Move one site's counts between patterns (called by all lanes of the warp that owns the site).
-__device__ __forceinline__ void agg_move_site(const AggTable &t, unsigned long long code_old, unsigned long long code_new,
-                                              const int4 *tile, int lane)
+__device__ __forceinline__ int agg_move_site(const AggTable &t, unsigned long long code_old, unsigned long long code_new,
+                                             const int4 *tile, int lane)
 {
     int so = 0, sn = 0;
     if (lane == 0) { so = agg_slot(t, code_old, false); sn = agg_slot(t, code_new, true); }
@@ -104,48 +105,7 @@ __device__ __forceinline__ void agg_move_site(const AggTable &t, unsigned long l
         if (n.z) { atomicAdd(pn + s * 4 + 2, (unsigned long long)n.z); atomicAdd(po + s * 4 + 2, 0ull - (unsigned long long)n.z); }
         if (n.w) { atomicAdd(pn + s * 4 + 3, (unsigned long long)n.w); atomicAdd(po + s * 4 + 3, 0ull - (unsigned long long)n.w); }
     }
-}
-
-// Rebuild, step 1 (only when ctl[0]): free every key and zero the used part of N.
-__global__ void agg_reset_kernel(AggTable t)
-{
-    if (!t.ctl[0]) return;
-    const size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = i0; i <= t.hmask; i += st) { t.keys[i] = MUB_EMPTY; t.ids[i] = -1; }
-    unsigned int used = *t.nslots;
-    if (used > t.cap_slots) used = t.cap_slots;
-    const size_t n = (size_t)used * t.S * 4;
-    for (size_t i = i0; i < n; i += st) t.N[i] = 0ull;
-}
-// step 2 (one thread): hand the request over to the aggregation pass
-__global__ void agg_begin_kernel(AggTable t)
-{
-    t.ctl[1] = t.ctl[0];
-    if (t.ctl[0]) { *t.nslots = 0u; t.ctl[3] = 0; }
-    t.ctl[0] = 0;
-}
-
-// step 3 (only when ctl[1]): one warp per site
-__global__ void __launch_bounds__(256) mu_aggregate_kernel(MuAggParams p)
-{
-    if (!p.t.ctl[1]) return;
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    for (int v = gw; v < p.V; v += nw) {
-        const unsigned long long code = load_tau_code(p.tau + (size_t)v * p.G, p.G, lane);
-        int id = 0;
-        if (lane == 0) id = agg_slot(p.t, code, true);
-        id = __shfl_sync(DESMAN_FULL_MASK, id, 0);
-        unsigned long long *dst = p.t.N + (size_t)id * p.S * 4;
-        const int4 *src = p.counts + (size_t)v * p.S;
-        for (int s = lane; s < p.S; s += 32) {
-            const int4 n = ld_counts(src + s);
-            if (n.x) atomicAdd(dst + s * 4 + 0, (unsigned long long)n.x);
-            if (n.y) atomicAdd(dst + s * 4 + 1, (unsigned long long)n.y);
-            if (n.z) atomicAdd(dst + s * 4 + 2, (unsigned long long)n.z);
-            if (n.w) atomicAdd(dst + s * 4 + 3, (unsigned long long)n.w);
-        }
-    }
+    return sn;
 }
 
 // K4 on the table: sum_v sum_s sum_b n*log p = sum_slots sum_s sum_a N[slot][s][a]*log(sum_g gamma[s,g]*eta[tau_g,a])

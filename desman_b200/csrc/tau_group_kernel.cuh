@@ -1,0 +1,545 @@
+// desman_b200/csrc/tau_group_kernel.cuh -- K1g: pattern-grouped screening pass of the tau Gibbs update
+// (c_sample_tau.c:130-188), plus the bookkeeping that keeps the site groups current.
+//
+// Why.  In the per-site kernel (tau_kernel.cuh) every (v,g) step evaluates 12*S logs: 6e8 MUFU operations per sweep at
+// BASELINE config C3, a ~150 us floor, ten times the HBM floor of the count tensor.  But the log terms of a step,
+//     Wd[g][a][s][b] = log(P_sb - eta[cur_g][b]*gamma[s][g] + eta[a][b]*gamma[s][g]) - log P_sb,    P_sb = sum_h eta[tau_h][b]*gamma[s][h],
+// depend on the site only through its haplotype pattern tau_v (the key of the persistent pattern table, mu_agg_kernel.cuh),
+// and a converged chain has ~12*2^G patterns for V sites.  So the sites are grouped by pattern, the table Wd is built ONCE
+// per group (in shared memory, same FP32/MUFU arithmetic and error model as tier 1 of the per-site kernel), and the
+// log-likelihood differences of a site become a small dense contraction of its count row with that table:
+//     D[v][g][a] = sum_{s,b} n[v][s][b] * Wd[g][a][s][b]           (3*G*4*S FFMA per site, no transcendental)
+// As long as the pattern of a site does not change during its walk over the strains (no flip), the D of all G steps
+// come from the same table.  A step whose current base leads every other candidate by more than 60 nats after the rigorous
+// error bound is decided ("stay", exactly as tier 1 of the per-site kernel); a site with any undecided step is appended to a
+// work list together with the bit mask of those steps, and the per-site kernel then walks only the listed sites, skipping
+// the decided steps until the first flip.  Results are therefore identical to the per-site kernel's, draw for draw.
+//
+// Mapping.  One warp per work item (pattern, <= 128 sites); the warp owns a private Wd table in shared memory.  A pass
+// contracts 16 sites: lane = (r, o), r = 4 site rows of 4 sites each (register tile), o = 8 sample groups (s = o + 8k).
+// Every LDS.128 of the table feeds 16 FFMA (measured on B200: LDS.128 costs 4 LSU cycles per warp unless all 32 lanes
+// read the same address, tools/ubench; 4 sites per lane balance the LSU and FMA pipes).  Count rows are read as 128-bit
+// cells, 8 consecutive cells (one 128-B line) per site row and instruction, after a TMA bulk prefetch into L2 one pass
+// ahead (cp.async.bulk.prefetch.L2).  Partial sums are combined over the 8 sample groups with a transposing
+// butterfly (3 levels; every lane ends with the complete sums of GB/2 (site, strain) pairs).
+#pragma once
+#include "common.cuh"
+#include "mu_agg_kernel.cuh"
+#include "tau_kernel.cuh"
+
+#define TG_ITEM_SITES 128
+#define TG_PASS_SITES 16
+#define TG_MAX_WARPS 4
+
+struct TauGroup {
+    int *site_slot;     // [V] table slot of the site's current pattern (mu_aggregate / agg_move_site keep it)
+    int *order;         // [V] sites of multi-site patterns, sorted by slot
+    int *singles;       // [V] sites that are alone in their pattern (straight to the per-site kernel)
+    int4 *items;        // {slot, begin in order[], count, 0}
+    uint2 *work;        // [V] {site, mask of undecided strains}
+    int *slot_cnt, *slot_fill, *slot_start, *slot_item;   // [cap_slots] regroup scratch
+    int *gctl;          // [GC_COUNT]
+};
+
+struct TauGroupParams {
+    const float4 *countsf;   // [V][S] counts as FP32 (exact: counts <= 2^24)
+    const float *nsite;      // [V] reads of the site, rounded up
+    const double *gamma;     // [S][G]
+    const double *eta;       // [16]
+    const uint32_t *words;   // MT19937 words [V*G] (a zero word means u == 0: per-site kernel), or nullptr (Philox: u > 0)
+    int V, S, G;
+    const unsigned long long *slot_code;
+    TauGroup grp;
+    unsigned long long *tier_counts;
+};
+
+__device__ __forceinline__ float4 ld_countsf(const float4 *p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ void l2_prefetch_row(const void *p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// one level of the transposing butterfly: N values per lane -> N/2; lanes with (lane & mask) keep the upper half
+template <int N>
+__device__ __forceinline__ void tg_reduce_level(float (&v)[N], bool upper, int mask)
+{
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) {
+        const float send = upper ? v[i] : v[i + N / 2];
+        const float keep = upper ? v[i + N / 2] : v[i];
+        v[i] = keep + __shfl_xor_sync(DESMAN_FULL_MASK, send, mask);
+    }
+}
+
+// Table layout: Wd[s][row] float4 (b = 0..3), row = g*3 + j, sample-major with one float4 of padding per sample so that
+// the 8 lanes of a quarter warp (consecutive s) hit 8 different bank groups and the rows of one sample are immediate
+// offsets of one base address.  Sp = S rounded up to 16 (the sample loop is unrolled by two 8-sample steps).
+static inline size_t tg_table_bytes(int S, int G, int GB)
+{
+    const size_t Sp = (size_t)((S + 15) & ~15), nGB = (size_t)((G + GB - 1) / GB);
+    return Sp * (nGB * GB * 3 + 1) * sizeof(float4);
+}
+static inline size_t tg_shared_bytes(int S, int G)
+{
+    const size_t Sp = (size_t)((S + 15) & ~15);
+    return (size_t)G * Sp * (sizeof(double) + sizeof(float)) + 16 * sizeof(double) + 4 * sizeof(float4);
+}
+
+// acc[i][j] += n[i] . Wd[s][j]   for the 4 sites of the lane and the NJ rows of one strain block
+template <int NJ>
+__device__ __forceinline__ void tg_step(float (&acc)[4 * NJ], const float4 (&n)[4], const float4 *__restrict__ Ws)
+{
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+        const float4 w = Ws[j];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            float a = acc[i * NJ + j];
+            a = fmaf(n[i].x, w.x, a); a = fmaf(n[i].y, w.y, a); a = fmaf(n[i].z, w.z, a); a = fmaf(n[i].w, w.w, a);
+            acc[i * NJ + j] = a;
+        }
+    }
+}
+
+template <int GB>
+__global__ void __launch_bounds__(TG_MAX_WARPS * 32, 1) tau_group_kernel(TauGroupParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int *gctl = p.grp.gctl;
+    if (!(gctl[GC_HAVE] && gctl[GC_CALM])) return;
+    const int S = p.S, G = p.G;
+    const int Sp = (S + 15) & ~15, nk = Sp >> 3;
+    const int nGB = (G + GB - 1) / GB;
+    constexpr int NJ = GB * 3;            // table rows of one strain block
+    constexpr int NV = 4 * NJ;            // partial sums per lane and pass
+    constexpr int PP = GB / 2;            // (site, strain) pairs a lane ends up with
+    const int STR = nGB * NJ + 1;         // float4 per sample (odd: conflict-free)
+
+    double *gT = reinterpret_cast<double *>(smem_raw);                    // [G][Sp]
+    double *eta_s = gT + (size_t)G * Sp;                                  // [16]
+    float4 *eta32 = reinterpret_cast<float4 *>(eta_s + 16);               // [4]
+    float *gT32 = reinterpret_cast<float *>(eta32 + 4);                   // [G][Sp]
+    float4 *Wall = reinterpret_cast<float4 *>(gT32 + (size_t)G * Sp);     // [warps][Sp][STR]
+    __shared__ unsigned int gmin_bits, emin_bits;
+
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { gmin_bits = 0x7f800000u; emin_bits = 0x7f800000u; }
+    __syncthreads();
+    float gmin_l = __int_as_float(0x7f800000);
+    for (int i = threadIdx.x; i < G * Sp; i += blockDim.x) {
+        const int g = i / Sp, s = i - g * Sp;
+        const double x = (s < S) ? p.gamma[(size_t)s * G + g] : 0.0;
+        gT[i] = x;
+        gT32[i] = (float)x;
+        if (s < S) gmin_l = fminf(gmin_l, fmaxf((float)x, 0.f));
+    }
+    atomicMin(&gmin_bits, __float_as_uint(gmin_l));
+    if (threadIdx.x < 16) {
+        eta_s[threadIdx.x] = p.eta[threadIdx.x];
+        reinterpret_cast<float *>(eta32)[threadIdx.x] = (float)p.eta[threadIdx.x];
+        atomicMin(&emin_bits, __float_as_uint(fmaxf((float)p.eta[threadIdx.x], 0.f)));
+    }
+    __syncthreads();
+    // launch-level a-priori error bound per read (log2 units), same model as tier 1 of tau_sample_kernel:
+    // every table entry is lg2(q) - lg2(P) with q, P >= qmin; the FP32 sum of one output passes through 4*nk FFMA and
+    // 3 shuffle adds, and the subtraction lq - lP adds one more rounding per unit of |lg2|
+    const float qmin = 0.99f * __uint_as_float(gmin_bits) * __uint_as_float(emin_bits);
+    const bool fast_ok = qmin >= TAU_QMIN;
+    const float mq0 = fmaxf(1.0f, 1.0f - log2f(fmaxf(qmin, TAU_QMIN)));
+    const float c1 = 2.3841858e-7f + (float)(4 * nk + 9) * 5.9604645e-8f;
+    const float e_read = TAU_C0 + c1 * (2.0f * mq0) + TAU_CANCEL(G) / fmaxf(qmin, TAU_QMIN);
+    const float LN2 = 0.69314718f;
+    const float bn_scale = e_read * LN2 * 1.0001f;
+
+    float4 *W = Wall + (size_t)wib * Sp * STR;
+    const int r = lane >> 3, o = lane & 7;
+    const bool owner = (o & 1) == 0;
+    const int isl = o >> 1;                                   // site (within the row) this lane decides for
+    const uint32_t fullG = (G >= 32) ? 0xffffffffu : ((1u << G) - 1u);
+    const uint32_t row_bytes = (uint32_t)S * 16u;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    unsigned int n_decided = 0;
+
+    while (true) {
+        int it = 0;
+        if (lane == 0) it = atomicAdd(p.grp.gctl + GC_CURSOR, 1);
+        it = __shfl_sync(DESMAN_FULL_MASK, it, 0);
+        if (it >= gctl[GC_NITEMS]) break;
+        const int4 item = p.grp.items[it];
+        const int slot = item.x, count = item.z;
+        const int *ord = p.grp.order + item.y;
+        const uint64_t code = p.slot_code[slot];
+        // sites of the first pass (index 0 stands in for the missing sites of a partial pass: computed, never used)
+        int v[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) { const int idx = r * 4 + i; v[i] = ord[idx < count ? idx : 0]; }
+        if (lane < TG_PASS_SITES && lane < count) l2_prefetch_row(p.countsf + (size_t)ord[lane] * S, row_bytes);
+
+        // ---- the pattern's table: Wd[s][g*3+j][b] = lg2(base_sb + eta[a_j][b]*gamma[s][g]) - lg2(P_sb), a_j = (cur_g+1+j)&3
+        __syncwarp();
+        for (int s = lane; s < Sp; s += 32) {
+            float4 *Ws = W + (size_t)s * STR;
+            if (s < S && fast_ok) {
+                double P0 = 0.0, P1 = 0.0, P2 = 0.0, P3 = 0.0;
+                for (int h = 0; h < G; h++) {
+                    const double2 *e = reinterpret_cast<const double2 *>(eta_s + 4 * code_get(code, h));
+                    const double2 e01 = e[0], e23 = e[1];
+                    const double gm = gT[h * Sp + s];
+                    P0 = fma(e01.x, gm, P0); P1 = fma(e01.y, gm, P1); P2 = fma(e23.x, gm, P2); P3 = fma(e23.y, gm, P3);
+                }
+                const float l0 = lg2_fast((float)P0), l1 = lg2_fast((float)P1), l2 = lg2_fast((float)P2), l3 = lg2_fast((float)P3);
+                for (int g = 0; g < G; g++) {
+                    const int cur = code_get(code, g);
+                    const double2 *ecp = reinterpret_cast<const double2 *>(eta_s + 4 * cur);
+                    const double2 ec01 = ecp[0], ec23 = ecp[1];
+                    const double gg = gT[g * Sp + s];
+                    const float gf = gT32[g * Sp + s];
+                    const float q0 = fmaxf((float)fma(-ec01.x, gg, P0), 0.f), q1 = fmaxf((float)fma(-ec01.y, gg, P1), 0.f),
+                                q2 = fmaxf((float)fma(-ec23.x, gg, P2), 0.f), q3 = fmaxf((float)fma(-ec23.y, gg, P3), 0.f);
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        const float4 ea = eta32[(cur + 1 + j) & 3];
+                        float4 w;
+                        w.x = lg2_fast(fmaf(ea.x, gf, q0)) - l0;
+                        w.y = lg2_fast(fmaf(ea.y, gf, q1)) - l1;
+                        w.z = lg2_fast(fmaf(ea.z, gf, q2)) - l2;
+                        w.w = lg2_fast(fmaf(ea.w, gf, q3)) - l3;
+                        Ws[g * 3 + j] = w;
+                    }
+                }
+                for (int t = G * 3; t < nGB * NJ; t++) Ws[t] = zero4;
+            } else {
+                for (int t = 0; t < nGB * NJ; t++) Ws[t] = zero4;
+            }
+        }
+        __syncwarp();
+
+        float4 na[4];                                                  // count cells of sample step 0 of the current pass
+#pragma unroll
+        for (int i = 0; i < 4; i++) na[i] = (o < S) ? ld_countsf(p.countsf + (size_t)v[i] * S + o) : zero4;
+
+        for (int base = 0; base < count; base += TG_PASS_SITES) {
+            const bool more = base + TG_PASS_SITES < count;
+            // next pass: its site indices now (used at the end of this pass), its rows into L2 while this pass is contracted
+            int vn[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { const int idx = base + TG_PASS_SITES + r * 4 + i; vn[i] = ord[idx < count ? idx : 0]; }
+            if (more && lane < TG_PASS_SITES && base + TG_PASS_SITES + lane < count)
+                l2_prefetch_row(p.countsf + (size_t)ord[base + TG_PASS_SITES + lane] * S, row_bytes);
+            const bool have_own = base + r * 4 + isl < count;
+            const int vown = v[0] * (isl == 0) + v[1] * (isl == 1) + v[2] * (isl == 2) + v[3] * (isl == 3);
+            const float nown = p.nsite[vown];
+            const int sown = p.grp.site_slot[vown];
+            const float4 *row[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) row[i] = p.countsf + (size_t)v[i] * S + o;
+            uint32_t mask = 0;
+
+            for (int gb = 0; gb < nGB; gb++) {
+                const float4 *Wb = W + (size_t)o * STR + gb * NJ;
+                float acc[NV];
+#pragma unroll
+                for (int i = 0; i < NV; i++) acc[i] = 0.f;
+                if (gb > 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; i++) na[i] = (o < S) ? ld_countsf(row[i]) : zero4;
+                }
+                float4 nb[4];
+                for (int k = 0; k < nk; k += 2) {
+                    const int s1 = o + 8 * (k + 1), s2 = o + 8 * (k + 2);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) nb[i] = (s1 < S) ? ld_countsf(row[i] + 8 * (k + 1)) : zero4;
+                    tg_step<NJ>(acc, na, Wb + (size_t)(8 * k) * STR);
+#pragma unroll
+                    for (int i = 0; i < 4; i++) na[i] = (s2 < S) ? ld_countsf(row[i] + 8 * (k + 2)) : zero4;
+                    tg_step<NJ>(acc, nb, Wb + (size_t)(8 * k + 8) * STR);
+                }
+                if (gb == nGB - 1 && more) {
+                    // first sample step of the next pass: in flight during the reduction below
+#pragma unroll
+                    for (int i = 0; i < 4; i++) na[i] = (o < S) ? ld_countsf(p.countsf + (size_t)vn[i] * S + o) : zero4;
+                }
+                // combine the 8 sample groups: lane o ends with values [o*NV/8, (o+1)*NV/8) = pairs (isl, gl = (o&1)*PP + q)
+                tg_reduce_level<NV>(acc, (o & 4) != 0, 4);
+                tg_reduce_level<NV / 2>(reinterpret_cast<float(&)[NV / 2]>(acc), (o & 2) != 0, 2);
+                tg_reduce_level<NV / 4>(reinterpret_cast<float(&)[NV / 4]>(acc), (o & 1) != 0, 1);
+                const float bn = nown * bn_scale + 1e-6f;
+                uint32_t ml = 0;
+#pragma unroll
+                for (int q = 0; q < PP; q++) {
+                    const float d0 = acc[3 * q], d1 = acc[3 * q + 1], d2 = acc[3 * q + 2];
+                    const float top = fmaxf(fmaxf(d0, d1), d2);
+                    const bool fin = (fabsf(d0) + fabsf(d1) + fabsf(d2)) < 1.0e30f;
+                    const bool stay = fin && (top * LN2 + bn < -TAU_GAP);
+                    if (!stay) ml |= 1u << ((o & 1) * PP + q);
+                }
+                ml |= __shfl_xor_sync(DESMAN_FULL_MASK, ml, 1);
+                mask |= ml << (gb * GB);
+            }
+            mask &= fullG;
+            bool push = false;
+            if (owner && have_own) {
+                if (!fast_ok || sown != slot) mask = fullG;                           // orphan: its pattern is not this group's
+                if (p.words) {
+                    const uint32_t *w = p.words + (size_t)vown * G;
+                    for (int g = 0; g < G; g++) if (w[g] == 0u) mask = fullG;         // u == 0 (c_sample_tau.c:174): reference-order path
+                }
+                push = mask != 0u;
+                if (!push) n_decided += (unsigned int)G;
+            }
+            const unsigned int bal = __ballot_sync(DESMAN_FULL_MASK, push);
+            if (bal) {
+                int pos = 0;
+                if (lane == 0) pos = atomicAdd(p.grp.gctl + GC_NWORK, __popc(bal));
+                pos = __shfl_sync(DESMAN_FULL_MASK, pos, 0) + __popc(bal & ((1u << lane) - 1u));
+                if (push) p.grp.work[pos] = make_uint2((unsigned int)vown, mask);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) v[i] = vn[i];
+        }
+    }
+    n_decided = (unsigned int)warp_sum_u64((unsigned long long)n_decided);
+    if (lane == 0 && n_decided && p.tier_counts) atomicAdd(p.tier_counts, (unsigned long long)n_decided);
+}
+
+// =====================================================================================================================
+// Tensor-core form of the screening pass (used when every count is < 2048, i.e. exact in TF32).
+//
+// The contraction D[site][col] = sum_{s,b} n[site][s][b] * Wd[s][col][b], col = g*3 + j, is a [16 sites x 4S] x [4S x 3G]
+// product per pass: warp-level mma.sync m16n8k8 (TF32 operands, FP32 accumulators).  The k index of one MMA is laid
+// out as k = t -> (sample s0+t, base beta), k = t+4 -> (sample s0+t, base beta+1) (t = lane & 3, beta = 0 or 2), so that a
+// lane's A fragment of the two MMAs of a 4-sample group is exactly one 128-bit count cell per site row (rows g and
+// g+8, g = lane >> 2) and its B fragment is one 128-bit word Wd[s0+t][col = 8*tile + g] of the table.  The FP32 table
+// entry is split on the fly into a TF32 head (11 significant bits) and a remainder; two MMAs per entry recover it to
+// ~2^-20 relative.  Counts are integers < 2^11: exact.
+// Error model (on top of the per-entry model of the FFMA form): representation of Wd by head + truncated remainder
+// <= 2^-20 |Wd|; every MMA accumulation step is charged 2^-20 of the running magnitude (documented tensor-core behaviour is
+// exact products, alignment and truncation to >= 24 bits: 8x margin); Sp/4 groups x 2 x 2 steps per output.  With the
+// measured max |Wd| of the item that is ~1e-3 log2 units per read; tests/test_gpu_group.py checks the measured error of D
+// against this bound on random inputs.
+// One CTA (4 warps) per work item; the warps share the item's table and take its 16-site passes round robin.
+#define TGM_WARPS 4
+
+static inline int tgm_tiles(int G) { return (3 * G + 7) / 8; }
+static inline size_t tgm_table_bytes(int S, int G)
+{
+    const size_t Sp = (size_t)((S + 15) & ~15);
+    return Sp * (size_t)(8 * tgm_tiles(G) + 2) * sizeof(float4);
+}
+
+__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+{
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int NT>
+__device__ __forceinline__ void tgm_group(float (&ch)[NT][4], float (&cl)[NT][4], const float4 &cA, const float4 &cB,
+                                          const float4 *__restrict__ Wq)
+{
+    const uint32_t ax = __float_as_uint(cA.x), ay = __float_as_uint(cA.y), az = __float_as_uint(cA.z), aw = __float_as_uint(cA.w);
+    const uint32_t bx = __float_as_uint(cB.x), by = __float_as_uint(cB.y), bz = __float_as_uint(cB.z), bw = __float_as_uint(cB.w);
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+        const float4 w = Wq[8 * nt];
+        const uint32_t hx = __float_as_uint(w.x) & 0xffffe000u, hy = __float_as_uint(w.y) & 0xffffe000u,
+                       hz = __float_as_uint(w.z) & 0xffffe000u, hw = __float_as_uint(w.w) & 0xffffe000u;
+        const uint32_t lx = __float_as_uint(w.x - __uint_as_float(hx)), ly = __float_as_uint(w.y - __uint_as_float(hy)),
+                       lz = __float_as_uint(w.z - __uint_as_float(hz)), lw = __float_as_uint(w.w - __uint_as_float(hw));
+        mma_tf32(ch[nt], ax, bx, ay, by, hx, hy);
+        mma_tf32(cl[nt], ax, bx, ay, by, lx, ly);
+        mma_tf32(ch[nt], az, bz, aw, bw, hz, hw);
+        mma_tf32(cl[nt], az, bz, aw, bw, lz, lw);
+    }
+}
+
+template <int NT>
+__global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGroupParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int *gctl = p.grp.gctl;
+    if (!(gctl[GC_HAVE] && gctl[GC_CALM])) return;
+    const int S = p.S, G = p.G;
+    const int Sp = (S + 15) & ~15, nq = Sp >> 2;      // 4-sample groups
+    constexpr int STR = 8 * NT + 2;                   // float4 per sample: = 2 (mod 8) -> conflict-free fragment loads
+
+    double *gT = reinterpret_cast<double *>(smem_raw);                    // [G][Sp]
+    double *eta_s = gT + (size_t)G * Sp;                                  // [16]
+    float4 *eta32 = reinterpret_cast<float4 *>(eta_s + 16);               // [4]
+    float *gT32 = reinterpret_cast<float *>(eta32 + 4);                   // [G][Sp]
+    float4 *W = reinterpret_cast<float4 *>(gT32 + (size_t)G * Sp);        // [Sp][STR]
+    __shared__ unsigned int gmin_bits, emin_bits, wmax_bits[2];
+    __shared__ int s_it[2];
+
+    const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
+    if (tid == 0) { gmin_bits = 0x7f800000u; emin_bits = 0x7f800000u; wmax_bits[0] = 0u; wmax_bits[1] = 0u; s_it[0] = atomicAdd(p.grp.gctl + GC_CURSOR, 1); }
+    __syncthreads();
+    float gmin_l = __int_as_float(0x7f800000);
+    for (int i = tid; i < G * Sp; i += blockDim.x) {
+        const int g = i / Sp, s = i - g * Sp;
+        const double x = (s < S) ? p.gamma[(size_t)s * G + g] : 0.0;
+        gT[i] = x;
+        gT32[i] = (float)x;
+        if (s < S) gmin_l = fminf(gmin_l, fmaxf((float)x, 0.f));
+    }
+    atomicMin(&gmin_bits, __float_as_uint(gmin_l));
+    if (tid < 16) {
+        eta_s[tid] = p.eta[tid];
+        reinterpret_cast<float *>(eta32)[tid] = (float)p.eta[tid];
+        atomicMin(&emin_bits, __float_as_uint(fmaxf((float)p.eta[tid], 0.f)));
+    }
+    __syncthreads();
+    const float qmin = 0.99f * __uint_as_float(gmin_bits) * __uint_as_float(emin_bits);
+    const bool fast_ok = qmin >= TAU_QMIN;
+    const float mq0 = fmaxf(1.0f, 1.0f - log2f(fmaxf(qmin, TAU_QMIN)));
+    // per read, log2 units: entry model (relative parts, lg2.approx floors, lg2.approx and the lq - lP rounding per unit of
+    // |lg2|, FP64 cancellation) + [TF32 split + Sp accumulation steps] * 2^-20 * max|Wd| of the item
+    const float e_entry = TAU_C0 + (2.3841858e-7f + 5.9604645e-8f) * (2.0f * mq0) + TAU_CANCEL(G) / fmaxf(qmin, TAU_QMIN);
+    const float e_mma = (float)(Sp + 1) * 9.5367432e-7f;
+    const float LN2 = 0.69314718f;
+
+    const int g8 = lane >> 2, t4 = lane & 3;
+    const uint32_t fullG = (G >= 32) ? 0xffffffffu : ((1u << G) - 1u);
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int nitems = gctl[GC_NITEMS];
+    // build tasks: (sample, chunk of strains); H chunks so that the CTA's threads are all busy
+    const int H = max(1, min(G, (int)blockDim.x / Sp)), GH = (G + H - 1) / H;
+    unsigned int n_decided = 0;
+
+    for (int iter = 0;; iter++) {
+        const int it = s_it[iter & 1];
+        if (it >= nitems) break;
+        int nxt = 0;
+        if (tid == 0) nxt = atomicAdd(p.grp.gctl + GC_CURSOR, 1);          // in flight while this item is processed
+        const int4 item = p.grp.items[it];
+        const int slot = item.x, count = item.z;
+        const int *ord = p.grp.order + item.y;
+        const uint64_t code = p.slot_code[slot];
+        // first pass of this warp: sites (rows g8 and g8+8) -- issued before the table build hides their latency
+        int base = wib * TG_PASS_SITES;
+        int v0 = ord[base + g8 < count ? base + g8 : 0], v1 = ord[base + g8 + 8 < count ? base + g8 + 8 : 0];
+
+        // ---- the pattern's table: Wd[s][g*3+j][b] = lg2(base_sb + eta[a_j][b]*gamma[s][g]) - lg2(P_sb), a_j = (cur_g+1+j)&3
+        float wmax = 0.f;
+        for (int task = tid; task < Sp * H; task += blockDim.x) {
+            const int s = task % Sp, h = task / Sp;
+            const int glo = h * GH, ghi = min(G, glo + GH);
+            float4 *Ws = W + (size_t)s * STR;
+            if (s < S && fast_ok) {
+                double P0 = 0.0, P1 = 0.0, P2 = 0.0, P3 = 0.0;
+                for (int hh = 0; hh < G; hh++) {
+                    const double2 *e = reinterpret_cast<const double2 *>(eta_s + 4 * code_get(code, hh));
+                    const double2 e01 = e[0], e23 = e[1];
+                    const double gm = gT[hh * Sp + s];
+                    P0 = fma(e01.x, gm, P0); P1 = fma(e01.y, gm, P1); P2 = fma(e23.x, gm, P2); P3 = fma(e23.y, gm, P3);
+                }
+                const float l0 = lg2_fast((float)P0), l1 = lg2_fast((float)P1), l2 = lg2_fast((float)P2), l3 = lg2_fast((float)P3);
+                for (int g = glo; g < ghi; g++) {
+                    const int cur = code_get(code, g);
+                    const double2 *ecp = reinterpret_cast<const double2 *>(eta_s + 4 * cur);
+                    const double2 ec01 = ecp[0], ec23 = ecp[1];
+                    const double gg = gT[g * Sp + s];
+                    const float gf = gT32[g * Sp + s];
+                    const float q0 = fmaxf((float)fma(-ec01.x, gg, P0), 0.f), q1 = fmaxf((float)fma(-ec01.y, gg, P1), 0.f),
+                                q2 = fmaxf((float)fma(-ec23.x, gg, P2), 0.f), q3 = fmaxf((float)fma(-ec23.y, gg, P3), 0.f);
+#pragma unroll
+                    for (int j = 0; j < 3; j++) {
+                        const float4 ea = eta32[(cur + 1 + j) & 3];
+                        float4 w;
+                        w.x = lg2_fast(fmaf(ea.x, gf, q0)) - l0;
+                        w.y = lg2_fast(fmaf(ea.y, gf, q1)) - l1;
+                        w.z = lg2_fast(fmaf(ea.z, gf, q2)) - l2;
+                        w.w = lg2_fast(fmaf(ea.w, gf, q3)) - l3;
+                        wmax = fmaxf(wmax, fmaxf(fmaxf(fabsf(w.x), fabsf(w.y)), fmaxf(fabsf(w.z), fabsf(w.w))));
+                        Ws[g * 3 + j] = w;
+                    }
+                }
+                if (h == H - 1) for (int c = G * 3; c < 8 * NT; c++) Ws[c] = zero4;
+            } else {
+                for (int c = glo * 3; c < (h == H - 1 ? 8 * NT : ghi * 3); c++) Ws[c] = zero4;
+            }
+        }
+        wmax = warp_max(wmax);
+        if (lane == 0) atomicMax(&wmax_bits[iter & 1], __float_as_uint(wmax));
+        __syncthreads();
+        if (tid == 0) wmax_bits[(iter + 1) & 1] = 0u;
+        const float bn_scale = (e_entry + e_mma * __uint_as_float(wmax_bits[iter & 1])) * LN2 * 1.0001f;
+
+        for (; base < count; base += TGM_WARPS * TG_PASS_SITES) {
+            const int nb = base + TGM_WARPS * TG_PASS_SITES;               // this warp's next pass
+            const int vn0 = ord[nb + g8 < count ? nb + g8 : 0], vn1 = ord[nb + g8 + 8 < count ? nb + g8 + 8 : 0];
+            const bool have0 = base + g8 < count, have1 = base + g8 + 8 < count;
+            const float n0 = p.nsite[v0], n1 = p.nsite[v1];
+            const int sl0 = p.grp.site_slot[v0], sl1 = p.grp.site_slot[v1];
+            const float4 *rowA = p.countsf + (size_t)v0 * S + t4, *rowB = p.countsf + (size_t)v1 * S + t4;
+            const float4 *Wq = W + (size_t)t4 * STR + g8;
+            float ch[NT][4], cl[NT][4];
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int i = 0; i < 4; i++) { ch[nt][i] = 0.f; cl[nt][i] = 0.f; }
+            // 4-sample groups, four at a time: 8 cells in flight per lane
+            for (int q = 0; q < nq; q += 4) {
+                float4 cA[4], cB[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const bool ok = 4 * (q + u) + t4 < S;
+                    cA[u] = ok ? ld_countsf(rowA + 4 * (q + u)) : zero4;
+                    cB[u] = ok ? ld_countsf(rowB + 4 * (q + u)) : zero4;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) tgm_group<NT>(ch, cl, cA[u], cB[u], Wq + (size_t)(4 * (q + u)) * STR);
+            }
+            // a strain is decided "stay" iff each of its three candidates trails the current base by > 60 nats after the bound
+            const float bn0 = n0 * bn_scale + 1e-6f, bn1 = n1 * bn_scale + 1e-6f;
+            uint32_t m0 = 0, m1 = 0;
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++)
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const int col = 8 * nt + 2 * t4 + i;
+                    if (col < 3 * G) {
+                        const int g = col / 3;
+                        const float d0 = ch[nt][i] + cl[nt][i], d1 = ch[nt][2 + i] + cl[nt][2 + i];
+                        if (!(d0 * LN2 + bn0 < -TAU_GAP)) m0 |= 1u << g;
+                        if (!(d1 * LN2 + bn1 < -TAU_GAP)) m1 |= 1u << g;
+                    }
+                }
+            m0 |= __shfl_xor_sync(DESMAN_FULL_MASK, m0, 1); m0 |= __shfl_xor_sync(DESMAN_FULL_MASK, m0, 2);
+            m1 |= __shfl_xor_sync(DESMAN_FULL_MASK, m1, 1); m1 |= __shfl_xor_sync(DESMAN_FULL_MASK, m1, 2);
+            // lanes t4 == 0 / 1 own the sites of rows g8 / g8+8
+            const bool own = (t4 == 0 && have0) || (t4 == 1 && have1);
+            const int vown = (t4 == 0) ? v0 : v1;
+            uint32_t mask = ((t4 == 0) ? m0 : m1) & fullG;
+            bool push = false;
+            if (own) {
+                if (!fast_ok || ((t4 == 0) ? sl0 : sl1) != slot) mask = fullG;      // orphan: its pattern is not this group's
+                if (p.words) {
+                    const uint32_t *w = p.words + (size_t)vown * G;
+                    for (int g = 0; g < G; g++) if (w[g] == 0u) mask = fullG;         // u == 0 (c_sample_tau.c:174): reference-order path
+                }
+                push = mask != 0u;
+                if (!push) n_decided += (unsigned int)G;
+            }
+            const unsigned int bal = __ballot_sync(DESMAN_FULL_MASK, push);
+            if (bal) {
+                int pos = 0;
+                if (lane == 0) pos = atomicAdd(p.grp.gctl + GC_NWORK, __popc(bal));
+                pos = __shfl_sync(DESMAN_FULL_MASK, pos, 0) + __popc(bal & ((1u << lane) - 1u));
+                if (push) p.grp.work[pos] = make_uint2((unsigned int)vown, mask);
+            }
+            v0 = vn0; v1 = vn1;
+        }
+        if (tid == 0) s_it[(iter + 1) & 1] = nxt;
+        __syncthreads();
+    }
+    n_decided = (unsigned int)warp_sum_u64((unsigned long long)n_decided);
+    if (lane == 0 && n_decided && p.tier_counts) atomicAdd(p.tier_counts, (unsigned long long)n_decided);
+}

@@ -41,6 +41,12 @@ struct TauParams {
     uint32_t *tau_last;      // [V][G] iteration at which the current base was adopted
     uint32_t iter;           // iteration index inside the current update() call
     int exact_only;          // 1: every (v,g) step takes the FP64 reference-order path (validation)
+    // grouped mode (tau_group_kernel.cuh): walk only the listed sites and, until the first flip of a site, only the
+    // strains the screening pass left undecided.  Active iff gctl[GC_HAVE] && gctl[GC_CALM] (same test as the screening pass).
+    const uint2 *work;       // {site, mask of undecided strains}, gctl[GC_NWORK] entries; nullptr: every site, every strain
+    const int *singles;      // sites alone in their pattern, gctl[GC_NSINGLES] entries
+    int *gctl;
+    int *site_slot;          // [V] slot of the site's pattern, kept current on flips
     unsigned long long *tier_counts;  // [3] += draws decided by tier 1 / 2 / 3 (or nullptr)
 };
 
@@ -271,7 +277,21 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
     const float cancel0 = ccan / fmaxf(qmin, TAU_QMIN);                     // a-priori bound of the P/q amplification
     unsigned int flips = 0, n1 = 0, n2 = 0, n3 = 0;
 
-    for (int v = gw; v < p.V; v += nw) {
+    int nsite = p.V, nwork = 0;
+    bool listed = false;
+    if (p.work && p.gctl[GC_HAVE] && p.gctl[GC_CALM]) {
+        listed = true;
+        nwork = p.gctl[GC_NWORK];
+        nsite = nwork + p.gctl[GC_NSINGLES];
+    }
+
+    for (int i = gw; i < nsite; i += nw) {
+        int v = i;
+        uint32_t todo = 0xffffffffu;                 // strains the screening pass did not decide
+        if (listed) {
+            if (i < nwork) { const uint2 e = p.work[i]; v = (int)e.x; todo = e.y; }
+            else v = p.singles[i - nwork];
+        }
         const int4 *src = p.counts + (size_t)v * S;
         uint64_t code = load_tau_code(p.tau + (size_t)v * G, G, lane);
         const uint64_t code_in = code;
@@ -309,11 +329,13 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
         __syncwarp();
 
         for (int g = 0; g < G; g++) {
+            if (!((todo >> g) & 1u) && code == code_in) { n1++; continue; }   // decided "stay" by the screening pass
             const int cur = code_get(code, g);
             const uint32_t w = ww[g];
-            const double u = (double)w / 4294967296.0;              // gsl_rng_uniform, c_sample_tau.c:174
+            // MT19937 mode: gsl_rng_uniform, c_sample_tau.c:174 (u = 0 possible).  Philox mode: mid-point of the word's cell.
+            const double u = p.words ? (double)w / 4294967296.0 : ((double)w + 0.5) / 4294967296.0;
             int t = -1;
-            if (fast_ok && w != 0u) {
+            if (fast_ok && (w != 0u || !p.words)) {
                 // ---- tier 1: D_j = (E_j - KK)*ln2 = L(a_j) - L(cur), j = 0..2, with the a-priori bounds from qmin
                 const double *eta_cur = eta_s + 4 * cur;
                 float E0, E1, E2, KK, mq;
@@ -376,7 +398,10 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
         }
         if (code != code_in) {
             if (lane < G) p.tau[(size_t)v * G + lane] = (uint8_t)code_get(code, lane);
-            if (p.agg.N) agg_move_site(p.agg, code_in, code, tile, lane);
+            if (p.agg.N) {
+                const int sn = agg_move_site(p.agg, code_in, code, tile, lane);
+                if (p.site_slot && lane == 0) { p.site_slot[v] = sn; atomicAdd(p.gctl + GC_ORPHANS, 1); }
+            }
         }
 
         __syncwarp();

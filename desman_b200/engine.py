@@ -189,6 +189,12 @@ class Engine:
     def set_option(self, name, value):
         check(self._L.desman_set_option(self._h, name.encode(), int(value)), "desman_set_option")
 
+    def get_group_stats(self):
+        """Site groups of the tau screening pass: dict(have, calm, items, singles, work, orphans, slots, configured)."""
+        out = np.zeros(8, dtype=np.int64)
+        check(self._L.desman_get_group_stats(self._h, _lib.ptr_i64(out)), "desman_get_group_stats")
+        return dict(zip(("have", "calm", "items", "singles", "work", "orphans", "slots", "configured"), out.tolist()))
+
     def get_tier_counts(self, reset=True):
         out = np.zeros(3, dtype=np.int64)
         check(self._L.desman_get_tier_counts(self._h, _lib.ptr_i64(out), int(reset)), "desman_get_tier_counts")
@@ -199,8 +205,8 @@ class Engine:
 
     def get_timing(self):
         el = C.c_double(0)
-        kms = (C.c_double * 7)()
-        kl = (C.c_int64 * 7)()
+        kms = (C.c_double * len(_lib.K_NAMES))()
+        kl = (C.c_int64 * len(_lib.K_NAMES))()
         check(self._L.desman_get_timing(self._h, C.byref(el), kms, kl), "desman_get_timing")
         return dict(elapsed_ms=el.value, kernel_ms=dict(zip(_lib.K_NAMES, list(kms))),
                     kernel_launches=dict(zip(_lib.K_NAMES, list(kl))))

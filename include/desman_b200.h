@@ -113,6 +113,12 @@ int desman_nmft_factorize(desman_ctx *ctx, const int64_t *snps, int64_t V, int S
  * many draws were decided by the FP32 gap test / the FP64 CDF brackets / the FP64 reference-order recompute. */
 int desman_set_option(desman_ctx *ctx, const char *name, int64_t value);
 int desman_get_tier_counts(desman_ctx *ctx, int64_t out[3], int reset);
+/* "tau_group" = 1: the tau update first screens the sites grouped by haplotype pattern (one table of log terms per
+ * pattern, a dense FP32 contraction per site) and walks only the undecided sites with the per-site kernel; 0: per-site
+ * kernel for every site; 2 (default): 1 iff 12*2^G <= V/2.  Same draws either way.  desman_get_group_stats returns
+ * {groups valid, chain calm, work items, single-site patterns, sites left to the per-site kernel in the last sweep,
+ *  orphans since the last regroup, pattern slots in use, grouping configured}. */
+int desman_get_group_stats(desman_ctx *ctx, int64_t out[8]);
 
 /* Multi-GPU: one context per process/GPU, sites sharded by desman_set_counts(v0, V_total).
  * desman_comm_unique_id fills a 128-byte NCCL id on rank 0; every rank calls desman_comm_init. */
@@ -121,7 +127,7 @@ int desman_comm_init(desman_ctx *ctx, const char id[128], int rank, int nranks);
 
 /* Measurement hooks (bench.py): device-timed sweeps with CUDA events on the engine's stream. */
 enum { DESMAN_K_TAU = 0, DESMAN_K_MU = 1, DESMAN_K_DRAW = 2, DESMAN_K_FINAL = 3, DESMAN_K_MT = 4,
-       DESMAN_K_NMFT = 5, DESMAN_K_OTHER = 6, DESMAN_K_COUNT = 7 };
+       DESMAN_K_NMFT = 5, DESMAN_K_OTHER = 6, DESMAN_K_TAU_GROUP = 7, DESMAN_K_MAINT = 8, DESMAN_K_COUNT = 9 };
 int desman_set_profiling(desman_ctx *ctx, int per_kernel_events, int flush_l2_between_sweeps);
 /* elapsed_ms: sum over sweeps of the event-timed sweep durations of the last update()/update_tau() */
 int desman_get_timing(desman_ctx *ctx, double *elapsed_ms, double kernel_ms[DESMAN_K_COUNT],

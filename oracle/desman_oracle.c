@@ -151,9 +151,12 @@ void oracle_tau_step_probs(const int64_t *tau_index_v, const double *pi, const d
     free(idx); free(scratch);
 }
 
-int oracle_sample_tau_words(int64_t *tau, const double *pi, const double *eta,
-                            const int64_t *variants, int V, int G, int S,
-                            const uint32_t *words)
+/* midpoint = 0: u = w / 2^32 (gsl_rng_uniform, c_sample_tau.c:174; u = 0 possible);
+ * midpoint = 1: u = (w + 0.5) / 2^32 (the Philox contract of the GPU chain: u is never 0, so a step whose
+ * current base holds all but < 2^-33 of the mass is decided without looking at the word). */
+static int sample_tau_words_impl(int64_t *tau, const double *pi, const double *eta,
+                                 const int64_t *variants, int V, int G, int S,
+                                 const uint32_t *words, int midpoint)
 {
     int nchange = 0;
 #pragma omp parallel reduction(+ : nchange)
@@ -173,7 +176,8 @@ int oracle_sample_tau_words(int64_t *tau, const double *pi, const double *eta,
                 double p[4];
                 tau_step_logp(idx, pi, eta, nv, G, S, g, scratch, p);
                 softmax4(p);                                                /* :172 */
-                double u = words[(size_t)v * G + g] / 4294967296.0;         /* :174 gsl_rng_uniform */
+                double u = midpoint ? ((double)words[(size_t)v * G + g] + 0.5) / 4294967296.0
+                                    : words[(size_t)v * G + g] / 4294967296.0;  /* :174 gsl_rng_uniform */
                 int t = pick4(p, u);                                        /* :176 */
                 if (t != idx[g]) {                                          /* :178-185 */
                     tv[g * 4 + idx[g]] = 0;
@@ -186,6 +190,13 @@ int oracle_sample_tau_words(int64_t *tau, const double *pi, const double *eta,
         free(idx); free(scratch);
     }
     return nchange;
+}
+
+int oracle_sample_tau_words(int64_t *tau, const double *pi, const double *eta,
+                            const int64_t *variants, int V, int G, int S,
+                            const uint32_t *words)
+{
+    return sample_tau_words_impl(tau, pi, eta, variants, V, G, S, words, 0);
 }
 
 int oracle_sample_tau_mt(int64_t *tau, const double *pi, const double *eta,
@@ -212,7 +223,7 @@ int oracle_sample_tau_philox(int64_t *tau, const double *pi, const double *eta,
             philox((uint32_t)(v0 + v), (uint32_t)g, sweep, (uint32_t)ORACLE_STAGE_TAU << 28, seed, o);
             w[(size_t)v * G + g] = o[0];
         }
-    int r = oracle_sample_tau_words(tau, pi, eta, variants, V, G, S, w);
+    int r = sample_tau_words_impl(tau, pi, eta, variants, V, G, S, w, 1);
     free(w);
     return r;
 }
