@@ -148,7 +148,6 @@ struct desman_ctx {
     bool counts_tf32_exact = false;
     float4 *countsf = nullptr;               // [V][S] FP32 copy of the counts
     float *nsite = nullptr;                  // [V]
-    bool countsf_valid = false;
     size_t countsf_cap = 0;
     int *grp_site_slot = nullptr, *grp_order = nullptr, *grp_singles = nullptr, *grp_slot4 = nullptr, *grp_gctl = nullptr,
         *grp_blk = nullptr;
@@ -402,7 +401,6 @@ extern "C" int desman_set_counts(desman_ctx *c, const int64_t *variants, int64_t
     c->V = V; c->S = S; c->v0 = v0; c->V_total = V_total;
     c->ll_const_valid = false;
     c->agg_valid = false;
-    c->countsf_valid = false;
     c->total_reads = (double)total.load();
     c->counts_tf32_exact = or_all.load() < 2048;   // every count < 2^11: exact as a TF32 operand
     return DESMAN_OK;
@@ -600,7 +598,7 @@ static int ensure_agg(desman_ctx *c)
         CU(cudaMalloc(&c->grp_order, V * sizeof(int)));
         CU(cudaMalloc(&c->grp_singles, V * sizeof(int)));
         CU(cudaMalloc(&c->grp_slot4, 4 * c->agg_cap_slots * sizeof(int)));
-        CU(cudaMalloc(&c->grp_items, (V / 2 + V / TG_ITEM_SITES + 64) * sizeof(int4)));
+        CU(cudaMalloc(&c->grp_items, 2 * (V / 2 + V / TG_ITEM_SITES + 64) * sizeof(int4)));
         CU(cudaMalloc(&c->grp_work, V * sizeof(uint2)));
         c->grp_cap_v = V; c->grp_cap_slots = c->agg_cap_slots;
         c->agg_valid = false;
@@ -644,7 +642,7 @@ static MuAggParams agg_params(desman_ctx *c, const double *gamma, const double *
 // per CTA of the kernel (each warp owns one table in shared memory).
 static bool group_use_mma(const desman_ctx *c)
 {
-    return c->tau_group_mma && c->counts_tf32_exact && tgm_tiles(c->G) <= 6 &&
+    return c->tau_group_mma && c->counts_tf32_exact && tgm_tiles(c->G) <= 3 &&
            tg_shared_bytes(c->S, c->G) + tgm_table_bytes(c->S, c->G) + 1024 <= 200 * 1024;
 }
 
@@ -678,7 +676,6 @@ static TauGroup group_ptrs(desman_ctx *c)
 
 static int ensure_countsf(desman_ctx *c)
 {
-    if (c->countsf_valid) return DESMAN_OK;
     const size_t ncell = (size_t)c->V * c->S;
     if (ncell > c->countsf_cap) {
         if (c->countsf) cudaFree(c->countsf);
@@ -687,10 +684,8 @@ static int ensure_countsf(desman_ctx *c)
         CU(cudaMalloc(&c->countsf, ncell * sizeof(float4)));
         CU(cudaMalloc(&c->nsite, (size_t)c->V * sizeof(float)));
         c->countsf_cap = ncell;
+        c->agg_valid = false;     // filled by the next regroup
     }
-    counts_to_float_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(c->counts, c->countsf, c->nsite, (int)c->V, c->S);
-    CU(cudaGetLastError());
-    c->countsf_valid = true;
     return DESMAN_OK;
 }
 
@@ -703,6 +698,8 @@ static int sync_table(desman_ctx *c)
     const bool grouping = group_config(c, nullptr, nullptr);
     if (grouping) RET(ensure_countsf(c));
     if (!c->agg_valid) {
+        const int zero = 0;   // new counts / state: the groups (and the row copy that follows them) are rebuilt with the table
+        CU(cudaMemcpyAsync(c->grp_gctl + GC_HAVE, &zero, sizeof(int), cudaMemcpyHostToDevice, c->stream));
         const int one = 1;
         CU(cudaMemcpyAsync(c->agg_ctl, &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
         // optimistic: a freshly uploaded state is screened on its first sweep (a converged state pays off at once; after a
@@ -724,6 +721,7 @@ static int sync_table(desman_ctx *c)
     p.blk = c->grp_blk;
     p.zero64 = c->stats; p.nzero64 = (int)((size_t)c->S * c->G + 16);
     p.red_i = c->red_i;
+    p.countsf = c->countsf; p.nsite = c->nsite;
     void *args[] = {&p};
     {
         KSpan k(c, DESMAN_K_MAINT);
@@ -815,7 +813,6 @@ static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, boo
         TauGroupParams q;
         q.countsf = c->countsf; q.nsite = c->nsite; q.gamma = gamma; q.eta = eta; q.words = p.words;
         q.V = (int)c->V; q.S = c->S; q.G = c->G;
-        q.slot_code = c->agg_code;
         q.grp = group_ptrs(c);
         q.tier_counts = c->tiers;
         {
@@ -824,10 +821,7 @@ static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, boo
                 switch (tgm_tiles(c->G)) {
                 case 1: RET(launch_tau_group_mma_t<1>(c, q)); break;
                 case 2: RET(launch_tau_group_mma_t<2>(c, q)); break;
-                case 3: RET(launch_tau_group_mma_t<3>(c, q)); break;
-                case 4: RET(launch_tau_group_mma_t<4>(c, q)); break;
-                case 5: RET(launch_tau_group_mma_t<5>(c, q)); break;
-                default: RET(launch_tau_group_mma_t<6>(c, q)); break;
+                default: RET(launch_tau_group_mma_t<3>(c, q)); break;
                 }
             } else if (gb == 4) RET(launch_tau_group_t<4>(c, q, gwarps));
             else RET(launch_tau_group_t<8>(c, q, gwarps));

@@ -21,6 +21,8 @@ struct MaintParams {
     unsigned long long *zero64;  // per-sweep accumulators cleared here: the statistics ...
     int nzero64;
     unsigned long long *red_i;   // ... and [2] fixed-point ll | nchange
+    float4 *countsf;             // [V][S] FP32 copy of the count rows in group order (row pos <-> site grp.order[pos])
+    float *nsite;                // [V] reads per row, rounded up
 };
 
 #define MAINT_THREADS 256
@@ -155,8 +157,16 @@ __global__ void __launch_bounds__(MAINT_THREADS) table_maintain_kernel(MaintPara
             const int st = p.grp.slot_start[sl] + off.x, it0 = p.grp.slot_item[sl] + off.y, itp = all.y + off.z + p.grp.slot_fill[sl];
             p.grp.slot_start[sl] = st;
             const int nfull = c / TG_ITEM_SITES;
-            for (int j = 0; j < nfull; j++) p.grp.items[it0 + j] = make_int4(sl, st + j * TG_ITEM_SITES, TG_ITEM_SITES, 0);
-            if (c % TG_ITEM_SITES) p.grp.items[itp] = make_int4(sl, st + nfull * TG_ITEM_SITES, c % TG_ITEM_SITES, 0);
+            const unsigned long long code = t.slot_code[sl];
+            const int4 rec1 = make_int4((int)(unsigned int)code, (int)(unsigned int)(code >> 32), 0, 0);
+            for (int j = 0; j < nfull; j++) {
+                p.grp.items[2 * (it0 + j)] = make_int4(sl, st + j * TG_ITEM_SITES, TG_ITEM_SITES, 0);
+                p.grp.items[2 * (it0 + j) + 1] = rec1;
+            }
+            if (c % TG_ITEM_SITES) {
+                p.grp.items[2 * itp] = make_int4(sl, st + nfull * TG_ITEM_SITES, c % TG_ITEM_SITES, 0);
+                p.grp.items[2 * itp + 1] = rec1;
+            }
         }
         p.grp.slot_fill[sl] = 0;
     }
@@ -166,22 +176,19 @@ __global__ void __launch_bounds__(MAINT_THREADS) table_maintain_kernel(MaintPara
         if (p.grp.slot_cnt[sl] == 1) p.grp.singles[p.grp.slot_start[sl]] = (int)v;
         else p.grp.order[p.grp.slot_start[sl] + atomicAdd(p.grp.slot_fill + sl, 1)] = (int)v;
     }
-}
-
-// counts int32x4 -> FP32x4 copy for the screening pass (exact, counts <= 2^24) + per-site read totals rounded up
-__global__ void __launch_bounds__(256) counts_to_float_kernel(const int4 *__restrict__ counts, float4 *__restrict__ countsf,
-                                                              float *__restrict__ nsite, int V, int S)
-{
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
-    for (int v = gw; v < V; v += nw) {
+    grid.sync();
+    // the count rows of the grouped sites, converted to FP32 (exact: counts <= 2^24) and laid out in group order, so that the
+    // sites of a work item are one contiguous block of rows: the screening pass streams them without an index hop
+    const int nrows = V - gctl[GC_NSINGLES];
+    for (int pos = gw; pos < nrows; pos += nw) {
+        const int v = p.grp.order[pos];
         long long tot = 0;
-        for (int s = lane; s < S; s += 32) {
-            const int4 n = counts[(size_t)v * S + s];
-            countsf[(size_t)v * S + s] = make_float4((float)n.x, (float)n.y, (float)n.z, (float)n.w);
+        for (int s2 = lane; s2 < S; s2 += 32) {
+            const int4 n = ld_counts(p.a.counts + (size_t)v * S + s2);
+            p.countsf[(size_t)pos * S + s2] = make_float4((float)n.x, (float)n.y, (float)n.z, (float)n.w);
             tot += (long long)n.x + n.y + n.z + n.w;
         }
         tot = (long long)warp_sum_u64((unsigned long long)tot);
-        if (lane == 0) nsite[v] = __ll2float_ru(tot);
+        if (lane == 0) p.nsite[pos] = __ll2float_ru(tot);
     }
 }

@@ -35,20 +35,19 @@ struct TauGroup {
     int *site_slot;     // [V] table slot of the site's current pattern (mu_aggregate / agg_move_site keep it)
     int *order;         // [V] sites of multi-site patterns, sorted by slot
     int *singles;       // [V] sites that are alone in their pattern (straight to the per-site kernel)
-    int4 *items;        // {slot, begin in order[], count, 0}
+    int4 *items;        // two words per work item: {slot, first row, rows, 0}, {pattern code lo, hi, 0, 0}
     uint2 *work;        // [V] {site, mask of undecided strains}
     int *slot_cnt, *slot_fill, *slot_start, *slot_item;   // [cap_slots] regroup scratch
     int *gctl;          // [GC_COUNT]
 };
 
 struct TauGroupParams {
-    const float4 *countsf;   // [V][S] counts as FP32 (exact: counts <= 2^24)
-    const float *nsite;      // [V] reads of the site, rounded up
+    const float4 *countsf;   // [rows][S] counts as FP32 (exact: counts <= 2^24), rows in group order: row pos <-> site order[pos]
+    const float *nsite;      // [rows] reads of the row's site, rounded up
     const double *gamma;     // [S][G]
     const double *eta;       // [16]
     const uint32_t *words;   // MT19937 words [V*G] (a zero word means u == 0: per-site kernel), or nullptr (Philox: u > 0)
     int V, S, G;
-    const unsigned long long *slot_code;
     TauGroup grp;
     unsigned long long *tier_counts;
 };
@@ -60,6 +59,7 @@ __device__ __forceinline__ float4 ld_countsf(const float4 *p)
     return r;
 }
 
+// TMA bulk prefetch of a contiguous block of count rows into L2 (one instruction per warp: the address is warp-uniform)
 __device__ __forceinline__ void l2_prefetch_row(const void *p, uint32_t bytes)
 {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
@@ -171,15 +171,11 @@ __global__ void __launch_bounds__(TG_MAX_WARPS * 32, 1) tau_group_kernel(TauGrou
         if (lane == 0) it = atomicAdd(p.grp.gctl + GC_CURSOR, 1);
         it = __shfl_sync(DESMAN_FULL_MASK, it, 0);
         if (it >= gctl[GC_NITEMS]) break;
-        const int4 item = p.grp.items[it];
-        const int slot = item.x, count = item.z;
-        const int *ord = p.grp.order + item.y;
-        const uint64_t code = p.slot_code[slot];
-        // sites of the first pass (index 0 stands in for the missing sites of a partial pass: computed, never used)
-        int v[4];
-#pragma unroll
-        for (int i = 0; i < 4; i++) { const int idx = r * 4 + i; v[i] = ord[idx < count ? idx : 0]; }
-        if (lane < TG_PASS_SITES && lane < count) l2_prefetch_row(p.countsf + (size_t)ord[lane] * S, row_bytes);
+        const int4 item = p.grp.items[2 * it], item1 = p.grp.items[2 * it + 1];
+        const int slot = item.x, begin = item.y, count = item.z;
+        const uint64_t code = ((uint64_t)(unsigned int)item1.y << 32) | (unsigned int)item1.x;
+        const float4 *rows = p.countsf + (size_t)begin * S;        // the item's count rows are contiguous
+        l2_prefetch_row(rows, (uint32_t)min(count, TG_PASS_SITES) * row_bytes);
 
         // ---- the pattern's table: Wd[s][g*3+j][b] = lg2(base_sb + eta[a_j][b]*gamma[s][g]) - lg2(P_sb), a_j = (cur_g+1+j)&3
         __syncwarp();
@@ -222,23 +218,28 @@ __global__ void __launch_bounds__(TG_MAX_WARPS * 32, 1) tau_group_kernel(TauGrou
 
         float4 na[4];                                                  // count cells of sample step 0 of the current pass
 #pragma unroll
-        for (int i = 0; i < 4; i++) na[i] = (o < S) ? ld_countsf(p.countsf + (size_t)v[i] * S + o) : zero4;
+        for (int i = 0; i < 4; i++) {                                  // (row 0 stands in for the missing rows of a partial pass)
+            const int idx = r * 4 + i;
+            na[i] = (o < S) ? ld_countsf(rows + (size_t)(idx < count ? idx : 0) * S + o) : zero4;
+        }
 
         for (int base = 0; base < count; base += TG_PASS_SITES) {
             const bool more = base + TG_PASS_SITES < count;
-            // next pass: its site indices now (used at the end of this pass), its rows into L2 while this pass is contracted
-            int vn[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) { const int idx = base + TG_PASS_SITES + r * 4 + i; vn[i] = ord[idx < count ? idx : 0]; }
-            if (more && lane < TG_PASS_SITES && base + TG_PASS_SITES + lane < count)
-                l2_prefetch_row(p.countsf + (size_t)ord[base + TG_PASS_SITES + lane] * S, row_bytes);
-            const bool have_own = base + r * 4 + isl < count;
-            const int vown = v[0] * (isl == 0) + v[1] * (isl == 1) + v[2] * (isl == 2) + v[3] * (isl == 3);
-            const float nown = p.nsite[vown];
+            // next pass: its rows into L2 while this pass is contracted
+            if (more) l2_prefetch_row(rows + (size_t)(base + TG_PASS_SITES) * S, (uint32_t)min(count - base - TG_PASS_SITES, TG_PASS_SITES) * row_bytes);
+            const int iown = base + r * 4 + isl;
+            const bool have_own = iown < count;
+            const int pown = begin + (have_own ? iown : 0);
+            const float nown = p.nsite[pown];
+            const int vown = p.grp.order[pown];
             const int sown = p.grp.site_slot[vown];
-            const float4 *row[4];
+            const float4 *row[4], *rown[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) row[i] = p.countsf + (size_t)v[i] * S + o;
+            for (int i = 0; i < 4; i++) {
+                const int idx = base + r * 4 + i, idn = idx + TG_PASS_SITES;
+                row[i] = rows + (size_t)(idx < count ? idx : 0) * S + o;
+                rown[i] = rows + (size_t)(idn < count ? idn : 0) * S + o;
+            }
             uint32_t mask = 0;
 
             for (int gb = 0; gb < nGB; gb++) {
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(TG_MAX_WARPS * 32, 1) tau_group_kernel(TauGrou
                 if (gb == nGB - 1 && more) {
                     // first sample step of the next pass: in flight during the reduction below
 #pragma unroll
-                    for (int i = 0; i < 4; i++) na[i] = (o < S) ? ld_countsf(p.countsf + (size_t)vn[i] * S + o) : zero4;
+                    for (int i = 0; i < 4; i++) na[i] = (o < S) ? ld_countsf(rown[i]) : zero4;
                 }
                 // combine the 8 sample groups: lane o ends with values [o*NV/8, (o+1)*NV/8) = pairs (isl, gl = (o&1)*PP + q)
                 tg_reduce_level<NV>(acc, (o & 4) != 0, 4);
@@ -300,8 +301,6 @@ __global__ void __launch_bounds__(TG_MAX_WARPS * 32, 1) tau_group_kernel(TauGrou
                 pos = __shfl_sync(DESMAN_FULL_MASK, pos, 0) + __popc(bal & ((1u << lane) - 1u));
                 if (push) p.grp.work[pos] = make_uint2((unsigned int)vown, mask);
             }
-#pragma unroll
-            for (int i = 0; i < 4; i++) v[i] = vn[i];
         }
     }
     n_decided = (unsigned int)warp_sum_u64((unsigned long long)n_decided);
@@ -311,56 +310,66 @@ __global__ void __launch_bounds__(TG_MAX_WARPS * 32, 1) tau_group_kernel(TauGrou
 // =====================================================================================================================
 // Tensor-core form of the screening pass (used when every count is < 2048, i.e. exact in TF32).
 //
-// The contraction D[site][col] = sum_{s,b} n[site][s][b] * Wd[s][col][b], col = g*3 + j, is a [16 sites x 4S] x [4S x 3G]
-// product per pass: warp-level mma.sync m16n8k8 (TF32 operands, FP32 accumulators).  The k index of one MMA is laid
-// out as k = t -> (sample s0+t, base beta), k = t+4 -> (sample s0+t, base beta+1) (t = lane & 3, beta = 0 or 2), so that a
-// lane's A fragment of the two MMAs of a 4-sample group is exactly one 128-bit count cell per site row (rows g and
-// g+8, g = lane >> 2) and its B fragment is one 128-bit word Wd[s0+t][col = 8*tile + g] of the table.  The FP32 table
-// entry is split on the fly into a TF32 head (11 significant bits) and a remainder; two MMAs per entry recover it to
-// ~2^-20 relative.  Counts are integers < 2^11: exact.
+// The contraction D[col][site] = sum_{s,b} Wd[s][col][b] * n[site][s][b], col = g*3 + j, is a [3G x 4S] x [4S x 16 sites]
+// product per pass: warp-level mma.sync m16n8k8 (TF32 operands, FP32 accumulators) with the TABLE as the A operand
+// (16 table columns per M tile) and the COUNTS as the B operand (8 sites per N tile, two N tiles per pass).  The k index
+// of one MMA is laid out as k = t -> (sample s0+t, base beta), k = t+4 -> (sample s0+t, base beta+1) (t = lane & 3, beta =
+// 0 or 2), so that the B fragments of the two MMAs of a 4-sample group are the two halves of ONE 128-bit count cell of
+// site g (g = lane >> 2) -- no register shuffling between the load and the MMA -- and the A fragments are 128-bit words
+// of the table, which is stored in fragment order: Wm[s][beta/2][tile][g] = {Wd[s][16 tile+g][beta], Wd[s][16 tile+g+8][beta],
+// Wd[s][16 tile+g][beta+1], Wd[s][16 tile+g+8][beta+1]}.  The FP32 table entry is split on the fly into a TF32 head (11
+// significant bits) and a remainder; two MMAs per entry recover it to ~2^-20 relative.  Counts are integers < 2^11: exact.
 // Error model (on top of the per-entry model of the FFMA form): representation of Wd by head + truncated remainder
 // <= 2^-20 |Wd|; every MMA accumulation step is charged 2^-20 of the running magnitude (documented tensor-core behaviour is
-// exact products, alignment and truncation to >= 24 bits: 8x margin); Sp/4 groups x 2 x 2 steps per output.  With the
-// measured max |Wd| of the item that is ~1e-3 log2 units per read; tests/test_gpu_group.py checks the measured error of D
-// against this bound on random inputs.
-// One CTA (4 warps) per work item; the warps share the item's table and take its 16-site passes round robin.
+// exact products, alignment and truncation to >= 24 bits: 8x margin); Sp/4 groups x 2 x 2 steps per output; |Wd| is bounded a
+// priori from min(gamma)*min(eta): ~2e-3 log2 units per read.
+// One CTA (4 warps) per work item, items dealt round robin (long items first); the warps share the item's table and take its
+// 16-site passes round robin.  Count rows are pulled into L2 by TMA bulk prefetches (cp.async.bulk.prefetch.L2) one round
+// of passes / one item ahead, so the 128-bit loads of a pass find them there.
 #define TGM_WARPS 4
 
-static inline int tgm_tiles(int G) { return (3 * G + 7) / 8; }
+static inline int tgm_tiles(int G) { return (3 * G + 15) / 16; }
 static inline size_t tgm_table_bytes(int S, int G)
 {
     const size_t Sp = (size_t)((S + 15) & ~15);
-    return Sp * (size_t)(8 * tgm_tiles(G) + 2) * sizeof(float4);
+    return Sp * (size_t)(16 * tgm_tiles(G) + 2) * sizeof(float4);
 }
 
-__device__ __forceinline__ void mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1)
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
 {
     asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-template <int NT>
-__device__ __forceinline__ void tgm_group(float (&ch)[NT][4], float (&cl)[NT][4], const float4 &cA, const float4 &cB,
+__device__ __forceinline__ void tf32_split(const float4 &w, uint32_t (&h)[4], uint32_t (&l)[4])
+{
+    h[0] = __float_as_uint(w.x) & 0xffffe000u; h[1] = __float_as_uint(w.y) & 0xffffe000u;
+    h[2] = __float_as_uint(w.z) & 0xffffe000u; h[3] = __float_as_uint(w.w) & 0xffffe000u;
+    l[0] = __float_as_uint(w.x - __uint_as_float(h[0])); l[1] = __float_as_uint(w.y - __uint_as_float(h[1]));
+    l[2] = __float_as_uint(w.z - __uint_as_float(h[2])); l[3] = __float_as_uint(w.w - __uint_as_float(h[3]));
+}
+
+// one 4-sample group: cell0 / cell1 = this lane's count cells of the sites of N tile 0 / 1
+template <int MT>
+__device__ __forceinline__ void tgm_group(float (&ch)[MT][2][4], float (&cl)[MT][2][4], const float4 &c0, const float4 &c1,
                                           const float4 *__restrict__ Wq)
 {
-    const uint32_t ax = __float_as_uint(cA.x), ay = __float_as_uint(cA.y), az = __float_as_uint(cA.z), aw = __float_as_uint(cA.w);
-    const uint32_t bx = __float_as_uint(cB.x), by = __float_as_uint(cB.y), bz = __float_as_uint(cB.z), bw = __float_as_uint(cB.w);
+    const uint32_t x0 = __float_as_uint(c0.x), y0 = __float_as_uint(c0.y), z0 = __float_as_uint(c0.z), w0 = __float_as_uint(c0.w);
+    const uint32_t x1 = __float_as_uint(c1.x), y1 = __float_as_uint(c1.y), z1 = __float_as_uint(c1.z), w1 = __float_as_uint(c1.w);
 #pragma unroll
-    for (int nt = 0; nt < NT; nt++) {
-        const float4 w = Wq[8 * nt];
-        const uint32_t hx = __float_as_uint(w.x) & 0xffffe000u, hy = __float_as_uint(w.y) & 0xffffe000u,
-                       hz = __float_as_uint(w.z) & 0xffffe000u, hw = __float_as_uint(w.w) & 0xffffe000u;
-        const uint32_t lx = __float_as_uint(w.x - __uint_as_float(hx)), ly = __float_as_uint(w.y - __uint_as_float(hy)),
-                       lz = __float_as_uint(w.z - __uint_as_float(hz)), lw = __float_as_uint(w.w - __uint_as_float(hw));
-        mma_tf32(ch[nt], ax, bx, ay, by, hx, hy);
-        mma_tf32(cl[nt], ax, bx, ay, by, lx, ly);
-        mma_tf32(ch[nt], az, bz, aw, bw, hz, hw);
-        mma_tf32(cl[nt], az, bz, aw, bw, lz, lw);
+    for (int mt = 0; mt < MT; mt++) {
+        uint32_t h[4], l[4];
+        tf32_split(Wq[8 * mt], h, l);                      // bases 0,1
+        mma_tf32(ch[mt][0], h, x0, y0); mma_tf32(ch[mt][1], h, x1, y1);
+        mma_tf32(cl[mt][0], l, x0, y0); mma_tf32(cl[mt][1], l, x1, y1);
+        tf32_split(Wq[8 * MT + 8 * mt], h, l);             // bases 2,3
+        mma_tf32(ch[mt][0], h, z0, w0); mma_tf32(ch[mt][1], h, z1, w1);
+        mma_tf32(cl[mt][0], l, z0, w0); mma_tf32(cl[mt][1], l, z1, w1);
     }
 }
 
-template <int NT>
+template <int MT>
 __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGroupParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -368,18 +377,20 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
     if (!(gctl[GC_HAVE] && gctl[GC_CALM])) return;
     const int S = p.S, G = p.G;
     const int Sp = (S + 15) & ~15, nq = Sp >> 2;      // 4-sample groups
-    constexpr int STR = 8 * NT + 2;                   // float4 per sample: = 2 (mod 8) -> conflict-free fragment loads
+    constexpr int STR = 16 * MT + 2;                  // float4 per sample: = 2 (mod 8) -> conflict-free fragment loads
 
     double *gT = reinterpret_cast<double *>(smem_raw);                    // [G][Sp]
     double *eta_s = gT + (size_t)G * Sp;                                  // [16]
     float4 *eta32 = reinterpret_cast<float4 *>(eta_s + 16);               // [4]
     float *gT32 = reinterpret_cast<float *>(eta32 + 4);                   // [G][Sp]
-    float4 *W = reinterpret_cast<float4 *>(gT32 + (size_t)G * Sp);        // [Sp][STR]
-    __shared__ unsigned int gmin_bits, emin_bits, wmax_bits[2];
-    __shared__ int s_it[2];
+    float4 *W = reinterpret_cast<float4 *>(gT32 + (size_t)G * Sp);        // [Sp][STR] fragment order
+    float *Wf = reinterpret_cast<float *>(W);
+    __shared__ unsigned int gmin_bits, emin_bits;
 
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
-    if (tid == 0) { gmin_bits = 0x7f800000u; emin_bits = 0x7f800000u; wmax_bits[0] = 0u; wmax_bits[1] = 0u; s_it[0] = atomicAdd(p.grp.gctl + GC_CURSOR, 1); }
+    if (tid == 0) { gmin_bits = 0x7f800000u; emin_bits = 0x7f800000u; }
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = tid; i < Sp * STR; i += blockDim.x) W[i] = zero4;        // padding rows / columns / samples stay zero
     __syncthreads();
     float gmin_l = __int_as_float(0x7f800000);
     for (int i = tid; i < G * Sp; i += blockDim.x) {
@@ -396,43 +407,59 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
         atomicMin(&emin_bits, __float_as_uint(fmaxf((float)p.eta[tid], 0.f)));
     }
     __syncthreads();
+    // unnormalised input (rows of gamma or eta summing to more than 1): no screening, every site goes to the per-site kernel
+    __shared__ int unnorm;
+    if (tid == 0) unnorm = 0;
+    __syncthreads();
+    for (int s = tid; s < S + 4; s += blockDim.x) {
+        double t = 0.0;
+        if (s < S) for (int g = 0; g < G; g++) t += gT[g * Sp + s];
+        else for (int b = 0; b < 4; b++) t += eta_s[4 * (s - S) + b];
+        if (!(t <= 1.0001)) unnorm = 1;
+    }
+    __syncthreads();
     const float qmin = 0.99f * __uint_as_float(gmin_bits) * __uint_as_float(emin_bits);
-    const bool fast_ok = qmin >= TAU_QMIN;
+    const bool fast_ok = qmin >= TAU_QMIN && !unnorm;
     const float mq0 = fmaxf(1.0f, 1.0f - log2f(fmaxf(qmin, TAU_QMIN)));
     // per read, log2 units: entry model (relative parts, lg2.approx floors, lg2.approx and the lq - lP rounding per unit of
     // |lg2|, FP64 cancellation) + [TF32 split + Sp accumulation steps] * 2^-20 * max|Wd| of the item
     const float e_entry = TAU_C0 + (2.3841858e-7f + 5.9604645e-8f) * (2.0f * mq0) + TAU_CANCEL(G) / fmaxf(qmin, TAU_QMIN);
     const float e_mma = (float)(Sp + 1) * 9.5367432e-7f;
     const float LN2 = 0.69314718f;
+    // q, P <= 1 (convex combinations of eta entries), so lg2 q, lg2 P <= 0 and |Wd| = |lg2 q - lg2 P| <= mq0
+    const float bn_scale = (e_entry + e_mma * mq0) * LN2 * 1.0001f;
 
     const int g8 = lane >> 2, t4 = lane & 3;
     const uint32_t fullG = (G >= 32) ? 0xffffffffu : ((1u << G) - 1u);
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const uint32_t row_bytes = (uint32_t)S * 16u;
     const int nitems = gctl[GC_NITEMS];
     // build tasks: (sample, chunk of strains); H chunks so that the CTA's threads are all busy
     const int H = max(1, min(G, (int)blockDim.x / Sp)), GH = (G + H - 1) / H;
     unsigned int n_decided = 0;
+    constexpr int ROUND = TGM_WARPS * TG_PASS_SITES;      // sites the CTA contracts per round of passes
 
-    for (int iter = 0;; iter++) {
-        const int it = s_it[iter & 1];
-        if (it >= nitems) break;
-        int nxt = 0;
-        if (tid == 0) nxt = atomicAdd(p.grp.gctl + GC_CURSOR, 1);          // in flight while this item is processed
-        const int4 item = p.grp.items[it];
-        const int slot = item.x, count = item.z;
-        const int *ord = p.grp.order + item.y;
-        const uint64_t code = p.slot_code[slot];
-        // first pass of this warp: sites (rows g8 and g8+8) -- issued before the table build hides their latency
-        int base = wib * TG_PASS_SITES;
-        int v0 = ord[base + g8 < count ? base + g8 : 0], v1 = ord[base + g8 + 8 < count ? base + g8 + 8 : 0];
+    // the work items of this CTA: blockIdx.x, + gridDim.x, ...; the record of the next one is fetched an item ahead
+    int4 nxt0 = make_int4(0, 0, 0, 0), nxt1 = nxt0;
+    if ((int)blockIdx.x < nitems) {
+        nxt0 = p.grp.items[2 * blockIdx.x]; nxt1 = p.grp.items[2 * blockIdx.x + 1];
+        if (tid == 0) l2_prefetch_row(p.countsf + (size_t)nxt0.y * S, (uint32_t)min(nxt0.z, ROUND) * row_bytes);
+    }
+
+    int iter = 0;
+    for (int it = blockIdx.x; it < nitems; it += gridDim.x, iter++) {
+        const int4 item = nxt0, item1 = nxt1;
+        const int slot = item.x, begin = item.y, count = item.z;
+        const uint64_t code = ((uint64_t)(unsigned int)item1.y << 32) | (unsigned int)item1.x;
+        const float4 *rows = p.countsf + (size_t)begin * S;            // the item's count rows are contiguous
+        if (it + (int)gridDim.x < nitems) { nxt0 = p.grp.items[2 * (it + gridDim.x)]; nxt1 = p.grp.items[2 * (it + gridDim.x) + 1]; }
+        int base = wib * TG_PASS_SITES;                                 // first pass of this warp
 
         // ---- the pattern's table: Wd[s][g*3+j][b] = lg2(base_sb + eta[a_j][b]*gamma[s][g]) - lg2(P_sb), a_j = (cur_g+1+j)&3
-        float wmax = 0.f;
         for (int task = tid; task < Sp * H; task += blockDim.x) {
             const int s = task % Sp, h = task / Sp;
             const int glo = h * GH, ghi = min(G, glo + GH);
-            float4 *Ws = W + (size_t)s * STR;
             if (s < S && fast_ok) {
+                float *Ws = Wf + (size_t)s * STR * 4;
                 double P0 = 0.0, P1 = 0.0, P2 = 0.0, P3 = 0.0;
                 for (int hh = 0; hh < G; hh++) {
                     const double2 *e = reinterpret_cast<const double2 *>(eta_s + 4 * code_get(code, hh));
@@ -452,75 +479,85 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
 #pragma unroll
                     for (int j = 0; j < 3; j++) {
                         const float4 ea = eta32[(cur + 1 + j) & 3];
-                        float4 w;
-                        w.x = lg2_fast(fmaf(ea.x, gf, q0)) - l0;
-                        w.y = lg2_fast(fmaf(ea.y, gf, q1)) - l1;
-                        w.z = lg2_fast(fmaf(ea.z, gf, q2)) - l2;
-                        w.w = lg2_fast(fmaf(ea.w, gf, q3)) - l3;
-                        wmax = fmaxf(wmax, fmaxf(fmaxf(fabsf(w.x), fabsf(w.y)), fmaxf(fabsf(w.z), fabsf(w.w))));
-                        Ws[g * 3 + j] = w;
+                        const float wx = lg2_fast(fmaf(ea.x, gf, q0)) - l0, wy = lg2_fast(fmaf(ea.y, gf, q1)) - l1,
+                                    wz = lg2_fast(fmaf(ea.z, gf, q2)) - l2, ww = lg2_fast(fmaf(ea.w, gf, q3)) - l3;
+                        // fragment order: float4 index (beta/2)*8*MT + (c>>4)*8 + (c&7), component ((c>>3)&1) + 2*(b&1)
+                        const int c = g * 3 + j;
+                        float *dst = Ws + 4 * ((c >> 4) * 8 + (c & 7)) + ((c >> 3) & 1);
+                        dst[0] = wx; dst[2] = wy;
+                        dst[32 * MT] = wz; dst[32 * MT + 2] = ww;
                     }
                 }
-                if (h == H - 1) for (int c = G * 3; c < 8 * NT; c++) Ws[c] = zero4;
-            } else {
-                for (int c = glo * 3; c < (h == H - 1 ? 8 * NT : ghi * 3); c++) Ws[c] = zero4;
             }
         }
-        wmax = warp_max(wmax);
-        if (lane == 0) atomicMax(&wmax_bits[iter & 1], __float_as_uint(wmax));
+        // first round of the next item into L2 while this one is contracted
+        if (tid == 0 && it + (int)gridDim.x < nitems) l2_prefetch_row(p.countsf + (size_t)nxt0.y * S, (uint32_t)min(nxt0.z, ROUND) * row_bytes);
         __syncthreads();
-        if (tid == 0) wmax_bits[(iter + 1) & 1] = 0u;
-        const float bn_scale = (e_entry + e_mma * __uint_as_float(wmax_bits[iter & 1])) * LN2 * 1.0001f;
 
-        for (; base < count; base += TGM_WARPS * TG_PASS_SITES) {
-            const int nb = base + TGM_WARPS * TG_PASS_SITES;               // this warp's next pass
-            const int vn0 = ord[nb + g8 < count ? nb + g8 : 0], vn1 = ord[nb + g8 + 8 < count ? nb + g8 + 8 : 0];
-            const bool have0 = base + g8 < count, have1 = base + g8 + 8 < count;
-            const float n0 = p.nsite[v0], n1 = p.nsite[v1];
-            const int sl0 = p.grp.site_slot[v0], sl1 = p.grp.site_slot[v1];
-            const float4 *rowA = p.countsf + (size_t)v0 * S + t4, *rowB = p.countsf + (size_t)v1 * S + t4;
+        for (; base < count; base += ROUND) {
+            // this warp's next pass into L2
+            if (base + ROUND < count) l2_prefetch_row(rows + (size_t)(base + ROUND) * S, (uint32_t)min(count - base - ROUND, TG_PASS_SITES) * row_bytes);
+            // the site this lane decides for: lanes g8 < 4 own row k = {2 t4, 2 t4 + 1, 8 + 2 t4, 9 + 2 t4}[g8] of the pass
+            const int kown = ((g8 & 2) << 2) + 2 * t4 + (g8 & 1);
+            const bool own = g8 < 4 && base + kown < count;
+            const int vown = p.grp.order[begin + (base + kown < count ? base + kown : 0)];
+            // read totals of the 4 sites whose sums this lane holds
+            float nk[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int idx = base + ((k & 2) << 2) + 2 * t4 + (k & 1);
+                nk[k] = p.nsite[begin + (idx < count ? idx : 0)];
+            }
+            const int sown = p.grp.site_slot[vown];
+            const float4 *row0 = rows + (size_t)(base + g8 < count ? base + g8 : 0) * S + t4,
+                         *row1 = rows + (size_t)(base + g8 + 8 < count ? base + g8 + 8 : 0) * S + t4;
             const float4 *Wq = W + (size_t)t4 * STR + g8;
-            float ch[NT][4], cl[NT][4];
+            float ch[MT][2][4], cl[MT][2][4];
 #pragma unroll
-            for (int nt = 0; nt < NT; nt++)
+            for (int mt = 0; mt < MT; mt++)
 #pragma unroll
-                for (int i = 0; i < 4; i++) { ch[nt][i] = 0.f; cl[nt][i] = 0.f; }
+                for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) { ch[mt][nt][i] = 0.f; cl[mt][nt][i] = 0.f; }
             // 4-sample groups, four at a time: 8 cells in flight per lane
             for (int q = 0; q < nq; q += 4) {
-                float4 cA[4], cB[4];
+                float4 c0[4], c1[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
                     const bool ok = 4 * (q + u) + t4 < S;
-                    cA[u] = ok ? ld_countsf(rowA + 4 * (q + u)) : zero4;
-                    cB[u] = ok ? ld_countsf(rowB + 4 * (q + u)) : zero4;
+                    c0[u] = ok ? ld_countsf(row0 + 4 * (q + u)) : zero4;
+                    c1[u] = ok ? ld_countsf(row1 + 4 * (q + u)) : zero4;
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) tgm_group<NT>(ch, cl, cA[u], cB[u], Wq + (size_t)(4 * (q + u)) * STR);
+                for (int u = 0; u < 4; u++) tgm_group<MT>(ch, cl, c0[u], c1[u], Wq + (size_t)(4 * (q + u)) * STR);
             }
-            // a strain is decided "stay" iff each of its three candidates trails the current base by > 60 nats after the bound
-            const float bn0 = n0 * bn_scale + 1e-6f, bn1 = n1 * bn_scale + 1e-6f;
-            uint32_t m0 = 0, m1 = 0;
+            // a strain is decided "stay" iff each of its three candidates trails the current base by > 60 nats after the bound.
+            // accumulator (mt, nt, i): table column 16 mt + 8 (i >> 1) + g8, site 8 nt + 2 t4 + (i & 1)
+            uint32_t m[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
-            for (int nt = 0; nt < NT; nt++)
+            for (int mt = 0; mt < MT; mt++)
 #pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    const int col = 8 * nt + 2 * t4 + i;
-                    if (col < 3 * G) {
-                        const int g = col / 3;
-                        const float d0 = ch[nt][i] + cl[nt][i], d1 = ch[nt][2 + i] + cl[nt][2 + i];
-                        if (!(d0 * LN2 + bn0 < -TAU_GAP)) m0 |= 1u << g;
-                        if (!(d1 * LN2 + bn1 < -TAU_GAP)) m1 |= 1u << g;
+                for (int hf = 0; hf < 2; hf++) {
+                    const int c = 16 * mt + 8 * hf + g8;
+                    if (c < 3 * G) {
+                        const uint32_t bit = 1u << (c / 3);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const float d = ch[mt][k >> 1][2 * hf + (k & 1)] + cl[mt][k >> 1][2 * hf + (k & 1)];
+                            if (!(d * LN2 + (nk[k] * bn_scale + 1e-6f) < -TAU_GAP)) m[k] |= bit;
+                        }
                     }
                 }
-            m0 |= __shfl_xor_sync(DESMAN_FULL_MASK, m0, 1); m0 |= __shfl_xor_sync(DESMAN_FULL_MASK, m0, 2);
-            m1 |= __shfl_xor_sync(DESMAN_FULL_MASK, m1, 1); m1 |= __shfl_xor_sync(DESMAN_FULL_MASK, m1, 2);
-            // lanes t4 == 0 / 1 own the sites of rows g8 / g8+8
-            const bool own = (t4 == 0 && have0) || (t4 == 1 && have1);
-            const int vown = (t4 == 0) ? v0 : v1;
-            uint32_t mask = ((t4 == 0) ? m0 : m1) & fullG;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                m[k] |= __shfl_xor_sync(DESMAN_FULL_MASK, m[k], 4);
+                m[k] |= __shfl_xor_sync(DESMAN_FULL_MASK, m[k], 8);
+                m[k] |= __shfl_xor_sync(DESMAN_FULL_MASK, m[k], 16);
+            }
+            uint32_t mask = ((g8 & 3) == 0 ? m[0] : (g8 & 3) == 1 ? m[1] : (g8 & 3) == 2 ? m[2] : m[3]) & fullG;
             bool push = false;
             if (own) {
-                if (!fast_ok || ((t4 == 0) ? sl0 : sl1) != slot) mask = fullG;      // orphan: its pattern is not this group's
+                if (!fast_ok || sown != slot) mask = fullG;                           // orphan: its pattern is not this group's
                 if (p.words) {
                     const uint32_t *w = p.words + (size_t)vown * G;
                     for (int g = 0; g < G; g++) if (w[g] == 0u) mask = fullG;         // u == 0 (c_sample_tau.c:174): reference-order path
@@ -535,9 +572,7 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
                 pos = __shfl_sync(DESMAN_FULL_MASK, pos, 0) + __popc(bal & ((1u << lane) - 1u));
                 if (push) p.grp.work[pos] = make_uint2((unsigned int)vown, mask);
             }
-            v0 = vn0; v1 = vn1;
         }
-        if (tid == 0) s_it[(iter + 1) & 1] = nxt;
         __syncthreads();
     }
     n_decided = (unsigned int)warp_sum_u64((unsigned long long)n_decided);
