@@ -23,7 +23,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "nvcc")
-    cmd = [nvcc] + FLAGS + ["-o", OUT, SRC, "-ldl"]
+    cmd = [nvcc] + FLAGS + os.environ.get("DESMAN_B200_NVCC_FLAGS", "").split() + ["-o", OUT, SRC, "-ldl"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)

@@ -136,7 +136,7 @@ struct desman_ctx {
     unsigned long long *agg_keys = nullptr, *agg_code = nullptr, *agg_N = nullptr;
     int *agg_ids = nullptr;
     unsigned int *agg_nslots = nullptr;
-    int *agg_ctl = nullptr;                  // [4] rebuild wanted | rebuild running | overflow | flips since rebuild
+    int *agg_ctl = nullptr;                  // [AGG_CTL_WORDS] rebuild wanted | - | overflow | flips since rebuild | work cursors of K2b
     size_t agg_H = 0, agg_cap_slots = 0, agg_cap_cells = 0;
     bool agg_valid = false;                  // device table reflects the current device tau and counts
     double total_reads = 0.0, ll_scale = 1.0;
@@ -585,8 +585,8 @@ static int ensure_agg(desman_ctx *c)
         c->agg_valid = false;
     }
     if (!c->agg_ctl) {
-        CU(cudaMalloc(&c->agg_ctl, 4 * sizeof(int)));
-        CU(cudaMemsetAsync(c->agg_ctl, 0, 4 * sizeof(int), c->stream));
+        CU(cudaMalloc(&c->agg_ctl, AGG_CTL_WORDS * sizeof(int)));
+        CU(cudaMemsetAsync(c->agg_ctl, 0, AGG_CTL_WORDS * sizeof(int), c->stream));
     }
     // site groups of the screening pass
     if (V > c->grp_cap_v || c->agg_cap_slots > c->grp_cap_slots) {

@@ -22,8 +22,15 @@
 #include "common.cuh"
 
 #define STAGE_MUB 7
+#define STAGE_MUC 8
+#define STAGE_MUC 8
 #define MUB_WARPS 8
 #define MUB_EMPTY 0xffffffffffffffffull
+#define AGG_CTL_WORDS 16          // ctl[4 + chunk]: work cursor of mu_binomial_kernel for sample chunk `chunk` (< MUB_CURSORS)
+#define MUB_CURSORS 12
+#ifndef MUB_MIN_BLOCKS
+#define MUB_MIN_BLOCKS 2
+#endif
 
 // Persistent pattern table.  N[slot][s][a] = sum of the counts of all sites whose haplotype pattern is slot_code[slot].
 // Built by mu_aggregate_kernel, then kept current by the tau kernel (a site that changes pattern moves its counts),
@@ -239,7 +246,97 @@ __device__ __noinline__ long long binomial_draw_d(long long n, double p, double 
 // shared memory per warp: w[G][32], suf[G+1][32] (double), acc[G][32], E[16][32] (unsigned long long)
 static inline size_t mub_smem_bytes(int G) { return (size_t)MUB_WARPS * 32 * 8 * (size_t)(3 * G + 1 + 16) + 16 * 8; }
 
-__global__ void __launch_bounds__(MUB_WARPS * 32) mu_binomial_kernel(MuAggParams p)
+// One work item: the pattern `slot`, this lane's sample s.  The multinomial of a cell (slot, s, a) over the strains, weights
+// gamma[s,g]*eta[tau_g,a], factorises exactly over the CLASSES of the pattern (class b = the strains with tau_g == b): first
+// the reads are split over the classes with weights eta[b,a]*Gamma_b (Gamma_b = sum of gamma over the class) -- these are the
+// E statistics (HaploSNP_Sampler.py:301) -- and then, inside a class, over its strains with weights gamma[s,g], which do not
+// depend on the observed base a: the four class totals are merged before that second split (:309 sums over a anyway).
+// A biallelic pattern costs 4 + (G - 2) binomial draws per (slot, s) instead of 4 (G - 1).
+//   phase A  cell (slot,s,a), classes present in ascending b: X_b ~ Bin(rem, W_b/suf, suf'/suf), W_b = eta[b,a]*Gamma_b, stream
+//            ctr = (code, sweep, STAGE_MUB<<28 | a<<26 | s), draw index b
+//   phase B  class b with M_b = sum_a X reads, strains ascending: X_g ~ Bin(rem, gamma_g/suf, suf'/suf), stream
+//            ctr = (code, sweep, STAGE_MUC<<28 | b<<26 | s), draw index g
+// identical, operation for operation, to oracle_mu_stats_agg.
+__device__ __forceinline__ void mub_item(const MuAggParams &p, BinStream &st, int slot, bool valid, int s, int lane, int G,
+                                         const double *eta_s, double *wS, double *sufS, unsigned long long *accS,
+                                         unsigned long long *eS)
+{
+    const int S = p.S;
+    const unsigned long long code = p.t.slot_code[slot];
+    st.c0 = (uint32_t)code; st.c1 = (uint32_t)(code >> 32);
+    long long n[4] = {0, 0, 0, 0};
+    if (valid) {
+        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(p.t.N + ((size_t)slot * S + s) * 4);
+        const ulonglong2 lo = src[0], hi = src[1];
+        n[0] = (long long)lo.x; n[1] = (long long)lo.y; n[2] = (long long)hi.x; n[3] = (long long)hi.y;
+    }
+    if ((n[0] | n[1] | n[2] | n[3]) <= 0) return;
+    // class masks (warp-uniform) and class abundances Gamma_b (ascending g, rounded adds)
+    uint32_t cmask[4] = {0u, 0u, 0u, 0u};
+    double Gm[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int g = 0; g < G; g++) {
+        const int b = code_get(code, g);
+        const double gm = p.gamma[(size_t)s * G + g];
+        wS[g * 32 + lane] = gm;
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (b == k) { cmask[k] |= 1u << g; Gm[k] = __dadd_rn(Gm[k], gm); }
+    }
+    const int lastk = cmask[3] ? 3 : cmask[2] ? 2 : cmask[1] ? 1 : 0;
+    long long M[4] = {0, 0, 0, 0};
+    // ---- phase A
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        if (n[a] <= 0) continue;
+        st.c3 = ((uint32_t)STAGE_MUB << 28) | ((uint32_t)a << 26) | (uint32_t)s;
+        double W[4], suf[5];
+        suf[4] = 0.0;
+#pragma unroll
+        for (int k = 3; k >= 0; k--) {
+            W[k] = cmask[k] ? __dmul_rn(eta_s[4 * k + a], Gm[k]) : 0.0;
+            suf[k] = cmask[k] ? __dadd_rn(W[k], suf[k + 1]) : suf[k + 1];
+        }
+        long long rem = n[a];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (!cmask[k]) continue;
+            const bool last = (k == lastk);
+            long long x;
+            if (last) x = rem;
+            else if (rem == 0) x = 0;
+            else x = binomial_draw_d(rem, __ddiv_rn(W[k], suf[k]), __ddiv_rn(suf[k + 1], suf[k]), st, k);
+            rem -= x;
+            if (x) { M[k] += x; eS[(a * 4 + k) * 32 + lane] += (unsigned long long)x; }
+        }
+    }
+    // ---- phase B
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (!cmask[k] || M[k] <= 0) continue;
+        st.c3 = ((uint32_t)STAGE_MUC << 28) | ((uint32_t)k << 26) | (uint32_t)s;
+        const int gl = 31 - __clz(cmask[k]);                 // last strain of the class
+        double suf = 0.0;
+        for (int g = gl; g >= 0; g--)
+            if ((cmask[k] >> g) & 1u) { suf = __dadd_rn(wS[g * 32 + lane], suf); sufS[g * 32 + lane] = suf; }
+        long long rem = M[k];
+        double sg = suf;                                      // suffix sum at the current strain
+        for (int g = 0; g <= gl; g++) {
+            if (!((cmask[k] >> g) & 1u)) continue;
+            long long x;
+            if (g == gl) x = rem;
+            else {
+                // suffix sum after this strain = suffix sum at the next strain of the class
+                const uint32_t higher = cmask[k] & ~((2u << g) - 1u);
+                const double sn = sufS[(__ffs(higher) - 1) * 32 + lane];
+                x = (rem == 0) ? 0 : binomial_draw_d(rem, __ddiv_rn(wS[g * 32 + lane], sg), __ddiv_rn(sn, sg), st, g);
+                sg = sn;
+            }
+            rem -= x;
+            if (x) accS[g * 32 + lane] += (unsigned long long)x;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(MUB_WARPS * 32, MUB_MIN_BLOCKS) mu_binomial_kernel(MuAggParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = p.S, G = p.G;
@@ -263,39 +360,23 @@ __global__ void __launch_bounds__(MUB_WARPS * 32) mu_binomial_kernel(MuAggParams
     BinStream st;
     st.c2 = p.sweep; st.k0 = (uint32_t)p.seed; st.k1 = (uint32_t)(p.seed >> 32) ^ p.shard;
 
-    // work item = (slot, base a) for this warp's sample chunk: 4x more, 4x smaller items than one per slot, which
-    // matters because the number of patterns P can be a few thousand only
-    for (int item = gw / nch; item < 4 * P; item += nw / nch) {
-        const int slot = item >> 2, a = item & 3;
-        const unsigned long long code = p.t.slot_code[slot];
-        st.c0 = (uint32_t)code; st.c1 = (uint32_t)(code >> 32);
-        long long n = 0;
-        if (valid) n = (long long)p.t.N[((size_t)slot * S + s) * 4 + a];
-        if (n <= 0) continue;
-        st.c3 = ((uint32_t)STAGE_MUB << 28) | ((uint32_t)a << 26) | (uint32_t)s;
-        // weights and suffix sums (descending, rounded adds)
-        double suf = 0.0;
-        sufS[G * 32 + lane] = 0.0;
-        for (int g = G - 1; g >= 0; g--) {
-            const double w = __dmul_rn(p.gamma[(size_t)s * G + g], eta_s[4 * code_get(code, g) + a]);
-            suf = __dadd_rn(w, suf);
-            wS[g * 32 + lane] = w;
-            sufS[g * 32 + lane] = suf;
+    // work item = pattern slot, for this warp's sample chunk.  Items are handed out dynamically (one cursor per sample
+    // chunk, cleared by table_maintain_kernel at the start of the sweep): their cost varies with the counts (inversion vs.
+    // rejection, number of attempts), and a static deal left a quarter of the SM time idle at the tail.  The statistics are
+    // integer sums, so the schedule does not change the result.
+    const bool dyn = nch <= MUB_CURSORS;
+    int item = gw / nch;
+    while (true) {
+        if (dyn) {
+            if (lane == 0) item = atomicAdd(p.t.ctl + 4 + chunk, 1);
+            item = __shfl_sync(DESMAN_FULL_MASK, item, 0);
         }
-        long long rem = n;
-        for (int g = 0; g < G; g++) {
-            long long x;
-            if (g == G - 1) x = rem;
-            else if (rem == 0) x = 0;
-            else {
-                const double sg = sufS[g * 32 + lane];
-                x = binomial_draw_d(rem, __ddiv_rn(wS[g * 32 + lane], sg), __ddiv_rn(sufS[(g + 1) * 32 + lane], sg), st, g);
-            }
-            rem -= x;
-            if (x) {
-                accS[g * 32 + lane] += (unsigned long long)x;
-                eS[(a * 4 + code_get(code, g)) * 32 + lane] += (unsigned long long)x;
-            }
+        if (item >= P) break;
+        const int item_cur = item;
+        if (!dyn) item += nw / nch;
+        {
+            const int item = item_cur;
+            mub_item(p, st, item, valid, s, lane, G, eta_s, wS, sufS, accS, eS);
         }
     }
     __syncwarp();

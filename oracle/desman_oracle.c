@@ -317,6 +317,7 @@ void oracle_mu_stats(const int64_t *tau, const double *gamma, const double *eta,
  * All arithmetic outside the three logs of the BTRS slow path is +,*,/,sqrt,floor in IEEE double without
  * contraction, identical in the CUDA kernel. */
 #define ORACLE_STAGE_MUB 7
+#define ORACLE_STAGE_MUC 8
 
 static inline double u53w(uint32_t hi, uint32_t lo)
 {
@@ -440,32 +441,73 @@ void oracle_mu_stats_agg(const int64_t *tau, const double *gamma, const double *
     {
         int64_t *lmu = (int64_t *)calloc((size_t)S * G + 16, sizeof(int64_t));
         int64_t *le = lmu + (size_t)S * G;
-        double w[64], suf[65];
+        double sufg[65];
 #pragma omp for schedule(dynamic, 8)
         for (int pi = 0; pi < P; pi++) {
             const uint64_t c = uniq[pi];
-            for (int s = 0; s < S; s++)
+            /* classes of the pattern: class b = the strains whose base is b */
+            uint32_t cmask[4] = {0u, 0u, 0u, 0u};
+            for (int g = 0; g < G; g++) cmask[(c >> (2 * g)) & 3] |= 1u << g;
+            const int lastk = cmask[3] ? 3 : cmask[2] ? 2 : cmask[1] ? 1 : 0;
+            for (int s = 0; s < S; s++) {
+                const int64_t *n = N + ((size_t)pi * S + s) * 4;
+                if ((n[0] | n[1] | n[2] | n[3]) <= 0) continue;
+                /* class abundances: ascending g, rounded adds from 0.0 */
+                double Gm[4] = {0.0, 0.0, 0.0, 0.0};
+                for (int g = 0; g < G; g++) { const int b = (int)((c >> (2 * g)) & 3); Gm[b] = Gm[b] + gamma[s * G + g]; }
+                int64_t M[4] = {0, 0, 0, 0};
+                bin_stream st;
+                st.c0 = (uint32_t)c; st.c1 = (uint32_t)(c >> 32); st.c2 = sweep;
+                st.seed = seed; st.shard = (uint32_t)v0;
+                /* phase A: reads observed as a, split over the classes (the E statistics, HaploSNP_Sampler.py:301) */
                 for (int a = 0; a < 4; a++) {
-                    int64_t n = N[((size_t)pi * S + s) * 4 + a];
-                    if (n <= 0) continue;
-                    for (int g = 0; g < G; g++) w[g] = gamma[s * G + g] * eta[((c >> (2 * g)) & 3) * 4 + a];
-                    suf[G] = 0.0;
-                    for (int g = G - 1; g >= 0; g--) suf[g] = w[g] + suf[g + 1];
-                    bin_stream st;
-                    st.c0 = (uint32_t)c; st.c1 = (uint32_t)(c >> 32); st.c2 = sweep;
+                    if (n[a] <= 0) continue;
                     st.c3 = ((uint32_t)ORACLE_STAGE_MUB << 28) | ((uint32_t)a << 26) | (uint32_t)s;
-                    st.seed = seed; st.shard = (uint32_t)v0;
-                    int64_t rem = n;
-                    for (int g = 0; g < G; g++) {
+                    double W[4], suf[5];
+                    suf[4] = 0.0;
+                    for (int k = 3; k >= 0; k--) {
+                        W[k] = cmask[k] ? eta[4 * k + a] * Gm[k] : 0.0;
+                        suf[k] = cmask[k] ? W[k] + suf[k + 1] : suf[k + 1];
+                    }
+                    int64_t rem = n[a];
+                    for (int k = 0; k < 4; k++) {
+                        if (!cmask[k]) continue;
                         int64_t x;
-                        if (g == G - 1) x = rem;
+                        if (k == lastk) x = rem;
                         else if (rem == 0) x = 0;
-                        else { st.g = g; x = binomial_draw(rem, w[g] / suf[g], suf[g + 1] / suf[g], &st); }
+                        else { st.g = k; x = binomial_draw(rem, W[k] / suf[k], suf[k + 1] / suf[k], &st); }
                         rem -= x;
-                        lmu[s * G + g] += x;
-                        le[a * 4 + (int)((c >> (2 * g)) & 3)] += x;
+                        M[k] += x;
+                        le[a * 4 + k] += x;
                     }
                 }
+                /* phase B: the reads of a class, split over its strains with weights gamma (:309, summed over a) */
+                for (int k = 0; k < 4; k++) {
+                    if (!cmask[k] || M[k] <= 0) continue;
+                    st.c3 = ((uint32_t)ORACLE_STAGE_MUC << 28) | ((uint32_t)k << 26) | (uint32_t)s;
+                    int gl = 0;
+                    for (int g = 0; g < G; g++) if ((cmask[k] >> g) & 1u) gl = g;
+                    double suf = 0.0;
+                    for (int g = gl; g >= 0; g--) if ((cmask[k] >> g) & 1u) { suf = gamma[s * G + g] + suf; sufg[g] = suf; }
+                    int64_t rem = M[k];
+                    double sg = suf;
+                    for (int g = 0; g <= gl; g++) {
+                        if (!((cmask[k] >> g) & 1u)) continue;
+                        int64_t x;
+                        if (g == gl) x = rem;
+                        else {
+                            int gn = g + 1;
+                            while (!((cmask[k] >> gn) & 1u)) gn++;
+                            const double sn = sufg[gn];
+                            st.g = g;
+                            x = (rem == 0) ? 0 : binomial_draw(rem, gamma[s * G + g] / sg, sn / sg, &st);
+                            sg = sn;
+                        }
+                        rem -= x;
+                        lmu[s * G + g] += x;
+                    }
+                }
+            }
         }
 #pragma omp critical
         {
