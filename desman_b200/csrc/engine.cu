@@ -133,7 +133,8 @@ struct desman_ctx {
     int fixed_tau = 0;                       // 1: update() skips the tau draw (update_fixed_tau, HaploSNP_Sampler.py:409-428)
     int mu_mode = 2;                         // 1: pattern-aggregated binomial statistics (K2b), 0: per-read categorical (K2),
                                              // 2: choose from (V, G): aggregated iff the ~12*2^G possible biallelic patterns are <= V/2
-    unsigned long long *agg_keys = nullptr, *agg_code = nullptr, *agg_N = nullptr;
+    unsigned long long *agg_keys = nullptr, *agg_code = nullptr, *agg_N = nullptr, *agg_classM = nullptr;
+    int classM_G = 0, classM_S = 0;
     int *agg_ids = nullptr;
     unsigned int *agg_nslots = nullptr;
     int *agg_ctl = nullptr;                  // [AGG_CTL_WORDS] rebuild wanted | - | overflow | flips since rebuild | work cursors of K2b
@@ -273,7 +274,7 @@ extern "C" int desman_ctx_destroy(desman_ctx *c)
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     void *ptrs[] = {c->counts, c->tau, c->tau_star, c->gamma, c->eta, c->eta_new, c->gamma_star, c->eta_star, c->stats,
                     c->red_i, c->agg_ctl, c->scal, c->flag, c->tau_cnt, c->tau_last, c->mt_state, c->words,
-                    c->scratch, c->flush_buf, c->tiers, c->agg_keys, c->agg_code, c->agg_N, c->agg_ids, c->agg_nslots,
+                    c->scratch, c->flush_buf, c->tiers, c->agg_keys, c->agg_code, c->agg_N, c->agg_ids, c->agg_nslots, c->agg_classM,
                     c->countsf, c->nsite, c->grp_site_slot, c->grp_order, c->grp_singles, c->grp_slot4, c->grp_gctl, c->grp_blk,
                     c->grp_items, c->grp_work};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -588,6 +589,15 @@ static int ensure_agg(desman_ctx *c)
         CU(cudaMalloc(&c->agg_ctl, AGG_CTL_WORDS * sizeof(int)));
         CU(cudaMemsetAsync(c->agg_ctl, 0, AGG_CTL_WORDS * sizeof(int), c->stream));
     }
+    // merged class totals of the statistics kernels: dense over the sets of strains
+    if (c->G <= MUC_MAX_G && (c->G != c->classM_G || c->S != c->classM_S)) {
+        if (c->agg_classM) cudaFree(c->agg_classM);
+        c->agg_classM = nullptr; c->classM_G = c->classM_S = 0;
+        const size_t n = ((size_t)1 << c->G) * c->S;
+        CU(cudaMalloc(&c->agg_classM, n * sizeof(unsigned long long)));
+        CU(cudaMemsetAsync(c->agg_classM, 0, n * sizeof(unsigned long long), c->stream));
+        c->classM_G = c->G; c->classM_S = c->S;
+    }
     // site groups of the screening pass
     if (V > c->grp_cap_v || c->agg_cap_slots > c->grp_cap_slots) {
         for (void *q : {(void *)c->grp_site_slot, (void *)c->grp_order, (void *)c->grp_singles, (void *)c->grp_slot4,
@@ -634,6 +644,7 @@ static MuAggParams agg_params(desman_ctx *c, const double *gamma, const double *
     p.t = agg_table(c);
     p.sum_mu = c->stats; p.esum = c->stats + (size_t)c->S * c->G;
     p.ll_scale = c->ll_scale; p.ll_fx = c->red_i;
+    p.classM = (c->G <= MUC_MAX_G && c->classM_G == c->G && c->classM_S == c->S) ? c->agg_classM : nullptr;
     return p;
 }
 
@@ -860,6 +871,15 @@ static int launch_mu_agg(desman_ctx *c, const double *gamma, const double *eta)
     {
         KSpan k(c, DESMAN_K_MU);
         mu_binomial_kernel<<<grid, MUB_WARPS * 32, smem, c->stream>>>(p);
+        if (p.classM) {
+            const size_t smem2 = muc_smem_bytes(c->G);
+            CU(cudaFuncSetAttribute(mu_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            long long want = (((long long)1 << c->G) * nch + MUB_WARPS - 1) / MUB_WARPS;
+            int grid2 = (int)(want < grid ? want : grid);
+            if (grid2 < 1) grid2 = 1;
+            while ((grid2 * MUB_WARPS) % nch) grid2++;
+            mu_class_kernel<<<grid2, MUB_WARPS * 32, smem2, c->stream>>>(p);
+        }
     }
     CU(cudaGetLastError());
     return DESMAN_OK;

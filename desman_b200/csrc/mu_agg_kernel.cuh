@@ -23,7 +23,9 @@
 
 #define STAGE_MUB 7
 #define STAGE_MUC 8
+#define MUC_MAX_G 16              // up to here the within-class splits are merged over all patterns sharing the class (dense table)
 #define STAGE_MUC 8
+#define MUC_MAX_G 16              // up to here the within-class splits are merged over all patterns sharing the class (dense table)
 #define MUB_WARPS 8
 #define MUB_EMPTY 0xffffffffffffffffull
 #define AGG_CTL_WORDS 16          // ctl[4 + chunk]: work cursor of mu_binomial_kernel for sample chunk `chunk` (< MUB_CURSORS)
@@ -62,6 +64,7 @@ struct MuAggParams {
     AggTable t;
     unsigned long long *sum_mu;  // [S][G] +=
     unsigned long long *esum;    // [16]   += (esum[a_obs*4 + b_true])
+    unsigned long long *classM;  // [2^G][S] reads per (set of strains, sample) awaiting their within-class split (G <= MUC_MAX_G), or null
     double ll_scale;             // 2^k of the fixed-point log-likelihood accumulator
     unsigned long long *ll_fx;   // += llrint(sum n*log p * 2^k)  (two's complement)
 };
@@ -256,7 +259,9 @@ static inline size_t mub_smem_bytes(int G) { return (size_t)MUB_WARPS * 32 * 8 *
 //            ctr = (code, sweep, STAGE_MUB<<28 | a<<26 | s), draw index b
 //   phase B  class b with M_b = sum_a X reads, strains ascending: X_g ~ Bin(rem, gamma_g/suf, suf'/suf), stream
 //            ctr = (code, sweep, STAGE_MUC<<28 | b<<26 | s), draw index g
-// identical, operation for operation, to oracle_mu_stats_agg.
+// The weights of phase B depend on the class only through its SET of strains, so for G <= MUC_MAX_G the class totals of all
+// patterns are first merged per (set, sample) in classM and split once (mu_class_kernel: ctr = (set, 0, sweep, STAGE_MUC<<28 | s));
+// a one-strain class needs no draw.  Identical, operation for operation, to oracle_mu_stats_agg.
 __device__ __forceinline__ void mub_item(const MuAggParams &p, BinStream &st, int slot, bool valid, int s, int lane, int G,
                                          const double *eta_s, double *wS, double *sufS, unsigned long long *accS,
                                          unsigned long long *eS)
@@ -309,6 +314,15 @@ __device__ __forceinline__ void mub_item(const MuAggParams &p, BinStream &st, in
         }
     }
     // ---- phase B
+    if (p.classM) {                                            // merged over patterns: mu_class_kernel does the split
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (!cmask[k] || M[k] <= 0) continue;
+            if ((cmask[k] & (cmask[k] - 1u)) == 0u) accS[(31 - __clz(cmask[k])) * 32 + lane] += (unsigned long long)M[k];
+            else atomicAdd(p.classM + (size_t)cmask[k] * S + s, (unsigned long long)M[k]);
+        }
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 4; k++) {
         if (!cmask[k] || M[k] <= 0) continue;
@@ -390,3 +404,60 @@ __global__ void __launch_bounds__(MUB_WARPS * 32, MUB_MIN_BLOCKS) mu_binomial_ke
         if (lane == 0 && t) atomicAdd(p.esum + i, t);
     }
 }
+
+// Within-class split, merged over patterns (G <= MUC_MAX_G): one warp per (set of strains, 32-sample chunk); the M reads of the
+// set at sample s are dealt to its strains (ascending) by a chain of conditional binomials with weights gamma[s,g].
+__global__ void __launch_bounds__(MUB_WARPS * 32, MUB_MIN_BLOCKS) mu_class_kernel(MuAggParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int S = p.S, G = p.G;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    double *wS = reinterpret_cast<double *>(smem_raw) + (size_t)wib * 32 * (3 * G + 1);       // [G][32]
+    double *sufS = wS + G * 32;                                                              // [G+1][32]
+    unsigned long long *accS = reinterpret_cast<unsigned long long *>(sufS + (G + 1) * 32);  // [G][32]
+    for (int i = lane; i < G * 32; i += 32) accS[i] = 0ull;
+    __syncwarp();
+    const int nch = (S + 31) >> 5;
+    const int gw = blockIdx.x * MUB_WARPS + wib, nw = gridDim.x * MUB_WARPS;      // nw % nch == 0 (host)
+    const int chunk = gw % nch, s = chunk * 32 + lane;
+    const bool valid = s < S;
+    if (valid) for (int g = 0; g < G; g++) wS[g * 32 + lane] = p.gamma[(size_t)s * G + g];
+    BinStream st;
+    st.c1 = 0u; st.c2 = p.sweep; st.k0 = (uint32_t)p.seed; st.k1 = (uint32_t)(p.seed >> 32) ^ p.shard;
+    st.c3 = ((uint32_t)STAGE_MUC << 28) | (uint32_t)s;
+    const uint32_t nmask = 1u << G;
+    for (uint32_t mask = 3u + (uint32_t)(gw / nch); mask < nmask; mask += (uint32_t)(nw / nch)) {
+        if ((mask & (mask - 1u)) == 0u) continue;              // one strain: settled in phase A
+        long long M = 0;
+        if (valid) M = (long long)p.classM[(size_t)mask * S + s];
+        if (M <= 0) continue;
+        p.classM[(size_t)mask * S + s] = 0ull;                  // consumed
+        st.c0 = mask;
+        const int gl = 31 - __clz(mask);
+        double suf = 0.0;
+        for (int g = gl; g >= 0; g--)
+            if ((mask >> g) & 1u) { suf = __dadd_rn(wS[g * 32 + lane], suf); sufS[g * 32 + lane] = suf; }
+        long long rem = M;
+        double sg = suf;
+        for (int g = 0; g <= gl; g++) {
+            if (!((mask >> g) & 1u)) continue;
+            long long x;
+            if (g == gl) x = rem;
+            else {
+                const uint32_t higher = mask & ~((2u << g) - 1u);
+                const double sn = sufS[(__ffs(higher) - 1) * 32 + lane];
+                x = (rem == 0) ? 0 : binomial_draw_d(rem, __ddiv_rn(wS[g * 32 + lane], sg), __ddiv_rn(sn, sg), st, g);
+                sg = sn;
+            }
+            rem -= x;
+            if (x) accS[g * 32 + lane] += (unsigned long long)x;
+        }
+    }
+    __syncwarp();
+    if (valid)
+        for (int g = 0; g < G; g++) {
+            const unsigned long long x = accS[g * 32 + lane];
+            if (x) atomicAdd(p.sum_mu + (size_t)s * G + g, x);
+        }
+}
+static inline size_t muc_smem_bytes(int G) { return (size_t)MUB_WARPS * 32 * 8 * (size_t)(3 * G + 1); }

@@ -318,6 +318,7 @@ void oracle_mu_stats(const int64_t *tau, const double *gamma, const double *eta,
  * contraction, identical in the CUDA kernel. */
 #define ORACLE_STAGE_MUB 7
 #define ORACLE_STAGE_MUC 8
+#define ORACLE_MUC_MAX_G 16
 
 static inline double u53w(uint32_t hi, uint32_t lo)
 {
@@ -437,6 +438,7 @@ void oracle_mu_stats_agg(const int64_t *tau, const double *gamma, const double *
         const int64_t *src = variants + (size_t)v * S * 4;
         for (int i = 0; i < S * 4; i++) dst[i] += src[i];
     }
+    int64_t *classM = (G <= ORACLE_MUC_MAX_G) ? (int64_t *)calloc(((size_t)1 << G) * S, sizeof(int64_t)) : NULL;
 #pragma omp parallel
     {
         int64_t *lmu = (int64_t *)calloc((size_t)S * G + 16, sizeof(int64_t));
@@ -481,7 +483,20 @@ void oracle_mu_stats_agg(const int64_t *tau, const double *gamma, const double *
                         le[a * 4 + k] += x;
                     }
                 }
-                /* phase B: the reads of a class, split over its strains with weights gamma (:309, summed over a) */
+                /* phase B: the reads of a class, split over its strains with weights gamma (:309, summed over a).
+                 * The weights depend on the class only through its set of strains: for G <= ORACLE_MUC_MAX_G the totals of
+                 * all patterns are merged per (set, sample) first and split once, below. */
+                if (classM) {
+                    for (int k = 0; k < 4; k++) {
+                        if (!cmask[k] || M[k] <= 0) continue;
+                        if ((cmask[k] & (cmask[k] - 1u)) == 0u) { int g = 0; while (!((cmask[k] >> g) & 1u)) g++; lmu[s * G + g] += M[k]; }
+                        else {
+#pragma omp atomic
+                            classM[(size_t)cmask[k] * S + s] += M[k];
+                        }
+                    }
+                    continue;
+                }
                 for (int k = 0; k < 4; k++) {
                     if (!cmask[k] || M[k] <= 0) continue;
                     st.c3 = ((uint32_t)ORACLE_STAGE_MUC << 28) | ((uint32_t)k << 26) | (uint32_t)s;
@@ -515,6 +530,54 @@ void oracle_mu_stats_agg(const int64_t *tau, const double *gamma, const double *
             for (int i = 0; i < 16; i++) esum[i] += le[i];
         }
         free(lmu);
+    }
+    if (classM) {
+        /* merged within-class split: set of strains `mask`, sample s, M reads; strains ascending, weights gamma[s,g];
+         * stream ctr = (mask, 0, sweep, STAGE_MUC<<28 | s), draw index g */
+        const uint32_t nmask = 1u << G;
+#pragma omp parallel
+        {
+            int64_t *lmu = (int64_t *)calloc((size_t)S * G, sizeof(int64_t));
+            double sufg[65];
+#pragma omp for schedule(dynamic, 16)
+            for (int64_t mk = 3; mk < (int64_t)nmask; mk++) {
+                const uint32_t mask = (uint32_t)mk;
+                if ((mask & (mask - 1u)) == 0u) continue;
+                int gl = 0;
+                for (int g = 0; g < G; g++) if ((mask >> g) & 1u) gl = g;
+                for (int s = 0; s < S; s++) {
+                    const int64_t M = classM[(size_t)mask * S + s];
+                    if (M <= 0) continue;
+                    bin_stream st;
+                    st.c0 = mask; st.c1 = 0u; st.c2 = sweep;
+                    st.c3 = ((uint32_t)ORACLE_STAGE_MUC << 28) | (uint32_t)s;
+                    st.seed = seed; st.shard = (uint32_t)v0;
+                    double suf = 0.0;
+                    for (int g = gl; g >= 0; g--) if ((mask >> g) & 1u) { suf = gamma[s * G + g] + suf; sufg[g] = suf; }
+                    int64_t rem = M;
+                    double sg = suf;
+                    for (int g = 0; g <= gl; g++) {
+                        if (!((mask >> g) & 1u)) continue;
+                        int64_t x;
+                        if (g == gl) x = rem;
+                        else {
+                            int gn = g + 1;
+                            while (!((mask >> gn) & 1u)) gn++;
+                            const double sn = sufg[gn];
+                            st.g = g;
+                            x = (rem == 0) ? 0 : binomial_draw(rem, gamma[s * G + g] / sg, sn / sg, &st);
+                            sg = sn;
+                        }
+                        rem -= x;
+                        lmu[s * G + g] += x;
+                    }
+                }
+            }
+#pragma omp critical
+            for (size_t i = 0; i < (size_t)S * G; i++) sum_mu[i] += lmu[i];
+            free(lmu);
+        }
+        free(classM);
     }
     free(code); free(uniq); free(N);
 }
