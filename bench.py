@@ -87,12 +87,14 @@ def measured_hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def algorithmic_bytes(kernel, V, S, G):
+def algorithmic_bytes(kernel, V, S, G, slots=None):
     """DESIGN.md section 5 / SURVEY.md 8d: bytes one launch must move under the canonical packed layout."""
-    if kernel == "tau_sample":      # counts once, tau read+write, gamma, eta
+    if kernel in ("tau_sample", "tau_update"):      # counts once, tau read+write, gamma, eta
         return 16 * V * S + 2 * V * G + 8 * S * G + 128
-    if kernel == "mu_stats":        # per-read form: counts once, tau read, gamma, eta, statistics out.  (The pattern-
-        return 16 * V * S + V * G + 8 * S * G + 128 + 8 * (S * G + 16)   # aggregated form reads the small table instead.)
+    if kernel == "mu_stats" and slots:   # pattern-aggregated form: the table N[slot][s][4] (uint64) once, codes, gamma, eta, statistics
+        return 32 * slots * S + 8 * slots + 8 * S * G + 128 + 8 * (S * G + 16)
+    if kernel == "mu_stats":        # per-read form: counts once, tau read, gamma, eta, statistics out
+        return 16 * V * S + V * G + 8 * S * G + 128 + 8 * (S * G + 16)
     raise KeyError(kernel)
 
 
@@ -180,10 +182,11 @@ def run_b200(args):
     clk = clocks.stop()
     tm = e.get_timing()
     ms_total = max_over_ranks(td, tm["elapsed_ms"])
-    # per sweep: agg_reset, agg_begin, mu_aggregate (the three exit at once unless a table rebuild is pending),
-    # mu_binomial, draw_gamma_eta, tau_sample, ll_table, finalize_sweep, copy_tau_if; +6 for the pre-sweep ll/lp/star
-    # pass and +1 for flush_tau_counts (the L2 flush writes sit outside the timed events)
-    launches = 9 * K + 7
+    # counted by the engine at every launch site: per sweep table_maintain, mu_binomial, mu_class, draw_gamma_eta,
+    # tau_group_mma, tau_sample, ll_table, finalize_sweep, copy_tau_if; + the pre-sweep maintain/ll/finalize/copy pass and
+    # flush_tau_counts (the L2 flush writes sit outside the timed events and are not counted)
+    launches = int(sum(tm["kernel_launches"].values()))
+    grp = e.get_group_stats()
     value = (V_total / UNIT_V) * K / (ms_total / 1e3)
 
     # ---- per-kernel pass (events around every launch) for the roofline object
@@ -192,8 +195,10 @@ def run_b200(args):
     e.update(Kp)
     tk = e.get_timing()
     kms = {k: v / Kp for k, v in tk["kernel_ms"].items()}
+    # the tau update = screening pass over the pattern groups (tau_group) + per-site kernel on the sites it left undecided
+    kms["tau_update"] = kms["tau_group"] + kms["tau_sample"]
     peak, peak_src = measured_hbm_peak()
-    dom = max(("tau_sample", "mu_stats"), key=lambda k: kms[k])
+    dom = max(("tau_update", "mu_stats"), key=lambda k: kms[k])
 
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -201,7 +206,7 @@ def run_b200(args):
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch", {})
 
     def roof(kernel):
-        b = algorithmic_bytes(kernel, V, S, G)
+        b = algorithmic_bytes(kernel, V, S, G, slots=grp["slots"] if engine.auto_mu_mode(V, G) == 1 else None)
         ach = b / (kms[kernel] * 1e-3) / 1e9
         return dict(kernel=kernel, bound="hbm", achieved=ach, peak=peak, unit="GB/s", frac=ach / peak,
                     traffic=traffic.get(kernel),
@@ -249,7 +254,8 @@ def run_b200(args):
         "gpu_launches": launches,
         "clocks": clk,
         "roofline": roof(dom),
-        "roofline_tau_sample": roof("tau_sample"),
+        "roofline_tau_sample": roof("tau_update"),
+        "tau_groups": grp,
         "kernel_ms_per_sweep": kms,
         "wall_s_timed_region": t_wall,
         "chain": {"lp_first": float(res["lp_store"][0]), "lp_last": float(res["lp_store"][-1]),

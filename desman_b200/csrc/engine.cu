@@ -196,11 +196,11 @@ static cudaEvent_t get_event(desman_ctx *c)
     return c->ev_pool[c->ev_used++];
 }
 
-struct KSpan {  // brackets one kernel launch with events when per-kernel profiling is on
+struct KSpan {  // brackets n kernel launches with events when per-kernel profiling is on; k_launch counts the launches
     desman_ctx *c; int kind; cudaEvent_t a = nullptr;
-    KSpan(desman_ctx *c_, int kind_) : c(c_), kind(kind_)
+    KSpan(desman_ctx *c_, int kind_, int n = 1) : c(c_), kind(kind_)
     {
-        c->k_launch[kind]++;
+        c->k_launch[kind] += n;
         if (c->prof_kernels) { a = get_event(c); cudaEventRecord(a, c->stream); }
     }
     ~KSpan()
@@ -869,7 +869,7 @@ static int launch_mu_agg(desman_ctx *c, const double *gamma, const double *eta)
     int grid = c->sm_count * occ;
     while ((grid * MUB_WARPS) % nch) grid++;
     {
-        KSpan k(c, DESMAN_K_MU);
+        KSpan k(c, DESMAN_K_MU, p.classM ? 2 : 1);
         mu_binomial_kernel<<<grid, MUB_WARPS * 32, smem, c->stream>>>(p);
         if (p.classM) {
             const size_t smem2 = muc_smem_bytes(c->G);
@@ -951,7 +951,11 @@ static int launch_draw(desman_ctx *c, const unsigned long long *stats, double *g
     CU(cudaFuncSetAttribute(draw_gamma_eta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         KSpan k(c, DESMAN_K_DRAW);
-        draw_gamma_eta_kernel<<<1, 256, smem, c->stream>>>(p);
+        // one variate per thread where possible: the kernel is one latency chain (rejection sampler in FP64) per variate
+        int threads = ((c->S * c->G + 16 + 31) / 32) * 32;
+        if (threads > DRAW_MAX_THREADS) threads = DRAW_MAX_THREADS;
+        if (threads < 64) threads = 64;
+        draw_gamma_eta_kernel<<<1, threads, smem, c->stream>>>(p);
     }
     CU(cudaGetLastError());
     return DESMAN_OK;
@@ -979,7 +983,7 @@ static int launch_finalize(desman_ctx *c, const double *gamma, const double *eta
     p.gctl = group_config(c, nullptr, nullptr) ? c->grp_gctl : nullptr;
     p.V_local = (long long)c->V;
     {
-        KSpan k(c, DESMAN_K_FINAL);
+        KSpan k(c, DESMAN_K_FINAL, 2);
         finalize_sweep_kernel<<<1, 256, 0, c->stream>>>(p);
         copy_tau_if_kernel<<<c->sm_count, 256, 0, c->stream>>>(c->tau, c->tau_star, (size_t)c->V * c->G, c->flag);
     }
@@ -1153,7 +1157,10 @@ extern "C" int desman_update(desman_ctx *c, int n_iter, double *gamma_store, dou
         sweep_end(c);
         c->sweep++;
     }
-    flush_tau_counts_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(c->tau, c->tau_cnt, c->tau_last, nvg, (uint32_t)n_iter);
+    {
+        KSpan k(c, DESMAN_K_OTHER);
+        flush_tau_counts_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(c->tau, c->tau_cnt, c->tau_last, nvg, (uint32_t)n_iter);
+    }
     CU(cudaGetLastError());
     c->last_n_iter = (uint32_t)n_iter;
     RET(fetch_stores(c, n_iter, sb, gamma_store, eta_store, ll_store, lp_store, nchange_store));

@@ -113,6 +113,7 @@ __device__ double gamma_variate(double shape, uint32_t k0, uint32_t k1, uint32_t
     return y;
 }
 
+#define DRAW_MAX_THREADS 1024
 struct DrawParams {
     const unsigned long long *sum_mu;  // [S][G]
     const unsigned long long *esum;    // [16] esum[a_obs*4+b_true]
@@ -124,7 +125,7 @@ struct DrawParams {
     double *eta_out;    // [16]
 };
 
-__global__ void __launch_bounds__(256) draw_gamma_eta_kernel(DrawParams p)
+__global__ void __launch_bounds__(DRAW_MAX_THREADS) draw_gamma_eta_kernel(DrawParams p)
 {
     extern __shared__ double y[];  // [S*G + 16]
     const int S = p.S, G = p.G, nG = S * G;
@@ -248,8 +249,12 @@ __global__ void copy_tau_if_kernel(const uint8_t *__restrict__ src, uint8_t *__r
                                    const int *__restrict__ flag)
 {
     if (*flag == 0) return;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        dst[i] = src[i];
+    // 16-byte words (cudaMalloc'ed buffers are 256-byte aligned), byte tail
+    const size_t n16 = n / 16, i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+    for (size_t i = i0; i < n16; i += st) d4[i] = s4[i];
+    for (size_t i = n16 * 16 + i0; i < n; i += st) dst[i] = src[i];
 }
 
 // close the lazy occupancy counters at the end of an update(): cnt[vg][tau_vg] += n_iter - last[vg]

@@ -332,7 +332,7 @@ static inline int tgm_tiles(int G) { return (3 * G + 15) / 16; }
 static inline size_t tgm_table_bytes(int S, int G)
 {
     const size_t Sp = (size_t)((S + 15) & ~15);
-    return Sp * (size_t)(16 * tgm_tiles(G) + 2) * sizeof(float4);
+    return Sp * (size_t)(16 * tgm_tiles(G) + 2) * sizeof(float4) + (size_t)3 * tgm_tiles(G) * 8 * 32 * sizeof(float);   // + split-pass sums
 }
 
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
@@ -385,6 +385,7 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
     float *gT32 = reinterpret_cast<float *>(eta32 + 4);                   // [G][Sp]
     float4 *W = reinterpret_cast<float4 *>(gT32 + (size_t)G * Sp);        // [Sp][STR] fragment order
     float *Wf = reinterpret_cast<float *>(W);
+    float *red = Wf + (size_t)Sp * STR * 4;                               // [TGM_WARPS - 1][MT * 8][32] partial sums of split passes
     __shared__ unsigned int gmin_bits, emin_bits;
 
     const int tid = threadIdx.x, lane = tid & 31, wib = tid >> 5;
@@ -424,7 +425,7 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
     // per read, log2 units: entry model (relative parts, lg2.approx floors, lg2.approx and the lq - lP rounding per unit of
     // |lg2|, FP64 cancellation) + [TF32 split + Sp accumulation steps] * 2^-20 * max|Wd| of the item
     const float e_entry = TAU_C0 + (2.3841858e-7f + 5.9604645e-8f) * (2.0f * mq0) + TAU_CANCEL(G) / fmaxf(qmin, TAU_QMIN);
-    const float e_mma = (float)(Sp + 1) * 9.5367432e-7f;
+    const float e_mma = (float)(Sp + 8) * 9.5367432e-7f;   // + the FP32 adds that join the partial sums of a split pass
     const float LN2 = 0.69314718f;
     // q, P <= 1 (convex combinations of eta entries), so lg2 q, lg2 P <= 0 and |Wd| = |lg2 q - lg2 P| <= mq0
     const float bn_scale = (e_entry + e_mma * mq0) * LN2 * 1.0001f;
@@ -445,8 +446,15 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
         if (tid == 0) l2_prefetch_row(p.countsf + (size_t)nxt0.y * S, (uint32_t)min(nxt0.z, ROUND) * row_bytes);
     }
 
+#ifdef TGM_PROFILE
+    long long t_build = 0, t_pass = 0, t_sync1 = 0, t_sync2 = 0, t_all0 = clock64(), n_it = 0, n_sites = 0;
+#define TGM_T(x) const long long x = clock64()
+#else
+#define TGM_T(x)
+#endif
     int iter = 0;
     for (int it = blockIdx.x; it < nitems; it += gridDim.x, iter++) {
+        TGM_T(tp0);
         const int4 item = nxt0, item1 = nxt1;
         const int slot = item.x, begin = item.y, count = item.z;
         const uint64_t code = ((uint64_t)(unsigned int)item1.y << 32) | (unsigned int)item1.x;
@@ -492,25 +500,14 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
         }
         // first round of the next item into L2 while this one is contracted
         if (tid == 0 && it + (int)gridDim.x < nitems) l2_prefetch_row(p.countsf + (size_t)nxt0.y * S, (uint32_t)min(nxt0.z, ROUND) * row_bytes);
+        TGM_T(tp1);
         __syncthreads();
+        TGM_T(tp2);
 
-        for (; base < count; base += ROUND) {
-            // this warp's next pass into L2
-            if (base + ROUND < count) l2_prefetch_row(rows + (size_t)(base + ROUND) * S, (uint32_t)min(count - base - ROUND, TG_PASS_SITES) * row_bytes);
-            // the site this lane decides for: lanes g8 < 4 own row k = {2 t4, 2 t4 + 1, 8 + 2 t4, 9 + 2 t4}[g8] of the pass
-            const int kown = ((g8 & 2) << 2) + 2 * t4 + (g8 & 1);
-            const bool own = g8 < 4 && base + kown < count;
-            const int vown = p.grp.order[begin + (base + kown < count ? base + kown : 0)];
-            // read totals of the 4 sites whose sums this lane holds
-            float nk[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const int idx = base + ((k & 2) << 2) + 2 * t4 + (k & 1);
-                nk[k] = p.nsite[begin + (idx < count ? idx : 0)];
-            }
-            const int sown = p.grp.site_slot[vown];
-            const float4 *row0 = rows + (size_t)(base + g8 < count ? base + g8 : 0) * S + t4,
-                         *row1 = rows + (size_t)(base + g8 + 8 < count ? base + g8 + 8 : 0) * S + t4;
+        // ---- contraction of one 16-site pass over the 4-sample groups [qlo, qhi): D (hi + lo parts) -> acc[mt][nt][4]
+        auto contract = [&](int pbase, int qlo, int qhi, float (&acc)[MT][2][4]) {
+            const float4 *row0 = rows + (size_t)(pbase + g8 < count ? pbase + g8 : 0) * S + t4,
+                         *row1 = rows + (size_t)(pbase + g8 + 8 < count ? pbase + g8 + 8 : 0) * S + t4;
             const float4 *Wq = W + (size_t)t4 * STR + g8;
             float ch[MT][2][4], cl[MT][2][4];
 #pragma unroll
@@ -519,8 +516,8 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
                 for (int nt = 0; nt < 2; nt++)
 #pragma unroll
                     for (int i = 0; i < 4; i++) { ch[mt][nt][i] = 0.f; cl[mt][nt][i] = 0.f; }
-            // 4-sample groups, four at a time: 8 cells in flight per lane
-            for (int q = 0; q < nq; q += 4) {
+            // four groups at a time: 8 cells in flight per lane
+            for (int q = qlo; q < qhi; q += 4) {
                 float4 c0[4], c1[4];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
@@ -531,8 +528,28 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
 #pragma unroll
                 for (int u = 0; u < 4; u++) tgm_group<MT>(ch, cl, c0[u], c1[u], Wq + (size_t)(4 * (q + u)) * STR);
             }
-            // a strain is decided "stay" iff each of its three candidates trails the current base by > 60 nats after the bound.
-            // accumulator (mt, nt, i): table column 16 mt + 8 (i >> 1) + g8, site 8 nt + 2 t4 + (i & 1)
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) acc[mt][nt][i] = ch[mt][nt][i] + cl[mt][nt][i];
+        };
+        // ---- decisions of one pass from its complete sums; undecided sites go to the work list
+        // accumulator (mt, nt, i): table column 16 mt + 8 (i >> 1) + g8, site 8 nt + 2 t4 + (i & 1)
+        auto decide = [&](int pbase, const float (&acc)[MT][2][4]) {
+            // the site this lane decides for: lanes g8 < 4 own row k = {2 t4, 2 t4 + 1, 8 + 2 t4, 9 + 2 t4}[g8] of the pass
+            const int kown = ((g8 & 2) << 2) + 2 * t4 + (g8 & 1);
+            const bool own = g8 < 4 && pbase + kown < count;
+            const int vown = p.grp.order[begin + (pbase + kown < count ? pbase + kown : 0)];
+            const int sown = p.grp.site_slot[vown];
+            float nk[4];                                                  // read totals of the 4 sites whose sums this lane holds
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int idx = pbase + ((k & 2) << 2) + 2 * t4 + (k & 1);
+                nk[k] = p.nsite[begin + (idx < count ? idx : 0)];
+            }
+            // a strain is decided "stay" iff each of its three candidates trails the current base by > 60 nats after the bound
             uint32_t m[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
             for (int mt = 0; mt < MT; mt++)
@@ -543,7 +560,7 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
                         const uint32_t bit = 1u << (c / 3);
 #pragma unroll
                         for (int k = 0; k < 4; k++) {
-                            const float d = ch[mt][k >> 1][2 * hf + (k & 1)] + cl[mt][k >> 1][2 * hf + (k & 1)];
+                            const float d = acc[mt][k >> 1][2 * hf + (k & 1)];
                             if (!(d * LN2 + (nk[k] * bn_scale + 1e-6f) < -TAU_GAP)) m[k] |= bit;
                         }
                     }
@@ -572,9 +589,57 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
                 pos = __shfl_sync(DESMAN_FULL_MASK, pos, 0) + __popc(bal & ((1u << lane) - 1u));
                 if (push) p.grp.work[pos] = make_uint2((unsigned int)vown, mask);
             }
+        };
+
+        const int np = (count + TG_PASS_SITES - 1) / TG_PASS_SITES;
+        if (np > 2) {
+            // long item: whole passes, round robin over the warps
+            for (; base < count; base += ROUND) {
+                if (base + ROUND < count) l2_prefetch_row(rows + (size_t)(base + ROUND) * S, (uint32_t)min(count - base - ROUND, TG_PASS_SITES) * row_bytes);
+                float acc[MT][2][4];
+                contract(base, 0, nq, acc);
+                decide(base, acc);
+            }
+        } else {
+            // short item (one or two passes): the warps split the SAMPLES of a pass (4 or 2 warps per pass) and the partial
+            // sums meet in shared memory, so that all four warps work and the item's latency is a fraction of a pass
+            const int kw = (np == 1) ? TGM_WARPS : TGM_WARPS / 2;
+            const int pass = wib / kw, part = wib % kw;
+            const int qper = ((nq / 4 + kw - 1) / kw) * 4;
+            const int qlo = min(nq, part * qper), qhi = min(nq, qlo + qper);
+            float acc[MT][2][4];
+            contract(pass * TG_PASS_SITES, qlo, qhi, acc);
+            if (part > 0) {
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                    for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                        for (int i = 0; i < 4; i++) red[((wib - 1) * MT * 8 + (mt * 2 + nt) * 4 + i) * 32 + lane] = acc[mt][nt][i];
+            }
+            __syncthreads();
+            if (part == 0) {
+                for (int w2 = wib + 1; w2 < wib + kw; w2++)
+#pragma unroll
+                    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                        for (int nt = 0; nt < 2; nt++)
+#pragma unroll
+                            for (int i = 0; i < 4; i++) acc[mt][nt][i] += red[((w2 - 1) * MT * 8 + (mt * 2 + nt) * 4 + i) * 32 + lane];
+                decide(pass * TG_PASS_SITES, acc);
+            }
         }
+        TGM_T(tp3);
         __syncthreads();
+#ifdef TGM_PROFILE
+        { const long long tp4 = clock64(); t_build += tp1 - tp0; t_sync1 += tp2 - tp1; t_pass += tp3 - tp2; t_sync2 += tp4 - tp3; n_it++; n_sites += count; }
+#endif
     }
+#ifdef TGM_PROFILE
+    if (lane == 0 && (blockIdx.x % 97 == 0 || blockIdx.x == gridDim.x - 1) && p.tier_counts)
+        printf("cta %4d warp %d items %lld sites %lld build %lld sync1 %lld pass %lld sync2 %lld total %lld\n", (int)blockIdx.x, wib, n_it, n_sites,
+               t_build, t_sync1, t_pass, t_sync2, clock64() - t_all0);
+#endif
     n_decided = (unsigned int)warp_sum_u64((unsigned long long)n_decided);
     if (lane == 0 && n_decided && p.tier_counts) atomicAdd(p.tier_counts, (unsigned long long)n_decided);
 }
