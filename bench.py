@@ -228,7 +228,7 @@ def run_b200(args):
     barrier(td)
     t_e2e = max_over_ranks(td, t_e2e)
     h2d = p["counts"].nbytes + tau_host.nbytes + hs.gamma.nbytes + hs.eta.nbytes
-    d2h = (hs.gamma_store.nbytes + hs.eta_store.nbytes + 3 * 8 * K + 2 * tau_host.nbytes + hs._tau_sum.nbytes // 2 +
+    d2h = (hs.gamma_store.nbytes + hs.eta_store.nbytes + 3 * 8 * K + 2 * tau_host.nbytes + hs._tau_sum.nbytes +
            2 * (hs.gamma.nbytes + hs.eta.nbytes))
     e2e_value = (V_total / UNIT_V) * K / t_e2e
     hs.close()

@@ -184,8 +184,14 @@ class HaploSNP_Sampler():
         self.tauIndices = self._site_codes(self._tau_index())               # :228-231, vectorised
 
     def _site_codes(self, idx):
-        w = np.array([4 ** (self.G - g - 1) for g in range(self.G)], dtype=object if self.G > 31 else np.int64)
-        return idx.astype(w.dtype) @ w
+        if self.G > 31:
+            w = np.array([4 ** (self.G - g - 1) for g in range(self.G)], dtype=object)
+            return idx.astype(object) @ w
+        code = np.zeros(idx.shape[0], dtype=np.int64)                      # base-4 digits, strain 0 most significant
+        for g in range(self.G):
+            code <<= 2
+            code |= idx[:, g]
+        return code
 
     def tauDist(self, tau1, tau2):
         return int((np.argmax(tau1, axis=1) != np.argmax(tau2, axis=1)).sum())
@@ -267,7 +273,7 @@ class HaploSNP_Sampler():
         self.nchange_store = res["nchange"]
         if n_iter > 0:
             self.ll, self.lp = float(res["ll_store"][-1]), float(res["lp_store"][-1])
-        self._tau_sum = eng.get_tau_sum()
+        self._tau_sum = eng.get_tau_sum(compact=True)        # uint32 occupancy counters; tauMean() divides them
         self._timing = eng.get_timing()
         self.updateTauIndices()
         self.tauIndices_star = self._site_codes(self._tau_star_ix)

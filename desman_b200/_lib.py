@@ -49,6 +49,7 @@ SYMBOLS = {
     "desman_get_star": (C.c_int, [_ctx, _p64, _pd, _pd, _pd, C.POINTER(C.c_int)]),
     "desman_get_star_index": (C.c_int, [_ctx, _pu8]),
     "desman_get_tau_sum": (C.c_int, [_ctx, _p64]),
+    "desman_get_tau_sum_u32": (C.c_int, [_ctx, C.POINTER(C.c_uint32)]),
     "desman_nmft_factorize": (C.c_int, [_ctx, _p64, C.c_int64, C.c_int, C.c_int, _pd, _pd, C.c_int, C.c_double, C.c_int,
                                         C.POINTER(C.c_int), _pd, _pd]),
     "desman_set_option": (C.c_int, [_ctx, C.c_char_p, C.c_int64]),

@@ -336,6 +336,24 @@ extern "C" int desman_get_rng(desman_ctx *c, uint32_t *sweep, uint64_t *mt_words
 }
 
 // ------------------------------------------------------------------------------------------ data
+// host-side conversion loops run on a few threads (the arrays of the class surface are tens to hundreds of MB)
+static int host_threads(size_t n)
+{
+    if (n < ((size_t)1 << 16)) return 1;
+    unsigned int hc = std::thread::hardware_concurrency();
+    if (hc == 0) hc = 4;
+    return (int)(hc > 16 ? 16 : hc);
+}
+template <typename F>
+static void parallel_ranges(size_t n, F f)
+{
+    const int nt = host_threads(n);
+    if (nt == 1) { f((size_t)0, n); return; }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back(f, n * t / nt, n * (t + 1) / nt);
+    for (auto &x : th) x.join();
+}
+
 extern "C" int desman_set_counts(desman_ctx *c, const int64_t *variants, int64_t V, int S, int64_t v0, int64_t V_total)
 {
     if (!variants || V <= 0 || S <= 0) return fail(DESMAN_EINVAL, "desman_set_counts: need V > 0, S > 0 and a counts pointer");
@@ -372,7 +390,7 @@ extern "C" int desman_set_counts(desman_ctx *c, const int64_t *variants, int64_t
         CU(cudaEventSynchronize(c->pin_ev[buf]));                       // previous copy out of this buffer finished
         int4 *dst = g_pin[buf];
         const int64_t *src = variants + off * 4;
-        const int nt = (n >= ((size_t)1 << 16)) ? 8 : 1;
+        const int nt = host_threads(n);
         auto work = [&](int t) {
             const size_t lo = n * t / nt, hi = n * (t + 1) / nt;
             int64_t orv = 0, sum = 0, orc = 0;
@@ -471,12 +489,17 @@ static int ensure_state(desman_ctx *c, int G)
 // int64 one-hot [n,4] -> uint8 index; first b with tau == 1 (c_sample_tau.c:115-123); rows without a 1 are rejected
 static int onehot_to_index(const int64_t *tau, size_t n, uint8_t *idx)
 {
-    for (size_t i = 0; i < n; i++) {
-        const int64_t *t = tau + i * 4;
-        int b = t[0] == 1 ? 0 : t[1] == 1 ? 1 : t[2] == 1 ? 2 : t[3] == 1 ? 3 : -1;
-        if (b < 0) return fail(DESMAN_EINVAL, "tau row %zu is not one-hot (undefined behaviour in the reference, c_sample_tau.c:115-123)", i);
-        idx[i] = (uint8_t)b;
-    }
+    std::atomic<long long> bad(-1);
+    parallel_ranges(n, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+            const int64_t *t = tau + i * 4;
+            int b = t[0] == 1 ? 0 : t[1] == 1 ? 1 : t[2] == 1 ? 2 : t[3] == 1 ? 3 : -1;
+            if (b < 0) { bad = (long long)i; b = 0; }
+            idx[i] = (uint8_t)b;
+        }
+    });
+    if (bad >= 0)
+        return fail(DESMAN_EINVAL, "tau row %lld is not one-hot (undefined behaviour in the reference, c_sample_tau.c:115-123)", bad.load());
     return DESMAN_OK;
 }
 
@@ -527,11 +550,13 @@ extern "C" int desman_set_state(desman_ctx *c, const int64_t *tau, const double 
 
 static void index_to_onehot(const uint8_t *idx, size_t n, int64_t *tau)
 {
-    for (size_t i = 0; i < n; i++) {
-        int64_t *t = tau + i * 4;
-        t[0] = t[1] = t[2] = t[3] = 0;
-        t[idx[i] & 3] = 1;
-    }
+    parallel_ranges(n, [&](size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+            int64_t *t = tau + i * 4;
+            t[0] = t[1] = t[2] = t[3] = 0;
+            t[idx[i] & 3] = 1;
+        }
+    });
 }
 
 extern "C" int desman_get_state(desman_ctx *c, int64_t *tau, double *gamma, double *eta)
@@ -1239,7 +1264,15 @@ extern "C" int desman_get_tau_sum(desman_ctx *c, int64_t *tau_sum)
     std::vector<uint32_t> h(n);
     CU(cudaMemcpyAsync(h.data(), c->tau_cnt, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    for (size_t i = 0; i < n; i++) tau_sum[i] = (int64_t)h[i];
+    parallel_ranges(n, [&](size_t lo, size_t hi) { for (size_t i = lo; i < hi; i++) tau_sum[i] = (int64_t)h[i]; });
+    return DESMAN_OK;
+}
+
+extern "C" int desman_get_tau_sum_u32(desman_ctx *c, uint32_t *tau_sum)
+{
+    RET(require_state(c));
+    CU(cudaMemcpyAsync(tau_sum, c->tau_cnt, (size_t)c->V * c->G * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return DESMAN_OK;
 }
 

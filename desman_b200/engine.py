@@ -156,7 +156,12 @@ class Engine:
         check(self._L.desman_get_star_index(self._h, out.ctypes.data_as(_lib._pu8)), "desman_get_star_index")
         return out
 
-    def get_tau_sum(self):
+    def get_tau_sum(self, compact=False):
+        """tau_store.sum(axis=0) of the last update()/update_tau(); compact=True: the device's uint32 counters as they are."""
+        if compact:
+            out = np.empty((self.V, self.G, 4), dtype=np.uint32)
+            check(self._L.desman_get_tau_sum_u32(self._h, out.ctypes.data_as(C.POINTER(C.c_uint32))), "desman_get_tau_sum_u32")
+            return out
         out = np.empty((self.V, self.G, 4), dtype=np.int64)
         check(self._L.desman_get_tau_sum(self._h, _lib.ptr_i64(out)), "desman_get_tau_sum")
         return out

@@ -98,6 +98,7 @@ int desman_get_star_index(desman_ctx *ctx, uint8_t *tau_star_idx /*V*G*/);   /* 
 /* sum over the sweeps of the last update()/update_tau() of one-hot tau: tau_store.sum(axis=0)
  * (tauMean :479-483, probabilisticTau :834-840) */
 int desman_get_tau_sum(desman_ctx *ctx, int64_t *tau_sum /*V*G*4*/);
+int desman_get_tau_sum_u32(desman_ctx *ctx, uint32_t *tau_sum /*V*G*4*/);   /* same counters, as kept on the device */
 
 /* NMFT initialiser (Init_NMFT.py).  snps int64 [V,S,4]; tau [4V,G] (rows v + a*V) and gamma [G,S] hold
  * the random initial factors on entry and the result on exit.  fix_gamma = 0: factorize (:98-115);

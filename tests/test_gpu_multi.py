@@ -21,14 +21,23 @@ from desman_b200.parallel import exchange_unique_id, shard_bounds
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
 dist.init_process_group("nccl")
-p = synth_problem(4001, 64, 8, depth=30.0, seed=9, ambiguous=True)
+grouped = os.environ.get("DESMAN_CASE") == "grouped"
+if grouped:      # converged start, few flips: the screening pass of the tau update is active on every rank
+    from test_gpu_group import mild_problem
+    p = mild_problem(4001, 64, 8, 30.0, 9)
+    tau0, gamma0 = p["tau_true"], p["gamma_true"]
+else:
+    p = synth_problem(4001, 64, 8, depth=30.0, seed=9, ambiguous=True)
+    tau0, gamma0 = p["tau0"], p["gamma0"]
 lo, hi = shard_bounds(4001, rank, world)
 e = engine.Engine(rank, seed=4242)
 e.set_option("mu_mode", 0)   # per-read contract: statistics independent of how the sites are sharded
+e.set_option("tau_group", 1 if grouped else 0)
 e.set_counts(p["counts"][lo:hi], v0=lo, V_total=4001)
 e.comm_init(exchange_unique_id(dist, engine.Engine.comm_unique_id), rank, world)
-e.set_state(onehot(p["tau0"][lo:hi]), p["gamma0"], p["eta0"])
+e.set_state(onehot(tau0[lo:hi]), gamma0, p["eta0"])
 out = e.update(8)
+assert (e.get_timing()["kernel_launches"]["tau_group"] == 8) == grouped
 np.savez(os.path.join(os.environ["DESMAN_OUT"], "r%d.npz" % rank), tau=e.get_tau_index(), gamma=out["gamma_store"],
          eta=out["eta_store"], ll=out["ll_store"], nchange=out["nchange"], star=e.get_star()["iter"])
 e.close()
@@ -36,7 +45,8 @@ dist.destroy_process_group()
 '''
 
 
-def test_two_gpu_sharded_update_equals_one_gpu(tmp_path):
+@pytest.mark.parametrize("case", ["plain", "grouped"])
+def test_two_gpu_sharded_update_equals_one_gpu(tmp_path, case):
     from conftest import onehot, synth_problem
     from desman_b200 import _lib, engine
     if _lib.device_count() < 2:
@@ -44,16 +54,23 @@ def test_two_gpu_sharded_update_equals_one_gpu(tmp_path):
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     script = tmp_path / "w.py"
     script.write_text(SCRIPT)
-    env = dict(os.environ, DESMAN_ROOT=ROOT, DESMAN_OUT=str(tmp_path))
+    env = dict(os.environ, DESMAN_ROOT=ROOT, DESMAN_OUT=str(tmp_path), DESMAN_CASE=case)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", str(port), str(script)],
                        env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
-    p = synth_problem(4001, 64, 8, depth=30.0, seed=9, ambiguous=True)
+    if case == "grouped":
+        from test_gpu_group import mild_problem
+        p = mild_problem(4001, 64, 8, 30.0, 9)
+        tau0, gamma0 = p["tau_true"], p["gamma_true"]
+    else:
+        p = synth_problem(4001, 64, 8, depth=30.0, seed=9, ambiguous=True)
+        tau0, gamma0 = p["tau0"], p["gamma0"]
     e = engine.Engine(0, seed=4242)
     e.set_option("mu_mode", 0)
+    e.set_option("tau_group", 0)      # one GPU, per-site kernel only: the sharded grouped run must reproduce it
     e.set_counts(p["counts"])
-    e.set_state(onehot(p["tau0"]), p["gamma0"], p["eta0"])
+    e.set_state(onehot(tau0), gamma0, p["eta0"])
     one = e.update(8)
     tau1 = e.get_tau_index()
     e.close()
