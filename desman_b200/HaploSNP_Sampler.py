@@ -85,6 +85,9 @@ class HaploSNP_Sampler():
         self._comm = comm             # (uid, rank, nranks)
         self._eng = None
         self._eng_mode = None
+        self._counts_up = False
+        if comm is not None:          # a rank of a sharded chain: context and communicator are set up with the object;
+            self._context()           # counts and state still travel with the first driver call
 
     # ------------------------------------------------------------------ tau / tau_star: one-hot views built on demand
     # The engine keeps tau as uint8 base indices [V,G]; the reference's int64 one-hot [V,G,4] layout (32x larger) is
@@ -124,21 +127,29 @@ class HaploSNP_Sampler():
         return ix
 
     # ------------------------------------------------------------------ device plumbing
-    def _engine(self, mode=RNG_PHILOX):
+    def _context(self, mode=RNG_PHILOX):
+        """Device context (+ communicator of a sharded chain) without any data on it."""
         if self._eng is None or self._eng_mode != mode:
             sweep = _sampletau.global_sweep()
             if self._eng is not None:
                 sweep = self._eng.get_rng()[0]
                 self._eng.close()
             self._eng = Engine(self._device, self._seed, mode)
-            v0, vt = self._shard if self._shard is not None else (0, self.V)
-            self._eng.set_counts(self.variants, v0=v0, V_total=vt)
             if self._comm is not None:
                 self._eng.comm_init(*self._comm)
             self._eng.set_rng(self._seed, sweep=sweep)
             self._eng_mode = mode
-        self._eng.set_hyper(self.alpha_constant, self.delta_constant, self.epsilon)
+            self._counts_up = False
         return self._eng
+
+    def _engine(self, mode=RNG_PHILOX):
+        eng = self._context(mode)
+        if not self._counts_up:
+            v0, vt = self._shard if self._shard is not None else (0, self.V)
+            eng.set_counts(self.variants, v0=v0, V_total=vt)
+            self._counts_up = True
+        eng.set_hyper(self.alpha_constant, self.delta_constant, self.epsilon)
+        return eng
 
     def _push(self, eng, gamma=None, tau=None, eta=None):
         gamma = self.gamma if gamma is None else gamma

@@ -22,6 +22,7 @@
 #include "tau_kernel.cuh"
 #include "tau_group_kernel.cuh"
 #include "maintain_kernel.cuh"
+#include "exchange_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------ errors
 static thread_local char g_err[1024] = "";
@@ -64,13 +65,14 @@ struct NcclApi {
     int (*GetUniqueId)(nccl_uid_t *) = nullptr;
     int (*CommInitRank)(nccl_comm_t *, int, nccl_uid_t, int) = nullptr;
     int (*AllReduce)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
     int (*CommDestroy)(nccl_comm_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
 };
 static NcclApi g_nccl;
-enum { NCCL_INT64 = 4, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
+enum { NCCL_INT8 = 0, NCCL_INT64 = 4, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8, NCCL_SUM = 0 };
 
 static int nccl_load()
 {
@@ -84,6 +86,7 @@ static int nccl_load()
     g_nccl.GetUniqueId = (int (*)(nccl_uid_t *))dlsym(h, "ncclGetUniqueId");
     g_nccl.CommInitRank = (int (*)(nccl_comm_t *, int, nccl_uid_t, int))dlsym(h, "ncclCommInitRank");
     g_nccl.AllReduce = (int (*)(const void *, void *, size_t, int, int, nccl_comm_t, cudaStream_t))dlsym(h, "ncclAllReduce");
+    g_nccl.AllGather = (int (*)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t))dlsym(h, "ncclAllGather");
     g_nccl.CommDestroy = (int (*)(nccl_comm_t))dlsym(h, "ncclCommDestroy");
     g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
     g_nccl.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
@@ -163,6 +166,12 @@ struct desman_ctx {
     // comm
     nccl_comm_t comm = nullptr;
     int rank = 0, nranks = 1;
+    // peer-memory mailboxes of the one-shot exchange (exchange_kernel.cuh); xch_ok == false: NCCL all-reduce instead
+    bool xch_ok = false;
+    unsigned long long *xch_mail[XCH_MAX_RANKS] = {nullptr};
+    int xch_cap_words = 0;
+    unsigned long long xch_seq = 0;
+    int *xch_err = nullptr;
     // profiling
     int prof_kernels = 0, prof_flush = 0;
     uint4 *flush_buf = nullptr;
@@ -271,6 +280,11 @@ extern "C" int desman_ctx_destroy(desman_ctx *c)
     if (!c) return DESMAN_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    for (int r = 0; r < XCH_MAX_RANKS; r++) {
+        if (!c->xch_mail[r]) continue;
+        if (r == c->rank) cudaFree(c->xch_mail[r]); else cudaIpcCloseMemHandle(c->xch_mail[r]);
+    }
+    if (c->xch_err) cudaFree(c->xch_err);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     void *ptrs[] = {c->counts, c->tau, c->tau_star, c->gamma, c->eta, c->eta_new, c->gamma_star, c->eta_star, c->stats,
                     c->red_i, c->agg_ctl, c->scal, c->flag, c->tau_cnt, c->tau_last, c->mt_state, c->words,
@@ -898,11 +912,10 @@ static int launch_mu_agg(desman_ctx *c, const double *gamma, const double *eta)
         mu_binomial_kernel<<<grid, MUB_WARPS * 32, smem, c->stream>>>(p);
         if (p.classM) {
             const size_t smem2 = muc_smem_bytes(c->G);
-            CU(cudaFuncSetAttribute(mu_class_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-            long long want = (((long long)1 << c->G) * nch + MUB_WARPS - 1) / MUB_WARPS;
-            int grid2 = (int)(want < grid ? want : grid);
+            const int nch8 = (c->S + 7) / 8;
+            long long want = (((long long)1 << c->G) * nch8 + MUB_WARPS - 1) / MUB_WARPS;
+            int grid2 = (int)(want < (long long)c->sm_count * 4 ? want : (long long)c->sm_count * 4);
             if (grid2 < 1) grid2 = 1;
-            while ((grid2 * MUB_WARPS) % nch) grid2++;
             mu_class_kernel<<<grid2, MUB_WARPS * 32, smem2, c->stream>>>(p);
         }
     }
@@ -950,17 +963,31 @@ static int launch_mu(desman_ctx *c, const double *gamma, const double *eta)
     return DESMAN_OK;
 }
 
+static int exchange_sum(desman_ctx *c, unsigned long long *data, int words)
+{
+    XchParams p;
+    for (int r = 0; r < XCH_MAX_RANKS; r++) p.mail[r] = c->xch_mail[r];
+    p.rank = c->rank; p.nranks = c->nranks; p.words = words; p.cap_words = c->xch_cap_words;
+    p.seq = ++c->xch_seq; p.data = data; p.err = c->xch_err;
+    exchange_sum_kernel<<<1, 512, 0, c->stream>>>(p);
+    CU(cudaGetLastError());
+    return DESMAN_OK;
+}
+
 static int allreduce_stats(desman_ctx *c)
 {
     if (c->nranks <= 1) return DESMAN_OK;
     KSpan k(c, DESMAN_K_OTHER);
-    NC(g_nccl.AllReduce(c->stats, c->stats, (size_t)c->S * c->G + 16, NCCL_UINT64, NCCL_SUM, c->comm, c->stream));
+    const size_t n = (size_t)c->S * c->G + 16;
+    if (c->xch_ok && (int)n <= c->xch_cap_words) return exchange_sum(c, c->stats, (int)n);
+    NC(g_nccl.AllReduce(c->stats, c->stats, n, NCCL_UINT64, NCCL_SUM, c->comm, c->stream));
     return DESMAN_OK;
 }
 static int allreduce_red(desman_ctx *c)
 {
     if (c->nranks <= 1) return DESMAN_OK;
     KSpan k(c, DESMAN_K_OTHER);
+    if (c->xch_ok) return exchange_sum(c, c->red_i, 2);      // two's complement sums: same bits as the int64 all-reduce
     NC(g_nccl.AllReduce(c->red_i, c->red_i, 2, NCCL_INT64, NCCL_SUM, c->comm, c->stream));
     return DESMAN_OK;
 }
@@ -1132,6 +1159,12 @@ static int fetch_stores(desman_ctx *c, int n_iter, const StoreBufs &sb, double *
     if (eta_store && sb.es) CU(cudaMemcpyAsync(eta_store, sb.es, (size_t)n_iter * 16 * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (nchange_store) for (int i = 0; i < n_iter; i++) nchange_store[i] = (int64_t)llround(nch[i]);
+    if (c->xch_ok) {
+        int xe = 0;
+        CU(cudaMemcpyAsync(&xe, c->xch_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (xe) return fail(DESMAN_ECOMM, "peer-memory exchange timed out waiting for another rank");
+    }
     if (c->agg_ctl) {
         int ctl[3] = {0, 0, 0};
         CU(cudaMemcpyAsync(ctl, c->agg_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, c->stream));
@@ -1308,6 +1341,48 @@ extern "C" int desman_comm_init(desman_ctx *c, const char id[128], int rank, int
     memcpy(u.internal, id, 128);
     NC(g_nccl.CommInitRank(&c->comm, nranks, u, rank));
     c->rank = rank; c->nranks = nranks;
+    // peer-memory mailboxes for the per-sweep exchange; any failure here leaves the NCCL all-reduce in place
+    const char *env = getenv("DESMAN_B200_P2P");
+    if (env && !atoi(env)) return DESMAN_OK;
+    if (nranks > XCH_MAX_RANKS || !g_nccl.AllGather) return DESMAN_OK;
+    const int cap = 4096;                                             // words per contribution (S*G + 16 must fit)
+    const size_t words = (size_t)2 * nranks * cap + nranks;
+    unsigned long long *mine = nullptr;
+    if (cudaMalloc(&mine, words * sizeof(unsigned long long)) != cudaSuccess) { cudaGetLastError(); return DESMAN_OK; }
+    cudaMemsetAsync(mine, 0, words * sizeof(unsigned long long), c->stream);
+    cudaIpcMemHandle_t hmine;
+    if (cudaIpcGetMemHandle(&hmine, mine) != cudaSuccess) { cudaGetLastError(); cudaFree(mine); return DESMAN_OK; }
+    // all-gather the handles (bytes) through NCCL: every rank learns every mailbox
+    char *dh = nullptr;
+    CU(cudaMalloc(&dh, sizeof(cudaIpcMemHandle_t) * (size_t)(nranks + 1)));
+    CU(cudaMemcpyAsync(dh + sizeof(cudaIpcMemHandle_t) * (size_t)nranks, &hmine, sizeof(hmine), cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllGather(dh + sizeof(cudaIpcMemHandle_t) * (size_t)nranks, dh, sizeof(cudaIpcMemHandle_t), NCCL_INT8, c->comm, c->stream));
+    std::vector<cudaIpcMemHandle_t> all(nranks);
+    CU(cudaMemcpyAsync(all.data(), dh, sizeof(cudaIpcMemHandle_t) * (size_t)nranks, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(dh);
+    int ok = 1;
+    for (int r = 0; r < nranks; r++) {
+        if (r == rank) { c->xch_mail[r] = mine; continue; }
+        void *q = nullptr;
+        if (cudaIpcOpenMemHandle(&q, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+        c->xch_mail[r] = (unsigned long long *)q;
+    }
+    // every rank must take the same path: agree on success with a tiny all-reduce (min via sum of failures)
+    long long *dflag = nullptr;
+    CU(cudaMalloc(&dflag, sizeof(long long)));
+    long long bad = ok ? 0 : 1;
+    CU(cudaMemcpyAsync(dflag, &bad, sizeof(bad), cudaMemcpyHostToDevice, c->stream));
+    NC(g_nccl.AllReduce(dflag, dflag, 1, NCCL_INT64, NCCL_SUM, c->comm, c->stream));
+    CU(cudaMemcpyAsync(&bad, dflag, sizeof(bad), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(dflag);
+    if (bad == 0) {
+        CU(cudaMalloc(&c->xch_err, sizeof(int)));
+        CU(cudaMemsetAsync(c->xch_err, 0, sizeof(int), c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->xch_cap_words = cap; c->xch_seq = 0; c->xch_ok = true;
+    }
     return DESMAN_OK;
 }
 

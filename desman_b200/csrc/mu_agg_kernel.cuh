@@ -405,59 +405,74 @@ __global__ void __launch_bounds__(MUB_WARPS * 32, MUB_MIN_BLOCKS) mu_binomial_ke
     }
 }
 
-// Within-class split, merged over patterns (G <= MUC_MAX_G): one warp per (set of strains, 32-sample chunk); the M reads of the
-// set at sample s are dealt to its strains (ascending) by a chain of conditional binomials with weights gamma[s,g].
+// Within-class split, merged over patterns (G <= MUC_MAX_G).  The M reads of the set `mask` at sample s are dealt to its strains
+// by a balanced binary tree of binomial splits: node over the (ascending) strain positions [lo, hi), n = hi - lo >= 2, splits at
+// mid = lo + (n+1)/2:  X_left ~ Bin(M_node, L/(L+R), R/(L+R)),  L, R = sums of gamma[s,g] over the halves (ascending, rounded
+// adds).  The tree has depth <= 4 and the nodes of a level are independent, so a quad of lanes works on one sample and the latency
+// is that of <= 4 draws (a chain over the strains costs up to 15).  Stream: ctr = (mask, 0, sweep, STAGE_MUC<<28 | s), draw index
+// = heap number of the node - 1 (root 1, children 2i, 2i+1).  One warp per (mask, 8 samples); mirrors oracle_mu_stats_agg.
 __global__ void __launch_bounds__(MUB_WARPS * 32, MUB_MIN_BLOCKS) mu_class_kernel(MuAggParams p)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ long long nodeM_s[MUB_WARPS][8][32];          // reads at the nodes of the current item, per sample
+    __shared__ int pos2g_s[MUB_WARPS][32];
     const int S = p.S, G = p.G;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    double *wS = reinterpret_cast<double *>(smem_raw) + (size_t)wib * 32 * (3 * G + 1);       // [G][32]
-    double *sufS = wS + G * 32;                                                              // [G+1][32]
-    unsigned long long *accS = reinterpret_cast<unsigned long long *>(sufS + (G + 1) * 32);  // [G][32]
-    for (int i = lane; i < G * 32; i += 32) accS[i] = 0ull;
-    __syncwarp();
-    const int nch = (S + 31) >> 5;
-    const int gw = blockIdx.x * MUB_WARPS + wib, nw = gridDim.x * MUB_WARPS;      // nw % nch == 0 (host)
-    const int chunk = gw % nch, s = chunk * 32 + lane;
-    const bool valid = s < S;
-    if (valid) for (int g = 0; g < G; g++) wS[g * 32 + lane] = p.gamma[(size_t)s * G + g];
+    long long (*nodeM)[32] = nodeM_s[wib];
+    int *pos2g = pos2g_s[wib];
+    const int gw = blockIdx.x * MUB_WARPS + wib, nw = gridDim.x * MUB_WARPS;
+    const int sl = lane >> 2, q4 = lane & 3;                 // sample within the chunk, lane within the quad
+    const int nch = (S + 7) >> 3;
     BinStream st;
     st.c1 = 0u; st.c2 = p.sweep; st.k0 = (uint32_t)p.seed; st.k1 = (uint32_t)(p.seed >> 32) ^ p.shard;
-    st.c3 = ((uint32_t)STAGE_MUC << 28) | (uint32_t)s;
-    const uint32_t nmask = 1u << G;
-    for (uint32_t mask = 3u + (uint32_t)(gw / nch); mask < nmask; mask += (uint32_t)(nw / nch)) {
-        if ((mask & (mask - 1u)) == 0u) continue;              // one strain: settled in phase A
+    const long long nitems = ((long long)1 << G) * nch;
+    for (long long item = gw; item < nitems; item += nw) {
+        const uint32_t mask = (uint32_t)(item / nch);
+        if ((mask & (mask - 1u)) == 0u) continue;              // empty or one strain: settled in phase A
+        const int s = (int)(item % nch) * 8 + sl;
+        const bool valid = s < S;
         long long M = 0;
-        if (valid) M = (long long)p.classM[(size_t)mask * S + s];
-        if (M <= 0) continue;
-        p.classM[(size_t)mask * S + s] = 0ull;                  // consumed
+        if (valid && q4 == 0) {
+            M = (long long)p.classM[(size_t)mask * S + s];
+            if (M > 0) p.classM[(size_t)mask * S + s] = 0ull;   // consumed
+        }
+        if (!__any_sync(DESMAN_FULL_MASK, M > 0)) continue;
+        const int m = __popc(mask);
+        __syncwarp();
+        if (lane < m) pos2g[lane] = (int)__fns(mask, 0, lane + 1);
+        if (q4 == 0) nodeM[sl][1] = M;
+        __syncwarp();
         st.c0 = mask;
-        const int gl = 31 - __clz(mask);
-        double suf = 0.0;
-        for (int g = gl; g >= 0; g--)
-            if ((mask >> g) & 1u) { suf = __dadd_rn(wS[g * 32 + lane], suf); sufS[g * 32 + lane] = suf; }
-        long long rem = M;
-        double sg = suf;
-        for (int g = 0; g <= gl; g++) {
-            if (!((mask >> g) & 1u)) continue;
-            long long x;
-            if (g == gl) x = rem;
-            else {
-                const uint32_t higher = mask & ~((2u << g) - 1u);
-                const double sn = sufS[(__ffs(higher) - 1) * 32 + lane];
-                x = (rem == 0) ? 0 : binomial_draw_d(rem, __ddiv_rn(wS[g * 32 + lane], sg), __ddiv_rn(sn, sg), st, g);
-                sg = sn;
+        st.c3 = ((uint32_t)STAGE_MUC << 28) | (uint32_t)s;
+        int depth = 0;
+        while ((1 << depth) < m) depth++;
+        for (int level = 0; level < depth; level++) {
+            for (int id = (1 << level) + q4; id < (2 << level); id += 4) {
+                // range of node `id`: descend from the root along the bits below the leading one
+                int lo = 0, hi = m;
+                for (int b = level - 1; b >= 0; b--) {
+                    const int mid = lo + (hi - lo + 1) / 2;
+                    if ((id >> b) & 1) lo = mid; else hi = mid;
+                }
+                const int n = hi - lo;
+                if (n < 2 || !valid) continue;                  // (a range of one strain was credited by its parent)
+                const long long Mn = nodeM[sl][id];
+                const int mid = lo + (n + 1) / 2;
+                long long xl = 0;
+                if (Mn > 0) {
+                    double L = 0.0, R = 0.0;
+                    for (int i = lo; i < mid; i++) L = __dadd_rn(L, p.gamma[(size_t)s * G + pos2g[i]]);
+                    for (int i = mid; i < hi; i++) R = __dadd_rn(R, p.gamma[(size_t)s * G + pos2g[i]]);
+                    const double T = __dadd_rn(L, R);
+                    xl = binomial_draw_d(Mn, __ddiv_rn(L, T), __ddiv_rn(R, T), st, id - 1);
+                }
+                const long long xr = Mn - xl;
+                if (mid - lo >= 2) nodeM[sl][2 * id] = xl;
+                else if (xl) atomicAdd(p.sum_mu + (size_t)s * G + pos2g[lo], (unsigned long long)xl);
+                if (hi - mid >= 2) nodeM[sl][2 * id + 1] = xr;
+                else if (xr) atomicAdd(p.sum_mu + (size_t)s * G + pos2g[mid], (unsigned long long)xr);
             }
-            rem -= x;
-            if (x) accS[g * 32 + lane] += (unsigned long long)x;
+            __syncwarp();
         }
     }
-    __syncwarp();
-    if (valid)
-        for (int g = 0; g < G; g++) {
-            const unsigned long long x = accS[g * 32 + lane];
-            if (x) atomicAdd(p.sum_mu + (size_t)s * G + g, x);
-        }
 }
-static inline size_t muc_smem_bytes(int G) { return (size_t)MUB_WARPS * 32 * 8 * (size_t)(3 * G + 1); }
+static inline size_t muc_smem_bytes(int G) { (void)G; return 0; }

@@ -532,19 +532,22 @@ void oracle_mu_stats_agg(const int64_t *tau, const double *gamma, const double *
         free(lmu);
     }
     if (classM) {
-        /* merged within-class split: set of strains `mask`, sample s, M reads; strains ascending, weights gamma[s,g];
-         * stream ctr = (mask, 0, sweep, STAGE_MUC<<28 | s), draw index g */
+        /* merged within-class split: set of strains `mask`, sample s, M reads, dealt by a balanced binary tree of binomial
+         * splits over the ascending strain positions [lo, hi): mid = lo + (n+1)/2, X_left ~ Bin(M_node, L/(L+R), R/(L+R)),
+         * L, R = sums of gamma[s,g] over the halves (ascending, rounded adds); stream ctr = (mask, 0, sweep, STAGE_MUC<<28 | s),
+         * draw index = heap number of the node - 1 (root 1, children 2i, 2i+1) */
         const uint32_t nmask = 1u << G;
 #pragma omp parallel
         {
             int64_t *lmu = (int64_t *)calloc((size_t)S * G, sizeof(int64_t));
-            double sufg[65];
 #pragma omp for schedule(dynamic, 16)
             for (int64_t mk = 3; mk < (int64_t)nmask; mk++) {
                 const uint32_t mask = (uint32_t)mk;
                 if ((mask & (mask - 1u)) == 0u) continue;
-                int gl = 0;
-                for (int g = 0; g < G; g++) if ((mask >> g) & 1u) gl = g;
+                int pos2g[32], m = 0;
+                for (int g = 0; g < G; g++) if ((mask >> g) & 1u) pos2g[m++] = g;
+                int depth = 0;
+                while ((1 << depth) < m) depth++;
                 for (int s = 0; s < S; s++) {
                     const int64_t M = classM[(size_t)mask * S + s];
                     if (M <= 0) continue;
@@ -552,25 +555,32 @@ void oracle_mu_stats_agg(const int64_t *tau, const double *gamma, const double *
                     st.c0 = mask; st.c1 = 0u; st.c2 = sweep;
                     st.c3 = ((uint32_t)ORACLE_STAGE_MUC << 28) | (uint32_t)s;
                     st.seed = seed; st.shard = (uint32_t)v0;
-                    double suf = 0.0;
-                    for (int g = gl; g >= 0; g--) if ((mask >> g) & 1u) { suf = gamma[s * G + g] + suf; sufg[g] = suf; }
-                    int64_t rem = M;
-                    double sg = suf;
-                    for (int g = 0; g <= gl; g++) {
-                        if (!((mask >> g) & 1u)) continue;
-                        int64_t x;
-                        if (g == gl) x = rem;
-                        else {
-                            int gn = g + 1;
-                            while (!((mask >> gn) & 1u)) gn++;
-                            const double sn = sufg[gn];
-                            st.g = g;
-                            x = (rem == 0) ? 0 : binomial_draw(rem, gamma[s * G + g] / sg, sn / sg, &st);
-                            sg = sn;
+                    int64_t nodeM[64];
+                    nodeM[1] = M;
+                    for (int level = 0; level < depth; level++)
+                        for (int id = 1 << level; id < (2 << level); id++) {
+                            int lo = 0, hi = m;
+                            for (int b = level - 1; b >= 0; b--) {
+                                const int mid = lo + (hi - lo + 1) / 2;
+                                if ((id >> b) & 1) lo = mid; else hi = mid;
+                            }
+                            const int n = hi - lo;
+                            if (n < 2) continue;
+                            const int64_t Mn = nodeM[id];
+                            const int mid = lo + (n + 1) / 2;
+                            int64_t xl = 0;
+                            if (Mn > 0) {
+                                double L = 0.0, R = 0.0;
+                                for (int i = lo; i < mid; i++) L = L + gamma[s * G + pos2g[i]];
+                                for (int i = mid; i < hi; i++) R = R + gamma[s * G + pos2g[i]];
+                                const double T = L + R;
+                                st.g = id - 1;
+                                xl = binomial_draw(Mn, L / T, R / T, &st);
+                            }
+                            const int64_t xr = Mn - xl;
+                            if (mid - lo >= 2) nodeM[2 * id] = xl; else lmu[s * G + pos2g[lo]] += xl;
+                            if (hi - mid >= 2) nodeM[2 * id + 1] = xr; else lmu[s * G + pos2g[mid]] += xr;
                         }
-                        rem -= x;
-                        lmu[s * G + g] += x;
-                    }
                 }
             }
 #pragma omp critical
