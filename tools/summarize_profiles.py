@@ -82,7 +82,12 @@ if __name__ == "__main__":
     g = os.path.join(ROOT, "gpurun_out")
     tot, total = launches(os.path.join(g, "launches_%s.csv" % tag), tag)
     d = details(os.path.join(g, "prof_%s_final.ncu-rep" % tag), tag)
-    traffic = {k.replace("_kernel", "").replace("<8>", ""): v["dram_bytes"] for k, v in d.items()}
+    traffic = {k.replace("_kernel", "").replace("<8>", "").replace("<2>", ""): v["dram_bytes"] for k, v in d.items()}
+    # the steps bench.py reports: tau update = screening pass + per-site kernel; mu/E statistics = class split + within-class split
+    if "tau_group_mma" in traffic:
+        traffic["tau_update"] = traffic["tau_group_mma"] + traffic.get("tau_sample", 0.0)
+    if "mu_binomial" in traffic:
+        traffic["mu_stats"] = traffic["mu_binomial"] + traffic.get("mu_class", 0.0)
     json.dump({"source": "ncu --set full --clock-control none, bench.py config c3 (V=100000 S=64 G=8), one launch each",
                "dram_bytes_per_launch": traffic}, open(os.path.join(OUT, "traffic.json"), "w"), indent=1)
     print(open(os.path.join(OUT, "%s_launch_list_summary.csv" % tag)).read())
