@@ -52,7 +52,8 @@ struct TauParams {
 
 #define TAU_WARPS 8
 #define TAU_GAP 60.0f            // nats; exp(-60) = 8.8e-27, 3*exp(-60) << 2^-32
-#define TAU_SLACK 1.0e-9         // absolute slack on CDF brackets (covers all FP64 rounding)
+#define TAU_SLACK 1.0e-9         // absolute slack on CDF brackets evaluated in FP64
+#define TAU_SLACK32 1.0e-4       // ... and in FP32 fast math (tau_bracket_decide)
 
 // ---------------------------------------------------------------------------------------------
 // Reference arithmetic (c_sample_tau.c:136-170) in FP64 for ONE (v,g): base over h ascending skipping
@@ -196,33 +197,43 @@ __device__ __noinline__ int tau_bracket_decide(const int4 *tile, const double2 *
     float eb = nlane * (TAU_C0 + c1 * (mq + mlP) + ccan * exp2f(fminf(mq + mlP, 120.f)));
     warp_sum4(D0, D1, D2, eb, lane);
     const float Bn = eb * LN2 * 1.0001f + 1e-6f;
-    if (!(Bn < 1.0e30f)) return -1;
-    const double x0 = (double)(D0 * LN2), x1 = (double)(D1 * LN2), x2 = (double)(D2 * LN2);
-    const double B = (double)Bn;
-    double eh[4], el[4];
+    if (!((fabsf(D0) + fabsf(D1) + fabsf(D2) + Bn) < 1.0e30f)) return -1;
+    // The brackets themselves are evaluated in FP32 (ex2.approx, fast division): every bracket end carries a relative error
+    // below 1e-5 (argument rounding |x| 2^-24 log2e for |x| <= 100, ex2.approx 2^-22, three adds, one division), absorbed
+    // by the absolute slack TAU_SLACK32 = 1e-4 on the CDF.  u inside a widened bracket (probability ~2e-4 per test) goes to
+    // tier 3 like any other undecided draw.
+    // the exponents are differenced in FP64 first (|D| can be 1e5 nats, where a float ulp is 8e-3), then exponentiated in FP32
+    const double x0 = (double)(D0 * LN2), x1 = (double)(D1 * LN2), x2 = (double)(D2 * LN2), B = (double)Bn;
+    double dh[4], dl[4];
     double M = -1.0e300;
     // a_j = (cur+1+j)&3  <=>  j = (a-cur-1)&3 ; j == 3 is cur itself (exactly 0, no error)
-#pragma unroll 1
+#pragma unroll
     for (int a = 0; a < 4; a++) {
         const int j = (a - cur - 1) & 3;
         const double d = (j == 0) ? x0 : (j == 1) ? x1 : (j == 2) ? x2 : 0.0;
         const double bb = (j == 3) ? 0.0 : B;
-        eh[a] = d + bb; el[a] = d - bb;
-        M = fmax(M, eh[a]);
+        dh[a] = d + bb; dl[a] = d - bb;
+        M = fmax(M, dh[a]);
     }
-#pragma unroll 1
-    for (int a = 0; a < 4; a++) { eh[a] = exp(eh[a] - M); el[a] = exp(el[a] - M); }
+    float eh[4], el[4];
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+        // FP32 range: terms below e^-80 of the largest are rounded in the SAFE direction -- the upper ends up (to e^-80), the
+        // lower ends down (to 0) -- which can only widen a bracket (cplus = ah/(ah+rl) grows, cminus = al/(al+rh) shrinks)
+        eh[a] = __expf((float)fmax(dh[a] - M, -80.0));
+        el[a] = (dl[a] - M < -80.0) ? 0.0f : __expf((float)(dl[a] - M));
+    }
     int below = 0, above = 0;     // number of boundaries certainly > u / certainly <= u
-    double ah = 0.0, al = 0.0;
+    float ah = 0.0f, al = 0.0f;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         ah += eh[k]; al += el[k];
-        double rh = 0.0, rl = 0.0;
+        float rh = 0.0f, rl = 0.0f;
 #pragma unroll
         for (int a = k + 1; a < 4; a++) { rh += eh[a]; rl += el[a]; }
-        const double cplus = ah / (ah + rl), cminus = al / (al + rh);
-        if (u < cminus - TAU_SLACK) below++;
-        else if (u >= cplus + TAU_SLACK) above++;
+        const float cplus = __fdividef(ah, ah + rl), cminus = __fdividef(al, al + rh);
+        if (u < (double)cminus - TAU_SLACK32) below++;
+        else if (u >= (double)cplus + TAU_SLACK32) above++;
     }
     return (below + above == 3) ? above : -1;    // boundaries are ordered: t = #boundaries <= u
 }
@@ -335,7 +346,14 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
             // MT19937 mode: gsl_rng_uniform, c_sample_tau.c:174 (u = 0 possible).  Philox mode: mid-point of the word's cell.
             const double u = p.words ? (double)w / 4294967296.0 : ((double)w + 0.5) / 4294967296.0;
             int t = -1;
-            if (fast_ok && (w != 0u || !p.words)) {
+            const bool usable = fast_ok && (w != 0u || !p.words);
+            if (usable && listed && code == code_in) {
+                // a step the screening pass left open: its gap test already failed on the same kind of sums, so go straight
+                // to the tracked sums and the brackets (which also settle a decisive flip)
+                t = tau_bracket_decide(tile, Pw, Kw, gT + g * Sp, gT32 + g * Sp, eta_s + 4 * cur, eta32, cur, nch, lane, nlane, mlP,
+                                       c1, ccan, u);
+                if (t >= 0) n2++;
+            } else if (usable) {
                 // ---- tier 1: D_j = (E_j - KK)*ln2 = L(a_j) - L(cur), j = 0..2, with the a-priori bounds from qmin
                 const double *eta_cur = eta_s + 4 * cur;
                 float E0, E1, E2, KK, mq;
