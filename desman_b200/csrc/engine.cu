@@ -185,12 +185,25 @@ struct desman_ctx {
     int64_t k_launch[DESMAN_K_COUNT] = {0};
 };
 
+// Device buffers come from the device's stream-ordered pool (cudaMallocAsync) with the release threshold lifted, so the large
+// buffers of a closed context are handed to the next one without a trip to the driver (an engine is created per
+// HaploSNP_Sampler object: tens of ms of cudaMalloc/cudaFree otherwise).  The IPC mailboxes keep cudaMalloc (IPC needs it).
+template <typename T>
+static cudaError_t dmalloc(desman_ctx *c, T **p, size_t bytes)
+{
+    return cudaMallocAsync((void **)p, bytes ? bytes : 1, c->stream);
+}
+static void dfree(desman_ctx *c, void *p)
+{
+    if (p) cudaFreeAsync(p, c->stream);
+}
+
 static int ensure_scratch(desman_ctx *c, size_t bytes)
 {
     if (bytes <= c->scratch_cap) return DESMAN_OK;
-    if (c->scratch) cudaFree(c->scratch);
+    if (c->scratch) dfree(c, c->scratch);
     c->scratch = nullptr; c->scratch_cap = 0;
-    CU(cudaMalloc(&c->scratch, bytes));
+    CU(dmalloc(c, &c->scratch, bytes));
     c->scratch_cap = bytes;
     return DESMAN_OK;
 }
@@ -254,22 +267,27 @@ extern "C" int desman_ctx_create(desman_ctx **out, int device, uint64_t seed, in
     desman_ctx *c = new desman_ctx();
     c->device = device;
     c->rng_mode = rng_mode;
-    cudaDeviceProp prop;
-    CU(cudaGetDeviceProperties(&prop, device));
-    c->sm_count = prop.multiProcessorCount;
+    CU(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device));
+    {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            unsigned long long thr = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+        } else cudaGetLastError();
+    }
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
-    CU(cudaMalloc(&c->eta, 16 * sizeof(double)));
-    CU(cudaMalloc(&c->eta_new, 16 * sizeof(double)));
-    CU(cudaMalloc(&c->eta_star, 16 * sizeof(double)));
-    CU(cudaMalloc(&c->red_i, 2 * sizeof(unsigned long long)));
-    CU(cudaMalloc(&c->scal, 4 * sizeof(double)));
-    CU(cudaMalloc(&c->flag, sizeof(int)));
-    CU(cudaMalloc(&c->tiers, 3 * sizeof(unsigned long long)));
+    CU(dmalloc(c, &c->eta, 16 * sizeof(double)));
+    CU(dmalloc(c, &c->eta_new, 16 * sizeof(double)));
+    CU(dmalloc(c, &c->eta_star, 16 * sizeof(double)));
+    CU(dmalloc(c, &c->red_i, 2 * sizeof(unsigned long long)));
+    CU(dmalloc(c, &c->scal, 4 * sizeof(double)));
+    CU(dmalloc(c, &c->flag, sizeof(int)));
+    CU(dmalloc(c, &c->tiers, 3 * sizeof(unsigned long long)));
     CU(cudaMemset(c->tiers, 0, 3 * sizeof(unsigned long long)));
     { const char *ex = getenv("DESMAN_B200_TAU_EXACT"); c->tau_exact = (ex && atoi(ex)) ? 1 : 0; }
     { const char *tg = getenv("DESMAN_B200_TAU_GROUP"); if (tg) c->tau_group = atoi(tg); if (c->tau_group < 0 || c->tau_group > 2) c->tau_group = 2; }
     { const char *mm = getenv("DESMAN_B200_MU_MODE"); if (mm) c->mu_mode = atoi(mm); if (c->mu_mode < 0 || c->mu_mode > 2) c->mu_mode = 2; }
-    CU(cudaMalloc(&c->mt_state, 624 * sizeof(uint32_t)));
+    CU(dmalloc(c, &c->mt_state, 624 * sizeof(uint32_t)));
     CU(cudaMemset(c->scal, 0, 4 * sizeof(double)));
     *out = c;
     return desman_set_rng(c, seed, 0, 0);
@@ -291,7 +309,7 @@ extern "C" int desman_ctx_destroy(desman_ctx *c)
                     c->scratch, c->flush_buf, c->tiers, c->agg_keys, c->agg_code, c->agg_N, c->agg_ids, c->agg_nslots, c->agg_classM,
                     c->countsf, c->nsite, c->grp_site_slot, c->grp_order, c->grp_singles, c->grp_slot4, c->grp_gctl, c->grp_blk,
                     c->grp_items, c->grp_work};
-    for (void *p : ptrs) if (p) cudaFree(p);
+    for (void *p : ptrs) if (p) dfree(c, p);
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) if (c->pin_ev[i]) cudaEventDestroy(c->pin_ev[i]);
     cudaStreamDestroy(c->stream);
@@ -377,9 +395,9 @@ extern "C" int desman_set_counts(desman_ctx *c, const int64_t *variants, int64_t
     CU(cudaSetDevice(c->device));
     const size_t ncell = (size_t)V * S;
     if (ncell > c->counts_cap) {
-        if (c->counts) cudaFree(c->counts);
+        if (c->counts) dfree(c, c->counts);
         c->counts = nullptr; c->counts_cap = 0;
-        CU(cudaMalloc(&c->counts, ncell * sizeof(int4)));
+        CU(dmalloc(c, &c->counts, ncell * sizeof(int4)));
         c->counts_cap = ncell;
     }
     // Repack int64 -> int32x4 on the host with a few threads straight into pinned staging buffers and stream the
@@ -445,25 +463,25 @@ static int ensure_ll_const(desman_ctx *c)
     if (c->ll_const_valid) return DESMAN_OK;
     const int nb = c->sm_count * 4;
     double *dpart = nullptr;
-    CU(cudaMalloc(&dpart, nb * sizeof(double)));
+    CU(dmalloc(c, &dpart, nb * sizeof(double)));
     lgamma_const_kernel<<<nb, 256, 0, c->stream>>>(c->counts, (size_t)c->V * c->S, dpart);
     CU(cudaGetLastError());
     std::vector<double> part(nb);
     CU(cudaMemcpyAsync(part.data(), dpart, nb * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    cudaFree(dpart);
+    dfree(c, dpart);
     double t = 0.0;
     for (double x : part) t += x;
     c->ll_const = t;
     c->ll_const_total = t;
     if (c->nranks > 1) {   // one-time sum over the shards
         double *d = nullptr;
-        CU(cudaMalloc(&d, sizeof(double)));
+        CU(dmalloc(c, &d, sizeof(double)));
         CU(cudaMemcpyAsync(d, &t, sizeof(double), cudaMemcpyHostToDevice, c->stream));
         NC(g_nccl.AllReduce(d, d, 1, NCCL_FLOAT64, NCCL_SUM, c->comm, c->stream));
         CU(cudaMemcpyAsync(&c->ll_const_total, d, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
-        cudaFree(d);
+        dfree(c, d);
     }
     c->ll_const_valid = true;
     return DESMAN_OK;
@@ -475,20 +493,20 @@ static int ensure_state(desman_ctx *c, int G)
     if (G < 1 || G > DESMAN_MAX_G) return fail(DESMAN_EINVAL, "G must be in [1, %d]", DESMAN_MAX_G);
     const size_t nvg = (size_t)c->V * G, nsg = (size_t)c->S * G;
     if (nvg > c->cap_vg) {
-        for (void *p : {(void *)c->tau, (void *)c->tau_star, (void *)c->tau_cnt, (void *)c->tau_last}) if (p) cudaFree(p);
+        for (void *p : {(void *)c->tau, (void *)c->tau_star, (void *)c->tau_cnt, (void *)c->tau_last}) if (p) dfree(c, p);
         c->tau = c->tau_star = nullptr; c->tau_cnt = c->tau_last = nullptr; c->cap_vg = 0;
-        CU(cudaMalloc(&c->tau, nvg));
-        CU(cudaMalloc(&c->tau_star, nvg));
-        CU(cudaMalloc(&c->tau_cnt, nvg * 4 * sizeof(uint32_t)));
-        CU(cudaMalloc(&c->tau_last, nvg * sizeof(uint32_t)));
+        CU(dmalloc(c, &c->tau, nvg));
+        CU(dmalloc(c, &c->tau_star, nvg));
+        CU(dmalloc(c, &c->tau_cnt, nvg * 4 * sizeof(uint32_t)));
+        CU(dmalloc(c, &c->tau_last, nvg * sizeof(uint32_t)));
         c->cap_vg = nvg;
     }
     if (nsg > c->cap_sg) {
-        for (void *p : {(void *)c->gamma, (void *)c->gamma_star, (void *)c->stats}) if (p) cudaFree(p);
+        for (void *p : {(void *)c->gamma, (void *)c->gamma_star, (void *)c->stats}) if (p) dfree(c, p);
         c->gamma = c->gamma_star = nullptr; c->stats = nullptr; c->cap_sg = 0;
-        CU(cudaMalloc(&c->gamma, nsg * sizeof(double)));
-        CU(cudaMalloc(&c->gamma_star, nsg * sizeof(double)));
-        CU(cudaMalloc(&c->stats, (nsg + 16) * sizeof(unsigned long long)));
+        CU(dmalloc(c, &c->gamma, nsg * sizeof(double)));
+        CU(dmalloc(c, &c->gamma_star, nsg * sizeof(double)));
+        CU(dmalloc(c, &c->stats, (nsg + 16) * sizeof(unsigned long long)));
         c->cap_sg = nsg;
     }
     if (G != c->G) {
@@ -609,53 +627,53 @@ static int ensure_agg(desman_ctx *c)
 {
     const size_t V = (size_t)c->V, slots = V * 5 / 2 + 64, cells = slots * c->S * 4;
     if (slots > c->agg_cap_slots || cells > c->agg_cap_cells) {
-        for (void *q : {(void *)c->agg_keys, (void *)c->agg_code, (void *)c->agg_N, (void *)c->agg_ids, (void *)c->agg_nslots}) if (q) cudaFree(q);
+        for (void *q : {(void *)c->agg_keys, (void *)c->agg_code, (void *)c->agg_N, (void *)c->agg_ids, (void *)c->agg_nslots}) if (q) dfree(c, q);
         c->agg_keys = c->agg_code = c->agg_N = nullptr; c->agg_ids = nullptr; c->agg_nslots = nullptr;
         c->agg_cap_slots = c->agg_cap_cells = 0;
         size_t H = 64;
         while (H < 4 * slots / 3) H <<= 1;
-        CU(cudaMalloc(&c->agg_keys, H * sizeof(unsigned long long)));
-        CU(cudaMalloc(&c->agg_ids, H * sizeof(int)));
-        CU(cudaMalloc(&c->agg_code, slots * sizeof(unsigned long long)));
-        CU(cudaMalloc(&c->agg_nslots, sizeof(unsigned int)));
-        CU(cudaMalloc(&c->agg_N, cells * sizeof(unsigned long long)));
+        CU(dmalloc(c, &c->agg_keys, H * sizeof(unsigned long long)));
+        CU(dmalloc(c, &c->agg_ids, H * sizeof(int)));
+        CU(dmalloc(c, &c->agg_code, slots * sizeof(unsigned long long)));
+        CU(dmalloc(c, &c->agg_nslots, sizeof(unsigned int)));
+        CU(dmalloc(c, &c->agg_N, cells * sizeof(unsigned long long)));
         CU(cudaMemsetAsync(c->agg_N, 0, cells * sizeof(unsigned long long), c->stream));
         CU(cudaMemsetAsync(c->agg_nslots, 0, sizeof(unsigned int), c->stream));
         c->agg_H = H; c->agg_cap_slots = slots; c->agg_cap_cells = cells;
         c->agg_valid = false;
     }
     if (!c->agg_ctl) {
-        CU(cudaMalloc(&c->agg_ctl, AGG_CTL_WORDS * sizeof(int)));
+        CU(dmalloc(c, &c->agg_ctl, AGG_CTL_WORDS * sizeof(int)));
         CU(cudaMemsetAsync(c->agg_ctl, 0, AGG_CTL_WORDS * sizeof(int), c->stream));
     }
     // merged class totals of the statistics kernels: dense over the sets of strains
     if (c->G <= MUC_MAX_G && (c->G != c->classM_G || c->S != c->classM_S)) {
-        if (c->agg_classM) cudaFree(c->agg_classM);
+        if (c->agg_classM) dfree(c, c->agg_classM);
         c->agg_classM = nullptr; c->classM_G = c->classM_S = 0;
         const size_t n = ((size_t)1 << c->G) * c->S;
-        CU(cudaMalloc(&c->agg_classM, n * sizeof(unsigned long long)));
+        CU(dmalloc(c, &c->agg_classM, n * sizeof(unsigned long long)));
         CU(cudaMemsetAsync(c->agg_classM, 0, n * sizeof(unsigned long long), c->stream));
         c->classM_G = c->G; c->classM_S = c->S;
     }
     // site groups of the screening pass
     if (V > c->grp_cap_v || c->agg_cap_slots > c->grp_cap_slots) {
         for (void *q : {(void *)c->grp_site_slot, (void *)c->grp_order, (void *)c->grp_singles, (void *)c->grp_slot4,
-                        (void *)c->grp_items, (void *)c->grp_work}) if (q) cudaFree(q);
+                        (void *)c->grp_items, (void *)c->grp_work}) if (q) dfree(c, q);
         c->grp_site_slot = c->grp_order = c->grp_singles = c->grp_slot4 = nullptr; c->grp_items = nullptr; c->grp_work = nullptr;
         c->grp_cap_v = c->grp_cap_slots = 0;
-        CU(cudaMalloc(&c->grp_site_slot, V * sizeof(int)));
-        CU(cudaMalloc(&c->grp_order, V * sizeof(int)));
-        CU(cudaMalloc(&c->grp_singles, V * sizeof(int)));
-        CU(cudaMalloc(&c->grp_slot4, 4 * c->agg_cap_slots * sizeof(int)));
-        CU(cudaMalloc(&c->grp_items, 2 * (V / 2 + V / TG_ITEM_SITES + 64) * sizeof(int4)));
-        CU(cudaMalloc(&c->grp_work, V * sizeof(uint2)));
+        CU(dmalloc(c, &c->grp_site_slot, V * sizeof(int)));
+        CU(dmalloc(c, &c->grp_order, V * sizeof(int)));
+        CU(dmalloc(c, &c->grp_singles, V * sizeof(int)));
+        CU(dmalloc(c, &c->grp_slot4, 4 * c->agg_cap_slots * sizeof(int)));
+        CU(dmalloc(c, &c->grp_items, 2 * (V / 2 + V / TG_ITEM_SITES + 64) * sizeof(int4)));
+        CU(dmalloc(c, &c->grp_work, V * sizeof(uint2)));
         c->grp_cap_v = V; c->grp_cap_slots = c->agg_cap_slots;
         c->agg_valid = false;
     }
     if (!c->grp_gctl) {
-        CU(cudaMalloc(&c->grp_gctl, GC_COUNT * sizeof(int)));
+        CU(dmalloc(c, &c->grp_gctl, GC_COUNT * sizeof(int)));
         CU(cudaMemsetAsync(c->grp_gctl, 0, GC_COUNT * sizeof(int), c->stream));
-        CU(cudaMalloc(&c->grp_blk, 4 * 2048 * sizeof(int)));
+        CU(dmalloc(c, &c->grp_blk, 4 * 2048 * sizeof(int)));
     }
     // fixed-point scale of the log-likelihood accumulator: |sum n log p| <= reads * 88 must stay below 2^62
     const double reads = (c->total_reads > 1.0 ? c->total_reads : 1.0) * ((double)c->V_total / (double)c->V);
@@ -728,11 +746,11 @@ static int ensure_countsf(desman_ctx *c)
 {
     const size_t ncell = (size_t)c->V * c->S;
     if (ncell > c->countsf_cap) {
-        if (c->countsf) cudaFree(c->countsf);
-        if (c->nsite) cudaFree(c->nsite);
+        if (c->countsf) dfree(c, c->countsf);
+        if (c->nsite) dfree(c, c->nsite);
         c->countsf = nullptr; c->nsite = nullptr; c->countsf_cap = 0;
-        CU(cudaMalloc(&c->countsf, ncell * sizeof(float4)));
-        CU(cudaMalloc(&c->nsite, (size_t)c->V * sizeof(float)));
+        CU(dmalloc(c, &c->countsf, ncell * sizeof(float4)));
+        CU(dmalloc(c, &c->nsite, (size_t)c->V * sizeof(float)));
         c->countsf_cap = ncell;
         c->agg_valid = false;     // filled by the next regroup
     }
@@ -797,9 +815,9 @@ static int gen_mt_words(desman_ctx *c)
 {
     const size_t total = (size_t)c->V_total * c->G, lo = (size_t)c->v0 * c->G, n = (size_t)c->V * c->G;
     if (n > c->words_cap) {
-        if (c->words) cudaFree(c->words);
+        if (c->words) dfree(c, c->words);
         c->words = nullptr; c->words_cap = 0;
-        CU(cudaMalloc(&c->words, n * sizeof(uint32_t)));
+        CU(dmalloc(c, &c->words, n * sizeof(uint32_t)));
         c->words_cap = n;
     }
     {
@@ -1179,7 +1197,7 @@ static int prepare_profiling(desman_ctx *c)
     timing_reset(c);
     if (c->prof_flush && !c->flush_buf) {
         c->flush_n = ((size_t)256 << 20) / sizeof(uint4);
-        CU(cudaMalloc(&c->flush_buf, c->flush_n * sizeof(uint4)));
+        CU(dmalloc(c, &c->flush_buf, c->flush_n * sizeof(uint4)));
     }
     return DESMAN_OK;
 }
