@@ -66,6 +66,8 @@ def run_chain(eng_mod, p, G, group, n_iter, tau0, gamma0, eta0, seed=4242, mu_mo
 CASES = [  # V, S, G, depth: strain blocks of 8 (G = 5, 8, 6), of 4 (G = 3, 4, 9, 12), ragged S, S < 8, deep and shallow counts
     (3000, 64, 5, 20.0), (2500, 64, 8, 30.0), (1500, 7, 3, 8.0), (1200, 130, 12, 10.0), (1000, 40, 4, 5.0),
     (900, 64, 9, 25.0), (700, 33, 6, 300.0), (400, 3, 2, 50.0),
+    (300, 5, 1, 30.0),        # one strain: patterns are the four bases
+    (600, 16, 4, 4000.0),     # counts >= 2048 are not exact in TF32: the FFMA form takes over whatever tau_group_mma says
 ]
 
 
