@@ -1360,8 +1360,10 @@ extern "C" int desman_comm_init(desman_ctx *c, const char id[128], int rank, int
     NC(g_nccl.CommInitRank(&c->comm, nranks, u, rank));
     c->rank = rank; c->nranks = nranks;
     // peer-memory mailboxes for the per-sweep exchange; any failure here leaves the NCCL all-reduce in place
+    // opt-in (DESMAN_B200_P2P=1): measured on 2 GPUs the two exchanges of a sweep cost the same either way (the time is
+    // inter-rank skew, not protocol latency), and NCCL waits for a late rank where the spin limit of the kernel gives up
     const char *env = getenv("DESMAN_B200_P2P");
-    if (env && !atoi(env)) return DESMAN_OK;
+    if (!env || !atoi(env)) return DESMAN_OK;
     if (nranks > XCH_MAX_RANKS || !g_nccl.AllGather) return DESMAN_OK;
     const int cap = 4096;                                             // words per contribution (S*G + 16 must fit)
     const size_t words = (size_t)2 * nranks * cap + nranks;
