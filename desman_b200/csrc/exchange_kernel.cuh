@@ -53,8 +53,8 @@ __global__ void __launch_bounds__(512) exchange_sum_kernel(XchParams p)
         st_release_sys(p.mail[r] + (size_t)2 * n * p.cap_words + p.rank, p.seq);
         long long spins = 0;
         while (ld_acquire_sys(flags + r) < p.seq) {
-            if (++spins > (1ll << 26)) { *p.err = 1; break; }      // ~ seconds: a peer died; do not hang the GPU
-            __nanosleep(20);
+            if (++spins > (1ll << 28)) { *p.err = 1; break; }      // ~ half a minute: a peer died; do not hang the GPU
+            __nanosleep(64);
         }
     }
     __syncthreads();
