@@ -121,7 +121,8 @@ struct desman_ctx {
     uint8_t *tau = nullptr, *tau_star = nullptr;
     double *gamma = nullptr, *eta = nullptr, *eta_new = nullptr, *gamma_star = nullptr, *eta_star = nullptr;
     unsigned long long *stats = nullptr;     // [S*G + 16] sum_mu | esum
-    unsigned long long *red_i = nullptr;     // [2] fixed-point sum n*log p | nchange  (one int64 all-reduce under sharding)
+    unsigned long long *red_base = nullptr;  // [2][2] two parities of ...
+    unsigned long long *red_i = nullptr;     // [2] fixed-point sum n*log p | nchange of the current sweep (= red_base + 2*parity)
     double *scal = nullptr;                  // [4] lp_star, iter_star, ll, lp
     int *flag = nullptr;
     uint32_t *tau_cnt = nullptr, *tau_last = nullptr;
@@ -279,7 +280,8 @@ extern "C" int desman_ctx_create(desman_ctx **out, int device, uint64_t seed, in
     CU(dmalloc(c, &c->eta, 16 * sizeof(double)));
     CU(dmalloc(c, &c->eta_new, 16 * sizeof(double)));
     CU(dmalloc(c, &c->eta_star, 16 * sizeof(double)));
-    CU(dmalloc(c, &c->red_i, 2 * sizeof(unsigned long long)));
+    CU(dmalloc(c, &c->red_base, 4 * sizeof(unsigned long long)));
+    c->red_i = c->red_base;
     CU(dmalloc(c, &c->scal, 4 * sizeof(double)));
     CU(dmalloc(c, &c->flag, sizeof(int)));
     CU(dmalloc(c, &c->tiers, 3 * sizeof(unsigned long long)));
@@ -305,7 +307,7 @@ extern "C" int desman_ctx_destroy(desman_ctx *c)
     if (c->xch_err) cudaFree(c->xch_err);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
     void *ptrs[] = {c->counts, c->tau, c->tau_star, c->gamma, c->eta, c->eta_new, c->gamma_star, c->eta_star, c->stats,
-                    c->red_i, c->agg_ctl, c->scal, c->flag, c->tau_cnt, c->tau_last, c->mt_state, c->words,
+                    c->red_base, c->agg_ctl, c->scal, c->flag, c->tau_cnt, c->tau_last, c->mt_state, c->words,
                     c->scratch, c->flush_buf, c->tiers, c->agg_keys, c->agg_code, c->agg_N, c->agg_ids, c->agg_nslots, c->agg_classM,
                     c->countsf, c->nsite, c->grp_site_slot, c->grp_order, c->grp_singles, c->grp_slot4, c->grp_gctl, c->grp_blk,
                     c->grp_items, c->grp_work};
@@ -981,24 +983,35 @@ static int launch_mu(desman_ctx *c, const double *gamma, const double *eta)
     return DESMAN_OK;
 }
 
-static int exchange_sum(desman_ctx *c, unsigned long long *data, int words)
+static int exchange_sum(desman_ctx *c, unsigned long long *data, int words, unsigned long long *data2 = nullptr, int words2 = 0)
 {
     XchParams p;
     for (int r = 0; r < XCH_MAX_RANKS; r++) p.mail[r] = c->xch_mail[r];
     p.rank = c->rank; p.nranks = c->nranks; p.words = words; p.cap_words = c->xch_cap_words;
+    p.data2 = data2; p.words2 = words2;
     p.seq = ++c->xch_seq; p.data = data; p.err = c->xch_err;
     exchange_sum_kernel<<<1, 512, 0, c->stream>>>(p);
     CU(cudaGetLastError());
     return DESMAN_OK;
 }
 
-static int allreduce_stats(desman_ctx *c)
+// the statistics of this sweep and, with them, the [ll, nchange] words `red2` of the previous one (or null): ONE
+// synchronisation point per sweep under sharding (every exchange costs the skew between the ranks)
+static int allreduce_stats(desman_ctx *c, unsigned long long *red2 = nullptr)
 {
     if (c->nranks <= 1) return DESMAN_OK;
     KSpan k(c, DESMAN_K_OTHER);
     const size_t n = (size_t)c->S * c->G + 16;
-    if (c->xch_ok && (int)n <= c->xch_cap_words) return exchange_sum(c, c->stats, (int)n);
+    if (c->xch_ok && (int)n + 2 <= c->xch_cap_words) return exchange_sum(c, c->stats, (int)n, red2, red2 ? 2 : 0);
+    if (red2 && g_nccl.GroupStart && g_nccl.GroupEnd) {
+        NC(g_nccl.GroupStart());
+        NC(g_nccl.AllReduce(c->stats, c->stats, n, NCCL_UINT64, NCCL_SUM, c->comm, c->stream));
+        NC(g_nccl.AllReduce(red2, red2, 2, NCCL_INT64, NCCL_SUM, c->comm, c->stream));
+        NC(g_nccl.GroupEnd());
+        return DESMAN_OK;
+    }
     NC(g_nccl.AllReduce(c->stats, c->stats, n, NCCL_UINT64, NCCL_SUM, c->comm, c->stream));
+    if (red2) NC(g_nccl.AllReduce(red2, red2, 2, NCCL_INT64, NCCL_SUM, c->comm, c->stream));
     return DESMAN_OK;
 }
 static int allreduce_red(desman_ctx *c)
@@ -1034,13 +1047,21 @@ static int launch_draw(desman_ctx *c, const unsigned long long *stats, double *g
 struct StoreBufs { double *ll = nullptr, *lp = nullptr, *nch = nullptr, *gs = nullptr, *es = nullptr; };
 
 // ll (from the table) -> lp, stores, MAP bookkeeping.  gamma/eta: the state the likelihood is evaluated at.
+static int launch_finalize_only(desman_ctx *c, const unsigned long long *red, const double *gamma, const double *eta, int it,
+                                int star_mode, const StoreBufs &sb, bool store_ge);
 static int launch_finalize(desman_ctx *c, const double *gamma, const double *eta, int it, int star_mode, const StoreBufs &sb,
                            bool store_ge)
 {
     RET(launch_ll(c, gamma, eta));
     RET(allreduce_red(c));
+    return launch_finalize_only(c, c->red_i, gamma, eta, it, star_mode, sb, store_ge);
+}
+// lp, stores, MAP bookkeeping from the (already summed) words red = [fixed-point ll, nchange]
+static int launch_finalize_only(desman_ctx *c, const unsigned long long *red, const double *gamma, const double *eta, int it,
+                                int star_mode, const StoreBufs &sb, bool store_ge)
+{
     FinalParams p;
-    p.red_i = (const long long *)c->red_i; p.ll_const = c->ll_const_total; p.ll_inv_scale = 1.0 / c->ll_scale;
+    p.red_i = (const long long *)red; p.ll_const = c->ll_const_total; p.ll_inv_scale = 1.0 / c->ll_scale;
     p.gamma = gamma; p.eta = eta; p.eta_commit = nullptr;
     p.S = c->S; p.G = c->G; p.V_total = (double)c->V_total; p.alpha = c->alpha; p.delta = c->delta;
     p.lg_alphaG = lgamma(c->alpha * c->G); p.lg_alpha = lgamma(c->alpha);
@@ -1221,18 +1242,33 @@ extern "C" int desman_update(desman_ctx *c, int n_iter, double *gamma_store, dou
     // pre-sweep ll/lp and star state (:336-338)
     RET(sync_table(c));
     RET(launch_finalize(c, c->gamma, c->eta, -1, 0, sb, false));
+    // Under sharding the [ll, nchange] words of sweep k travel with the statistics of sweep k+1 (one exchange, i.e. one
+    // inter-rank synchronisation, per sweep instead of two), and lp / stores / MAP bookkeeping of sweep k follow that exchange --
+    // still before gamma and tau of sweep k+1 change.  The words are double buffered on the parity of the sweep.
+    const bool lagged = c->nranks > 1;
     for (int it = 0; it < n_iter; it++) {
         sweep_begin(c);
+        unsigned long long *red_prev = c->red_i;
+        if (lagged) c->red_i = c->red_base + 2 * (it & 1);
         RET(sync_table(c));                                             // clears the accumulators; table upkeep when pending
         RET(launch_mu(c, c->gamma, c->eta));                            // sampleMu   (:341)
-        RET(allreduce_stats(c));
+        if (lagged && it > 0) {
+            RET(allreduce_stats(c, red_prev));
+            RET(launch_finalize_only(c, red_prev, c->gamma, c->eta, it - 1, 0, sb, true));   // ll, lp, stores, star of sweep it-1
+        } else RET(allreduce_stats(c));
         RET(launch_draw(c, c->stats, c->gamma, c->eta_new));            // sampleGamma (:342) + sampleEta's draw (:347)
         if (!c->fixed_tau) RET(launch_tau(c, c->gamma, c->eta, true, true, (uint32_t)it));       // sample_tau (:345), old eta (nchange cleared by sync_table)
         CU(cudaMemcpyAsync(c->eta, c->eta_new, 16 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));   // eta <- new (:347)
-        RET(launch_finalize(c, c->gamma, c->eta, it, 0, sb, true));     // ll, lp, stores, star (:349-358)
+        if (lagged) RET(launch_ll(c, c->gamma, c->eta));                // sum n*log p of sweep it; reduced with the next exchange
+        else RET(launch_finalize(c, c->gamma, c->eta, it, 0, sb, true));     // ll, lp, stores, star (:349-358)
         sweep_end(c);
         c->sweep++;
     }
+    if (lagged && n_iter > 0) {
+        RET(allreduce_red(c));
+        RET(launch_finalize_only(c, c->red_i, c->gamma, c->eta, n_iter - 1, 0, sb, true));
+    }
+    c->red_i = c->red_base;
     {
         KSpan k(c, DESMAN_K_OTHER);
         flush_tau_counts_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(c->tau, c->tau_cnt, c->tau_last, nvg, (uint32_t)n_iter);

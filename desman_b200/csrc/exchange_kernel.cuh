@@ -21,6 +21,8 @@ struct XchParams {
     int cap_words;                             // XCH_WORDS of the mailbox layout
     unsigned long long seq;                    // number of this exchange (1, 2, ...)
     unsigned long long *data;                  // in: this rank's contribution; out: the sum over ranks
+    unsigned long long *data2;                 // optional second segment (appended to the first in the mailbox), or null
+    int words2;
     int *err;                                  // set to 1 if a peer never showed up (spin limit)
 };
 
@@ -37,12 +39,12 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 
 __global__ void __launch_bounds__(512) exchange_sum_kernel(XchParams p)
 {
-    const int n = p.nranks, W = p.words;
+    const int n = p.nranks, W1 = p.words, W = p.words + p.words2;
     const size_t slot_off = ((size_t)(p.seq & 1ull) * n + p.rank) * p.cap_words;
     // 1. my contribution into every mailbox (peer stores over NVLink; the local one is a plain store)
     for (int i = threadIdx.x; i < W * n; i += blockDim.x) {
         const int r = i / W, j = i - r * W;
-        p.mail[r][slot_off + j] = p.data[j];
+        p.mail[r][slot_off + j] = (j < W1) ? p.data[j] : p.data2[j - W1];
     }
     __threadfence_system();
     __syncthreads();
@@ -63,6 +65,6 @@ __global__ void __launch_bounds__(512) exchange_sum_kernel(XchParams p)
     for (int j = threadIdx.x; j < W; j += blockDim.x) {
         unsigned long long acc = 0ull;
         for (int r = 0; r < n; r++) acc += mine[(size_t)r * p.cap_words + j];
-        p.data[j] = acc;
+        if (j < W1) p.data[j] = acc; else p.data2[j - W1] = acc;
     }
 }
