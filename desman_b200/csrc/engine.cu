@@ -277,6 +277,12 @@ extern "C" int desman_ctx_create(desman_ctx **out, int device, uint64_t seed, in
         } else cudaGetLastError();
     }
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {
+        double inv[65];
+        inv[0] = 0.0;
+        for (int x = 1; x <= 64; x++) inv[x] = 1.0 / (double)x;
+        CU(cudaMemcpyToSymbol(c_inv_small, inv, sizeof(inv)));
+    }
     CU(dmalloc(c, &c->eta, 16 * sizeof(double)));
     CU(dmalloc(c, &c->eta_new, 16 * sizeof(double)));
     CU(dmalloc(c, &c->eta_star, 16 * sizeof(double)));
@@ -806,7 +812,7 @@ static int launch_ll(desman_ctx *c, const double *gamma, const double *eta)
     MuAggParams p = agg_params(c, gamma, eta);
     {
         KSpan k(c, DESMAN_K_FINAL);
-        ll_table_kernel<<<c->sm_count * 2, 256, 0, c->stream>>>(p);
+        ll_table_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(p);       // ~one (slot, 32 samples) item per warp: a latency chain
     }
     CU(cudaGetLastError());
     return DESMAN_OK;

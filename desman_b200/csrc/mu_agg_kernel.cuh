@@ -180,6 +180,9 @@ __device__ double stirling_tail_d(double k)
 
 struct BinStream { uint32_t c0, c1, c2, c3, k0, k1; };
 
+// 1/x for x = 1..64, correctly rounded (filled by the host with 1.0 / x in IEEE double)
+__constant__ double c_inv_small[65];
+
 __device__ __forceinline__ void bin_uniforms_d(const BinStream &st, int g, uint32_t attempt, double &u1, double &u2)
 {
     const uint4 o = philox4x32_10(st.c0, st.c1, st.c2, st.c3, st.k0 ^ (((uint32_t)(g + 1) << 20) | attempt), st.k1);
@@ -207,7 +210,10 @@ __device__ __noinline__ long long binomial_draw_d(long long n, double p, double 
             u = __dadd_rn(u, -r);
             x++;
             if (x > n) { x = n; break; }
-            r = __ddiv_rn(__dmul_rn(r, __dmul_rn(s, (double)(n - x + 1))), (double)x);
+            // r_x = r_{x-1} * s * (n-x+1) / x; for x <= 64 the division is a multiplication by the correctly rounded 1/x
+            // (a table; the oracle forms the same 1.0/x), which takes ~80 cycles out of every step of the search
+            const double num = __dmul_rn(r, __dmul_rn(s, (double)(n - x + 1)));
+            r = (x <= 64) ? __dmul_rn(num, c_inv_small[x]) : __ddiv_rn(num, (double)x);
             if (x > 4096) break;
         }
     } else {

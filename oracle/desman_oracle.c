@@ -369,7 +369,11 @@ static int64_t binomial_draw(int64_t n, double p, double q, const bin_stream *st
             u = u - r;
             x++;
             if (x > n) { x = n; break; }
-            r = (r * (s * (double)(n - x + 1))) / (double)x;
+            {   /* for x <= 64 the GPU multiplies by the correctly rounded reciprocal instead of dividing */
+                const double num = r * (s * (double)(n - x + 1));
+                if (x <= 64) { const double inv = 1.0 / (double)x; r = num * inv; }
+                else r = num / (double)x;
+            }
             if (x > 4096) break;        /* numerical guard: mass beyond here is < 1e-300 */
         }
     } else {
