@@ -3,7 +3,7 @@
 // KL-divergence multiplicative updates of X[4V,S] ~ tau[4V,G] * gamma[G,S] with per-(v,g) simplex
 // renormalisation.  The reference does four np.dot products and a Python V*G loop per iteration
 // (Init_NMFT.py:158-181).  Here one iteration is three launches, all bandwidth-bound on X:
-//   nmft_gamma_kernel  (tiny)   reduce the per-block partials of the previous pass in fixed order,
+//   nmft_gamma_kernel  (small)  reduce the per-block partials of the previous pass in fixed order,
 //                               evaluate the stop rule |div_prev - div| > min_change on the device,
 //                               apply the gamma update (:161-166) and the eps clamp (:88-91)
 //   nmft_tau_kernel    (site)   tau update (:170-181): one warp per site, lanes over samples
@@ -56,11 +56,14 @@ struct NmftParams {
     double min_change;
 };
 
-// grid = ceil(S/32) blocks of 256 threads; block b owns sample columns [32b, 32b+32).
+// grid = ceil(S/4) blocks of 256 threads; block b owns sample columns [4b, 4b+4).  Warp <-> strain (8 at a time), lane =
+// (sample of the block) x (8 partial-sum lanes striding over the per-block partials of the stats pass): every (g,s) sum over
+// the ~300 partials is 37 pipelined loads and a fixed-order 3-level shuffle tree instead of one thread's 300 dependent loads.
+#define NMFT_GS 4
 __global__ void __launch_bounds__(256) nmft_gamma_kernel(NmftParams p)
 {
     __shared__ double red[256];
-    __shared__ double col[32][33];
+    __shared__ double col[32][NMFT_GS + 1];
     __shared__ int go;
     const int S = p.S, G = p.G, stride = G * S + G + 1;
     // total divergence of the previous pass (every block computes the same bits)
@@ -88,93 +91,98 @@ __global__ void __launch_bounds__(256) nmft_gamma_kernel(NmftParams p)
     }
     __syncthreads();
     if (!go) return;
-    const int s_local = threadIdx.x & 31, gsub = threadIdx.x >> 5;    // 8 strain rows at a time
-    const int s = blockIdx.x * 32 + s_local;
+    const int lane = threadIdx.x & 31, gsub = threadIdx.x >> 5;       // 8 strain rows at a time
+    const int s_local = lane >> 3, j = lane & 7;
+    const int s = blockIdx.x * NMFT_GS + s_local;
     if (!p.fix_gamma) {
         for (int g0 = 0; g0 < G; g0 += 8) {
             const int g = g0 + gsub;
             double newg = 0.0;
-            if (g < G && s < S) {
+            if (g < G) {                                                  // (warp-uniform)
+                double num = 0.0, h1 = 0.0;
                 if (G > 1) {
-                    double num = 0.0, h1 = 0.0;
-                    for (int b = 0; b < p.nblocks; b++) {
-                        num += p.partial[(size_t)b * stride + g * S + s];
+                    for (int b = j; b < p.nblocks; b += 8) {
+                        if (s < S) num += p.partial[(size_t)b * stride + g * S + s];
                         h1 += p.partial[(size_t)b * stride + G * S + g];
                     }
-                    newg = p.gamma_adj[g * S + s] * (nzd(num) / nzd(h1));                 // :163
+#pragma unroll
+                    for (int m = 4; m > 0; m >>= 1) {
+                        num += __shfl_xor_sync(DESMAN_FULL_MASK, num, m);
+                        h1 += __shfl_xor_sync(DESMAN_FULL_MASK, h1, m);
+                    }
+                    if (s < S) newg = p.gamma_adj[g * S + s] * (nzd(num) / nzd(h1));      // :163
                 } else newg = 1.0;                                                        // :167-168
+                if (j == 0) col[g][s_local] = newg;
             }
-            if (g < G) col[g][s_local] = newg;
         }
         __syncthreads();
-        if (gsub == 0 && s < S) {
+        if (threadIdx.x < NMFT_GS && blockIdx.x * NMFT_GS + (int)threadIdx.x < S) {
+            const int sl = threadIdx.x, ss = blockIdx.x * NMFT_GS + sl;
             double cs = 0.0;
-            for (int g = 0; g < G; g++) cs += col[g][s_local];                            // :165
+            for (int g = 0; g < G; g++) cs += col[g][sl];                                 // :165
             for (int g = 0; g < G; g++) {
-                const double x = (G > 1) ? col[g][s_local] / cs : 1.0;                    // :166
-                p.gamma[g * S + s] = x;
-                p.gamma_adj[g * S + s] = fmax(x, NMFT_EPS);                               // _adjustment :88-91
+                const double x = (G > 1) ? col[g][sl] / cs : 1.0;                         // :166
+                p.gamma[g * S + ss] = x;
+                p.gamma_adj[g * S + ss] = fmax(x, NMFT_EPS);                              // _adjustment :88-91
             }
         }
     }
 }
 
-// t1[g] = sum_s gamma'[g][s]   (Init_NMFT.py:170)  -- one block, fixed order
-__global__ void __launch_bounds__(256) nmft_t1_kernel(NmftParams p)
-{
-    if (p.st_out->done) return;
-    __shared__ double red[256];
-    for (int g = 0; g < p.G; g++) {
-        double acc = 0.0;
-        for (int s = threadIdx.x; s < p.S; s += 256) acc += p.gamma[g * p.S + s];
-        red[threadIdx.x] = acc;
-        __syncthreads();
-        for (int m = 128; m > 0; m >>= 1) {
-            if (threadIdx.x < m) red[threadIdx.x] += red[threadIdx.x + m];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) p.t1[g] = red[0];
-        __syncthreads();
-    }
-}
-
-// tau update (Init_NMFT.py:170-181) + clamp (:88-91 when gamma is being fitted).  One warp per site.
+// tau update (Init_NMFT.py:170-181) + clamp (:88-91 when gamma is being fitted).  One warp per site, three phases:
+//   1  lanes over samples:  r[a][s] = (X / (tau gamma))[a][s], zeros -> eps in both operands (du.elop)
+//   2  lanes over the 4G outputs (a,g): numT[a][g] = sum_s r[a][s] gamma[g][s] (:172) as a sequential dot product per lane -- no
+//      cross-lane reduction at all -- and the multiplicative update tau * numT / t1 with its division in parallel
+//   3  lanes over strains: renormalisation over the 4 bases (:176-181)
+// t1[g] = sum_s gamma'[g][s] (:170) is formed by every CTA in its prologue in a fixed order (it was a launch of its own).
+// Shared-memory rows are padded by 2 doubles so that lanes reading different rows at the same sample hit different banks.
 __global__ void __launch_bounds__(NMFT_WARPS * 32) nmft_tau_kernel(NmftParams p)
 {
     if (p.st_out->done) return;
     extern __shared__ double sm[];
-    const int S = p.S, G = p.G;
-    double *gm = sm;                                   // [G][S] gamma'
-    double *t1 = gm + (size_t)G * S;                   // [G]
+    const int S = p.S, G = p.G, Sr = S + 2;
+    double *gm = sm;                                   // [G][Sr] gamma'
+    double *t1 = gm + (size_t)G * Sr;                  // [G]
     double *tw = t1 + G;                               // [NMFT_WARPS][8][G]: old tau rows [4][G], new rows [4][G]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < G * S; i += blockDim.x) gm[i] = p.gamma[i];
-    for (int i = threadIdx.x; i < G; i += blockDim.x) t1[i] = p.t1[i];
+    for (int i = threadIdx.x; i < G * S; i += blockDim.x) { const int g = i / S, ss = i - g * S; gm[g * Sr + ss] = p.gamma[i]; }
+    __syncthreads();
+    for (int g = wib; g < G; g += NMFT_WARPS) {
+        double acc = 0.0;
+        for (int ss = lane; ss < S; ss += 32) acc += gm[g * Sr + ss];
+        acc = warp_sum(acc);
+        if (lane == 0) t1[g] = acc;
+    }
     __syncthreads();
     double *told = tw + (size_t)wib * 8 * G, *tnew = told + 4 * G;
-    double *rb = tw + (size_t)NMFT_WARPS * 8 * G + (size_t)wib * S;   // [S] per warp
+    double *rb = tw + (size_t)NMFT_WARPS * 8 * G + (size_t)wib * 4 * Sr;   // [4][Sr] per warp
     const int gw = blockIdx.x * NMFT_WARPS + wib, nw = gridDim.x * NMFT_WARPS;
     for (int v = gw; v < p.V; v += nw) {
         double *tv = p.tau + (size_t)v * 4 * G;
         for (int i = lane; i < 4 * G; i += 32) told[i] = tv[i];
         __syncwarp();
         const double *Xv = p.X + (size_t)v * 4 * S;
-        for (int a = 0; a < 4; a++) {
-            // r[s] = (X / (tau gamma))[a][s], zeros -> eps in both operands (du.elop)
-            for (int s = lane; s < S; s += 32) {
+        for (int ss = lane; ss < S; ss += 32) {
+#pragma unroll
+            for (int a = 0; a < 4; a++) {
                 double pa = 0.0;
-                for (int h = 0; h < G; h++) pa = fma(told[a * G + h], gm[h * S + s], pa);
-                rb[s] = nzd(Xv[a * S + s]) / nzd(pa);
+                for (int h = 0; h < G; h++) pa = fma(told[a * G + h], gm[h * Sr + ss], pa);
+                rb[a * Sr + ss] = nzd(Xv[a * S + ss]) / nzd(pa);
             }
-            __syncwarp();
-            for (int g = 0; g < G; g++) {
-                // numT[a][g] = sum_s r[s] * gamma[g][s]      (:172)
-                double acc = 0.0;
-                for (int s = lane; s < S; s += 32) acc = fma(rb[s], gm[g * S + s], acc);
-                acc = warp_sum(acc);
-                if (lane == 0) tnew[a * G + g] = told[a * G + g] * (nzd(acc) / nzd(t1[g]));
+        }
+        __syncwarp();
+        for (int o = lane; o < 4 * G; o += 32) {
+            const int a = o / G, g = o - a * G;
+            const double *ra = rb + a * Sr, *gg = gm + g * Sr;
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;                                // four chains: DFMA latency, not rate
+            int ss = 0;
+            for (; ss + 4 <= S; ss += 4) {
+                a0 = fma(ra[ss], gg[ss], a0); a1 = fma(ra[ss + 1], gg[ss + 1], a1);
+                a2 = fma(ra[ss + 2], gg[ss + 2], a2); a3 = fma(ra[ss + 3], gg[ss + 3], a3);
             }
-            __syncwarp();
+            for (; ss < S; ss++) a0 = fma(ra[ss], gg[ss], a0);
+            const double acc = (a0 + a1) + (a2 + a3);
+            tnew[o] = told[o] * (nzd(acc) / nzd(t1[g]));
         }
         __syncwarp();
         for (int g = lane; g < G; g += 32) {
@@ -229,8 +237,9 @@ __global__ void __launch_bounds__(NMFT_WARPS * 32) nmft_stats_kernel(NmftParams 
 #pragma unroll
                 for (int g = 0; g < GP; g++) if (g < G) pa = fma(tl[a * G + g], gcol[g], pa);
                 const double pc = fmax(pa, NMFT_EPS);                                     // _adjustment_input :93-97
-                dv += x * log(nzd(x) / nzd(pc)) - x + pc;                                 // :156
-                const double r = nzd(x) / nzd(pa);
+                const double q = nzd(x) / nzd(pc);
+                dv += x * log(q) - x + pc;                                                // :156
+                const double r = (pc == pa) ? q : nzd(x) / nzd(pa);                       // same quotient unless pa was clamped
 #pragma unroll
                 for (int g = 0; g < GP; g++) if (g < G) num[g] = fma(tl[a * G + g], r, num[g]);
             }
@@ -288,9 +297,9 @@ static int nmft_factorize_impl(cudaStream_t stream, int sm_count, const int64_t 
     int grid_stats = sm_count * 2;
     grid_stats = ((grid_stats * NMFT_WARPS + nch - 1) / nch * nch + NMFT_WARPS - 1) / NMFT_WARPS;
     while ((grid_stats * NMFT_WARPS) % nch) grid_stats++;
-    const int grid_tau = (int)((V + NMFT_WARPS - 1) / NMFT_WARPS < sm_count * 4 ? (V + NMFT_WARPS - 1) / NMFT_WARPS : sm_count * 4);
+    int grid_tau = sm_count * 2;        // one resident wave (set from the occupancy below)
     const size_t stride = nG + G + 1;
-    const size_t smem_tau = sizeof(double) * (nG + G + (size_t)NMFT_WARPS * 8 * G + (size_t)NMFT_WARPS * S);
+    const size_t smem_tau = sizeof(double) * ((size_t)G * (S + 2) + G + (size_t)NMFT_WARPS * 8 * G + (size_t)NMFT_WARPS * 4 * (S + 2));
     const size_t smem_stats = sizeof(double) * (2 * nG + G + (size_t)NMFT_WARPS * 4 * G);
     double *dX = nullptr, *dT = nullptr, *dG = nullptr, *dGa = nullptr, *dt1 = nullptr, *dP = nullptr, *dTr = nullptr;
     long long *dS = nullptr;
@@ -340,6 +349,12 @@ static int nmft_factorize_impl(cudaStream_t stream, int sm_count, const int64_t 
     p.trace = div_trace ? dTr : nullptr; p.V = (int)V; p.S = S; p.G = G; p.max_iter = max_iter; p.fix_gamma = fix_gamma;
     p.min_change = min_change;
     NMFT_CU(cudaFuncSetAttribute(nmft_tau_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tau));
+    {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, nmft_tau_kernel, NMFT_WARPS * 32, smem_tau) != cudaSuccess || occ < 1) occ = 1;
+        grid_tau = sm_count * occ;
+        if ((int64_t)grid_tau * NMFT_WARPS > V) grid_tau = (int)((V + NMFT_WARPS - 1) / NMFT_WARPS);
+    }
 
 #define NMFT_STATS()                                                                     \
     do {                                                                                 \
@@ -359,8 +374,7 @@ static int nmft_factorize_impl(cudaStream_t stream, int sm_count, const int64_t 
         while (!finished) {
             for (int b = 0; b < 64; b++) {   // enqueue a batch of iterations; the stop rule lives on the device
                 p.st_in = dSt + parity; p.st_out = dSt + (parity ^ 1);
-                nmft_gamma_kernel<<<nch, 256, 0, stream>>>(p);
-                nmft_t1_kernel<<<1, 256, 0, stream>>>(p);
+                nmft_gamma_kernel<<<(S + NMFT_GS - 1) / NMFT_GS, 256, 0, stream>>>(p);
                 nmft_tau_kernel<<<grid_tau, NMFT_WARPS * 32, smem_tau, stream>>>(p);
                 NMFT_STATS();
                 parity ^= 1;
