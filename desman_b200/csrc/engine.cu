@@ -376,6 +376,18 @@ extern "C" int desman_get_rng(desman_ctx *c, uint32_t *sweep, uint64_t *mt_words
 }
 
 // ------------------------------------------------------------------------------------------ data
+// process-wide pinned staging buffers (pinning is slow): 2 x 32 MB, used by the count upload and the large downloads
+static const size_t PIN_CELLS = (size_t)2 << 20;                       // int4 cells per buffer
+static int4 *g_pin[2] = {nullptr, nullptr};
+static std::mutex g_pin_mu;
+static int ensure_pinned()
+{
+    if (!g_pin[0]) {
+        CU(cudaMallocHost(&g_pin[0], PIN_CELLS * sizeof(int4)));
+        CU(cudaMallocHost(&g_pin[1], PIN_CELLS * sizeof(int4)));
+    }
+    return DESMAN_OK;
+}
 // host-side conversion loops run on a few threads (the arrays of the class surface are tens to hundreds of MB)
 static int host_threads(size_t n)
 {
@@ -410,14 +422,9 @@ extern "C" int desman_set_counts(desman_ctx *c, const int64_t *variants, int64_t
     }
     // Repack int64 -> int32x4 on the host with a few threads straight into pinned staging buffers and stream the
     // packed cells (half the bytes of the int64 tensor) to the device, double-buffered.
-    const size_t chunk_cells = (size_t)2 << 20;                         // 32 MB of packed cells per buffer
-    static int4 *g_pin[2] = {nullptr, nullptr};                          // process-wide pinned staging (pinning is slow)
-    static std::mutex g_pin_mu;
+    const size_t chunk_cells = PIN_CELLS;                               // 32 MB of packed cells per buffer
     std::lock_guard<std::mutex> pin_lock(g_pin_mu);
-    if (!g_pin[0]) {
-        CU(cudaMallocHost(&g_pin[0], chunk_cells * sizeof(int4)));
-        CU(cudaMallocHost(&g_pin[1], chunk_cells * sizeof(int4)));
-    }
+    RET(ensure_pinned());
     if (!c->pin_ev[0]) {
         CU(cudaEventCreateWithFlags(&c->pin_ev[0], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->pin_ev[1], cudaEventDisableTiming));
@@ -531,12 +538,20 @@ static int onehot_to_index(const int64_t *tau, size_t n, uint8_t *idx)
 {
     std::atomic<long long> bad(-1);
     parallel_ranges(n, [&](size_t lo, size_t hi) {
+        long long mybad = -1;
         for (size_t i = lo; i < hi; i++) {
             const int64_t *t = tau + i * 4;
-            int b = t[0] == 1 ? 0 : t[1] == 1 ? 1 : t[2] == 1 ? 2 : t[3] == 1 ? 3 : -1;
-            if (b < 0) { bad = (long long)i; b = 0; }
+            // a valid row is {0,1}^4 with exactly one 1: index = t1 + 2 t2 + 3 t3 (branch-free); anything else falls back to
+            // the reference's "first b with tau == 1" rule (c_sample_tau.c:115-123) or is rejected
+            const int64_t orv = t[0] | t[1] | t[2] | t[3], sum = t[0] + t[1] + t[2] + t[3];
+            int b = (int)(t[1] + 2 * t[2] + 3 * t[3]);
+            if ((orv & ~(int64_t)1) != 0 || sum != 1) {
+                b = t[0] == 1 ? 0 : t[1] == 1 ? 1 : t[2] == 1 ? 2 : t[3] == 1 ? 3 : -1;
+                if (b < 0) { mybad = (long long)i; b = 0; }
+            }
             idx[i] = (uint8_t)b;
         }
+        if (mybad >= 0) bad = mybad;
     });
     if (bad >= 0)
         return fail(DESMAN_EINVAL, "tau row %lld is not one-hot (undefined behaviour in the reference, c_sample_tau.c:115-123)", bad.load());
@@ -1364,8 +1379,29 @@ extern "C" int desman_get_tau_sum(desman_ctx *c, int64_t *tau_sum)
 extern "C" int desman_get_tau_sum_u32(desman_ctx *c, uint32_t *tau_sum)
 {
     RET(require_state(c));
-    CU(cudaMemcpyAsync(tau_sum, c->tau_cnt, (size_t)c->V * c->G * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    // pageable D2H copies crawl through a driver bounce buffer: go through the pinned staging buffers (double buffered) and
+    // copy out on a few threads
+    std::lock_guard<std::mutex> pin_lock(g_pin_mu);
+    RET(ensure_pinned());
+    const size_t total = (size_t)c->V * c->G * 4 * sizeof(uint32_t), chunk = PIN_CELLS * sizeof(int4);
+    const char *src = (const char *)c->tau_cnt;
+    char *dst = (char *)tau_sum;
+    int buf = 0;
+    size_t off_prev = 0, n_prev = 0;
+    for (size_t off = 0; off < total || n_prev; off += chunk, buf ^= 1) {
+        size_t n = 0;
+        if (off < total) {
+            n = (total - off < chunk) ? total - off : chunk;
+            CU(cudaMemcpyAsync(g_pin[buf], src + off, n, cudaMemcpyDeviceToHost, c->stream));
+        }
+        if (n_prev) {          // copy out the previous chunk while this one is in flight
+            const char *ps = (const char *)g_pin[buf ^ 1];
+            char *pd = dst + off_prev;
+            parallel_ranges(n_prev, [&](size_t lo, size_t hi) { memcpy(pd + lo, ps + lo, hi - lo); });
+        }
+        CU(cudaStreamSynchronize(c->stream));
+        off_prev = off; n_prev = n;
+    }
     return DESMAN_OK;
 }
 
