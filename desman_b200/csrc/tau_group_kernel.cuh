@@ -537,18 +537,27 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
         };
         // ---- decisions of one pass from its complete sums; undecided sites go to the work list
         // accumulator (mt, nt, i): table column 16 mt + 8 (i >> 1) + g8, site 8 nt + 2 t4 + (i & 1)
-        auto decide = [&](int pbase, const float (&acc)[MT][2][4]) {
-            // the site this lane decides for: lanes g8 < 4 own row k = {2 t4, 2 t4 + 1, 8 + 2 t4, 9 + 2 t4}[g8] of the pass
+        // what the decisions of a pass need besides its sums, fetched BEFORE the contraction so that the (dependent) loads are
+        // not waited for after it: the site this lane decides for (lanes g8 < 4 own row k = {2 t4, 2 t4 + 1, 8 + 2 t4, 9 + 2 t4}[g8]
+        // of the pass), its current slot, and the read totals of the 4 sites whose sums this lane holds
+        struct PassMeta { int vown, sown; float nk[4]; };
+        auto fetch_meta = [&](int pbase) {
+            PassMeta mt_;
             const int kown = ((g8 & 2) << 2) + 2 * t4 + (g8 & 1);
-            const bool own = g8 < 4 && pbase + kown < count;
-            const int vown = p.grp.order[begin + (pbase + kown < count ? pbase + kown : 0)];
-            const int sown = p.grp.site_slot[vown];
-            float nk[4];                                                  // read totals of the 4 sites whose sums this lane holds
+            mt_.vown = p.grp.order[begin + (pbase + kown < count ? pbase + kown : 0)];
+            mt_.sown = p.grp.site_slot[mt_.vown];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 const int idx = pbase + ((k & 2) << 2) + 2 * t4 + (k & 1);
-                nk[k] = p.nsite[begin + (idx < count ? idx : 0)];
+                mt_.nk[k] = p.nsite[begin + (idx < count ? idx : 0)];
             }
+            return mt_;
+        };
+        auto decide = [&](int pbase, const float (&acc)[MT][2][4], const PassMeta &pm) {
+            const int kown = ((g8 & 2) << 2) + 2 * t4 + (g8 & 1);
+            const bool own = g8 < 4 && pbase + kown < count;
+            const int vown = pm.vown, sown = pm.sown;
+            const float (&nk)[4] = pm.nk;
             // a strain is decided "stay" iff each of its three candidates trails the current base by > 60 nats after the bound
             uint32_t m[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
@@ -597,8 +606,9 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
             for (; base < count; base += ROUND) {
                 if (base + ROUND < count) l2_prefetch_row(rows + (size_t)(base + ROUND) * S, (uint32_t)min(count - base - ROUND, TG_PASS_SITES) * row_bytes);
                 float acc[MT][2][4];
+                const PassMeta pm = fetch_meta(base);
                 contract(base, 0, nq, acc);
-                decide(base, acc);
+                decide(base, acc, pm);
             }
         } else {
             // short item (one or two passes): the warps split the SAMPLES of a pass (4 or 2 warps per pass) and the partial
@@ -608,6 +618,7 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
             const int qper = ((nq / 4 + kw - 1) / kw) * 4;
             const int qlo = min(nq, part * qper), qhi = min(nq, qlo + qper);
             float acc[MT][2][4];
+            const PassMeta pm = fetch_meta(pass * TG_PASS_SITES);
             contract(pass * TG_PASS_SITES, qlo, qhi, acc);
             if (part > 0) {
 #pragma unroll
@@ -626,7 +637,7 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
                         for (int nt = 0; nt < 2; nt++)
 #pragma unroll
                             for (int i = 0; i < 4; i++) acc[mt][nt][i] += red[((w2 - 1) * MT * 8 + (mt * 2 + nt) * 4 + i) * 32 + lane];
-                decide(pass * TG_PASS_SITES, acc);
+                decide(pass * TG_PASS_SITES, acc, pm);
             }
         }
         TGM_T(tp3);
