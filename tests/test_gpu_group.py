@@ -167,3 +167,29 @@ def test_grouped_chain_at_C2_size_matches_exact_path(eng_mod):
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
     assert res[0][4]["tau_group"] == 12 and res[1][4]["tau_group"] == 0
     assert res[0][3]["work"] + res[0][3]["singles"] < 2000
+
+
+def _random_shapes(n, seed=2024):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        G = int(rng.integers(1, 13))
+        S = int(rng.choice([1, 2, 5, 8, 15, 16, 17, 31, 33, 48, 64, 65, 100, 129]))
+        V = int(rng.integers(150, 900))
+        depth = float(rng.choice([2.0, 10.0, 60.0, 400.0]))
+        out.append((V, S, G, depth))
+    return out
+
+
+@pytest.mark.parametrize("V,S,G,depth", _random_shapes(10))
+def test_grouped_chain_identical_random_shapes(eng_mod, V, S, G, depth):
+    """Seeded random shapes (ragged S around the 8/16/32-sample tile edges, G from 1 to 12, shallow to deep counts): the tensor-core
+    and FFMA forms of the screening pass against the per-site kernel alone, 5 sweeps from the true state."""
+    p = mild_problem(V, S, G, depth, 977 * V + 31 * S + G)
+    tau0 = p["tau_true"]
+    b = run_chain(eng_mod, p, G, 0, 5, tau0, p["gamma_true"], p["eta0"])
+    for mma in (1, 0):
+        a = run_chain(eng_mod, p, G, 1, 5, tau0, p["gamma_true"], p["eta0"], mma=mma)
+        for k in ("tau", "nchange", "ll", "gamma", "tau_sum", "star"):
+            assert np.array_equal(a[k], b[k]), (k, mma)
+        assert a["tiers"].sum() == 5 * V * G
