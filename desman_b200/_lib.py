@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdesman_b200.so")
+# DESMAN_B200_LIB: an instrumented build of the same library (tools/kprof.py); never a different implementation
+LIB_PATH = os.environ.get("DESMAN_B200_LIB") or os.path.join(_HERE, "libdesman_b200.so")
 
 RNG_MT19937, RNG_PHILOX = 0, 1
 MAX_G = 32

@@ -5,6 +5,47 @@
 
 #define DESMAN_FULL_MASK 0xffffffffu
 
+// Programmatic dependent launch (engine.cu launch_k): the kernels of a sweep form one dependent chain on one stream, and each
+// completion -> launch hand-over costs ~4 us on B200 when left to the stream.  Every kernel of the chain starts with
+// pdl_enter(): wait until the preceding grid has completed and its writes are visible, then allow the next grid of the chain
+// to be scheduled (its CTAs become resident as this grid's CTAs retire and park in their own wait).  Without the launch
+// attribute both instructions are no-ops.  Nothing produced by an earlier kernel may be read before pdl_enter().
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// -DKPROF build (diagnosis only, tools/kprof.py): %globaltimer stamps of every CTA's entry / exit (and of the phases of a few
+// kernels) recorded in a device buffer that desman_kprof_dump() copies out.  The product build compiles none of it.
+enum { KP_MAINT = 0, KP_MUB, KP_MUC, KP_DRAW, KP_TGM, KP_TAU, KP_LL, KP_FIN, KP_COPY, KP_TAU_WARP, KP_TGM_PRO };
+#ifdef KPROF
+struct KRec { int kid, cta, warp, x; unsigned long long t0, t1, a, b, c, d; };
+#define KREC_CAP (1 << 18)
+__device__ KRec g_krec[KREC_CAP];
+__device__ unsigned int g_krec_n;
+__device__ __forceinline__ unsigned long long gtimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __noinline__ void krec_put(int kid, int cta, int warp, int x, unsigned long long t0, unsigned long long t1,
+                                      unsigned long long a = 0, unsigned long long b = 0, unsigned long long c = 0, unsigned long long d = 0)
+{
+    const unsigned int i = atomicAdd(&g_krec_n, 1u);
+    if (i < KREC_CAP) g_krec[i] = KRec{kid, cta, warp, x, t0, t1, a, b, c, d};
+}
+struct KProfScope {
+    int kid; unsigned long long t0;
+    __device__ KProfScope(int k) : kid(k), t0(gtimer()) {}
+    __device__ ~KProfScope() { if (threadIdx.x == 0) krec_put(kid, (int)blockIdx.x, 0, 0, t0, gtimer()); }
+};
+#define KPROF_SCOPE(kid) KProfScope kprof_scope_(kid)
+#else
+#define KPROF_SCOPE(kid)
+#endif
+
 // counter "stage" tags of the Philox contract; c3 = stage<<28 | ...
 enum { STAGE_TAU = 1, STAGE_MU = 2, STAGE_GAMMA = 3, STAGE_ETA = 4, STAGE_GAMMA_BOOST = 5, STAGE_ETA_BOOST = 6 };
 

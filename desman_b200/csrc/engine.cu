@@ -133,6 +133,7 @@ struct desman_ctx {
     size_t counts_cap = 0;
     size_t cap_vg = 0, cap_sg = 0;
     uint32_t last_n_iter = 0;
+    int pdl = 1;                             // programmatic dependent launch of the sweep's kernels (common.cuh pdl_enter)
     int tau_exact = 0;                       // 1: FP64 reference-order path for every draw
     int fixed_tau = 0;                       // 1: update() skips the tau draw (update_fixed_tau, HaploSNP_Sampler.py:409-428)
     int mu_mode = 2;                         // 1: pattern-aggregated binomial statistics (K2b), 0: per-read categorical (K2),
@@ -197,6 +198,22 @@ static cudaError_t dmalloc(desman_ctx *c, T **p, size_t bytes)
 static void dfree(desman_ctx *c, void *p)
 {
     if (p) cudaFreeAsync(p, c->stream);
+}
+
+// Launch of a kernel of the sweep's dependent chain (every such kernel begins with pdl_enter(), common.cuh): with the
+// programmatic-stream-serialization attribute the grid may be scheduled while its predecessor drains; its pdl_enter()
+// still orders everything it does after the predecessor's completion.
+template <typename... KA, typename... A>
+static cudaError_t launch_k(desman_ctx *c, void (*kern)(KA...), unsigned int grid, unsigned int block, size_t smem, A... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = c->pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, KA(args)...);
 }
 
 static int ensure_scratch(desman_ctx *c, size_t bytes)
@@ -292,6 +309,7 @@ extern "C" int desman_ctx_create(desman_ctx **out, int device, uint64_t seed, in
     CU(dmalloc(c, &c->flag, sizeof(int)));
     CU(dmalloc(c, &c->tiers, 3 * sizeof(unsigned long long)));
     CU(cudaMemset(c->tiers, 0, 3 * sizeof(unsigned long long)));
+    { const char *pd = getenv("DESMAN_B200_PDL"); if (pd) c->pdl = atoi(pd) ? 1 : 0; }
     { const char *ex = getenv("DESMAN_B200_TAU_EXACT"); c->tau_exact = (ex && atoi(ex)) ? 1 : 0; }
     { const char *tg = getenv("DESMAN_B200_TAU_GROUP"); if (tg) c->tau_group = atoi(tg); if (c->tau_group < 0 || c->tau_group > 2) c->tau_group = 2; }
     { const char *mm = getenv("DESMAN_B200_MU_MODE"); if (mm) c->mu_mode = atoi(mm); if (c->mu_mode < 0 || c->mu_mode > 2) c->mu_mode = 2; }
@@ -827,7 +845,7 @@ static int launch_ll(desman_ctx *c, const double *gamma, const double *eta)
     MuAggParams p = agg_params(c, gamma, eta);
     {
         KSpan k(c, DESMAN_K_FINAL);
-        ll_table_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(p);       // ~one (slot, 32 samples) item per warp: a latency chain
+        CU(launch_k(c, ll_table_kernel, c->sm_count * 4, 256, 0, p));       // ~one (slot, 32 samples) item per warp: a latency chain
     }
     CU(cudaGetLastError());
     return DESMAN_OK;
@@ -860,7 +878,7 @@ static int launch_tau_group_mma_t(desman_ctx *c, const TauGroupParams &p)
     CU(cudaFuncSetAttribute(tau_group_mma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tau_group_mma_kernel<NT>, TGM_WARPS * 32, smem) != cudaSuccess || occ < 1) occ = 1;
-    tau_group_mma_kernel<NT><<<c->sm_count * occ, TGM_WARPS * 32, smem, c->stream>>>(p);
+    CU(launch_k(c, tau_group_mma_kernel<NT>, c->sm_count * occ, TGM_WARPS * 32, smem, p));
     CU(cudaGetLastError());
     return DESMAN_OK;
 }
@@ -872,7 +890,7 @@ static int launch_tau_group_t(desman_ctx *c, const TauGroupParams &p, int warps)
     CU(cudaFuncSetAttribute(tau_group_kernel<GB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tau_group_kernel<GB>, warps * 32, smem) != cudaSuccess || occ < 1) occ = 1;
-    tau_group_kernel<GB><<<c->sm_count * occ, warps * 32, smem, c->stream>>>(p);
+    CU(launch_k(c, tau_group_kernel<GB>, c->sm_count * occ, warps * 32, smem, p));
     CU(cudaGetLastError());
     return DESMAN_OK;
 }
@@ -924,7 +942,7 @@ static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, boo
     CU(cudaFuncSetAttribute(tau_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         KSpan k(c, DESMAN_K_TAU);
-        tau_sample_kernel<<<grid, TAU_WARPS * 32, smem, c->stream>>>(p);
+        CU(launch_k(c, tau_sample_kernel, grid, TAU_WARPS * 32, smem, p));
     }
     CU(cudaGetLastError());
     return DESMAN_OK;
@@ -933,7 +951,7 @@ static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, boo
 template <int GP>
 static void launch_mu_t(desman_ctx *c, const MuParams &p, int grid)
 {
-    mu_stats_kernel<GP><<<grid, MU_WARPS * 32, 0, c->stream>>>(p);
+    launch_k(c, mu_stats_kernel<GP>, grid, MU_WARPS * 32, 0, p);
 }
 
 // K2b: one conditional-binomial chain per (pattern, sample, base) of the (synchronised) pattern table.
@@ -950,14 +968,14 @@ static int launch_mu_agg(desman_ctx *c, const double *gamma, const double *eta)
     while ((grid * MUB_WARPS) % nch) grid++;
     {
         KSpan k(c, DESMAN_K_MU, p.classM ? 2 : 1);
-        mu_binomial_kernel<<<grid, MUB_WARPS * 32, smem, c->stream>>>(p);
+        CU(launch_k(c, mu_binomial_kernel, grid, MUB_WARPS * 32, smem, p));
         if (p.classM) {
             const size_t smem2 = muc_smem_bytes(c->G);
             const int nch8 = (c->S + 7) / 8;
             long long want = (((long long)1 << c->G) * nch8 + MUB_WARPS - 1) / MUB_WARPS;
             int grid2 = (int)(want < (long long)c->sm_count * 4 ? want : (long long)c->sm_count * 4);
             if (grid2 < 1) grid2 = 1;
-            mu_class_kernel<<<grid2, MUB_WARPS * 32, smem2, c->stream>>>(p);
+            CU(launch_k(c, mu_class_kernel, grid2, MUB_WARPS * 32, smem2, p));
         }
     }
     CU(cudaGetLastError());
@@ -1059,7 +1077,7 @@ static int launch_draw(desman_ctx *c, const unsigned long long *stats, double *g
         int threads = ((c->S * c->G + 16 + 31) / 32) * 32;
         if (threads > DRAW_MAX_THREADS) threads = DRAW_MAX_THREADS;
         if (threads < 64) threads = 64;
-        draw_gamma_eta_kernel<<<1, threads, smem, c->stream>>>(p);
+        CU(launch_k(c, draw_gamma_eta_kernel, 1, threads, smem, p));
     }
     CU(cudaGetLastError());
     return DESMAN_OK;
@@ -1069,21 +1087,22 @@ struct StoreBufs { double *ll = nullptr, *lp = nullptr, *nch = nullptr, *gs = nu
 
 // ll (from the table) -> lp, stores, MAP bookkeeping.  gamma/eta: the state the likelihood is evaluated at.
 static int launch_finalize_only(desman_ctx *c, const unsigned long long *red, const double *gamma, const double *eta, int it,
-                                int star_mode, const StoreBufs &sb, bool store_ge);
+                                int star_mode, const StoreBufs &sb, bool store_ge, double *eta_commit = nullptr);
+// eta_commit: where the chain's eta lives when `eta` is the freshly drawn eta_new (committed by the finalize kernel: :347)
 static int launch_finalize(desman_ctx *c, const double *gamma, const double *eta, int it, int star_mode, const StoreBufs &sb,
-                           bool store_ge)
+                           bool store_ge, double *eta_commit = nullptr)
 {
     RET(launch_ll(c, gamma, eta));
     RET(allreduce_red(c));
-    return launch_finalize_only(c, c->red_i, gamma, eta, it, star_mode, sb, store_ge);
+    return launch_finalize_only(c, c->red_i, gamma, eta, it, star_mode, sb, store_ge, eta_commit);
 }
 // lp, stores, MAP bookkeeping from the (already summed) words red = [fixed-point ll, nchange]
 static int launch_finalize_only(desman_ctx *c, const unsigned long long *red, const double *gamma, const double *eta, int it,
-                                int star_mode, const StoreBufs &sb, bool store_ge)
+                                int star_mode, const StoreBufs &sb, bool store_ge, double *eta_commit)
 {
     FinalParams p;
     p.red_i = (const long long *)red; p.ll_const = c->ll_const_total; p.ll_inv_scale = 1.0 / c->ll_scale;
-    p.gamma = gamma; p.eta = eta; p.eta_commit = nullptr;
+    p.gamma = gamma; p.eta = eta; p.eta_commit = eta_commit;
     p.S = c->S; p.G = c->G; p.V_total = (double)c->V_total; p.alpha = c->alpha; p.delta = c->delta;
     p.lg_alphaG = lgamma(c->alpha * c->G); p.lg_alpha = lgamma(c->alpha);
     p.lg_delta4 = lgamma(4.0 * c->delta); p.lg_delta = lgamma(c->delta);
@@ -1096,8 +1115,8 @@ static int launch_finalize_only(desman_ctx *c, const unsigned long long *red, co
     p.V_local = (long long)c->V;
     {
         KSpan k(c, DESMAN_K_FINAL, 2);
-        finalize_sweep_kernel<<<1, 256, 0, c->stream>>>(p);
-        copy_tau_if_kernel<<<c->sm_count, 256, 0, c->stream>>>(c->tau, c->tau_star, (size_t)c->V * c->G, c->flag);
+        CU(launch_k(c, finalize_sweep_kernel, 1, 256, 0, p));
+        CU(launch_k(c, copy_tau_if_kernel, c->sm_count, 256, 0, (const uint8_t *)c->tau, c->tau_star, (size_t)c->V * c->G, (const int *)c->flag));
     }
     CU(cudaGetLastError());
     return DESMAN_OK;
@@ -1279,9 +1298,10 @@ extern "C" int desman_update(desman_ctx *c, int n_iter, double *gamma_store, dou
         } else RET(allreduce_stats(c));
         RET(launch_draw(c, c->stats, c->gamma, c->eta_new));            // sampleGamma (:342) + sampleEta's draw (:347)
         if (!c->fixed_tau) RET(launch_tau(c, c->gamma, c->eta, true, true, (uint32_t)it));       // sample_tau (:345), old eta (nchange cleared by sync_table)
-        CU(cudaMemcpyAsync(c->eta, c->eta_new, 16 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));   // eta <- new (:347)
-        if (lagged) RET(launch_ll(c, c->gamma, c->eta));                // sum n*log p of sweep it; reduced with the next exchange
-        else RET(launch_finalize(c, c->gamma, c->eta, it, 0, sb, true));     // ll, lp, stores, star (:349-358)
+        if (lagged) {
+            CU(cudaMemcpyAsync(c->eta, c->eta_new, 16 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));   // eta <- new (:347)
+            RET(launch_ll(c, c->gamma, c->eta));                        // sum n*log p of sweep it; reduced with the next exchange
+        } else RET(launch_finalize(c, c->gamma, c->eta_new, it, 0, sb, true, c->eta));   // eta <- new (:347); ll, lp, stores, star (:349-358)
         sweep_end(c);
         c->sweep++;
     }
@@ -1499,7 +1519,7 @@ extern "C" int desman_set_option(desman_ctx *c, const char *name, int64_t value)
     if (!strcmp(name, "tau_exact")) { c->tau_exact = value ? 1 : 0; return DESMAN_OK; }
     if (!strcmp(name, "fixed_tau")) { c->fixed_tau = value ? 1 : 0; return DESMAN_OK; }
     if (!strcmp(name, "mu_mode")) { c->mu_mode = (value == 0 || value == 1) ? (int)value : 2; return DESMAN_OK; }
-    if (!strcmp(name, "tau_group_mma")) { c->tau_group_mma = value ? 1 : 0; return DESMAN_OK; }
+    if (!strcmp(name, "pdl")) { c->pdl = value ? 1 : 0; return DESMAN_OK; }
     if (!strcmp(name, "tau_group_mma")) { c->tau_group_mma = value ? 1 : 0; return DESMAN_OK; }
     if (!strcmp(name, "tau_group")) { c->tau_group = (value == 0 || value == 1) ? (int)value : 2; c->agg_valid = false; return DESMAN_OK; }
     return fail(DESMAN_EINVAL, "unknown option '%s'", name);
@@ -1530,6 +1550,20 @@ extern "C" int desman_get_group_stats(desman_ctx *c, int64_t out[8])
 }
 
 // ------------------------------------------------------------------------------------------ measurement
+#ifdef KPROF
+// diagnosis build only (tools/kprof.py): copy out / reset the device-side timeline records
+extern "C" int desman_kprof_dump(void *out, int cap, int reset)
+{
+    unsigned int n = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&n, g_krec_n, sizeof(n));
+    if (n > KREC_CAP) n = KREC_CAP;
+    if ((int)n > cap) n = cap;
+    if (out && n) cudaMemcpyFromSymbol(out, g_krec, (size_t)n * sizeof(KRec));
+    if (reset) { const unsigned int z = 0; cudaMemcpyToSymbol(g_krec_n, &z, sizeof(z)); }
+    return (int)n;
+}
+#endif
 extern "C" int desman_set_profiling(desman_ctx *c, int per_kernel_events, int flush_l2_between_sweeps)
 {
     c->prof_kernels = per_kernel_events; c->prof_flush = flush_l2_between_sweeps;

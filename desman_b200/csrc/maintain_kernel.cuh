@@ -52,6 +52,8 @@ __device__ __forceinline__ int4 block_excl_scan4(int4 v, int4 &tot, int (*sh)[4]
 
 __global__ void __launch_bounds__(MAINT_THREADS) table_maintain_kernel(MaintParams p)
 {
+    pdl_enter();
+    KPROF_SCOPE(KP_MAINT);
     cg::grid_group grid = cg::this_grid();
     __shared__ int sh[MAINT_THREADS / 32][4];
     const AggTable &t = p.a.t;

@@ -127,6 +127,8 @@ struct DrawParams {
 
 __global__ void __launch_bounds__(DRAW_MAX_THREADS) draw_gamma_eta_kernel(DrawParams p)
 {
+    pdl_enter();
+    KPROF_SCOPE(KP_DRAW);
     extern __shared__ double y[];  // [S*G + 16]
     const int S = p.S, G = p.G, nG = S * G;
     const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
@@ -190,6 +192,8 @@ struct FinalParams {
 // logPosterior (HaploSNP_Sampler.py:444-461) + star bookkeeping (:326-332, :351-358)
 __global__ void __launch_bounds__(256) finalize_sweep_kernel(FinalParams p)
 {
+    pdl_enter();
+    KPROF_SCOPE(KP_FIN);
     __shared__ double sh[256];
     const int nG = p.S * p.G;
     double acc = 0.0;
@@ -248,6 +252,8 @@ __global__ void __launch_bounds__(256) finalize_sweep_kernel(FinalParams p)
 __global__ void copy_tau_if_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t n,
                                    const int *__restrict__ flag)
 {
+    pdl_enter();
+    KPROF_SCOPE(KP_COPY);
     if (*flag == 0) return;
     // 16-byte words (cudaMalloc'ed buffers are 256-byte aligned), byte tail
     const size_t n16 = n / 16, i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x, st = (size_t)gridDim.x * blockDim.x;

@@ -123,6 +123,8 @@ __device__ __forceinline__ int agg_move_site(const AggTable &t, unsigned long lo
 // accumulated in 64-bit fixed point, so the total does not depend on slot numbering or scheduling (bitwise reproducible).
 __global__ void __launch_bounds__(256) ll_table_kernel(MuAggParams p)
 {
+    pdl_enter();
+    KPROF_SCOPE(KP_LL);
     __shared__ double eta_s[16];
     if (threadIdx.x < 16) eta_s[threadIdx.x] = p.eta[threadIdx.x];
     __syncthreads();
@@ -358,6 +360,8 @@ __device__ __forceinline__ void mub_item(const MuAggParams &p, BinStream &st, in
 
 __global__ void __launch_bounds__(MUB_WARPS * 32, MUB_MIN_BLOCKS) mu_binomial_kernel(MuAggParams p)
 {
+    pdl_enter();
+    KPROF_SCOPE(KP_MUB);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = p.S, G = p.G;
     double *eta_s = reinterpret_cast<double *>(smem_raw);                    // [16]
@@ -419,6 +423,8 @@ __global__ void __launch_bounds__(MUB_WARPS * 32, MUB_MIN_BLOCKS) mu_binomial_ke
 // = heap number of the node - 1 (root 1, children 2i, 2i+1).  One warp per (mask, 8 samples); mirrors oracle_mu_stats_agg.
 __global__ void __launch_bounds__(MUB_WARPS * 32, MUB_MIN_BLOCKS) mu_class_kernel(MuAggParams p)
 {
+    pdl_enter();
+    KPROF_SCOPE(KP_MUC);
     __shared__ long long nodeM_s[MUB_WARPS][8][32];          // reads at the nodes of the current item, per sample
     __shared__ int pos2g_s[MUB_WARPS][32];
     const int S = p.S, G = p.G;

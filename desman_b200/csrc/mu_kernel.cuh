@@ -43,6 +43,7 @@ __device__ __forceinline__ uint32_t ge_carry(uint32_t x, unsigned long long neg_
 template <int GP>
 __global__ void __launch_bounds__(MU_WARPS * 32, 2) mu_stats_kernel(MuParams p)
 {
+    pdl_enter();
     __shared__ double eta_s[16];
     const int S = p.S, G = p.G;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;

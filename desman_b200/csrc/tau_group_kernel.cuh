@@ -110,6 +110,7 @@ __device__ __forceinline__ void tg_step(float (&acc)[4 * NJ], const float4 (&n)[
 template <int GB>
 __global__ void __launch_bounds__(TG_MAX_WARPS * 32, 1) tau_group_kernel(TauGroupParams p)
 {
+    pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int *gctl = p.grp.gctl;
     if (!(gctl[GC_HAVE] && gctl[GC_CALM])) return;
@@ -372,6 +373,8 @@ __device__ __forceinline__ void tgm_group(float (&ch)[MT][2][4], float (&cl)[MT]
 template <int MT>
 __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGroupParams p)
 {
+    pdl_enter();
+    KPROF_SCOPE(KP_TGM);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int *gctl = p.grp.gctl;
     if (!(gctl[GC_HAVE] && gctl[GC_CALM])) return;
@@ -446,6 +449,9 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
         if (tid == 0) l2_prefetch_row(p.countsf + (size_t)nxt0.y * S, (uint32_t)min(nxt0.z, ROUND) * row_bytes);
     }
 
+#ifdef KPROF
+    if (tid == 0) krec_put(KP_TGM_PRO, (int)blockIdx.x, 0, nitems, gtimer(), 0);
+#endif
 #ifdef TGM_PROFILE
     long long t_build = 0, t_pass = 0, t_sync1 = 0, t_sync2 = 0, t_all0 = clock64(), n_it = 0, n_sites = 0;
 #define TGM_T(x) const long long x = clock64()

@@ -240,6 +240,8 @@ __device__ __noinline__ int tau_bracket_decide(const int4 *tile, const double2 *
 
 __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams p)
 {
+    pdl_enter();
+    KPROF_SCOPE(KP_TAU);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = p.S, G = p.G;
     const int Sp = (S + 31) & ~31;
@@ -287,6 +289,14 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
     const float c1 = TAU_C1(nch), ccan = TAU_CANCEL(G);
     const float cancel0 = ccan / fmaxf(qmin, TAU_QMIN);                     // a-priori bound of the P/q amplification
     unsigned int flips = 0, n1 = 0, n2 = 0, n3 = 0;
+#ifdef KPROF
+    const unsigned long long kp_pro = gtimer();
+    unsigned long long kp_stage = 0, kp_steps = 0, kp_move = 0, kp_first = 0;
+    int kp_sites = 0;
+#define KP_T(x) const unsigned long long x = gtimer()
+#else
+#define KP_T(x)
+#endif
 
     int nsite = p.V, nwork = 0;
     bool listed = false;
@@ -303,6 +313,7 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
             if (i < nwork) { const uint2 e = p.work[i]; v = (int)e.x; todo = e.y; }
             else v = p.singles[i - nwork];
         }
+        KP_T(kp0);
         const int4 *src = p.counts + (size_t)v * S;
         uint64_t code = load_tau_code(p.tau + (size_t)v * G, G, lane);
         const uint64_t code_in = code;
@@ -338,6 +349,7 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
             mlP = fmaxf(mlP, fmaxf(fmaxf(fabsf(l0), fabsf(l1)), fmaxf(fabsf(l2), fabsf(l3))));
         }
         __syncwarp();
+        KP_T(kp1);
 
         for (int g = 0; g < G; g++) {
             if (!((todo >> g) & 1u) && code == code_in) { n1++; continue; }   // decided "stay" by the screening pass
@@ -414,6 +426,7 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
                 }
             }
         }
+        KP_T(kp2);
         if (code != code_in) {
             if (lane < G) p.tau[(size_t)v * G + lane] = (uint8_t)code_get(code, lane);
             if (p.agg.N) {
@@ -423,7 +436,13 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
         }
 
         __syncwarp();
+#ifdef KPROF
+        { const unsigned long long kp3 = gtimer(); if (!kp_sites) kp_first = kp0; kp_sites++; kp_stage += kp1 - kp0; kp_steps += kp2 - kp1; kp_move += kp3 - kp2; }
+#endif
     }
+#ifdef KPROF
+    if (lane == 0) krec_put(KP_TAU_WARP, (int)blockIdx.x, wib, (int)(kp_sites | (n2 << 8) | (n3 << 20) | (flips << 24)), kp_pro, gtimer(), kp_first, kp_stage, kp_steps, kp_move);
+#endif
 
     if (lane == 0 && flips) atomicAdd(p.nchange, (unsigned long long)flips);
     if (lane == 0 && p.tier_counts) {

@@ -1,0 +1,101 @@
+"""Timeline of a sweep from %globaltimer stamps recorded by a -DKPROF build (diagnosis only; the product build has none of it).
+
+    python tools/kprof.py --build                       (here: build/libdesman_b200_kprof.so)
+    DESMAN_B200_LIB=build/libdesman_b200_kprof.so python tools/kprof.py > gpurun_out/kprof.txt   (on the GPU box)
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "build", "libdesman_b200_kprof.so")
+
+if "--build" in sys.argv:
+    from desman_b200 import build as b
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    cmd = ["nvcc"] + b.FLAGS + ["-DKPROF", "-o", OUT, b.SRC, "-ldl"]
+    subprocess.run(cmd, check=True, capture_output=True)
+    print(OUT)
+    sys.exit(0)
+
+from desman_b200 import _lib, engine
+from desman_b200.synth import CHAIN_SEED, synth_counts
+
+NAMES = ["maintain", "mu_binomial", "mu_class", "draw", "tau_group_mma", "tau_sample", "ll_table", "finalize", "copy_tau_if",
+         "tau_warp", "tgm_prologue"]
+REC = np.dtype([("kid", "i4"), ("cta", "i4"), ("warp", "i4"), ("x", "i4"), ("t0", "u8"), ("t1", "u8"), ("a", "u8"), ("b", "u8"),
+                ("c", "u8"), ("d", "u8")])
+
+flush = "--no-flush" not in sys.argv
+p = synth_counts(100000, 64, 8)
+e = engine.Engine(0, seed=CHAIN_SEED)
+e.set_counts(p["counts"]); e.set_state(None, p["gamma0"], p["eta0"], G=8); e.set_tau_index(p["tau0"])
+e.set_profiling(False, flush)
+e.update(20)
+L = _lib.lib()
+L.desman_kprof_dump.restype = ctypes.c_int
+L.desman_kprof_dump.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+L.desman_kprof_dump(None, 0, 1)
+NS = 4
+e.update(NS)
+e.synchronize()
+buf = np.zeros(1 << 18, dtype=REC)
+n = L.desman_kprof_dump(buf.ctypes.data, len(buf), 1)
+r = buf[:n]
+print("records", n, "sweep ms", e.get_timing()["elapsed_ms"] / NS, e.get_group_stats())
+t_base = int(r["t0"].min())
+# launches: records of one kernel id whose [t0,t1] chain overlaps
+rows = []
+for kid in range(9):
+    k = r[r["kid"] == kid]
+    if not len(k):
+        continue
+    k = np.sort(k, order="t0")
+    cur = None
+    for x in k:
+        if cur is None or int(x["t0"]) > cur["exit"]:
+            cur = dict(kid=kid, entry=int(x["t0"]), exit=int(x["t1"]), first_exit=int(x["t1"]), last_entry=int(x["t0"]), n=0)
+            rows.append(cur)
+        cur["exit"] = max(cur["exit"], int(x["t1"])); cur["first_exit"] = min(cur["first_exit"], int(x["t1"]))
+        cur["last_entry"] = max(cur["last_entry"], int(x["t0"])); cur["n"] += 1
+rows.sort(key=lambda d: d["entry"])
+prev = None
+for d in rows:
+    print("%-14s start %9.2f us  gap %6.2f  dur %7.2f  first-exit %7.2f  last-entry +%5.2f  ctas %d" % (
+        NAMES[d["kid"]], (d["entry"] - t_base) / 1e3, ((d["entry"] - prev) / 1e3) if prev else 0.0, (d["exit"] - d["entry"]) / 1e3,
+        (d["first_exit"] - d["entry"]) / 1e3, (d["last_entry"] - d["entry"]) / 1e3, d["n"]))
+    prev = d["exit"]
+# the last tau_sample launch: per-warp phases
+ts = [d for d in rows if d["kid"] == 5][-1]
+w = r[(r["kid"] == 9) & (r["t0"] >= ts["entry"]) & (r["t1"] <= ts["exit"])]
+print("tau_sample last launch: warps", len(w), "launch entry->exit us", (ts["exit"] - ts["entry"]) / 1e3)
+pro = (w["t0"].astype(np.int64) - ts["entry"]) / 1e3
+end = (w["t1"].astype(np.int64) - ts["entry"]) / 1e3
+sites = w["x"] & 0xff; n2 = (w["x"] >> 8) & 0xfff; n3 = (w["x"] >> 20) & 0xf; fl = (w["x"] >> 24) & 0xff
+print("prologue done  us: min %.2f med %.2f max %.2f" % (pro.min(), np.median(pro), pro.max()))
+print("warp end       us: min %.2f med %.2f p90 %.2f max %.2f" % (end.min(), np.median(end), np.percentile(end, 90), end.max()))
+print("sites per warp: ", np.bincount(sites)[:6], " tier3 warps", int((n3 > 0).sum()), " flips", int(fl.sum()))
+has = sites > 0
+for nm in ("b", "c", "d"):
+    v = w[nm][has] / np.maximum(sites[has], 1) / 1e3
+    print("per-site %s us: med %.2f p90 %.2f max %.2f" % ({"b": "stage", "c": "steps", "d": "move"}[nm], np.median(v), np.percentile(v, 90), v.max()))
+order = np.argsort(end)[-8:]
+for i in order:
+    print("  slow warp cta %d w %d: pro %.2f end %.2f sites %d n2 %d n3 %d flips %d stage %.2f steps %.2f move %.2f" % (
+        w["cta"][i], w["warp"][i], pro[i], end[i], sites[i], n2[i], n3[i], fl[i], w["b"][i] / 1e3, w["c"][i] / 1e3, w["d"][i] / 1e3))
+# the last tau_group launch: prologue and exits
+tg = [d for d in rows if d["kid"] == 4][-1]
+g = r[(r["kid"] == 4) & (r["t0"] >= tg["entry"]) & (r["t1"] <= tg["exit"])]
+gp = r[(r["kid"] == 10) & (r["t0"] >= tg["entry"]) & (r["t0"] <= tg["exit"])]
+ex = (g["t1"].astype(np.int64) - tg["entry"]) / 1e3
+print("tau_group last launch: ctas", len(g), "prologue done us: med %.2f max %.2f" % (np.median((gp["t0"].astype(np.int64) - tg["entry"]) / 1e3), ((gp["t0"].astype(np.int64) - tg["entry"]) / 1e3).max()))
+print("cta exit us: min %.2f p10 %.2f med %.2f p90 %.2f max %.2f" % (ex.min(), np.percentile(ex, 10), np.median(ex), np.percentile(ex, 90), ex.max()))
+for kid in (1, 2):
+    m = [d for d in rows if d["kid"] == kid][-1]
+    g = r[(r["kid"] == kid) & (r["t0"] >= m["entry"]) & (r["t1"] <= m["exit"])]
+    ex = (g["t1"].astype(np.int64) - m["entry"]) / 1e3
+    print(NAMES[kid], "cta exit us: min %.2f p10 %.2f med %.2f p90 %.2f max %.2f" % (ex.min(), np.percentile(ex, 10), np.median(ex), np.percentile(ex, 90), ex.max()))
