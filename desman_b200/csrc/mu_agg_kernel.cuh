@@ -296,6 +296,7 @@ __device__ __forceinline__ void mub_item(const MuAggParams &p, BinStream &st, in
     }
     const int lastk = cmask[3] ? 3 : cmask[2] ? 2 : cmask[1] ? 1 : 0;
     long long M[4] = {0, 0, 0, 0};
+
     // ---- phase A
 #pragma unroll
     for (int a = 0; a < 4; a++) {
@@ -358,6 +359,49 @@ __device__ __forceinline__ void mub_item(const MuAggParams &p, BinStream &st, in
     }
 }
 
+// The same phase A for ONE observed base a of (slot, s), n = N[slot][s][a] reads (merged phase B only): the class totals of the
+// four bases meet in classM / accS by addition, so the bases of a (slot, sample) are independent work items -- one draw per lane
+// and item instead of four in a row.  Operation for operation the arithmetic of mub_item.
+__device__ __forceinline__ void mub_item_base(const MuAggParams &p, BinStream &st, unsigned long long code, int a, long long n, int s,
+                                              int lane, int G, const double *eta_s, unsigned long long *accS, unsigned long long *eS)
+{
+    if (n <= 0) return;
+    const int S = p.S;
+    st.c0 = (uint32_t)code; st.c1 = (uint32_t)(code >> 32);
+    uint32_t cmask[4] = {0u, 0u, 0u, 0u};
+    double Gm[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int g = 0; g < G; g++) {
+        const int b = code_get(code, g);
+        const double gm = p.gamma[(size_t)s * G + g];
+#pragma unroll
+        for (int k = 0; k < 4; k++) if (b == k) { cmask[k] |= 1u << g; Gm[k] = __dadd_rn(Gm[k], gm); }
+    }
+    const int lastk = cmask[3] ? 3 : cmask[2] ? 2 : cmask[1] ? 1 : 0;
+    st.c3 = ((uint32_t)STAGE_MUB << 28) | ((uint32_t)a << 26) | (uint32_t)s;
+    double W[4], suf[5];
+    suf[4] = 0.0;
+#pragma unroll
+    for (int k = 3; k >= 0; k--) {
+        W[k] = cmask[k] ? __dmul_rn(eta_s[4 * k + a], Gm[k]) : 0.0;
+        suf[k] = cmask[k] ? __dadd_rn(W[k], suf[k + 1]) : suf[k + 1];
+    }
+    long long rem = n;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (!cmask[k]) continue;
+        long long x;
+        if (k == lastk) x = rem;
+        else if (rem == 0) x = 0;
+        else x = binomial_draw_d(rem, __ddiv_rn(W[k], suf[k]), __ddiv_rn(suf[k + 1], suf[k]), st, k);
+        rem -= x;
+        if (x) {
+            eS[(a * 4 + k) * 32 + lane] += (unsigned long long)x;
+            if ((cmask[k] & (cmask[k] - 1u)) == 0u) accS[(31 - __clz(cmask[k])) * 32 + lane] += (unsigned long long)x;
+            else atomicAdd(p.classM + (size_t)cmask[k] * S + s, (unsigned long long)x);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(MUB_WARPS * 32, MUB_MIN_BLOCKS) mu_binomial_kernel(MuAggParams p)
 {
     pdl_enter();
@@ -389,18 +433,55 @@ __global__ void __launch_bounds__(MUB_WARPS * 32, MUB_MIN_BLOCKS) mu_binomial_ke
     // rejection, number of attempts), and a static deal left a quarter of the SM time idle at the tail.  The statistics are
     // integer sums, so the schedule does not change the result.
     const bool dyn = nch <= MUB_CURSORS;
-    int item = gw / nch;
-    while (true) {
-        if (dyn) {
-            if (lane == 0) item = atomicAdd(p.t.ctl + 4 + chunk, 1);
-            item = __shfl_sync(DESMAN_FULL_MASK, item, 0);
+    if (dyn && p.classM) {
+        // Merged within-class split: an item is (slot, observed base) -- a lane's four draws of a slot were a sequential chain of
+        // ~10 us and a warp saw 1.3 such items per sweep at C3 (first CTA done at 19 us, last at 34 us, tools/kprof.py).  The
+        // ticket -> code -> count chain of an item (three dependent memory latencies, ~3 us) is taken off the critical path: the
+        // ticket of item i+2 is drawn and the operands of item i+1 are fetched before item i is processed.
+        const int nitem = 4 * P;
+        // the first item of a warp is its own number within the chunk (no atomic storm at the start); tickets follow from there
+        const int first = gw / nch, nfirst = nw / nch;
+        auto draw_ticket = [&]() { int t = 0; if (lane == 0) t = nfirst + atomicAdd(p.t.ctl + 4 + chunk, 1); return t; };
+        auto fetch = [&](int it, unsigned long long &code, long long &n) {
+            code = 0ull; n = 0;
+            if (it < nitem) {
+                code = p.t.slot_code[it >> 2];
+                if (valid) n = (long long)p.t.N[((size_t)(it >> 2) * S + s) * 4 + (it & 3)];
+            }
+        };
+        int it1 = first;
+        int raw2 = draw_ticket();
+        unsigned long long code1; long long n1;
+        fetch(it1, code1, n1);
+#ifdef KPROF
+        unsigned long long kp_items = 0; const unsigned long long kp_t0 = gtimer();
+#endif
+        while (it1 < nitem) {
+            const int cur = it1;
+            const unsigned long long code = code1;
+            const long long n = n1;
+            it1 = __shfl_sync(DESMAN_FULL_MASK, raw2, 0);
+            fetch(it1, code1, n1);
+            raw2 = draw_ticket();
+            mub_item_base(p, st, code, cur & 3, n, s, lane, G, eta_s, accS, eS);
+#ifdef KPROF
+            kp_items++;
+#endif
         }
-        if (item >= P) break;
-        const int item_cur = item;
-        if (!dyn) item += nw / nch;
-        {
-            const int item = item_cur;
-            mub_item(p, st, item, valid, s, lane, G, eta_s, wS, sufS, accS, eS);
+#ifdef KPROF
+        if (lane == 0) krec_put(KP_MUB_WARP, (int)blockIdx.x, wib, (int)kp_items, kp_t0, gtimer(), 0, 0, 0, 0);
+#endif
+    } else {
+        int item = gw / nch;
+        while (true) {
+            if (dyn) {
+                if (lane == 0) item = atomicAdd(p.t.ctl + 4 + chunk, 1);
+                item = __shfl_sync(DESMAN_FULL_MASK, item, 0);
+            }
+            if (item >= P) break;
+            const int item_cur = item;
+            if (!dyn) item += nw / nch;
+            mub_item(p, st, item_cur, valid, s, lane, G, eta_s, wS, sufS, accS, eS);
         }
     }
     __syncwarp();

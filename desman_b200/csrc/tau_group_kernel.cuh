@@ -442,7 +442,10 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
     unsigned int n_decided = 0;
     constexpr int ROUND = TGM_WARPS * TG_PASS_SITES;      // sites the CTA contracts per round of passes
 
-    // the work items of this CTA: blockIdx.x, + gridDim.x, ...; the record of the next one is fetched an item ahead
+    // the work items of this CTA: blockIdx.x first, then tickets from the sweep's cursor (items are numbered long first, so the
+    // hand-out is longest-processing-time-first: the static deal left CTAs between 28 and 57 us busy, tools/kprof.py).  The
+    // ticket of the next item is drawn while the table of this one is built; its record is fetched during the contraction.
+    __shared__ int next_item_s;
     int4 nxt0 = make_int4(0, 0, 0, 0), nxt1 = nxt0;
     if ((int)blockIdx.x < nitems) {
         nxt0 = p.grp.items[2 * blockIdx.x]; nxt1 = p.grp.items[2 * blockIdx.x + 1];
@@ -458,14 +461,15 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
 #else
 #define TGM_T(x)
 #endif
-    int iter = 0;
-    for (int it = blockIdx.x; it < nitems; it += gridDim.x, iter++) {
+    int it = blockIdx.x;
+    while (it < nitems) {
         TGM_T(tp0);
+        int ticket = 0;
+        if (tid == 0) ticket = (int)gridDim.x + atomicAdd(p.grp.gctl + GC_CURSOR, 1);
         const int4 item = nxt0, item1 = nxt1;
         const int slot = item.x, begin = item.y, count = item.z;
         const uint64_t code = ((uint64_t)(unsigned int)item1.y << 32) | (unsigned int)item1.x;
         const float4 *rows = p.countsf + (size_t)begin * S;            // the item's count rows are contiguous
-        if (it + (int)gridDim.x < nitems) { nxt0 = p.grp.items[2 * (it + gridDim.x)]; nxt1 = p.grp.items[2 * (it + gridDim.x) + 1]; }
         int base = wib * TG_PASS_SITES;                                 // first pass of this warp
 
         // ---- the pattern's table: Wd[s][g*3+j][b] = lg2(base_sb + eta[a_j][b]*gamma[s][g]) - lg2(P_sb), a_j = (cur_g+1+j)&3
@@ -505,10 +509,18 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
             }
         }
         // first round of the next item into L2 while this one is contracted
-        if (tid == 0 && it + (int)gridDim.x < nitems) l2_prefetch_row(p.countsf + (size_t)nxt0.y * S, (uint32_t)min(nxt0.z, ROUND) * row_bytes);
+        if (tid == 0) {
+            next_item_s = ticket;
+            if (ticket < nitems) {
+                const int4 r = p.grp.items[2 * ticket];
+                l2_prefetch_row(p.countsf + (size_t)r.y * S, (uint32_t)min(r.z, ROUND) * row_bytes);
+            }
+        }
         TGM_T(tp1);
         __syncthreads();
         TGM_T(tp2);
+        const int it_next = next_item_s;
+        if (it_next < nitems) { nxt0 = p.grp.items[2 * it_next]; nxt1 = p.grp.items[2 * it_next + 1]; }
 
         // ---- contraction of one 16-site pass over the 4-sample groups [qlo, qhi): D (hi + lo parts) -> acc[mt][nt][4]
         auto contract = [&](int pbase, int qlo, int qhi, float (&acc)[MT][2][4]) {
@@ -648,6 +660,7 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
         }
         TGM_T(tp3);
         __syncthreads();
+        it = it_next;
 #ifdef TGM_PROFILE
         { const long long tp4 = clock64(); t_build += tp1 - tp0; t_sync1 += tp2 - tp1; t_pass += tp3 - tp2; t_sync2 += tp4 - tp3; n_it++; n_sites += count; }
 #endif

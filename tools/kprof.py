@@ -26,7 +26,7 @@ from desman_b200 import _lib, engine
 from desman_b200.synth import CHAIN_SEED, synth_counts
 
 NAMES = ["maintain", "mu_binomial", "mu_class", "draw", "tau_group_mma", "tau_sample", "ll_table", "finalize", "copy_tau_if",
-         "tau_warp", "tgm_prologue"]
+         "tau_warp", "tgm_prologue", "mub_warp"]
 REC = np.dtype([("kid", "i4"), ("cta", "i4"), ("warp", "i4"), ("x", "i4"), ("t0", "u8"), ("t1", "u8"), ("a", "u8"), ("b", "u8"),
                 ("c", "u8"), ("d", "u8")])
 
@@ -99,3 +99,11 @@ for kid in (1, 2):
     g = r[(r["kid"] == kid) & (r["t0"] >= m["entry"]) & (r["t1"] <= m["exit"])]
     ex = (g["t1"].astype(np.int64) - m["entry"]) / 1e3
     print(NAMES[kid], "cta exit us: min %.2f p10 %.2f med %.2f p90 %.2f max %.2f" % (ex.min(), np.percentile(ex, 10), np.median(ex), np.percentile(ex, 90), ex.max()))
+mb = [d for d in rows if d["kid"] == 1][-1]
+w = r[(r["kid"] == 11) & (r["t0"] >= mb["entry"]) & (r["t1"] <= mb["exit"] + 2000)]
+if len(w):
+    it = np.maximum(w["x"], 1)
+    print("mu_binomial warps %d items/warp med %d max %d | per warp us: ticket med %.2f  load med %.2f  draw med %.2f  total med %.2f max %.2f" % (
+        len(w), np.median(w["x"]), w["x"].max(), np.median(w["a"]) / 1e3, np.median(w["b"]) / 1e3, np.median(w["c"]) / 1e3,
+        np.median(w["t1"].astype(np.int64) - w["t0"].astype(np.int64)) / 1e3, (w["t1"].astype(np.int64) - w["t0"].astype(np.int64)).max() / 1e3))
+    print("  per item us (lane 0): ticket %.2f load %.2f draw %.2f" % (np.median(w["a"] / it) / 1e3, np.median(w["b"] / it) / 1e3, np.median(w["c"] / it) / 1e3))
