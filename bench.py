@@ -263,7 +263,7 @@ def run_b200(args):
     }
     if world == 1 and not args.no_cpu:
         out["cpu_baseline"] = cpu_baseline(p, V, S, G, budget_s=args.cpu_seconds)
-    print(json.dumps(out))
+    emit(out)
 
 
 # ---------------------------------------------------------------------------------------------- CPU arms
@@ -343,10 +343,24 @@ def run_reference(args):
            "cpu_baseline": {"value": value, "unit": "sweeps/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(out)
+
+
+def emit(out):
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(out) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    # Libraries below us may write to fd 1 (NCCL prints its version banner there when NCCL_DEBUG is set in the box's
+    # environment): everything but the result line goes to stderr.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
