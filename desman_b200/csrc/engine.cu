@@ -742,6 +742,7 @@ static MuAggParams agg_params(desman_ctx *c, const double *gamma, const double *
     p.t = agg_table(c);
     p.sum_mu = c->stats; p.esum = c->stats + (size_t)c->S * c->G;
     p.ll_scale = c->ll_scale; p.ll_fx = c->red_i;
+    p.eta_commit = nullptr;
     p.classM = (c->G <= MUC_MAX_G && c->classM_G == c->G && c->classM_S == c->S) ? c->agg_classM : nullptr;
     return p;
 }
@@ -840,9 +841,10 @@ static int sync_table(desman_ctx *c)
 }
 
 // sum n*log p of the current device tau under (gamma, eta) into red_i[0] (fixed point, cleared by sync_table)
-static int launch_ll(desman_ctx *c, const double *gamma, const double *eta)
+static int launch_ll(desman_ctx *c, const double *gamma, const double *eta, double *eta_commit = nullptr)
 {
     MuAggParams p = agg_params(c, gamma, eta);
+    p.eta_commit = eta_commit;
     {
         KSpan k(c, DESMAN_K_FINAL);
         CU(launch_k(c, ll_table_kernel, c->sm_count * 4, 256, 0, p));       // ~one (slot, 32 samples) item per warp: a latency chain
@@ -1298,10 +1300,8 @@ extern "C" int desman_update(desman_ctx *c, int n_iter, double *gamma_store, dou
         } else RET(allreduce_stats(c));
         RET(launch_draw(c, c->stats, c->gamma, c->eta_new));            // sampleGamma (:342) + sampleEta's draw (:347)
         if (!c->fixed_tau) RET(launch_tau(c, c->gamma, c->eta, true, true, (uint32_t)it));       // sample_tau (:345), old eta (nchange cleared by sync_table)
-        if (lagged) {
-            CU(cudaMemcpyAsync(c->eta, c->eta_new, 16 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));   // eta <- new (:347)
-            RET(launch_ll(c, c->gamma, c->eta));                        // sum n*log p of sweep it; reduced with the next exchange
-        } else RET(launch_finalize(c, c->gamma, c->eta_new, it, 0, sb, true, c->eta));   // eta <- new (:347); ll, lp, stores, star (:349-358)
+        if (lagged) RET(launch_ll(c, c->gamma, c->eta_new, c->eta));     // eta <- new (:347); sum n*log p of sweep it, reduced with the next exchange
+        else RET(launch_finalize(c, c->gamma, c->eta_new, it, 0, sb, true, c->eta));   // eta <- new (:347); ll, lp, stores, star (:349-358)
         sweep_end(c);
         c->sweep++;
     }

@@ -67,6 +67,7 @@ struct MuAggParams {
     unsigned long long *classM;  // [2^G][S] reads per (set of strains, sample) awaiting their within-class split (G <= MUC_MAX_G), or null
     double ll_scale;             // 2^k of the fixed-point log-likelihood accumulator
     unsigned long long *ll_fx;   // += llrint(sum n*log p * 2^k)  (two's complement)
+    double *eta_commit;          // ll_table_kernel: if non-null, eta_commit[0..15] = eta (the chain's eta <- eta_new, :347)
 };
 
 __device__ __forceinline__ unsigned int mix_code(unsigned long long x)
@@ -126,7 +127,10 @@ __global__ void __launch_bounds__(256) ll_table_kernel(MuAggParams p)
     pdl_enter();
     KPROF_SCOPE(KP_LL);
     __shared__ double eta_s[16];
-    if (threadIdx.x < 16) eta_s[threadIdx.x] = p.eta[threadIdx.x];
+    if (threadIdx.x < 16) {
+        eta_s[threadIdx.x] = p.eta[threadIdx.x];
+        if (blockIdx.x == 0 && p.eta_commit) p.eta_commit[threadIdx.x] = eta_s[threadIdx.x];
+    }
     __syncthreads();
     const int S = p.S, G = p.G, lane = threadIdx.x & 31;
     const int nch = (S + 31) >> 5;
