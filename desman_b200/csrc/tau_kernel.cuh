@@ -309,9 +309,14 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
     for (int i = gw; i < nsite; i += nw) {
         int v = i;
         uint32_t todo = 0xffffffffu;                 // strains the screening pass did not decide
+        bool screened = false;                       // todo comes from the gap test of the screening pass
         if (listed) {
-            if (i < nwork) { const uint2 e = p.work[i]; v = (int)e.x; todo = e.y; }
-            else v = p.singles[i - nwork];
+            if (i < nwork) {
+                const uint2 e = p.work[i]; v = (int)e.x; todo = e.y;
+                // a full mask is what orphans of their group (and sites with a zero MT word) get without any test: their
+                // steps are ordinary ones, mostly settled by the cheap gap test, and must not be sent straight to the brackets
+                screened = todo != ((G >= 32) ? 0xffffffffu : ((1u << G) - 1u));
+            } else v = p.singles[i - nwork];
         }
         KP_T(kp0);
         const int4 *src = p.counts + (size_t)v * S;
@@ -359,7 +364,7 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
             const double u = p.words ? (double)w / 4294967296.0 : ((double)w + 0.5) / 4294967296.0;
             int t = -1;
             const bool usable = fast_ok && (w != 0u || !p.words);
-            if (usable && listed && code == code_in) {
+            if (usable && screened && code == code_in) {
                 // a step the screening pass left open: its gap test already failed on the same kind of sums, so go straight
                 // to the tracked sums and the brackets (which also settle a decisive flip)
                 t = tau_bracket_decide(tile, Pw, Kw, gT + g * Sp, gT32 + g * Sp, eta_s + 4 * cur, eta32, cur, nch, lane, nlane, mlP,
