@@ -10,6 +10,12 @@
 // pdl_enter(): wait until the preceding grid has completed and its writes are visible, then allow the next grid of the chain
 // to be scheduled (its CTAs become resident as this grid's CTAs retire and park in their own wait).  Without the launch
 // attribute both instructions are no-ops.  Nothing produced by an earlier kernel may be read before pdl_enter().
+// PDL_EARLY: a few kernels run the part of their prologue that reads nothing of the immediately preceding grid (shared-memory
+// initialisation; operands written two or more grids earlier, which are complete because the predecessor passed its own
+// pdl_enter() before this grid could be scheduled) BEFORE pdl_enter(), i.e. under the tail of the predecessor.
+#ifndef PDL_EARLY
+#define PDL_EARLY 1
+#endif
 __device__ __forceinline__ void pdl_enter()
 {
     asm volatile("griddepcontrol.wait;" ::: "memory");

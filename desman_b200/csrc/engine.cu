@@ -802,7 +802,7 @@ static int ensure_countsf(desman_ctx *c)
 // Start of a sweep: ONE cooperative launch that clears the per-sweep accumulators (statistics, fixed-point ll, nchange,
 // work-list length) and, only when a request is pending (host: state upload; device: finalize_sweep_kernel), rebuilds the
 // pattern table and regroups the sites (maintain_kernel.cuh).
-static int sync_table(desman_ctx *c)
+static int sync_table(desman_ctx *c, bool deferred_star_copy = false)
 {
     RET(ensure_agg(c));
     const bool grouping = group_config(c, nullptr, nullptr);
@@ -832,6 +832,7 @@ static int sync_table(desman_ctx *c)
     p.zero64 = c->stats; p.nzero64 = (int)((size_t)c->S * c->G + 16);
     p.red_i = c->red_i;
     p.countsf = c->countsf; p.nsite = c->nsite;
+    p.star_flag = deferred_star_copy ? c->flag : nullptr; p.tau_star = c->tau_star;
     void *args[] = {&p};
     {
         KSpan k(c, DESMAN_K_MAINT);
@@ -1089,18 +1090,25 @@ struct StoreBufs { double *ll = nullptr, *lp = nullptr, *nch = nullptr, *gs = nu
 
 // ll (from the table) -> lp, stores, MAP bookkeeping.  gamma/eta: the state the likelihood is evaluated at.
 static int launch_finalize_only(desman_ctx *c, const unsigned long long *red, const double *gamma, const double *eta, int it,
-                                int star_mode, const StoreBufs &sb, bool store_ge, double *eta_commit = nullptr);
+                                int star_mode, const StoreBufs &sb, bool store_ge, double *eta_commit = nullptr, bool copy_now = true);
 // eta_commit: where the chain's eta lives when `eta` is the freshly drawn eta_new (committed by the finalize kernel: :347)
+// copy_now = false: the MAP snapshot tau_star <- tau (if lp improved) is left to the next sync_table(c, true), or to the caller
 static int launch_finalize(desman_ctx *c, const double *gamma, const double *eta, int it, int star_mode, const StoreBufs &sb,
-                           bool store_ge, double *eta_commit = nullptr)
+                           bool store_ge, double *eta_commit = nullptr, bool copy_now = true)
 {
     RET(launch_ll(c, gamma, eta));
     RET(allreduce_red(c));
-    return launch_finalize_only(c, c->red_i, gamma, eta, it, star_mode, sb, store_ge, eta_commit);
+    return launch_finalize_only(c, c->red_i, gamma, eta, it, star_mode, sb, store_ge, eta_commit, copy_now);
+}
+static int launch_star_copy(desman_ctx *c)
+{
+    KSpan k(c, DESMAN_K_FINAL);
+    CU(launch_k(c, copy_tau_if_kernel, c->sm_count, 256, 0, (const uint8_t *)c->tau, c->tau_star, (size_t)c->V * c->G, (const int *)c->flag));
+    return DESMAN_OK;
 }
 // lp, stores, MAP bookkeeping from the (already summed) words red = [fixed-point ll, nchange]
 static int launch_finalize_only(desman_ctx *c, const unsigned long long *red, const double *gamma, const double *eta, int it,
-                                int star_mode, const StoreBufs &sb, bool store_ge, double *eta_commit)
+                                int star_mode, const StoreBufs &sb, bool store_ge, double *eta_commit, bool copy_now)
 {
     FinalParams p;
     p.red_i = (const long long *)red; p.ll_const = c->ll_const_total; p.ll_inv_scale = 1.0 / c->ll_scale;
@@ -1116,10 +1124,10 @@ static int launch_finalize_only(desman_ctx *c, const unsigned long long *red, co
     p.gctl = group_config(c, nullptr, nullptr) ? c->grp_gctl : nullptr;
     p.V_local = (long long)c->V;
     {
-        KSpan k(c, DESMAN_K_FINAL, 2);
+        KSpan k(c, DESMAN_K_FINAL);
         CU(launch_k(c, finalize_sweep_kernel, 1, 256, 0, p));
-        CU(launch_k(c, copy_tau_if_kernel, c->sm_count, 256, 0, (const uint8_t *)c->tau, c->tau_star, (size_t)c->V * c->G, (const int *)c->flag));
     }
+    if (copy_now) RET(launch_star_copy(c));
     CU(cudaGetLastError());
     return DESMAN_OK;
 }
@@ -1292,7 +1300,9 @@ extern "C" int desman_update(desman_ctx *c, int n_iter, double *gamma_store, dou
         sweep_begin(c);
         unsigned long long *red_prev = c->red_i;
         if (lagged) c->red_i = c->red_base + 2 * (it & 1);
-        RET(sync_table(c));                                             // clears the accumulators; table upkeep when pending
+        // clears the accumulators; table upkeep when pending; the MAP snapshot of the previous sweep (single rank: under
+        // sharding the bookkeeping of sweep it-1 follows the exchange below and keeps its own copy launch)
+        RET(sync_table(c, !lagged && it > 0));
         RET(launch_mu(c, c->gamma, c->eta));                            // sampleMu   (:341)
         if (lagged && it > 0) {
             RET(allreduce_stats(c, red_prev));
@@ -1301,14 +1311,14 @@ extern "C" int desman_update(desman_ctx *c, int n_iter, double *gamma_store, dou
         RET(launch_draw(c, c->stats, c->gamma, c->eta_new));            // sampleGamma (:342) + sampleEta's draw (:347)
         if (!c->fixed_tau) RET(launch_tau(c, c->gamma, c->eta, true, true, (uint32_t)it));       // sample_tau (:345), old eta (nchange cleared by sync_table)
         if (lagged) RET(launch_ll(c, c->gamma, c->eta_new, c->eta));     // eta <- new (:347); sum n*log p of sweep it, reduced with the next exchange
-        else RET(launch_finalize(c, c->gamma, c->eta_new, it, 0, sb, true, c->eta));   // eta <- new (:347); ll, lp, stores, star (:349-358)
+        else RET(launch_finalize(c, c->gamma, c->eta_new, it, 0, sb, true, c->eta, false));   // eta <- new (:347); ll, lp, stores, star (:349-358)
         sweep_end(c);
         c->sweep++;
     }
     if (lagged && n_iter > 0) {
         RET(allreduce_red(c));
         RET(launch_finalize_only(c, c->red_i, c->gamma, c->eta, n_iter - 1, 0, sb, true));
-    }
+    } else if (n_iter > 0) RET(launch_star_copy(c));                    // the snapshot of the last sweep
     c->red_i = c->red_base;
     {
         KSpan k(c, DESMAN_K_OTHER);

@@ -23,6 +23,10 @@ struct MaintParams {
     unsigned long long *red_i;   // ... and [2] fixed-point ll | nchange
     float4 *countsf;             // [V][S] FP32 copy of the count rows in group order (row pos <-> site grp.order[pos])
     float *nsite;                // [V] reads per row, rounded up
+    // deferred MAP snapshot of the previous sweep (update(): tau does not change between its finalize and this launch):
+    // if (*star_flag) tau_star <- tau, in place of a separate copy_tau_if launch per sweep; star_flag == nullptr: none
+    const int *star_flag;
+    uint8_t *tau_star;
 };
 
 #define MAINT_THREADS 256
@@ -66,6 +70,13 @@ __global__ void __launch_bounds__(MAINT_THREADS) table_maintain_kernel(MaintPara
     if (gtid < 2) p.red_i[gtid] = 0ull;
     if (gtid >= 4 && gtid < AGG_CTL_WORDS) t.ctl[gtid] = 0;          // work cursors of mu_binomial_kernel
     if (gtid == 0 && gctl) { gctl[GC_NWORK] = 0; gctl[GC_CURSOR] = 0; }
+    if (p.star_flag && *p.star_flag) {
+        const size_t n = (size_t)p.a.V * p.a.G, n16 = n / 16;
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.a.tau);
+        uint4 *dst = reinterpret_cast<uint4 *>(p.tau_star);
+        for (size_t i = gtid; i < n16; i += gsz) dst[i] = src[i];
+        for (size_t i = n16 * 16 + gtid; i < n; i += gsz) p.tau_star[i] = p.a.tau[i];
+    }
     if (!do_rebuild && !do_regroup) return;
 
     const int V = p.a.V, S = p.a.S, G = p.a.G;

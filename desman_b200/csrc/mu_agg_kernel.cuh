@@ -408,7 +408,9 @@ __device__ __forceinline__ void mub_item_base(const MuAggParams &p, BinStream &s
 
 __global__ void __launch_bounds__(MUB_WARPS * 32, MUB_MIN_BLOCKS) mu_binomial_kernel(MuAggParams p)
 {
+#if !PDL_EARLY
     pdl_enter();
+#endif
     KPROF_SCOPE(KP_MUB);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = p.S, G = p.G;
@@ -418,8 +420,12 @@ __global__ void __launch_bounds__(MUB_WARPS * 32, MUB_MIN_BLOCKS) mu_binomial_ke
     double *sufS = wS + G * 32;                                              // [G+1][32]
     unsigned long long *accS = reinterpret_cast<unsigned long long *>(sufS + (G + 1) * 32);   // [G][32]
     unsigned long long *eS = accS + G * 32;                                  // [16][32]
+    // (eta: committed by the finalize kernel of the previous sweep, several grids ago -- read under the predecessor's tail)
     if (threadIdx.x < 16) eta_s[threadIdx.x] = p.eta[threadIdx.x];
     for (int i = lane; i < (G + 16) * 32; i += 32) accS[i] = 0ull;
+#if PDL_EARLY
+    pdl_enter();
+#endif
     __syncthreads();
 
     const int nch = (S + 31) >> 5;

@@ -27,7 +27,9 @@
 #include "mu_agg_kernel.cuh"
 #include "tau_kernel.cuh"
 
-#define TG_ITEM_SITES 128
+#ifndef TG_ITEM_SITES
+#define TG_ITEM_SITES 64     // sites per work item (A/B at C3: 256: 66 us, 128: 60.8, 64: 58.3, 48: 63.4, 32: 68.3 for the screening pass)
+#endif
 #define TG_PASS_SITES 16
 #define TG_MAX_WARPS 4
 
@@ -327,13 +329,15 @@ __global__ void __launch_bounds__(TG_MAX_WARPS * 32, 1) tau_group_kernel(TauGrou
 // One CTA (4 warps) per work item, items dealt round robin (long items first); the warps share the item's table and take its
 // 16-site passes round robin.  Count rows are pulled into L2 by TMA bulk prefetches (cp.async.bulk.prefetch.L2) one round
 // of passes / one item ahead, so the 128-bit loads of a pass find them there.
+#ifndef TGM_WARPS
 #define TGM_WARPS 4
+#endif
 
 static inline int tgm_tiles(int G) { return (3 * G + 15) / 16; }
 static inline size_t tgm_table_bytes(int S, int G)
 {
     const size_t Sp = (size_t)((S + 15) & ~15);
-    return Sp * (size_t)(16 * tgm_tiles(G) + 2) * sizeof(float4) + (size_t)3 * tgm_tiles(G) * 8 * 32 * sizeof(float);   // + split-pass sums
+    return Sp * (size_t)(16 * tgm_tiles(G) + 2) * sizeof(float4) + (size_t)(TGM_WARPS - 1) * tgm_tiles(G) * 8 * 32 * sizeof(float);   // + split-pass sums
 }
 
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
@@ -371,13 +375,13 @@ __device__ __forceinline__ void tgm_group(float (&ch)[MT][2][4], float (&cl)[MT]
 }
 
 template <int MT>
-__global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGroupParams p)
+__global__ void __launch_bounds__(TGM_WARPS * 32, 16 / TGM_WARPS) tau_group_mma_kernel(TauGroupParams p)
 {
+#if !PDL_EARLY
     pdl_enter();
-    KPROF_SCOPE(KP_TGM);
+#endif
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int *gctl = p.grp.gctl;
-    if (!(gctl[GC_HAVE] && gctl[GC_CALM])) return;
     const int S = p.S, G = p.G;
     const int Sp = (S + 15) & ~15, nq = Sp >> 2;      // 4-sample groups
     constexpr int STR = 16 * MT + 2;                  // float4 per sample: = 2 (mod 8) -> conflict-free fragment loads
@@ -395,6 +399,11 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 4) tau_group_mma_kernel(TauGro
     if (tid == 0) { gmin_bits = 0x7f800000u; emin_bits = 0x7f800000u; }
     const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = tid; i < Sp * STR; i += blockDim.x) W[i] = zero4;        // padding rows / columns / samples stay zero
+#if PDL_EARLY
+    pdl_enter();                                                          // (shared memory only so far)
+#endif
+    KPROF_SCOPE(KP_TGM);
+    if (!(gctl[GC_HAVE] && gctl[GC_CALM])) return;
     __syncthreads();
     float gmin_l = __int_as_float(0x7f800000);
     for (int i = tid; i < G * Sp; i += blockDim.x) {

@@ -240,7 +240,14 @@ __device__ __noinline__ int tau_bracket_decide(const int4 *tile, const double2 *
 
 __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams p)
 {
-    pdl_enter();
+    // After the screening pass, gamma and eta are operands written at least two grids ago: the prologue that stages them runs
+    // before pdl_enter() (PDL_EARLY, common.cuh).  Without the screening pass the preceding grid may be the one that drew gamma.
+#if PDL_EARLY
+    const bool early = p.work != nullptr;
+#else
+    const bool early = false;
+#endif
+    if (!early) pdl_enter();
     KPROF_SCOPE(KP_TAU);
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int S = p.S, G = p.G;
@@ -298,6 +305,7 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
 #define KP_T(x)
 #endif
 
+    if (early) pdl_enter();
     int nsite = p.V, nwork = 0;
     bool listed = false;
     if (p.work && p.gctl[GC_HAVE] && p.gctl[GC_CALM]) {
