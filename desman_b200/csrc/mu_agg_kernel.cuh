@@ -26,7 +26,9 @@
 #define MUC_MAX_G 16              // up to here the within-class splits are merged over all patterns sharing the class (dense table)
 #define STAGE_MUC 8
 #define MUC_MAX_G 16              // up to here the within-class splits are merged over all patterns sharing the class (dense table)
+#ifndef MUB_WARPS
 #define MUB_WARPS 8
+#endif
 #define MUB_EMPTY 0xffffffffffffffffull
 #define AGG_CTL_WORDS 16          // ctl[4 + chunk]: work cursor of mu_binomial_kernel for sample chunk `chunk` (< MUB_CURSORS)
 #define MUB_CURSORS 12
@@ -479,7 +481,7 @@ __global__ void __launch_bounds__(MUB_WARPS * 32, MUB_MIN_BLOCKS) mu_binomial_ke
 #endif
         }
 #ifdef KPROF
-        if (lane == 0) krec_put(KP_MUB_WARP, (int)blockIdx.x, wib, (int)kp_items, kp_t0, gtimer(), 0, 0, 0, 0);
+        if (lane == 0 && blockIdx.x % 8 == 0) krec_put(KP_MUB_WARP, (int)blockIdx.x, wib, (int)kp_items, kp_t0, gtimer(), 0, 0, 0, 0);
 #endif
     } else {
         int item = gw / nch;

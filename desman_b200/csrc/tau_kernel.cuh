@@ -454,7 +454,7 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
 #endif
     }
 #ifdef KPROF
-    if (lane == 0) krec_put(KP_TAU_WARP, (int)blockIdx.x, wib, (int)(kp_sites | (n2 << 8) | (n3 << 20) | (flips << 24)), kp_pro, gtimer(), kp_first, kp_stage, kp_steps, kp_move);
+    if (lane == 0 && blockIdx.x % 8 == 0) krec_put(KP_TAU_WARP,   /* a sample of the CTAs: the records cost atomics at the end */ (int)blockIdx.x, wib, (int)(kp_sites | (n2 << 8) | (n3 << 20) | (flips << 24)), kp_pro, gtimer(), kp_first, kp_stage, kp_steps, kp_move);
 #endif
 
     if (lane == 0 && flips) atomicAdd(p.nchange, (unsigned long long)flips);

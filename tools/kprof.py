@@ -78,7 +78,7 @@ end = (w["t1"].astype(np.int64) - ts["entry"]) / 1e3
 sites = w["x"] & 0xff; n2 = (w["x"] >> 8) & 0xfff; n3 = (w["x"] >> 20) & 0xf; fl = (w["x"] >> 24) & 0xff
 print("prologue done  us: min %.2f med %.2f max %.2f" % (pro.min(), np.median(pro), pro.max()))
 print("warp end       us: min %.2f med %.2f p90 %.2f max %.2f" % (end.min(), np.median(end), np.percentile(end, 90), end.max()))
-print("sites per warp: ", np.bincount(sites)[:6], " tier3 warps", int((n3 > 0).sum()), " flips", int(fl.sum()))
+print("(per-warp records: every 8th CTA)  sites per warp: ", np.bincount(sites)[:6], " tier3 warps", int((n3 > 0).sum()), " flips", int(fl.sum()))
 has = sites > 0
 for nm in ("b", "c", "d"):
     v = w[nm][has] / np.maximum(sites[has], 1) / 1e3
