@@ -15,7 +15,7 @@
 // work list together with the bit mask of those steps, and the per-site kernel then walks only the listed sites, skipping
 // the decided steps until the first flip.  Results are therefore identical to the per-site kernel's, draw for draw.
 //
-// Mapping.  One warp per work item (pattern, <= 128 sites); the warp owns a private Wd table in shared memory.  A pass
+// Mapping.  One warp per work item (pattern, <= TG_ITEM_SITES sites); the warp owns a private Wd table in shared memory.  A pass
 // contracts 16 sites: lane = (r, o), r = 4 site rows of 4 sites each (register tile), o = 8 sample groups (s = o + 8k).
 // Every LDS.128 of the table feeds 16 FFMA (measured on B200: LDS.128 costs 4 LSU cycles per warp unless all 32 lanes
 // read the same address, tools/ubench; 4 sites per lane balance the LSU and FMA pipes).  Count rows are read as 128-bit
