@@ -321,10 +321,11 @@ def run_reference(args):
     K, W = args.steps, args.warmup
     world = args.gpus
     use_ref = oracle.have_ref()
-    # bounded sample: size Vs so that one step takes ~0.5 s
+    # bounded sample: size Vs so that one step takes ~0.5 s and the whole --steps K --warmup W run about two minutes at most
     p = synth_counts(min(V, 20000), S, G, shard=0)
     t_probe = cpu_sweep_sample(p, 1000, S, G, 1, use_ref)
-    Vs = int(max(500, min(p["counts"].shape[0], 1000 * 0.5 / max(t_probe, 1e-4))))
+    t_step = min(0.5, 120.0 / max(K + W, 1))
+    Vs = int(max(200, min(p["counts"].shape[0], 1000 * t_step / max(t_probe, 1e-4))))
     for _ in range(W):
         cpu_sweep_sample(p, Vs, S, G, 1, use_ref)
     t = cpu_sweep_sample(p, Vs, S, G, K, use_ref)
@@ -363,7 +364,7 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=500, help="timed sweeps (default: the 500 iterations of BASELINE config C3)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
