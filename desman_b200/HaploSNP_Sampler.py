@@ -23,6 +23,16 @@ from ._lib import RNG_MT19937, RNG_PHILOX
 from .engine import Engine
 
 
+def du_log_dirichlet(x, alpha):
+    """Desman_Utils.log_dirichlet_pdf (Desman_Utils.py:35-44)."""
+    from scipy.special import gammaln
+    ret = gammaln(np.sum(alpha))
+    for i in range(len(alpha)):
+        ret += (alpha[i] - 1.0) * np.log(x[i])
+        ret -= gammaln(alpha[i])
+    return float(ret)
+
+
 class Constants(object):
     MAX_LOG_DIR_PROB = 100.0
 
@@ -261,7 +271,13 @@ class HaploSNP_Sampler():
     def _ll_lp(self, cGamma, cTau, cEta):
         cTau = np.asarray(cTau)
         if not (((cTau == 0) | (cTau == 1)).all() and (cTau.sum(axis=2) == 1).all()):
-            raise NotImplementedError("log-likelihood of a non-one-hot tau (DIC, :486-496) is outside the hot path")
+            # a real-valued tau (the tauMean of DIC, :486-496): general kernel; the tau prior term of lp (:459) is the same
+            eng = self._engine()
+            self._push(eng)
+            ll = eng.loglik_general(cTau, cGamma, cEta)
+            prior = sum(du_log_dirichlet(np.asarray(cGamma)[s], self.alpha) for s in range(self.S))
+            prior += sum(du_log_dirichlet(np.asarray(cEta)[a], self.delta) for a in range(4))
+            return ll, ll + prior + self.V * self.G * np.log(0.25)
         eng = self._engine()
         self._push(eng, gamma=np.asarray(cGamma), tau=cTau, eta=np.asarray(cEta))
         return eng.loglik()
@@ -426,12 +442,48 @@ class HaploSNP_Sampler():
         self._set_tau_map()
         self.updateTauIndices()
 
-    # ------------------------------------------------------------------ outside the hot path
-    def _next(self, *a, **k):
-        raise NotImplementedError("4^G joint-state enumeration (assignTau/logTauProb/Chib) is not part of the "
-                                  "Gibbs hot path; see DESIGN.md 'out of scope'")
+    # ------------------------------------------------------------------ joint-state enumeration
+    def sampleLogProb(self, adLogProbS):
+        dP = np.exp(adLogProbS - np.max(adLogProbS))                           # :124-127
+        dP = dP / np.sum(dP, axis=0)
+        return np.flatnonzero(self.randomState.multinomial(1, dP, 1))[0]
 
-    assignTau = logTauProb = chibMarginalLogLikelihood = chibMarginalLogLikelihood2 = sampleTauFixTau = _next
+    def assignTau(self, assignMatrix):
+        """Tau for new sets of variants (:233-261): the log-probabilities of all 4^G joint states per site come from the
+        device (FP64 tiled product); the draw per site is the reference's numpy multinomial from self.randomState, in site order."""
+        assignMatrix = np.asarray(assignMatrix)
+        N = assignMatrix.shape[0]
+        variants = np.ascontiguousarray(np.reshape(assignMatrix, (N, self.S, 4)), dtype=np.int64)
+        eng = self._engine()
+        self._push(eng)
+        T = 4 ** self.G
+        assign = np.zeros((N, self.G, 4), dtype=np.int64)
+        conf = np.zeros(N)
+        shifts = 2 * (self.G - 1 - np.arange(self.G))
+        step = max(1, (1 << 25) // T)                                          # <= 256 MB of log-probabilities at a time
+        for lo in range(0, N, step):
+            lp = eng.state_logprob(self.gamma_star, self.eta_star, variants=variants[lo:lo + step], want_logprob=True)["logprob"]
+            for i in range(lp.shape[0]):
+                dP = np.exp(lp[i] - np.max(lp[i]))
+                dP = dP / np.sum(dP, axis=0)
+                t = np.flatnonzero(self.randomState.multinomial(1, dP, 1))[0]
+                conf[lo + i] = np.amax(dP)
+                assign[lo + i, np.arange(self.G), (int(t) >> shifts) & 3] = 1      # tauStates[t] (:95-103)
+        return (assign, conf)
+
+    def logTauProb(self, cGamma, cEta):
+        """sum_v log P(tau_star[v] | counts[v], gamma, eta) over the 4^G joint states of a site (:498-524)."""
+        eng = self._engine()
+        self._push(eng)
+        idx = np.ascontiguousarray(self.tauIndices_star, dtype=np.int64)
+        r = eng.state_logprob(cGamma, cEta, index=idx)
+        return float(np.sum(r["lp_at_index"] - r["lse"]))
 
     def DIC(self):
-        raise NotImplementedError("DIC needs the likelihood of the non-one-hot tauMean (:486-496); outside the hot path")
+        return self.meanDeviance() + 2.0 * self.logLikelihood(self.gammaMean(), self.tauMean(), self.etaMean())   # :486-496
+
+    def _next(self, *a, **k):
+        raise NotImplementedError("chibMarginalLogLikelihood[2] / sampleTauFixTau read E_store / mu_store and draw from numpy's "
+                                  "sequential stream per (v,g) step; they have no caller in the reference (DESIGN.md section 7)")
+
+    chibMarginalLogLikelihood = chibMarginalLogLikelihood2 = sampleTauFixTau = _next

@@ -45,6 +45,8 @@ SYMBOLS = {
     "desman_mu_stats": (C.c_int, [_ctx, _p64, _p64]),
     "desman_draw_gamma_eta": (C.c_int, [_ctx, _p64, _p64, _pd, _pd]),
     "desman_loglik": (C.c_int, [_ctx, _pd, _pd]),
+    "desman_loglik_general": (C.c_int, [_ctx, _pd, _pd, _pd, C.c_int, _pd]),
+    "desman_state_logprob": (C.c_int, [_ctx, _p64, C.c_int64, C.c_int, _pd, _pd, C.c_int, _p64, _pd, _pd, _pd, _pd, _p64]),
     "desman_update": (C.c_int, [_ctx, C.c_int, _pd, _pd, _pd, _pd, _p64]),
     "desman_update_tau": (C.c_int, [_ctx, C.c_int, _pd, _pd, _pd, _pd, _p64]),
     "desman_get_star": (C.c_int, [_ctx, _p64, _pd, _pd, _pd, C.POINTER(C.c_int)]),

@@ -21,6 +21,7 @@
 #include "nmft_kernel.cuh"
 #include "tau_kernel.cuh"
 #include "tau_group_kernel.cuh"
+#include "state_kernel.cuh"
 #include "maintain_kernel.cuh"
 #include "exchange_kernel.cuh"
 
@@ -1218,6 +1219,108 @@ extern "C" int desman_loglik(desman_ctx *c, double *ll, double *lp)
     if (ll) *ll = h_ll;
     if (lp) *lp = h_ll + prior;
     return DESMAN_OK;
+}
+
+// ------------------------------------------------------------------------------------------ joint states, general tau
+extern "C" int desman_loglik_general(desman_ctx *c, const double *tau, const double *gamma, const double *eta, int G, double *ll)
+{
+    if (!c || c->V <= 0) return fail(DESMAN_ESTATE, "no counts set");
+    if (!tau || !gamma || !eta || !ll || G < 1 || G > DESMAN_MAX_G) return fail(DESMAN_EINVAL, "desman_loglik_general: bad argument");
+    CU(cudaSetDevice(c->device));
+    RET(ensure_ll_const(c));
+    const size_t ntau = (size_t)c->V * G * 4, nsg = (size_t)c->S * G;
+    const int nb = c->sm_count * 4;
+    double *d = nullptr;
+    CU(dmalloc(c, &d, (ntau + nsg + 16 + nb) * sizeof(double)));
+    double *d_tau = d, *d_gamma = d + ntau, *d_eta = d_gamma + nsg, *d_part = d_eta + 16;
+    CU(cudaMemcpyAsync(d_tau, tau, ntau * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_gamma, gamma, nsg * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_eta, eta, 16 * 8, cudaMemcpyHostToDevice, c->stream));
+    loglik_general_kernel<<<nb, 256, 0, c->stream>>>(c->counts, d_tau, d_gamma, d_eta, (int)c->V, c->S, G, d_part);
+    CU(cudaGetLastError());
+    std::vector<double> h(nb);
+    CU(cudaMemcpyAsync(h.data(), d_part, nb * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    dfree(c, d);
+    if (c->nranks > 1) return fail(DESMAN_ESTATE, "desman_loglik_general is a single-rank call");
+    double t = 0.0;
+    for (int i = 0; i < nb; i++) t += h[i];
+    *ll = c->ll_const_total + t;
+    return DESMAN_OK;
+}
+
+extern "C" int desman_state_logprob(desman_ctx *c, const int64_t *variants, int64_t N, int S, const double *gamma, const double *eta,
+                                    int G, const int64_t *index, double *logprob, double *lp_at_index, double *maxlp, double *lse,
+                                    int64_t *argmax)
+{
+    if (!c) return fail(DESMAN_EINVAL, "desman_state_logprob: ctx is NULL");
+    if (!variants) {
+        if (c->V <= 0) return fail(DESMAN_ESTATE, "no counts set");
+        N = c->V; S = c->S;
+    }
+    if (N <= 0 || S <= 0 || !gamma || !eta || G < 1) return fail(DESMAN_EINVAL, "desman_state_logprob: bad argument");
+    if (index && !lp_at_index) return fail(DESMAN_EINVAL, "desman_state_logprob: index without lp_at_index");
+    const int K = 4 * S;
+    if (G > 15 || ((size_t)1 << (2 * G)) * (size_t)K * 8 > ((size_t)4 << 30))
+        return fail(DESMAN_EINVAL, "4^G joint states do not fit: 4^%d * %d doubles exceed 4 GiB (the reference's own tauStates "
+                                   "table, HaploSNP_Sampler.py:95-103, is out of reach well before that)", G, K);
+    const long long T = 1ll << (2 * G);
+    if (index) for (int64_t n = 0; n < N; n++) if (index[n] < 0 || index[n] >= T) return fail(DESMAN_EINVAL, "index[%lld] is not a state", (long long)n);
+    CU(cudaSetDevice(c->device));
+    const int nblk = (int)((T + ST_BN - 1) / ST_BN);
+    // sites per pass: partials (24 B per site and state block) within 64 MB, the optional full rows within 256 MB
+    long long Nc = ((long long)64 << 20) / ((long long)nblk * 24);
+    if (logprob) { const long long m = ((long long)256 << 20) / (T * 8); if (m < Nc) Nc = m; }
+    Nc = (Nc / ST_BM) * ST_BM;
+    if (Nc < ST_BM) Nc = ST_BM;
+    if (Nc > N) Nc = N;
+    const size_t nsg = (size_t)S * G;
+    double *d_gamma = nullptr, *d_ls = nullptr, *d_cd = nullptr, *d_pm = nullptr, *d_ps = nullptr, *d_lp = nullptr, *d_out = nullptr,
+           *d_full = nullptr;
+    long long *d_pa = nullptr, *d_idx = nullptr, *d_v64 = nullptr, *d_arg = nullptr;
+    int rc = DESMAN_OK;
+    auto body = [&]() -> int {
+        CU(dmalloc(c, &d_gamma, (nsg + 16) * 8));
+        CU(dmalloc(c, &d_ls, (size_t)K * T * 8));
+        CU(dmalloc(c, &d_cd, (size_t)K * Nc * 8));
+        CU(dmalloc(c, &d_pm, (size_t)Nc * nblk * 8));
+        CU(dmalloc(c, &d_ps, (size_t)Nc * nblk * 8));
+        CU(dmalloc(c, &d_pa, (size_t)Nc * nblk * 8));
+        CU(dmalloc(c, &d_out, (size_t)Nc * 2 * 8));
+        CU(dmalloc(c, &d_arg, (size_t)Nc * 8));
+        CU(dmalloc(c, &d_lp, (size_t)Nc * 8));
+        if (index) CU(dmalloc(c, &d_idx, (size_t)Nc * 8));
+        if (variants) CU(dmalloc(c, &d_v64, (size_t)Nc * K * 8));
+        if (logprob) CU(dmalloc(c, &d_full, (size_t)Nc * T * 8));
+        CU(cudaMemcpyAsync(d_gamma, gamma, nsg * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(d_gamma + nsg, eta, 16 * 8, cudaMemcpyHostToDevice, c->stream));
+        state_logsite_kernel<<<c->sm_count * 8, 256, 0, c->stream>>>(d_gamma, d_gamma + nsg, S, G, T, d_ls);
+        CU(cudaGetLastError());
+        for (long long n0 = 0; n0 < N; n0 += Nc) {
+            const int nc = (int)((N - n0 < Nc) ? N - n0 : Nc);
+            if (variants) CU(cudaMemcpyAsync(d_v64, variants + (size_t)n0 * K, (size_t)nc * K * 8, cudaMemcpyHostToDevice, c->stream));
+            if (index) CU(cudaMemcpyAsync(d_idx, index + n0, (size_t)nc * 8, cudaMemcpyHostToDevice, c->stream));
+            state_counts_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(variants ? d_v64 : nullptr, c->counts, variants ? 0 : n0, nc, K, d_cd);
+            StateParams p;
+            p.Cd = d_cd; p.logSiteT = d_ls; p.Nc = nc; p.K = K; p.T = T; p.nblk = nblk;
+            p.part_max = d_pm; p.part_sum = d_ps; p.part_arg = d_pa;
+            p.index = index ? d_idx : nullptr; p.lp_at_index = d_lp; p.logprob = d_full;
+            state_logprob_kernel<<<dim3((unsigned)nblk, (unsigned)((nc + ST_BM - 1) / ST_BM)), 256, 0, c->stream>>>(p);
+            state_reduce_kernel<<<(nc + 127) / 128, 128, 0, c->stream>>>(d_pm, d_ps, d_pa, nc, nblk, d_out, d_out + nc, d_arg);
+            CU(cudaGetLastError());
+            if (maxlp) CU(cudaMemcpyAsync(maxlp + n0, d_out, (size_t)nc * 8, cudaMemcpyDeviceToHost, c->stream));
+            if (lse) CU(cudaMemcpyAsync(lse + n0, d_out + nc, (size_t)nc * 8, cudaMemcpyDeviceToHost, c->stream));
+            if (argmax) CU(cudaMemcpyAsync(argmax + n0, d_arg, (size_t)nc * 8, cudaMemcpyDeviceToHost, c->stream));
+            if (index) CU(cudaMemcpyAsync(lp_at_index + n0, d_lp, (size_t)nc * 8, cudaMemcpyDeviceToHost, c->stream));
+            if (logprob) CU(cudaMemcpyAsync(logprob + (size_t)n0 * T, d_full, (size_t)nc * T * 8, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        }
+        return DESMAN_OK;
+    };
+    rc = body();
+    void *bufs[] = {d_gamma, d_ls, d_cd, d_pm, d_ps, d_pa, d_out, d_arg, d_lp, d_idx, d_v64, d_full};
+    for (void *b : bufs) if (b) dfree(c, b);
+    return rc;
 }
 
 // ------------------------------------------------------------------------------------------ chains

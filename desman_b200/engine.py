@@ -122,6 +122,51 @@ class Engine:
         check(self._L.desman_loglik(self._h, C.byref(ll), C.byref(lp)), "desman_loglik")
         return ll.value, lp.value
 
+    def loglik_general(self, tau, gamma, eta):
+        """logLikelihood (:431-442) under a real-valued tau [V,G,4] (the tauMean of DIC, :486-496)."""
+        tau = np.ascontiguousarray(tau, dtype=np.float64)
+        gamma = np.ascontiguousarray(gamma, dtype=np.float64)
+        eta = np.ascontiguousarray(eta, dtype=np.float64)
+        if tau.ndim != 3 or tau.shape[0] != self.V or tau.shape[2] != 4 or gamma.shape != (self.S, tau.shape[1]) or eta.shape != (4, 4):
+            raise ValueError("loglik_general: tau [V,G,4], gamma [S,G], eta [4,4] expected")
+        ll = C.c_double(0)
+        check(self._L.desman_loglik_general(self._h, _lib.ptr_d(tau), _lib.ptr_d(gamma), _lib.ptr_d(eta), tau.shape[1], C.byref(ll)),
+              "desman_loglik_general")
+        return ll.value
+
+    def state_logprob(self, gamma, eta, variants=None, index=None, want_logprob=False):
+        """Log-probabilities of all 4^G joint states per site (assignTau :233-261, logTauProb :498-524).
+        variants: int64 [N,S,4] or None for the counts of the engine.  Returns a dict: maxlp [N], lse [N] (log sum exp over the
+        states), argmax [N], and, if asked for, lp_at_index [N] (index [N] given) and logprob [N,4^G]."""
+        gamma = np.ascontiguousarray(gamma, dtype=np.float64)
+        eta = np.ascontiguousarray(eta, dtype=np.float64)
+        if gamma.ndim != 2 or eta.shape != (4, 4):
+            raise ValueError("state_logprob: gamma [S,G], eta [4,4] expected")
+        S, G = gamma.shape
+        pv, N = None, self.V
+        if variants is not None:
+            variants, pv = _lib.as_i64(variants, "variants")
+            if variants.ndim != 3 or variants.shape[1] != S or variants.shape[2] != 4:
+                raise ValueError("state_logprob: variants [N,%d,4] expected" % S)
+            N = variants.shape[0]
+        elif S != self.S:
+            raise ValueError("state_logprob: gamma has %d samples, the engine's counts %d" % (S, self.S))
+        out = dict(maxlp=np.empty(N), lse=np.empty(N), argmax=np.empty(N, dtype=np.int64))
+        pi = pl = pf = None
+        if index is not None:
+            index, pi = _lib.as_i64(index, "index")
+            if index.shape != (N,):
+                raise ValueError("state_logprob: index [N] expected")
+            out["lp_at_index"] = np.empty(N)
+            pl = _lib.ptr_d(out["lp_at_index"])
+        if want_logprob:
+            out["logprob"] = np.empty((N, 4 ** G))
+            pf = _lib.ptr_d(out["logprob"])
+        check(self._L.desman_state_logprob(self._h, pv, N, S, _lib.ptr_d(gamma), _lib.ptr_d(eta), G, pi, pf, pl,
+                                           _lib.ptr_d(out["maxlp"]), _lib.ptr_d(out["lse"]), _lib.ptr_i64(out["argmax"])),
+              "desman_state_logprob")
+        return out
+
     # ------------------------------------------------------------------ chains
     def update(self, n_iter):
         S, G = self.S, self.G

@@ -83,6 +83,17 @@ int desman_mu_stats(desman_ctx *ctx, int64_t *sum_mu /*S*G*/, int64_t *esum /*16
 int desman_draw_gamma_eta(desman_ctx *ctx, const int64_t *sum_mu, const int64_t *esum,
                           double *gamma /*S*G*/, double *eta /*16*/);          /* :263-281 (does not change state) */
 int desman_loglik(desman_ctx *ctx, double *ll, double *lp);                      /* :431-461 */
+/* logLikelihood under a real-valued tau [V,G,4] (the tauMean of DIC, :479-496) on the counts of the context */
+int desman_loglik_general(desman_ctx *ctx, const double *tau /*V*G*4*/, const double *gamma /*S*G*/, const double *eta /*16*/,
+                          int G, double *ll);
+/* Joint-state enumeration (assignTau :233-261, logTauProb :498-524): for N sites and all T = 4^G states t (strain g = digit
+ * G-1-g of t in base 4, the reference's tauStates order) stateLogProb[n][t] = sum_{s,b} n_sb log(sum_g gamma[s,g] eta[t_g,b]).
+ * variants: int64 [N,S,4] host counts, or NULL for the counts of the context (then N = V, S = the context's).  Outputs, each
+ * may be NULL: logprob [N,T] (all of it: mind the size), maxlp [N], lse [N] = log sum_t exp, argmax [N] (first maximum);
+ * lp_at_index [N] = stateLogProb[n][index[n]] when index is given.  4^G * 4S doubles must fit in 4 GiB (G <= 10 at S = 64). */
+int desman_state_logprob(desman_ctx *ctx, const int64_t *variants, int64_t N, int S, const double *gamma /*S*G*/,
+                         const double *eta /*16*/, int G, const int64_t *index, double *logprob, double *lp_at_index,
+                         double *maxlp, double *lse, int64_t *argmax);
 
 /* update(): n_iter full Gibbs sweeps on device (HaploSNP_Sampler.py:334-365).  Output arrays may be
  * NULL; gamma_store [n_iter,S,G], eta_store [n_iter,4,4], ll_store/lp_store/nchange_store [n_iter]. */

@@ -372,6 +372,58 @@ def nmft_get_tau(tau, V, G):
     return out
 
 
+# ------------------------------------------------------------------ joint-state enumeration (numpy restatement, small G)
+def tau_states(G):
+    """tauStates [4^G,G] as base indices: Desman_Utils.cartesian order, strain 0 the slowest digit
+    (HaploSNP_Sampler.py:95-103; tauMap :112-116)."""
+    t = np.arange(4 ** G, dtype=np.int64)
+    return np.stack([(t >> (2 * (G - 1 - g))) & 3 for g in range(G)], axis=1)
+
+
+def state_logprob(variants, gamma, eta):
+    """stateLogProb[n,t] = sum(log(siteProb[t]) * variants[n]) with siteProb[t] = baseProbabilityGivenTau(tauStates[t])
+    (HaploSNP_Sampler.py:129-135, :239-255, :503-517)."""
+    gamma, eta = np.asarray(gamma, dtype=np.float64), np.asarray(eta, dtype=np.float64)
+    st = tau_states(gamma.shape[1])                                             # [T,G]
+    site = np.einsum("sg,tgb->tsb", gamma, eta[st])                             # [T,S,4]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.einsum("tsb,nsb->nt", np.log(site), np.asarray(variants, dtype=np.float64))
+
+
+def log_tau_prob(variants, gamma, eta, index):
+    """logTauProb (:498-524): sum_v log(dP[v, index[v]]), dP = exp(lp - max) / sum."""
+    lp = state_logprob(variants, gamma, eta)
+    ret = 0.0
+    for v in range(lp.shape[0]):
+        dP = np.exp(lp[v] - np.max(lp[v]))
+        dP = dP / np.sum(dP, axis=0)
+        ret += np.log(dP[index[v]])
+    return float(ret)
+
+
+def assign_tau(variants, gamma, eta, random_state):
+    """assignTau (:233-261) with the reference's own numpy draw per site; returns (base indices [N,G], conf [N])."""
+    lp = state_logprob(variants, gamma, eta)
+    st = tau_states(np.asarray(gamma).shape[1])
+    out = np.zeros((lp.shape[0], st.shape[1]), dtype=np.uint8)
+    conf = np.zeros(lp.shape[0])
+    for n in range(lp.shape[0]):
+        dP = np.exp(lp[n] - np.max(lp[n]))
+        dP = dP / np.sum(dP, axis=0)
+        t = np.flatnonzero(random_state.multinomial(1, dP, 1))[0]
+        conf[n] = np.amax(dP)
+        out[n] = st[t]
+    return out, conf
+
+
+def loglik_general(variants, tau_real, gamma, eta):
+    """logLikelihood (:431-442, Desman_Utils.py:28-33) for a real-valued tau [V,G,4]."""
+    from scipy.special import gammaln
+    c = np.asarray(variants, dtype=np.float64)
+    p = np.einsum("vga,sg,ab->vsb", np.asarray(tau_real, dtype=np.float64), gamma, eta)
+    return float((gammaln(c.sum(2) + 1.0) - gammaln(c + 1.0).sum(2) + (c * np.log(p)).sum(2)).sum())
+
+
 def num_threads():
     return lib().oracle_num_threads()
 

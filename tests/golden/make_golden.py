@@ -16,6 +16,7 @@ Outputs (all under tests/golden/):
   sample_tau_kat.npz    kernel-level known answers from the reference C
   loglik_kat.npz        logLikelihood/logPosterior from the reference Python
   mu_stats_ref.npz      Monte-Carlo moments of the reference sampleMu -> (sum_mu, Esum)
+  assign_kat.npz        assignTau / logTauProb / logLikelihood(real-valued tau) of the reference Python
   cog0015.npz           the COG0015 count tensor after Variant_Filter (config C1 input)
   cog0015_i3.npz        recorded NMFT + Gibbs chain of `desman ... -g 5 -i 3`
   cog0015_i3/           the CLI's output files of that run
@@ -349,6 +350,47 @@ def make_cog0015_input():
     print("  COG0015 input:", snps.shape, "max", snps.max(), "zeros %.3f" % (snps == 0).mean())
 
 
+# ------------------------------------------------------------------ F. joint-state enumeration (assignTau, logTauProb), DIC
+def make_assign_kat():
+    """assignTau (:233-261), logTauProb (:498-524) and logLikelihood of a real-valued tau (DIC, :486-496) of the UNMODIFIED
+    reference class (full constructor: tauStates[4^G,G,4] is small for G <= 5)."""
+    rng = np.random.default_rng(4242)
+    out = {}
+    spec = [(20, 3, 6, 30), (10, 5, 16, 40), (8, 1, 4, 12), (12, 2, 3, 25)]
+    for ci, (V, G, S, depth) in enumerate(spec):
+        counts = synth_counts(rng, V, S, depth, 1)
+        newc = synth_counts(rng, V + 3, S, depth, 1)
+        h = hsnp.HaploSNP_Sampler(np.copy(counts), G, RandomState(11 + ci), max_iter=3)
+        gamma = rng.dirichlet(np.full(G, 0.7), size=S)
+        gamma[gamma < 1e-6] = 1e-6
+        gamma = gamma / gamma.sum(axis=1)[:, None]
+        eta = rng.dirichlet(np.array([60.0, 1.0, 1.0, 1.0]), size=4)
+        eta = np.array([np.roll(eta[a], a) for a in range(4)])
+        h.gamma_star, h.eta_star = np.copy(gamma), np.copy(eta)
+        # the most probable joint state of every site, the runner-up at every third one (stays clear of exp underflow: the
+        # reference takes math.log of the normalised probability)
+        sp = np.array([h.baseProbabilityGivenTau(h.tauStates[t], gamma, eta) for t in range(h.nTauStates)])
+        lp = np.einsum("tsb,vsb->vt", np.log(sp), counts.astype(float))
+        order = np.argsort(-lp, axis=1, kind="stable")
+        star = order[:, 0].copy()
+        if h.nTauStates > 1:
+            star[::3] = order[::3, 1]
+        h.tauIndices_star = star.astype(np.int64)
+        ltp = float(h.logTauProb(gamma, eta))
+        h.randomState = RandomState(9000 + ci)
+        aT, conf = h.assignTau(np.reshape(newc, (V + 3, S * 4)))
+        after = h.randomState.random_sample(2)
+        tau_real = rng.dirichlet(np.full(4, 0.3), size=(V, G))
+        ll_real = float(h.logLikelihood(gamma, tau_real, eta))
+        out.update({f"c{ci}_counts": counts.astype(np.int32), f"c{ci}_new": newc.astype(np.int32), f"c{ci}_gamma": gamma,
+                    f"c{ci}_eta": eta, f"c{ci}_star": star.astype(np.int64), f"c{ci}_logtauprob": np.array(ltp),
+                    f"c{ci}_assign": np.argmax(aT, axis=2).astype(np.uint8), f"c{ci}_conf": conf, f"c{ci}_rng_after": after,
+                    f"c{ci}_tau_real": tau_real, f"c{ci}_ll_real": np.array(ll_real), f"c{ci}_rng_seed": np.array(9000 + ci)})
+        print(f"  assign KAT case {ci}: V={V} G={G} S={S} logTauProb={ltp:.6f} ll(real tau)={ll_real:.6f} conf[:3]={conf[:3]}")
+    out["ncases"] = np.array(len(spec))
+    np.savez_compressed(os.path.join(HERE, "assign_kat.npz"), **out)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["kat", "loglik", "mu", "input", "i3"]
     oracle.build()
@@ -358,6 +400,8 @@ if __name__ == "__main__":
         make_loglik_kat()
     if "mu" in what:
         make_mu_stats_ref()
+    if "assign" in what:
+        make_assign_kat()
     if "input" in what:
         make_cog0015_input()
     if "i3" in what:
