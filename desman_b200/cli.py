@@ -134,9 +134,28 @@ def main(argv=None):
         output_Results.output_collated_Tau(haplo_SNP_NS, variants)
         haplo_SNP_NS.close()
 
+    # assign if assignment file given (bin/desman:208-240, without the `import ipdb; ipdb.set_trace()` left at :213-214)
     if args.assign_file is not None:
-        raise NotImplementedError("-a/--assign_file enumerates 4^G joint states (assignTau) and stops in a debugger in the "
-                                  "reference (bin/desman:213-214); outside the Gibbs hot path")
+        assigns = p.read_csv(args.assign_file, header=0, index_col=0)
+        assigns_matrix = assigns.to_numpy()
+        assigns_matrix = np.delete(assigns_matrix, 0, 1)
+        (assignTau, confTau) = haplo_SNP.assignTau(assigns_matrix)
+        assign_contig_names = assigns.index.tolist()
+        assign_position = assigns['Position']
+        AV = assigns_matrix.shape[0]
+        assign_tau_res = np.reshape(assignTau, (AV, haplo_SNP.G * 4))
+        assign_tau_df = p.DataFrame(assign_tau_res, index=assign_contig_names)
+        conf_tau_df = p.DataFrame(confTau, index=assign_contig_names)
+        assign_tau_df['Position'] = assign_position
+        conf_tau_df['Position'] = assign_position
+        cols = assign_tau_df.columns.tolist()
+        cols = cols[-1:] + cols[:-1]
+        assign_tau_df = assign_tau_df[cols]
+        assign_tau_df.to_csv(args.output_dir + "/Assigned_Tau_star.csv")
+        cols = conf_tau_df.columns.tolist()
+        cols = cols[-1:] + cols[:-1]
+        conf_tau_df = conf_tau_df[cols]
+        conf_tau_df.to_csv(args.output_dir + "/Assigned_Tau_conf.csv")
     haplo_SNP.close()
     sampletau.freeRNG()
 

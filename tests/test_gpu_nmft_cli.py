@@ -191,3 +191,25 @@ def test_cli_random_select_branch(tmp_path, tau_rng):
     assert fitp[0] == "Fit" and np.isfinite(float(fitp[3])) and float(fitp[4]) > 0
     log = open(out / "log_file.txt").read()
     assert "Perform NTF initialisation on not selected SNPs fixed gamma" in log and "nll =" in log
+
+
+def test_cli_assign_branch(tmp_path):
+    """`-a file`: assignTau over all 4^G joint states for the positions of a second table (bin/desman:208-240, minus the
+    debugger trap the reference left at :213-214): Assigned_Tau_star.csv / Assigned_Tau_conf.csv in the reference's layout."""
+    freq = tmp_path / "cog0015.freq"
+    _write_freq(str(freq))
+    lines = open(freq).read().splitlines()
+    assign = tmp_path / "assign.freq"
+    assign.write_text("\n".join(lines[:1] + lines[100:140]) + "\n")
+    out = tmp_path / "out"
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bin", "desman"), str(freq), "-g", "3", "-i", "8", "-a", str(assign),
+                        "-o", str(out)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    star = open(out / "Assigned_Tau_star.csv").read().splitlines()
+    assert len(star) == 41 and star[0] == ",Position,0,1,2,3,4,5,6,7,8,9,10,11"
+    tau = np.loadtxt(out / "Assigned_Tau_star.csv", delimiter=",", skiprows=1, usecols=range(2, 14))
+    assert (tau.reshape(40, 3, 4).sum(2) == 1).all()
+    conf = np.loadtxt(out / "Assigned_Tau_conf.csv", delimiter=",", skiprows=1, usecols=(1, 2))
+    assert np.array_equal(conf[:, 0], np.arange(100, 140)) and ((conf[:, 1] > 0) & (conf[:, 1] <= 1.0 + 1e-12)).all()
+    # positions 100..139 are rows of the fitted table itself: with the fitted gamma/eta most of them are assigned with confidence
+    assert np.median(conf[:, 1]) > 0.9
