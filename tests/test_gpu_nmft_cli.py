@@ -160,8 +160,9 @@ def test_sampler_class_surface_on_gpu(oracle_mod):
     hs.gamma_store, hs.eta_store = gs, es
     hs.updateTau()
     assert hs.ll_store.shape == (7,) and (hs.tauMean().sum(2) > 0.999).all()
+    assert np.isfinite(hs.DIC())                                              # value checked in test_gpu_states.py
     with pytest.raises(NotImplementedError):
-        hs.DIC()
+        hs.chibMarginalLogLikelihood()
     hs.close()
     sampletau.freeRNG()
 
