@@ -192,7 +192,13 @@ struct FinalParams {
 // logPosterior (HaploSNP_Sampler.py:444-461) + star bookkeeping (:326-332, :351-358)
 __global__ void __launch_bounds__(256) finalize_sweep_kernel(FinalParams p)
 {
+    // The log-priors and the bookkeeping words read below were written at least two grids ago (gamma, eta_new: the draw
+    // kernel; stale slots, orphans: the tau kernels; lp_star: the previous finalize) -- the grid right before this one is the
+    // log-likelihood pass or the exchange, which write red_i only.  So everything but red_i is formed before pdl_enter(),
+    // under the tail of that grid (PDL_EARLY, common.cuh).
+#if !PDL_EARLY
     pdl_enter();
+#endif
     KPROF_SCOPE(KP_FIN);
     __shared__ double sh[256];
     const int nG = p.S * p.G;
@@ -206,15 +212,25 @@ __global__ void __launch_bounds__(256) finalize_sweep_kernel(FinalParams p)
         __syncthreads();
     }
     __shared__ int upd;
+    double prior = 0.0, lp_star = 0.0;
+    long long stale0 = 0, used = 0, orphans = 0;
     if (threadIdx.x == 0) {
-        const double prior = sh[0] + p.S * (p.lg_alphaG - p.G * p.lg_alpha) + 4.0 * (p.lg_delta4 - 4.0 * p.lg_delta) +
-                             p.V_total * (double)p.G * log(0.25);
+        prior = sh[0] + p.S * (p.lg_alphaG - p.G * p.lg_alpha) + 4.0 * (p.lg_delta4 - 4.0 * p.lg_delta) +
+                p.V_total * (double)p.G * log(0.25);
+        lp_star = p.scal[0];
+        if (p.agg_ctl) { stale0 = (long long)p.agg_ctl[3]; used = (long long)*p.agg_nslots; }
+        if (p.gctl) orphans = (long long)p.gctl[GC_ORPHANS];
+    }
+#if PDL_EARLY
+    pdl_enter();
+#endif
+    if (threadIdx.x == 0) {
         const double ll = p.ll_const + (double)p.red_i[0] * p.ll_inv_scale, lp = ll + prior;
         if (p.agg_ctl) {
             // pattern table upkeep: every flipped (v,g) may have left a stale slot behind.  Ask for a rebuild when the
             // stale slots could outnumber half the live ones, or when the slot array is close to its capacity bound.
-            const long long stale = (long long)p.agg_ctl[3] + (p.it >= 0 ? p.red_i[1] : 0);
-            const long long used = (long long)*p.agg_nslots, live = used > stale ? used - stale : 0;
+            const long long stale = stale0 + (p.it >= 0 ? p.red_i[1] : 0);
+            const long long live = used > stale ? used - stale : 0;
             p.agg_ctl[3] = (int)(stale > 0x3fffffff ? 0x3fffffff : stale);
             if (stale > live / 2 + 512 || used > (long long)p.agg_limit) p.agg_ctl[0] = 1;
         }
@@ -222,7 +238,7 @@ __global__ void __launch_bounds__(256) finalize_sweep_kernel(FinalParams p)
             // screening pass upkeep: it pays off while few sites flip; regroup when orphans (sites that left their group) pile up
             p.gctl[GC_CALM] = (double)p.red_i[1] <= p.V_total / 16.0;
             const long long lim = p.V_local / 128 > 64 ? p.V_local / 128 : 64;
-            if ((long long)p.gctl[GC_ORPHANS] > lim) p.gctl[GC_REGROUP] = 1;
+            if (orphans > lim) p.gctl[GC_REGROUP] = 1;
         }
         p.scal[2] = ll; p.scal[3] = lp;
         if (p.it >= 0) {
@@ -230,7 +246,7 @@ __global__ void __launch_bounds__(256) finalize_sweep_kernel(FinalParams p)
             if (p.lp_store) p.lp_store[p.it] = lp;
             if (p.nchange_store) p.nchange_store[p.it] = (double)p.red_i[1];
         }
-        upd = (p.it < 0) || (lp > p.scal[0]);
+        upd = (p.it < 0) || (lp > lp_star);
         if (upd) { p.scal[0] = lp; p.scal[1] = (double)(p.it < 0 ? 0 : p.it); }
         *p.flag = upd;
     }
