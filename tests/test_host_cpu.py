@@ -76,3 +76,23 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not bad.search(src), f
+
+
+def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours): exactly one line on stdout, valid JSON, our arm's
+    metric/unit/config names, impl = reference, a cpu_baseline describing the run, zero-copy e2e mirror of the value."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout[:500]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "sweeps/s" and d["higher_is_better"] is True and d["steps"] == 2
+    assert d["metric"].startswith("Gibbs sweeps/sec") and d["config"]["workload"].startswith("BASELINE config C3")
+    assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["e2e"] == {"value": d["value"], "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0
