@@ -14,7 +14,7 @@ def needs_build():
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))]
+    deps = [os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith((".cu", ".cuh"))]
     deps.append(os.path.join(os.path.dirname(HERE), "include", "desman_b200.h"))
     return any(os.path.getmtime(d) > t for d in deps)
 
