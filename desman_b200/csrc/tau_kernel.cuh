@@ -51,7 +51,9 @@ struct TauParams {
 };
 
 #define TAU_WARPS 8
-#define TAU_GAP 60.0f            // nats; exp(-60) = 8.8e-27, 3*exp(-60) << 2^-32
+#ifndef TAU_GAP
+#define TAU_GAP 60.0f            // nats; exp(-60) = 8.8e-27, 3*exp(-60) << 2^-32 (26 would do for the 2^-32 grid: DESIGN.md section 7)
+#endif
 #define TAU_SLACK 1.0e-9         // absolute slack on CDF brackets evaluated in FP64
 #define TAU_SLACK32 1.0e-4       // ... and in FP32 fast math (tau_bracket_decide)
 
