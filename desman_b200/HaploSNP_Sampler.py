@@ -139,17 +139,21 @@ class HaploSNP_Sampler():
     # ------------------------------------------------------------------ device plumbing
     def _context(self, mode=RNG_PHILOX):
         """Device context (+ communicator of a sharded chain) without any data on it."""
-        if self._eng is None or self._eng_mode != mode:
-            sweep = _sampletau.global_sweep()
-            if self._eng is not None:
-                sweep = self._eng.get_rng()[0]
-                self._eng.close()
+        if self._eng is None:
             self._eng = Engine(self._device, self._seed, mode)
             if self._comm is not None:
                 self._eng.comm_init(*self._comm)
-            self._eng.set_rng(self._seed, sweep=sweep)
+            self._eng.set_rng(self._seed, sweep=_sampletau.global_sweep())
             self._eng_mode = mode
             self._counts_up = False
+        elif self._eng_mode != mode:
+            # ONE context for the life of the object: the stream of the tau draws is a per-call choice.  The Philox sweep
+            # counter and the position in the MT19937 stream both survive the switch (alternating sampleMu / update with
+            # sampleTau / updateTau under tau_rng="mt19937" continues both streams), the counts stay on the device and the
+            # communicator of a sharded sampler is not initialised twice.
+            self._eng.set_option("rng_mode", mode)
+            self._eng.rng_mode = mode
+            self._eng_mode = mode
         return self._eng
 
     def _engine(self, mode=RNG_PHILOX):
@@ -178,6 +182,9 @@ class HaploSNP_Sampler():
         eng.set_state(np.ascontiguousarray(tau, dtype=np.int64), gamma, eta, G=self.G)
 
     def _pull(self, eng, full=True):
+        # the process-global sweep counter follows every driver, so a sampler created while this one is still open (the
+        # not-selected sampler of bin/desman -r) starts past the counters this chain has used
+        _sampletau.advance_global_sweep(eng.get_rng()[0])
         self._tau_ix, self._tau_oh = eng.get_tau_index(), None
         if full:
             _, self.gamma, self.eta = eng.get_state(want_tau=False)

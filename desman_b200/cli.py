@@ -45,7 +45,13 @@ def build_parser():
 
 
 def main(argv=None):
-    args = build_parser().parse_args(argv)
+    parser = build_parser()
+    args = parser.parse_args(argv)
+    if args.filter_variants is not None:
+        # variant calling (Variant_Filter.py:320-390) is outside this engine's scope: say so before any
+        # output is created; run the reference's Variant_Filter first and pass its sel_var.csv here
+        parser.error("-f/--filter_variants is not implemented by desman_b200 (variant calling is outside the GPU hot path); "
+                     "filter with the reference's Variant_Filter and pass the selected variants")
     genomes = args.genomes
     if genomes < 0:
         logging.error('Only positive haplotype number valid not  %d. Exiting!' % genomes)

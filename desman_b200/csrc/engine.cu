@@ -598,7 +598,10 @@ extern "C" int desman_get_tau_index(desman_ctx *c, uint8_t *tau_idx)
     return DESMAN_OK;
 }
 
-extern "C" int desman_set_state(desman_ctx *c, const int64_t *tau, const double *gamma, const double *eta, int G)
+// gamma_zero_ok: the reference ABI path (c_sample_tau) takes gamma with whole strain columns at exactly 0.0 -- the masked
+// abundances of Eta_Sampler.maskGamma (Eta_Sampler.py:147-157,367), which the reference C accepts -- as long as every sample
+// keeps a positive mixture; the chain drivers need log(gamma) for the prior and keep the strict test.
+static int set_state_impl(desman_ctx *c, const int64_t *tau, const double *gamma, const double *eta, int G, bool gamma_zero_ok)
 {
     CU(cudaSetDevice(c->device));
     RET(ensure_state(c, G));
@@ -610,8 +613,16 @@ extern "C" int desman_set_state(desman_ctx *c, const int64_t *tau, const double 
         c->agg_valid = false;
     }
     if (gamma) {
-        for (size_t i = 0; i < (size_t)c->S * G; i++)
-            if (!(gamma[i] > 0.0)) return fail(DESMAN_EINVAL, "gamma[%zu] = %g must be > 0", i, gamma[i]);
+        for (int s = 0; s < c->S; s++) {
+            double row = 0.0;
+            for (int g = 0; g < G; g++) {
+                const double x = gamma[(size_t)s * G + g];
+                if (!(gamma_zero_ok ? x >= 0.0 : x > 0.0))
+                    return fail(DESMAN_EINVAL, "gamma[%zu] = %g must be %s 0", (size_t)s * G + g, x, gamma_zero_ok ? ">=" : ">");
+                row += x;
+            }
+            if (!(row > 0.0)) return fail(DESMAN_EINVAL, "gamma row %d has no positive entry", s);
+        }
         CU(cudaMemcpyAsync(c->gamma, gamma, (size_t)c->S * G * sizeof(double), cudaMemcpyHostToDevice, c->stream));
     }
     if (eta) {
@@ -620,6 +631,11 @@ extern "C" int desman_set_state(desman_ctx *c, const int64_t *tau, const double 
     }
     CU(cudaStreamSynchronize(c->stream));
     return DESMAN_OK;
+}
+
+extern "C" int desman_set_state(desman_ctx *c, const int64_t *tau, const double *gamma, const double *eta, int G)
+{
+    return set_state_impl(c, tau, gamma, eta, G, false);
 }
 
 static void index_to_onehot(const uint8_t *idx, size_t n, int64_t *tau)
@@ -1633,6 +1649,11 @@ extern "C" int desman_set_option(desman_ctx *c, const char *name, int64_t value)
     if (!strcmp(name, "fixed_tau")) { c->fixed_tau = value ? 1 : 0; return DESMAN_OK; }
     if (!strcmp(name, "mu_mode")) { c->mu_mode = (value == 0 || value == 1) ? (int)value : 2; return DESMAN_OK; }
     if (!strcmp(name, "pdl")) { c->pdl = value ? 1 : 0; return DESMAN_OK; }
+    // stream of the tau draws; the Philox sweep counter and the MT19937 position are both kept across a switch
+    if (!strcmp(name, "rng_mode")) {
+        if (value != DESMAN_RNG_MT19937 && value != DESMAN_RNG_PHILOX) return fail(DESMAN_EINVAL, "bad rng_mode %lld", (long long)value);
+        c->rng_mode = (int)value; return DESMAN_OK;
+    }
     if (!strcmp(name, "tau_group_mma")) { c->tau_group_mma = value ? 1 : 0; return DESMAN_OK; }
     if (!strcmp(name, "tau_group")) { c->tau_group = (value == 0 || value == 1) ? (int)value : 2; c->agg_valid = false; return DESMAN_OK; }
     return fail(DESMAN_EINVAL, "unknown option '%s'", name);
@@ -1729,7 +1750,7 @@ extern "C" int c_sample_tau(long *anTau, double *adPi, double *adEta, long *anVa
     if (!anTau || !adPi || !adEta || !anVariants || nV <= 0 || nG <= 0 || nS <= 0) { fail(DESMAN_EINVAL, "c_sample_tau: bad arguments"); return -1; }
     // the reference borrows all four arrays for the call and retains nothing (c_sample_tau.c:107-114,192-195)
     if (desman_set_counts(c, (const int64_t *)anVariants, nV, nS, 0, nV) != DESMAN_OK) return -1;
-    if (desman_set_state(c, (const int64_t *)anTau, adPi, adEta, nG) != DESMAN_OK) return -1;
+    if (set_state_impl(c, (const int64_t *)anTau, adPi, adEta, nG, true) != DESMAN_OK) return -1;
     std::vector<uint8_t> before((size_t)nV * nG), after((size_t)nV * nG);
     if (desman_get_tau_index(c, before.data()) != DESMAN_OK) return -1;
     int64_t nchange = 0;

@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(TG_MAX_WARPS * 32, 1) tau_group_kernel(TauGrou
         const double x = (s < S) ? p.gamma[(size_t)s * G + g] : 0.0;
         gT[i] = x;
         gT32[i] = (float)x;
-        if (s < S) gmin_l = fminf(gmin_l, fmaxf((float)x, 0.f));
+        if (s < S && x > 0.0) gmin_l = fminf(gmin_l, (float)x);     // masked strains (gamma == 0): q = P there
     }
     atomicMin(&gmin_bits, __float_as_uint(gmin_l));
     if (threadIdx.x < 16) {
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 16 / TGM_WARPS) tau_group_mma_
         const double x = (s < S) ? p.gamma[(size_t)s * G + g] : 0.0;
         gT[i] = x;
         gT32[i] = (float)x;
-        if (s < S) gmin_l = fminf(gmin_l, fmaxf((float)x, 0.f));
+        if (s < S && x > 0.0) gmin_l = fminf(gmin_l, (float)x);     // masked strains (gamma == 0): q = P there
     }
     atomicMin(&gmin_bits, __float_as_uint(gmin_l));
     if (tid < 16) {

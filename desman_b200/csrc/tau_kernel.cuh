@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
         const double x = (s < S) ? p.gamma[(size_t)s * G + g] : 0.0;
         gT[i] = x;
         gT32[i] = (float)x;
-        if (s < S) gmin_l = fminf(gmin_l, fmaxf((float)x, 0.f));
+        if (s < S && x > 0.0) gmin_l = fminf(gmin_l, (float)x);     // masked strains (gamma == 0): q = P there
     }
     atomicMin(&gmin_bits, __float_as_uint(gmin_l));
     if (threadIdx.x < 16) {

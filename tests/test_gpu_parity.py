@@ -354,3 +354,71 @@ def test_tau_fast_path_long_chain_equals_exact_at_C2_size(eng_mod):
     assert np.array_equal(res[0][2], res[1][2])
     t = res[0][3]
     assert t[2] < 0.01 * t.sum()            # the FP64 recompute is the rare path
+
+
+# ------------------------------------------------------------------ round-2 advisor findings
+def test_dropin_masked_gamma_columns_vs_reference_C(oracle_mod):
+    """Eta_Sampler.sampleTauC hands sample_tau a gamma whose columns are exactly 0.0 for the strains a gene lacks
+    (maskGamma, Eta_Sampler.py:147-157,367).  The reference C accepts that; so must the drop-in, with identical draws
+    (the step of a masked strain is a uniform draw over the four bases: all candidates leave the mixture unchanged)."""
+    import ctypes as C
+    from desman_b200 import _lib, sampletau
+    V, S, G = 400, 40, 6
+    p = synth_problem(V, S, G, depth=25.0, seed=77, ambiguous=True)
+    rng = np.random.default_rng(3)
+    use_ref = oracle_mod.have_ref()
+    seed = 99
+    tau_g, tau_r = onehot(p["tau0"]), onehot(p["tau0"])
+    if use_ref:
+        R = oracle_mod.RefSampleTau(seed)
+    else:
+        st = oracle_mod.MT19937()
+        oracle_mod.lib().oracle_mt_seed(C.byref(st), seed)
+    sampletau.initRNG(); sampletau.setRNG(seed)
+    for k, masked in enumerate([(1,), (0, 4), (2, 3, 5), ()]):
+        gamma = rng.dirichlet(np.ones(G), size=S)
+        gamma[:, list(masked)] = 0.0
+        gamma /= gamma.sum(1)[:, None]
+        n_gpu = sampletau.sample_tau(tau_g, gamma, p["eta0"], p["counts"])
+        if use_ref:
+            n_ref = R.sample_tau(tau_r, gamma, p["eta0"], p["counts"])
+        else:
+            n_ref = oracle_mod.lib().oracle_sample_tau_mt(
+                tau_r.ctypes.data_as(oracle_mod._p64), oracle_mod._f64(gamma)[1], oracle_mod._f64(p["eta0"])[1],
+                oracle_mod._i64(p["counts"])[1], V, G, S, C.byref(st))
+        assert n_gpu == n_ref and np.array_equal(tau_g, tau_r), (k, masked)
+    # a sample whose whole mixture is zero stays an error (log 0 in the reference)
+    gamma = rng.dirichlet(np.ones(G), size=S); gamma[3, :] = 0.0
+    with pytest.raises(_lib.DesmanB200Error, match="no positive entry"):
+        sampletau.sample_tau(tau_g, gamma, p["eta0"], p["counts"])
+    sampletau.freeRNG()
+    if use_ref:
+        R.close()
+
+
+def test_sampler_keeps_both_streams_across_rng_mode_switches(oracle_mod):
+    """tau_rng='mt19937': sampleTau (MT19937 words) interleaved with sampleMu / sampleGamma (Philox counters) on ONE sampler.
+    Every sampleTau must consume the NEXT V*G words of the GSL stream -- not restart it -- and the context is not re-created."""
+    from numpy.random import RandomState
+    from desman_b200 import sampletau
+    from desman_b200.HaploSNP_Sampler import HaploSNP_Sampler
+    V, S, G = 300, 24, 4
+    p = synth_problem(V, S, G, depth=6.0, seed=12, ambiguous=True)
+    seed = 4242
+    sampletau.initRNG(); sampletau.setRNG(seed)
+    hs = HaploSNP_Sampler(p["counts"], G, RandomState(1), max_iter=2, tau_rng="mt19937")
+    hs.tau = onehot(p["tau0"]); hs.gamma = p["gamma0"].copy()
+    tau_o = onehot(p["tau0"])
+    words = oracle_mod.mt_words(seed, 3 * V * G)
+    eng_ids = []
+    for k in range(3):
+        n = hs.sampleTau()
+        eng_ids.append(id(hs._eng))
+        n_o = oracle_mod.sample_tau_words(tau_o, hs.gamma, hs.eta, p["counts"], words[k * V * G:(k + 1) * V * G])
+        assert n == n_o and np.array_equal(hs.tau, tau_o), k
+        sm, es = hs.sampleMu(hs.tau, hs.gamma, hs.eta)         # Philox-mode calls in between
+        assert sm.sum() == p["counts"].sum()
+        hs.sampleGamma(); hs.sampleEta()
+    assert len(set(eng_ids)) == 1
+    hs.close()
+    sampletau.freeRNG()
