@@ -130,4 +130,6 @@ enum { GC_REGROUP = 0,   // regroup wanted (finalize_sweep sets it when orphans 
        GC_CALM = 2,      // the previous sweep flipped few sites: the screening pass pays off
        GC_NITEMS = 3, GC_NSINGLES = 4, GC_NWORK = 5, GC_CURSOR = 6,
        GC_ORPHANS = 7,   // sites that changed pattern since the last regroup (screened out by their slot mismatch)
-       GC_COUNT = 8 };
+       GC_IMG_OK = 8,    // the fp16 count image of the tensor-memory screening pass (tau_group_tc_kernel.cuh) was built and fits
+       GC_IMG_ROWS = 9,  // its padded row count
+       GC_COUNT = 12 };

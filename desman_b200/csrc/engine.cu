@@ -21,6 +21,7 @@
 #include "nmft_kernel.cuh"
 #include "tau_kernel.cuh"
 #include "tau_group_kernel.cuh"
+#include "tau_group_tc_kernel.cuh"
 #include "state_kernel.cuh"
 #include "maintain_kernel.cuh"
 #include "exchange_kernel.cuh"
@@ -152,6 +153,11 @@ struct desman_ctx {
     // pattern groups for the screening pass of the tau update (tau_group_kernel.cuh)
     int tau_group = 2;                       // 0: off, 1: on, 2: on iff the ~12*2^G biallelic patterns are <= V/2
     int tau_group_mma = 1;                   // 1: tensor-core form of the screening pass where it applies; 0: FFMA form
+    int tau_group_tc = 1;                    // 1: tcgen05 / TMEM / TMA form (tau_group_tc_kernel.cuh) where it applies; 0: mma.sync / FFMA forms
+    unsigned char *img = nullptr;            // fp16x4 count image in UMMA operand order
+    int *img_site = nullptr, *site_row = nullptr;
+    float *img_nsite = nullptr;
+    size_t img_cap_rows = 0, img_bytes = 0, img_cap_v = 0;
     bool counts_tf32_exact = false;
     float4 *countsf = nullptr;               // [V][S] FP32 copy of the counts
     float *nsite = nullptr;                  // [V]
@@ -313,6 +319,7 @@ extern "C" int desman_ctx_create(desman_ctx **out, int device, uint64_t seed, in
     { const char *pd = getenv("DESMAN_B200_PDL"); if (pd) c->pdl = atoi(pd) ? 1 : 0; }
     { const char *ex = getenv("DESMAN_B200_TAU_EXACT"); c->tau_exact = (ex && atoi(ex)) ? 1 : 0; }
     { const char *tg = getenv("DESMAN_B200_TAU_GROUP"); if (tg) c->tau_group = atoi(tg); if (c->tau_group < 0 || c->tau_group > 2) c->tau_group = 2; }
+    { const char *tc = getenv("DESMAN_B200_TAU_GROUP_TC"); if (tc) c->tau_group_tc = atoi(tc) ? 1 : 0; }
     { const char *mm = getenv("DESMAN_B200_MU_MODE"); if (mm) c->mu_mode = atoi(mm); if (c->mu_mode < 0 || c->mu_mode > 2) c->mu_mode = 2; }
     CU(dmalloc(c, &c->mt_state, 624 * sizeof(uint32_t)));
     CU(cudaMemset(c->scal, 0, 4 * sizeof(double)));
@@ -331,6 +338,7 @@ extern "C" int desman_ctx_destroy(desman_ctx *c)
     }
     if (c->xch_err) cudaFree(c->xch_err);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
+    for (void *q : {(void *)c->img, (void *)c->img_site, (void *)c->img_nsite, (void *)c->site_row}) if (q) dfree(c, q);
     void *ptrs[] = {c->counts, c->tau, c->tau_star, c->gamma, c->eta, c->eta_new, c->gamma_star, c->eta_star, c->stats,
                     c->red_base, c->agg_ctl, c->scal, c->flag, c->tau_cnt, c->tau_last, c->mt_state, c->words,
                     c->scratch, c->flush_buf, c->tiers, c->agg_keys, c->agg_code, c->agg_N, c->agg_ids, c->agg_nslots, c->agg_classM,
@@ -722,7 +730,7 @@ static int ensure_agg(desman_ctx *c)
         CU(dmalloc(c, &c->grp_site_slot, V * sizeof(int)));
         CU(dmalloc(c, &c->grp_order, V * sizeof(int)));
         CU(dmalloc(c, &c->grp_singles, V * sizeof(int)));
-        CU(dmalloc(c, &c->grp_slot4, 4 * c->agg_cap_slots * sizeof(int)));
+        CU(dmalloc(c, &c->grp_slot4, 5 * c->agg_cap_slots * sizeof(int)));
         CU(dmalloc(c, &c->grp_items, 2 * (V / 2 + V / TG_ITEM_SITES + 64) * sizeof(int4)));
         CU(dmalloc(c, &c->grp_work, V * sizeof(uint2)));
         c->grp_cap_v = V; c->grp_cap_slots = c->agg_cap_slots;
@@ -731,7 +739,7 @@ static int ensure_agg(desman_ctx *c)
     if (!c->grp_gctl) {
         CU(dmalloc(c, &c->grp_gctl, GC_COUNT * sizeof(int)));
         CU(cudaMemsetAsync(c->grp_gctl, 0, GC_COUNT * sizeof(int), c->stream));
-        CU(dmalloc(c, &c->grp_blk, 4 * 2048 * sizeof(int)));
+        CU(dmalloc(c, &c->grp_blk, 8 * 2048 * sizeof(int)));
     }
     // fixed-point scale of the log-likelihood accumulator: |sum n log p| <= reads * 88 must stay below 2^62
     const double reads = (c->total_reads > 1.0 ? c->total_reads : 1.0) * ((double)c->V_total / (double)c->V);
@@ -773,10 +781,31 @@ static bool group_use_mma(const desman_ctx *c)
            tg_shared_bytes(c->S, c->G) + tgm_table_bytes(c->S, c->G) + 1024 <= 200 * 1024;
 }
 
+// Shape of the tensor-memory screening pass: K blocks of <= 64 samples (balanced, multiples of 4), table columns padded to 8
+// (the widest K block of 64, 32 or 16 samples whose two count stages and two table buffers fit in shared memory)
+static bool tc_shape(const desman_ctx *c, int *SK, int *nkb, int *NC)
+{
+    *NC = (3 * c->G + 7) & ~7;
+    for (int kmax = 64; kmax >= 16; kmax >>= 1) {
+        const int nb = (c->S + kmax - 1) / kmax;
+        *nkb = nb;
+        *SK = (((c->S + nb - 1) / nb) + 3) & ~3;
+        if (tc_layout(c->S, c->G, *SK, *nkb, *NC).total + 2048 <= 227 * 1024) return true;
+    }
+    return false;
+}
+static bool group_use_tc(const desman_ctx *c)
+{
+    if (!c->tau_group_tc || !c->counts_tf32_exact || 3 * c->G > 64) return false;       // counts < 2048: exact in FP16
+    int SK, nkb, NC;
+    return tc_shape(c, &SK, &nkb, &NC);
+}
+
 static bool group_config(const desman_ctx *c, int *gb, int *warps)
 {
     if (c->tau_group == 0 || c->tau_exact) return false;
     if (c->tau_group == 2 && !(c->G <= 24 && 12.0 * ldexp(1.0, c->G) <= (double)c->V / 2.0)) return false;
+    if (group_use_tc(c)) return true;
     if (group_use_mma(c)) return true;
     const int r = c->G % 8, GB = (r >= 1 && r <= 4) ? 4 : 8;
     const size_t table = tg_table_bytes(c->S, c->G, GB), shared = tg_shared_bytes(c->S, c->G) + 1024;
@@ -801,6 +830,30 @@ static TauGroup group_ptrs(desman_ctx *c)
     return g;
 }
 
+// fp16 count image + row tables of the tensor-memory screening pass: capacity 2 V + 1024 rows (every multi-site pattern is
+// padded to a multiple of 8 rows; a regroup that needs more switches the pass off for that grouping, GC_IMG_OK)
+static int ensure_img(desman_ctx *c)
+{
+    int SK, nkb, NC;
+    tc_shape(c, &SK, &nkb, &NC);
+    const size_t rows = (((size_t)2 * c->V + 1024) + 7) & ~(size_t)7;
+    const size_t bytes = rows * (size_t)SK * nkb * 8;
+    if (rows > c->img_cap_rows || bytes > c->img_bytes || (size_t)c->V > c->img_cap_v) {
+        for (void *q : {(void *)c->img, (void *)c->img_site, (void *)c->img_nsite, (void *)c->site_row}) if (q) dfree(c, q);
+        c->img = nullptr; c->img_site = c->site_row = nullptr; c->img_nsite = nullptr; c->img_cap_rows = c->img_bytes = c->img_cap_v = 0;
+        CU(dmalloc(c, &c->img, bytes));
+        CU(dmalloc(c, &c->img_site, rows * sizeof(int)));
+        CU(dmalloc(c, &c->img_nsite, rows * sizeof(float)));
+        CU(dmalloc(c, &c->site_row, (size_t)c->V * sizeof(int)));
+        CU(cudaMemsetAsync(c->img, 0, bytes, c->stream));
+        CU(cudaMemsetAsync(c->img_site, 0, rows * sizeof(int), c->stream));
+        CU(cudaMemsetAsync(c->img_nsite, 0, rows * sizeof(float), c->stream));
+        c->img_cap_rows = rows; c->img_bytes = bytes; c->img_cap_v = (size_t)c->V;
+        c->agg_valid = false;     // filled by the next regroup
+    }
+    return DESMAN_OK;
+}
+
 static int ensure_countsf(desman_ctx *c)
 {
     const size_t ncell = (size_t)c->V * c->S;
@@ -823,7 +876,9 @@ static int sync_table(desman_ctx *c, bool deferred_star_copy = false)
 {
     RET(ensure_agg(c));
     const bool grouping = group_config(c, nullptr, nullptr);
+    const bool use_tc = grouping && group_use_tc(c);
     if (grouping) RET(ensure_countsf(c));
+    if (use_tc) RET(ensure_img(c));
     if (!c->agg_valid) {
         const int zero = 0;   // new counts / state: the groups (and the row copy that follows them) are rebuilt with the table
         CU(cudaMemcpyAsync(c->grp_gctl + GC_HAVE, &zero, sizeof(int), cudaMemcpyHostToDevice, c->stream));
@@ -850,6 +905,15 @@ static int sync_table(desman_ctx *c, bool deferred_star_copy = false)
     p.red_i = c->red_i;
     p.countsf = c->countsf; p.nsite = c->nsite;
     p.star_flag = deferred_star_copy ? c->flag : nullptr; p.tau_star = c->tau_star;
+    p.item_sites = use_tc ? TC_ROWS : TG_ITEM_SITES;
+    p.img = nullptr; p.img_site = nullptr; p.img_nsite = nullptr; p.site_row = nullptr; p.slot_img = nullptr;
+    p.img_cap_rows = 0; p.SK = 4; p.nkb = 1;
+    if (use_tc) {
+        int NC;
+        tc_shape(c, &p.SK, &p.nkb, &NC);
+        p.img = c->img; p.img_site = c->img_site; p.img_nsite = c->img_nsite; p.site_row = c->site_row;
+        p.slot_img = c->grp_slot4 + 4 * c->grp_cap_slots; p.img_cap_rows = (long long)c->img_cap_rows;
+    }
     void *args[] = {&p};
     {
         KSpan k(c, DESMAN_K_MAINT);
@@ -903,6 +967,20 @@ static int launch_tau_group_mma_t(desman_ctx *c, const TauGroupParams &p)
     return DESMAN_OK;
 }
 
+static int launch_tau_group_tc(desman_ctx *c, const TauGroupParams &q, float *dbg)
+{
+    TauGroupTcParams p;
+    tc_shape(c, &p.SK, &p.nkb, &p.NC);
+    p.img = c->img; p.img_site = c->img_site; p.img_nsite = c->img_nsite; p.img_rg = (long long)(c->img_cap_rows / 8);
+    p.gamma = q.gamma; p.eta = q.eta; p.words = q.words; p.V = q.V; p.S = q.S; p.G = q.G;
+    p.grp = q.grp; p.tier_counts = q.tier_counts; p.dbg = dbg;
+    const size_t smem = tc_layout(c->S, c->G, p.SK, p.nkb, p.NC).total;
+    CU(cudaFuncSetAttribute(tau_group_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(launch_k(c, tau_group_tc_kernel, c->sm_count, TC_THREADS, smem, p));
+    CU(cudaGetLastError());
+    return DESMAN_OK;
+}
+
 template <int GB>
 static int launch_tau_group_t(desman_ctx *c, const TauGroupParams &p, int warps)
 {
@@ -937,6 +1015,7 @@ static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, boo
     p.exact_only = c->tau_exact;
     p.tier_counts = c->tiers;
     p.work = nullptr; p.singles = nullptr; p.gctl = nullptr; p.site_slot = nullptr;
+    p.img_site = nullptr; p.site_row = nullptr; p.need_img = 0;
     int gb = 8, gwarps = 1;
     if (p.agg.N && group_config(c, &gb, &gwarps)) {
         TauGroupParams q;
@@ -946,7 +1025,10 @@ static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, boo
         q.tier_counts = c->tiers;
         {
             KSpan k(c, DESMAN_K_TAU_GROUP);
-            if (group_use_mma(c)) {
+            if (group_use_tc(c)) {
+                RET(launch_tau_group_tc(c, q, nullptr));
+                p.img_site = c->img_site; p.site_row = c->site_row; p.need_img = 1;
+            } else if (group_use_mma(c)) {
                 switch (tgm_tiles(c->G)) {
                 case 1: RET(launch_tau_group_mma_t<1>(c, q)); break;
                 case 2: RET(launch_tau_group_mma_t<2>(c, q)); break;
@@ -1339,6 +1421,40 @@ extern "C" int desman_state_logprob(desman_ctx *c, const int64_t *variants, int6
     return rc;
 }
 
+// Validation of the tensor-memory screening pass (tests only): regroup the current state and return, per site, the 3G sums
+// D[v][3g+j] (log2 units) its contraction produced (NaN: the site is in no group) and the site's undecided-strain mask
+// (0xffffffff: not listed = every step decided "stay").
+extern "C" int desman_debug_screen(desman_ctx *c, float *D, uint32_t *mask)
+{
+    RET(require_state(c));
+    if (!group_config(c, nullptr, nullptr) || !group_use_tc(c))
+        return fail(DESMAN_ESTATE, "desman_debug_screen: the tensor-memory screening pass does not apply to this shape / option set");
+    RET(sync_table(c));
+    const size_t n = (size_t)c->V * 3 * c->G;
+    float *dD = nullptr;
+    CU(dmalloc(c, &dD, n * sizeof(float)));
+    CU(cudaMemsetAsync(dD, 0xff, n * sizeof(float), c->stream));
+    TauGroupParams q;
+    q.countsf = c->countsf; q.nsite = c->nsite; q.gamma = c->gamma; q.eta = c->eta; q.words = nullptr;
+    q.V = (int)c->V; q.S = c->S; q.G = c->G; q.grp = group_ptrs(c); q.tier_counts = nullptr;
+    int rc = launch_tau_group_tc(c, q, dD);
+    if (rc == DESMAN_OK && D) CU(cudaMemcpyAsync(D, dD, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    int g[GC_COUNT];
+    CU(cudaMemcpyAsync(g, c->grp_gctl, sizeof(g), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    dfree(c, dD);
+    if (rc != DESMAN_OK) return rc;
+    if (!g[GC_IMG_OK]) return fail(DESMAN_ESTATE, "desman_debug_screen: the count image did not fit (%d rows)", g[GC_IMG_ROWS]);
+    if (mask) {
+        for (size_t v = 0; v < (size_t)c->V; v++) mask[v] = 0xffffffffu;
+        std::vector<uint2> w((size_t)g[GC_NWORK]);
+        if (!w.empty()) CU(cudaMemcpyAsync(w.data(), c->grp_work, w.size() * sizeof(uint2), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        for (auto &e : w) mask[e.x] = e.y;
+    }
+    return DESMAN_OK;
+}
+
 // ------------------------------------------------------------------------------------------ chains
 static int alloc_stores(desman_ctx *c, int n_iter, bool with_ge, StoreBufs *sb, const double *h_gs, const double *h_es)
 {
@@ -1655,6 +1771,7 @@ extern "C" int desman_set_option(desman_ctx *c, const char *name, int64_t value)
         c->rng_mode = (int)value; return DESMAN_OK;
     }
     if (!strcmp(name, "tau_group_mma")) { c->tau_group_mma = value ? 1 : 0; return DESMAN_OK; }
+    if (!strcmp(name, "tau_group_tc")) { c->tau_group_tc = value ? 1 : 0; c->agg_valid = false; return DESMAN_OK; }
     if (!strcmp(name, "tau_group")) { c->tau_group = (value == 0 || value == 1) ? (int)value : 2; c->agg_valid = false; return DESMAN_OK; }
     return fail(DESMAN_EINVAL, "unknown option '%s'", name);
 }

@@ -10,6 +10,7 @@
 #include <cooperative_groups.h>
 #include "common.cuh"
 #include "mu_agg_kernel.cuh"
+#include <cuda_fp16.h>
 #include "tau_group_kernel.cuh"
 
 namespace cg = cooperative_groups;
@@ -27,6 +28,16 @@ struct MaintParams {
     // if (*star_flag) tau_star <- tau, in place of a separate copy_tau_if launch per sweep; star_flag == nullptr: none
     const int *star_flag;
     uint8_t *tau_star;
+    int item_sites;              // sites per work item (multiple of 8): TG_ITEM_SITES, or TC_ROWS for the tensor-memory pass
+    // count image of the tensor-memory screening pass (tau_group_tc_kernel.cuh), or img == nullptr: fp16x4 cells in the
+    // K-major no-swizzle UMMA order [K block][row group][KC chunks][8 rows][16 bytes]; every item starts at a multiple of 8 rows
+    unsigned char *img;
+    int *img_site;               // [img_cap_rows] site of an image row (~site once the site has left its group)
+    float *img_nsite;            // [img_cap_rows]
+    int *site_row;               // [V] image row of a site, -1: none (singles)
+    int *slot_img;               // [cap_slots] first image row of a slot's items
+    long long img_cap_rows;
+    int SK, nkb;                 // samples per K block, K blocks
 };
 
 #define MAINT_THREADS 256
@@ -125,6 +136,7 @@ __global__ void __launch_bounds__(MAINT_THREADS) table_maintain_kernel(MaintPara
     // scan, step 1: every block scans its segment of the slots: sites of multi-site patterns | full items | partial items |
     // singles.  Full items (TG_ITEM_SITES sites) are numbered before all partial ones, so the dynamic schedule of the
     // screening pass hands out the long items first and its tail is made of short ones.
+    const int ITEM = p.item_sites;
     const int seg = (nsl + (int)gridDim.x - 1) / (int)gridDim.x;
     const int lo = (int)blockIdx.x * seg, hi = min(nsl, lo + seg);
     {
@@ -132,7 +144,7 @@ __global__ void __launch_bounds__(MAINT_THREADS) table_maintain_kernel(MaintPara
         for (int base = lo; base < hi; base += MAINT_THREADS) {
             const int sl = base + (int)threadIdx.x;
             const int c = (sl < hi) ? p.grp.slot_cnt[sl] : 0;
-            const int4 val = make_int4(c >= 2 ? c : 0, c >= 2 ? c / TG_ITEM_SITES : 0, (c >= 2 && c % TG_ITEM_SITES) ? 1 : 0, c == 1 ? 1 : 0);
+            const int4 val = make_int4(c >= 2 ? c : 0, c >= 2 ? c / ITEM : 0, (c >= 2 && c % ITEM) ? 1 : 0, c == 1 ? 1 : 0);
             int4 tot;
             const int4 ex = block_excl_scan4(val, tot, sh);
             if (sl < hi) {
@@ -145,6 +157,18 @@ __global__ void __launch_bounds__(MAINT_THREADS) table_maintain_kernel(MaintPara
         if (threadIdx.x == 0) {
             p.blk[4 * blockIdx.x] = carry.x; p.blk[4 * blockIdx.x + 1] = carry.y; p.blk[4 * blockIdx.x + 2] = carry.z;
             p.blk[4 * blockIdx.x + 3] = carry.w;
+        }
+        if (p.img) {   // image rows: every multi-site slot padded to a multiple of 8 rows (items are multiples of 8 but the last)
+            int carry8 = 0;
+            for (int base = lo; base < hi; base += MAINT_THREADS) {
+                const int sl = base + (int)threadIdx.x;
+                const int c = (sl < hi) ? p.grp.slot_cnt[sl] : 0;
+                int4 tot;
+                const int4 ex = block_excl_scan4(make_int4(c >= 2 ? (c + 7) & ~7 : 0, 0, 0, 0), tot, sh);
+                if (sl < hi) p.slot_img[sl] = carry8 + ex.x;
+                carry8 += tot.x;
+            }
+            if (threadIdx.x == 0) p.blk[4 * gridDim.x + blockIdx.x] = carry8;
         }
     }
     grid.sync();
@@ -163,6 +187,21 @@ __global__ void __launch_bounds__(MAINT_THREADS) table_maintain_kernel(MaintPara
         if (gtid == 0) { gctl[GC_NITEMS] = all.y + all.z; gctl[GC_NSINGLES] = all.w; gctl[GC_HAVE] = 1; }
         __syncthreads();
     }
+    int off8 = 0;
+    bool img_ok = false;
+    if (p.img) {
+        int4 part = make_int4(0, 0, 0, 0), o8;
+        for (int b = (int)threadIdx.x; b < (int)gridDim.x; b += MAINT_THREADS) {
+            const int x = p.blk[4 * gridDim.x + b];
+            if (b < (int)blockIdx.x) part.x += x;
+            part.y += x;
+        }
+        block_excl_scan4(part, o8, sh);
+        __syncthreads();
+        off8 = o8.x;
+        img_ok = (long long)o8.y <= p.img_cap_rows;
+        if (gtid == 0) { gctl[GC_IMG_OK] = img_ok ? 1 : 0; gctl[GC_IMG_ROWS] = o8.y; }
+    }
     // step 3: global positions and the items of this block's slots
     for (int sl = lo + (int)threadIdx.x; sl < hi; sl += MAINT_THREADS) {
         const int c = p.grp.slot_cnt[sl];
@@ -170,15 +209,19 @@ __global__ void __launch_bounds__(MAINT_THREADS) table_maintain_kernel(MaintPara
         else if (c >= 2) {
             const int st = p.grp.slot_start[sl] + off.x, it0 = p.grp.slot_item[sl] + off.y, itp = all.y + off.z + p.grp.slot_fill[sl];
             p.grp.slot_start[sl] = st;
-            const int nfull = c / TG_ITEM_SITES;
+            const int nfull = c / ITEM;
             const unsigned long long code = t.slot_code[sl];
-            const int4 rec1 = make_int4((int)(unsigned int)code, (int)(unsigned int)(code >> 32), 0, 0);
+            int img0 = 0;                                           // first image row of the slot (a multiple of 8)
+            if (p.img) { img0 = p.slot_img[sl] + off8; p.slot_img[sl] = img0; }
+            int4 rec1 = make_int4((int)(unsigned int)code, (int)(unsigned int)(code >> 32), 0, 0);
             for (int j = 0; j < nfull; j++) {
-                p.grp.items[2 * (it0 + j)] = make_int4(sl, st + j * TG_ITEM_SITES, TG_ITEM_SITES, 0);
+                p.grp.items[2 * (it0 + j)] = make_int4(sl, st + j * ITEM, ITEM, 0);
+                rec1.z = img0 + j * ITEM;
                 p.grp.items[2 * (it0 + j) + 1] = rec1;
             }
-            if (c % TG_ITEM_SITES) {
-                p.grp.items[2 * itp] = make_int4(sl, st + nfull * TG_ITEM_SITES, c % TG_ITEM_SITES, 0);
+            if (c % ITEM) {
+                p.grp.items[2 * itp] = make_int4(sl, st + nfull * ITEM, c % ITEM, 0);
+                rec1.z = img0 + nfull * ITEM;
                 p.grp.items[2 * itp + 1] = rec1;
             }
         }
@@ -204,5 +247,33 @@ __global__ void __launch_bounds__(MAINT_THREADS) table_maintain_kernel(MaintPara
         }
         tot = (long long)warp_sum_u64((unsigned long long)tot);
         if (lane == 0) p.nsite[pos] = __ll2float_ru(tot);
+    }
+    if (!p.img) return;
+    // the same rows as fp16x4 cells (exact: the host enables this pass only when every count < 2048) in the operand order of
+    // the tensor-memory screening pass; samples beyond S inside the last K block are written as zeros
+    for (size_t v = gtid; v < (size_t)V; v += gsz) p.site_row[v] = -1;
+    if (!img_ok) return;
+    grid.sync();
+    const int KC = p.SK / 2, Spad = p.SK * p.nkb;
+    const size_t kb_stride = (size_t)(p.img_cap_rows / 8) * KC * 128;
+    for (int pos = gw; pos < nrows; pos += nw) {
+        const int v = p.grp.order[pos];
+        const int sl = p.grp.site_slot[v];
+        const int row = p.slot_img[sl] + (pos - p.grp.slot_start[sl]);
+        long long tot = 0;
+        for (int s2 = lane; s2 < Spad; s2 += 32) {
+            int4 n = make_int4(0, 0, 0, 0);
+            if (s2 < S) n = ld_counts(p.a.counts + (size_t)v * S + s2);
+            tot += (long long)n.x + n.y + n.z + n.w;
+            const int kb = s2 / p.SK, sl2 = s2 - kb * p.SK;
+            uint2 cell;
+            cell.x = (uint32_t)__half_as_ushort(__int2half_rn(n.x)) | ((uint32_t)__half_as_ushort(__int2half_rn(n.y)) << 16);
+            cell.y = (uint32_t)__half_as_ushort(__int2half_rn(n.z)) | ((uint32_t)__half_as_ushort(__int2half_rn(n.w)) << 16);
+            unsigned char *dst = p.img + (size_t)kb * kb_stride + ((size_t)(row >> 3) * KC + (size_t)(sl2 >> 1)) * 128 +
+                                 (size_t)(row & 7) * 16 + (size_t)(sl2 & 1) * 8;
+            *reinterpret_cast<uint2 *>(dst) = cell;
+        }
+        tot = (long long)warp_sum_u64((unsigned long long)tot);
+        if (lane == 0) { p.img_site[row] = v; p.img_nsite[row] = __ll2float_ru(tot); p.site_row[v] = row; }
     }
 }

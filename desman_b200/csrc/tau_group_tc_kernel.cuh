@@ -1,0 +1,473 @@
+// desman_b200/csrc/tau_group_tc_kernel.cuh -- K1t: the screening pass of the tau Gibbs update (c_sample_tau.c:130-188) on the
+// Blackwell tensor path: TMA bulk copies (cp.async.bulk + mbarrier) stage the count rows in shared memory, tcgen05.mma
+// contracts them with the pattern's table, the sums live in tensor memory and come back with tcgen05.ld.
+//
+// What is computed is exactly what tau_group_kernel.cuh describes: for a work item (one haplotype pattern, <= 128 sites) the
+// log-likelihood differences of a site's G steps are a dense contraction of its count row with the pattern's table,
+//     D[site][c] = sum_{s,b} n[site][s][b] * Wd[c][s][b],      c = 3 g + j,   Wd = lg2(q) - lg2(P)  (same FP32 arithmetic),
+// a [sites x 4S] x [4S x 3G] product.  Here the SITES are the M dimension of the MMA (128 rows = 128 TMEM lanes, one thread of the
+// epilogue per site: the 3G sums of a site sit in ONE thread's registers and the gap test needs no shuffle) and the table
+// columns the N dimension.  Operands are FP16 (kind::f16, FP32 accumulation in TMEM):
+//   * counts < 2048 are exact in FP16 (11-bit significand): the group-ordered copy of the count rows is kept as fp16x4 cells
+//     (8 bytes per (v,s) instead of 16: the pass reads HALF the bytes of the canonical int32x4 tensor);
+//   * a table entry is split as  Wd = h + l/1024,  h = fp16(Wd), l = fp16((Wd - h)*1024)  (|Wd - h - l/1024| <= 2^-22 |Wd|; the
+//     scaling keeps l normal); h and l are separate columns of the B operand (N = 2*NC), summed by the epilogue.
+// Layout (no swizzle, K-major, the canonical "interleaved" UMMA layout): 8 rows x 16 bytes form a 128-byte core matrix; core
+// matrices that are neighbours along K are LBO = 128 bytes apart, 8-row groups SBO = KC*128 bytes apart (KC = 16-byte chunks
+// per K block).  The regroup pass (maintain_kernel.cuh) writes the count image in exactly this order, every work item padded
+// to a multiple of 8 rows, so the rows of an item for one K block are ONE contiguous span of global memory: one
+// cp.async.bulk per (item, K block), no tensor map, no register staging.
+// Roles (warp-specialised, one persistent CTA per SM; everything between them goes through mbarriers):
+//   warps 0-3   epilogue: TMEM -> registers (warp w owns lanes 32w..32w+31), gap test, work list
+//   warp 4      producer: work tickets, item records, bulk copies of the count rows (2-stage ring)
+//   warp 5      MMA issuer (one elected lane)
+//   warps 6-13  table builders: mixture P in FP64, the 12 lg2 per (strain, sample), fp16 split, stores in B-operand order
+// Results are those of the FFMA / mma.sync forms draw for draw (the error model below is charged instead of theirs).
+#pragma once
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "mu_agg_kernel.cuh"
+#include "tau_kernel.cuh"
+#include "tau_group_kernel.cuh"
+
+#define TC_ROWS 128                 // sites per work item = M of the MMA
+#define TC_EPI_WARPS 4
+#define TC_BUILD_WARPS 8
+#define TC_THREADS ((TC_EPI_WARPS + 2 + TC_BUILD_WARPS) * 32)
+#define TC_NREC 4                   // item-record ring
+#define TC_LO_SCALE 1024.0f
+
+struct TauGroupTcParams {
+    const unsigned char *img;  // count image: [K block][row group][KC chunks][8 rows][16 bytes], fp16x4 cells
+    const int *img_site;       // [rows] site of an image row (-1: padding)
+    const float *img_nsite;    // [rows] reads of the row's site, rounded up
+    long long img_rg;          // row groups (of 8 rows) per K block of the image
+    const double *gamma;       // [S][G]
+    const double *eta;         // [16]
+    const uint32_t *words;     // MT19937 words [V*G] or nullptr (Philox)
+    int V, S, G;
+    int SK, nkb;               // samples per K block (multiple of 4, <= 64), K blocks
+    int NC;                    // table columns padded to a multiple of 8 (3G <= NC); N of the MMA = 2*NC
+    TauGroup grp;
+    unsigned long long *tier_counts;
+    float *dbg;                // [V][3G] the sums D (log2 units) of every screened site, or nullptr (validation only)
+};
+
+struct TcRec { int slot, count, img0; unsigned int code_lo, code_hi; int pad[3]; };
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier; the rows are read once per pass: evict first
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (FP16 operands, FP32 accumulation)
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 8 consecutive FP32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float (&v)[8])
+{
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the registers of a tcgen05.ld are defined only after tcgen05.wait::ld: re-define them (empty volatile asm, ordered after the
+// wait) so that no use can be scheduled ahead of it
+__device__ __forceinline__ void tc_launder8(float (&v)[8])
+{
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]));
+}
+
+// shared-memory matrix descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor: start >> 4 in [0,14), LBO >> 4 in [16,30),
+// SBO >> 4 in [32,46), version 1 in [46,48), layout type 0 = SWIZZLE_NONE in [61,64))
+__device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46);
+}
+
+// ------------------------------------------------------------------------------------------------ sizes (host + device)
+struct TcLayout {
+    int Sp, KC, N, acc_stride, tmem_cols;
+    size_t off_gT, off_eta, off_eta32, off_gT32, off_P, off_lP, off_rec, off_bar, off_stage, off_table, stage_bytes, table_bytes, total;
+};
+__host__ __device__ static inline TcLayout tc_layout(int S, int G, int SK, int nkb, int NC)
+{
+    TcLayout L;
+    L.Sp = SK * nkb;                                   // samples incl. padding
+    L.KC = SK / 2;                                     // 16-byte chunks per K block (4 samples = 2 chunks = one MMA K step)
+    L.N = 2 * NC;
+    L.acc_stride = L.N <= 32 ? 32 : L.N <= 64 ? 64 : L.N <= 128 ? 128 : 256;
+    L.tmem_cols = 2 * L.acc_stride < 32 ? 32 : 2 * L.acc_stride;
+    size_t o = 0;
+    L.off_gT = o; o += sizeof(double) * (size_t)G * L.Sp;
+    L.off_eta = o; o += sizeof(double) * 16;
+    L.off_P = o; o += sizeof(double) * 4 * (size_t)L.Sp;
+    L.off_eta32 = o; o += sizeof(float) * 16;
+    L.off_gT32 = o; o += sizeof(float) * (size_t)G * L.Sp;
+    L.off_lP = o; o += sizeof(float) * 4 * (size_t)L.Sp;
+    L.off_rec = o; o += sizeof(TcRec) * TC_NREC;
+    o = (o + 15) & ~(size_t)15;
+    L.off_bar = o; o += 8 * 24;
+    o = (o + 1023) & ~(size_t)1023;
+    L.stage_bytes = (size_t)(TC_ROWS / 8) * L.KC * 128;
+    L.table_bytes = (size_t)(L.N / 8) * L.KC * 128;
+    L.off_stage = o; o += 2 * L.stage_bytes;
+    L.off_table = o; o += 2 * L.table_bytes;
+    L.total = o;
+    return L;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+__global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcParams p)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];      // (no swizzle: the operands need 16-byte alignment only)
+    const int S = p.S, G = p.G, SK = p.SK, nkb = p.nkb, NC = p.NC;
+    const TcLayout L = tc_layout(S, G, SK, nkb, NC);
+    const int Sp = L.Sp, KC = L.KC;
+    double *gT = reinterpret_cast<double *>(smem + L.off_gT);           // [G][Sp]
+    double *eta_s = reinterpret_cast<double *>(smem + L.off_eta);       // [16]
+    double *P64 = reinterpret_cast<double *>(smem + L.off_P);           // [Sp][4] mixture of the item being built
+    float4 *eta32 = reinterpret_cast<float4 *>(smem + L.off_eta32);     // [4]
+    float *gT32 = reinterpret_cast<float *>(smem + L.off_gT32);         // [G][Sp]
+    float4 *lP = reinterpret_cast<float4 *>(smem + L.off_lP);           // [Sp] lg2 P
+    TcRec *rec = reinterpret_cast<TcRec *>(smem + L.off_rec);           // [TC_NREC]
+    const uint32_t bar0 = smem_u32(smem + L.off_bar);
+    // barriers: rec_full[4] rec_empty[4] cnt_full[2] cnt_empty[2] tab_full[2] tab_empty[2] acc_full[2] acc_empty[2]
+    const uint32_t rec_full = bar0, rec_empty = bar0 + 8 * 4, cnt_full = bar0 + 8 * 8, cnt_empty = bar0 + 8 * 10,
+                   tab_full = bar0 + 8 * 12, tab_empty = bar0 + 8 * 14, acc_full = bar0 + 8 * 16, acc_empty = bar0 + 8 * 18;
+    const uint32_t stage0 = smem_u32(smem + L.off_stage), table0 = smem_u32(smem + L.off_table);
+    __shared__ uint32_t tmem_base_s;
+    __shared__ unsigned int gmin_bits, emin_bits;
+    __shared__ int unnorm;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // ---- prologue that touches nothing of the preceding grid: barriers, zeroed operand buffers
+    if (tid == 0) {
+        for (int i = 0; i < TC_NREC; i++) { mbar_init(rec_full + 8 * i, 1); mbar_init(rec_empty + 8 * i, TC_EPI_WARPS); }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(cnt_full + 8 * i, 1); mbar_init(cnt_empty + 8 * i, 1);
+            mbar_init(tab_full + 8 * i, TC_BUILD_WARPS); mbar_init(tab_empty + 8 * i, 1);
+            mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, TC_EPI_WARPS);
+        }
+        gmin_bits = 0x7f800000u; emin_bits = 0x7f800000u; unnorm = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    {   // stages: rows beyond an item's own stay zero / finite; tables: padded columns and samples stay zero for good
+        uint4 *z = reinterpret_cast<uint4 *>(smem + L.off_stage);
+        const size_t n16 = (2 * L.stage_bytes + 2 * L.table_bytes) / 16;
+        for (size_t i = tid; i < n16; i += TC_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    pdl_enter();
+    KPROF_SCOPE(KP_TGM);
+    const int *gctl = p.grp.gctl;
+    if (!(gctl[GC_HAVE] && gctl[GC_CALM] && gctl[GC_IMG_OK])) return;
+    const int nitems = gctl[GC_NITEMS];
+    if ((int)blockIdx.x >= nitems) return;
+
+    if (warp == 0) {   // TMEM: two accumulators of N columns (allocation: power of two >= 32), owned by warp 0
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)L.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    float gmin_l = __int_as_float(0x7f800000);
+    for (int i = tid; i < G * Sp; i += TC_THREADS) {
+        const int g = i / Sp, s = i - g * Sp;
+        const double x = (s < S) ? p.gamma[(size_t)s * G + g] : 0.0;
+        gT[i] = x;
+        gT32[i] = (float)x;
+        if (s < S && x > 0.0) gmin_l = fminf(gmin_l, (float)x);
+    }
+    atomicMin(&gmin_bits, __float_as_uint(gmin_l));
+    if (tid < 16) {
+        eta_s[tid] = p.eta[tid];
+        reinterpret_cast<float *>(eta32)[tid] = (float)p.eta[tid];
+        atomicMin(&emin_bits, __float_as_uint(fmaxf((float)p.eta[tid], 0.f)));
+    }
+    fence_proxy_async();               // the zero fill above is read by the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    // unnormalised input (rows of gamma or eta summing to more than 1): no screening, every site goes to the per-site kernel
+    for (int s = tid; s < S + 4; s += TC_THREADS) {
+        double t = 0.0;
+        if (s < S) for (int g = 0; g < G; g++) t += gT[g * Sp + s];
+        else for (int b = 0; b < 4; b++) t += eta_s[4 * (s - S) + b];
+        if (!(t <= 1.0001)) unnorm = 1;
+    }
+    __syncthreads();
+    const uint32_t tmem_base = tmem_base_s;
+    const float qmin = 0.99f * __uint_as_float(gmin_bits) * __uint_as_float(emin_bits);
+    const bool fast_ok = qmin >= TAU_QMIN && !unnorm;
+    const float mq0 = fmaxf(1.0f, 1.0f - log2f(fmaxf(qmin, TAU_QMIN)));
+    // per read, log2 units: the entry model of the FFMA form (relative parts, lg2.approx floors, lg2.approx and the lq - lP
+    // rounding per unit of |lg2|, FP64 cancellation) + [fp16 split 2^-22 + one FP32 accumulation step per 4 samples and piece,
+    // each charged 2^-20 of the running magnitude + the hi + lo/1024 add] * max|Wd|, |Wd| <= mq0
+    const float e_entry = TAU_C0 + (2.3841858e-7f + 5.9604645e-8f) * (2.0f * mq0) + TAU_CANCEL(G) / fmaxf(qmin, TAU_QMIN);
+    const float e_mma = (float)(Sp / 2 + 12) * 9.5367432e-7f;
+    const float LN2 = 0.69314718f;
+    const float bn_scale = (e_entry + e_mma * mq0) * LN2 * 1.0001f;
+    const uint32_t fullG = (G >= 32) ? 0xffffffffu : ((1u << G) - 1u);
+    const uint32_t sbo = (uint32_t)KC * 128u;
+    const int ncol = 3 * G;
+
+    if (warp == TC_EPI_WARPS) {
+        // =============================================================== producer
+        if (lane == 0) {
+            const size_t kb_stride = (size_t)p.img_rg * KC * 128;
+            uint32_t u = 0;
+            for (uint32_t i = 0;; i++) {
+                const uint32_t r = i % TC_NREC;
+                mbar_wait(rec_empty + 8 * r, ((i / TC_NREC) & 1u) ^ 1u);
+                const int it = (i == 0) ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(p.grp.gctl + GC_CURSOR, 1);
+                TcRec rc;
+                rc.slot = 0; rc.count = 0; rc.img0 = 0; rc.code_lo = 0; rc.code_hi = 0; rc.pad[0] = rc.pad[1] = rc.pad[2] = 0;
+                if (it < nitems) {
+                    const int4 a = p.grp.items[2 * it], b = p.grp.items[2 * it + 1];
+                    rc.slot = a.x; rc.count = a.z; rc.img0 = b.z; rc.code_lo = (unsigned int)b.x; rc.code_hi = (unsigned int)b.y;
+                }
+                rec[r] = rc;
+                mbar_arrive(rec_full + 8 * r);                         // (release: the record is visible to the waiters)
+                if (rc.count == 0) break;
+                const uint32_t rows8 = ((uint32_t)rc.count + 7u) & ~7u;
+                const uint32_t bytes = rows8 * (uint32_t)KC * 16u;
+                for (int kb = 0; kb < nkb; kb++, u++) {
+                    const uint32_t cs = u & 1u;
+                    mbar_wait(cnt_empty + 8 * cs, ((u >> 1) & 1u) ^ 1u);
+                    mbar_arrive_tx(cnt_full + 8 * cs, bytes);
+                    tma_bulk_g2s(stage0 + cs * (uint32_t)L.stage_bytes,
+                                 p.img + (size_t)kb * kb_stride + (size_t)(rc.img0 >> 3) * KC * 128, bytes, cnt_full + 8 * cs);
+                }
+            }
+        }
+    } else if (warp == TC_EPI_WARPS + 1) {
+        // =============================================================== MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(L.N >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);   // F16 x F16 -> F32, K-major A and B
+            uint32_t u = 0;
+            for (uint32_t i = 0;; i++) {
+                const uint32_t r = i % TC_NREC;
+                mbar_wait(rec_full + 8 * r, (i / TC_NREC) & 1u);
+                if (rec[r].count == 0) break;
+                const uint32_t as = i & 1u;
+                mbar_wait(acc_empty + 8 * as, ((i >> 1) & 1u) ^ 1u);
+                const uint32_t d = tmem_base + as * (uint32_t)L.acc_stride;
+                for (int kb = 0; kb < nkb; kb++, u++) {
+                    const uint32_t cs = u & 1u;
+                    mbar_wait(tab_full + 8 * cs, (u >> 1) & 1u);
+                    mbar_wait(cnt_full + 8 * cs, (u >> 1) & 1u);
+                    tc_fence_after();
+                    const uint64_t a0 = tc_desc(stage0 + cs * (uint32_t)L.stage_bytes, 128u, sbo);
+                    const uint64_t b0 = tc_desc(table0 + cs * (uint32_t)L.table_bytes, 128u, sbo);
+                    for (int k = 0; k < KC / 2; k++)                      // one K step = 16 fp16 = 2 chunks = 256 bytes = 16 units
+                        tc_mma_f16(d, a0 + (uint64_t)(16 * k), b0 + (uint64_t)(16 * k), idesc, (kb | k) ? 1u : 0u);
+                    tc_commit(cnt_empty + 8 * cs);
+                    tc_commit(tab_empty + 8 * cs);
+                }
+                tc_commit(acc_full + 8 * as);
+            }
+        }
+    } else if (warp >= TC_EPI_WARPS + 2) {
+        // =============================================================== table builders (8 warps)
+        const int bt = tid - (TC_EPI_WARPS + 2) * 32, bw = bt >> 5;
+        constexpr int NB = TC_BUILD_WARPS * 32;
+        const int nl = (lane >> 1) & 7, shf = lane & 1, sp = lane >> 4;
+        const int noct = NC >> 3, nquad = SK >> 2;
+        uint32_t u = 0;
+        for (uint32_t i = 0;; i++) {
+            const uint32_t r = i % TC_NREC;
+            mbar_wait(rec_full + 8 * r, (i / TC_NREC) & 1u);
+            const TcRec rc = rec[r];
+            if (rc.count == 0) break;
+            const uint64_t code = ((uint64_t)rc.code_hi << 32) | rc.code_lo;
+            // phase 1: the pattern's mixture P[s][b] (FP64, ascending h) and lg2 P
+            asm volatile("bar.sync 1, %0;" ::"n"(NB) : "memory");             // the previous item's phase 2 has read P
+            for (int t = bt; t < 4 * Sp; t += NB) {
+                const int s = t >> 2, b = t & 3;
+                double P = 1.0;
+                if (s < S) {
+                    P = 0.0;
+                    for (int h = 0; h < G; h++) P = fma(eta_s[4 * code_get(code, h) + b], gT[h * Sp + s], P);
+                }
+                P64[t] = P;
+                reinterpret_cast<float *>(lP)[t] = lg2_fast((float)P);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NB) : "memory");
+            for (int kb = 0; kb < nkb; kb++, u++) {
+                const uint32_t ts = u & 1u;
+                mbar_wait(tab_empty + 8 * ts, ((u >> 1) & 1u) ^ 1u);
+                unsigned char *tab = smem + L.off_table + ts * L.table_bytes;
+                // phase 2: a warp task = 8 table columns x 4 samples; a lane = one (column, sample): 4 bases -> 8 + 8 bytes
+                for (int task = bw; task < noct * nquad; task += TC_BUILD_WARPS) {
+                    const int o = task % noct, sq = task / noct;
+                    const int c = 8 * o + nl, sl = 4 * sq + 2 * sp + shf, s = kb * SK + sl;
+                    if (c < ncol && s < S) {
+                        float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+                        if (fast_ok) {
+                            const int g = c / 3, j = c - 3 * g;
+                            const int cur = code_get(code, g);
+                            const double2 *ecp = reinterpret_cast<const double2 *>(eta_s + 4 * cur);
+                            const double2 ec01 = ecp[0], ec23 = ecp[1];
+                            const double2 P01 = reinterpret_cast<const double2 *>(P64)[2 * s], P23 = reinterpret_cast<const double2 *>(P64)[2 * s + 1];
+                            const float4 l = lP[s];
+                            const double gg = gT[g * Sp + s];
+                            const float gf = gT32[g * Sp + s];
+                            const float q0 = fmaxf((float)fma(-ec01.x, gg, P01.x), 0.f), q1 = fmaxf((float)fma(-ec01.y, gg, P01.y), 0.f),
+                                        q2 = fmaxf((float)fma(-ec23.x, gg, P23.x), 0.f), q3 = fmaxf((float)fma(-ec23.y, gg, P23.y), 0.f);
+                            const float4 ea = eta32[(cur + 1 + j) & 3];
+                            w0 = lg2_fast(fmaf(ea.x, gf, q0)) - l.x; w1 = lg2_fast(fmaf(ea.y, gf, q1)) - l.y;
+                            w2 = lg2_fast(fmaf(ea.z, gf, q2)) - l.z; w3 = lg2_fast(fmaf(ea.w, gf, q3)) - l.w;
+                        }
+                        const __half h0 = __float2half_rn(w0), h1 = __float2half_rn(w1), h2 = __float2half_rn(w2), h3 = __float2half_rn(w3);
+                        const __half l0 = __float2half_rn((w0 - __half2float(h0)) * TC_LO_SCALE), l1 = __float2half_rn((w1 - __half2float(h1)) * TC_LO_SCALE),
+                                     l2 = __float2half_rn((w2 - __half2float(h2)) * TC_LO_SCALE), l3 = __float2half_rn((w3 - __half2float(h3)) * TC_LO_SCALE);
+                        uint2 hv, lv;
+                        hv.x = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                        hv.y = (uint32_t)__half_as_ushort(h2) | ((uint32_t)__half_as_ushort(h3) << 16);
+                        lv.x = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                        lv.y = (uint32_t)__half_as_ushort(l2) | ((uint32_t)__half_as_ushort(l3) << 16);
+                        const size_t off = (size_t)(sl >> 1) * 128 + (size_t)nl * 16 + (size_t)shf * 8;
+                        *reinterpret_cast<uint2 *>(tab + (size_t)o * sbo + off) = hv;               // rows [0, NC): h
+                        *reinterpret_cast<uint2 *>(tab + (size_t)(noct + o) * sbo + off) = lv;      // rows [NC, 2 NC): l
+                    }
+                }
+                fence_proxy_async();                                     // generic-proxy stores -> async-proxy reads of the MMA
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tab_full + 8 * ts);
+            }
+        }
+    } else {
+        // =============================================================== epilogue (warps 0-3: TMEM lanes 32 w .. 32 w + 31)
+        unsigned int n_decided = 0;
+        const int row = warp * 32 + lane;
+        const int nch = (G + 7) / 8;                                       // chunks of 8 strains = 24 table columns
+        for (uint32_t i = 0;; i++) {
+            const uint32_t r = i % TC_NREC;
+            mbar_wait(rec_full + 8 * r, (i / TC_NREC) & 1u);
+            const TcRec rc = rec[r];
+            if (rc.count == 0) break;
+            // what the decision needs besides the sums, fetched before the sums are waited for
+            const bool have = row < rc.count;
+            int vraw = 0;
+            float nk = 0.f;
+            if (have) { vraw = p.img_site[rc.img0 + row]; nk = p.img_nsite[rc.img0 + row]; }
+            const bool orphan = vraw < 0;                                   // the site has left this group (tau_sample_kernel marks the row)
+            const int vown = orphan ? ~vraw : vraw;
+            bool zero_word = false;
+            if (have && p.words) {
+                const uint32_t *w = p.words + (size_t)vown * G;
+                for (int g = 0; g < G; g++) zero_word |= (w[g] == 0u);      // u == 0 (c_sample_tau.c:174): reference-order path
+            }
+            const uint32_t as = i & 1u;
+            mbar_wait(acc_full + 8 * as, (i >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + as * (uint32_t)L.acc_stride + ((uint32_t)(warp * 32) << 16);
+            const float bn = nk * bn_scale + 1e-6f;
+            uint32_t mask = 0;
+            for (int ch = 0; ch < nch; ch++) {
+                float hi[24], lo[24];
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    const int c0 = 24 * ch + 8 * q;                       // (warp-uniform guards: the loads are .sync.aligned)
+                    if (c0 < NC) {
+                        tc_ld8(t0 + (uint32_t)c0, reinterpret_cast<float(&)[8]>(hi[8 * q]));
+                        tc_ld8(t0 + (uint32_t)(NC + c0), reinterpret_cast<float(&)[8]>(lo[8 * q]));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) { hi[8 * q + e] = 0.f; lo[8 * q + e] = 0.f; }
+                    }
+                }
+                tc_wait_ld();
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    tc_launder8(reinterpret_cast<float(&)[8]>(hi[8 * q]));
+                    tc_launder8(reinterpret_cast<float(&)[8]>(lo[8 * q]));
+                }
+#pragma unroll
+                for (int gl = 0; gl < 8; gl++) {
+                    const int g = 8 * ch + gl;
+                    if (g < G) {
+                        const float d0 = fmaf(lo[3 * gl], 1.0f / TC_LO_SCALE, hi[3 * gl]), d1 = fmaf(lo[3 * gl + 1], 1.0f / TC_LO_SCALE, hi[3 * gl + 1]),
+                                    d2 = fmaf(lo[3 * gl + 2], 1.0f / TC_LO_SCALE, hi[3 * gl + 2]);
+                        const bool stay = (d0 * LN2 + bn < -TAU_GAP) && (d1 * LN2 + bn < -TAU_GAP) && (d2 * LN2 + bn < -TAU_GAP);
+                        if (!stay) mask |= 1u << g;
+                        if (p.dbg && have) {
+                            float *dst = p.dbg + (size_t)vown * ncol + 3 * g;
+                            dst[0] = d0; dst[1] = d1; dst[2] = d2;
+                        }
+                    }
+                }
+            }
+            // the sums are in registers: hand the accumulator and the record back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(acc_empty + 8 * as); mbar_arrive(rec_empty + 8 * r); }
+            bool push = false;
+            if (have) {
+                if (!fast_ok || orphan || zero_word) mask = fullG;            // orphan: its pattern is not this group's
+                push = mask != 0u;
+                if (!push) n_decided += (unsigned int)G;
+            }
+            const unsigned int bal = __ballot_sync(DESMAN_FULL_MASK, push);
+            if (bal) {
+                int pos = 0;
+                if (lane == 0) pos = atomicAdd(p.grp.gctl + GC_NWORK, __popc(bal));
+                pos = __shfl_sync(DESMAN_FULL_MASK, pos, 0) + __popc(bal & ((1u << lane) - 1u));
+                if (push) p.grp.work[pos] = make_uint2((unsigned int)vown, mask);
+            }
+        }
+        n_decided = (unsigned int)warp_sum_u64((unsigned long long)n_decided);
+        if (lane == 0 && n_decided && p.tier_counts) atomicAdd(p.tier_counts, (unsigned long long)n_decided);
+    }
+    // ---- teardown: every role is done with tensor memory
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L.tmem_cols) : "memory");
+    }
+}

@@ -47,6 +47,12 @@ struct TauParams {
     const int *singles;      // sites alone in their pattern, gctl[GC_NSINGLES] entries
     int *gctl;
     int *site_slot;          // [V] slot of the site's pattern, kept current on flips
+    // tensor-memory screening pass (tau_group_tc_kernel.cuh): a site that leaves its group is marked in the row table of the
+    // count image (img_site[row] = ~site), so that pass needs no gather to recognise orphans; need_img: the work list is
+    // only valid if the image was built (gctl[GC_IMG_OK])
+    int *img_site;
+    const int *site_row;
+    int need_img;
     unsigned long long *tier_counts;  // [3] += draws decided by tier 1 / 2 / 3 (or nullptr)
 };
 
@@ -310,7 +316,7 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
     if (early) pdl_enter();
     int nsite = p.V, nwork = 0;
     bool listed = false;
-    if (p.work && p.gctl[GC_HAVE] && p.gctl[GC_CALM]) {
+    if (p.work && p.gctl[GC_HAVE] && p.gctl[GC_CALM] && (!p.need_img || p.gctl[GC_IMG_OK])) {
         listed = true;
         nwork = p.gctl[GC_NWORK];
         nsite = nwork + p.gctl[GC_NSINGLES];
@@ -446,7 +452,10 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
             if (lane < G) p.tau[(size_t)v * G + lane] = (uint8_t)code_get(code, lane);
             if (p.agg.N) {
                 const int sn = agg_move_site(p.agg, code_in, code, tile, lane);
-                if (p.site_slot && lane == 0) { p.site_slot[v] = sn; atomicAdd(p.gctl + GC_ORPHANS, 1); }
+                if (p.site_slot && lane == 0) {
+                    p.site_slot[v] = sn; atomicAdd(p.gctl + GC_ORPHANS, 1);
+                    if (p.site_row) { const int r = p.site_row[v]; if (r >= 0) p.img_site[r] = ~v; }
+                }
             }
         }
 

@@ -245,6 +245,15 @@ class Engine:
         check(self._L.desman_get_group_stats(self._h, _lib.ptr_i64(out)), "desman_get_group_stats")
         return dict(zip(("have", "calm", "items", "singles", "work", "orphans", "slots", "configured"), out.tolist()))
 
+    def debug_screen(self):
+        """Validation of the tensor-memory screening pass: (D [V,G,3] float32 log2-units sums, NaN where a site is in no
+        group; mask [V] uint32 of undecided strains, 0xffffffff where the site is not on the work list)."""
+        D = np.empty((self.V, self.G, 3), dtype=np.float32)
+        mask = np.empty(self.V, dtype=np.uint32)
+        check(self._L.desman_debug_screen(self._h, D.ctypes.data_as(C.POINTER(C.c_float)),
+                                          mask.ctypes.data_as(C.POINTER(C.c_uint32))), "desman_debug_screen")
+        return D, mask
+
     def get_tier_counts(self, reset=True):
         out = np.zeros(3, dtype=np.int64)
         check(self._L.desman_get_tier_counts(self._h, _lib.ptr_i64(out), int(reset)), "desman_get_tier_counts")

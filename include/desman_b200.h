@@ -131,6 +131,12 @@ int desman_get_tier_counts(desman_ctx *ctx, int64_t out[3], int reset);
  * {groups valid, chain calm, work items, single-site patterns, sites left to the per-site kernel in the last sweep,
  *  orphans since the last regroup, pattern slots in use, grouping configured}. */
 int desman_get_group_stats(desman_ctx *ctx, int64_t out[8]);
+/* "tau_group_tc" = 1 (default): where every count is < 2048 the screening pass runs on the Blackwell tensor path (TMA bulk
+ * copies into shared memory, tcgen05.mma with the sums in tensor memory; tau_group_tc_kernel.cuh); 0: mma.sync / FFMA forms.
+ * desman_debug_screen (validation only) regroups the current state, runs that pass once and returns per site the 3G sums
+ * D[v][3g+j] = L(candidate j of strain g) - L(current base) in log2 units (NaN: site in no group) and the mask of strains
+ * the gap test left undecided (0xffffffff: none, the site is not on the work list). */
+int desman_debug_screen(desman_ctx *ctx, float *D /*V*3G*/, uint32_t *mask /*V*/);
 
 /* Multi-GPU: one context per process/GPU, sites sharded by desman_set_counts(v0, V_total).
  * desman_comm_unique_id fills a 128-byte NCCL id on rank 0; every rank calls desman_comm_init. */

@@ -46,9 +46,11 @@ def eng_mod():
     return engine
 
 
-def run_chain(eng_mod, p, G, group, n_iter, tau0, gamma0, eta0, seed=4242, mu_mode=1, chunks=1, mma=1):
+def run_chain(eng_mod, p, G, group, n_iter, tau0, gamma0, eta0, seed=4242, mu_mode=1, chunks=1, mma=1, tc=1):
+    """tc=1: tcgen05 / TMEM / TMA form of the screening pass (default); tc=0, mma=1: mma.sync form; tc=0, mma=0: FFMA form."""
     e = eng_mod.Engine(0, seed=seed)
     e.set_option("tau_group", group)
+    e.set_option("tau_group_tc", tc)
     e.set_option("tau_group_mma", mma)
     e.set_option("mu_mode", mu_mode)
     e.set_counts(p["counts"])
@@ -76,13 +78,15 @@ def test_grouped_chain_identical_to_per_site_chain_from_converged_state(eng_mod,
     """Start at the true haplotypes (few patterns, many sites each): the screening pass is active from the first sweep."""
     p = mild_problem(V, S, G, depth, 31 * V + G)
     tau0 = p["tau_true"]
-    a = run_chain(eng_mod, p, G, 1, 8, tau0, p["gamma_true"], p["eta0"])              # tensor-core screening pass
-    f = run_chain(eng_mod, p, G, 1, 8, tau0, p["gamma_true"], p["eta0"], mma=0)       # FFMA screening pass
+    a = run_chain(eng_mod, p, G, 1, 8, tau0, p["gamma_true"], p["eta0"])              # tcgen05 screening pass (TMA + TMEM)
+    m = run_chain(eng_mod, p, G, 1, 8, tau0, p["gamma_true"], p["eta0"], tc=0)        # mma.sync screening pass
+    f = run_chain(eng_mod, p, G, 1, 8, tau0, p["gamma_true"], p["eta0"], tc=0, mma=0) # FFMA screening pass
     b = run_chain(eng_mod, p, G, 0, 8, tau0, p["gamma_true"], p["eta0"])              # per-site kernel only
     for k in ("tau", "nchange", "ll", "lp", "gamma", "tau_sum", "star"):
         assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(m[k], b[k]), k
         assert np.array_equal(f[k], b[k]), k
-    assert a["tiers"].sum() == 8 * V * G and b["tiers"].sum() == 8 * V * G and f["tiers"].sum() == 8 * V * G
+    assert a["tiers"].sum() == 8 * V * G and b["tiers"].sum() == 8 * V * G and f["tiers"].sum() == 8 * V * G and m["tiers"].sum() == 8 * V * G
     assert a["launches"]["tau_group"] == 8 and f["launches"]["tau_group"] == 8 and b["launches"]["tau_group"] == 0
     # (the two forms of the screening pass use different error bounds, so they need not decide exactly the same steps)
     st = a["stats"]
@@ -188,8 +192,70 @@ def test_grouped_chain_identical_random_shapes(eng_mod, V, S, G, depth):
     p = mild_problem(V, S, G, depth, 977 * V + 31 * S + G)
     tau0 = p["tau_true"]
     b = run_chain(eng_mod, p, G, 0, 5, tau0, p["gamma_true"], p["eta0"])
-    for mma in (1, 0):
-        a = run_chain(eng_mod, p, G, 1, 5, tau0, p["gamma_true"], p["eta0"], mma=mma)
+    for tc, mma in ((1, 1), (0, 1), (0, 0)):
+        a = run_chain(eng_mod, p, G, 1, 5, tau0, p["gamma_true"], p["eta0"], mma=mma, tc=tc)
         for k in ("tau", "nchange", "ll", "gamma", "tau_sum", "star"):
-            assert np.array_equal(a[k], b[k]), (k, mma)
+            assert np.array_equal(a[k], b[k]), (k, tc, mma)
         assert a["tiers"].sum() == 5 * V * G
+
+
+# ------------------------------------------------------------------ the tensor-memory contraction itself
+def _screen_reference(counts, tau_idx, gamma, eta):
+    """D[v][g][j] = sum_{s,b} n[v,s,b] * (log2 q - log2 P) in float64: P = mixture of the site's pattern, q = P with strain g moved
+    from its current base to candidate a_j = (cur + 1 + j) & 3 (tau_group_kernel.cuh; c_sample_tau.c:136-170 differences)."""
+    V, G = tau_idx.shape
+    P = np.einsum("sg,vgb->vsb", gamma, eta[tau_idx])                           # [V,S,4]
+    lP = np.log2(P)
+    D = np.zeros((V, G, 3))
+    n = counts.astype(np.float64)
+    for g in range(G):
+        cur = tau_idx[:, g]
+        base = P - gamma[None, :, g, None] * eta[cur][:, None, :]
+        for j in range(3):
+            a = (cur + 1 + j) & 3
+            q = base + gamma[None, :, g, None] * eta[a][:, None, :]
+            D[:, g, j] = (n * (np.log2(q) - lP)).sum((1, 2))
+    return D
+
+
+@pytest.mark.parametrize("V,S,G,depth", [(4000, 64, 8, 100.0), (3000, 64, 5, 20.0), (1500, 7, 3, 8.0), (1200, 130, 12, 10.0),
+                                          (900, 256, 16, 30.0), (700, 33, 6, 300.0), (500, 96, 20, 15.0), (300, 5, 1, 30.0),
+                                          (2000, 64, 8, 1500.0)])
+def test_tc_screening_sums_against_float64(eng_mod, V, S, G, depth):
+    """The tcgen05 contraction (fp16 counts x [h | l] split table, FP32 accumulation in tensor memory) against a float64 evaluation
+    of the same sums for every grouped site: the observed error must stay inside the bound the gap test charges (this is
+    also the measurement of the tensor-core accumulation error the bound assumes), and no step the float64 sums leave open
+    (within 60 nats of the current base) may be missing from the work list."""
+    p = mild_problem(V, S, G, depth, 17 * V + G)
+    if p["counts"].max() >= 2048:
+        pytest.skip("counts not exact in fp16")
+    tau = p["tau_true"]
+    if G > 8:      # 2^G possible patterns: draw the state from a pool of 24 of them so that the sites do share patterns
+        tau = tau[np.random.default_rng(G).integers(0, 24, size=V)]
+    e = eng_mod.Engine(0, seed=1)
+    e.set_option("tau_group", 1)
+    e.set_counts(p["counts"])
+    e.set_state(onehot(tau), p["gamma_true"], p["eta0"])
+    D, mask = e.debug_screen()
+    st = e.get_group_stats()
+    e.close()
+    ref = _screen_reference(p["counts"], tau, p["gamma_true"], p["eta0"])
+    grouped = ~np.isnan(D[:, 0, 0])
+    assert grouped.sum() >= V // 2 and st["items"] > 0, st
+    nsite = p["counts"].sum((1, 2)).astype(np.float64)
+    err = np.abs(D[grouped].astype(np.float64) - ref[grouped]).max((1, 2))
+    # bound per read in log2 units (tau_group_tc_kernel.cuh: bn_scale / ln2), evaluated like the kernel does
+    qmin = 0.99 * np.float32(p["gamma_true"].min()) * np.float32(p["eta0"].min())
+    mq0 = max(1.0, 1.0 - np.log2(qmin))
+    Sp = 2 * ((S + 3) // 4 * 4)                                                 # >= the padded sample count of any K-block split
+    e_entry = (6 * 2.0 ** -24 * 1.4427 + 2 * 2.0 ** -22) + (2.0 ** -22 + 2.0 ** -24) * 2 * mq0 + (2 * G + 2) * 2.0 ** -53 * 1.4427 / qmin
+    bound = nsite[grouped] * (e_entry + (Sp / 2 + 12) * 2.0 ** -20 * mq0) + 1e-6
+    assert (err <= bound).all(), (float((err / bound).max()), int(np.argmax(err / bound)))
+    print("tc screening: max |D - D64| / bound = %.4f, max abs err %.3e log2 units over %d sites" % (float((err / bound).max()), float(err.max()), int(grouped.sum())))
+    # every step that is open by the float64 sums is on the work list with its bit set
+    open64 = (ref.max(2) * np.log(2.0) > -60.0)                                # [V,G]
+    listed = mask != 0xFFFFFFFF
+    for v in np.flatnonzero(grouped & open64.any(1)):
+        assert listed[v], v
+        want = sum(1 << g for g in range(G) if open64[v, g])
+        assert (int(mask[v]) & want) == want, (v, hex(int(mask[v])), hex(want))
