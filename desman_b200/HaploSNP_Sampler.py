@@ -83,6 +83,7 @@ class HaploSNP_Sampler():
         self._set_tau_map()
 
         self._tau_sum = None          # tau_store.sum(axis=0) of the last update()/updateTau()
+        self._Esum_store = None       # E_store[i].sum(axis=(0,1)) per sweep of the last update()
         self._sum_mu = None           # mu.sum(axis=(0,2)) of the last sampleMu()
         self._Esum = None             # E.sum(axis=(0,1))
         self._timing = None
@@ -318,6 +319,7 @@ class HaploSNP_Sampler():
         self._push(eng)
         res = eng.update(self.max_iter)
         self.gamma_store, self.eta_store = res["gamma_store"], res["eta_store"]
+        self._Esum_store = eng.get_esum_store(self.max_iter) if self.max_iter > 0 else None
         self._finish(eng, res, self.max_iter, True)
         self._log_progress(res, "nlp")
 
@@ -489,8 +491,99 @@ class HaploSNP_Sampler():
     def DIC(self):
         return self.meanDeviance() + 2.0 * self.logLikelihood(self.gammaMean(), self.tauMean(), self.etaMean())   # :486-496
 
-    def _next(self, *a, **k):
-        raise NotImplementedError("chibMarginalLogLikelihood[2] / sampleTauFixTau read E_store / mu_store and draw from numpy's "
-                                  "sequential stream per (v,g) step; they have no caller in the reference (DESIGN.md section 7)")
+    # ------------------------------------------------------------------ Chib's marginal likelihood (:538-710)
+    # Compositions of the device primitives above under the Philox counter contract: the reference
+    # draws every step from numpy's sequential stream, so its estimates are reproduced in law, not draw for draw; the same
+    # compositions of the CPU oracle's primitives give these values to 1e-9 (tests/test_gpu_states.py).
+    def normaliseLogProb(self, logProb):
+        logProb = logProb - np.max(logProb)                                    # :186-194
+        return logProb - np.log(np.exp(logProb).sum())
 
-    chibMarginalLogLikelihood = chibMarginalLogLikelihood2 = sampleTauFixTau = _next
+    def logMean(self, logStore):
+        maxLog = np.max(logStore)                                              # :526-536
+        return maxLog + np.log(np.exp(logStore - maxLog).sum()) - np.log(logStore.shape[0])
+
+    def tauOne(self, tauSlice):
+        return int(np.argmax(np.asarray(tauSlice) == 1))                       # :610-618
+
+    def sampleTauFixTau(self, fixedTau, H, gammaStar, etaStar):
+        """Redraw strains [H, G) of every site in order at (gammaStar, etaStar), in place on fixedTau; returns the normalised
+        log-probabilities [V,4] of strain H's bases before its draw (:196-222).  One launch of the per-site tau kernel."""
+        eng = self._engine()
+        self._push(eng, gamma=gammaStar, tau=fixedTau, eta=etaStar)
+        logp, _ = eng.sample_tau_fix(H)
+        _sampletau.advance_global_sweep(eng.get_rng()[0])
+        idx = eng.get_tau_index()
+        fixedTau[...] = 0
+        np.put_along_axis(fixedTau, idx[..., None].astype(np.int64), 1, axis=2)
+        return logp
+
+    def _log_gamma_post(self, sum_mu):
+        return sum(du_log_dirichlet(self.gamma_star[s, :], self.alpha + sum_mu[s, :]) for s in range(self.S))
+
+    def _log_eta_post(self, sum_E):
+        return sum(du_log_dirichlet(self.eta_star[a, :], self.delta + sum_E[:, a]) for a in range(4))
+
+    def chibMarginalLogLikelihood(self):
+        """Chib's estimator with the joint-state tau term (:621-710)."""
+        cMLogL = self.logLikelihood(self.gamma_star, self.tau_star, self.eta_star)
+        for s in range(self.S):
+            cMLogL += du_log_dirichlet(self.gamma_star[s, :], self.alpha)
+        for a in range(4):
+            cMLogL += du_log_dirichlet(self.eta_star[a, :], self.delta)
+        cMLogL += self.V * np.log(1.0 / float(self.nTauStates))
+        storeLogTau = np.array([self.logTauProb(self.gamma_store[i], self.eta_store[i]) for i in range(self.tau_comp_iter)])
+        logTauHat = self.logMean(storeLogTau)
+        eng = self._engine()
+        storeLogGamma = np.zeros(self.max_iter)
+        for i in range(self.max_iter):                                          # pi term (:664-681)
+            sum_mu, _ = self.sampleMu(self.tau_star, self.gamma, self.eta)
+            self.sampleGamma()
+            self.sampleEta()
+            eng.set_option("advance_sweep", 1)
+            storeLogGamma[i] = self._log_gamma_post(sum_mu)
+        logGammaHat = self.logMean(storeLogGamma)
+        storeLogEpsilon = np.zeros(self.max_iter)
+        for i in range(self.max_iter):                                          # epsilon term (:690-703)
+            _, sum_E = self.sampleMu(self.tau_star, self.gamma_star, self.eta)
+            self._eta_draw = None
+            self.sampleEta()
+            eng.set_option("advance_sweep", 1)
+            storeLogEpsilon[i] = self._log_eta_post(sum_E)
+        logEpsilonHat = self.logMean(storeLogEpsilon)
+        _sampletau.advance_global_sweep(eng.get_rng()[0])
+        print(str(cMLogL) + "," + str(logGammaHat) + "," + str(logEpsilonHat) + "," + str(logTauHat))
+        return cMLogL - logGammaHat - logEpsilonHat - logTauHat
+
+    def chibMarginalLogLikelihood2(self):
+        """Chib's estimator with the strain-by-strain tau term (:538-608); the eta term reads the per-sweep Esum of the
+        last update() (E_store[i].sum(axis=(0,1)), :557)."""
+        if getattr(self, "_Esum_store", None) is None or self._Esum_store.shape[0] < self.max_iter:
+            raise ValueError("chibMarginalLogLikelihood2 needs the E statistics of a preceding update()")
+        cMLogL = self.logLikelihood(self.gamma_star, self.tau_star, self.eta_star)
+        logGammaPrior = sum(du_log_dirichlet(self.gamma_star[s, :], self.alpha) for s in range(self.S))
+        logEtaPrior = sum(du_log_dirichlet(self.eta_star[a, :], self.delta) for a in range(4))
+        logTauPrior = self.V * self.G * np.log(1.0 / 4.0)
+        storeLogEpsilon = np.array([self._log_eta_post(self._Esum_store[i]) for i in range(self.max_iter)])
+        logEpsilonHat = self.logMean(storeLogEpsilon)
+        storeLogGamma = np.zeros(self.max_iter)
+        for i in range(self.max_iter):                                          # (:566-583)
+            self.sampleTau(self.gamma, self.eta_star)
+            sum_mu, _ = self.sampleMu(self.tau, self.gamma, self.eta_star)
+            self.sampleGamma()
+            self._eta_draw = None
+            print(str(i) + ",GC," + str(self._log_gamma_post(sum_mu)))
+            storeLogGamma[i] = self._log_gamma_post(sum_mu)
+        logGammaHat = self.logMean(storeLogGamma)
+        logTauHat = 0.0
+        star_ix = self._tau_index(star=True)
+        for h in range(self.G):                                                 # (:587-603)
+            workingTau = np.copy(self.tau_star)
+            storeLogTau = np.zeros(self.max_iter)
+            for i in range(self.max_iter):
+                tauLogProb = self.sampleTauFixTau(workingTau, h, self.gamma_star, self.eta_star)
+                temp = float(tauLogProb[np.arange(self.V), star_ix[:, h]].sum())
+                storeLogTau[i] = temp
+                print(str(i) + ",GT," + str(h) + "," + str(temp))
+            logTauHat += self.logMean(storeLogTau)
+        return cMLogL + logEtaPrior - logEpsilonHat + logGammaPrior - logGammaHat + logTauPrior - logTauHat

@@ -158,6 +158,8 @@ struct desman_ctx {
     int *img_site = nullptr, *site_row = nullptr;
     float *img_nsite = nullptr;
     size_t img_cap_rows = 0, img_bytes = 0, img_cap_v = 0;
+    unsigned long long *esum_store = nullptr;   // [n_iter][16] Esum of every sweep of the last update()
+    size_t esum_store_cap = 0;
     bool counts_tf32_exact = false;
     float4 *countsf = nullptr;               // [V][S] FP32 copy of the counts
     float *nsite = nullptr;                  // [V]
@@ -338,7 +340,7 @@ extern "C" int desman_ctx_destroy(desman_ctx *c)
     }
     if (c->xch_err) cudaFree(c->xch_err);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-    for (void *q : {(void *)c->img, (void *)c->img_site, (void *)c->img_nsite, (void *)c->site_row}) if (q) dfree(c, q);
+    for (void *q : {(void *)c->img, (void *)c->img_site, (void *)c->img_nsite, (void *)c->site_row, (void *)c->esum_store}) if (q) dfree(c, q);
     void *ptrs[] = {c->counts, c->tau, c->tau_star, c->gamma, c->eta, c->eta_new, c->gamma_star, c->eta_star, c->stats,
                     c->red_base, c->agg_ctl, c->scal, c->flag, c->tau_cnt, c->tau_last, c->mt_state, c->words,
                     c->scratch, c->flush_buf, c->tiers, c->agg_keys, c->agg_code, c->agg_N, c->agg_ids, c->agg_nslots, c->agg_classM,
@@ -996,7 +998,8 @@ static int launch_tau_group_t(desman_ctx *c, const TauGroupParams &p, int warps)
 // One tau pass (gamma, eta: device pointers).  maintain: keep the pattern table current (it must be in sync); then the
 // screening pass runs first where groups are kept, and the per-site kernel walks its work list only.
 // red_i[1] (nchange) must be zero on entry (sync_table, or the caller's memset).
-static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, bool maintain, bool count_occupancy, uint32_t iter)
+static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, bool maintain, bool count_occupancy, uint32_t iter,
+                      int g_begin = 0, double *logp_out = nullptr)
 {
     TauParams p;
     p.counts = c->counts; p.tau = c->tau; p.gamma = gamma; p.eta = eta;
@@ -1016,6 +1019,7 @@ static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, boo
     p.tier_counts = c->tiers;
     p.work = nullptr; p.singles = nullptr; p.gctl = nullptr; p.site_slot = nullptr;
     p.img_site = nullptr; p.site_row = nullptr; p.need_img = 0;
+    p.g_begin = g_begin; p.logp_out = logp_out;
     int gb = 8, gwarps = 1;
     if (p.agg.N && group_config(c, &gb, &gwarps)) {
         TauGroupParams q;
@@ -1164,9 +1168,11 @@ static int allreduce_red(desman_ctx *c)
     return DESMAN_OK;
 }
 
-static int launch_draw(desman_ctx *c, const unsigned long long *stats, double *gamma_out, double *eta_out)
+static int launch_draw(desman_ctx *c, const unsigned long long *stats, double *gamma_out, double *eta_out,
+                       unsigned long long *esum_keep = nullptr)
 {
     DrawParams p;
+    p.esum_keep = esum_keep;
     p.sum_mu = stats; p.esum = stats + (size_t)c->S * c->G;
     p.S = c->S; p.G = c->G; p.alpha = c->alpha; p.delta = c->delta; p.epsilon = c->epsilon;
     p.seed = c->seed; p.sweep = c->sweep; p.gamma_out = gamma_out; p.eta_out = eta_out;
@@ -1252,6 +1258,30 @@ extern "C" int desman_sample_tau(desman_ctx *c, int64_t *nchange)
     if (c->nranks > 1) return fail(DESMAN_ESTATE, "desman_sample_tau is a single-rank call");
     if (nchange) *nchange = (int64_t)n;
     return DESMAN_OK;
+}
+
+// sampleTauFixTau (HaploSNP_Sampler.py:196-222) on the current device state: strains [H, G) are redrawn in order (Philox
+// contract of the tau draws), logp [V][4] = normalised log-probabilities of strain H's bases before its draw
+extern "C" int desman_sample_tau_fix(desman_ctx *c, int H, double *logp, int64_t *nchange)
+{
+    RET(require_state(c));
+    if (H < 0 || H >= c->G) return fail(DESMAN_EINVAL, "desman_sample_tau_fix: H must be in [0, G)");
+    if (c->rng_mode != DESMAN_RNG_PHILOX) return fail(DESMAN_ESTATE, "desman_sample_tau_fix draws under the Philox contract");
+    if (c->nranks > 1) return fail(DESMAN_ESTATE, "desman_sample_tau_fix is a single-rank call");
+    double *dl = nullptr;
+    if (logp) CU(dmalloc(c, &dl, (size_t)c->V * 4 * sizeof(double)));
+    CU(cudaMemsetAsync(c->red_i + 1, 0, sizeof(unsigned long long), c->stream));
+    int rc = launch_tau(c, c->gamma, c->eta, false, false, 0, H, dl);
+    c->sweep++;
+    unsigned long long n = 0;
+    if (rc == DESMAN_OK) {
+        CU(cudaMemcpyAsync(&n, c->red_i + 1, sizeof(n), cudaMemcpyDeviceToHost, c->stream));
+        if (logp) CU(cudaMemcpyAsync(logp, dl, (size_t)c->V * 4 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    if (dl) dfree(c, dl);
+    if (nchange) *nchange = (int64_t)n;
+    return rc;
 }
 
 extern "C" int desman_mu_stats(desman_ctx *c, int64_t *sum_mu, int64_t *esum)
@@ -1520,6 +1550,12 @@ extern "C" int desman_update(desman_ctx *c, int n_iter, double *gamma_store, dou
     RET(ensure_ll_const(c));
     StoreBufs sb;
     RET(alloc_stores(c, n_iter > 0 ? n_iter : 1, true, &sb, nullptr, nullptr));
+    if ((size_t)n_iter > c->esum_store_cap) {          // E_store[i].sum(axis=(0,1)) per sweep (chibMarginalLogLikelihood2, :557)
+        if (c->esum_store) dfree(c, c->esum_store);
+        c->esum_store = nullptr; c->esum_store_cap = 0;
+        CU(dmalloc(c, &c->esum_store, (size_t)n_iter * 16 * sizeof(unsigned long long)));
+        c->esum_store_cap = (size_t)n_iter;
+    }
     RET(prepare_profiling(c));
     const size_t nvg = (size_t)c->V * c->G;
     CU(cudaMemsetAsync(c->tau_cnt, 0, nvg * 4 * sizeof(uint32_t), c->stream));
@@ -1543,7 +1579,7 @@ extern "C" int desman_update(desman_ctx *c, int n_iter, double *gamma_store, dou
             RET(allreduce_stats(c, red_prev));
             RET(launch_finalize_only(c, red_prev, c->gamma, c->eta, it - 1, 0, sb, true));   // ll, lp, stores, star of sweep it-1
         } else RET(allreduce_stats(c));
-        RET(launch_draw(c, c->stats, c->gamma, c->eta_new));            // sampleGamma (:342) + sampleEta's draw (:347)
+        RET(launch_draw(c, c->stats, c->gamma, c->eta_new, c->esum_store + (size_t)it * 16));   // sampleGamma (:342) + sampleEta's draw (:347)
         if (!c->fixed_tau) RET(launch_tau(c, c->gamma, c->eta, true, true, (uint32_t)it));       // sample_tau (:345), old eta (nchange cleared by sync_table)
         if (lagged) RET(launch_ll(c, c->gamma, c->eta_new, c->eta));     // eta <- new (:347); sum n*log p of sweep it, reduced with the next exchange
         else RET(launch_finalize(c, c->gamma, c->eta_new, it, 0, sb, true, c->eta, false));   // eta <- new (:347); ll, lp, stores, star (:349-358)
@@ -1619,6 +1655,17 @@ extern "C" int desman_get_star(desman_ctx *c, int64_t *tau_star, double *gamma_s
     if (tau_star) index_to_onehot(idx.data(), idx.size(), tau_star);
     if (lp_star) *lp_star = sc[0];
     if (iter_star) *iter_star = (int)sc[1];
+    return DESMAN_OK;
+}
+
+// Esum[a_obs][b_true] of every sweep of the last desman_update (E_store[i].sum(axis=(0,1)), HaploSNP_Sampler.py:557)
+extern "C" int desman_get_esum_store(desman_ctx *c, int64_t *esum_store)
+{
+    RET(require_state(c));
+    const size_t n = (size_t)c->last_n_iter * 16;
+    if (!esum_store || n == 0 || c->last_n_iter > c->esum_store_cap) return fail(DESMAN_ESTATE, "no update() to report");
+    CU(cudaMemcpyAsync(esum_store, c->esum_store, n * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return DESMAN_OK;
 }
 
@@ -1765,6 +1812,9 @@ extern "C" int desman_set_option(desman_ctx *c, const char *name, int64_t value)
     if (!strcmp(name, "fixed_tau")) { c->fixed_tau = value ? 1 : 0; return DESMAN_OK; }
     if (!strcmp(name, "mu_mode")) { c->mu_mode = (value == 0 || value == 1) ? (int)value : 2; return DESMAN_OK; }
     if (!strcmp(name, "pdl")) { c->pdl = value ? 1 : 0; return DESMAN_OK; }
+    // the single-step calls that draw no tau (mu_stats, draw_gamma_eta) leave the Philox sweep counter where it is: a caller
+    // looping over them (chibMarginalLogLikelihood, HaploSNP_Sampler.py:621-710) moves it on itself
+    if (!strcmp(name, "advance_sweep")) { c->sweep += (uint32_t)value; return DESMAN_OK; }
     // stream of the tau draws; the Philox sweep counter and the MT19937 position are both kept across a switch
     if (!strcmp(name, "rng_mode")) {
         if (value != DESMAN_RNG_MT19937 && value != DESMAN_RNG_PHILOX) return fail(DESMAN_EINVAL, "bad rng_mode %lld", (long long)value);

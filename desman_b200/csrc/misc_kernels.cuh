@@ -123,6 +123,7 @@ struct DrawParams {
     uint32_t sweep;
     double *gamma_out;  // [S][G]
     double *eta_out;    // [16]
+    unsigned long long *esum_keep;  // if non-null: [16] copy of esum (E_store[i].sum(axis=(0,1)) of this sweep, HaploSNP_Sampler.py:557)
 };
 
 __global__ void __launch_bounds__(DRAW_MAX_THREADS) draw_gamma_eta_kernel(DrawParams p)
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(DRAW_MAX_THREADS) draw_gamma_eta_kernel(DrawPa
             y[i] = gamma_variate(p.alpha + (double)p.sum_mu[i], k0, k1, p.sweep, (uint32_t)i, STAGE_GAMMA,
                                  STAGE_GAMMA_BOOST);
         } else {
+            if (p.esum_keep) p.esum_keep[i - nG] = p.esum[i - nG];
             const int j = i - nG, t = j >> 2, o = j & 3;   // eta[t][o] ~ Gamma(delta + Esum[o][t])  (:276-281)
             y[i] = gamma_variate(p.delta + (double)p.esum[o * 4 + t], k0, k1, p.sweep, (uint32_t)j, STAGE_ETA,
                                  STAGE_ETA_BOOST);

@@ -10,8 +10,9 @@
 // columns the N dimension.  Operands are FP16 (kind::f16, FP32 accumulation in TMEM):
 //   * counts < 2048 are exact in FP16 (11-bit significand): the group-ordered copy of the count rows is kept as fp16x4 cells
 //     (8 bytes per (v,s) instead of 16: the pass reads HALF the bytes of the canonical int32x4 tensor);
-//   * a table entry is split as  Wd = h + l/1024,  h = fp16(Wd), l = fp16((Wd - h)*1024)  (|Wd - h - l/1024| <= 2^-22 |Wd|; the
-//     scaling keeps l normal); h and l are separate columns of the B operand (N = 2*NC), summed by the epilogue.
+//   * a table entry is split as  Wd = h + l,  h = fp16(Wd), l = fp16(Wd - h)  (|Wd - h - l| <= max(2^-22 |Wd|, 2^-25): below
+//     6e-5 the remainder l is a subnormal fp16 with spacing 2^-24); h and l are separate columns of the B operand
+//     (N = 2*NC), summed by the epilogue.
 // Layout (no swizzle, K-major, the canonical "interleaved" UMMA layout): 8 rows x 16 bytes form a 128-byte core matrix; core
 // matrices that are neighbours along K are LBO = 128 bytes apart, 8-row groups SBO = KC*128 bytes apart (KC = 16-byte chunks
 // per K block).  The regroup pass (maintain_kernel.cuh) writes the count image in exactly this order, every work item padded
@@ -21,7 +22,7 @@
 //   warps 0-3   epilogue: TMEM -> registers (warp w owns lanes 32w..32w+31), gap test, work list
 //   warp 4      producer: work tickets, item records, bulk copies of the count rows (2-stage ring)
 //   warp 5      MMA issuer (one elected lane)
-//   warps 6-13  table builders: mixture P in FP64, the 12 lg2 per (strain, sample), fp16 split, stores in B-operand order
+//   warps 6-21  table builders: mixture P in FP64, the 12 lg2 per (strain, sample), fp16 split, stores in B-operand order
 // Results are those of the FFMA / mma.sync forms draw for draw (the error model below is charged instead of theirs).
 #pragma once
 #include <cuda_fp16.h>
@@ -32,10 +33,11 @@
 
 #define TC_ROWS 128                 // sites per work item = M of the MMA
 #define TC_EPI_WARPS 4
-#define TC_BUILD_WARPS 8
+#ifndef TC_BUILD_WARPS
+#define TC_BUILD_WARPS 16
+#endif
 #define TC_THREADS ((TC_EPI_WARPS + 2 + TC_BUILD_WARPS) * 32)
 #define TC_NREC 4                   // item-record ring
-#define TC_LO_SCALE 1024.0f
 
 struct TauGroupTcParams {
     const unsigned char *img;  // count image: [K block][row group][KC chunks][8 rows][16 bytes], fp16x4 cells
@@ -80,6 +82,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t"
         "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// A whole warp waits: ONE lane polls (31 fewer pollers competing with the working warps for issue slots), the others park
+// at the warp barrier
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane)
+{
+    if (lane == 0) mbar_wait(bar, parity);
+    __syncwarp();
 }
 // TMA bulk copy global -> shared, completion counted in bytes on an mbarrier; the rows are read once per pass: evict first
 __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
@@ -134,7 +143,7 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, 
 // ------------------------------------------------------------------------------------------------ sizes (host + device)
 struct TcLayout {
     int Sp, KC, N, acc_stride, tmem_cols;
-    size_t off_gT, off_eta, off_eta32, off_gT32, off_P, off_lP, off_rec, off_bar, off_stage, off_table, stage_bytes, table_bytes, total;
+    size_t off_gT, off_eta, off_eta32, off_gT32, off_rec, off_bar, off_stage, off_table, stage_bytes, table_bytes, total;
 };
 __host__ __device__ static inline TcLayout tc_layout(int S, int G, int SK, int nkb, int NC)
 {
@@ -147,13 +156,11 @@ __host__ __device__ static inline TcLayout tc_layout(int S, int G, int SK, int n
     size_t o = 0;
     L.off_gT = o; o += sizeof(double) * (size_t)G * L.Sp;
     L.off_eta = o; o += sizeof(double) * 16;
-    L.off_P = o; o += sizeof(double) * 4 * (size_t)L.Sp;
     L.off_eta32 = o; o += sizeof(float) * 16;
     L.off_gT32 = o; o += sizeof(float) * (size_t)G * L.Sp;
-    L.off_lP = o; o += sizeof(float) * 4 * (size_t)L.Sp;
     L.off_rec = o; o += sizeof(TcRec) * TC_NREC;
     o = (o + 15) & ~(size_t)15;
-    L.off_bar = o; o += 8 * 24;
+    L.off_bar = o; o += 8 * 32;
     o = (o + 1023) & ~(size_t)1023;
     L.stage_bytes = (size_t)(TC_ROWS / 8) * L.KC * 128;
     L.table_bytes = (size_t)(L.N / 8) * L.KC * 128;
@@ -162,6 +169,15 @@ __host__ __device__ static inline TcLayout tc_layout(int S, int G, int SK, int n
     L.total = o;
     return L;
 }
+
+// -DTC_PROFILE (diagnosis build, tools/prof_tg.py): cycles every role spends in each of its waits, printed by a few CTAs
+#ifdef TC_PROFILE
+#define TCW(acc, stmt) do { const long long t_ = clock64(); stmt; acc += clock64() - t_; } while (0)
+#define TCP(x) x
+#else
+#define TCW(acc, stmt) stmt
+#define TCP(x)
+#endif
 
 // ------------------------------------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcParams p)
@@ -172,10 +188,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
     const int Sp = L.Sp, KC = L.KC;
     double *gT = reinterpret_cast<double *>(smem + L.off_gT);           // [G][Sp]
     double *eta_s = reinterpret_cast<double *>(smem + L.off_eta);       // [16]
-    double *P64 = reinterpret_cast<double *>(smem + L.off_P);           // [Sp][4] mixture of the item being built
     float4 *eta32 = reinterpret_cast<float4 *>(smem + L.off_eta32);     // [4]
     float *gT32 = reinterpret_cast<float *>(smem + L.off_gT32);         // [G][Sp]
-    float4 *lP = reinterpret_cast<float4 *>(smem + L.off_lP);           // [Sp] lg2 P
     TcRec *rec = reinterpret_cast<TcRec *>(smem + L.off_rec);           // [TC_NREC]
     const uint32_t bar0 = smem_u32(smem + L.off_bar);
     // barriers: rec_full[4] rec_empty[4] cnt_full[2] cnt_empty[2] tab_full[2] tab_empty[2] acc_full[2] acc_empty[2]
@@ -241,13 +255,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
     }
     __syncthreads();
     const uint32_t tmem_base = tmem_base_s;
+#ifdef KPROF
+    if (tid == 0) krec_put(KP_TGM_PRO, (int)blockIdx.x, 0, nitems, gtimer(), 0);
+#endif
     const float qmin = 0.99f * __uint_as_float(gmin_bits) * __uint_as_float(emin_bits);
     const bool fast_ok = qmin >= TAU_QMIN && !unnorm;
     const float mq0 = fmaxf(1.0f, 1.0f - log2f(fmaxf(qmin, TAU_QMIN)));
     // per read, log2 units: the entry model of the FFMA form (relative parts, lg2.approx floors, lg2.approx and the lq - lP
     // rounding per unit of |lg2|, FP64 cancellation) + [fp16 split 2^-22 + one FP32 accumulation step per 4 samples and piece,
     // each charged 2^-20 of the running magnitude + the hi + lo/1024 add] * max|Wd|, |Wd| <= mq0
-    const float e_entry = TAU_C0 + (2.3841858e-7f + 5.9604645e-8f) * (2.0f * mq0) + TAU_CANCEL(G) / fmaxf(qmin, TAU_QMIN);
+    const float e_entry = TAU_C0 + (2.3841858e-7f + 5.9604645e-8f) * (2.0f * mq0) + TAU_CANCEL(G) / fmaxf(qmin, TAU_QMIN) + 2.9802322e-8f;   // (+ 2^-25: subnormal remainder)
     const float e_mma = (float)(Sp / 2 + 12) * 9.5367432e-7f;
     const float LN2 = 0.69314718f;
     const float bn_scale = (e_entry + e_mma * mq0) * LN2 * 1.0001f;
@@ -260,9 +277,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
         if (lane == 0) {
             const size_t kb_stride = (size_t)p.img_rg * KC * 128;
             uint32_t u = 0;
+            TCP(long long w_rec = 0; long long w_cnt = 0; long long n_it = 0; long long rows = 0; const long long t_all = clock64(););
             for (uint32_t i = 0;; i++) {
                 const uint32_t r = i % TC_NREC;
-                mbar_wait(rec_empty + 8 * r, ((i / TC_NREC) & 1u) ^ 1u);
+                TCW(w_rec, mbar_wait(rec_empty + 8 * r, ((i / TC_NREC) & 1u) ^ 1u));
                 const int it = (i == 0) ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(p.grp.gctl + GC_CURSOR, 1);
                 TcRec rc;
                 rc.slot = 0; rc.count = 0; rc.img0 = 0; rc.code_lo = 0; rc.code_hi = 0; rc.pad[0] = rc.pad[1] = rc.pad[2] = 0;
@@ -277,29 +295,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
                 const uint32_t bytes = rows8 * (uint32_t)KC * 16u;
                 for (int kb = 0; kb < nkb; kb++, u++) {
                     const uint32_t cs = u & 1u;
-                    mbar_wait(cnt_empty + 8 * cs, ((u >> 1) & 1u) ^ 1u);
+                    TCW(w_cnt, mbar_wait(cnt_empty + 8 * cs, ((u >> 1) & 1u) ^ 1u));
                     mbar_arrive_tx(cnt_full + 8 * cs, bytes);
                     tma_bulk_g2s(stage0 + cs * (uint32_t)L.stage_bytes,
                                  p.img + (size_t)kb * kb_stride + (size_t)(rc.img0 >> 3) * KC * 128, bytes, cnt_full + 8 * cs);
                 }
+                TCP(n_it++; rows += rc.count;);
             }
+            TCP(if (blockIdx.x % 37 == 0) printf("cta %3d producer: items %lld rows %lld total %lld wait rec_empty %lld cnt_empty %lld\n", (int)blockIdx.x, n_it, rows, clock64() - t_all, w_rec, w_cnt););
         }
     } else if (warp == TC_EPI_WARPS + 1) {
         // =============================================================== MMA issuer
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | ((uint32_t)(L.N >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);   // F16 x F16 -> F32, K-major A and B
             uint32_t u = 0;
+            TCP(long long w_rec = 0; long long w_acc = 0; long long w_tab = 0; long long w_cnt = 0; const long long t_all = clock64(););
             for (uint32_t i = 0;; i++) {
                 const uint32_t r = i % TC_NREC;
-                mbar_wait(rec_full + 8 * r, (i / TC_NREC) & 1u);
+                TCW(w_rec, mbar_wait(rec_full + 8 * r, (i / TC_NREC) & 1u));
                 if (rec[r].count == 0) break;
                 const uint32_t as = i & 1u;
-                mbar_wait(acc_empty + 8 * as, ((i >> 1) & 1u) ^ 1u);
+                TCW(w_acc, mbar_wait(acc_empty + 8 * as, ((i >> 1) & 1u) ^ 1u));
                 const uint32_t d = tmem_base + as * (uint32_t)L.acc_stride;
                 for (int kb = 0; kb < nkb; kb++, u++) {
                     const uint32_t cs = u & 1u;
-                    mbar_wait(tab_full + 8 * cs, (u >> 1) & 1u);
-                    mbar_wait(cnt_full + 8 * cs, (u >> 1) & 1u);
+                    TCW(w_tab, mbar_wait(tab_full + 8 * cs, (u >> 1) & 1u));
+                    TCW(w_cnt, mbar_wait(cnt_full + 8 * cs, (u >> 1) & 1u));
                     tc_fence_after();
                     const uint64_t a0 = tc_desc(stage0 + cs * (uint32_t)L.stage_bytes, 128u, sbo);
                     const uint64_t b0 = tc_desc(table0 + cs * (uint32_t)L.table_bytes, 128u, sbo);
@@ -310,84 +331,93 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
                 }
                 tc_commit(acc_full + 8 * as);
             }
+            TCP(if (blockIdx.x % 37 == 0) printf("cta %3d mma: total %lld wait rec_full %lld acc_empty %lld tab_full %lld cnt_full(after tab) %lld\n", (int)blockIdx.x, clock64() - t_all, w_rec, w_acc, w_tab, w_cnt););
         }
     } else if (warp >= TC_EPI_WARPS + 2) {
-        // =============================================================== table builders (8 warps)
-        const int bt = tid - (TC_EPI_WARPS + 2) * 32, bw = bt >> 5;
-        constexpr int NB = TC_BUILD_WARPS * 32;
-        const int nl = (lane >> 1) & 7, shf = lane & 1, sp = lane >> 4;
-        const int noct = NC >> 3, nquad = SK >> 2;
+        // =============================================================== table builders (TC_BUILD_WARPS warps, no cross-warp dependency)
+        // A warp task = 8 strains x 4 samples; a lane = one (strain, sample): its base q[b] = P[b] - eta[cur][b] gamma (FP64, one
+        // rounding) serves the 3 candidates x 4 bases = 12 table entries it writes.  The mixture P[s][b] = sum_h eta[tau_h][b]
+        // gamma[s][h] (FP64, ascending h) of the task's 4 samples is formed by lanes 0-15 (one (sample, base) each; lanes 16-31
+        // mirror them) and handed round by shuffles.  Stores: for a fixed candidate the 8 strains of a task hit 8 different rows
+        // mod 8 (3 is coprime to 8), so a half warp writes 16 distinct 8-byte pieces of 128-byte core matrices: conflict-free.
+        const int bw = warp - (TC_EPI_WARPS + 2);
+        const int gl = (lane >> 1) & 7, shf = lane & 1, sp = lane >> 4;
+        const int ps = (lane >> 2) & 3, pbb = lane & 3;                   // the (sample, base) pair this lane forms P for
+        const int mys = 2 * sp + shf;                                      // this lane's sample within the task
+        const int ngo = (G + 7) >> 3, noct = NC >> 3, nquad = SK >> 2, ntask = ngo * nquad;
         uint32_t u = 0;
+        TCP(long long w_rec = 0; long long w_tab = 0; long long t_work = 0; const long long t_all = clock64(););
         for (uint32_t i = 0;; i++) {
             const uint32_t r = i % TC_NREC;
-            mbar_wait(rec_full + 8 * r, (i / TC_NREC) & 1u);
+            TCW(w_rec, mbar_wait_warp(rec_full + 8 * r, (i / TC_NREC) & 1u, lane));
             const TcRec rc = rec[r];
             if (rc.count == 0) break;
             const uint64_t code = ((uint64_t)rc.code_hi << 32) | rc.code_lo;
-            // phase 1: the pattern's mixture P[s][b] (FP64, ascending h) and lg2 P
-            asm volatile("bar.sync 1, %0;" ::"n"(NB) : "memory");             // the previous item's phase 2 has read P
-            for (int t = bt; t < 4 * Sp; t += NB) {
-                const int s = t >> 2, b = t & 3;
-                double P = 1.0;
-                if (s < S) {
-                    P = 0.0;
-                    for (int h = 0; h < G; h++) P = fma(eta_s[4 * code_get(code, h) + b], gT[h * Sp + s], P);
-                }
-                P64[t] = P;
-                reinterpret_cast<float *>(lP)[t] = lg2_fast((float)P);
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(NB) : "memory");
             for (int kb = 0; kb < nkb; kb++, u++) {
                 const uint32_t ts = u & 1u;
-                mbar_wait(tab_empty + 8 * ts, ((u >> 1) & 1u) ^ 1u);
+                TCW(w_tab, mbar_wait_warp(tab_empty + 8 * ts, ((u >> 1) & 1u) ^ 1u, lane));
+                TCP(const long long tw0 = clock64(););
                 unsigned char *tab = smem + L.off_table + ts * L.table_bytes;
-                // phase 2: a warp task = 8 table columns x 4 samples; a lane = one (column, sample): 4 bases -> 8 + 8 bytes
-                for (int task = bw; task < noct * nquad; task += TC_BUILD_WARPS) {
-                    const int o = task % noct, sq = task / noct;
-                    const int c = 8 * o + nl, sl = 4 * sq + 2 * sp + shf, s = kb * SK + sl;
-                    if (c < ncol && s < S) {
-                        float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-                        if (fast_ok) {
-                            const int g = c / 3, j = c - 3 * g;
-                            const int cur = code_get(code, g);
-                            const double2 *ecp = reinterpret_cast<const double2 *>(eta_s + 4 * cur);
-                            const double2 ec01 = ecp[0], ec23 = ecp[1];
-                            const double2 P01 = reinterpret_cast<const double2 *>(P64)[2 * s], P23 = reinterpret_cast<const double2 *>(P64)[2 * s + 1];
-                            const float4 l = lP[s];
-                            const double gg = gT[g * Sp + s];
-                            const float gf = gT32[g * Sp + s];
-                            const float q0 = fmaxf((float)fma(-ec01.x, gg, P01.x), 0.f), q1 = fmaxf((float)fma(-ec01.y, gg, P01.y), 0.f),
-                                        q2 = fmaxf((float)fma(-ec23.x, gg, P23.x), 0.f), q3 = fmaxf((float)fma(-ec23.y, gg, P23.y), 0.f);
-                            const float4 ea = eta32[(cur + 1 + j) & 3];
-                            w0 = lg2_fast(fmaf(ea.x, gf, q0)) - l.x; w1 = lg2_fast(fmaf(ea.y, gf, q1)) - l.y;
-                            w2 = lg2_fast(fmaf(ea.z, gf, q2)) - l.z; w3 = lg2_fast(fmaf(ea.w, gf, q3)) - l.w;
+                for (int task = bw; task < ntask; task += TC_BUILD_WARPS) {
+                    const int go = task % ngo, sq = task / ngo;
+                    // ---- mixture of the task's 4 samples
+                    const int s_p = kb * SK + 4 * sq + ps;
+                    double Pv = 1.0;                                        // padding samples: finite logs
+                    if (s_p < S) {
+                        Pv = 0.0;
+                        for (int h = 0; h < G; h++) Pv = fma(eta_s[4 * code_get(code, h) + pbb], gT[h * Sp + s_p], Pv);
+                    }
+                    const float lv_ = lg2_fast((float)Pv);
+                    const double P0 = __shfl_sync(DESMAN_FULL_MASK, Pv, 4 * mys + 0), P1 = __shfl_sync(DESMAN_FULL_MASK, Pv, 4 * mys + 1),
+                                 P2 = __shfl_sync(DESMAN_FULL_MASK, Pv, 4 * mys + 2), P3 = __shfl_sync(DESMAN_FULL_MASK, Pv, 4 * mys + 3);
+                    const float l0 = __shfl_sync(DESMAN_FULL_MASK, lv_, 4 * mys + 0), l1 = __shfl_sync(DESMAN_FULL_MASK, lv_, 4 * mys + 1),
+                                l2 = __shfl_sync(DESMAN_FULL_MASK, lv_, 4 * mys + 2), l3 = __shfl_sync(DESMAN_FULL_MASK, lv_, 4 * mys + 3);
+                    const int g = 8 * go + gl, sl = 4 * sq + mys, s = kb * SK + sl;
+                    if (g < G && s < S) {
+                        const int cur = code_get(code, g);
+                        const double2 *ecp = reinterpret_cast<const double2 *>(eta_s + 4 * cur);
+                        const double2 ec01 = ecp[0], ec23 = ecp[1];
+                        const double gg = gT[g * Sp + s];
+                        const float gf = gT32[g * Sp + s];
+                        const float q0 = fmaxf((float)fma(-ec01.x, gg, P0), 0.f), q1 = fmaxf((float)fma(-ec01.y, gg, P1), 0.f),
+                                    q2 = fmaxf((float)fma(-ec23.x, gg, P2), 0.f), q3 = fmaxf((float)fma(-ec23.y, gg, P3), 0.f);
+                        const size_t off_s = (size_t)(sl >> 1) * 128 + (size_t)shf * 8;
+#pragma unroll
+                        for (int j = 0; j < 3; j++) {
+                            float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
+                            if (fast_ok) {
+                                const float4 ea = eta32[(cur + 1 + j) & 3];
+                                w0 = lg2_fast(fmaf(ea.x, gf, q0)) - l0; w1 = lg2_fast(fmaf(ea.y, gf, q1)) - l1;
+                                w2 = lg2_fast(fmaf(ea.z, gf, q2)) - l2; w3 = lg2_fast(fmaf(ea.w, gf, q3)) - l3;
+                            }
+                            const __half2 h01 = __floats2half2_rn(w0, w1), h23 = __floats2half2_rn(w2, w3);
+                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                            const __half2 l01 = __floats2half2_rn(w0 - f01.x, w1 - f01.y), l23 = __floats2half2_rn(w2 - f23.x, w3 - f23.y);
+                            uint2 hv, lv;
+                            hv.x = *reinterpret_cast<const uint32_t *>(&h01); hv.y = *reinterpret_cast<const uint32_t *>(&h23);
+                            lv.x = *reinterpret_cast<const uint32_t *>(&l01); lv.y = *reinterpret_cast<const uint32_t *>(&l23);
+                            const int n = 3 * g + j;
+                            const size_t off = off_s + (size_t)(n & 7) * 16;
+                            *reinterpret_cast<uint2 *>(tab + (size_t)(n >> 3) * sbo + off) = hv;              // rows [0, NC): h
+                            *reinterpret_cast<uint2 *>(tab + (size_t)(noct + (n >> 3)) * sbo + off) = lv;     // rows [NC, 2 NC): l
                         }
-                        const __half h0 = __float2half_rn(w0), h1 = __float2half_rn(w1), h2 = __float2half_rn(w2), h3 = __float2half_rn(w3);
-                        const __half l0 = __float2half_rn((w0 - __half2float(h0)) * TC_LO_SCALE), l1 = __float2half_rn((w1 - __half2float(h1)) * TC_LO_SCALE),
-                                     l2 = __float2half_rn((w2 - __half2float(h2)) * TC_LO_SCALE), l3 = __float2half_rn((w3 - __half2float(h3)) * TC_LO_SCALE);
-                        uint2 hv, lv;
-                        hv.x = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                        hv.y = (uint32_t)__half_as_ushort(h2) | ((uint32_t)__half_as_ushort(h3) << 16);
-                        lv.x = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-                        lv.y = (uint32_t)__half_as_ushort(l2) | ((uint32_t)__half_as_ushort(l3) << 16);
-                        const size_t off = (size_t)(sl >> 1) * 128 + (size_t)nl * 16 + (size_t)shf * 8;
-                        *reinterpret_cast<uint2 *>(tab + (size_t)o * sbo + off) = hv;               // rows [0, NC): h
-                        *reinterpret_cast<uint2 *>(tab + (size_t)(noct + o) * sbo + off) = lv;      // rows [NC, 2 NC): l
                     }
                 }
                 fence_proxy_async();                                     // generic-proxy stores -> async-proxy reads of the MMA
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tab_full + 8 * ts);
+                TCP(t_work += clock64() - tw0;);
             }
         }
+        TCP(if (lane == 0 && bw == 0 && blockIdx.x % 37 == 0) printf("cta %3d tables: total %lld wait rec_full %lld tab_empty %lld work %lld\n", (int)blockIdx.x, clock64() - t_all, w_rec, w_tab, t_work););
     } else {
         // =============================================================== epilogue (warps 0-3: TMEM lanes 32 w .. 32 w + 31)
         unsigned int n_decided = 0;
         const int row = warp * 32 + lane;
-        const int nch = (G + 7) / 8;                                       // chunks of 8 strains = 24 table columns
+        TCP(long long w_rec = 0; long long w_acc = 0; const long long t_all = clock64(););
         for (uint32_t i = 0;; i++) {
             const uint32_t r = i % TC_NREC;
-            mbar_wait(rec_full + 8 * r, (i / TC_NREC) & 1u);
+            TCW(w_rec, mbar_wait_warp(rec_full + 8 * r, (i / TC_NREC) & 1u, lane));
             const TcRec rc = rec[r];
             if (rc.count == 0) break;
             // what the decision needs besides the sums, fetched before the sums are waited for
@@ -403,45 +433,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
                 for (int g = 0; g < G; g++) zero_word |= (w[g] == 0u);      // u == 0 (c_sample_tau.c:174): reference-order path
             }
             const uint32_t as = i & 1u;
-            mbar_wait(acc_full + 8 * as, (i >> 1) & 1u);
+            TCW(w_acc, mbar_wait_warp(acc_full + 8 * as, (i >> 1) & 1u, lane));
             tc_fence_after();
             const uint32_t t0 = tmem_base + as * (uint32_t)L.acc_stride + ((uint32_t)(warp * 32) << 16);
             const float bn = nk * bn_scale + 1e-6f;
-            uint32_t mask = 0;
-            for (int ch = 0; ch < nch; ch++) {
-                float hi[24], lo[24];
-#pragma unroll
-                for (int q = 0; q < 3; q++) {
-                    const int c0 = 24 * ch + 8 * q;                       // (warp-uniform guards: the loads are .sync.aligned)
-                    if (c0 < NC) {
-                        tc_ld8(t0 + (uint32_t)c0, reinterpret_cast<float(&)[8]>(hi[8 * q]));
-                        tc_ld8(t0 + (uint32_t)(NC + c0), reinterpret_cast<float(&)[8]>(lo[8 * q]));
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < 8; e++) { hi[8 * q + e] = 0.f; lo[8 * q + e] = 0.f; }
-                    }
-                }
+            // 8 columns at a time (16 registers): a column is "open" unless its candidate trails the current base by more than
+            // the gap after the bound; a strain is decided "stay" iff its three columns are closed
+            unsigned long long open = 0ull;
+            for (int c0 = 0; c0 < NC; c0 += 8) {
+                float hi[8], lo[8];
+                tc_ld8(t0 + (uint32_t)c0, hi);
+                tc_ld8(t0 + (uint32_t)(NC + c0), lo);
                 tc_wait_ld();
+                tc_launder8(hi);
+                tc_launder8(lo);
 #pragma unroll
-                for (int q = 0; q < 3; q++) {
-                    tc_launder8(reinterpret_cast<float(&)[8]>(hi[8 * q]));
-                    tc_launder8(reinterpret_cast<float(&)[8]>(lo[8 * q]));
-                }
-#pragma unroll
-                for (int gl = 0; gl < 8; gl++) {
-                    const int g = 8 * ch + gl;
-                    if (g < G) {
-                        const float d0 = fmaf(lo[3 * gl], 1.0f / TC_LO_SCALE, hi[3 * gl]), d1 = fmaf(lo[3 * gl + 1], 1.0f / TC_LO_SCALE, hi[3 * gl + 1]),
-                                    d2 = fmaf(lo[3 * gl + 2], 1.0f / TC_LO_SCALE, hi[3 * gl + 2]);
-                        const bool stay = (d0 * LN2 + bn < -TAU_GAP) && (d1 * LN2 + bn < -TAU_GAP) && (d2 * LN2 + bn < -TAU_GAP);
-                        if (!stay) mask |= 1u << g;
-                        if (p.dbg && have) {
-                            float *dst = p.dbg + (size_t)vown * ncol + 3 * g;
-                            dst[0] = d0; dst[1] = d1; dst[2] = d2;
-                        }
-                    }
+                for (int e = 0; e < 8; e++) {
+                    const float d = hi[e] + lo[e];
+                    if (!(d * LN2 + bn < -TAU_GAP)) open |= 1ull << (c0 + e);
+                    if (p.dbg && have && c0 + e < ncol) p.dbg[(size_t)vown * ncol + c0 + e] = d;
                 }
             }
+            uint32_t mask = 0;
+            for (int g = 0; g < G; g++) if ((open >> (3 * g)) & 7ull) mask |= 1u << g;
             // the sums are in registers: hand the accumulator and the record back
             tc_fence_before();
             __syncwarp();
@@ -462,6 +476,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
         }
         n_decided = (unsigned int)warp_sum_u64((unsigned long long)n_decided);
         if (lane == 0 && n_decided && p.tier_counts) atomicAdd(p.tier_counts, (unsigned long long)n_decided);
+        TCP(if (lane == 0 && warp == 0 && blockIdx.x % 37 == 0) printf("cta %3d epilogue: total %lld wait rec_full %lld acc_full %lld\n", (int)blockIdx.x, clock64() - t_all, w_rec, w_acc););
     }
     // ---- teardown: every role is done with tensor memory
     tc_fence_before();

@@ -53,6 +53,10 @@ struct TauParams {
     int *img_site;
     const int *site_row;
     int need_img;
+    // sampleTauFixTau (HaploSNP_Sampler.py:196-222): strains below g_begin keep their base; logp_out [V][4] (or nullptr) gets the
+    // normalised log-probabilities (normaliseLogProb, :186-194) of strain g_begin's four bases before its draw
+    int g_begin;
+    double *logp_out;
     unsigned long long *tier_counts;  // [3] += draws decided by tier 1 / 2 / 3 (or nullptr)
 };
 
@@ -372,14 +376,15 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
         __syncwarp();
         KP_T(kp1);
 
-        for (int g = 0; g < G; g++) {
+        for (int g = p.g_begin; g < G; g++) {
             if (!((todo >> g) & 1u) && code == code_in) { n1++; continue; }   // decided "stay" by the screening pass
             const int cur = code_get(code, g);
             const uint32_t w = ww[g];
             // MT19937 mode: gsl_rng_uniform, c_sample_tau.c:174 (u = 0 possible).  Philox mode: mid-point of the word's cell.
             const double u = p.words ? (double)w / 4294967296.0 : ((double)w + 0.5) / 4294967296.0;
             int t = -1;
-            const bool usable = fast_ok && (w != 0u || !p.words);
+            const bool record = p.logp_out != nullptr && g == p.g_begin;      // this step's log-probabilities are an output: FP64 path
+            const bool usable = fast_ok && (w != 0u || !p.words) && !record;
             if (usable && screened && code == code_in) {
                 // a step the screening pass left open: its gap test already failed on the same kind of sums, so go straight
                 // to the tracked sums and the brackets (which also settle a decisive flip)
@@ -421,6 +426,14 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
                 tau_exact_logp(tile, gT, eta_s, code, g, S, Sp, G, lane, L);
                 t = tau_exact_pick(L, u);
                 n3++;
+                if (record && lane == 0) {
+                    double mx = L[0];
+                    for (int b = 1; b < 4; b++) if (L[b] > mx) mx = L[b];
+                    double sum = 0.0;
+                    for (int b = 0; b < 4; b++) sum += exp(L[b] - mx);
+                    const double ls = log(sum);
+                    for (int b = 0; b < 4; b++) p.logp_out[(size_t)v * 4 + b] = (L[b] - mx) - ls;
+                }
             }
             if (t != cur) {
                 // P += (eta[t][b] - eta[cur][b]) * gamma[s][g]; refresh K = sum_b n_b lg2 P_b

@@ -103,6 +103,13 @@ class Engine:
         check(self._L.desman_sample_tau(self._h, C.byref(n)), "desman_sample_tau")
         return n.value
 
+    def sample_tau_fix(self, H, want_logp=True):
+        """sampleTauFixTau (:196-222): redraw strains [H, G); returns (logp [V,4] or None, nchange)."""
+        logp = np.empty((self.V, 4)) if want_logp else None
+        n = C.c_int64(0)
+        check(self._L.desman_sample_tau_fix(self._h, int(H), _lib.ptr_d(logp), C.byref(n)), "desman_sample_tau_fix")
+        return logp, n.value
+
     def mu_stats(self):
         sm = np.zeros((self.S, self.G), dtype=np.int64)
         es = np.zeros((4, 4), dtype=np.int64)
@@ -195,6 +202,12 @@ class Engine:
         check(self._L.desman_get_star(self._h, _lib.ptr_i64(tau), _lib.ptr_d(gamma), _lib.ptr_d(eta), C.byref(lp),
                                       C.byref(it)), "desman_get_star")
         return dict(tau=tau, gamma=gamma, eta=eta, lp=lp.value, iter=it.value)
+
+    def get_esum_store(self, n_iter):
+        """E_store[i].sum(axis=(0,1)) [n_iter,4,4] of the last update() (Esum[a_obs,b_true] per sweep)."""
+        out = np.empty((n_iter, 4, 4), dtype=np.int64)
+        check(self._L.desman_get_esum_store(self._h, _lib.ptr_i64(out)), "desman_get_esum_store")
+        return out
 
     def get_star_index(self):
         out = np.empty((self.V, self.G), dtype=np.uint8)

@@ -106,6 +106,8 @@ int desman_update_tau(desman_ctx *ctx, int n_iter, const double *gamma_store, co
 int desman_get_star(desman_ctx *ctx, int64_t *tau_star, double *gamma_star, double *eta_star,
                     double *lp_star, int *iter_star);
 int desman_get_star_index(desman_ctx *ctx, uint8_t *tau_star_idx /*V*G*/);   /* tau_star as base indices */
+/* E_store[i].sum(axis=(0,1)) for every sweep i of the last desman_update: Esum[a_obs][b_true] (:557) */
+int desman_get_esum_store(desman_ctx *ctx, int64_t *esum_store /*n_iter*16*/);
 /* sum over the sweeps of the last update()/update_tau() of one-hot tau: tau_store.sum(axis=0)
  * (tauMean :479-483, probabilisticTau :834-840) */
 int desman_get_tau_sum(desman_ctx *ctx, int64_t *tau_sum /*V*G*4*/);
@@ -137,6 +139,12 @@ int desman_get_group_stats(desman_ctx *ctx, int64_t out[8]);
  * D[v][3g+j] = L(candidate j of strain g) - L(current base) in log2 units (NaN: site in no group) and the mask of strains
  * the gap test left undecided (0xffffffff: none, the site is not on the work list). */
 int desman_debug_screen(desman_ctx *ctx, float *D /*V*3G*/, uint32_t *mask /*V*/);
+
+/* sampleTauFixTau (HaploSNP_Sampler.py:196-222) on the current device state: strains [H, G) of every site are redrawn in
+ * order under the Philox contract of the tau draws; logp [V][4] (may be NULL) = normalised log-probabilities
+ * (normaliseLogProb, :186-194) of strain H's four bases before its draw.  Option "advance_sweep" = n moves the Philox sweep
+ * counter on by n (loops over desman_mu_stats / desman_draw_gamma_eta, which leave it where it is). */
+int desman_sample_tau_fix(desman_ctx *ctx, int H, double *logp /*V*4*/, int64_t *nchange);
 
 /* Multi-GPU: one context per process/GPU, sites sharded by desman_set_counts(v0, V_total).
  * desman_comm_unique_id fills a 128-byte NCCL id on rank 0; every rank calls desman_comm_init. */

@@ -154,9 +154,21 @@ void oracle_tau_step_probs(const int64_t *tau_index_v, const double *pi, const d
 /* midpoint = 0: u = w / 2^32 (gsl_rng_uniform, c_sample_tau.c:174; u = 0 possible);
  * midpoint = 1: u = (w + 0.5) / 2^32 (the Philox contract of the GPU chain: u is never 0, so a step whose
  * current base holds all but < 2^-33 of the mass is decided without looking at the word). */
+/* g_begin > 0 / logp_out != NULL: sampleTauFixTau (HaploSNP_Sampler.py:196-222): strains below g_begin keep their base, and
+ * the normalised log-probabilities (normaliseLogProb, :186-194) of the four bases of strain g_begin are recorded per site
+ * before its draw. */
+static int sample_tau_words_impl2(int64_t *tau, const double *pi, const double *eta,
+                                  const int64_t *variants, int V, int G, int S,
+                                  const uint32_t *words, int midpoint, int g_begin, double *logp_out);
 static int sample_tau_words_impl(int64_t *tau, const double *pi, const double *eta,
                                  const int64_t *variants, int V, int G, int S,
                                  const uint32_t *words, int midpoint)
+{
+    return sample_tau_words_impl2(tau, pi, eta, variants, V, G, S, words, midpoint, 0, NULL);
+}
+static int sample_tau_words_impl2(int64_t *tau, const double *pi, const double *eta,
+                                  const int64_t *variants, int V, int G, int S,
+                                  const uint32_t *words, int midpoint, int g_begin, double *logp_out)
 {
     int nchange = 0;
 #pragma omp parallel reduction(+ : nchange)
@@ -172,9 +184,15 @@ static int sample_tau_words_impl(int64_t *tau, const double *pi, const double *e
                 for (int b = 0; b < 4; b++) if (tv[g * 4 + b] == 1) { idx[g] = b; break; }
             }
             const int64_t *nv = variants + (size_t)v * S * 4;
-            for (int g = 0; g < G; g++) {
+            for (int g = g_begin; g < G; g++) {
                 double p[4];
                 tau_step_logp(idx, pi, eta, nv, G, S, g, scratch, p);
+                if (logp_out && g == g_begin) {                             /* normaliseLogProb, HaploSNP_Sampler.py:186-194 */
+                    double mx = p[0], sum = 0.0;
+                    for (int b = 1; b < 4; b++) if (p[b] > mx) mx = p[b];
+                    for (int b = 0; b < 4; b++) sum += exp(p[b] - mx);
+                    for (int b = 0; b < 4; b++) logp_out[(size_t)v * 4 + b] = (p[b] - mx) - log(sum);
+                }
                 softmax4(p);                                                /* :172 */
                 double u = midpoint ? ((double)words[(size_t)v * G + g] + 0.5) / 4294967296.0
                                     : words[(size_t)v * G + g] / 4294967296.0;  /* :174 gsl_rng_uniform */
@@ -224,6 +242,28 @@ int oracle_sample_tau_philox(int64_t *tau, const double *pi, const double *eta,
             w[(size_t)v * G + g] = o[0];
         }
     int r = sample_tau_words_impl(tau, pi, eta, variants, V, G, S, w, 1);
+    free(w);
+    return r;
+}
+
+/* sampleTauFixTau (HaploSNP_Sampler.py:196-222) under the Philox contract of the tau draws: strains [H, G) are redrawn in
+ * order with u = (w + 0.5) / 2^32, w = Philox(ctr = (v0 + v, g, sweep, STAGE_TAU << 28)).x, by sample4(softmax(L), u) exactly
+ * like a tau step (the reference draws from numpy's sequential multinomial, which has no parallel form); logp_out[v][b] =
+ * normalised log-probabilities of strain H's four bases before its draw. */
+int oracle_sample_tau_fix_philox(int64_t *tau, const double *pi, const double *eta,
+                                 const int64_t *variants, int V, int G, int S,
+                                 uint64_t seed, uint32_t sweep, int64_t v0, int H, double *logp_out)
+{
+    size_t n = (size_t)V * G;
+    uint32_t *w = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
+#pragma omp parallel for schedule(static)
+    for (int v = 0; v < V; v++)
+        for (int g = 0; g < G; g++) {
+            uint32_t o[4];
+            philox((uint32_t)(v0 + v), (uint32_t)g, sweep, (uint32_t)ORACLE_STAGE_TAU << 28, seed, o);
+            w[(size_t)v * G + g] = o[0];
+        }
+    int r = sample_tau_words_impl2(tau, pi, eta, variants, V, G, S, w, 1, H, logp_out);
     free(w);
     return r;
 }

@@ -45,6 +45,9 @@ int oracle_sample_tau_mt(int64_t *tau, const double *pi, const double *eta,
 int oracle_sample_tau_philox(int64_t *tau, const double *pi, const double *eta,
                              const int64_t *variants, int V, int G, int S,
                              uint64_t seed, uint32_t sweep, int64_t v0);
+int oracle_sample_tau_fix_philox(int64_t *tau, const double *pi, const double *eta,
+                                 const int64_t *variants, int V, int G, int S,
+                                 uint64_t seed, uint32_t sweep, int64_t v0, int H, double *logp_out);
 /* the four candidate log-likelihoods and normalised probabilities of one (v,g) step
  * (c_sample_tau.c:136-172), for inspection in tests */
 void oracle_tau_step_probs(const int64_t *tau_index_v, const double *pi, const double *eta,

@@ -65,6 +65,9 @@ def lib():
         L.oracle_sample_tau_philox.argtypes = [_p64, _pd, _pd, _p64, C.c_int, C.c_int, C.c_int,
                                                C.c_uint64, C.c_uint32, C.c_int64]
         L.oracle_sample_tau_philox.restype = C.c_int
+        L.oracle_sample_tau_fix_philox.argtypes = [_p64, _pd, _pd, _p64, C.c_int, C.c_int, C.c_int,
+                                                   C.c_uint64, C.c_uint32, C.c_int64, C.c_int, _pd]
+        L.oracle_sample_tau_fix_philox.restype = C.c_int
         L.oracle_tau_step_probs.argtypes = [_p64, _pd, _pd, _p64, C.c_int, C.c_int, C.c_int, _pd, _pd]
         L.oracle_mu_stats.argtypes = [_p64, _pd, _pd, _p64, C.c_int, C.c_int, C.c_int,
                                       C.c_uint64, C.c_uint32, C.c_int64, _p64, _p64]
@@ -176,6 +179,21 @@ def sample_tau_philox(tau, pi, eta, variants, seed, sweep, v0=0):
     eta, pe = _f64(eta)
     variants, pv = _i64(variants)
     return lib().oracle_sample_tau_philox(tau.ctypes.data_as(_p64), ppi, pe, pv, V, G, S, seed, sweep, v0)
+
+
+def sample_tau_fix_philox(tau, H, pi, eta, variants, seed, sweep, v0=0):
+    """sampleTauFixTau (HaploSNP_Sampler.py:196-222) under the Philox contract; tau int64 one-hot, in place.
+    Returns (storeHLogProb [V,4], nchange)."""
+    assert tau.dtype == np.int64 and tau.flags.c_contiguous
+    V, G = tau.shape[0], tau.shape[1]
+    S = pi.shape[0]
+    pi, ppi = _f64(pi)
+    eta, pe = _f64(eta)
+    variants, pv = _i64(variants)
+    logp = np.zeros((V, 4))
+    n = lib().oracle_sample_tau_fix_philox(tau.ctypes.data_as(_p64), ppi, pe, pv, V, G, S, seed, sweep, v0, H,
+                                           logp.ctypes.data_as(_pd))
+    return logp, n
 
 
 class RefSampleTau:

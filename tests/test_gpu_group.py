@@ -248,7 +248,7 @@ def test_tc_screening_sums_against_float64(eng_mod, V, S, G, depth):
     qmin = 0.99 * np.float32(p["gamma_true"].min()) * np.float32(p["eta0"].min())
     mq0 = max(1.0, 1.0 - np.log2(qmin))
     Sp = 2 * ((S + 3) // 4 * 4)                                                 # >= the padded sample count of any K-block split
-    e_entry = (6 * 2.0 ** -24 * 1.4427 + 2 * 2.0 ** -22) + (2.0 ** -22 + 2.0 ** -24) * 2 * mq0 + (2 * G + 2) * 2.0 ** -53 * 1.4427 / qmin
+    e_entry = (6 * 2.0 ** -24 * 1.4427 + 2 * 2.0 ** -22) + (2.0 ** -22 + 2.0 ** -24) * 2 * mq0 + (2 * G + 2) * 2.0 ** -53 * 1.4427 / qmin + 2.0 ** -25
     bound = nsite[grouped] * (e_entry + (Sp / 2 + 12) * 2.0 ** -20 * mq0) + 1e-6
     assert (err <= bound).all(), (float((err / bound).max()), int(np.argmax(err / bound)))
     print("tc screening: max |D - D64| / bound = %.4f, max abs err %.3e log2 units over %d sites" % (float((err / bound).max()), float(err.max()), int(grouped.sum())))
