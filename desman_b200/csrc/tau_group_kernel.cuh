@@ -10,7 +10,7 @@
 // log-likelihood differences of a site become a small dense contraction of its count row with that table:
 //     D[v][g][a] = sum_{s,b} n[v][s][b] * Wd[g][a][s][b]           (3*G*4*S FFMA per site, no transcendental)
 // As long as the pattern of a site does not change during its walk over the strains (no flip), the D of all G steps
-// come from the same table.  A step whose current base leads every other candidate by more than 60 nats after the rigorous
+// come from the same table.  A step whose current base leads every other candidate by more than TAU_GAP nats after the rigorous
 // error bound is decided ("stay", exactly as tier 1 of the per-site kernel); a site with any undecided step is appended to a
 // work list together with the bit mask of those steps, and the per-site kernel then walks only the listed sites, skipping
 // the decided steps until the first flip.  Results are therefore identical to the per-site kernel's, draw for draw.
@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 16 / TGM_WARPS) tau_group_mma_
             const bool own = g8 < 4 && pbase + kown < count;
             const int vown = pm.vown, sown = pm.sown;
             const float (&nk)[4] = pm.nk;
-            // a strain is decided "stay" iff each of its three candidates trails the current base by > 60 nats after the bound
+            // a strain is decided "stay" iff each of its three candidates trails the current base by more than TAU_GAP nats after the bound
             uint32_t m[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
             for (int mt = 0; mt < MT; mt++)

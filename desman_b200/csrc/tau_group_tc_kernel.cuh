@@ -10,9 +10,9 @@
 // columns the N dimension.  Operands are FP16 (kind::f16, FP32 accumulation in TMEM):
 //   * counts < 2048 are exact in FP16 (11-bit significand): the group-ordered copy of the count rows is kept as fp16x4 cells
 //     (8 bytes per (v,s) instead of 16: the pass reads HALF the bytes of the canonical int32x4 tensor);
-//   * a table entry is split as  Wd = h + l,  h = fp16(Wd), l = fp16(Wd - h)  (|Wd - h - l| <= max(2^-22 |Wd|, 2^-25): below
-//     6e-5 the remainder l is a subnormal fp16 with spacing 2^-24); h and l are separate columns of the B operand
-//     (N = 2*NC), summed by the epilogue.
+//   * a table entry is split as  Wd = h + l,  h = Wd truncated to 11 significant bits, l = fp16(Wd - h)
+//     (|Wd - h - l| <= 2^-21 |Wd| + 2^-24: below 2^-14 both pieces are subnormal fp16 values on the 2^-24 grid); h and l are
+//     separate columns of the B operand (N = 2*NC), summed by the epilogue.
 // Layout (no swizzle, K-major, the canonical "interleaved" UMMA layout): 8 rows x 16 bytes form a 128-byte core matrix; core
 // matrices that are neighbours along K are LBO = 128 bytes apart, 8-row groups SBO = KC*128 bytes apart (KC = 16-byte chunks
 // per K block).  The regroup pass (maintain_kernel.cuh) writes the count image in exactly this order, every work item padded
@@ -20,9 +20,10 @@
 // cp.async.bulk per (item, K block), no tensor map, no register staging.
 // Roles (warp-specialised, one persistent CTA per SM; everything between them goes through mbarriers):
 //   warps 0-3   epilogue: TMEM -> registers (warp w owns lanes 32w..32w+31), gap test, work list
-//   warp 4      producer: work tickets, item records, bulk copies of the count rows (2-stage ring)
+//   warp 4      ticket fetcher: work tickets and item records up to 8 items ahead, L2 prefetch of the item's rows
 //   warp 5      MMA issuer (one elected lane)
-//   warps 6-21  table builders: mixture P in FP64, the 12 lg2 per (strain, sample), fp16 split, stores in B-operand order
+//   warp 6      copy issuer: bulk copies of the count rows (2-stage ring)
+//   warps 7-22  table builders: mixture P in FP64, the 12 lg2 per (strain, sample), fp16 split, stores in B-operand order
 // Results are those of the FFMA / mma.sync forms draw for draw (the error model below is charged instead of theirs).
 #pragma once
 #include <cuda_fp16.h>
@@ -36,8 +37,8 @@
 #ifndef TC_BUILD_WARPS
 #define TC_BUILD_WARPS 16
 #endif
-#define TC_THREADS ((TC_EPI_WARPS + 2 + TC_BUILD_WARPS) * 32)
-#define TC_NREC 4                   // item-record ring
+#define TC_THREADS ((TC_EPI_WARPS + 3 + TC_BUILD_WARPS) * 32)
+#define TC_NREC 8                   // item-record ring: how far the tickets run ahead
 
 struct TauGroupTcParams {
     const unsigned char *img;  // count image: [K block][row group][KC chunks][8 rows][16 bytes], fp16x4 cells
@@ -132,6 +133,17 @@ __device__ __forceinline__ void tc_launder8(float (&v)[8])
     asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]));
 }
 
+#define TC_WL_CAP 128
+// a warp's staged work-list entries -> the global list
+__device__ __forceinline__ void tc_flush_worklist(const TauGroup &grp, const uint2 *wl, int n, int lane)
+{
+    int pos = 0;
+    if (lane == 0) pos = atomicAdd(grp.gctl + GC_NWORK, n);
+    pos = __shfl_sync(DESMAN_FULL_MASK, pos, 0);
+    for (int k = lane; k < n; k += 32) grp.work[pos + k] = wl[k];
+    __syncwarp();
+}
+
 // shared-memory matrix descriptor, no swizzle, K-major (cute::UMMA::SmemDescriptor: start >> 4 in [0,14), LBO >> 4 in [16,30),
 // SBO >> 4 in [32,46), version 1 in [46,48), layout type 0 = SWIZZLE_NONE in [61,64))
 __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
@@ -143,7 +155,7 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, 
 // ------------------------------------------------------------------------------------------------ sizes (host + device)
 struct TcLayout {
     int Sp, KC, N, acc_stride, tmem_cols;
-    size_t off_gT, off_eta, off_eta32, off_gT32, off_rec, off_bar, off_stage, off_table, stage_bytes, table_bytes, total;
+    size_t off_gT, off_eta, off_eta32, off_gT32, off_wl, off_rec, off_bar, off_stage, off_table, stage_bytes, table_bytes, total;
 };
 __host__ __device__ static inline TcLayout tc_layout(int S, int G, int SK, int nkb, int NC)
 {
@@ -158,9 +170,10 @@ __host__ __device__ static inline TcLayout tc_layout(int S, int G, int SK, int n
     L.off_eta = o; o += sizeof(double) * 16;
     L.off_eta32 = o; o += sizeof(float) * 16;
     L.off_gT32 = o; o += sizeof(float) * (size_t)G * L.Sp;
+    L.off_wl = o; o += sizeof(uint2) * TC_WL_CAP * TC_EPI_WARPS;
     L.off_rec = o; o += sizeof(TcRec) * TC_NREC;
     o = (o + 15) & ~(size_t)15;
-    L.off_bar = o; o += 8 * 32;
+    L.off_bar = o; o += 8 * 40;
     o = (o + 1023) & ~(size_t)1023;
     L.stage_bytes = (size_t)(TC_ROWS / 8) * L.KC * 128;
     L.table_bytes = (size_t)(L.N / 8) * L.KC * 128;
@@ -179,6 +192,18 @@ __host__ __device__ static inline TcLayout tc_layout(int S, int G, int SK, int n
 #define TCP(x)
 #endif
 
+// -DKPROF: per-item events of every role of a few CTAs (tools/kprof.py prints the pipeline of one CTA)
+// (time stamps go to shared memory and are written out when the CTA is done: a record costs a global atomic, and one per
+// event would stretch the very hand-overs it is meant to show)
+#ifdef KPROF
+#define TCE_ITEMS 32
+#define TCE(role, item) do { if ((item) < TCE_ITEMS) atomicMax(&tce_s[role][item], gtimer()); } while (0)
+#define TCE_MIN(role, item) do { if ((item) < TCE_ITEMS) atomicMin(&tce_s[role][item], gtimer()); } while (0)
+#else
+#define TCE(role, item)
+#define TCE_MIN(role, item)
+#endif
+
 // ------------------------------------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcParams p)
 {
@@ -192,11 +217,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
     float *gT32 = reinterpret_cast<float *>(smem + L.off_gT32);         // [G][Sp]
     TcRec *rec = reinterpret_cast<TcRec *>(smem + L.off_rec);           // [TC_NREC]
     const uint32_t bar0 = smem_u32(smem + L.off_bar);
-    // barriers: rec_full[4] rec_empty[4] cnt_full[2] cnt_empty[2] tab_full[2] tab_empty[2] acc_full[2] acc_empty[2]
-    const uint32_t rec_full = bar0, rec_empty = bar0 + 8 * 4, cnt_full = bar0 + 8 * 8, cnt_empty = bar0 + 8 * 10,
-                   tab_full = bar0 + 8 * 12, tab_empty = bar0 + 8 * 14, acc_full = bar0 + 8 * 16, acc_empty = bar0 + 8 * 18;
+    // barriers: rec_full[NREC] rec_empty[NREC] cnt_full[2] cnt_empty[2] tab_full[2] tab_empty[2] acc_full[2] acc_empty[2]
+    const uint32_t rec_full = bar0, rec_empty = bar0 + 8 * TC_NREC, cnt_full = bar0 + 8 * (2 * TC_NREC), cnt_empty = cnt_full + 8 * 2,
+                   tab_full = cnt_full + 8 * 4, tab_empty = cnt_full + 8 * 6, acc_full = cnt_full + 8 * 8, acc_empty = cnt_full + 8 * 10;
     const uint32_t stage0 = smem_u32(smem + L.off_stage), table0 = smem_u32(smem + L.off_table);
     __shared__ uint32_t tmem_base_s;
+#ifdef KPROF
+    __shared__ unsigned long long tce_s[8][TCE_ITEMS];   // roles: 0 copy issued, 1 mma committed, 2/3 table start first/last, 4/5 table done first/last, 6 acc seen, 7 item done
+    for (int i = threadIdx.x; i < 8 * TCE_ITEMS; i += TC_THREADS) tce_s[i / TCE_ITEMS][i % TCE_ITEMS] = (i / TCE_ITEMS == 2 || i / TCE_ITEMS == 4) ? ~0ull : 0ull;
+#endif
     __shared__ unsigned int gmin_bits, emin_bits;
     __shared__ int unnorm;
 
@@ -264,7 +293,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
     // per read, log2 units: the entry model of the FFMA form (relative parts, lg2.approx floors, lg2.approx and the lq - lP
     // rounding per unit of |lg2|, FP64 cancellation) + [fp16 split 2^-22 + one FP32 accumulation step per 4 samples and piece,
     // each charged 2^-20 of the running magnitude + the hi + lo/1024 add] * max|Wd|, |Wd| <= mq0
-    const float e_entry = TAU_C0 + (2.3841858e-7f + 5.9604645e-8f) * (2.0f * mq0) + TAU_CANCEL(G) / fmaxf(qmin, TAU_QMIN) + 2.9802322e-8f;   // (+ 2^-25: subnormal remainder)
+    const float e_entry = TAU_C0 + (2.3841858e-7f + 5.9604645e-8f) * (2.0f * mq0) + TAU_CANCEL(G) / fmaxf(qmin, TAU_QMIN) + 5.9604645e-8f;   // (+ 2^-24: subnormal pieces)
     const float e_mma = (float)(Sp / 2 + 12) * 9.5367432e-7f;
     const float LN2 = 0.69314718f;
     const float bn_scale = (e_entry + e_mma * mq0) * LN2 * 1.0001f;
@@ -273,11 +302,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
     const int ncol = 3 * G;
 
     if (warp == TC_EPI_WARPS) {
-        // =============================================================== producer
+        // =============================================================== ticket fetcher: item records, up to TC_NREC items ahead
+        // (a ticket is a global atomic and an item record two dependent loads: ~2 us that must not sit between two copies);
+        // the rows of the item start moving into L2 at once
         if (lane == 0) {
             const size_t kb_stride = (size_t)p.img_rg * KC * 128;
-            uint32_t u = 0;
-            TCP(long long w_rec = 0; long long w_cnt = 0; long long n_it = 0; long long rows = 0; const long long t_all = clock64(););
+            TCP(long long w_rec = 0; long long n_it = 0; long long rows = 0; const long long t_all = clock64(););
             for (uint32_t i = 0;; i++) {
                 const uint32_t r = i % TC_NREC;
                 TCW(w_rec, mbar_wait(rec_empty + 8 * r, ((i / TC_NREC) & 1u) ^ 1u));
@@ -287,22 +317,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
                 if (it < nitems) {
                     const int4 a = p.grp.items[2 * it], b = p.grp.items[2 * it + 1];
                     rc.slot = a.x; rc.count = a.z; rc.img0 = b.z; rc.code_lo = (unsigned int)b.x; rc.code_hi = (unsigned int)b.y;
+                    const uint32_t bytes = (((uint32_t)rc.count + 7u) & ~7u) * (uint32_t)KC * 16u;
+                    for (int kb = 0; kb < nkb; kb++) l2_prefetch_row(p.img + (size_t)kb * kb_stride + (size_t)(rc.img0 >> 3) * KC * 128, bytes);
                 }
                 rec[r] = rc;
                 mbar_arrive(rec_full + 8 * r);                         // (release: the record is visible to the waiters)
                 if (rc.count == 0) break;
-                const uint32_t rows8 = ((uint32_t)rc.count + 7u) & ~7u;
-                const uint32_t bytes = rows8 * (uint32_t)KC * 16u;
+                TCP(n_it++; rows += rc.count;);
+            }
+            TCP(if (blockIdx.x % 37 == 0) printf("cta %3d tickets: items %lld rows %lld total %lld wait rec_empty %lld\n", (int)blockIdx.x, n_it, rows, clock64() - t_all, w_rec););
+        }
+    } else if (warp == TC_EPI_WARPS + 2) {
+        // =============================================================== copy issuer: count rows of (item, K block) into the stage ring
+        if (lane == 0) {
+            const size_t kb_stride = (size_t)p.img_rg * KC * 128;
+            uint32_t u = 0;
+            TCP(long long w_rec = 0; long long w_cnt = 0; const long long t_all = clock64(););
+            for (uint32_t i = 0;; i++) {
+                const uint32_t r = i % TC_NREC;
+                TCW(w_rec, mbar_wait(rec_full + 8 * r, (i / TC_NREC) & 1u));
+                const int count = rec[r].count, img0 = rec[r].img0;
+                if (count == 0) break;
+                const uint32_t bytes = (((uint32_t)count + 7u) & ~7u) * (uint32_t)KC * 16u;
                 for (int kb = 0; kb < nkb; kb++, u++) {
                     const uint32_t cs = u & 1u;
                     TCW(w_cnt, mbar_wait(cnt_empty + 8 * cs, ((u >> 1) & 1u) ^ 1u));
                     mbar_arrive_tx(cnt_full + 8 * cs, bytes);
                     tma_bulk_g2s(stage0 + cs * (uint32_t)L.stage_bytes,
-                                 p.img + (size_t)kb * kb_stride + (size_t)(rc.img0 >> 3) * KC * 128, bytes, cnt_full + 8 * cs);
+                                 p.img + (size_t)kb * kb_stride + (size_t)(img0 >> 3) * KC * 128, bytes, cnt_full + 8 * cs);
+                    TCE(0, i);
                 }
-                TCP(n_it++; rows += rc.count;);
             }
-            TCP(if (blockIdx.x % 37 == 0) printf("cta %3d producer: items %lld rows %lld total %lld wait rec_empty %lld cnt_empty %lld\n", (int)blockIdx.x, n_it, rows, clock64() - t_all, w_rec, w_cnt););
+            TCP(if (blockIdx.x % 37 == 0) printf("cta %3d copies: total %lld wait rec_full %lld cnt_empty %lld\n", (int)blockIdx.x, clock64() - t_all, w_rec, w_cnt););
         }
     } else if (warp == TC_EPI_WARPS + 1) {
         // =============================================================== MMA issuer
@@ -324,23 +370,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
                     tc_fence_after();
                     const uint64_t a0 = tc_desc(stage0 + cs * (uint32_t)L.stage_bytes, 128u, sbo);
                     const uint64_t b0 = tc_desc(table0 + cs * (uint32_t)L.table_bytes, 128u, sbo);
+#ifdef TC_ABL_MMA
+                    for (int k = 0; k < 1; k++)
+#else
                     for (int k = 0; k < KC / 2; k++)                      // one K step = 16 fp16 = 2 chunks = 256 bytes = 16 units
+#endif
                         tc_mma_f16(d, a0 + (uint64_t)(16 * k), b0 + (uint64_t)(16 * k), idesc, (kb | k) ? 1u : 0u);
                     tc_commit(cnt_empty + 8 * cs);
                     tc_commit(tab_empty + 8 * cs);
                 }
                 tc_commit(acc_full + 8 * as);
+                TCE(1, i);
             }
             TCP(if (blockIdx.x % 37 == 0) printf("cta %3d mma: total %lld wait rec_full %lld acc_empty %lld tab_full %lld cnt_full(after tab) %lld\n", (int)blockIdx.x, clock64() - t_all, w_rec, w_acc, w_tab, w_cnt););
         }
-    } else if (warp >= TC_EPI_WARPS + 2) {
+    } else if (warp >= TC_EPI_WARPS + 3) {
         // =============================================================== table builders (TC_BUILD_WARPS warps, no cross-warp dependency)
         // A warp task = 8 strains x 4 samples; a lane = one (strain, sample): its base q[b] = P[b] - eta[cur][b] gamma (FP64, one
         // rounding) serves the 3 candidates x 4 bases = 12 table entries it writes.  The mixture P[s][b] = sum_h eta[tau_h][b]
         // gamma[s][h] (FP64, ascending h) of the task's 4 samples is formed by lanes 0-15 (one (sample, base) each; lanes 16-31
         // mirror them) and handed round by shuffles.  Stores: for a fixed candidate the 8 strains of a task hit 8 different rows
         // mod 8 (3 is coprime to 8), so a half warp writes 16 distinct 8-byte pieces of 128-byte core matrices: conflict-free.
-        const int bw = warp - (TC_EPI_WARPS + 2);
+        const int bw = warp - (TC_EPI_WARPS + 3);
         const int gl = (lane >> 1) & 7, shf = lane & 1, sp = lane >> 4;
         const int ps = (lane >> 2) & 3, pbb = lane & 3;                   // the (sample, base) pair this lane forms P for
         const int mys = 2 * sp + shf;                                      // this lane's sample within the task
@@ -357,15 +408,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
                 const uint32_t ts = u & 1u;
                 TCW(w_tab, mbar_wait_warp(tab_empty + 8 * ts, ((u >> 1) & 1u) ^ 1u, lane));
                 TCP(const long long tw0 = clock64(););
+                if (lane == 0) { TCE_MIN(2, i); TCE(3, i); }
                 unsigned char *tab = smem + L.off_table + ts * L.table_bytes;
+#ifdef TC_ABL_TABLE
+                for (int task = ntask; task < ntask; task += TC_BUILD_WARPS) {
+#else
                 for (int task = bw; task < ntask; task += TC_BUILD_WARPS) {
+#endif
                     const int go = task % ngo, sq = task / ngo;
                     // ---- mixture of the task's 4 samples
                     const int s_p = kb * SK + 4 * sq + ps;
                     double Pv = 1.0;                                        // padding samples: finite logs
                     if (s_p < S) {
-                        Pv = 0.0;
-                        for (int h = 0; h < G; h++) Pv = fma(eta_s[4 * code_get(code, h) + pbb], gT[h * Sp + s_p], Pv);
+                        double Pa = 0.0, Pb = 0.0;                          // two chains: even and odd strains
+                        int h = 0;
+                        for (; h + 1 < G; h += 2) {
+                            Pa = fma(eta_s[4 * code_get(code, h) + pbb], gT[h * Sp + s_p], Pa);
+                            Pb = fma(eta_s[4 * code_get(code, h + 1) + pbb], gT[(h + 1) * Sp + s_p], Pb);
+                        }
+                        if (h < G) Pa = fma(eta_s[4 * code_get(code, h) + pbb], gT[h * Sp + s_p], Pa);
+                        Pv = Pa + Pb;
                     }
                     const float lv_ = lg2_fast((float)Pv);
                     const double P0 = __shfl_sync(DESMAN_FULL_MASK, Pv, 4 * mys + 0), P1 = __shfl_sync(DESMAN_FULL_MASK, Pv, 4 * mys + 1),
@@ -390,9 +452,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
                                 w0 = lg2_fast(fmaf(ea.x, gf, q0)) - l0; w1 = lg2_fast(fmaf(ea.y, gf, q1)) - l1;
                                 w2 = lg2_fast(fmaf(ea.z, gf, q2)) - l2; w3 = lg2_fast(fmaf(ea.w, gf, q3)) - l3;
                             }
-                            const __half2 h01 = __floats2half2_rn(w0, w1), h23 = __floats2half2_rn(w2, w3);
-                            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                            const __half2 l01 = __floats2half2_rn(w0 - f01.x, w1 - f01.y), l23 = __floats2half2_rn(w2 - f23.x, w3 - f23.y);
+                            // h = the entry truncated to fp16's 11 significant bits (a mask: exact in fp16 unless |w| < 2^-14, where
+                            // the conversion rounds it on the 2^-24 grid), l = fp16(w - h_truncated)
+                            const float t0 = __uint_as_float(__float_as_uint(w0) & 0xffffe000u), t1 = __uint_as_float(__float_as_uint(w1) & 0xffffe000u),
+                                        t2 = __uint_as_float(__float_as_uint(w2) & 0xffffe000u), t3 = __uint_as_float(__float_as_uint(w3) & 0xffffe000u);
+                            const __half2 h01 = __floats2half2_rn(t0, t1), h23 = __floats2half2_rn(t2, t3);
+                            const __half2 l01 = __floats2half2_rn(w0 - t0, w1 - t1), l23 = __floats2half2_rn(w2 - t2, w3 - t3);
                             uint2 hv, lv;
                             hv.x = *reinterpret_cast<const uint32_t *>(&h01); hv.y = *reinterpret_cast<const uint32_t *>(&h23);
                             lv.x = *reinterpret_cast<const uint32_t *>(&l01); lv.y = *reinterpret_cast<const uint32_t *>(&l23);
@@ -406,6 +471,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
                 fence_proxy_async();                                     // generic-proxy stores -> async-proxy reads of the MMA
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tab_full + 8 * ts);
+                if (lane == 0) { TCE_MIN(4, i); TCE(5, i); }
                 TCP(t_work += clock64() - tw0;);
             }
         }
@@ -414,6 +480,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
         // =============================================================== epilogue (warps 0-3: TMEM lanes 32 w .. 32 w + 31)
         unsigned int n_decided = 0;
         const int row = warp * 32 + lane;
+        uint2 *wl = reinterpret_cast<uint2 *>(smem + L.off_wl) + warp * TC_WL_CAP;
+        int wl_n = 0;
         TCP(long long w_rec = 0; long long w_acc = 0; const long long t_all = clock64(););
         for (uint32_t i = 0;; i++) {
             const uint32_t r = i % TC_NREC;
@@ -434,21 +502,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
             }
             const uint32_t as = i & 1u;
             TCW(w_acc, mbar_wait_warp(acc_full + 8 * as, (i >> 1) & 1u, lane));
+            if (warp == 0 && lane == 0) TCE(6, i);
             tc_fence_after();
             const uint32_t t0 = tmem_base + as * (uint32_t)L.acc_stride + ((uint32_t)(warp * 32) << 16);
             const float bn = nk * bn_scale + 1e-6f;
-            // 8 columns at a time (16 registers): a column is "open" unless its candidate trails the current base by more than
-            // the gap after the bound; a strain is decided "stay" iff its three columns are closed
+            // 24 columns at a time, all six loads in flight before the one wait; a column is "open" unless its candidate trails the
+            // current base by more than the gap after the bound; a strain is decided "stay" iff its three columns are closed
             unsigned long long open = 0ull;
-            for (int c0 = 0; c0 < NC; c0 += 8) {
-                float hi[8], lo[8];
-                tc_ld8(t0 + (uint32_t)c0, hi);
-                tc_ld8(t0 + (uint32_t)(NC + c0), lo);
-                tc_wait_ld();
-                tc_launder8(hi);
-                tc_launder8(lo);
+#ifdef TC_ABL_EPI
+            for (int c0 = NC; c0 < NC; c0 += 24) {
+#else
+            for (int c0 = 0; c0 < NC; c0 += 24) {
+#endif
+                float hi[24], lo[24];
 #pragma unroll
-                for (int e = 0; e < 8; e++) {
+                for (int q = 0; q < 3; q++) {
+                    if (c0 + 8 * q < NC) {                                  // (warp-uniform: the loads are .sync.aligned)
+                        tc_ld8(t0 + (uint32_t)(c0 + 8 * q), reinterpret_cast<float(&)[8]>(hi[8 * q]));
+                        tc_ld8(t0 + (uint32_t)(NC + c0 + 8 * q), reinterpret_cast<float(&)[8]>(lo[8 * q]));
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < 8; e++) { hi[8 * q + e] = -1.0e30f; lo[8 * q + e] = 0.f; }
+                    }
+                }
+                tc_wait_ld();
+#pragma unroll
+                for (int q = 0; q < 3; q++) {
+                    tc_launder8(reinterpret_cast<float(&)[8]>(hi[8 * q]));
+                    tc_launder8(reinterpret_cast<float(&)[8]>(lo[8 * q]));
+                }
+#pragma unroll
+                for (int e = 0; e < 24; e++) {
                     const float d = hi[e] + lo[e];
                     if (!(d * LN2 + bn < -TAU_GAP)) open |= 1ull << (c0 + e);
                     if (p.dbg && have && c0 + e < ncol) p.dbg[(size_t)vown * ncol + c0 + e] = d;
@@ -466,14 +550,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
                 push = mask != 0u;
                 if (!push) n_decided += (unsigned int)G;
             }
+            // work-list entries are staged per warp in shared memory and flushed in batches: one global atomic (~1 us with its
+            // return value) per ~100 entries instead of one per item
             const unsigned int bal = __ballot_sync(DESMAN_FULL_MASK, push);
             if (bal) {
-                int pos = 0;
-                if (lane == 0) pos = atomicAdd(p.grp.gctl + GC_NWORK, __popc(bal));
-                pos = __shfl_sync(DESMAN_FULL_MASK, pos, 0) + __popc(bal & ((1u << lane) - 1u));
-                if (push) p.grp.work[pos] = make_uint2((unsigned int)vown, mask);
+                if (wl_n + __popc(bal) > TC_WL_CAP) { tc_flush_worklist(p.grp, wl, wl_n, lane); wl_n = 0; }
+                if (push) wl[wl_n + __popc(bal & ((1u << lane) - 1u))] = make_uint2((unsigned int)vown, mask);
+                wl_n += __popc(bal);
+                __syncwarp();
             }
+            if (warp == 0 && lane == 0) TCE(7, i);
         }
+        if (wl_n) tc_flush_worklist(p.grp, wl, wl_n, lane);
         n_decided = (unsigned int)warp_sum_u64((unsigned long long)n_decided);
         if (lane == 0 && n_decided && p.tier_counts) atomicAdd(p.tier_counts, (unsigned long long)n_decided);
         TCP(if (lane == 0 && warp == 0 && blockIdx.x % 37 == 0) printf("cta %3d epilogue: total %lld wait rec_full %lld acc_full %lld\n", (int)blockIdx.x, clock64() - t_all, w_rec, w_acc););
@@ -481,6 +569,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
     // ---- teardown: every role is done with tensor memory
     tc_fence_before();
     __syncthreads();
+#ifdef KPROF
+    if (tid == 0 && blockIdx.x % 37 == 0)
+        for (int it = 0; it < TCE_ITEMS; it++)
+            for (int ro = 0; ro < 8; ro++)
+                if (tce_s[ro][it] != 0ull && tce_s[ro][it] != ~0ull) krec_put(KP_TC_EVT, (int)blockIdx.x, ro, it, tce_s[ro][it], 0);
+#endif
     if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)L.tmem_cols) : "memory");

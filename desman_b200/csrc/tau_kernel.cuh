@@ -11,8 +11,8 @@
 // arithmetic the kernel is bound by the FP64/log rate, ~100x above its HBM floor.  What has to be
 // reproduced, though, is only the DRAW t = sample4(softmax(L), u).  So per (v,g):
 //   tier 1  log-likelihood differences D_a = L_a - L_cur in FP32 (MUFU lg2.approx) with a rigorous
-//           running error bound B_a.  If one candidate leads every other by more than 60 nats even
-//           after the bounds, its probability differs from 1 by < 3e-26 < 2^-32 <= u-grid spacing,
+//           running error bound B_a.  If one candidate leads every other by more than TAU_GAP = 26 nats even
+//           after the bounds, its probability differs from 1 by < 1.6e-11 < 2^-33 <= what u can come within,
 //           so the draw is decided without evaluating a single exp.
 //   tier 2  otherwise the CDF boundaries are bracketed in FP64 from D_a +- B_a; if u lies outside
 //           every bracket (plus 1e-9 slack) the draw is decided.
@@ -62,7 +62,12 @@ struct TauParams {
 
 #define TAU_WARPS 8
 #ifndef TAU_GAP
-#define TAU_GAP 60.0f            // nats; exp(-60) = 8.8e-27, 3*exp(-60) << 2^-32 (26 would do for the 2^-32 grid: DESIGN.md section 7)
+// nats.  The uniforms live on a 2^-32 grid and are never 0 on the paths that use the gap test (Philox: u = (w + 1/2) / 2^32;
+// MT19937: a zero word goes to the reference-order path), so u is in [2^-33, 1 - 2^-32].  If one base leads every other by more
+// than g after the error bounds, every CDF boundary of sample4 is within 3 e^-g of 0 or 1; 3 e^-g < 2^-33 needs g > 23.97.
+// 26 leaves a factor 7.6 (3 e^-26 = 1.5e-11 against 2^-33 = 1.2e-10).  (60 in round 1: same-box A/B at C3, work list 2935 -> 640
+// sites, per-site kernel 29 -> 21 us, chains bit-identical.)
+#define TAU_GAP 26.0f
 #endif
 #define TAU_SLACK 1.0e-9         // absolute slack on CDF brackets evaluated in FP64
 #define TAU_SLACK32 1.0e-4       // ... and in FP32 fast math (tau_bracket_decide)
@@ -407,7 +412,7 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
                 int jm = (x0 == top) ? 0 : (x1 == top) ? 1 : 2;
                 const bool finite = (fabsf(x0) + fabsf(x1) + fabsf(x2) + Bn) < 1.0e30f;   // false for inf / NaN
                 if (finite) {
-                    if (top + Bn < -TAU_GAP) { t = cur; n1++; }     // cur leads everything by > 60 nats
+                    if (top + Bn < -TAU_GAP) { t = cur; n1++; }     // cur leads everything by more than the gap
                     else {
                         const float rest = fmaxf(fmaxf(jm == 0 ? 0.f : x0, jm == 1 ? 0.f : x1), fmaxf(jm == 2 ? 0.f : x2, 0.f));
                         if ((top - Bn) - (rest + Bn) > TAU_GAP) { t = (cur + 1 + jm) & 3; n1++; }

@@ -26,7 +26,7 @@ from desman_b200 import _lib, engine
 from desman_b200.synth import CHAIN_SEED, synth_counts
 
 NAMES = ["maintain", "mu_binomial", "mu_class", "draw", "tau_group_mma", "tau_sample", "ll_table", "finalize", "copy_tau_if",
-         "tau_warp", "tgm_prologue", "mub_warp"]
+         "tau_warp", "tgm_prologue", "mub_warp", "tc_evt"]
 REC = np.dtype([("kid", "i4"), ("cta", "i4"), ("warp", "i4"), ("x", "i4"), ("t0", "u8"), ("t1", "u8"), ("a", "u8"), ("b", "u8"),
                 ("c", "u8"), ("d", "u8")])
 
@@ -107,3 +107,19 @@ if len(w):
         len(w), np.median(w["x"]), w["x"].max(), np.median(w["a"]) / 1e3, np.median(w["b"]) / 1e3, np.median(w["c"]) / 1e3,
         np.median(w["t1"].astype(np.int64) - w["t0"].astype(np.int64)) / 1e3, (w["t1"].astype(np.int64) - w["t0"].astype(np.int64)).max() / 1e3))
     print("  per item us (lane 0): ticket %.2f load %.2f draw %.2f" % (np.median(w["a"] / it) / 1e3, np.median(w["b"] / it) / 1e3, np.median(w["c"] / it) / 1e3))
+
+# tensor-memory screening pass: the pipeline of one CTA of the last launch (events of every role per item, us from CTA entry)
+ev = r[(r["kid"] == 12) & (r["t0"] >= tg["entry"]) & (r["t0"] <= tg["exit"] + 100000)]
+if len(ev):
+    cta = int(ev["cta"].min())
+    ev = ev[ev["cta"] == cta]
+    ent = int(g[g["cta"] == cta]["t0"][0]) if (g["cta"] == cta).any() else tg["entry"]
+    roles = ["tma issued", "mma committed", "table start (first warp)", "table start (last)", "table done (first)", "table done (last)",
+             "acc seen", "item done"]
+    print("tc pipeline of cta %d (us from its entry); columns: %s" % (cta, ", ".join(roles)))
+    for it in sorted(set(ev["x"].tolist())):
+        row = []
+        for ro in range(8):
+            m = ev[(ev["x"] == it) & (ev["warp"] == ro)]
+            row.append("%6.2f" % ((int(m["t0"][0]) - ent) / 1e3) if len(m) else "   -  ")
+        print("  item %2d: %s" % (it, "  ".join(row)))
