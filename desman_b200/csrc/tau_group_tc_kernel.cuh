@@ -19,10 +19,10 @@
 // to a multiple of 8 rows, so the rows of an item for one K block are ONE contiguous span of global memory: one
 // cp.async.bulk per (item, K block), no tensor map, no register staging.
 // Roles (warp-specialised, one persistent CTA per SM; everything between them goes through mbarriers):
-//   warps 0-3   epilogue: TMEM -> registers (warp w owns lanes 32w..32w+31), gap test, work list
-//   warp 4      ticket fetcher: work tickets and item records up to 8 items ahead, L2 prefetch of the item's rows
+//   warps 0-3   epilogue: TMEM -> registers (warp w owns lanes 32w..32w+31 = rows of the item), gap test, work list
+//   warp 4      item fetcher: item records up to 8 items ahead (8 lanes, 8 records in flight), L2 prefetch of the item's rows
 //   warp 5      MMA issuer (one elected lane)
-//   warp 6      copy issuer: bulk copies of the count rows (2-stage ring)
+//   warp 6      copy issuer: bulk copies of the count rows (ring of stages)
 //   warps 7-22  table builders: mixture P in FP64, the 12 lg2 per (strain, sample), fp16 split, stores in B-operand order
 // Results are those of the FFMA / mma.sync forms draw for draw (the error model below is charged instead of theirs).
 #pragma once
@@ -32,8 +32,14 @@
 #include "tau_kernel.cuh"
 #include "tau_group_kernel.cuh"
 
-#define TC_ROWS 128                 // sites per work item = M of the MMA
-#define TC_EPI_WARPS 4
+// Sites per work item = M of the MMA.  (Same-box A/B at C3: 64-row items -- 2424 instead of 1823, in a ring of 4 stages -- cost
+// 53 us against 45: the pass is bound by the table build, which is per item.)
+#ifndef TC_ROWS
+#define TC_ROWS 128
+#endif
+#define TC_M 128
+#define TC_EPI_WARPS (TC_ROWS / 32) // TMEM lanes = rows of an item
+#define TC_MAXRING 8
 #ifndef TC_BUILD_WARPS
 #define TC_BUILD_WARPS 16
 #endif
@@ -72,17 +78,20 @@ __device__ __forceinline__ void mbar_arrive_tx(uint32_t bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// (the suspend-time hint lets the hardware park the thread until the phase completes instead of returning after its short
+// default time-out: without it the 20-odd polling threads of a CTA issued 12 of the kernel's 20 million warp instructions --
+// ncu: issue slots 56 % busy, half of it try_wait + branch -- and the table builders competed with them for issue slots)
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra DONE_%=;\n\t"
         "bra WAIT_%=;\n\t"
         "DONE_%=:\n\t"
-        "}" ::"r"(bar), "r"(parity) : "memory");
+        "}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
 // A whole warp waits: ONE lane polls (31 fewer pollers competing with the working warps for issue slots), the others park
 // at the warp barrier
@@ -155,6 +164,7 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, 
 // ------------------------------------------------------------------------------------------------ sizes (host + device)
 struct TcLayout {
     int Sp, KC, N, acc_stride, tmem_cols;
+    int nst, ntb, nacc;                                // ring depths: count stages, table buffers, accumulators
     size_t off_gT, off_eta, off_eta32, off_gT32, off_wl, off_rec, off_bar, off_stage, off_table, stage_bytes, table_bytes, total;
 };
 __host__ __device__ static inline TcLayout tc_layout(int S, int G, int SK, int nkb, int NC)
@@ -164,7 +174,8 @@ __host__ __device__ static inline TcLayout tc_layout(int S, int G, int SK, int n
     L.KC = SK / 2;                                     // 16-byte chunks per K block (4 samples = 2 chunks = one MMA K step)
     L.N = 2 * NC;
     L.acc_stride = L.N <= 32 ? 32 : L.N <= 64 ? 64 : L.N <= 128 ? 128 : 256;
-    L.tmem_cols = 2 * L.acc_stride < 32 ? 32 : 2 * L.acc_stride;
+    L.nacc = L.acc_stride <= 64 ? 4 : 2;
+    L.tmem_cols = L.nacc * L.acc_stride < 32 ? 32 : L.nacc * L.acc_stride;
     size_t o = 0;
     L.off_gT = o; o += sizeof(double) * (size_t)G * L.Sp;
     L.off_eta = o; o += sizeof(double) * 16;
@@ -173,12 +184,21 @@ __host__ __device__ static inline TcLayout tc_layout(int S, int G, int SK, int n
     L.off_wl = o; o += sizeof(uint2) * TC_WL_CAP * TC_EPI_WARPS;
     L.off_rec = o; o += sizeof(TcRec) * TC_NREC;
     o = (o + 15) & ~(size_t)15;
-    L.off_bar = o; o += 8 * 40;
+    L.off_bar = o; o += 8 * (2 * TC_NREC + 6 * TC_MAXRING);
     o = (o + 1023) & ~(size_t)1023;
     L.stage_bytes = (size_t)(TC_ROWS / 8) * L.KC * 128;
     L.table_bytes = (size_t)(L.N / 8) * L.KC * 128;
-    L.off_stage = o; o += 2 * L.stage_bytes;
-    L.off_table = o; o += 2 * L.table_bytes;
+    // Ring depths from what shared memory is left (227 KB per CTA, 3 KB kept back): a stage is in flight from its copy to the
+    // completion of its MMA (HBM latency + transfer + hand-overs).  With TC_ROWS < 128 the MMA still reads M = 128 rows: the
+    // upper part comes from whatever follows (the next stage, or `pad`: finite fp16 data either way; its sums are never read).
+    const size_t budget = (size_t)224 * 1024, pad = (TC_ROWS < TC_M) ? (size_t)(TC_M - TC_ROWS) / 8 * L.KC * 128 : 0;
+    L.nst = 2; L.ntb = 2;
+    auto fits = [&](int nst, int ntb) { return o + (size_t)nst * L.stage_bytes + pad + (size_t)ntb * L.table_bytes <= budget; };
+    while (L.nst < 4 && fits(L.nst + 1, L.ntb)) L.nst++;
+    if (fits(L.nst, 3)) L.ntb = 3;
+    while (L.nst < TC_MAXRING && fits(L.nst + 1, L.ntb)) L.nst++;
+    L.off_stage = o; o += (size_t)L.nst * L.stage_bytes + pad;
+    L.off_table = o; o += (size_t)L.ntb * L.table_bytes;
     L.total = o;
     return L;
 }
@@ -217,9 +237,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
     float *gT32 = reinterpret_cast<float *>(smem + L.off_gT32);         // [G][Sp]
     TcRec *rec = reinterpret_cast<TcRec *>(smem + L.off_rec);           // [TC_NREC]
     const uint32_t bar0 = smem_u32(smem + L.off_bar);
-    // barriers: rec_full[NREC] rec_empty[NREC] cnt_full[2] cnt_empty[2] tab_full[2] tab_empty[2] acc_full[2] acc_empty[2]
-    const uint32_t rec_full = bar0, rec_empty = bar0 + 8 * TC_NREC, cnt_full = bar0 + 8 * (2 * TC_NREC), cnt_empty = cnt_full + 8 * 2,
-                   tab_full = cnt_full + 8 * 4, tab_empty = cnt_full + 8 * 6, acc_full = cnt_full + 8 * 8, acc_empty = cnt_full + 8 * 10;
+    // barriers: rec_full[NREC] rec_empty[NREC] cnt_full/empty[nst] tab_full/empty[ntb] acc_full/empty[nacc] (TC_MAXRING slots each)
+    const uint32_t rec_full = bar0, rec_empty = bar0 + 8 * TC_NREC, cnt_full = bar0 + 8 * (2 * TC_NREC), cnt_empty = cnt_full + 8 * TC_MAXRING,
+                   tab_full = cnt_full + 8 * 2 * TC_MAXRING, tab_empty = cnt_full + 8 * 3 * TC_MAXRING, acc_full = cnt_full + 8 * 4 * TC_MAXRING,
+                   acc_empty = cnt_full + 8 * 5 * TC_MAXRING;
+    const uint32_t nst = (uint32_t)L.nst, ntb = (uint32_t)L.ntb, nacc = (uint32_t)L.nacc;
     const uint32_t stage0 = smem_u32(smem + L.off_stage), table0 = smem_u32(smem + L.off_table);
     __shared__ uint32_t tmem_base_s;
 #ifdef KPROF
@@ -233,7 +255,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
     // ---- prologue that touches nothing of the preceding grid: barriers, zeroed operand buffers
     if (tid == 0) {
         for (int i = 0; i < TC_NREC; i++) { mbar_init(rec_full + 8 * i, 1); mbar_init(rec_empty + 8 * i, TC_EPI_WARPS); }
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < TC_MAXRING; i++) {
             mbar_init(cnt_full + 8 * i, 1); mbar_init(cnt_empty + 8 * i, 1);
             mbar_init(tab_full + 8 * i, TC_BUILD_WARPS); mbar_init(tab_empty + 8 * i, 1);
             mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, TC_EPI_WARPS);
@@ -243,7 +265,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
     }
     {   // stages: rows beyond an item's own stay zero / finite; tables: padded columns and samples stay zero for good
         uint4 *z = reinterpret_cast<uint4 *>(smem + L.off_stage);
-        const size_t n16 = (2 * L.stage_bytes + 2 * L.table_bytes) / 16;
+        const size_t n16 = (L.off_table + (size_t)L.ntb * L.table_bytes - L.off_stage) / 16;
         for (size_t i = tid; i < n16; i += TC_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
     }
     pdl_enter();
@@ -302,31 +324,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
     const int ncol = 3 * G;
 
     if (warp == TC_EPI_WARPS) {
-        // =============================================================== ticket fetcher: item records, up to TC_NREC items ahead
-        // (a ticket is a global atomic and an item record two dependent loads: ~2 us that must not sit between two copies);
-        // the rows of the item start moving into L2 at once
-        if (lane == 0) {
-            const size_t kb_stride = (size_t)p.img_rg * KC * 128;
-            TCP(long long w_rec = 0; long long n_it = 0; long long rows = 0; const long long t_all = clock64(););
-            for (uint32_t i = 0;; i++) {
-                const uint32_t r = i % TC_NREC;
-                TCW(w_rec, mbar_wait(rec_empty + 8 * r, ((i / TC_NREC) & 1u) ^ 1u));
-                const int it = (i == 0) ? (int)blockIdx.x : (int)gridDim.x + atomicAdd(p.grp.gctl + GC_CURSOR, 1);
+        // =============================================================== item fetcher: item records, up to TC_NREC items ahead
+        // Items are dealt round robin (item k of this CTA = blockIdx + k * gridDim; they are numbered longest first, so every
+        // CTA gets one item of every size band).  A record is two loads of ~1 us: eight lanes fetch eight records at a time
+        // (a single thread fetching one record after another -- or worse, drawing a ticket with a global atomic first -- was the
+        // period of the whole pipeline: 2.2 us per item), start the item's rows on their way into L2, and lane 0 publishes them
+        // in order as ring slots come free.
+        const size_t kb_stride = (size_t)p.img_rg * KC * 128;
+        TCP(long long w_rec = 0; long long n_it = 0; long long rows = 0; const long long t_all = clock64(););
+        bool done = false;
+        for (uint32_t base = 0; !done; base += 8) {
+            int4 a = make_int4(0, 0, 0, 0), b = make_int4(0, 0, 0, 0);
+            const long long it = (long long)blockIdx.x + (long long)(base + (uint32_t)lane) * (long long)gridDim.x;
+            if (lane < 8 && it < (long long)nitems) {
+                a = p.grp.items[2 * it]; b = p.grp.items[2 * it + 1];
+                const uint32_t bytes = (((uint32_t)a.z + 7u) & ~7u) * (uint32_t)KC * 16u;
+                for (int kb = 0; kb < nkb; kb++) l2_prefetch_row(p.img + (size_t)kb * kb_stride + (size_t)(b.z >> 3) * KC * 128, bytes);
+            }
+            for (int l = 0; l < 8 && !done; l++) {
                 TcRec rc;
-                rc.slot = 0; rc.count = 0; rc.img0 = 0; rc.code_lo = 0; rc.code_hi = 0; rc.pad[0] = rc.pad[1] = rc.pad[2] = 0;
-                if (it < nitems) {
-                    const int4 a = p.grp.items[2 * it], b = p.grp.items[2 * it + 1];
-                    rc.slot = a.x; rc.count = a.z; rc.img0 = b.z; rc.code_lo = (unsigned int)b.x; rc.code_hi = (unsigned int)b.y;
-                    const uint32_t bytes = (((uint32_t)rc.count + 7u) & ~7u) * (uint32_t)KC * 16u;
-                    for (int kb = 0; kb < nkb; kb++) l2_prefetch_row(p.img + (size_t)kb * kb_stride + (size_t)(rc.img0 >> 3) * KC * 128, bytes);
+                rc.slot = __shfl_sync(DESMAN_FULL_MASK, a.x, l); rc.count = __shfl_sync(DESMAN_FULL_MASK, a.z, l);
+                rc.img0 = __shfl_sync(DESMAN_FULL_MASK, b.z, l);
+                rc.code_lo = (unsigned int)__shfl_sync(DESMAN_FULL_MASK, b.x, l); rc.code_hi = (unsigned int)__shfl_sync(DESMAN_FULL_MASK, b.y, l);
+                rc.pad[0] = rc.pad[1] = rc.pad[2] = 0;
+                const uint32_t i = base + (uint32_t)l, r = i % TC_NREC;
+                if (lane == 0) {
+                    TCW(w_rec, mbar_wait(rec_empty + 8 * r, ((i / TC_NREC) & 1u) ^ 1u));
+                    rec[r] = rc;
+                    mbar_arrive(rec_full + 8 * r);                     // (release: the record is visible to the waiters)
                 }
-                rec[r] = rc;
-                mbar_arrive(rec_full + 8 * r);                         // (release: the record is visible to the waiters)
-                if (rc.count == 0) break;
+                __syncwarp();
+                if (rc.count == 0) done = true;                        // the sentinel: no more items
                 TCP(n_it++; rows += rc.count;);
             }
-            TCP(if (blockIdx.x % 37 == 0) printf("cta %3d tickets: items %lld rows %lld total %lld wait rec_empty %lld\n", (int)blockIdx.x, n_it, rows, clock64() - t_all, w_rec););
         }
+        TCP(if (lane == 0 && blockIdx.x % 37 == 0) printf("cta %3d items: %lld rows %lld total %lld wait rec_empty %lld\n", (int)blockIdx.x, n_it, rows, clock64() - t_all, w_rec););
     } else if (warp == TC_EPI_WARPS + 2) {
         // =============================================================== copy issuer: count rows of (item, K block) into the stage ring
         if (lane == 0) {
@@ -340,8 +372,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
                 if (count == 0) break;
                 const uint32_t bytes = (((uint32_t)count + 7u) & ~7u) * (uint32_t)KC * 16u;
                 for (int kb = 0; kb < nkb; kb++, u++) {
-                    const uint32_t cs = u & 1u;
-                    TCW(w_cnt, mbar_wait(cnt_empty + 8 * cs, ((u >> 1) & 1u) ^ 1u));
+                    const uint32_t cs = u % nst;
+                    TCW(w_cnt, mbar_wait(cnt_empty + 8 * cs, ((u / nst) & 1u) ^ 1u));
                     mbar_arrive_tx(cnt_full + 8 * cs, bytes);
                     tma_bulk_g2s(stage0 + cs * (uint32_t)L.stage_bytes,
                                  p.img + (size_t)kb * kb_stride + (size_t)(img0 >> 3) * KC * 128, bytes, cnt_full + 8 * cs);
@@ -353,23 +385,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
     } else if (warp == TC_EPI_WARPS + 1) {
         // =============================================================== MMA issuer
         if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(L.N >> 3) << 17) | ((uint32_t)(TC_ROWS >> 4) << 24);   // F16 x F16 -> F32, K-major A and B
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(L.N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);   // F16 x F16 -> F32, K-major A and B
             uint32_t u = 0;
             TCP(long long w_rec = 0; long long w_acc = 0; long long w_tab = 0; long long w_cnt = 0; const long long t_all = clock64(););
             for (uint32_t i = 0;; i++) {
                 const uint32_t r = i % TC_NREC;
                 TCW(w_rec, mbar_wait(rec_full + 8 * r, (i / TC_NREC) & 1u));
                 if (rec[r].count == 0) break;
-                const uint32_t as = i & 1u;
-                TCW(w_acc, mbar_wait(acc_empty + 8 * as, ((i >> 1) & 1u) ^ 1u));
+                const uint32_t as = i % nacc;
+                TCW(w_acc, mbar_wait(acc_empty + 8 * as, ((i / nacc) & 1u) ^ 1u));
                 const uint32_t d = tmem_base + as * (uint32_t)L.acc_stride;
                 for (int kb = 0; kb < nkb; kb++, u++) {
-                    const uint32_t cs = u & 1u;
-                    TCW(w_tab, mbar_wait(tab_full + 8 * cs, (u >> 1) & 1u));
-                    TCW(w_cnt, mbar_wait(cnt_full + 8 * cs, (u >> 1) & 1u));
+                    const uint32_t cs = u % nst, ts = u % ntb;
+                    TCW(w_tab, mbar_wait(tab_full + 8 * ts, (u / ntb) & 1u));
+                    TCW(w_cnt, mbar_wait(cnt_full + 8 * cs, (u / nst) & 1u));
                     tc_fence_after();
                     const uint64_t a0 = tc_desc(stage0 + cs * (uint32_t)L.stage_bytes, 128u, sbo);
-                    const uint64_t b0 = tc_desc(table0 + cs * (uint32_t)L.table_bytes, 128u, sbo);
+                    const uint64_t b0 = tc_desc(table0 + ts * (uint32_t)L.table_bytes, 128u, sbo);
 #ifdef TC_ABL_MMA
                     for (int k = 0; k < 1; k++)
 #else
@@ -377,7 +409,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
 #endif
                         tc_mma_f16(d, a0 + (uint64_t)(16 * k), b0 + (uint64_t)(16 * k), idesc, (kb | k) ? 1u : 0u);
                     tc_commit(cnt_empty + 8 * cs);
-                    tc_commit(tab_empty + 8 * cs);
+                    tc_commit(tab_empty + 8 * ts);
                 }
                 tc_commit(acc_full + 8 * as);
                 TCE(1, i);
@@ -388,16 +420,111 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
         // =============================================================== table builders (TC_BUILD_WARPS warps, no cross-warp dependency)
         // A warp task = 8 strains x 4 samples; a lane = one (strain, sample): its base q[b] = P[b] - eta[cur][b] gamma (FP64, one
         // rounding) serves the 3 candidates x 4 bases = 12 table entries it writes.  The mixture P[s][b] = sum_h eta[tau_h][b]
-        // gamma[s][h] (FP64, ascending h) of the task's 4 samples is formed by lanes 0-15 (one (sample, base) each; lanes 16-31
-        // mirror them) and handed round by shuffles.  Stores: for a fixed candidate the 8 strains of a task hit 8 different rows
-        // mod 8 (3 is coprime to 8), so a half warp writes 16 distinct 8-byte pieces of 128-byte core matrices: conflict-free.
+        // gamma[s][h] (FP64) of the task's 4 samples is formed by lanes 0-15 (one (sample, base) each; lanes 16-31 mirror them)
+        // and handed round by shuffles.  Stores: for a fixed candidate the 8 strains of a task hit 8 different rows mod 8 (3 is
+        // coprime to 8), so a half warp writes 16 distinct 8-byte pieces of 128-byte core matrices: conflict-free.
+        // The tasks of a warp are the same for every item (task = warp + k * TC_BUILD_WARPS): everything but the pattern --
+        // sample and strain of the lane, the addresses of its gamma entries and of its 6 stores -- is worked out once, before the
+        // item loop (the first version spent 300 of its 390 instructions per task on that arithmetic: ncu source page).
         const int bw = warp - (TC_EPI_WARPS + 3);
         const int gl = (lane >> 1) & 7, shf = lane & 1, sp = lane >> 4;
         const int ps = (lane >> 2) & 3, pbb = lane & 3;                   // the (sample, base) pair this lane forms P for
         const int mys = 2 * sp + shf;                                      // this lane's sample within the task
         const int ngo = (G + 7) >> 3, noct = NC >> 3, nquad = SK >> 2, ntask = ngo * nquad;
+        constexpr int TPRE = 2;                                            // tasks per warp and K block kept in registers
+        struct TaskC { const double *gTp; const double *gg; const float *gf; uint32_t off[3]; int g2; bool p_ok, ok; };
+        auto task_consts = [&](int task, int kb) {
+            TaskC t;
+            const int go = task % ngo, sq = task / ngo;
+            const int s_p = kb * SK + 4 * sq + ps, g = 8 * go + gl, sl = 4 * sq + mys, sm = kb * SK + sl;
+            t.p_ok = task < ntask && s_p < S;
+            t.ok = task < ntask && g < G && sm < S;
+            t.gTp = gT + (t.p_ok ? s_p : 0);
+            t.gg = gT + (t.ok ? g * Sp + sm : 0);
+            t.gf = gT32 + (t.ok ? g * Sp + sm : 0);
+            t.g2 = 2 * (t.ok ? g : 0);
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const int n = 3 * g + j;
+                t.off[j] = (uint32_t)(n >> 3) * sbo + (uint32_t)(sl >> 1) * 128u + (uint32_t)(n & 7) * 16u + (uint32_t)shf * 8u;
+            }
+            return t;
+        };
+        const bool pre_ok = nkb == 1;                                     // (with several K blocks the constants are re-derived per block)
+        TaskC pre[TPRE];
+#pragma unroll
+        for (int k = 0; k < TPRE; k++) pre[k] = task_consts(bw + k * TC_BUILD_WARPS, 0);
+        const uint32_t lo_off = (uint32_t)noct * sbo;                     // rows [NC, 2 NC): the remainders
+        // one task: the lane's 12 entries of table `tab` for pattern `code`
+        auto do_task = [&](const TaskC &t, uint64_t code, unsigned char *tab) {
+            double Pv = 1.0;                                                // padding samples: finite logs
+#ifdef TC_ABL_PLOOP
+            if (t.p_ok) Pv = 0.3 + 1e-3 * (double)(code & 15ull);
+            if (false) {
+#else
+            if (t.p_ok) {
+#endif
+                double Pa = 0.0, Pb = 0.0;                                  // two chains: even and odd strains
+                const double *e = eta_s + pbb;
+                const double *gp = t.gTp;
+                uint64_t cc = code;
+                int h = 0;
+                for (; h + 1 < G; h += 2, cc >>= 4, gp += 2 * Sp) {
+                    Pa = fma(e[4 * (int)(cc & 3ull)], gp[0], Pa);
+                    Pb = fma(e[4 * (int)((cc >> 2) & 3ull)], gp[Sp], Pb);
+                }
+                if (h < G) Pa = fma(e[4 * (int)(cc & 3ull)], gp[0], Pa);
+                Pv = Pa + Pb;
+            }
+            const float lv_ = lg2_fast((float)Pv);
+#ifdef TC_ABL_SHFL
+            const double P0 = Pv, P1 = Pv + 1e-9, P2 = Pv + 2e-9, P3 = Pv + 3e-9;
+            const float l0 = lv_, l1 = lv_ + 1e-3f, l2 = lv_ + 2e-3f, l3 = lv_ + 3e-3f;
+#else
+            const double P0 = __shfl_sync(DESMAN_FULL_MASK, Pv, 4 * mys + 0), P1 = __shfl_sync(DESMAN_FULL_MASK, Pv, 4 * mys + 1),
+                         P2 = __shfl_sync(DESMAN_FULL_MASK, Pv, 4 * mys + 2), P3 = __shfl_sync(DESMAN_FULL_MASK, Pv, 4 * mys + 3);
+            const float l0 = __shfl_sync(DESMAN_FULL_MASK, lv_, 4 * mys + 0), l1 = __shfl_sync(DESMAN_FULL_MASK, lv_, 4 * mys + 1),
+                        l2 = __shfl_sync(DESMAN_FULL_MASK, lv_, 4 * mys + 2), l3 = __shfl_sync(DESMAN_FULL_MASK, lv_, 4 * mys + 3);
+#endif
+            if (t.ok) {
+                const int cur = (int)((code >> t.g2) & 3ull);
+                const double2 *ecp = reinterpret_cast<const double2 *>(eta_s + 4 * cur);
+                const double2 ec01 = ecp[0], ec23 = ecp[1];
+                const double gg = *t.gg;
+                const float gf = *t.gf;
+#ifdef TC_ABL_F64
+                const float q0 = fmaxf(fmaf(-(float)ec01.x, gf, l0), 0.f), q1 = fmaxf(fmaf(-(float)ec01.y, gf, l1), 0.f),
+                            q2 = fmaxf(fmaf(-(float)ec23.x, gf, l2), 0.f), q3 = fmaxf(fmaf(-(float)ec23.y, gf, l3), 0.f);
+                (void)gg;
+#else
+                const float q0 = fmaxf((float)fma(-ec01.x, gg, P0), 0.f), q1 = fmaxf((float)fma(-ec01.y, gg, P1), 0.f),
+                            q2 = fmaxf((float)fma(-ec23.x, gg, P2), 0.f), q3 = fmaxf((float)fma(-ec23.y, gg, P3), 0.f);
+#endif
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    const float4 ea = eta32[(cur + 1 + j) & 3];
+#ifdef TC_ABL_LG2
+                    const float w0 = fmaf(ea.x, gf, q0) - l0, w1 = fmaf(ea.y, gf, q1) - l1, w2 = fmaf(ea.z, gf, q2) - l2, w3 = fmaf(ea.w, gf, q3) - l3;
+#else
+                    const float w0 = lg2_fast(fmaf(ea.x, gf, q0)) - l0, w1 = lg2_fast(fmaf(ea.y, gf, q1)) - l1,
+                                w2 = lg2_fast(fmaf(ea.z, gf, q2)) - l2, w3 = lg2_fast(fmaf(ea.w, gf, q3)) - l3;
+#endif
+                    // h = the entry truncated to fp16's 11 significant bits (a mask: exact in fp16 unless |w| < 2^-14, where the
+                    // conversion rounds it on the 2^-24 grid), l = fp16(w - h_truncated)
+                    const float t0 = __uint_as_float(__float_as_uint(w0) & 0xffffe000u), t1 = __uint_as_float(__float_as_uint(w1) & 0xffffe000u),
+                                t2 = __uint_as_float(__float_as_uint(w2) & 0xffffe000u), t3 = __uint_as_float(__float_as_uint(w3) & 0xffffe000u);
+                    const __half2 h01 = __floats2half2_rn(t0, t1), h23 = __floats2half2_rn(t2, t3);
+                    const __half2 l01 = __floats2half2_rn(w0 - t0, w1 - t1), l23 = __floats2half2_rn(w2 - t2, w3 - t3);
+                    uint2 hv, lv;
+                    hv.x = *reinterpret_cast<const uint32_t *>(&h01); hv.y = *reinterpret_cast<const uint32_t *>(&h23);
+                    lv.x = *reinterpret_cast<const uint32_t *>(&l01); lv.y = *reinterpret_cast<const uint32_t *>(&l23);
+                    *reinterpret_cast<uint2 *>(tab + t.off[j]) = hv;                 // rows [0, NC): h
+                    *reinterpret_cast<uint2 *>(tab + t.off[j] + lo_off) = lv;        // rows [NC, 2 NC): l
+                }
+            }
+        };
         uint32_t u = 0;
-        TCP(long long w_rec = 0; long long w_tab = 0; long long t_work = 0; const long long t_all = clock64(););
+        TCP(long long w_rec = 0; long long w_tab = 0; long long t_work = 0; long long t_task = 0; long long t_fence = 0; const long long t_all = clock64(););
         for (uint32_t i = 0;; i++) {
             const uint32_t r = i % TC_NREC;
             TCW(w_rec, mbar_wait_warp(rec_full + 8 * r, (i / TC_NREC) & 1u, lane));
@@ -405,77 +532,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
             if (rc.count == 0) break;
             const uint64_t code = ((uint64_t)rc.code_hi << 32) | rc.code_lo;
             for (int kb = 0; kb < nkb; kb++, u++) {
-                const uint32_t ts = u & 1u;
-                TCW(w_tab, mbar_wait_warp(tab_empty + 8 * ts, ((u >> 1) & 1u) ^ 1u, lane));
+                const uint32_t ts = u % ntb;
+                TCW(w_tab, mbar_wait_warp(tab_empty + 8 * ts, ((u / ntb) & 1u) ^ 1u, lane));
                 TCP(const long long tw0 = clock64(););
                 if (lane == 0) { TCE_MIN(2, i); TCE(3, i); }
                 unsigned char *tab = smem + L.off_table + ts * L.table_bytes;
-#ifdef TC_ABL_TABLE
-                for (int task = ntask; task < ntask; task += TC_BUILD_WARPS) {
-#else
-                for (int task = bw; task < ntask; task += TC_BUILD_WARPS) {
-#endif
-                    const int go = task % ngo, sq = task / ngo;
-                    // ---- mixture of the task's 4 samples
-                    const int s_p = kb * SK + 4 * sq + ps;
-                    double Pv = 1.0;                                        // padding samples: finite logs
-                    if (s_p < S) {
-                        double Pa = 0.0, Pb = 0.0;                          // two chains: even and odd strains
-                        int h = 0;
-                        for (; h + 1 < G; h += 2) {
-                            Pa = fma(eta_s[4 * code_get(code, h) + pbb], gT[h * Sp + s_p], Pa);
-                            Pb = fma(eta_s[4 * code_get(code, h + 1) + pbb], gT[(h + 1) * Sp + s_p], Pb);
-                        }
-                        if (h < G) Pa = fma(eta_s[4 * code_get(code, h) + pbb], gT[h * Sp + s_p], Pa);
-                        Pv = Pa + Pb;
-                    }
-                    const float lv_ = lg2_fast((float)Pv);
-                    const double P0 = __shfl_sync(DESMAN_FULL_MASK, Pv, 4 * mys + 0), P1 = __shfl_sync(DESMAN_FULL_MASK, Pv, 4 * mys + 1),
-                                 P2 = __shfl_sync(DESMAN_FULL_MASK, Pv, 4 * mys + 2), P3 = __shfl_sync(DESMAN_FULL_MASK, Pv, 4 * mys + 3);
-                    const float l0 = __shfl_sync(DESMAN_FULL_MASK, lv_, 4 * mys + 0), l1 = __shfl_sync(DESMAN_FULL_MASK, lv_, 4 * mys + 1),
-                                l2 = __shfl_sync(DESMAN_FULL_MASK, lv_, 4 * mys + 2), l3 = __shfl_sync(DESMAN_FULL_MASK, lv_, 4 * mys + 3);
-                    const int g = 8 * go + gl, sl = 4 * sq + mys, s = kb * SK + sl;
-                    if (g < G && s < S) {
-                        const int cur = code_get(code, g);
-                        const double2 *ecp = reinterpret_cast<const double2 *>(eta_s + 4 * cur);
-                        const double2 ec01 = ecp[0], ec23 = ecp[1];
-                        const double gg = gT[g * Sp + s];
-                        const float gf = gT32[g * Sp + s];
-                        const float q0 = fmaxf((float)fma(-ec01.x, gg, P0), 0.f), q1 = fmaxf((float)fma(-ec01.y, gg, P1), 0.f),
-                                    q2 = fmaxf((float)fma(-ec23.x, gg, P2), 0.f), q3 = fmaxf((float)fma(-ec23.y, gg, P3), 0.f);
-                        const size_t off_s = (size_t)(sl >> 1) * 128 + (size_t)shf * 8;
+#ifndef TC_ABL_TABLE
+                if (fast_ok) {                                           // (otherwise the tables stay zero and every site is listed)
+                    if (pre_ok) {
 #pragma unroll
-                        for (int j = 0; j < 3; j++) {
-                            float w0 = 0.f, w1 = 0.f, w2 = 0.f, w3 = 0.f;
-                            if (fast_ok) {
-                                const float4 ea = eta32[(cur + 1 + j) & 3];
-                                w0 = lg2_fast(fmaf(ea.x, gf, q0)) - l0; w1 = lg2_fast(fmaf(ea.y, gf, q1)) - l1;
-                                w2 = lg2_fast(fmaf(ea.z, gf, q2)) - l2; w3 = lg2_fast(fmaf(ea.w, gf, q3)) - l3;
-                            }
-                            // h = the entry truncated to fp16's 11 significant bits (a mask: exact in fp16 unless |w| < 2^-14, where
-                            // the conversion rounds it on the 2^-24 grid), l = fp16(w - h_truncated)
-                            const float t0 = __uint_as_float(__float_as_uint(w0) & 0xffffe000u), t1 = __uint_as_float(__float_as_uint(w1) & 0xffffe000u),
-                                        t2 = __uint_as_float(__float_as_uint(w2) & 0xffffe000u), t3 = __uint_as_float(__float_as_uint(w3) & 0xffffe000u);
-                            const __half2 h01 = __floats2half2_rn(t0, t1), h23 = __floats2half2_rn(t2, t3);
-                            const __half2 l01 = __floats2half2_rn(w0 - t0, w1 - t1), l23 = __floats2half2_rn(w2 - t2, w3 - t3);
-                            uint2 hv, lv;
-                            hv.x = *reinterpret_cast<const uint32_t *>(&h01); hv.y = *reinterpret_cast<const uint32_t *>(&h23);
-                            lv.x = *reinterpret_cast<const uint32_t *>(&l01); lv.y = *reinterpret_cast<const uint32_t *>(&l23);
-                            const int n = 3 * g + j;
-                            const size_t off = off_s + (size_t)(n & 7) * 16;
-                            *reinterpret_cast<uint2 *>(tab + (size_t)(n >> 3) * sbo + off) = hv;              // rows [0, NC): h
-                            *reinterpret_cast<uint2 *>(tab + (size_t)(noct + (n >> 3)) * sbo + off) = lv;     // rows [NC, 2 NC): l
-                        }
+                        for (int k = 0; k < TPRE; k++)
+                            if (bw + k * TC_BUILD_WARPS < ntask) do_task(pre[k], code, tab);
+                        for (int task = bw + TPRE * TC_BUILD_WARPS; task < ntask; task += TC_BUILD_WARPS) do_task(task_consts(task, 0), code, tab);
+                    } else {
+                        for (int task = bw; task < ntask; task += TC_BUILD_WARPS) do_task(task_consts(task, kb), code, tab);
                     }
                 }
+#endif
+                TCP(const long long tw1 = clock64(););
                 fence_proxy_async();                                     // generic-proxy stores -> async-proxy reads of the MMA
+                TCP(const long long tw2 = clock64(););
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tab_full + 8 * ts);
                 if (lane == 0) { TCE_MIN(4, i); TCE(5, i); }
-                TCP(t_work += clock64() - tw0;);
+                TCP(t_work += clock64() - tw0; t_task += tw1 - tw0; t_fence += tw2 - tw1;);
             }
         }
-        TCP(if (lane == 0 && bw == 0 && blockIdx.x % 37 == 0) printf("cta %3d tables: total %lld wait rec_full %lld tab_empty %lld work %lld\n", (int)blockIdx.x, clock64() - t_all, w_rec, w_tab, t_work););
+        TCP(if (lane == 0 && bw == 0 && blockIdx.x % 37 == 0) printf("cta %3d tables: total %lld wait rec_full %lld tab_empty %lld work %lld (task %lld fence %lld)\n", (int)blockIdx.x, clock64() - t_all, w_rec, w_tab, t_work, t_task, t_fence););
     } else {
         // =============================================================== epilogue (warps 0-3: TMEM lanes 32 w .. 32 w + 31)
         unsigned int n_decided = 0;
@@ -500,8 +583,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
                 const uint32_t *w = p.words + (size_t)vown * G;
                 for (int g = 0; g < G; g++) zero_word |= (w[g] == 0u);      // u == 0 (c_sample_tau.c:174): reference-order path
             }
-            const uint32_t as = i & 1u;
-            TCW(w_acc, mbar_wait_warp(acc_full + 8 * as, (i >> 1) & 1u, lane));
+            const uint32_t as = i % nacc;
+            TCW(w_acc, mbar_wait_warp(acc_full + 8 * as, (i / nacc) & 1u, lane));
             if (warp == 0 && lane == 0) TCE(6, i);
             tc_fence_after();
             const uint32_t t0 = tmem_base + as * (uint32_t)L.acc_stride + ((uint32_t)(warp * 32) << 16);
