@@ -24,7 +24,7 @@ __device__ __forceinline__ void pdl_enter()
 
 // -DKPROF build (diagnosis only, tools/kprof.py): %globaltimer stamps of every CTA's entry / exit (and of the phases of a few
 // kernels) recorded in a device buffer that desman_kprof_dump() copies out.  The product build compiles none of it.
-enum { KP_MAINT = 0, KP_MUB, KP_MUC, KP_DRAW, KP_TGM, KP_TAU, KP_LL, KP_FIN, KP_COPY, KP_TAU_WARP, KP_TGM_PRO, KP_MUB_WARP, KP_TC_EVT };
+enum { KP_MAINT = 0, KP_MUB, KP_MUC, KP_DRAW, KP_TGM, KP_TAU, KP_LL, KP_FIN, KP_COPY, KP_TAU_WARP, KP_TGM_PRO, KP_MUB_WARP, KP_TC_EVT, KP_TAUO };
 #ifdef KPROF
 struct KRec { int kid, cta, warp, x; unsigned long long t0, t1, a, b, c, d; };
 #define KREC_CAP (1 << 18)

@@ -20,6 +20,7 @@
 #include "mu_kernel.cuh"
 #include "nmft_kernel.cuh"
 #include "tau_kernel.cuh"
+#include "tau_open_kernel.cuh"
 #include "tau_group_kernel.cuh"
 #include "tau_group_tc_kernel.cuh"
 #include "state_kernel.cuh"
@@ -153,6 +154,9 @@ struct desman_ctx {
     // pattern groups for the screening pass of the tau update (tau_group_kernel.cuh)
     int tau_group = 2;                       // 0: off, 1: on, 2: on iff the ~12*2^G biallelic patterns are <= V/2
     int tau_group_mma = 1;                   // 1: tensor-core form of the screening pass where it applies; 0: FFMA form
+    int tau_open = 1;                        // 1: the work list of the screening pass is walked by tau_open_kernel (one CTA per site)
+    int tauo_grid = 0;
+    size_t tauo_smem = 0;
     int tau_group_tc = 1;                    // 1: tcgen05 / TMEM / TMA form (tau_group_tc_kernel.cuh) where it applies; 0: mma.sync / FFMA forms
     unsigned char *img = nullptr;            // fp16x4 count image in UMMA operand order
     int *img_site = nullptr, *site_row = nullptr;
@@ -1019,7 +1023,7 @@ static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, boo
     p.tier_counts = c->tiers;
     p.work = nullptr; p.singles = nullptr; p.gctl = nullptr; p.site_slot = nullptr;
     p.img_site = nullptr; p.site_row = nullptr; p.need_img = 0;
-    p.g_begin = g_begin; p.logp_out = logp_out;
+    p.g_begin = g_begin; p.logp_out = logp_out; p.skip_listed = 0;
     int gb = 8, gwarps = 1;
     if (p.agg.N && group_config(c, &gb, &gwarps)) {
         TauGroupParams q;
@@ -1046,8 +1050,24 @@ static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, boo
     const size_t smem = tau_smem_bytes(c->S, c->G);
     if (smem > 227 * 1024) return fail(DESMAN_EINVAL, "S*G too large for the shared-memory tile (%zu bytes)", smem);
     CU(cudaFuncSetAttribute(tau_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const size_t smem_o = tauo_smem_bytes(c->S, c->G);
+    const bool open_kernel = p.work != nullptr && c->tau_open && smem_o <= 200 * 1024;
     {
-        KSpan k(c, DESMAN_K_TAU);
+        KSpan k(c, DESMAN_K_TAU, open_kernel ? 2 : 1);
+        if (open_kernel) {
+            // the work list of the screening pass: one CTA per listed site, its open steps in parallel (tau_open_kernel.cuh);
+            // tau_sample_kernel then runs only if the list is not valid (burn-in: no groups, or the chain is not calm)
+            if (!c->tauo_grid) {
+                CU(cudaFuncSetAttribute(tau_open_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_o));
+                int occ = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tau_open_kernel, TAUO_WARPS * 32, smem_o) != cudaSuccess || occ < 1) occ = 1;
+                c->tauo_grid = c->sm_count * occ;
+                c->tauo_smem = smem_o;
+            }
+            if (c->tauo_smem != smem_o) { CU(cudaFuncSetAttribute(tau_open_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_o)); c->tauo_smem = smem_o; }
+            CU(launch_k(c, tau_open_kernel, c->tauo_grid, TAUO_WARPS * 32, smem_o, p));
+            p.skip_listed = 1;
+        }
         CU(launch_k(c, tau_sample_kernel, grid, TAU_WARPS * 32, smem, p));
     }
     CU(cudaGetLastError());
@@ -1821,6 +1841,7 @@ extern "C" int desman_set_option(desman_ctx *c, const char *name, int64_t value)
         c->rng_mode = (int)value; return DESMAN_OK;
     }
     if (!strcmp(name, "tau_group_mma")) { c->tau_group_mma = value ? 1 : 0; return DESMAN_OK; }
+    if (!strcmp(name, "tau_open")) { c->tau_open = value ? 1 : 0; return DESMAN_OK; }
     if (!strcmp(name, "tau_group_tc")) { c->tau_group_tc = value ? 1 : 0; c->agg_valid = false; return DESMAN_OK; }
     if (!strcmp(name, "tau_group")) { c->tau_group = (value == 0 || value == 1) ? (int)value : 2; c->agg_valid = false; return DESMAN_OK; }
     return fail(DESMAN_EINVAL, "unknown option '%s'", name);

@@ -57,6 +57,7 @@ struct TauParams {
     // normalised log-probabilities (normaliseLogProb, :186-194) of strain g_begin's four bases before its draw
     int g_begin;
     double *logp_out;
+    int skip_listed;         // 1: when the work list is valid this launch does nothing (tau_open_kernel walks the list)
     unsigned long long *tier_counts;  // [3] += draws decided by tier 1 / 2 / 3 (or nullptr)
 };
 
@@ -264,6 +265,9 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
 #else
     const bool early = false;
 #endif
+    // the work list is walked by tau_open_kernel: nothing to do here when it is valid (the control words that say so were
+    // written at least two grids ago; the wait still has to happen: the next grid of the chain orders itself after THIS one)
+    if (p.skip_listed && p.gctl[GC_HAVE] && p.gctl[GC_CALM] && (!p.need_img || p.gctl[GC_IMG_OK])) { pdl_enter(); return; }
     if (!early) pdl_enter();
     KPROF_SCOPE(KP_TAU);
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -26,7 +26,7 @@ from desman_b200 import _lib, engine
 from desman_b200.synth import CHAIN_SEED, synth_counts
 
 NAMES = ["maintain", "mu_binomial", "mu_class", "draw", "tau_group_mma", "tau_sample", "ll_table", "finalize", "copy_tau_if",
-         "tau_warp", "tgm_prologue", "mub_warp", "tc_evt"]
+         "tau_warp", "tgm_prologue", "mub_warp", "tc_evt", "tau_open"]
 REC = np.dtype([("kid", "i4"), ("cta", "i4"), ("warp", "i4"), ("x", "i4"), ("t0", "u8"), ("t1", "u8"), ("a", "u8"), ("b", "u8"),
                 ("c", "u8"), ("d", "u8")])
 
@@ -50,7 +50,7 @@ print("records", n, "sweep ms", e.get_timing()["elapsed_ms"] / NS, e.get_group_s
 t_base = int(r["t0"].min())
 # launches: records of one kernel id whose [t0,t1] chain overlaps
 rows = []
-for kid in range(9):
+for kid in list(range(9)) + [13]:
     k = r[r["kid"] == kid]
     if not len(k):
         continue
@@ -69,10 +69,24 @@ for d in rows:
         NAMES[d["kid"]], (d["entry"] - t_base) / 1e3, ((d["entry"] - prev) / 1e3) if prev else 0.0, (d["exit"] - d["entry"]) / 1e3,
         (d["first_exit"] - d["entry"]) / 1e3, (d["last_entry"] - d["entry"]) / 1e3, d["n"]))
     prev = d["exit"]
+to = [d for d in rows if d["kid"] == 13]
+if to:
+    g13 = r[(r["kid"] == 13) & (r["t0"] >= to[-1]["entry"]) & (r["t1"] <= to[-1]["exit"])]
+    ex = (g13["t1"].astype(np.int64) - to[-1]["entry"]) / 1e3
+    en = (g13["t0"].astype(np.int64) - to[-1]["entry"]) / 1e3
+    print("tau_open last launch: ctas %d  cta (post-prologue) start us: med %.2f max %.2f  exit us: min %.2f p10 %.2f med %.2f p90 %.2f max %.2f" % (
+        len(g13), np.median(en), en.max(), ex.min(), np.percentile(ex, 10), np.median(ex), np.percentile(ex, 90), ex.max()))
 # the last tau_sample launch: per-warp phases
+if not [d for d in rows if d["kid"] == 5]:
+    print("(no tau_sample records: the work list was walked by tau_open_kernel)")
+    sys.exit(0)
 ts = [d for d in rows if d["kid"] == 5][-1]
 w = r[(r["kid"] == 9) & (r["t0"] >= ts["entry"]) & (r["t1"] <= ts["exit"])]
 print("tau_sample last launch: warps", len(w), "launch entry->exit us", (ts["exit"] - ts["entry"]) / 1e3)
+if not len(w):
+    w = r[:0]
+    print("(tau_sample: no per-warp records: the work list was walked by tau_open_kernel)")
+    raise SystemExit(0) if "--full" not in sys.argv else None
 pro = (w["t0"].astype(np.int64) - ts["entry"]) / 1e3
 end = (w["t1"].astype(np.int64) - ts["entry"]) / 1e3
 sites = w["x"] & 0xff; n2 = (w["x"] >> 8) & 0xfff; n3 = (w["x"] >> 20) & 0xf; fl = (w["x"] >> 24) & 0xff
