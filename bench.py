@@ -31,6 +31,14 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 UNIT_V = 100000
+
+
+def workload_name(cfg_key, V, S, G):
+    """The ONE workload string both arms print (the driver compares them)."""
+    return "BASELINE config %s per GPU: synthetic V=%d S=%d G=%d, full Gibbs sweep (mu/E stats, gamma, tau, eta, ll/lp, MAP, tau sums)" % (
+        cfg_key.upper(), V, S, G)
+
+
 CONFIGS = {
     "c2": dict(V=10000, S=64, G=8),
     "c3": dict(V=100000, S=64, G=8),
@@ -170,6 +178,7 @@ def run_b200(args):
 
     # ---- device-resident timing: `value`
     e = make_engine()
+    exchange_name = e.comm_kind()
     e.set_profiling(False, not args.no_flush)
     e.update(W)                                           # warm-up sweeps (untimed)
     clocks = ClockSampler(local)
@@ -187,6 +196,17 @@ def run_b200(args):
     # flush_tau_counts (the L2 flush writes sit outside the timed events and are not counted)
     launches = int(sum(tm["kernel_launches"].values()))
     grp = e.get_group_stats()
+    rank_check = None
+    if td is not None:     # every rank draws gamma / eta itself from the exchanged statistics: they must agree bit for bit
+        import torch
+        _, g_now, e_now = e.get_state(want_tau=False)
+        mine = torch.tensor(np.concatenate([g_now.ravel(), e_now.ravel()]).view(np.int64), device="cuda")
+        allg = [torch.empty_like(mine) for _ in range(world)]
+        td.all_gather(allg, mine)
+        same = all(bool(torch.equal(allg[0], x)) for x in allg[1:])
+        if not same:
+            raise SystemExit("bench.py: gamma/eta differ between ranks after %d sweeps (exchange %s)" % (K, exchange_name))
+        rank_check = "gamma and eta bit-identical on %d ranks after the timed sweeps" % world
     value = (V_total / UNIT_V) * K / (ms_total / 1e3)
 
     # ---- per-kernel pass (events around every launch) for the roofline object
@@ -198,7 +218,9 @@ def run_b200(args):
     # the tau update = screening pass over the pattern groups (tau_group) + per-site kernel on the sites it left undecided
     kms["tau_update"] = kms["tau_group"] + kms["tau_sample"]
     peak, peak_src = measured_hbm_peak()
-    dom = max(("tau_update", "mu_stats"), key=lambda k: kms[k])
+    # the roofline object describes the tau update: the kernel pair the north star names and the only part of the sweep that
+    # streams the count tensor (the statistics read the ~3 MB pattern table at G <= 8; their line is printed beside it)
+    dom = "tau_update"
 
     traffic = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -212,6 +234,23 @@ def run_b200(args):
                     traffic=traffic.get(kernel),
                     algorithmic_bytes=b, ms=kms[kernel], peak_source=peak_src)
     e.close()
+
+    # ---- NMFT initialiser on the same tensor (reported separately): device time of the iteration loop
+    nmft = None
+    if rank == 0 and not args.no_nmft:
+        rng = np.random.default_rng(1)
+        tau0 = rng.dirichlet(np.full(4, 0.01), size=V * G).reshape(V, G, 4).transpose(2, 0, 1).reshape(4 * V, G).copy()
+        gam0 = rng.dirichlet(np.full(G, 0.01), size=S).T.copy()
+        en = engine.Engine(local, seed=1)
+        en.nmft_factorize(p["counts"], tau0, gam0, max_iter=64, min_change=0.0)          # warm-up (allocation, first launches)
+        en.nmft_factorize(p["counts"], tau0, gam0, max_iter=192, min_change=0.0)
+        ms, iters = engine.Engine.nmft_last_timing()
+        en.close()
+        per = ms / max(iters, 1)
+        nb = 8 * 4 * V * S + 2 * 8 * 4 * V * G      # X once, tau read + written, per iteration (f64)
+        nmft = {"iters_per_s": 1e3 / per, "ms_per_iter": per, "iters_timed": iters,
+                "roofline": {"bound": "hbm", "achieved": nb / (per * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": nb / (per * 1e-3) / 1e9 / peak, "algorithmic_bytes": nb, "peak_source": peak_src}}
 
     # ---- end to end through the plugin call, host buffers in, host results out
     tau_host = onehot_from_index(p["tau0"])
@@ -242,12 +281,12 @@ def run_b200(args):
         "metric": "Gibbs sweeps/sec (V variants x S samples x G strains)", "value": value, "unit": "sweeps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "BASELINE config C3 per GPU: synthetic V=%d S=%d G=%d, full Gibbs sweep "
-                               "(mu/E stats, gamma, tau, eta, ll/lp, MAP, tau sums); V_total=%d sharded over %d GPU(s), "
-                               "value in sweeps of the %d-site unit" % (V, S, G, V_total, world, UNIT_V),
+        "config": {"workload": workload_name(args.config, V, S, G),
+                   "sharding": "V_total=%d sharded over %d GPU(s), value in sweeps of the %d-site unit" % (V_total, world, UNIT_V),
                    "V_per_gpu": V, "V_total": V_total, "S": S, "G": G, "rng": "philox4x32-10 counter contract",
                    "l2": "not flushed" if args.no_flush else "flushed between sweeps (256 MiB write outside the timed events)",
-                   "parallelism": "variant-position shard x%d, 1 all-reduce of S*G+16 int64 + 2 f64 per sweep" % world,
+                   "parallelism": "variant-position shard x%d, 1 exchange of S*G+16 int64 + 2 words per sweep" % world,
+                   "collective": ("none" if world == 1 else exchange_name),
                    "e2e_call": "HaploSNP_Sampler.update() with max_iter=%d from host numpy arrays" % K},
         "e2e": {"value": e2e_value, "unit": "sweeps/s", "h2d_bytes_per_step": h2d / K, "d2h_bytes_per_step": d2h / K,
                 "seconds": t_e2e},
@@ -255,7 +294,10 @@ def run_b200(args):
         "clocks": clk,
         "roofline": roof(dom),
         "roofline_tau_sample": roof("tau_update"),
+        "roofline_mu_stats": roof("mu_stats"),
         "tau_groups": grp,
+        "nmft": nmft,
+        "rank_consistency": rank_check,
         "kernel_ms_per_sweep": kms,
         "wall_s_timed_region": t_wall,
         "chain": {"lp_first": float(res["lp_store"][0]), "lp_last": float(res["lp_store"][-1]),
@@ -314,7 +356,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: the CPU arm uses every host core whatever launched it
+    ncpu = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(ncpu)
     from oracle import oracle
+    oracle.set_num_threads(ncpu)
     from desman_b200.synth import synth_counts
     cfg = CONFIGS[args.config]
     V, S, G = cfg["V"], cfg["S"], cfg["G"]
@@ -332,14 +378,15 @@ def run_reference(args):
     per_sweep_unit = t * UNIT_V / Vs                       # seconds per sweep of the 100000-site unit
     value = 1.0 / per_sweep_unit                           # CPU arm: one host, independent of --gpus
     cores = oracle.num_threads()
-    kind = "reference" if use_ref else "port"
+    # honest label: only the tau step is the reference's own code (its numpy steps cannot travel to the GPU box)
+    kind = "reference-tau+port" if use_ref else "port"
     sample = ("%d timed sweeps on %d of %d sites, scaled linearly in V; tau step: %s; other steps: C port of the reference's "
               "numpy code on %d OpenMP threads" % (K, Vs, V, "reference c_sample_tau.c (oracle/_ref, 1 thread)" if use_ref
                                                    else "C port (all threads)", cores))
     out = {"impl": "reference", "metric": "Gibbs sweeps/sec (V variants x S samples x G strains)", "value": value,
            "unit": "sweeps/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": per_sweep_unit * 1e3,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "BASELINE config C3: synthetic V=%d S=%d G=%d, full Gibbs sweep" % (V, S, G),
+           "config": {"workload": workload_name(args.config, V, S, G),
                       "V_per_gpu": V, "S": S, "G": G},
            "cpu_baseline": {"value": value, "unit": "sweeps/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": value, "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -370,6 +417,7 @@ def main():
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between sweeps")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-nmft", action="store_true", help="skip the NMFT iterations/s leg")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":

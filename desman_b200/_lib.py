@@ -61,6 +61,8 @@ SYMBOLS = {
     "desman_get_esum_store": (C.c_int, [_ctx, _p64]),
     "desman_sample_tau_fix": (C.c_int, [_ctx, C.c_int, _pd, C.POINTER(C.c_int64)]),
     "desman_debug_screen": (C.c_int, [_ctx, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    "desman_nmft_last_timing": (C.c_int, [_pd, C.POINTER(C.c_int)]),
+    "desman_comm_kind": (C.c_int, [_ctx]),
     "desman_comm_unique_id": (C.c_int, [C.c_char_p]),
     "desman_comm_init": (C.c_int, [_ctx, C.c_char_p, C.c_int, C.c_int]),
     "desman_set_profiling": (C.c_int, [_ctx, C.c_int, C.c_int]),

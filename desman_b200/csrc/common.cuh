@@ -132,4 +132,12 @@ enum { GC_REGROUP = 0,   // regroup wanted (finalize_sweep sets it when orphans 
        GC_ORPHANS = 7,   // sites that changed pattern since the last regroup (screened out by their slot mismatch)
        GC_IMG_OK = 8,    // the fp16 count image of the tensor-memory screening pass (tau_group_tc_kernel.cuh) was built and fits
        GC_IMG_ROWS = 9,  // its padded row count
+       GC_WORTH = 10,    // the grouping pays: enough sites share patterns (set at every regroup from the realised groups)
        GC_COUNT = 12 };
+// Is the work list of the screening pass valid for this sweep?  (One test for the screening kernels and the kernels that walk
+// the list: the groups exist, the chain is calm, the realised groups are worth a table each, and -- for the tensor-memory
+// form -- the count image was built.)
+__device__ __forceinline__ bool grp_active(const int *gctl, int need_img)
+{
+    return gctl[GC_HAVE] && gctl[GC_CALM] && gctl[GC_WORTH] && (!need_img || gctl[GC_IMG_OK]);
+}

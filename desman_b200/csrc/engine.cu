@@ -810,7 +810,9 @@ static bool group_use_tc(const desman_ctx *c)
 static bool group_config(const desman_ctx *c, int *gb, int *warps)
 {
     if (c->tau_group == 0 || c->tau_exact) return false;
-    if (c->tau_group == 2 && !(c->G <= 24 && 12.0 * ldexp(1.0, c->G) <= (double)c->V / 2.0)) return false;
+    // auto: keep groups whenever the shape allows it; whether they are USED is decided on the device at every regroup from
+    // the realised groups (GC_WORTH, maintain_kernel.cuh) -- at G >= 16 far fewer than the 12*2^G possible patterns occur
+    if (c->tau_group == 2 && !(c->G <= 24 && c->V >= 1024)) return false;
     if (group_use_tc(c)) return true;
     if (group_use_mma(c)) return true;
     const int r = c->G % 8, GB = (r >= 1 && r <= 4) ? 4 : 8;
@@ -912,6 +914,7 @@ static int sync_table(desman_ctx *c, bool deferred_star_copy = false)
     p.countsf = c->countsf; p.nsite = c->nsite;
     p.star_flag = deferred_star_copy ? c->flag : nullptr; p.tau_star = c->tau_star;
     p.item_sites = use_tc ? TC_ROWS : TG_ITEM_SITES;
+    p.force_worth = c->tau_group == 1;
     p.img = nullptr; p.img_site = nullptr; p.img_nsite = nullptr; p.site_row = nullptr; p.slot_img = nullptr;
     p.img_cap_rows = 0; p.SK = 4; p.nkb = 1;
     if (use_tc) {
@@ -1749,7 +1752,20 @@ extern "C" int desman_nmft_factorize(desman_ctx *c, const int64_t *snps, int64_t
                                div_final, div_trace, g_err, sizeof(g_err));
 }
 
+extern "C" int desman_nmft_last_timing(double *ms, int *iters)
+{
+    if (ms) *ms = g_nmft_last_ms;
+    if (iters) *iters = g_nmft_last_iters;
+    return DESMAN_OK;
+}
+
 // ------------------------------------------------------------------------------------------ comm
+// data plane of the per-sweep exchange: 0 none (one rank), 1 NCCL all-reduce, 2 one-shot peer-memory mailboxes (exchange_kernel.cuh)
+extern "C" int desman_comm_kind(desman_ctx *c)
+{
+    return c->nranks <= 1 ? 0 : (c->xch_ok ? 2 : 1);
+}
+
 extern "C" int desman_comm_unique_id(char id[128])
 {
     RET(nccl_load());
@@ -1867,7 +1883,7 @@ extern "C" int desman_get_group_stats(desman_ctx *c, int64_t out[8])
     if (c->agg_nslots) CU(cudaMemcpyAsync(&ns, c->agg_nslots, sizeof(ns), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     out[0] = h[GC_HAVE]; out[1] = h[GC_CALM]; out[2] = h[GC_NITEMS]; out[3] = h[GC_NSINGLES]; out[4] = h[GC_NWORK];
-    out[5] = h[GC_ORPHANS]; out[6] = (int64_t)ns; out[7] = group_config(c, nullptr, nullptr) ? 1 : 0;
+    out[5] = h[GC_ORPHANS]; out[6] = (int64_t)ns; out[7] = (group_config(c, nullptr, nullptr) ? 1 : 0) | (h[GC_WORTH] ? 2 : 0);
     return DESMAN_OK;
 }
 

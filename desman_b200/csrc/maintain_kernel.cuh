@@ -28,6 +28,7 @@ struct MaintParams {
     // if (*star_flag) tau_star <- tau, in place of a separate copy_tau_if launch per sweep; star_flag == nullptr: none
     const int *star_flag;
     uint8_t *tau_star;
+    int force_worth;             // 1: the caller insists on the grouping (option tau_group = 1): GC_WORTH is set whatever the groups look like
     int item_sites;              // sites per work item (multiple of 8): TG_ITEM_SITES, or TC_ROWS for the tensor-memory pass
     // count image of the tensor-memory screening pass (tau_group_tc_kernel.cuh), or img == nullptr: fp16x4 cells in the
     // K-major no-swizzle UMMA order [K block][row group][KC chunks][8 rows][16 bytes]; every item starts at a multiple of 8 rows
@@ -184,7 +185,13 @@ __global__ void __launch_bounds__(MAINT_THREADS) table_maintain_kernel(MaintPara
         block_excl_scan4(part, off, sh);
         __syncthreads();
         block_excl_scan4(mine, all, sh);
-        if (gtid == 0) { gctl[GC_NITEMS] = all.y + all.z; gctl[GC_NSINGLES] = all.w; gctl[GC_HAVE] = 1; }
+        if (gtid == 0) {
+            gctl[GC_NITEMS] = all.y + all.z; gctl[GC_NSINGLES] = all.w; gctl[GC_HAVE] = 1;
+            // a table per work item costs about what three sites cost the per-site kernel: the grouping pays when the items
+            // hold at least that many sites on average and a fair share of all sites is grouped at all
+            const long long grouped = (long long)V - all.w, items = (long long)all.y + all.z;
+            gctl[GC_WORTH] = (p.force_worth || (grouped >= 3 * items && grouped * 8 >= (long long)V)) ? 1 : 0;
+        }
         __syncthreads();
     }
     int off8 = 0;

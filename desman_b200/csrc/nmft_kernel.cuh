@@ -287,6 +287,10 @@ static void nmft_launch_stats(const NmftParams &p, int grid, size_t smem, cudaSt
     nmft_stats_kernel<GP><<<grid, NMFT_WARPS * 32, smem, st>>>(p);
 }
 
+// device time of the iteration loop of the last factorisation (CUDA events on its stream) and the iterations it ran
+static double g_nmft_last_ms = 0.0;
+static int g_nmft_last_iters = 0;
+
 static int nmft_factorize_impl(cudaStream_t stream, int sm_count, const int64_t *snps, int64_t V, int S, int G, double *tau,
                                double *gamma, int max_iter, double min_change, int fix_gamma, int *n_iter_done,
                                double *div_final, double *div_trace, char *err, size_t errn)
@@ -308,6 +312,7 @@ static int nmft_factorize_impl(cudaStream_t stream, int sm_count, const int64_t 
     NmftState hst;
     NmftParams p;
     int it_guard = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (smem_tau > 220 * 1024 || smem_stats > 220 * 1024) { snprintf(err, errn, "NMFT: G*S too large for shared memory"); return -1; }
 
     NMFT_CU(cudaMalloc(&dX, nX * 8));
@@ -368,6 +373,8 @@ static int nmft_factorize_impl(cudaStream_t stream, int sm_count, const int64_t 
     p.st_in = dSt; p.st_out = dSt;
     NMFT_STATS();
     NMFT_CU(cudaGetLastError());
+    cudaEventCreate(&ev0); cudaEventCreate(&ev1);
+    cudaEventRecord(ev0, stream);
     {
         int parity = 0;
         bool finished = false;
@@ -386,6 +393,7 @@ static int nmft_factorize_impl(cudaStream_t stream, int sm_count, const int64_t 
             if (++it_guard > (max_iter / 64) + 4) finished = true;
         }
     }
+    cudaEventRecord(ev1, stream);
     NMFT_CU(cudaMemcpyAsync(hT.data(), dT, nT * 8, cudaMemcpyDeviceToHost, stream));
     NMFT_CU(cudaMemcpyAsync(hG.data(), fix_gamma ? dG : dGa, nG * 8, cudaMemcpyDeviceToHost, stream));
     if (div_trace && hst.iter > 0) NMFT_CU(cudaMemcpyAsync(div_trace, dTr, (size_t)hst.iter * 8, cudaMemcpyDeviceToHost, stream));
@@ -396,7 +404,13 @@ static int nmft_factorize_impl(cudaStream_t stream, int sm_count, const int64_t 
     for (size_t i = 0; i < nG; i++) gamma[i] = hG[i];
     if (n_iter_done) *n_iter_done = hst.iter;
     if (div_final) *div_final = hst.div;
+    {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) { g_nmft_last_ms = ms; g_nmft_last_iters = hst.iter; }
+    }
 done:
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
     for (void *q : {(void *)dX, (void *)dT, (void *)dG, (void *)dGa, (void *)dt1, (void *)dP, (void *)dTr, (void *)dS, (void *)dSt})
         if (q) cudaFree(q);
     return rc;

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(TG_MAX_WARPS * 32, 1) tau_group_kernel(TauGrou
     pdl_enter();
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int *gctl = p.grp.gctl;
-    if (!(gctl[GC_HAVE] && gctl[GC_CALM])) return;
+    if (!grp_active(gctl, 0)) return;
     const int S = p.S, G = p.G;
     const int Sp = (S + 15) & ~15, nk = Sp >> 3;
     const int nGB = (G + GB - 1) / GB;
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(TGM_WARPS * 32, 16 / TGM_WARPS) tau_group_mma_
     pdl_enter();                                                          // (shared memory only so far)
 #endif
     KPROF_SCOPE(KP_TGM);
-    if (!(gctl[GC_HAVE] && gctl[GC_CALM])) return;
+    if (!grp_active(gctl, 0)) return;
     __syncthreads();
     float gmin_l = __int_as_float(0x7f800000);
     for (int i = tid; i < G * Sp; i += blockDim.x) {

@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
     pdl_enter();
     KPROF_SCOPE(KP_TGM);
     const int *gctl = p.grp.gctl;
-    if (!(gctl[GC_HAVE] && gctl[GC_CALM] && gctl[GC_IMG_OK])) return;
+    if (!grp_active(gctl, 1)) return;
     const int nitems = gctl[GC_NITEMS];
     if ((int)blockIdx.x >= nitems) return;
 

@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
 #endif
     // the work list is walked by tau_open_kernel: nothing to do here when it is valid (the control words that say so were
     // written at least two grids ago; the wait still has to happen: the next grid of the chain orders itself after THIS one)
-    if (p.skip_listed && p.gctl[GC_HAVE] && p.gctl[GC_CALM] && (!p.need_img || p.gctl[GC_IMG_OK])) { pdl_enter(); return; }
+    if (p.skip_listed && grp_active(p.gctl, p.need_img)) { pdl_enter(); return; }
     if (!early) pdl_enter();
     KPROF_SCOPE(KP_TAU);
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
     if (early) pdl_enter();
     int nsite = p.V, nwork = 0;
     bool listed = false;
-    if (p.work && p.gctl[GC_HAVE] && p.gctl[GC_CALM] && (!p.need_img || p.gctl[GC_IMG_OK])) {
+    if (p.work && grp_active(p.gctl, p.need_img)) {
         listed = true;
         nwork = p.gctl[GC_NWORK];
         nsite = nwork + p.gctl[GC_NSINGLES];

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(TAUO_WARPS * 32, 6) tau_open_kernel(TauParams 
     pdl_enter();
 #endif
     KPROF_SCOPE(KP_TAUO);
-    if (!(p.gctl[GC_HAVE] && p.gctl[GC_CALM] && (!p.need_img || p.gctl[GC_IMG_OK]))) return;   // no valid list: tau_sample_kernel walks every site
+    if (!grp_active(p.gctl, p.need_img)) return;   // no valid list: tau_sample_kernel walks every site
     const int nwork = p.gctl[GC_NWORK], nsite = nwork + p.gctl[GC_NSINGLES];
     unsigned int flips = 0, n1 = 0, n2 = 0, n3 = 0;
 

@@ -246,6 +246,16 @@ class Engine:
         check(_lib.lib().desman_comm_unique_id(buf), "desman_comm_unique_id")
         return buf.raw
 
+    def comm_kind(self):
+        """Data plane of the per-sweep exchange: 'none', 'nccl-allreduce' or 'p2p-mailbox' (one-shot over NVLink peer memory)."""
+        return ("none", "nccl-allreduce", "p2p-mailbox")[self._L.desman_comm_kind(self._h)]
+
+    @staticmethod
+    def nmft_last_timing():
+        ms, it = C.c_double(0), C.c_int(0)
+        check(_lib.lib().desman_nmft_last_timing(C.byref(ms), C.byref(it)), "desman_nmft_last_timing")
+        return ms.value, it.value
+
     def comm_init(self, uid, rank, nranks):
         check(self._L.desman_comm_init(self._h, uid, rank, nranks), "desman_comm_init")
 
@@ -256,7 +266,10 @@ class Engine:
         """Site groups of the tau screening pass: dict(have, calm, items, singles, work, orphans, slots, configured)."""
         out = np.zeros(8, dtype=np.int64)
         check(self._L.desman_get_group_stats(self._h, _lib.ptr_i64(out)), "desman_get_group_stats")
-        return dict(zip(("have", "calm", "items", "singles", "work", "orphans", "slots", "configured"), out.tolist()))
+        d = dict(zip(("have", "calm", "items", "singles", "work", "orphans", "slots", "configured"), out.tolist()))
+        d["worth"] = (d["configured"] >> 1) & 1          # the realised groups pay for a table each (decided on the device)
+        d["configured"] &= 1
+        return d
 
     def debug_screen(self):
         """Validation of the tensor-memory screening pass: (D [V,G,3] float32 log2-units sums, NaN where a site is in no

@@ -120,6 +120,9 @@ int desman_nmft_factorize(desman_ctx *ctx, const int64_t *snps, int64_t V, int S
                           double *tau, double *gamma, int max_iter, double min_change, int fix_gamma,
                           int *n_iter_done, double *div_final, double *div_trace);
 
+/* device time (CUDA events) of the iteration loop of the last desman_nmft_factorize of this process, and its iterations */
+int desman_nmft_last_timing(double *ms, int *iters);
+
 /* Engine options.  "mu_mode" = 1: mu/E statistics from pattern-aggregated conditional binomials; 0: one categorical
  * draw per read (both exact, different counter contracts); 2 (default): 1 iff 12*2^G <= V/2.  "fixed_tau" = 1 makes desman_update skip the tau draw (update_fixed_tau, HaploSNP_Sampler.py:409-428).
  * "tau_exact" = 1 forces the FP64 reference-order arithmetic for every tau draw (validation;
@@ -150,6 +153,8 @@ int desman_sample_tau_fix(desman_ctx *ctx, int H, double *logp /*V*4*/, int64_t 
  * desman_comm_unique_id fills a 128-byte NCCL id on rank 0; every rank calls desman_comm_init. */
 int desman_comm_unique_id(char id[128]);
 int desman_comm_init(desman_ctx *ctx, const char id[128], int rank, int nranks);
+/* data plane of the per-sweep exchange: 0 none (one rank), 1 NCCL all-reduce, 2 one-shot peer-memory mailboxes over NVLink */
+int desman_comm_kind(desman_ctx *ctx);
 
 /* Measurement hooks (bench.py): device-timed sweeps with CUDA events on the engine's stream. */
 enum { DESMAN_K_TAU = 0, DESMAN_K_MU = 1, DESMAN_K_DRAW = 2, DESMAN_K_FINAL = 3, DESMAN_K_MT = 4,

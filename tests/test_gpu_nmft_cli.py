@@ -161,8 +161,8 @@ def test_sampler_class_surface_on_gpu(oracle_mod):
     hs.updateTau()
     assert hs.ll_store.shape == (7,) and (hs.tauMean().sum(2) > 0.999).all()
     assert np.isfinite(hs.DIC())                                              # value checked in test_gpu_states.py
-    with pytest.raises(NotImplementedError):
-        hs.chibMarginalLogLikelihood()
+    hs.gamma_star, hs.eta_star = hs.gammaMean(), hs.etaMean()                # (updateTau keeps no gamma / eta star)
+    assert np.isfinite(hs.chibMarginalLogLikelihood2())                       # values checked in test_gpu_states.py
     hs.close()
     sampletau.freeRNG()
 
