@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("DESMAN_B200_LIB") or os.path.join(_HERE, "libdesman_b
 
 RNG_MT19937, RNG_PHILOX = 0, 1
 MAX_G = 32
-K_NAMES = ("tau_sample", "mu_stats", "draw_gamma_eta", "finalize", "mt19937", "nmft", "other", "tau_group", "maintain")
+K_NAMES = ("tau_sample", "mu_stats", "draw_gamma_eta", "finalize", "mt19937", "nmft", "other", "tau_group", "maintain", "tau_update")
 
 _p64 = C.POINTER(C.c_int64)
 _pd = C.POINTER(C.c_double)

@@ -254,7 +254,10 @@ struct KSpan {  // brackets n kernel launches with events when per-kernel profil
     KSpan(desman_ctx *c_, int kind_, int n = 1) : c(c_), kind(kind_)
     {
         c->k_launch[kind] += n;
-        if (c->prof_kernels) { a = get_event(c); cudaEventRecord(a, c->stream); }
+        // level 1: every span; level 2: only the span around the whole tau update
+        if (c->prof_kernels == 1 ? kind != DESMAN_K_TAU_UPDATE : (c->prof_kernels == 2 && kind == DESMAN_K_TAU_UPDATE)) {
+            a = get_event(c); cudaEventRecord(a, c->stream);
+        }
     }
     ~KSpan()
     {
@@ -1008,6 +1011,7 @@ static int launch_tau_group_t(desman_ctx *c, const TauGroupParams &p, int warps)
 static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, bool maintain, bool count_occupancy, uint32_t iter,
                       int g_begin = 0, double *logp_out = nullptr)
 {
+    KSpan whole(c, DESMAN_K_TAU_UPDATE, 0);
     TauParams p;
     p.counts = c->counts; p.tau = c->tau; p.gamma = gamma; p.eta = eta;
     p.words = nullptr;

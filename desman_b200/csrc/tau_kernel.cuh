@@ -108,6 +108,34 @@ __device__ __noinline__ void tau_exact_logp(const int4 *tile, const double *gT, 
     L[0] = warp_sum(L0); L[1] = warp_sum(L1); L[2] = warp_sum(L2); L[3] = warp_sum(L3);
 }
 
+// The same sum for ONE candidate base a (same lane / chunk order, same operations: bit-identical to L[a] of tau_exact_logp);
+// tau_open_kernel spreads the four candidates of a step over its four warps.
+__device__ __noinline__ double tau_exact_logp_cand(const int4 *tile, const double *gT, const double *eta_s, uint64_t code,
+                                                   int g, int S, int Sp, int G, int lane, int a)
+{
+    double L = 0.0;
+    const double *e = eta_s + 4 * a;
+    for (int s = lane; s < S; s += 32) {
+        const int4 n = tile[s];
+        if ((n.x | n.y | n.z | n.w) == 0) continue;
+        double b0 = 0.0, b1 = 0.0, b2 = 0.0, b3 = 0.0;
+        for (int h = 0; h < G; h++) {
+            if (h == g) continue;
+            const double *eh = eta_s + 4 * code_get(code, h);
+            const double gm = gT[h * Sp + s];
+            b0 = fma(eh[0], gm, b0); b1 = fma(eh[1], gm, b1);
+            b2 = fma(eh[2], gm, b2); b3 = fma(eh[3], gm, b3);
+        }
+        const double gg = gT[g * Sp + s];
+        const double f0 = (double)(float)n.x, f1 = (double)(float)n.y, f2 = (double)(float)n.z, f3 = (double)(float)n.w;
+        if (n.x) L = fma(f0, log(fma(e[0], gg, b0)), L);
+        if (n.y) L = fma(f1, log(fma(e[1], gg, b1)), L);
+        if (n.z) L = fma(f2, log(fma(e[2], gg, b2)), L);
+        if (n.w) L = fma(f3, log(fma(e[3], gg, b3)), L);
+    }
+    return warp_sum(L);
+}
+
 // normaliseLog4 + sample4 (c_sample_tau.c:48-91)
 __device__ __noinline__ int tau_exact_pick(const double L[4], double u)
 {

@@ -68,6 +68,11 @@ __global__ void __launch_bounds__(TAUO_WARPS * 32, 6) tau_open_kernel(TauParams 
     if (!grp_active(p.gctl, p.need_img)) return;   // no valid list: tau_sample_kernel walks every site
     const int nwork = p.gctl[GC_NWORK], nsite = nwork + p.gctl[GC_NSINGLES];
     unsigned int flips = 0, n1 = 0, n2 = 0, n3 = 0;
+#ifdef KPROF
+    const unsigned long long kp_t0 = gtimer();
+    unsigned long long kp_rounds = 0, kp_stage = 0, kp_steps = 0;
+    int kp_sites = 0;
+#endif
 
     // one (v,g) step against pattern `code`: the tiers of tau_sample_kernel; *tier = 1, 2 or 3
     auto step = [&](uint64_t code, int g, bool open_by_screening, float nlane, float mlP, int *tier) -> int {
@@ -106,12 +111,23 @@ __global__ void __launch_bounds__(TAUO_WARPS * 32, 6) tau_open_kernel(TauParams 
                 *tier = 2;
             }
         }
-        if (t < 0) {
-            double L[4];
-            tau_exact_logp(tile, gT, eta_s, code, g, S, Sp, G, lane, L);
-            t = tau_exact_pick(L, u);
-            *tier = 3;
+        if (t < 0) *tier = 3;       // FP64 reference-order recompute: done by the four warps together (exact3 below)
+        return t;
+    };
+    // tier 3 of one step, the four candidates on the four warps (each sum bit-identical to tau_exact_logp's); every thread
+    // returns the draw
+    __shared__ double L3[4];
+    auto exact3 = [&](uint64_t code, int g) -> int {
+        for (int a = wib; a < 4; a += TAUO_WARPS) {
+            const double La = tau_exact_logp_cand(tile, gT, eta_s, code, g, S, Sp, G, lane, a);
+            if (lane == 0) L3[a] = La;
         }
+        __syncthreads();
+        const uint32_t w = ww[g];
+        const double u = p.words ? (double)w / 4294967296.0 : ((double)w + 0.5) / 4294967296.0;
+        double L[4] = {L3[0], L3[1], L3[2], L3[3]};
+        const int t = tau_exact_pick(L, u);
+        __syncthreads();
         return t;
     };
     // this lane's reads and max |lg2 P| over its samples (what the error bounds of a step are charged on)
@@ -133,6 +149,10 @@ __global__ void __launch_bounds__(TAUO_WARPS * 32, 6) tau_open_kernel(TauParams 
         // a full mask is what orphans of their group, single-site patterns (and sites with a zero MT word) get without any test:
         // their steps are ordinary ones, mostly settled by the cheap gap test
         const bool screened = (i < nwork) && todo != fullG;
+#ifdef KPROF
+        const unsigned long long kp_a = gtimer();
+        kp_sites++;
+#endif
         const uint64_t code_in = load_tau_code(p.tau + (size_t)v * G, G, lane);
         // ---- stage the site: warp c takes the 32-sample chunk c; the last warp draws the G uniform words
         for (int c = wib; c < nch; c += TAUO_WARPS) {
@@ -165,6 +185,10 @@ __global__ void __launch_bounds__(TAUO_WARPS * 32, 6) tau_open_kernel(TauParams 
         }
         if (threadIdx.x == 0) first_flip = G;
         __syncthreads();
+#ifdef KPROF
+        const unsigned long long kp_b = gtimer();
+        kp_stage += kp_b - kp_a;
+#endif
         // ---- rounds: the pending strains, one per warp, against the current pattern; valid up to the first flip, which is then
         // applied (all warps, a chunk each) and makes every later strain pending again
         uint64_t code = code_in;
@@ -172,6 +196,9 @@ __global__ void __launch_bounds__(TAUO_WARPS * 32, 6) tau_open_kernel(TauParams 
         bool from_screening = screened;
         bool first_round = true;
         while (true) {
+#ifdef KPROF
+            kp_rounds++;
+#endif
             float nlane, mlP;
             lane_bounds(nlane, mlP);
             int k = 0;
@@ -182,10 +209,20 @@ __global__ void __launch_bounds__(TAUO_WARPS * 32, 6) tau_open_kernel(TauParams 
                 const int t = step(code, g, from_screening, nlane, mlP, &tier);
                 if (lane == 0) {
                     t_s[g] = t; t_s[32 + g] = tier;
-                    if (t != code_get(code, g)) atomicMin(&first_flip, g);
+                    if (t >= 0 && t != code_get(code, g)) atomicMin(&first_flip, g);
                 }
             }
             __syncthreads();
+            // steps left to the FP64 recompute (t < 0), in strain order; those after a flip need not be looked at
+            for (int g = 0; g < G && g < first_flip; g++) {
+                if (!((pending >> g) & 1u) || t_s[g] >= 0) continue;
+                const int t = exact3(code, g);                               // (uniform: every thread takes this path together)
+                if (threadIdx.x == 0) {
+                    t_s[g] = t;
+                    if (t != code_get(code, g) && g < first_flip) first_flip = g;
+                }
+                __syncthreads();
+            }
             const int gf = first_flip;                                       // G: no pending strain flipped
             if (wib == 0) {
                 // account for the decisions that stand: pending strains up to the flip; in the first round also the strains the
@@ -231,6 +268,9 @@ __global__ void __launch_bounds__(TAUO_WARPS * 32, 6) tau_open_kernel(TauParams 
             if (pending == 0u) break;
             __syncthreads();
         }
+#ifdef KPROF
+        kp_steps += gtimer() - kp_b;
+#endif
         if (code != code_in && wib == 0) {
             if (lane < G) p.tau[(size_t)v * G + lane] = (uint8_t)code_get(code, lane);
             if (p.agg.N) {
@@ -243,6 +283,9 @@ __global__ void __launch_bounds__(TAUO_WARPS * 32, 6) tau_open_kernel(TauParams 
         }
         __syncthreads();
     }
+#ifdef KPROF
+    if (threadIdx.x == 0) krec_put(KP_TAU_WARP, (int)blockIdx.x, 0, (int)(kp_sites | (n2 << 8) | (n3 << 20) | (flips << 24)), kp_t0, gtimer(), kp_rounds, kp_stage, kp_steps, 0);
+#endif
     if (wib == 0 && lane == 0) {
         if (flips) atomicAdd(p.nchange, (unsigned long long)flips);
         if (p.tier_counts) {

@@ -286,7 +286,7 @@ class Engine:
         return out
 
     def set_profiling(self, per_kernel_events=False, flush_l2=False):
-        check(self._L.desman_set_profiling(self._h, int(per_kernel_events), int(flush_l2)), "desman_set_profiling")
+        check(self._L.desman_set_profiling(self._h, int(per_kernel_events), int(flush_l2)), "desman_set_profiling")   # per_kernel_events: 0, 1 or 2 (see the header)
 
     def get_timing(self):
         el = C.c_double(0)

@@ -158,7 +158,12 @@ int desman_comm_kind(desman_ctx *ctx);
 
 /* Measurement hooks (bench.py): device-timed sweeps with CUDA events on the engine's stream. */
 enum { DESMAN_K_TAU = 0, DESMAN_K_MU = 1, DESMAN_K_DRAW = 2, DESMAN_K_FINAL = 3, DESMAN_K_MT = 4,
-       DESMAN_K_NMFT = 5, DESMAN_K_OTHER = 6, DESMAN_K_TAU_GROUP = 7, DESMAN_K_MAINT = 8, DESMAN_K_COUNT = 9 };
+       DESMAN_K_NMFT = 5, DESMAN_K_OTHER = 6, DESMAN_K_TAU_GROUP = 7, DESMAN_K_MAINT = 8, DESMAN_K_TAU_UPDATE = 9,
+       DESMAN_K_COUNT = 10 };
+/* per_kernel_events: 0 none (sweeps only); 1 an event pair around every kernel launch (an event between two launches also
+ * undoes their programmatic overlap, so these times add up to more than the sweep); 2 ONE pair around the whole tau update
+ * (screening pass + the kernels that walk its work list, launched as the dependent chain they are in production): reported
+ * as DESMAN_K_TAU_UPDATE and nothing else. */
 int desman_set_profiling(desman_ctx *ctx, int per_kernel_events, int flush_l2_between_sweeps);
 /* elapsed_ms: sum over sweeps of the event-timed sweep durations of the last update()/update_tau() */
 int desman_get_timing(desman_ctx *ctx, double *elapsed_ms, double kernel_ms[DESMAN_K_COUNT],

@@ -76,6 +76,19 @@ if to:
     en = (g13["t0"].astype(np.int64) - to[-1]["entry"]) / 1e3
     print("tau_open last launch: ctas %d  cta (post-prologue) start us: med %.2f max %.2f  exit us: min %.2f p10 %.2f med %.2f p90 %.2f max %.2f" % (
         len(g13), np.median(en), en.max(), ex.min(), np.percentile(ex, 10), np.median(ex), np.percentile(ex, 90), ex.max()))
+if to:
+    w = r[(r["kid"] == 9) & (r["t0"] >= to[-1]["entry"] - 20000) & (r["t1"] <= to[-1]["exit"] + 1000)]
+    if len(w):
+        dur = (w["t1"].astype(np.int64) - w["t0"].astype(np.int64)) / 1e3
+        sites = w["x"] & 0xff; n2 = (w["x"] >> 8) & 0xfff; n3 = (w["x"] >> 20) & 0xf; fl = (w["x"] >> 24) & 0xff
+        print("tau_open CTAs with sites: %d; per CTA us (after prologue): med %.2f p90 %.2f max %.2f" % (int((sites > 0).sum()), np.median(dur[sites > 0]), np.percentile(dur[sites > 0], 90), dur.max()))
+        for i in np.argsort(dur)[-8:]:
+            print("  slow cta %d: %.2f us  sites %d rounds %d n2 %d n3 %d flips %d  stage %.2f steps %.2f" % (
+                w["cta"][i], dur[i], sites[i], w["a"][i], n2[i], n3[i], fl[i], w["b"][i] / 1e3, w["c"][i] / 1e3))
+        has = sites > 0
+        print("  per site: stage med %.2f p90 %.2f   rounds+writeback med %.2f p90 %.2f max %.2f" % (
+            np.median(w["b"][has] / sites[has]) / 1e3, np.percentile(w["b"][has] / sites[has], 90) / 1e3,
+            np.median(w["c"][has] / sites[has]) / 1e3, np.percentile(w["c"][has] / sites[has], 90) / 1e3, (w["c"][has] / sites[has]).max() / 1e3))
 # the last tau_sample launch: per-warp phases
 if not [d for d in rows if d["kid"] == 5]:
     print("(no tau_sample records: the work list was walked by tau_open_kernel)")
