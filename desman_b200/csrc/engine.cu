@@ -1195,6 +1195,18 @@ static int allreduce_red(desman_ctx *c)
     return DESMAN_OK;
 }
 
+// The peer-memory exchange does not hang on a dead peer: after its spin limit it raises xch_err and carries on with what it
+// has.  Every API that exchanged checks the flag once its results are on the host (stream already synchronised).
+static int check_xch(desman_ctx *c)
+{
+    if (!c->xch_ok) return DESMAN_OK;
+    int xe = 0;
+    CU(cudaMemcpyAsync(&xe, c->xch_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (xe) return fail(DESMAN_ECOMM, "peer-memory exchange timed out waiting for another rank");
+    return DESMAN_OK;
+}
+
 static int launch_draw(desman_ctx *c, const unsigned long long *stats, double *gamma_out, double *eta_out,
                        unsigned long long *esum_keep = nullptr)
 {
@@ -1323,7 +1335,7 @@ extern "C" int desman_mu_stats(desman_ctx *c, int64_t *sum_mu, int64_t *esum)
     CU(cudaStreamSynchronize(c->stream));
     if (sum_mu) for (size_t i = 0; i < nsg; i++) sum_mu[i] = (int64_t)h[i];
     if (esum) for (int i = 0; i < 16; i++) esum[i] = (int64_t)h[nsg + i];
-    return DESMAN_OK;
+    return check_xch(c);
 }
 
 extern "C" int desman_draw_gamma_eta(desman_ctx *c, const int64_t *sum_mu, const int64_t *esum, double *gamma, double *eta)
@@ -1357,6 +1369,7 @@ extern "C" int desman_loglik(desman_ctx *c, double *ll, double *lp)
     CU(cudaMemcpyAsync(g.data(), c->gamma, g.size() * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaMemcpyAsync(e.data(), c->eta, 16 * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    RET(check_xch(c));
     const double h_ll = c->ll_const_total + (double)fx / c->ll_scale;
     // prior on host (tiny): Desman_Utils.py:35-44, HaploSNP_Sampler.py:448-459
     double prior = 0.0;
@@ -1540,12 +1553,7 @@ static int fetch_stores(desman_ctx *c, int n_iter, const StoreBufs &sb, double *
     if (eta_store && sb.es) CU(cudaMemcpyAsync(eta_store, sb.es, (size_t)n_iter * 16 * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     if (nchange_store) for (int i = 0; i < n_iter; i++) nchange_store[i] = (int64_t)llround(nch[i]);
-    if (c->xch_ok) {
-        int xe = 0;
-        CU(cudaMemcpyAsync(&xe, c->xch_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        if (xe) return fail(DESMAN_ECOMM, "peer-memory exchange timed out waiting for another rank");
-    }
+    RET(check_xch(c));
     if (c->agg_ctl) {
         int ctl[3] = {0, 0, 0};
         CU(cudaMemcpyAsync(ctl, c->agg_ctl, sizeof(ctl), cudaMemcpyDeviceToHost, c->stream));
