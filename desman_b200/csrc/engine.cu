@@ -1806,10 +1806,11 @@ extern "C" int desman_comm_init(desman_ctx *c, const char id[128], int rank, int
         cudaFree(dw);
     }
     // peer-memory mailboxes for the per-sweep exchange; any failure here leaves the NCCL all-reduce in place
-    // default: on from 4 ranks (DESMAN_B200_P2P=0/1 forces it).  Measured per sweep (two exchanges): 2 GPUs 33.6 us vs 31.0 us
-    // with NCCL -- inter-rank skew, not protocol latency --; 8 GPUs 45.7 us vs 64.8 us (83 % vs 76 % weak-scaling efficiency)
+    // default: on from 2 ranks (DESMAN_B200_P2P=0/1 forces it; tests/test_gpu_multi.py runs both data planes at 2 and 4 ranks
+    // against the oracle).  Measured per sweep at C3 per GPU, one exchange per sweep, event-timed incl. the wait for the slowest
+    // rank: 2 GPUs NCCL 43.8 us; 4 GPUs peer memory 21.6 us; round 1 at 8 GPUs, two exchanges: 45.7 us vs 64.8 us with NCCL
     const char *env = getenv("DESMAN_B200_P2P");
-    if (env ? !atoi(env) : nranks < 4) return DESMAN_OK;
+    if (env ? !atoi(env) : nranks < 2) return DESMAN_OK;
     if (nranks > XCH_MAX_RANKS || !g_nccl.AllGather) return DESMAN_OK;
     const int cap = 4096;                                             // words per contribution (S*G + 16 must fit)
     const size_t words = (size_t)2 * nranks * cap + nranks;

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(TAUO_WARPS * 32, 6) tau_open_kernel(TauParams 
     unsigned int flips = 0, n1 = 0, n2 = 0, n3 = 0;
 #ifdef KPROF
     const unsigned long long kp_t0 = gtimer();
-    unsigned long long kp_rounds = 0, kp_stage = 0, kp_steps = 0;
+    unsigned long long kp_rounds = 0, kp_stage = 0, kp_steps = 0, kp_q[3] = {0, 0, 0};
     int kp_sites = 0;
 #endif
 
@@ -200,7 +200,13 @@ __global__ void __launch_bounds__(TAUO_WARPS * 32, 6) tau_open_kernel(TauParams 
             kp_rounds++;
 #endif
             float nlane, mlP;
+#ifdef KPROF
+            const unsigned long long kq0 = gtimer();
+#endif
             lane_bounds(nlane, mlP);
+#ifdef KPROF
+            const unsigned long long kq1 = gtimer();
+#endif
             int k = 0;
             for (int g = 0; g < G; g++) {
                 if (!((pending >> g) & 1u)) continue;
@@ -212,7 +218,14 @@ __global__ void __launch_bounds__(TAUO_WARPS * 32, 6) tau_open_kernel(TauParams 
                     if (t >= 0 && t != code_get(code, g)) atomicMin(&first_flip, g);
                 }
             }
+#ifdef KPROF
+            const unsigned long long kq2 = gtimer();
+#endif
             __syncthreads();
+#ifdef KPROF
+            const unsigned long long kq3 = gtimer();
+            if (threadIdx.x == 0) { kp_q[0] += kq1 - kq0; kp_q[1] += kq2 - kq1; kp_q[2] += kq3 - kq2; }
+#endif
             // steps left to the FP64 recompute (t < 0), in strain order; those after a flip need not be looked at
             for (int g = 0; g < G && g < first_flip; g++) {
                 if (!((pending >> g) & 1u) || t_s[g] >= 0) continue;
@@ -284,7 +297,7 @@ __global__ void __launch_bounds__(TAUO_WARPS * 32, 6) tau_open_kernel(TauParams 
         __syncthreads();
     }
 #ifdef KPROF
-    if (threadIdx.x == 0) krec_put(KP_TAU_WARP, (int)blockIdx.x, 0, (int)(kp_sites | (n2 << 8) | (n3 << 20) | (flips << 24)), kp_t0, gtimer(), kp_rounds, kp_stage, kp_steps, 0);
+    if (threadIdx.x == 0) krec_put(KP_TAU_WARP, (int)blockIdx.x, 0, (int)(kp_sites | (n2 << 8) | (n3 << 20) | (flips << 24)), kp_t0, gtimer(), kp_rounds | (kp_q[0] << 8) | (kp_q[1] << 24) | (kp_q[2] << 44), kp_stage, kp_steps, 0);
 #endif
     if (wib == 0 && lane == 0) {
         if (flips) atomicAdd(p.nchange, (unsigned long long)flips);

@@ -82,9 +82,11 @@ if to:
         dur = (w["t1"].astype(np.int64) - w["t0"].astype(np.int64)) / 1e3
         sites = w["x"] & 0xff; n2 = (w["x"] >> 8) & 0xfff; n3 = (w["x"] >> 20) & 0xf; fl = (w["x"] >> 24) & 0xff
         print("tau_open CTAs with sites: %d; per CTA us (after prologue): med %.2f p90 %.2f max %.2f" % (int((sites > 0).sum()), np.median(dur[sites > 0]), np.percentile(dur[sites > 0], 90), dur.max()))
-        for i in np.argsort(dur)[-8:]:
-            print("  slow cta %d: %.2f us  sites %d rounds %d n2 %d n3 %d flips %d  stage %.2f steps %.2f" % (
-                w["cta"][i], dur[i], sites[i], w["a"][i], n2[i], n3[i], fl[i], w["b"][i] / 1e3, w["c"][i] / 1e3))
+        for i in list(np.argsort(dur)[-6:]) + list(np.flatnonzero(sites > 0)[:6]):
+            a = int(w["a"][i])
+            print("  cta %d: %.2f us  sites %d rounds %d n2 %d n3 %d flips %d  stage %.2f steps %.2f | thread 0: lane_bounds %.2f own step %.2f barrier wait %.2f" % (
+                w["cta"][i], dur[i], sites[i], a & 0xff, n2[i], n3[i], fl[i], w["b"][i] / 1e3, w["c"][i] / 1e3,
+                ((a >> 8) & 0xffff) / 1e3, ((a >> 24) & 0xfffff) / 1e3, (a >> 44) / 1e3))
         has = sites > 0
         print("  per site: stage med %.2f p90 %.2f   rounds+writeback med %.2f p90 %.2f max %.2f" % (
             np.median(w["b"][has] / sites[has]) / 1e3, np.percentile(w["b"][has] / sites[has], 90) / 1e3,
