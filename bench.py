@@ -160,6 +160,8 @@ def run_b200(args):
     cfg = CONFIGS[args.config]
     V, S, G = cfg["V"], cfg["S"], cfg["G"]
     K, W = args.steps, max(args.warmup, 3)
+    if args.strong:                     # strong scaling: the config's V sites shared out over the ranks
+        V = V // world
     V_total = V * world
     if _lib.device_count() < 1:
         raise SystemExit("bench.py: no CUDA device; desman_b200 has no CPU fallback")
@@ -286,7 +288,7 @@ def run_b200(args):
     out = {
         "metric": "Gibbs sweeps/sec (V variants x S samples x G strains)", "value": value, "unit": "sweeps/s",
         "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.config, V, S, G),
                    "sharding": "V_total=%d sharded over %d GPU(s), value in sweeps of the %d-site unit" % (V_total, world, UNIT_V),
                    "V_per_gpu": V, "V_total": V_total, "S": S, "G": G, "rng": "philox4x32-10 counter contract",
@@ -424,6 +426,7 @@ def main():
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between sweeps")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-nmft", action="store_true", help="skip the NMFT iterations/s leg")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: V of the config divided over the ranks (default: V per rank)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.impl == "reference":
