@@ -60,6 +60,7 @@ class HaploSNP_Sampler():
 
         # the constructor consumes the caller's stream exactly like the reference (:63, :72)
         self._tau_oh = self._tau_ix = self._tau_star_oh = self._tau_star_ix = None
+        self._tauIndices = self._tauIndices_star = None
         self.gamma = self.randomState.dirichlet(self.alpha, size=self.S)
         self.gamma_store = np.zeros((self.max_iter, self.S, self.G))
         if fixed_tau is None:
@@ -212,6 +213,28 @@ class HaploSNP_Sampler():
     def updateTauIndices(self):
         self.tauIndices = self._site_codes(self._tau_index())               # :228-231, vectorised
 
+    # tauIndices / tauIndices_star are derived from tau / tau_star (2 ms per 1e5 sites on the host): after a chain driver they
+    # are worked out when first read, not inside the driver
+    @property
+    def tauIndices(self):
+        if self._tauIndices is None:
+            self._tauIndices = self._site_codes(self._tau_index())
+        return self._tauIndices
+
+    @tauIndices.setter
+    def tauIndices(self, value):
+        self._tauIndices = value
+
+    @property
+    def tauIndices_star(self):
+        if self._tauIndices_star is None:
+            self._tauIndices_star = self._site_codes(self._tau_index(star=True))
+        return self._tauIndices_star
+
+    @tauIndices_star.setter
+    def tauIndices_star(self, value):
+        self._tauIndices_star = value
+
     def _site_codes(self, idx):
         if self.G > 31:
             w = np.array([4 ** (self.G - g - 1) for g in range(self.G)], dtype=object)
@@ -310,8 +333,7 @@ class HaploSNP_Sampler():
             self.ll, self.lp = float(res["ll_store"][-1]), float(res["lp_store"][-1])
         self._tau_sum = eng.get_tau_sum(compact=True)        # uint32 occupancy counters; tauMean() divides them
         self._timing = eng.get_timing()
-        self.updateTauIndices()
-        self.tauIndices_star = self._site_codes(self._tau_star_ix)
+        self._tauIndices = self._tauIndices_star = None                       # lazily, from the new tau / tau_star
 
     def update(self):
         """max_iter Gibbs sweeps mu/E -> gamma -> tau -> eta -> ll/lp with MAP tracking (:334-365)."""

@@ -59,6 +59,9 @@ SYMBOLS = {
     "desman_get_tier_counts": (C.c_int, [_ctx, _p64, C.c_int]),
     "desman_get_group_stats": (C.c_int, [_ctx, _p64]),
     "desman_get_esum_store": (C.c_int, [_ctx, _p64]),
+    "desman_batch_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(_p64), C.POINTER(C.c_int), C.c_int]),
+    "desman_batch_sample_tau": (C.c_int, [C.c_void_p, C.POINTER(_p64), C.POINTER(_pd), _pd, C.c_int, C.POINTER(C.c_int)]),
+    "desman_batch_destroy": (C.c_int, [C.c_void_p]),
     "desman_sample_tau_fix": (C.c_int, [_ctx, C.c_int, _pd, C.POINTER(C.c_int64)]),
     "desman_debug_screen": (C.c_int, [_ctx, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "desman_nmft_last_timing": (C.c_int, [_pd, C.POINTER(C.c_int)]),

@@ -1030,7 +1030,7 @@ static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, boo
     p.tier_counts = c->tiers;
     p.work = nullptr; p.singles = nullptr; p.gctl = nullptr; p.site_slot = nullptr;
     p.img_site = nullptr; p.site_row = nullptr; p.need_img = 0;
-    p.g_begin = g_begin; p.logp_out = logp_out; p.skip_listed = 0;
+    p.g_begin = g_begin; p.logp_out = logp_out; p.skip_listed = 0; p.prob_off = nullptr;
     int gb = 8, gwarps = 1;
     if (p.agg.N && group_config(c, &gb, &gwarps)) {
         TauGroupParams q;
@@ -1977,3 +1977,138 @@ extern "C" int c_sample_tau(long *anTau, double *adPi, double *adEta, long *anVa
         if (after[i] != before[i]) { anTau[i * 4 + before[i]] = 0; anTau[i * 4 + after[i]] = 1; }   // :178-184
     return (int)nchange;
 }
+
+// ------------------------------------------------------------------------------------------ batched reference ABI
+// Eta_Sampler (Eta_Sampler.py:355-369, :430-446) calls sample_tau once per gene and iteration, each call with its own masked
+// gamma and a few dozen to a few thousand sites: thousands of tiny launches, each re-uploading its counts.  A batch keeps the
+// counts of all genes resident and runs ONE launch per iteration over all of them; draw for draw (one process-global MT19937
+// stream, gene after gene, V_k*G words each) the results are those of the sequence of c_sample_tau calls it replaces.
+struct desman_batch {
+    int nprob = 0, S = 0;
+    std::vector<int> off;            // [nprob + 1] first site of every problem
+    int4 *counts = nullptr;
+    uint8_t *tau = nullptr;
+    double *gamma = nullptr, *eta = nullptr;
+    int *d_off = nullptr;
+    unsigned long long *nchange = nullptr;
+    size_t cap_vg = 0, cap_g = 0;
+    int maxV = 0;
+};
+
+extern "C" int desman_batch_create(desman_batch **out, int nprob, const int64_t *const *variants, const int *nV, int nS)
+{
+    if (!g_legacy) return fail(DESMAN_ESTATE, "desman_batch_create before c_initRNG");
+    if (!out || nprob <= 0 || !variants || !nV || nS <= 0) return fail(DESMAN_EINVAL, "desman_batch_create: bad arguments");
+    desman_ctx *c = g_legacy;
+    CU(cudaSetDevice(c->device));
+    desman_batch *b = new desman_batch();
+    b->nprob = nprob; b->S = nS; b->off.assign(nprob + 1, 0);
+    for (int k = 0; k < nprob; k++) {
+        if (nV[k] < 0 || (nV[k] > 0 && !variants[k])) { delete b; return fail(DESMAN_EINVAL, "desman_batch_create: problem %d", k); }
+        b->off[k + 1] = b->off[k] + nV[k];
+        if (nV[k] > b->maxV) b->maxV = nV[k];
+    }
+    const size_t Vt = (size_t)b->off[nprob];
+    if (Vt == 0) { delete b; return fail(DESMAN_EINVAL, "desman_batch_create: no sites"); }
+    std::vector<int4> h(Vt * nS);
+    long long bad = -1, big = 0;
+    for (int k = 0; k < nprob; k++) {
+        const int64_t *src = variants[k];
+        int4 *dst = h.data() + (size_t)b->off[k] * nS;
+        for (size_t i = 0; i < (size_t)nV[k] * nS; i++) {
+            const int64_t a0 = src[4 * i], a1 = src[4 * i + 1], a2 = src[4 * i + 2], a3 = src[4 * i + 3];
+            if ((a0 | a1 | a2 | a3 | (DESMAN_MAX_COUNT - a0) | (DESMAN_MAX_COUNT - a1) | (DESMAN_MAX_COUNT - a2) | (DESMAN_MAX_COUNT - a3)) < 0) bad = k;
+            big |= a0 | a1 | a2 | a3;
+            dst[i] = make_int4((int)a0, (int)a1, (int)a2, (int)a3);
+        }
+    }
+    if (bad >= 0) { delete b; return fail(DESMAN_EINVAL, "counts of problem %lld must be in [0, %d] per (v,s,base) cell", bad, DESMAN_MAX_COUNT); }
+    CU(cudaMalloc(&b->counts, Vt * nS * sizeof(int4)));
+    CU(cudaMalloc(&b->d_off, (nprob + 1) * sizeof(int)));
+    CU(cudaMalloc(&b->eta, 16 * sizeof(double)));
+    CU(cudaMalloc(&b->nchange, sizeof(unsigned long long)));
+    CU(cudaMemcpyAsync(b->counts, h.data(), Vt * nS * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(b->d_off, b->off.data(), (nprob + 1) * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *out = b;
+    return DESMAN_OK;
+}
+
+extern "C" int desman_batch_destroy(desman_batch *b)
+{
+    if (!b) return DESMAN_OK;
+    for (void *q : {(void *)b->counts, (void *)b->tau, (void *)b->gamma, (void *)b->eta, (void *)b->d_off, (void *)b->nchange}) if (q) cudaFree(q);
+    delete b;
+    return DESMAN_OK;
+}
+
+// tau[k]: int64 one-hot [V_k][G][4], mutated in place; pi[k]: [S][G] (columns may be exactly 0.0: masked strains); eta [4][4];
+// nchange[k] = flips of problem k.  Equivalent to c_sample_tau(tau[k], pi[k], eta, variants[k], ...) for k = 0 .. nprob-1.
+extern "C" int desman_batch_sample_tau(desman_batch *b, int64_t *const *tau, const double *const *pi, const double *eta, int nG,
+                                       int *nchange)
+{
+    if (!g_legacy) return fail(DESMAN_ESTATE, "desman_batch_sample_tau before c_initRNG");
+    if (!b || !tau || !pi || !eta || nG < 1 || nG > DESMAN_MAX_G) return fail(DESMAN_EINVAL, "desman_batch_sample_tau: bad arguments");
+    desman_ctx *c = g_legacy;
+    CU(cudaSetDevice(c->device));
+    const int S = b->S, np = b->nprob;
+    const size_t Vt = (size_t)b->off[np], nvg = Vt * nG, ng = (size_t)np * S * nG;
+    for (int i = 0; i < 16; i++) if (!(eta[i] > 0.0)) return fail(DESMAN_EINVAL, "eta[%d] = %g must be > 0", i, eta[i]);
+    std::vector<double> hg(ng);
+    for (int k = 0; k < np; k++) {
+        if (b->off[k + 1] == b->off[k]) continue;
+        for (int s2 = 0; s2 < S; s2++) {
+            double row = 0.0;
+            for (int g = 0; g < nG; g++) {
+                const double x = pi[k][(size_t)s2 * nG + g];
+                if (!(x >= 0.0)) return fail(DESMAN_EINVAL, "problem %d: gamma[%d][%d] = %g must be >= 0", k, s2, g, x);
+                row += x;
+                hg[((size_t)k * S + s2) * nG + g] = x;
+            }
+            if (!(row > 0.0)) return fail(DESMAN_EINVAL, "problem %d: gamma row %d has no positive entry", k, s2);
+        }
+    }
+    std::vector<uint8_t> before(nvg), after(nvg);
+    for (int k = 0; k < np; k++) {
+        const size_t n = (size_t)(b->off[k + 1] - b->off[k]) * nG;
+        if (n) RET(onehot_to_index(tau[k], n, before.data() + (size_t)b->off[k] * nG));
+    }
+    if (nvg > b->cap_vg) { if (b->tau) cudaFree(b->tau); b->tau = nullptr; CU(cudaMalloc(&b->tau, nvg)); b->cap_vg = nvg; }
+    if (ng > b->cap_g) { if (b->gamma) cudaFree(b->gamma); b->gamma = nullptr; CU(cudaMalloc(&b->gamma, ng * sizeof(double))); b->cap_g = ng; }
+    CU(cudaMemcpyAsync(b->tau, before.data(), nvg, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(b->gamma, hg.data(), ng * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(b->eta, eta, 16 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(b->nchange, 0, sizeof(unsigned long long), c->stream));
+    // the V_total * G words of the stream, in problem order (what the sequence of calls would have consumed)
+    const int64_t V_keep = c->V, Vt_keep = c->V_total, v0_keep = c->v0;
+    const int G_keep = c->G;
+    c->V = (int64_t)Vt; c->V_total = (int64_t)Vt; c->v0 = 0; c->G = nG;
+    int rc = gen_mt_words(c);
+    c->V = V_keep; c->V_total = Vt_keep; c->v0 = v0_keep; c->G = G_keep;
+    RET(rc);
+    TauParams p;
+    memset(&p, 0, sizeof(p));
+    p.counts = b->counts; p.tau = b->tau; p.gamma = b->gamma; p.eta = b->eta; p.words = c->words;
+    p.seed = c->seed; p.sweep = 0; p.v0 = 0; p.V = (int)Vt; p.S = S; p.G = nG;
+    p.nchange = b->nchange; p.tau_last = nullptr; p.exact_only = c->tau_exact; p.prob_off = b->d_off;
+    const size_t smem = tau_smem_bytes(S, nG);
+    if (smem > 227 * 1024) return fail(DESMAN_EINVAL, "S*G too large for the shared-memory tile (%zu bytes)", smem);
+    CU(cudaFuncSetAttribute(tau_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int gx = (b->maxV + TAU_WARPS - 1) / TAU_WARPS;
+    if (gx > 32) gx = 32;
+    if (gx < 1) gx = 1;
+    tau_sample_kernel<<<dim3((unsigned)gx, (unsigned)np), TAU_WARPS * 32, smem, c->stream>>>(p);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(after.data(), b->tau, nvg, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < np; k++) {
+        int n = 0;
+        int64_t *t = tau[k];
+        const size_t lo = (size_t)b->off[k] * nG, hi = (size_t)b->off[k + 1] * nG;
+        for (size_t i = lo; i < hi; i++)
+            if (after[i] != before[i]) { t[(i - lo) * 4 + before[i]] = 0; t[(i - lo) * 4 + after[i]] = 1; n++; }   // :178-184
+        if (nchange) nchange[k] = n;
+    }
+    return DESMAN_OK;
+}
+

@@ -58,6 +58,10 @@ struct TauParams {
     int g_begin;
     double *logp_out;
     int skip_listed;         // 1: when the work list is valid this launch does nothing (tau_open_kernel walks the list)
+    // batched small problems (Eta_Sampler.sampleTauC: one call per gene, each with its own masked gamma; Eta_Sampler.py:355-369):
+    // the sites of all problems are concatenated, prob_off[k] .. prob_off[k+1] are the sites of problem k, gamma holds one
+    // [S][G] matrix per problem and blockIdx.y is the problem a CTA works on; nullptr: one problem
+    const int *prob_off;
     unsigned long long *tier_counts;  // [3] += draws decided by tier 1 / 2 / 3 (or nullptr)
 };
 
@@ -315,10 +319,11 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     if (threadIdx.x == 0) { gmin_bits = 0x7f800000u; emin_bits = 0x7f800000u; }
     __syncthreads();
+    const double *gamma_k = p.prob_off ? p.gamma + (size_t)blockIdx.y * S * G : p.gamma;   // this CTA's problem
     float gmin_l = __int_as_float(0x7f800000);
     for (int i = threadIdx.x; i < G * Sp; i += blockDim.x) {
         const int g = i / Sp, s = i - g * Sp;
-        const double x = (s < S) ? p.gamma[(size_t)s * G + g] : 0.0;
+        const double x = (s < S) ? gamma_k[(size_t)s * G + g] : 0.0;
         gT[i] = x;
         gT32[i] = (float)x;
         if (s < S && x > 0.0) gmin_l = fminf(gmin_l, (float)x);     // masked strains (gamma == 0): q = P there
@@ -363,7 +368,9 @@ __global__ void __launch_bounds__(TAU_WARPS * 32, 3) tau_sample_kernel(TauParams
         nsite = nwork + p.gctl[GC_NSINGLES];
     }
 
-    for (int i = gw; i < nsite; i += nw) {
+    int i_begin = gw, i_end = nsite;
+    if (p.prob_off) { i_begin = p.prob_off[blockIdx.y] + gw; i_end = p.prob_off[blockIdx.y + 1]; }
+    for (int i = i_begin; i < i_end; i += nw) {
         int v = i;
         uint32_t todo = 0xffffffffu;                 // strains the screening pass did not decide
         bool screened = false;                       // todo comes from the gap test of the screening pass

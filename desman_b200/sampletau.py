@@ -89,3 +89,60 @@ def sample_tau(tau, pi, eta, variants):
     if n < 0:
         raise _lib.DesmanB200Error("c_sample_tau failed: " + _lib.last_error())
     return n
+
+
+class Batch:
+    """Many small sample_tau problems per launch (an addition to the reference module): what Eta_Sampler.sampleTauC does gene by
+    gene (Eta_Sampler.py:355-369, :430-446), with the counts of all genes resident on the device.
+
+        b = sampletau.Batch([variants_gene0, variants_gene1, ...])        # int64 [V_k,S,4] each, uploaded once
+        nchange = b.sample_tau([tau_gene0, ...], [gammaR_gene0, ...], epsilon)   # one launch; tau arrays mutated in place
+
+    Draw for draw (the process-global MT19937 stream of setRNG, gene after gene) the result equals
+    [sample_tau(tau_k, pi_k, eta, variants_k) for k in range(len(variants))]."""
+
+    def __init__(self, variants):
+        self._var = []
+        for v in variants:
+            _check(v, "variants", 3, np.int64, "long")
+            self._var.append(v)
+        if not self._var:
+            raise ValueError("Batch needs at least one problem")
+        self.S = self._var[0].shape[1]
+        if any(v.shape[1] != self.S or v.shape[2] != 4 for v in self._var):
+            raise ValueError("every problem must be [V_k,%d,4]" % self.S)
+        n = len(self._var)
+        ptrs = (_lib._p64 * n)(*[v.ctypes.data_as(_lib._p64) for v in self._var])
+        nV = (C.c_int * n)(*[v.shape[0] for v in self._var])
+        self._h = C.c_void_p()
+        if _lib.lib().desman_batch_create(C.byref(self._h), n, ptrs, nV, self.S) != 0:
+            raise _lib.DesmanB200Error("desman_batch_create failed: " + _lib.last_error())
+
+    def sample_tau(self, taus, pis, eta):
+        n = len(self._var)
+        if len(taus) != n or len(pis) != n:
+            raise ValueError("one tau and one pi per problem")
+        _check(eta, "eta", 2, np.float64, "double")
+        G = pis[0].shape[1]
+        for t, pi, v in zip(taus, pis, self._var):
+            _check(t, "tau", 3, np.int64, "long")
+            _check(pi, "pi", 2, np.float64, "double")
+            if t.shape != (v.shape[0], G, 4) or pi.shape != (self.S, G):
+                raise ValueError("tau must be [V_k,%d,4] and pi [%d,%d] for every problem" % (G, self.S, G))
+        tp = (_lib._p64 * n)(*[t.ctypes.data_as(_lib._p64) for t in taus])
+        pp = (_lib._pd * n)(*[x.ctypes.data_as(_lib._pd) for x in pis])
+        out = (C.c_int * n)()
+        if _lib.lib().desman_batch_sample_tau(self._h, tp, pp, eta.ctypes.data_as(_lib._pd), G, out) != 0:
+            raise _lib.DesmanB200Error("desman_batch_sample_tau failed: " + _lib.last_error())
+        return list(out)
+
+    def close(self):
+        if self._h:
+            _lib.lib().desman_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

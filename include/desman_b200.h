@@ -149,6 +149,16 @@ int desman_debug_screen(desman_ctx *ctx, float *D /*V*3G*/, uint32_t *mask /*V*/
  * counter on by n (loops over desman_mu_stats / desman_draw_gamma_eta, which leave it where it is). */
 int desman_sample_tau_fix(desman_ctx *ctx, int H, double *logp /*V*4*/, int64_t *nchange);
 
+/* Batched form of the reference ABI for callers that make many small sample_tau calls per iteration (Eta_Sampler.sampleTauC,
+ * Eta_Sampler.py:355-369,:430-446: one call per gene, each with its own masked gamma).  The counts of all problems are
+ * uploaded once and stay resident; desman_batch_sample_tau is ONE launch over all of them and, draw for draw (one
+ * process-global MT19937 stream, problem after problem), equals the sequence of c_sample_tau calls it replaces.  Needs c_initRNG. */
+typedef struct desman_batch desman_batch;
+int desman_batch_create(desman_batch **out, int nprob, const int64_t *const *variants /*[nprob] -> [V_k][S][4]*/, const int *nV, int nS);
+int desman_batch_sample_tau(desman_batch *b, int64_t *const *tau /*[nprob] -> one-hot [V_k][G][4], in place*/,
+                            const double *const *pi /*[nprob] -> [S][G]*/, const double *eta /*[4][4]*/, int nG, int *nchange /*[nprob]*/);
+int desman_batch_destroy(desman_batch *b);
+
 /* Multi-GPU: one context per process/GPU, sites sharded by desman_set_counts(v0, V_total).
  * desman_comm_unique_id fills a 128-byte NCCL id on rank 0; every rank calls desman_comm_init. */
 int desman_comm_unique_id(char id[128]);

@@ -422,3 +422,61 @@ def test_sampler_keeps_both_streams_across_rng_mode_switches(oracle_mod):
     assert len(set(eng_ids)) == 1
     hs.close()
     sampletau.freeRNG()
+
+
+def test_batched_small_calls_replay_an_eta_sampler_sequence(oracle_mod):
+    """Eta_Sampler.calcTauStar-style traffic (Eta_Sampler.py:430-446): every iteration calls sample_tau once per gene, each with
+    its own masked gamma (maskGamma, :147-157).  sampletau.Batch keeps the counts of all genes on the device and runs ONE launch
+    per iteration; tau and nchange of every gene must equal the sequence of calls to the reference's own C (oracle/_ref; the
+    oracle's restatement where that library did not travel), through several iterations of the one MT19937 stream."""
+    import ctypes as C
+    from desman_b200 import sampletau
+    rng = np.random.default_rng(11)
+    G, S, seed, n_iter = 5, 24, 20240611, 4
+    sizes = [37, 1, 260, 8, 96, 15, 530, 64]                       # genes of very different lengths
+    genes = []
+    for k, V in enumerate(sizes):
+        p = synth_problem(V, S, G, depth=12.0, seed=100 + k, ambiguous=True)
+        genes.append(dict(counts=p["counts"], tau=onehot(p["tau0"]), tau_ref=onehot(p["tau0"])))
+    gamma = rng.dirichlet(np.ones(G), size=S)
+    eta_gene = rng.random((len(sizes), G)) < 0.7                   # presence / absence of every strain in every gene
+    eta_gene[:, 0] = True
+    eps = 0.96 * np.identity(4) + 0.01
+    use_ref = oracle_mod.have_ref()
+    if use_ref:
+        R = oracle_mod.RefSampleTau(seed)
+    else:
+        st = oracle_mod.MT19937()
+        oracle_mod.lib().oracle_mt_seed(C.byref(st), seed)
+    sampletau.initRNG(); sampletau.setRNG(seed)
+    b = sampletau.Batch([g["counts"] for g in genes])
+    for it in range(n_iter):
+        pis = []
+        for k, g in enumerate(genes):
+            gR = gamma.copy()
+            gR[:, ~eta_gene[k]] = 0.0
+            gR /= gR.sum(1)[:, None]
+            pis.append(np.ascontiguousarray(gR))
+        n_gpu = b.sample_tau([g["tau"] for g in genes], pis, eps)
+        for k, g in enumerate(genes):
+            if use_ref:
+                n_ref = R.sample_tau(g["tau_ref"], pis[k], eps, g["counts"])
+            else:
+                n_ref = oracle_mod.lib().oracle_sample_tau_mt(
+                    g["tau_ref"].ctypes.data_as(oracle_mod._p64), oracle_mod._f64(pis[k])[1], oracle_mod._f64(eps)[1],
+                    oracle_mod._i64(g["counts"])[1], sizes[k], G, S, C.byref(st))
+            assert n_gpu[k] == n_ref, (it, k)
+            assert np.array_equal(g["tau"], g["tau_ref"]), (it, k)
+        gamma = rng.dirichlet(np.ones(G), size=S)
+    # the stream goes on where the batch left it: a plain call afterwards still matches
+    t1, t2 = genes[2]["tau"], genes[2]["tau_ref"]
+    n1 = sampletau.sample_tau(t1, gamma, eps, genes[2]["counts"])
+    if use_ref:
+        n2 = R.sample_tau(t2, gamma, eps, genes[2]["counts"])
+        R.close()
+    else:
+        n2 = oracle_mod.lib().oracle_sample_tau_mt(t2.ctypes.data_as(oracle_mod._p64), oracle_mod._f64(gamma)[1], oracle_mod._f64(eps)[1],
+                                                   oracle_mod._i64(genes[2]["counts"])[1], sizes[2], G, S, C.byref(st))
+    assert n1 == n2 and np.array_equal(t1, t2)
+    b.close()
+    sampletau.freeRNG()

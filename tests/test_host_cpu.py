@@ -93,6 +93,9 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["impl"] == "reference" and d["unit"] == "sweeps/s" and d["higher_is_better"] is True and d["steps"] == 2
     assert d["metric"].startswith("Gibbs sweeps/sec") and d["config"]["workload"].startswith("BASELINE config C3")
     assert d["value"] > 0 and d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["cores"] >= 1
-    assert d["cpu_baseline"]["kind"] in ("reference", "port")
+    # "reference-tau+port": tau by the reference's own c_sample_tau.c (oracle/_ref), the numpy steps by their C port
+    assert d["cpu_baseline"]["kind"] in ("reference-tau+port", "port")
+    import bench
+    assert d["config"]["workload"] == bench.workload_name("c3", 100000, 64, 8)          # the string our arm prints too
     assert d["e2e"] == {"value": d["value"], "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
