@@ -124,8 +124,8 @@ struct desman_ctx {
     uint8_t *tau = nullptr, *tau_star = nullptr;
     double *gamma = nullptr, *eta = nullptr, *eta_new = nullptr, *gamma_star = nullptr, *eta_star = nullptr;
     unsigned long long *stats = nullptr;     // [S*G + 16] sum_mu | esum
-    unsigned long long *red_base = nullptr;  // [2][2] two parities of ...
-    unsigned long long *red_i = nullptr;     // [2] fixed-point sum n*log p | nchange of the current sweep (= red_base + 2*parity)
+    unsigned long long *red_base = nullptr;  // [2][4] two parities of ...
+    unsigned long long *red_i = nullptr;     // [4] fixed-point sum n*log p | nchange | upkeep wishes | - of the current sweep (= red_base + 4*parity)
     double *scal = nullptr;                  // [4] lp_star, iter_star, ll, lp
     int *flag = nullptr;
     uint32_t *tau_cnt = nullptr, *tau_last = nullptr;
@@ -319,7 +319,8 @@ extern "C" int desman_ctx_create(desman_ctx **out, int device, uint64_t seed, in
     CU(dmalloc(c, &c->eta, 16 * sizeof(double)));
     CU(dmalloc(c, &c->eta_new, 16 * sizeof(double)));
     CU(dmalloc(c, &c->eta_star, 16 * sizeof(double)));
-    CU(dmalloc(c, &c->red_base, 4 * sizeof(unsigned long long)));
+    CU(dmalloc(c, &c->red_base, 8 * sizeof(unsigned long long)));
+    CU(cudaMemsetAsync(c->red_base, 0, 8 * sizeof(unsigned long long), c->stream));
     c->red_i = c->red_base;
     CU(dmalloc(c, &c->scal, 4 * sizeof(double)));
     CU(dmalloc(c, &c->flag, sizeof(int)));
@@ -776,6 +777,7 @@ static MuAggParams agg_params(desman_ctx *c, const double *gamma, const double *
     p.t = agg_table(c);
     p.sum_mu = c->stats; p.esum = c->stats + (size_t)c->S * c->G;
     p.ll_scale = c->ll_scale; p.ll_fx = c->red_i;
+    p.upkeep = 0; p.gctl_u = nullptr; p.V_local_u = (long long)c->V; p.agg_limit_u = (unsigned int)(c->V + c->V / 4);
     p.eta_commit = nullptr;
     p.classM = (c->G <= MUC_MAX_G && c->classM_G == c->G && c->classM_S == c->S) ? c->agg_classM : nullptr;
     return p;
@@ -935,10 +937,12 @@ static int sync_table(desman_ctx *c, bool deferred_star_copy = false)
 }
 
 // sum n*log p of the current device tau under (gamma, eta) into red_i[0] (fixed point, cleared by sync_table)
-static int launch_ll(desman_ctx *c, const double *gamma, const double *eta, double *eta_commit = nullptr)
+static int launch_ll(desman_ctx *c, const double *gamma, const double *eta, double *eta_commit = nullptr, bool upkeep = false)
 {
     MuAggParams p = agg_params(c, gamma, eta);
     p.eta_commit = eta_commit;
+    p.upkeep = upkeep ? 1 : 0;
+    p.gctl_u = group_config(c, nullptr, nullptr) ? c->grp_gctl : nullptr;
     {
         KSpan k(c, DESMAN_K_FINAL);
         CU(launch_k(c, ll_table_kernel, c->sm_count * 4, 256, 0, p));       // ~one (slot, 32 samples) item per warp: a latency chain
@@ -1162,7 +1166,7 @@ static int exchange_sum(desman_ctx *c, unsigned long long *data, int words, unsi
     p.rank = c->rank; p.nranks = c->nranks; p.words = words; p.cap_words = c->xch_cap_words;
     p.data2 = data2; p.words2 = words2;
     p.seq = ++c->xch_seq; p.data = data; p.err = c->xch_err;
-    exchange_sum_kernel<<<1, 512, 0, c->stream>>>(p);
+    CU(launch_k(c, exchange_sum_kernel, 1, 512, 0, p));
     CU(cudaGetLastError());
     return DESMAN_OK;
 }
@@ -1174,24 +1178,24 @@ static int allreduce_stats(desman_ctx *c, unsigned long long *red2 = nullptr)
     if (c->nranks <= 1) return DESMAN_OK;
     KSpan k(c, DESMAN_K_OTHER);
     const size_t n = (size_t)c->S * c->G + 16;
-    if (c->xch_ok && (int)n + 2 <= c->xch_cap_words) return exchange_sum(c, c->stats, (int)n, red2, red2 ? 2 : 0);
+    if (c->xch_ok && (int)n + 3 <= c->xch_cap_words) return exchange_sum(c, c->stats, (int)n, red2, red2 ? 3 : 0);
     if (red2 && g_nccl.GroupStart && g_nccl.GroupEnd) {
         NC(g_nccl.GroupStart());
         NC(g_nccl.AllReduce(c->stats, c->stats, n, NCCL_UINT64, NCCL_SUM, c->comm, c->stream));
-        NC(g_nccl.AllReduce(red2, red2, 2, NCCL_INT64, NCCL_SUM, c->comm, c->stream));
+        NC(g_nccl.AllReduce(red2, red2, 3, NCCL_INT64, NCCL_SUM, c->comm, c->stream));
         NC(g_nccl.GroupEnd());
         return DESMAN_OK;
     }
     NC(g_nccl.AllReduce(c->stats, c->stats, n, NCCL_UINT64, NCCL_SUM, c->comm, c->stream));
-    if (red2) NC(g_nccl.AllReduce(red2, red2, 2, NCCL_INT64, NCCL_SUM, c->comm, c->stream));
+    if (red2) NC(g_nccl.AllReduce(red2, red2, 3, NCCL_INT64, NCCL_SUM, c->comm, c->stream));
     return DESMAN_OK;
 }
 static int allreduce_red(desman_ctx *c)
 {
     if (c->nranks <= 1) return DESMAN_OK;
     KSpan k(c, DESMAN_K_OTHER);
-    if (c->xch_ok) return exchange_sum(c, c->red_i, 2);      // two's complement sums: same bits as the int64 all-reduce
-    NC(g_nccl.AllReduce(c->red_i, c->red_i, 2, NCCL_INT64, NCCL_SUM, c->comm, c->stream));
+    if (c->xch_ok) return exchange_sum(c, c->red_i, 3);      // two's complement sums: same bits as the int64 all-reduce
+    NC(g_nccl.AllReduce(c->red_i, c->red_i, 3, NCCL_INT64, NCCL_SUM, c->comm, c->stream));
     return DESMAN_OK;
 }
 
@@ -1240,7 +1244,7 @@ static int launch_finalize_only(desman_ctx *c, const unsigned long long *red, co
 static int launch_finalize(desman_ctx *c, const double *gamma, const double *eta, int it, int star_mode, const StoreBufs &sb,
                            bool store_ge, double *eta_commit = nullptr, bool copy_now = true)
 {
-    RET(launch_ll(c, gamma, eta));
+    RET(launch_ll(c, gamma, eta, nullptr, it >= 0));
     RET(allreduce_red(c));
     return launch_finalize_only(c, c->red_i, gamma, eta, it, star_mode, sb, store_ge, eta_commit, copy_now);
 }
@@ -1605,7 +1609,7 @@ extern "C" int desman_update(desman_ctx *c, int n_iter, double *gamma_store, dou
     for (int it = 0; it < n_iter; it++) {
         sweep_begin(c);
         unsigned long long *red_prev = c->red_i;
-        if (lagged) c->red_i = c->red_base + 2 * (it & 1);
+        if (lagged) c->red_i = c->red_base + 4 * (it & 1);
         // clears the accumulators; table upkeep when pending; the MAP snapshot of the previous sweep (single rank: under
         // sharding the bookkeeping of sweep it-1 follows the exchange below and keeps its own copy launch)
         RET(sync_table(c, !lagged && it > 0));
@@ -1616,7 +1620,7 @@ extern "C" int desman_update(desman_ctx *c, int n_iter, double *gamma_store, dou
         } else RET(allreduce_stats(c));
         RET(launch_draw(c, c->stats, c->gamma, c->eta_new, c->esum_store + (size_t)it * 16));   // sampleGamma (:342) + sampleEta's draw (:347)
         if (!c->fixed_tau) RET(launch_tau(c, c->gamma, c->eta, true, true, (uint32_t)it));       // sample_tau (:345), old eta (nchange cleared by sync_table)
-        if (lagged) RET(launch_ll(c, c->gamma, c->eta_new, c->eta));     // eta <- new (:347); sum n*log p of sweep it, reduced with the next exchange
+        if (lagged) RET(launch_ll(c, c->gamma, c->eta_new, c->eta, true));     // eta <- new (:347); sum n*log p of sweep it, reduced with the next exchange
         else RET(launch_finalize(c, c->gamma, c->eta_new, it, 0, sb, true, c->eta, false));   // eta <- new (:347); ll, lp, stores, star (:349-358)
         sweep_end(c);
         c->sweep++;

@@ -39,6 +39,7 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 
 __global__ void __launch_bounds__(512) exchange_sum_kernel(XchParams p)
 {
+    pdl_enter();         // a link of the sweep's dependent chain (common.cuh): scheduled under the tail of the statistics kernel
     const int n = p.nranks, W1 = p.words, W = p.words + p.words2;
     const size_t slot_off = ((size_t)(p.seq & 1ull) * n + p.rank) * p.cap_words;
     // 1. my contribution into every mailbox (peer stores over NVLink; the local one is a plain store)

@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(MAINT_THREADS) table_maintain_kernel(MaintPara
     const bool do_rebuild = t.ctl[0] != 0;
     const bool do_regroup = gctl && gctl[GC_CALM] && (do_rebuild || gctl[GC_REGROUP] || !gctl[GC_HAVE]);
     for (size_t i = gtid; i < (size_t)p.nzero64; i += gsz) p.zero64[i] = 0ull;
-    if (gtid < 2) p.red_i[gtid] = 0ull;
+    if (gtid < 4) p.red_i[gtid] = 0ull;
     if (gtid >= 4 && gtid < AGG_CTL_WORDS) t.ctl[gtid] = 0;          // work cursors of mu_binomial_kernel
     if (gtid == 0 && gctl) { gctl[GC_NWORK] = 0; gctl[GC_CURSOR] = 0; }
     if (p.star_flag && *p.star_flag) {

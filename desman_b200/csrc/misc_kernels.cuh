@@ -228,20 +228,16 @@ __global__ void __launch_bounds__(256) finalize_sweep_kernel(FinalParams p)
 #endif
     if (threadIdx.x == 0) {
         const double ll = p.ll_const + (double)p.red_i[0] * p.ll_inv_scale, lp = ll + prior;
-        if (p.agg_ctl) {
-            // pattern table upkeep: every flipped (v,g) may have left a stale slot behind.  Ask for a rebuild when the
-            // stale slots could outnumber half the live ones, or when the slot array is close to its capacity bound.
-            const long long stale = stale0 + (p.it >= 0 ? p.red_i[1] : 0);
-            const long long live = used > stale ? used - stale : 0;
-            p.agg_ctl[3] = (int)(stale > 0x3fffffff ? 0x3fffffff : stale);
-            if (stale > live / 2 + 512 || used > (long long)p.agg_limit) p.agg_ctl[0] = 1;
-        }
+        // upkeep wishes of the sweep (ll_table_kernel; summed over the ranks of a sharded chain by the exchange): a table rebuild
+        // (which implies a regroup) and / or a regroup of the site groups, on every rank in the same sweep
+        const unsigned long long wish = (unsigned long long)p.red_i[2];
+        if (p.agg_ctl && (wish >> 16)) p.agg_ctl[0] = 1;
         if (p.gctl && p.it >= 0) {
-            // screening pass upkeep: it pays off while few sites flip; regroup when orphans (sites that left their group) pile up
+            // the screening pass pays off while few sites flip
             p.gctl[GC_CALM] = (double)p.red_i[1] <= p.V_total / 16.0;
-            const long long lim = p.V_local / 128 > 64 ? p.V_local / 128 : 64;
-            if (orphans > lim) p.gctl[GC_REGROUP] = 1;
+            if (wish & 0xffffull) p.gctl[GC_REGROUP] = 1;
         }
+        (void)stale0; (void)used; (void)orphans;
         p.scal[2] = ll; p.scal[3] = lp;
         if (p.it >= 0) {
             if (p.ll_store) p.ll_store[p.it] = ll;

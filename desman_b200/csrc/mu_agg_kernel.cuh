@@ -70,6 +70,14 @@ struct MuAggParams {
     double ll_scale;             // 2^k of the fixed-point log-likelihood accumulator
     unsigned long long *ll_fx;   // += llrint(sum n*log p * 2^k)  (two's complement)
     double *eta_commit;          // ll_table_kernel: if non-null, eta_commit[0..15] = eta (the chain's eta <- eta_new, :347)
+    // Upkeep wishes of this rank, formed by ll_table_kernel at the end of a sweep and written to ll_fx[2] (the word travels
+    // with [ll, nchange] through the per-sweep exchange, so that every rank of a sharded chain regroups / rebuilds its table in
+    // the SAME sweep: unsynchronised, some rank was regrouping in every other sweep at 8 ranks and all the others waited for it):
+    // + 1 if the orphans of the site groups piled up, + 65536 if the pattern table wants a rebuild.  upkeep = 0: none.
+    int upkeep;
+    int *gctl_u;                 // site-group control words or null
+    long long V_local_u;
+    unsigned int agg_limit_u;
 };
 
 __device__ __forceinline__ unsigned int mix_code(unsigned long long x)
@@ -132,6 +140,20 @@ __global__ void __launch_bounds__(256) ll_table_kernel(MuAggParams p)
     if (threadIdx.x < 16) {
         eta_s[threadIdx.x] = p.eta[threadIdx.x];
         if (blockIdx.x == 0 && p.eta_commit) p.eta_commit[threadIdx.x] = eta_s[threadIdx.x];
+    }
+    if (p.upkeep && blockIdx.x == 0 && threadIdx.x == 32) {
+        // every flipped (v,g) of this sweep (ll_fx[1], still this rank's own count) may have left a stale slot behind: ask for a
+        // rebuild when the stale slots could outnumber half the live ones, or when the slot array is close to its capacity
+        // bound; ask for a regroup when the orphans piled up
+        const long long stale = (long long)p.t.ctl[3] + (long long)p.ll_fx[1], used = (long long)*p.t.nslots;
+        const long long live = used > stale ? used - stale : 0;
+        p.t.ctl[3] = (int)(stale > 0x3fffffff ? 0x3fffffff : stale);
+        unsigned long long wish = (stale > live / 2 + 512 || used > (long long)p.agg_limit_u) ? 65536ull : 0ull;
+        if (p.gctl_u) {
+            const long long lim = p.V_local_u / 128 > 64 ? p.V_local_u / 128 : 64;
+            if ((long long)p.gctl_u[GC_ORPHANS] > lim) wish += 1ull;
+        }
+        p.ll_fx[2] = wish;
     }
     __syncthreads();
     const int S = p.S, G = p.G, lane = threadIdx.x & 31;

@@ -1,4 +1,5 @@
-timeout 900 python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -4
+# tools/multi_check.sh -- multi-GPU tests + the C3 weak-scaling lines (run under `gpurun --gpus 4`)
+timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
 for n in 1 2 4; do
   if [ $n -eq 1 ]; then python bench.py --gpus 1 --steps 200 --warmup 5 --no-cpu --no-nmft > gpurun_out/r2_scale_$n.json 2> gpurun_out/r2_scale_$n.err
   else python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2950$n bench.py --gpus $n --steps 200 --warmup 5 --no-cpu --no-nmft > gpurun_out/r2_scale_$n.json 2> gpurun_out/r2_scale_$n.err; fi
