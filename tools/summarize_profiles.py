@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Turns the scratch ncu outputs in gpurun_out/ into the tracked summaries under profiles/ (round 1)."""
+"""Turns the scratch ncu outputs in gpurun_out/ into the tracked summaries under profiles/ (tag r1, r1b, r1c, r2, ...)."""
 import collections
 import csv
 import json
@@ -84,7 +84,9 @@ if __name__ == "__main__":
     d = details(os.path.join(g, "prof_%s_final.ncu-rep" % tag), tag)
     traffic = {k.replace("_kernel", "").replace("<8>", "").replace("<2>", ""): v["dram_bytes"] for k, v in d.items()}
     # the steps bench.py reports: tau update = screening pass + per-site kernel; mu/E statistics = class split + within-class split
-    if "tau_group_mma" in traffic:
+    if "tau_group_tc" in traffic:        # round 2: tensor-memory screening pass + the kernels that walk its work list
+        traffic["tau_update"] = traffic["tau_group_tc"] + traffic.get("tau_open", 0.0) + traffic.get("tau_sample", 0.0)
+    elif "tau_group_mma" in traffic:
         traffic["tau_update"] = traffic["tau_group_mma"] + traffic.get("tau_sample", 0.0)
     if "mu_binomial" in traffic:
         traffic["mu_stats"] = traffic["mu_binomial"] + traffic.get("mu_class", 0.0)
