@@ -983,13 +983,14 @@ static int launch_tau_group_mma_t(desman_ctx *c, const TauGroupParams &p)
     return DESMAN_OK;
 }
 
-static int launch_tau_group_tc(desman_ctx *c, const TauGroupParams &q, float *dbg)
+static int launch_tau_group_tc(desman_ctx *c, const TauGroupParams &q, float *dbg, int early = 0)
 {
     TauGroupTcParams p;
     tc_shape(c, &p.SK, &p.nkb, &p.NC);
     p.img = c->img; p.img_site = c->img_site; p.img_nsite = c->img_nsite; p.img_rg = (long long)(c->img_cap_rows / 8);
     p.gamma = q.gamma; p.eta = q.eta; p.words = q.words; p.V = q.V; p.S = q.S; p.G = q.G;
     p.grp = q.grp; p.tier_counts = q.tier_counts; p.dbg = dbg;
+    p.early = (early && c->pdl) ? 1 : 0;
     const size_t smem = tc_layout(c->S, c->G, p.SK, p.nkb, p.NC).total;
     CU(cudaFuncSetAttribute(tau_group_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU(launch_k(c, tau_group_tc_kernel, c->sm_count, TC_THREADS, smem, p));
@@ -1013,7 +1014,7 @@ static int launch_tau_group_t(desman_ctx *c, const TauGroupParams &p, int warps)
 // screening pass runs first where groups are kept, and the per-site kernel walks its work list only.
 // red_i[1] (nchange) must be zero on entry (sync_table, or the caller's memset).
 static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, bool maintain, bool count_occupancy, uint32_t iter,
-                      int g_begin = 0, double *logp_out = nullptr)
+                      int g_begin = 0, double *logp_out = nullptr, int early = 0)
 {
     KSpan whole(c, DESMAN_K_TAU_UPDATE, 0);
     TauParams p;
@@ -1045,7 +1046,7 @@ static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, boo
         {
             KSpan k(c, DESMAN_K_TAU_GROUP);
             if (group_use_tc(c)) {
-                RET(launch_tau_group_tc(c, q, nullptr));
+                RET(launch_tau_group_tc(c, q, nullptr, early));
                 p.img_site = c->img_site; p.site_row = c->site_row; p.need_img = 1;
             } else if (group_use_mma(c)) {
                 switch (tgm_tiles(c->G)) {
@@ -1619,7 +1620,8 @@ extern "C" int desman_update(desman_ctx *c, int n_iter, double *gamma_store, dou
             RET(launch_finalize_only(c, red_prev, c->gamma, c->eta, it - 1, 0, sb, true));   // ll, lp, stores, star of sweep it-1
         } else RET(allreduce_stats(c));
         RET(launch_draw(c, c->stats, c->gamma, c->eta_new, c->esum_store + (size_t)it * 16));   // sampleGamma (:342) + sampleEta's draw (:347)
-        if (!c->fixed_tau) RET(launch_tau(c, c->gamma, c->eta, true, true, (uint32_t)it));       // sample_tau (:345), old eta (nchange cleared by sync_table)
+        // (early: the statistics and draw launches separate the screening pass from the maintenance launch that wrote its inputs)
+        if (!c->fixed_tau) RET(launch_tau(c, c->gamma, c->eta, true, true, (uint32_t)it, 0, nullptr, 1));       // sample_tau (:345), old eta (nchange cleared by sync_table)
         if (lagged) RET(launch_ll(c, c->gamma, c->eta_new, c->eta, true));     // eta <- new (:347); sum n*log p of sweep it, reduced with the next exchange
         else RET(launch_finalize(c, c->gamma, c->eta_new, it, 0, sb, true, c->eta, false));   // eta <- new (:347); ll, lp, stores, star (:349-358)
         sweep_end(c);

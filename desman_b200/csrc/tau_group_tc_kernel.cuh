@@ -60,6 +60,7 @@ struct TauGroupTcParams {
     TauGroup grp;
     unsigned long long *tier_counts;
     float *dbg;                // [V][3G] the sums D (log2 units) of every screened site, or nullptr (validation only)
+    int early;                 // 1: control words, items and image are at least two grids old (see the kernel's prologue)
 };
 
 struct TcRec { int slot, count, img0; unsigned int code_lo, code_hi; int pad[3]; };
@@ -115,6 +116,13 @@ __device__ __forceinline__ void tc_commit(uint32_t bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// one lane of a converged warp
+__device__ __forceinline__ bool tc_elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0u;
+}
 // D[tmem] (+)= A[smem desc] * B[smem desc], kind::f16 (FP16 operands, FP32 accumulation)
 __device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
 {
@@ -165,7 +173,7 @@ __device__ __forceinline__ uint64_t tc_desc(uint32_t saddr, uint32_t lbo_bytes, 
 struct TcLayout {
     int Sp, KC, N, acc_stride, tmem_cols;
     int nst, ntb, nacc;                                // ring depths: count stages, table buffers, accumulators
-    size_t off_gT, off_eta, off_eta32, off_gT32, off_wl, off_rec, off_bar, off_stage, off_table, stage_bytes, table_bytes, total;
+    size_t off_gT, off_eta, off_eta32, off_gT32, off_wl, off_rec, off_soff, off_bar, off_stage, off_table, stage_bytes, table_bytes, total;
 };
 __host__ __device__ static inline TcLayout tc_layout(int S, int G, int SK, int nkb, int NC)
 {
@@ -183,6 +191,7 @@ __host__ __device__ static inline TcLayout tc_layout(int S, int G, int SK, int n
     L.off_gT32 = o; o += sizeof(float) * (size_t)G * L.Sp;
     L.off_wl = o; o += sizeof(uint2) * TC_WL_CAP * TC_EPI_WARPS;
     L.off_rec = o; o += sizeof(TcRec) * TC_NREC;
+    L.off_soff = o; o += sizeof(uint32_t) * 2 * TC_MAXRING;      // start / end of the live allocations of the stage ring
     o = (o + 15) & ~(size_t)15;
     L.off_bar = o; o += 8 * (2 * TC_NREC + 6 * TC_MAXRING);
     o = (o + 1023) & ~(size_t)1023;
@@ -215,13 +224,19 @@ __host__ __device__ static inline TcLayout tc_layout(int S, int G, int SK, int n
 // -DKPROF: per-item events of every role of a few CTAs (tools/kprof.py prints the pipeline of one CTA)
 // (time stamps go to shared memory and are written out when the CTA is done: a record costs a global atomic, and one per
 // event would stretch the very hand-overs it is meant to show)
+// role-end stamps of a few CTAs (time + SM clock); -DTC_NO_TCE leaves only these
 #ifdef KPROF
+#define TCR(role) do { if (blockIdx.x % 37 == 0) krec_put(KP_TC_EVT, (int)blockIdx.x, 100 + (role), 0, gtimer(), (unsigned long long)clock64()); } while (0)
+#else
+#define TCR(role)
+#endif
+#if defined(KPROF) && !defined(TC_NO_TCE)
+#define TC_TCE 1
 #define TCE_ITEMS 32
-#define TCE(role, item) do { if ((item) < TCE_ITEMS) atomicMax(&tce_s[role][item], gtimer()); } while (0)
-#define TCE_MIN(role, item) do { if ((item) < TCE_ITEMS) atomicMin(&tce_s[role][item], gtimer()); } while (0)
+// (plain stores by ONE writer per event: atomics from all the builder warps stretched the table builds they were timing)
+#define TCE(role, item) do { if ((item) < TCE_ITEMS && blockIdx.x % 37 == 0) tce_s[role][item] = gtimer(); } while (0)
 #else
 #define TCE(role, item)
-#define TCE_MIN(role, item)
 #endif
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -244,15 +259,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
     const uint32_t nst = (uint32_t)L.nst, ntb = (uint32_t)L.ntb, nacc = (uint32_t)L.nacc;
     const uint32_t stage0 = smem_u32(smem + L.off_stage), table0 = smem_u32(smem + L.off_table);
     __shared__ uint32_t tmem_base_s;
-#ifdef KPROF
-    __shared__ unsigned long long tce_s[8][TCE_ITEMS];   // roles: 0 copy issued, 1 mma committed, 2/3 table start first/last, 4/5 table done first/last, 6 acc seen, 7 item done
-    for (int i = threadIdx.x; i < 8 * TCE_ITEMS; i += TC_THREADS) tce_s[i / TCE_ITEMS][i % TCE_ITEMS] = (i / TCE_ITEMS == 2 || i / TCE_ITEMS == 4) ? ~0ull : 0ull;
+#ifdef TC_TCE
+    __shared__ unsigned long long tce_s[10][TCE_ITEMS];   // roles: 0 copy issued, 1 mma committed, 2/3 table start first/last, 4/5 table done first/last, 6 acc seen, 7 item done
+    for (int i = threadIdx.x; i < 10 * TCE_ITEMS; i += TC_THREADS) tce_s[i / TCE_ITEMS][i % TCE_ITEMS] = 0ull;
 #endif
     __shared__ unsigned int gmin_bits, emin_bits;
     __shared__ int unnorm;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // ---- prologue that touches nothing of the preceding grid: barriers, zeroed operand buffers
+    __shared__ __align__(8) unsigned long long par_ready_s;      // mbarrier: gamma / eta staged, gmin_bits / emin_bits / unnorm final
+    const uint32_t par_ready = smem_u32(&par_ready_s);
+    // ---- prologue that touches nothing of the preceding grid: barriers, zeroed operand buffers, tensor memory
     if (tid == 0) {
         for (int i = 0; i < TC_NREC; i++) { mbar_init(rec_full + 8 * i, 1); mbar_init(rec_empty + 8 * i, TC_EPI_WARPS); }
         for (int i = 0; i < TC_MAXRING; i++) {
@@ -260,6 +277,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
             mbar_init(tab_full + 8 * i, TC_BUILD_WARPS); mbar_init(tab_empty + 8 * i, 1);
             mbar_init(acc_full + 8 * i, 1); mbar_init(acc_empty + 8 * i, TC_EPI_WARPS);
         }
+        mbar_init(par_ready, 1);
         gmin_bits = 0x7f800000u; emin_bits = 0x7f800000u; unnorm = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -267,61 +285,58 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
         uint4 *z = reinterpret_cast<uint4 *>(smem + L.off_stage);
         const size_t n16 = (L.off_table + (size_t)L.ntb * L.table_bytes - L.off_stage) / 16;
         for (size_t i = tid; i < n16; i += TC_THREADS) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = tid; i < G * Sp; i += TC_THREADS) gT32[i] = 1.0f;    // (finite operands for the builders' warm-up pass)
+        if (tid < 16) reinterpret_cast<float *>(eta32)[tid] = 0.25f;
     }
-    pdl_enter();
+    // The group control words, the item records and the count image were written by the maintenance launch at the start of
+    // the sweep; inside desman_update at least two grids (statistics, draw) lie in between, so they are complete and visible
+    // when this grid starts (the grid before us passed ITS dependency wait before it let us launch): with p.early everything
+    // that needs only them -- the record fetch, the first copies, the L2 prefetches -- runs under the tail of the draw kernel.
+    // Only gamma / eta (the draw kernel's output) and the MT19937 words need the wait: table builders and epilogue.
+    if (!p.early) pdl_enter();
     KPROF_SCOPE(KP_TGM);
     const int *gctl = p.grp.gctl;
-    if (!grp_active(gctl, 1)) return;
-    const int nitems = gctl[GC_NITEMS];
-    if ((int)blockIdx.x >= nitems) return;
-
-    if (warp == 0) {   // TMEM: two accumulators of N columns (allocation: power of two >= 32), owned by warp 0
+    const int nitems = grp_active(gctl, 1) ? gctl[GC_NITEMS] : 0;
+    if ((int)blockIdx.x >= nitems) {
+        if (p.early) pdl_enter();
+        return;
+    }
+    if (warp == 0) {   // TMEM: accumulators of N columns (allocation: power of two >= 32), owned by warp 0
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)L.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-    }
-    float gmin_l = __int_as_float(0x7f800000);
-    for (int i = tid; i < G * Sp; i += TC_THREADS) {
-        const int g = i / Sp, s = i - g * Sp;
-        const double x = (s < S) ? p.gamma[(size_t)s * G + g] : 0.0;
-        gT[i] = x;
-        gT32[i] = (float)x;
-        if (s < S && x > 0.0) gmin_l = fminf(gmin_l, (float)x);
-    }
-    atomicMin(&gmin_bits, __float_as_uint(gmin_l));
-    if (tid < 16) {
-        eta_s[tid] = p.eta[tid];
-        reinterpret_cast<float *>(eta32)[tid] = (float)p.eta[tid];
-        atomicMin(&emin_bits, __float_as_uint(fmaxf((float)p.eta[tid], 0.f)));
     }
     fence_proxy_async();               // the zero fill above is read by the tensor core (async proxy)
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    // unnormalised input (rows of gamma or eta summing to more than 1): no screening, every site goes to the per-site kernel
-    for (int s = tid; s < S + 4; s += TC_THREADS) {
-        double t = 0.0;
-        if (s < S) for (int g = 0; g < G; g++) t += gT[g * Sp + s];
-        else for (int b = 0; b < 4; b++) t += eta_s[4 * (s - S) + b];
-        if (!(t <= 1.0001)) unnorm = 1;
-    }
-    __syncthreads();
     const uint32_t tmem_base = tmem_base_s;
-#ifdef KPROF
-    if (tid == 0) krec_put(KP_TGM_PRO, (int)blockIdx.x, 0, nitems, gtimer(), 0);
-#endif
-    const float qmin = 0.99f * __uint_as_float(gmin_bits) * __uint_as_float(emin_bits);
-    const bool fast_ok = qmin >= TAU_QMIN && !unnorm;
-    const float mq0 = fmaxf(1.0f, 1.0f - log2f(fmaxf(qmin, TAU_QMIN)));
-    // per read, log2 units: the entry model of the FFMA form (relative parts, lg2.approx floors, lg2.approx and the lq - lP
-    // rounding per unit of |lg2|, FP64 cancellation) + [fp16 split 2^-22 + one FP32 accumulation step per 4 samples and piece,
-    // each charged 2^-20 of the running magnitude + the hi + lo/1024 add] * max|Wd|, |Wd| <= mq0
-    const float e_entry = TAU_C0 + (2.3841858e-7f + 5.9604645e-8f) * (2.0f * mq0) + TAU_CANCEL(G) / fmaxf(qmin, TAU_QMIN) + 5.9604645e-8f;   // (+ 2^-24: subnormal pieces)
-    const float e_mma = (float)(Sp / 2 + 12) * 9.5367432e-7f;
-    const float LN2 = 0.69314718f;
-    const float bn_scale = (e_entry + e_mma * mq0) * LN2 * 1.0001f;
     const uint32_t fullG = (G >= 32) ? 0xffffffffu : ((1u << G) - 1u);
     const uint32_t sbo = (uint32_t)KC * 128u;
     const int ncol = 3 * G;
+    const float LN2 = 0.69314718f;
+    // what the builders and the epilogue derive from gamma / eta once they are staged (after par_ready)
+    struct TcConsts { bool fast_ok; float bn_scale; };
+    auto consts = [&]() {
+        TcConsts k;
+        const float qmin = 0.99f * __uint_as_float(gmin_bits) * __uint_as_float(emin_bits);
+        k.fast_ok = qmin >= TAU_QMIN && !unnorm;
+        const float mq0 = fmaxf(1.0f, 1.0f - log2f(fmaxf(qmin, TAU_QMIN)));
+        // per read, log2 units: the entry model of the FFMA form (relative parts, lg2.approx floors, lg2.approx and the lq - lP
+        // rounding per unit of |lg2|) + [fp16 split 2^-22 + one FP32 accumulation step per 4 samples and piece, each charged
+        // 2^-20 of the running magnitude + the hi + lo/1024 add] * max|Wd|, |Wd| <= mq0
+#ifdef TC_TABLE_F64
+        const float e_entry = TAU_C0 + (2.3841858e-7f + 5.9604645e-8f) * (2.0f * mq0) + TAU_CANCEL(G) / fmaxf(qmin, TAU_QMIN) + 5.9604645e-8f;   // (+ 2^-24: subnormal pieces)
+#else
+        // FP32 table build: a candidate q + eta gamma and the mixture P carry a relative error <= (G + 2) 2^-24 each (G - 1 FMA
+        // steps over non-negative terms, two operand roundings, the last FMA; 2 more kept in reserve) -> log2(e) (2G + 8) 2^-24
+        // on their lg2 difference; + the two lg2.approx floors; per unit of |lg2|: lg2.approx 2^-22, the difference 2^-24
+        const float e_entry = (float)(2 * G + 8) * 5.9604645e-8f * 1.4426950f + 2.0f * 2.3841858e-7f +
+                              (2.3841858e-7f + 5.9604645e-8f) * (2.0f * mq0) + 5.9604645e-8f;                   // (+ 2^-24: subnormal pieces)
+#endif
+        const float e_mma = (float)(Sp / 2 + 12) * 9.5367432e-7f;
+        k.bn_scale = (e_entry + e_mma * mq0) * LN2 * 1.0001f;
+        return k;
+    };
 
     if (warp == TC_EPI_WARPS) {
         // =============================================================== item fetcher: item records, up to TC_NREC items ahead
@@ -358,12 +373,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
                 TCP(n_it++; rows += rc.count;);
             }
         }
+        if (lane == 0) TCR(0);
         TCP(if (lane == 0 && blockIdx.x % 37 == 0) printf("cta %3d items: %lld rows %lld total %lld wait rec_empty %lld\n", (int)blockIdx.x, n_it, rows, clock64() - t_all, w_rec););
     } else if (warp == TC_EPI_WARPS + 2) {
         // =============================================================== copy issuer: count rows of (item, K block) into the stage ring
+        // The stage area is a BYTE ring, not a ring of full-size slots: an item's rows take what they need (8 rows x KC x 16 B
+        // granules; the average item of C3 is 27 of the 64 KB a 128-row item takes), so three to five copies are in flight
+        // instead of two.  Allocations are released in order (the MMA commits); an MMA always READS 128 rows from its start
+        // (rows beyond the item's own are whatever follows: finite fp16, sums never read), so a start must leave a full-size
+        // footprint below the end of the area.
         if (lane == 0) {
             const size_t kb_stride = (size_t)p.img_rg * KC * 128;
-            uint32_t u = 0;
+            volatile uint32_t *soff = reinterpret_cast<volatile uint32_t *>(smem + L.off_soff);
+            const uint32_t R = nst * (uint32_t)L.stage_bytes, F = (uint32_t)L.stage_bytes;
+            uint32_t u = 0, u_tail = 0, head = 0;
             TCP(long long w_rec = 0; long long w_cnt = 0; const long long t_all = clock64(););
             for (uint32_t i = 0;; i++) {
                 const uint32_t r = i % TC_NREC;
@@ -372,50 +395,84 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
                 if (count == 0) break;
                 const uint32_t bytes = (((uint32_t)count + 7u) & ~7u) * (uint32_t)KC * 16u;
                 for (int kb = 0; kb < nkb; kb++, u++) {
-                    const uint32_t cs = u % nst;
-                    TCW(w_cnt, mbar_wait(cnt_empty + 8 * cs, ((u / nst) & 1u) ^ 1u));
-                    mbar_arrive_tx(cnt_full + 8 * cs, bytes);
-                    tma_bulk_g2s(stage0 + cs * (uint32_t)L.stage_bytes,
-                                 p.img + (size_t)kb * kb_stride + (size_t)(img0 >> 3) * KC * 128, bytes, cnt_full + 8 * cs);
+                    if (head + F > R) head = 0;
+                    while (u_tail < u) {                                   // make room: the oldest live allocation first
+                        const uint32_t s = u_tail % TC_MAXRING;
+                        const bool full = (u - u_tail) == TC_MAXRING, overlap = soff[2 * s] < head + bytes && head < soff[2 * s + 1];
+                        if (!full && !overlap) break;
+                        TCW(w_cnt, mbar_wait(cnt_empty + 8 * s, (u_tail / TC_MAXRING) & 1u));
+                        u_tail++;
+                    }
+                    const uint32_t cs = u % TC_MAXRING;
+                    soff[2 * cs] = head; soff[2 * cs + 1] = head + bytes;
+#ifdef TC_ABL_NOCOPY
+                    mbar_arrive(cnt_full + 8 * cs);
+#else
+                    mbar_arrive_tx(cnt_full + 8 * cs, bytes);               // (release: the offsets are visible to the MMA issuer)
+                    tma_bulk_g2s(stage0 + head, p.img + (size_t)kb * kb_stride + (size_t)(img0 >> 3) * KC * 128, bytes, cnt_full + 8 * cs);
+#endif
+                    head += bytes;
                     TCE(0, i);
                 }
             }
+            TCR(1);
             TCP(if (blockIdx.x % 37 == 0) printf("cta %3d copies: total %lld wait rec_full %lld cnt_empty %lld\n", (int)blockIdx.x, clock64() - t_all, w_rec, w_cnt););
         }
     } else if (warp == TC_EPI_WARPS + 1) {
         // =============================================================== MMA issuer
-        if (lane == 0) {
-            const uint32_t idesc = (1u << 4) | ((uint32_t)(L.N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);   // F16 x F16 -> F32, K-major A and B
-            uint32_t u = 0;
-            TCP(long long w_rec = 0; long long w_acc = 0; long long w_tab = 0; long long w_cnt = 0; const long long t_all = clock64(););
-            for (uint32_t i = 0;; i++) {
-                const uint32_t r = i % TC_NREC;
-                TCW(w_rec, mbar_wait(rec_full + 8 * r, (i / TC_NREC) & 1u));
-                if (rec[r].count == 0) break;
-                const uint32_t as = i % nacc;
-                TCW(w_acc, mbar_wait(acc_empty + 8 * as, ((i / nacc) & 1u) ^ 1u));
-                const uint32_t d = tmem_base + as * (uint32_t)L.acc_stride;
-                for (int kb = 0; kb < nkb; kb++, u++) {
-                    const uint32_t cs = u % nst, ts = u % ntb;
-                    TCW(w_tab, mbar_wait(tab_full + 8 * ts, (u / ntb) & 1u));
-                    TCW(w_cnt, mbar_wait(cnt_full + 8 * cs, (u / nst) & 1u));
-                    tc_fence_after();
-                    const uint64_t a0 = tc_desc(stage0 + cs * (uint32_t)L.stage_bytes, 128u, sbo);
-                    const uint64_t b0 = tc_desc(table0 + ts * (uint32_t)L.table_bytes, 128u, sbo);
+        // The whole warp walks the loop (lane 0 polls the barriers), ONE ELECTED lane issues: with the branch warp-uniform and
+        // the issue under elect.sync the compiler emits straight uniform-datapath code; issued from inside `if (lane == 0)` every
+        // tcgen05.mma sat in its own "elect an active thread and loop" construct (ELECT / BRA.U.ANY), and the 16 MMAs of an item
+        // took the thread 1.3-1.8 us -- the longest stage of the pipeline (tools/ubench/umma_issue.cu: 0.5 us for a tight loop).
+        const uint32_t idesc = (1u << 4) | ((uint32_t)(L.N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);   // F16 x F16 -> F32, K-major A and B
+        const int nk = KC / 2;                                            // one K step = 16 fp16 = 2 chunks = 256 bytes = 16 units
+        uint32_t u = 0;
+        TCP(long long w_rec = 0; long long w_acc = 0; long long w_tab = 0; long long w_cnt = 0; const long long t_all = clock64(););
+        for (uint32_t i = 0;; i++) {
+            const uint32_t r = i % TC_NREC;
+            TCW(w_rec, mbar_wait_warp(rec_full + 8 * r, (i / TC_NREC) & 1u, lane));
+            if (rec[r].count == 0) break;
+            const uint32_t as = i % nacc;
+            TCW(w_acc, mbar_wait_warp(acc_empty + 8 * as, ((i / nacc) & 1u) ^ 1u, lane));
+            const uint32_t d = tmem_base + as * (uint32_t)L.acc_stride;
+            for (int kb = 0; kb < nkb; kb++, u++) {
+                const uint32_t cs = u % TC_MAXRING, ts = u % ntb;
+                TCW(w_tab, mbar_wait_warp(tab_full + 8 * ts, (u / ntb) & 1u, lane));
+                TCW(w_cnt, mbar_wait_warp(cnt_full + 8 * cs, (u / TC_MAXRING) & 1u, lane));
+                if (kb == 0 && lane == 0) TCE(8, i);
+                tc_fence_after();
+                if (tc_elect_one()) {
+                    uint64_t a = tc_desc(stage0 + reinterpret_cast<const volatile uint32_t *>(smem + L.off_soff)[2 * cs], 128u, sbo);
+                    uint64_t b = tc_desc(table0 + ts * (uint32_t)L.table_bytes, 128u, sbo);
 #ifdef TC_ABL_MMA
-                    for (int k = 0; k < 1; k++)
+                    tc_mma_f16(d, a, b, idesc, kb ? 1u : 0u);
 #else
-                    for (int k = 0; k < KC / 2; k++)                      // one K step = 16 fp16 = 2 chunks = 256 bytes = 16 units
+                    int k = 0;
+                    if (nk >= 4) {
+                        tc_mma_f16(d, a, b, idesc, kb ? 1u : 0u);
+                        tc_mma_f16(d, a + 16, b + 16, idesc, 1u);
+                        tc_mma_f16(d, a + 32, b + 32, idesc, 1u);
+                        tc_mma_f16(d, a + 48, b + 48, idesc, 1u);
+                        a += 64; b += 64;
+                        for (k = 4; k + 4 <= nk; k += 4, a += 64, b += 64) {
+                            tc_mma_f16(d, a, b, idesc, 1u);
+                            tc_mma_f16(d, a + 16, b + 16, idesc, 1u);
+                            tc_mma_f16(d, a + 32, b + 32, idesc, 1u);
+                            tc_mma_f16(d, a + 48, b + 48, idesc, 1u);
+                        }
+                    }
+                    for (; k < nk; k++, a += 16, b += 16) tc_mma_f16(d, a, b, idesc, (kb | k) ? 1u : 0u);
 #endif
-                        tc_mma_f16(d, a0 + (uint64_t)(16 * k), b0 + (uint64_t)(16 * k), idesc, (kb | k) ? 1u : 0u);
                     tc_commit(cnt_empty + 8 * cs);
                     tc_commit(tab_empty + 8 * ts);
+                    if (kb == nkb - 1) tc_commit(acc_full + 8 * as);
                 }
-                tc_commit(acc_full + 8 * as);
-                TCE(1, i);
+                __syncwarp();
             }
-            TCP(if (blockIdx.x % 37 == 0) printf("cta %3d mma: total %lld wait rec_full %lld acc_empty %lld tab_full %lld cnt_full(after tab) %lld\n", (int)blockIdx.x, clock64() - t_all, w_rec, w_acc, w_tab, w_cnt););
+            if (lane == 0) TCE(1, i);
         }
+        if (lane == 0) TCR(2);
+        TCP(if (lane == 0 && blockIdx.x % 37 == 0) printf("cta %3d mma: total %lld wait rec_full %lld acc_empty %lld tab_full %lld cnt_full(after tab) %lld\n", (int)blockIdx.x, clock64() - t_all, w_rec, w_acc, w_tab, w_cnt););
     } else if (warp >= TC_EPI_WARPS + 3) {
         // =============================================================== table builders (TC_BUILD_WARPS warps, no cross-warp dependency)
         // A warp task = 8 strains x 4 samples; a lane = one (strain, sample): its base q[b] = P[b] - eta[cur][b] gamma (FP64, one
@@ -432,7 +489,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
         const int mys = 2 * sp + shf;                                      // this lane's sample within the task
         const int ngo = (G + 7) >> 3, noct = NC >> 3, nquad = SK >> 2, ntask = ngo * nquad;
         constexpr int TPRE = 2;                                            // tasks per warp and K block kept in registers
-        struct TaskC { const double *gTp; const double *gg; const float *gf; uint32_t off[3]; int g2; bool p_ok, ok; };
+        struct TaskC { const double *gTp; const double *gg; const float *gf; const float *gcol; uint32_t off[3]; int g2, g; bool p_ok, ok; };
         auto task_consts = [&](int task, int kb) {
             TaskC t;
             const int go = task % ngo, sq = task / ngo;
@@ -443,6 +500,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
             t.gg = gT + (t.ok ? g * Sp + sm : 0);
             t.gf = gT32 + (t.ok ? g * Sp + sm : 0);
             t.g2 = 2 * (t.ok ? g : 0);
+            t.g = t.ok ? g : 0;
+            t.gcol = gT32 + (t.ok ? sm : 0);
 #pragma unroll
             for (int j = 0; j < 3; j++) {
                 const int n = 3 * g + j;
@@ -455,6 +514,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
 #pragma unroll
         for (int k = 0; k < TPRE; k++) pre[k] = task_consts(bw + k * TC_BUILD_WARPS, 0);
         const uint32_t lo_off = (uint32_t)noct * sbo;                     // rows [NC, 2 NC): the remainders
+#ifdef TC_TABLE_F64
         // one task: the lane's 12 entries of table `tab` for pattern `code`
         auto do_task = [&](const TaskC &t, uint64_t code, unsigned char *tab) {
             double Pv = 1.0;                                                // padding samples: finite logs
@@ -523,7 +583,97 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
                 }
             }
         };
+#else
+        // one task: the lane's 12 entries of table `tab` for pattern `code`.
+        // ALL IN FP32, and on purpose: FP64 arithmetic and FP64 -> FP32 conversions stall while tcgen05.mma are in flight
+        // (tools/ubench/umma_interfere.cu: DFMA and F2F.F32.F64 run 2.3 x slower next to a stream of these MMAs, FFMA / MUFU / SHFL
+        // do not) -- with the FP64 mixture of the first version every builder warp sat out a 3.3 us stall once or twice per launch.
+        // The base q[b] = sum over the OTHER strains of eta[tau_h][b] gamma[s][h] is formed directly (a sum of non-negative terms:
+        // no cancellation, relative error <= (G+1) 2^-24 incl. the operand roundings) instead of P - eta[cur][b] gamma[s][g]; the
+        // mixture the entries are taken relative to is P[b] = q[b] + eta[cur][b] gamma[s][g].
+        auto do_task = [&](const TaskC &t, uint64_t code, unsigned char *tab) {
+            if (!t.ok) return;
+            const int cur = (int)((code >> t.g2) & 3ull);
+            float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+            {
+                const float *gp = t.gcol;
+                uint64_t cc = code;
+                for (int h = 0; h < G; h++, cc >>= 2, gp += Sp) {
+                    const float4 e = eta32[(int)(cc & 3ull)];
+                    const float gm = (h == t.g) ? 0.f : *gp;                 // (adds exactly 0 for the lane's own strain)
+                    q0 = fmaf(e.x, gm, q0); q1 = fmaf(e.y, gm, q1); q2 = fmaf(e.z, gm, q2); q3 = fmaf(e.w, gm, q3);
+                }
+            }
+            const float gf = *t.gf;
+            const float4 ec = eta32[cur];
+            const float l0 = lg2_fast(fmaf(ec.x, gf, q0)), l1 = lg2_fast(fmaf(ec.y, gf, q1)), l2 = lg2_fast(fmaf(ec.z, gf, q2)),
+                        l3 = lg2_fast(fmaf(ec.w, gf, q3));
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const float4 ea = eta32[(cur + 1 + j) & 3];
+                const float w0 = lg2_fast(fmaf(ea.x, gf, q0)) - l0, w1 = lg2_fast(fmaf(ea.y, gf, q1)) - l1,
+                            w2 = lg2_fast(fmaf(ea.z, gf, q2)) - l2, w3 = lg2_fast(fmaf(ea.w, gf, q3)) - l3;
+                // h = the entry truncated to fp16's 11 significant bits (a mask: exact in fp16 unless |w| < 2^-14, where the
+                // conversion rounds it on the 2^-24 grid), l = fp16(w - h_truncated)
+                const float t0 = __uint_as_float(__float_as_uint(w0) & 0xffffe000u), t1 = __uint_as_float(__float_as_uint(w1) & 0xffffe000u),
+                            t2 = __uint_as_float(__float_as_uint(w2) & 0xffffe000u), t3 = __uint_as_float(__float_as_uint(w3) & 0xffffe000u);
+                const __half2 h01 = __floats2half2_rn(t0, t1), h23 = __floats2half2_rn(t2, t3);
+                const __half2 l01 = __floats2half2_rn(w0 - t0, w1 - t1), l23 = __floats2half2_rn(w2 - t2, w3 - t3);
+                uint2 hv, lv;
+                hv.x = *reinterpret_cast<const uint32_t *>(&h01); hv.y = *reinterpret_cast<const uint32_t *>(&h23);
+                lv.x = *reinterpret_cast<const uint32_t *>(&l01); lv.y = *reinterpret_cast<const uint32_t *>(&l23);
+                *reinterpret_cast<uint2 *>(tab + t.off[j]) = hv;                 // rows [0, NC): h
+                *reinterpret_cast<uint2 *>(tab + t.off[j] + lo_off) = lv;        // rows [NC, 2 NC): l
+            }
+        };
+#endif
+        const int bt = tid - (TC_EPI_WARPS + 3) * 32, nbt = TC_BUILD_WARPS * 32;
+        if (p.early) {
+            // warm-up pass over table buffer 0 with placeholder operands (every entry it writes is rewritten by item 0's build):
+            // the first table of a launch cost 3-4.7 us instead of 0.9 on instructions that came from HBM (L2 is cold at the
+            // start of a sweep); here that happens under the tail of the draw kernel
+            unsigned char *tab0 = smem + L.off_table;
+            if (pre_ok) {
+#pragma unroll
+                for (int k = 0; k < TPRE; k++)
+                    if (bw + k * TC_BUILD_WARPS < ntask) do_task(pre[k], 0ull, tab0);
+            } else {
+                for (int task = bw; task < ntask; task += TC_BUILD_WARPS) do_task(task_consts(task, 0), 0ull, tab0);
+            }
+            pdl_enter();
+        }
+        {   // gamma / eta of this sweep (the draw kernel's output) -> shared memory; smallest entries; normalisation check
+            float gmin_l = __int_as_float(0x7f800000);
+            for (int i = bt; i < G * Sp; i += nbt) {
+                const int g = i / Sp, s2 = i - g * Sp;
+                const double x = (s2 < S) ? p.gamma[(size_t)s2 * G + g] : 0.0;
+                gT[i] = x;
+                gT32[i] = (float)x;
+                if (s2 < S && x > 0.0) gmin_l = fminf(gmin_l, (float)x);
+            }
+            atomicMin(&gmin_bits, __float_as_uint(gmin_l));
+            if (bt < 16) {
+                eta_s[bt] = p.eta[bt];
+                reinterpret_cast<float *>(eta32)[bt] = (float)p.eta[bt];
+                atomicMin(&emin_bits, __float_as_uint(fmaxf((float)p.eta[bt], 0.f)));
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(nbt) : "memory");
+            // unnormalised input (rows of gamma or eta summing to more than 1): no screening, every site goes to the per-site kernel
+            for (int s2 = bt; s2 < S + 4; s2 += nbt) {
+                double t = 0.0;
+                if (s2 < S) for (int g = 0; g < G; g++) t += gT[g * Sp + s2];
+                else for (int b = 0; b < 4; b++) t += eta_s[4 * (s2 - S) + b];
+                if (!(t <= 1.0001)) unnorm = 1;
+            }
+            asm volatile("bar.sync 1, %0;" ::"r"(nbt) : "memory");
+            if (bt == 0) mbar_arrive(par_ready);
+        }
+        const bool fast_ok = consts().fast_ok;
+#ifdef KPROF
+        if (bt == 0) krec_put(KP_TGM_PRO, (int)blockIdx.x, 0, nitems, gtimer(), 0);
+#endif
         uint32_t u = 0;
+        if (lane == 0 && bw == 0) TCR(7);
         TCP(long long w_rec = 0; long long w_tab = 0; long long t_work = 0; long long t_task = 0; long long t_fence = 0; const long long t_all = clock64(););
         for (uint32_t i = 0;; i++) {
             const uint32_t r = i % TC_NREC;
@@ -535,7 +685,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
                 const uint32_t ts = u % ntb;
                 TCW(w_tab, mbar_wait_warp(tab_empty + 8 * ts, ((u / ntb) & 1u) ^ 1u, lane));
                 TCP(const long long tw0 = clock64(););
-                if (lane == 0) { TCE_MIN(2, i); TCE(3, i); }
+                if (lane == 0 && bw == 0) TCE(2, i);
+                if (lane == 0 && bw == TC_BUILD_WARPS - 1) TCE(3, i);
                 unsigned char *tab = smem + L.off_table + ts * L.table_bytes;
 #ifndef TC_ABL_TABLE
                 if (fast_ok) {                                           // (otherwise the tables stay zero and every site is listed)
@@ -550,14 +701,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
                 }
 #endif
                 TCP(const long long tw1 = clock64(););
+#ifndef TC_ABL_NOFENCE
                 fence_proxy_async();                                     // generic-proxy stores -> async-proxy reads of the MMA
+#endif
                 TCP(const long long tw2 = clock64(););
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tab_full + 8 * ts);
-                if (lane == 0) { TCE_MIN(4, i); TCE(5, i); }
+                if (lane == 0 && bw == 0) TCE(4, i);
+                if (lane == 0 && bw == TC_BUILD_WARPS - 1) TCE(5, i);
                 TCP(t_work += clock64() - tw0; t_task += tw1 - tw0; t_fence += tw2 - tw1;);
             }
         }
+        if (lane == 0 && bw == 0) TCR(3);
         TCP(if (lane == 0 && bw == 0 && blockIdx.x % 37 == 0) printf("cta %3d tables: total %lld wait rec_full %lld tab_empty %lld work %lld (task %lld fence %lld)\n", (int)blockIdx.x, clock64() - t_all, w_rec, w_tab, t_work, t_task, t_fence););
     } else {
         // =============================================================== epilogue (warps 0-3: TMEM lanes 32 w .. 32 w + 31)
@@ -566,16 +721,28 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
         uint2 *wl = reinterpret_cast<uint2 *>(smem + L.off_wl) + warp * TC_WL_CAP;
         int wl_n = 0;
         TCP(long long w_rec = 0; long long w_acc = 0; const long long t_all = clock64(););
+        if (p.early) pdl_enter();                                            // (MT19937 words; orphan marks of the previous sweep)
+        mbar_wait_warp(par_ready, 0u, lane);
+        const TcConsts kc = consts();
+        const bool fast_ok = kc.fast_ok;
+        const float bn_scale = kc.bn_scale;
+        // The site and read count of a row are two global loads (~1 us from HBM): they are issued ONE ITEM AHEAD (the record of
+        // item i+1 is waited for before the sums of item i), so that they are not on the per-item critical path of this role.
+        TCW(w_rec, mbar_wait_warp(rec_full, 0u, lane));
+        TcRec rc = rec[0];
+        int vraw = 0;
+        float nk = 0.f;
+        if (rc.count && row < rc.count) { vraw = p.img_site[rc.img0 + row]; nk = p.img_nsite[rc.img0 + row]; }
         for (uint32_t i = 0;; i++) {
             const uint32_t r = i % TC_NREC;
-            TCW(w_rec, mbar_wait_warp(rec_full + 8 * r, (i / TC_NREC) & 1u, lane));
-            const TcRec rc = rec[r];
             if (rc.count == 0) break;
-            // what the decision needs besides the sums, fetched before the sums are waited for
+            const uint32_t r1 = (i + 1) % TC_NREC;
+            TCW(w_rec, mbar_wait_warp(rec_full + 8 * r1, ((i + 1) / TC_NREC) & 1u, lane));
+            const TcRec rcn = rec[r1];
+            int vraw_n = 0;
+            float nk_n = 0.f;
+            if (rcn.count && row < rcn.count) { vraw_n = p.img_site[rcn.img0 + row]; nk_n = p.img_nsite[rcn.img0 + row]; }
             const bool have = row < rc.count;
-            int vraw = 0;
-            float nk = 0.f;
-            if (have) { vraw = p.img_site[rc.img0 + row]; nk = p.img_nsite[rc.img0 + row]; }
             const bool orphan = vraw < 0;                                   // the site has left this group (tau_sample_kernel marks the row)
             const int vown = orphan ? ~vraw : vraw;
             bool zero_word = false;
@@ -643,19 +810,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
                 __syncwarp();
             }
             if (warp == 0 && lane == 0) TCE(7, i);
+            rc = rcn; vraw = vraw_n; nk = nk_n;
         }
+        if (lane == 0 && warp == 0) TCR(4);
         if (wl_n) tc_flush_worklist(p.grp, wl, wl_n, lane);
         n_decided = (unsigned int)warp_sum_u64((unsigned long long)n_decided);
         if (lane == 0 && n_decided && p.tier_counts) atomicAdd(p.tier_counts, (unsigned long long)n_decided);
+        if (lane == 0 && warp == 0) TCR(5);
         TCP(if (lane == 0 && warp == 0 && blockIdx.x % 37 == 0) printf("cta %3d epilogue: total %lld wait rec_full %lld acc_full %lld\n", (int)blockIdx.x, clock64() - t_all, w_rec, w_acc););
     }
     // ---- teardown: every role is done with tensor memory
     tc_fence_before();
     __syncthreads();
-#ifdef KPROF
+    if (tid == 0) TCR(6);
+#ifdef TC_TCE
     if (tid == 0 && blockIdx.x % 37 == 0)
         for (int it = 0; it < TCE_ITEMS; it++)
-            for (int ro = 0; ro < 8; ro++)
+            for (int ro = 0; ro < 10; ro++)
                 if (tce_s[ro][it] != 0ull && tce_s[ro][it] != ~0ull) krec_put(KP_TC_EVT, (int)blockIdx.x, ro, it, tce_s[ro][it], 0);
 #endif
     if (warp == 0) {

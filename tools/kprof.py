@@ -17,7 +17,8 @@ OUT = os.path.join(ROOT, "build", "libdesman_b200_kprof.so")
 if "--build" in sys.argv:
     from desman_b200 import build as b
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
-    cmd = ["nvcc"] + b.FLAGS + ["-DKPROF", "-o", OUT, b.SRC, "-ldl"]
+    extra = [a for a in sys.argv[1:] if a.startswith("-D")]      # e.g. -DTC_NO_TCE: kernel scopes only, no per-item events
+    cmd = ["nvcc"] + b.FLAGS + ["-DKPROF"] + extra + ["-o", OUT, b.SRC, "-ldl"]
     subprocess.run(cmd, check=True, capture_output=True)
     print(OUT)
     sys.exit(0)
@@ -91,6 +92,56 @@ if to:
         print("  per site: stage med %.2f p90 %.2f   rounds+writeback med %.2f p90 %.2f max %.2f" % (
             np.median(w["b"][has] / sites[has]) / 1e3, np.percentile(w["b"][has] / sites[has], 90) / 1e3,
             np.median(w["c"][has] / sites[has]) / 1e3, np.percentile(w["c"][has] / sites[has], 90) / 1e3, (w["c"][has] / sites[has]).max() / 1e3))
+# the last screening launch: per-CTA prologue end and exit
+tgl = [d for d in rows if d["kid"] == 4]
+if tgl:
+    tg = tgl[-1]
+    g = r[(r["kid"] == 4) & (r["t0"] >= tg["entry"]) & (r["t1"] <= tg["exit"])]
+    gp = r[(r["kid"] == 10) & (r["t0"] >= tg["entry"]) & (r["t0"] <= tg["exit"])]
+    en = (g["t0"].astype(np.int64) - tg["entry"]) / 1e3
+    ex = (g["t1"].astype(np.int64) - tg["entry"]) / 1e3
+    pr = (gp["t0"].astype(np.int64) - tg["entry"]) / 1e3
+    print("screening last launch: ctas %d  scope entry us: med %.2f max %.2f | prologue done us: med %.2f max %.2f | exit us: min %.2f p10 %.2f med %.2f p90 %.2f max %.2f" % (
+        len(g), np.median(en), en.max(), np.median(pr) if len(pr) else -1, pr.max() if len(pr) else -1, ex.min(), np.percentile(ex, 10),
+        np.median(ex), np.percentile(ex, 90), ex.max()))
+    re_ = r[(r["kid"] == 12) & (r["warp"] >= 100) & (r["t0"] >= tg["entry"]) & (r["t0"] <= tg["exit"] + 100000)]
+    rn = ["fetcher done", "copy issuer done", "mma issuer done", "builder 0 done", "epilogue items done", "epilogue flushed", "teardown sync passed", "builder 0 start"]
+    for cta in sorted(set(re_["cta"].tolist())):
+        ent = int(g[g["cta"] == cta]["t0"][0]); exi = int(g[g["cta"] == cta]["t1"][0])
+        print("  cta %3d (us from its scope entry):  %s | exit %.2f" % (cta, "  ".join("%s %.2f" % (rn[int(w_) - 100], (int(t_) - ent) / 1e3)
+              for w_, t_ in sorted(zip(re_[re_["cta"] == cta]["warp"].tolist(), re_[re_["cta"] == cta]["t0"].tolist()))), (exi - ent) / 1e3))
+    for cta in sorted(set(re_["cta"].tolist())):
+        a = re_[(re_["cta"] == cta) & (re_["warp"] == 107)]; b = re_[(re_["cta"] == cta) & (re_["warp"] == 103)]
+        if len(a) and len(b):
+            print("  cta %3d builder 0: %.2f us = %d SM cycles -> %.0f MHz" % (cta, (int(b["t0"][0]) - int(a["t0"][0])) / 1e3, int(b["t1"][0]) - int(a["t1"][0]),
+                  (int(b["t1"][0]) - int(a["t1"][0])) / ((int(b["t0"][0]) - int(a["t0"][0])) / 1e3)))
+    ev = r[(r["kid"] == 12) & (r["warp"] < 100) & (r["t0"] >= tg["entry"]) & (r["t0"] <= tg["exit"] + 100000)]
+    if len(ev):
+        cta = int(ev["cta"].min())
+        ev = ev[ev["cta"] == cta]
+        ent = int(g[g["cta"] == cta]["t0"][0])
+        roles = ["tma issued", "mma committed", "table start (builder 0)", "table start (builder 15)", "table done (b0)", "table done (b15)",
+                 "acc seen", "item done", "mma operands ready"]
+        print("tc pipeline of cta %d (us from its scope entry); columns: %s" % (cta, ", ".join(roles)))
+        for it in sorted(set(ev["x"].tolist())):
+            row = []
+            for ro in range(9):
+                m = ev[(ev["x"] == it) & (ev["warp"] == ro)]
+                row.append("%6.2f" % ((int(m["t0"][0]) - ent) / 1e3) if len(m) else "   -  ")
+            print("  item %2d: %s" % (it, "  ".join(row)))
+    tb = r[(r["kid"] == 12) & (r["warp"] >= 200)]
+    if len(tb):
+        nit = int(tb["x"].max()) + 1
+        print("builder warps of cta 0, ns per item build (last launches mixed: the records carry durations); rows = warps 0-15, then builder 0's P loop / shuffles / entries")
+        for w_ in range(19):
+            m = tb[tb["warp"] == 200 + w_]
+            last = {}
+            for x_, t_ in zip(m["x"].tolist(), m["t0"].tolist()):
+                last[x_] = t_
+            print("  %2d: %s" % (w_, " ".join("%5d" % last.get(i_, 0) for i_ in range(nit))))
+    dr = [d for d in rows if d["kid"] == 3 and d["exit"] <= tg["entry"] + 2000]
+    if dr:
+        print("  (draw kernel before it: exit at %.2f us relative to the first screening scope entry)" % ((dr[-1]["exit"] - tg["entry"]) / 1e3))
 # the last tau_sample launch: per-warp phases
 if not [d for d in rows if d["kid"] == 5]:
     print("(no tau_sample records: the work list was walked by tau_open_kernel)")
@@ -143,12 +194,12 @@ if len(ev):
     cta = int(ev["cta"].min())
     ev = ev[ev["cta"] == cta]
     ent = int(g[g["cta"] == cta]["t0"][0]) if (g["cta"] == cta).any() else tg["entry"]
-    roles = ["tma issued", "mma committed", "table start (first warp)", "table start (last)", "table done (first)", "table done (last)",
-             "acc seen", "item done"]
+    roles = ["tma issued", "mma committed", "table start (builder 0)", "table start (builder 15)", "table done (b0)", "table done (b15)",
+             "acc seen", "item done", "mma operands ready"]
     print("tc pipeline of cta %d (us from its entry); columns: %s" % (cta, ", ".join(roles)))
     for it in sorted(set(ev["x"].tolist())):
         row = []
-        for ro in range(8):
+        for ro in range(9):
             m = ev[(ev["x"] == it) & (ev["warp"] == ro)]
             row.append("%6.2f" % ((int(m["t0"][0]) - ent) / 1e3) if len(m) else "   -  ")
         print("  item %2d: %s" % (it, "  ".join(row)))
