@@ -518,15 +518,28 @@ __global__ void __launch_bounds__(MUB_WARPS * 32, MUB_MIN_BLOCKS) mu_binomial_ke
             mub_item(p, st, item_cur, valid, s, lane, G, eta_s, wS, sufS, accS, eS);
         }
     }
-    __syncwarp();
-    if (valid)
-        for (int g = 0; g < G; g++) {
-            const unsigned long long x = accS[g * 32 + lane];
-            if (x) atomicAdd(p.sum_mu + (size_t)s * G + g, x);
+    // Flush: the accumulators of the CTA's warps are added up in shared memory first (row j of the (G + 16) x 32 accumulator
+    // block of a warp: strain j < G, else E entry j - G) -- one global atomic per (CTA, sample chunk, row, lane) instead of one
+    // per warp: 2368 warps flushing S*G + 16 words each put ~1200 (mu) and ~2400 (E) same-address atomics in a row in front of
+    // the grid's completion (5-8 us between the last CTA's exit and the start of the dependent launch, tools/kprof.py)
+    __syncthreads();
+    {
+        const size_t wstride = (size_t)32 * (3 * G + 1 + 16);                   // doubles (= 64-bit words) per warp region
+        const unsigned long long *acc0 = reinterpret_cast<const unsigned long long *>(eta_s + 16 + (size_t)(2 * G + 1) * 32);
+        const int nrow = G + 16;
+        // warps with the same sample chunk: wib' = wib0, wib0 + nch, ...  (chunk = (blockIdx * MUB_WARPS + wib') % nch)
+        for (int row = wib; row < nrow * min(nch, MUB_WARPS); row += MUB_WARPS) {
+            const int r = row % nrow, k = row / nrow;                            // k-th distinct chunk of this CTA: warps k, k + nch, ...
+            unsigned long long x = 0ull;
+            for (int w = k; w < MUB_WARPS; w += nch) x += acc0[(size_t)w * wstride + (size_t)r * 32 + lane];
+            const int ch = (int)(((long long)blockIdx.x * MUB_WARPS + k) % nch), s2 = ch * 32 + lane;
+            if (r < G) {
+                if (x && s2 < S) atomicAdd(p.sum_mu + (size_t)s2 * G + r, x);
+            } else {
+                x = warp_sum_u64(x);
+                if (lane == 0 && x) atomicAdd(p.esum + (r - G), x);
+            }
         }
-    for (int i = 0; i < 16; i++) {
-        const unsigned long long t = warp_sum_u64(eS[i * 32 + lane]);
-        if (lane == 0 && t) atomicAdd(p.esum + i, t);
     }
 }
 
