@@ -154,6 +154,8 @@ struct desman_ctx {
     // pattern groups for the screening pass of the tau update (tau_group_kernel.cuh)
     int tau_group = 2;                       // 0: off, 1: on, 2: on iff the ~12*2^G biallelic patterns are <= V/2
     int tau_group_mma = 1;                   // 1: tensor-core form of the screening pass where it applies; 0: FFMA form
+    bool star_fold = false;                  // sharded chain: the next screening launch takes the MAP snapshot (tau_star <- tau if flag)
+    int xch_fuse = 1;                        // exchange + bookkeeping of the previous sweep as one launch (peer-memory exchange only)
     int tau_open = 1;                        // 1: the work list of the screening pass is walked by tau_open_kernel (one CTA per site)
     int tauo_grid = 0;
     size_t tauo_smem = 0;
@@ -991,6 +993,11 @@ static int launch_tau_group_tc(desman_ctx *c, const TauGroupParams &q, float *db
     p.gamma = q.gamma; p.eta = q.eta; p.words = q.words; p.V = q.V; p.S = q.S; p.G = q.G;
     p.grp = q.grp; p.tier_counts = q.tier_counts; p.dbg = dbg;
     p.early = (early && c->pdl) ? 1 : 0;
+    p.star_src = nullptr; p.star_dst = nullptr; p.star_n = 0; p.star_flag = nullptr;
+    if (c->star_fold) {      // the conditional MAP snapshot of the sharded chain (the bookkeeping launch before the draw decided it)
+        p.star_src = c->tau; p.star_dst = c->tau_star; p.star_n = (size_t)c->V * c->G; p.star_flag = c->flag;
+        c->star_fold = false;
+    }
     const size_t smem = tc_layout(c->S, c->G, p.SK, p.nkb, p.NC).total;
     CU(cudaFuncSetAttribute(tau_group_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU(launch_k(c, tau_group_tc_kernel, c->sm_count, TC_THREADS, smem, p));
@@ -1013,6 +1020,14 @@ static int launch_tau_group_t(desman_ctx *c, const TauGroupParams &p, int warps)
 // One tau pass (gamma, eta: device pointers).  maintain: keep the pattern table current (it must be in sync); then the
 // screening pass runs first where groups are kept, and the per-site kernel walks its work list only.
 // red_i[1] (nchange) must be zero on entry (sync_table, or the caller's memset).
+// will launch_tau (maintain = true) run the tensor-memory screening launch?  (the same conditions, in the same order)
+static bool tau_runs_tc(desman_ctx *c)
+{
+    if (!c->agg_valid || !agg_table(c).N) return false;
+    int gb = 8, gw = 1;
+    return group_config(c, &gb, &gw) && group_use_tc(c);
+}
+
 static int launch_tau(desman_ctx *c, const double *gamma, const double *eta, bool maintain, bool count_occupancy, uint32_t iter,
                       int g_begin = 0, double *logp_out = nullptr, int early = 0)
 {
@@ -1255,9 +1270,8 @@ static int launch_star_copy(desman_ctx *c)
     CU(launch_k(c, copy_tau_if_kernel, c->sm_count, 256, 0, (const uint8_t *)c->tau, c->tau_star, (size_t)c->V * c->G, (const int *)c->flag));
     return DESMAN_OK;
 }
-// lp, stores, MAP bookkeeping from the (already summed) words red = [fixed-point ll, nchange]
-static int launch_finalize_only(desman_ctx *c, const unsigned long long *red, const double *gamma, const double *eta, int it,
-                                int star_mode, const StoreBufs &sb, bool store_ge, double *eta_commit, bool copy_now)
+static FinalParams final_params(desman_ctx *c, const unsigned long long *red, const double *gamma, const double *eta, int it,
+                                int star_mode, const StoreBufs &sb, bool store_ge, double *eta_commit)
 {
     FinalParams p;
     p.red_i = (const long long *)red; p.ll_const = c->ll_const_total; p.ll_inv_scale = 1.0 / c->ll_scale;
@@ -1272,6 +1286,13 @@ static int launch_finalize_only(desman_ctx *c, const unsigned long long *red, co
     p.agg_nslots = c->agg_nslots; p.agg_ctl = c->agg_ctl; p.agg_limit = (unsigned int)(c->V + c->V / 4);
     p.gctl = group_config(c, nullptr, nullptr) ? c->grp_gctl : nullptr;
     p.V_local = (long long)c->V;
+    return p;
+}
+// lp, stores, MAP bookkeeping from the (already summed) words red = [fixed-point ll, nchange, upkeep wishes]
+static int launch_finalize_only(desman_ctx *c, const unsigned long long *red, const double *gamma, const double *eta, int it,
+                                int star_mode, const StoreBufs &sb, bool store_ge, double *eta_commit, bool copy_now)
+{
+    const FinalParams p = final_params(c, red, gamma, eta, it, star_mode, sb, store_ge, eta_commit);
     {
         KSpan k(c, DESMAN_K_FINAL);
         CU(launch_k(c, finalize_sweep_kernel, 1, 256, 0, p));
@@ -1279,6 +1300,30 @@ static int launch_finalize_only(desman_ctx *c, const unsigned long long *red, co
     if (copy_now) RET(launch_star_copy(c));
     CU(cudaGetLastError());
     return DESMAN_OK;
+}
+// The sharded chain's exchange of sweep k (statistics + the three words of sweep k-1) and the bookkeeping of sweep k-1 that
+// consumes those words: one launch over peer memory (exchange_finalize_kernel), or the all-reduce followed by the finalize launch.
+static int exchange_and_finalize(desman_ctx *c, unsigned long long *red_prev, const double *gamma, const double *eta, int it,
+                                 const StoreBufs &sb, bool copy_now)
+{
+    const size_t n = (size_t)c->S * c->G + 16;
+    if (c->xch_ok && (int)n + 3 <= c->xch_cap_words && c->xch_fuse) {
+        XchParams x;
+        for (int r = 0; r < XCH_MAX_RANKS; r++) x.mail[r] = c->xch_mail[r];
+        x.rank = c->rank; x.nranks = c->nranks; x.words = (int)n; x.cap_words = c->xch_cap_words;
+        x.data2 = red_prev; x.words2 = 3;
+        x.seq = ++c->xch_seq; x.data = c->stats; x.err = c->xch_err;
+        const FinalParams f = final_params(c, red_prev, gamma, eta, it, 0, sb, true, nullptr);
+        {
+            KSpan k(c, DESMAN_K_OTHER);
+            CU(launch_k(c, exchange_finalize_kernel, 1, 512, 0, x, f));
+        }
+        if (copy_now) RET(launch_star_copy(c));
+        CU(cudaGetLastError());
+        return DESMAN_OK;
+    }
+    RET(allreduce_stats(c, red_prev));
+    return launch_finalize_only(c, red_prev, gamma, eta, it, 0, sb, true, nullptr, copy_now);
 }
 
 static int require_state(desman_ctx *c)
@@ -1616,12 +1661,14 @@ extern "C" int desman_update(desman_ctx *c, int n_iter, double *gamma_store, dou
         RET(sync_table(c, !lagged && it > 0));
         RET(launch_mu(c, c->gamma, c->eta));                            // sampleMu   (:341)
         if (lagged && it > 0) {
-            RET(allreduce_stats(c, red_prev));
-            RET(launch_finalize_only(c, red_prev, c->gamma, c->eta, it - 1, 0, sb, true));   // ll, lp, stores, star of sweep it-1
+            // ll, lp, stores, star of sweep it-1; its MAP snapshot tau_star <- tau rides in the screening launch when that runs
+            c->star_fold = !c->fixed_tau && tau_runs_tc(c);
+            RET(exchange_and_finalize(c, red_prev, c->gamma, c->eta, it - 1, sb, !c->star_fold));
         } else RET(allreduce_stats(c));
         RET(launch_draw(c, c->stats, c->gamma, c->eta_new, c->esum_store + (size_t)it * 16));   // sampleGamma (:342) + sampleEta's draw (:347)
         // (early: the statistics and draw launches separate the screening pass from the maintenance launch that wrote its inputs)
-        if (!c->fixed_tau) RET(launch_tau(c, c->gamma, c->eta, true, true, (uint32_t)it, 0, nullptr, 1));       // sample_tau (:345), old eta (nchange cleared by sync_table)
+        if (!c->fixed_tau) RET(launch_tau(c, c->gamma, c->eta, true, true, (uint32_t)it, 0, nullptr, 1));
+        if (c->star_fold) return fail(DESMAN_ESTATE, "internal: the MAP snapshot was not taken by the screening launch");       // sample_tau (:345), old eta (nchange cleared by sync_table)
         if (lagged) RET(launch_ll(c, c->gamma, c->eta_new, c->eta, true));     // eta <- new (:347); sum n*log p of sweep it, reduced with the next exchange
         else RET(launch_finalize(c, c->gamma, c->eta_new, it, 0, sb, true, c->eta, false));   // eta <- new (:347); ll, lp, stores, star (:349-358)
         sweep_end(c);
@@ -1816,6 +1863,7 @@ extern "C" int desman_comm_init(desman_ctx *c, const char id[128], int rank, int
     // against the oracle).  Measured per sweep at C3 per GPU, one exchange per sweep, event-timed incl. the wait for the slowest
     // rank: 2 GPUs NCCL 43.8 us; 4 GPUs peer memory 21.6 us; round 1 at 8 GPUs, two exchanges: 45.7 us vs 64.8 us with NCCL
     const char *env = getenv("DESMAN_B200_P2P");
+    if (const char *ef = getenv("DESMAN_B200_XCH_FUSE")) c->xch_fuse = atoi(ef) ? 1 : 0;   // (A/B of the fused exchange + bookkeeping launch)
     if (env ? !atoi(env) : nranks < 2) return DESMAN_OK;
     if (nranks > XCH_MAX_RANKS || !g_nccl.AllGather) return DESMAN_OK;
     const int cap = 4096;                                             // words per contribution (S*G + 16 must fit)
@@ -1877,6 +1925,7 @@ extern "C" int desman_set_option(desman_ctx *c, const char *name, int64_t value)
     }
     if (!strcmp(name, "tau_group_mma")) { c->tau_group_mma = value ? 1 : 0; return DESMAN_OK; }
     if (!strcmp(name, "tau_open")) { c->tau_open = value ? 1 : 0; return DESMAN_OK; }
+    if (!strcmp(name, "xch_fuse")) { c->xch_fuse = value ? 1 : 0; return DESMAN_OK; }
     if (!strcmp(name, "tau_group_tc")) { c->tau_group_tc = value ? 1 : 0; c->agg_valid = false; return DESMAN_OK; }
     if (!strcmp(name, "tau_group")) { c->tau_group = (value == 0 || value == 1) ? (int)value : 2; c->agg_valid = false; return DESMAN_OK; }
     return fail(DESMAN_EINVAL, "unknown option '%s'", name);

@@ -11,6 +11,7 @@
 // The sums are taken in rank order on every rank: identical results everywhere (the payloads are integers anyway).
 #pragma once
 #include "common.cuh"
+#include "misc_kernels.cuh"
 
 #define XCH_MAX_RANKS 16
 
@@ -37,9 +38,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     return v;
 }
 
-__global__ void __launch_bounds__(512) exchange_sum_kernel(XchParams p)
+// (all threads of the block; contains block barriers)
+__device__ __forceinline__ void exchange_sum_body(const XchParams &p)
 {
-    pdl_enter();         // a link of the sweep's dependent chain (common.cuh): scheduled under the tail of the statistics kernel
     const int n = p.nranks, W1 = p.words, W = p.words + p.words2;
     const size_t slot_off = ((size_t)(p.seq & 1ull) * n + p.rank) * p.cap_words;
     // 1. my contribution into every mailbox (peer stores over NVLink; the local one is a plain store)
@@ -68,4 +69,29 @@ __global__ void __launch_bounds__(512) exchange_sum_kernel(XchParams p)
         for (int r = 0; r < n; r++) acc += mine[(size_t)r * p.cap_words + j];
         if (j < W1) p.data[j] = acc; else p.data2[j - W1] = acc;
     }
+}
+
+__global__ void __launch_bounds__(512) exchange_sum_kernel(XchParams p)
+{
+    pdl_enter();         // a link of the sweep's dependent chain (common.cuh): scheduled under the tail of the statistics kernel
+    exchange_sum_body(p);
+}
+
+// The exchange of sweep k and the lp / stores / MAP bookkeeping of sweep k-1 that follows it in the sharded chain, as ONE launch:
+// both are single-block latency kernels, and a hand-over between two launches costs more than either's work.  The words the
+// bookkeeping reads (f.red_i) are the second segment of the exchange (x.data2), summed by this very block.
+__global__ void __launch_bounds__(512) exchange_finalize_kernel(XchParams x, FinalParams f)
+{
+    __shared__ double sh[256];
+    __shared__ int upd;
+#if !PDL_EARLY
+    pdl_enter();
+#endif
+    const FinalEarly e = finalize_early(f, sh);       // log-priors of gamma / eta of sweep k-1: drawn several grids ago
+#if PDL_EARLY
+    pdl_enter();
+#endif
+    exchange_sum_body(x);
+    __syncthreads();                                  // (the sums written by other threads of this block: visible to thread 0)
+    finalize_late(f, e, &upd);
 }

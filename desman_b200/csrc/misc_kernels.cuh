@@ -191,43 +191,40 @@ struct FinalParams {
     int *flag;                // 1 when the star state must be replaced
 };
 
-// logPosterior (HaploSNP_Sampler.py:444-461) + star bookkeeping (:326-332, :351-358)
-__global__ void __launch_bounds__(256) finalize_sweep_kernel(FinalParams p)
+// logPosterior (HaploSNP_Sampler.py:444-461) + star bookkeeping (:326-332, :351-358), in two parts that the fused
+// exchange + finalize kernel of the sharded chain (exchange_kernel.cuh) shares with finalize_sweep_kernel.  Both parts are
+// executed by ALL threads of a block of >= 256 threads (they contain block barriers); threads >= 256 only take part in those.
+struct FinalEarly { double prior, lp_star; };
+// part 1: the log-priors and lp_star -- nothing of it was written by the grid right before (see finalize_sweep_kernel)
+__device__ __forceinline__ FinalEarly finalize_early(const FinalParams &p, double *sh /* [256] shared */)
 {
-    // The log-priors and the bookkeeping words read below were written at least two grids ago (gamma, eta_new: the draw
-    // kernel; stale slots, orphans: the tau kernels; lp_star: the previous finalize) -- the grid right before this one is the
-    // log-likelihood pass or the exchange, which write red_i only.  So everything but red_i is formed before pdl_enter(),
-    // under the tail of that grid (PDL_EARLY, common.cuh).
-#if !PDL_EARLY
-    pdl_enter();
-#endif
-    KPROF_SCOPE(KP_FIN);
-    __shared__ double sh[256];
-    const int nG = p.S * p.G;
+    const int nG = p.S * p.G, t = threadIdx.x;
     double acc = 0.0;
-    for (int i = threadIdx.x; i < nG; i += 256) acc += (p.alpha - 1.0) * log(p.gamma[i]);
-    for (int i = threadIdx.x; i < 16; i += 256) acc += (p.delta - 1.0) * log(p.eta[i]);
-    sh[threadIdx.x] = acc;
+    if (t < 256) {
+        for (int i = t; i < nG; i += 256) acc += (p.alpha - 1.0) * log(p.gamma[i]);
+        for (int i = t; i < 16; i += 256) acc += (p.delta - 1.0) * log(p.eta[i]);
+        sh[t] = acc;
+    }
     __syncthreads();
     for (int m = 128; m > 0; m >>= 1) {
-        if (threadIdx.x < m) sh[threadIdx.x] += sh[threadIdx.x + m];
+        if (t < m) sh[t] += sh[t + m];
         __syncthreads();
     }
-    __shared__ int upd;
-    double prior = 0.0, lp_star = 0.0;
-    long long stale0 = 0, used = 0, orphans = 0;
-    if (threadIdx.x == 0) {
-        prior = sh[0] + p.S * (p.lg_alphaG - p.G * p.lg_alpha) + 4.0 * (p.lg_delta4 - 4.0 * p.lg_delta) +
-                p.V_total * (double)p.G * log(0.25);
-        lp_star = p.scal[0];
-        if (p.agg_ctl) { stale0 = (long long)p.agg_ctl[3]; used = (long long)*p.agg_nslots; }
-        if (p.gctl) orphans = (long long)p.gctl[GC_ORPHANS];
+    FinalEarly e;
+    e.prior = 0.0; e.lp_star = 0.0;
+    if (t == 0) {
+        e.prior = sh[0] + p.S * (p.lg_alphaG - p.G * p.lg_alpha) + 4.0 * (p.lg_delta4 - 4.0 * p.lg_delta) +
+                  p.V_total * (double)p.G * log(0.25);
+        e.lp_star = p.scal[0];
     }
-#if PDL_EARLY
-    pdl_enter();
-#endif
-    if (threadIdx.x == 0) {
-        const double ll = p.ll_const + (double)p.red_i[0] * p.ll_inv_scale, lp = ll + prior;
+    return e;
+}
+// part 2: needs red_i (the log-likelihood pass, or the exchange that summed it over the ranks)
+__device__ __forceinline__ void finalize_late(const FinalParams &p, const FinalEarly &e, int *upd /* shared */)
+{
+    const int nG = p.S * p.G, t = threadIdx.x;
+    if (t == 0) {
+        const double ll = p.ll_const + (double)p.red_i[0] * p.ll_inv_scale, lp = ll + e.prior;
         // upkeep wishes of the sweep (ll_table_kernel; summed over the ranks of a sharded chain by the exchange): a table rebuild
         // (which implies a regroup) and / or a regroup of the site groups, on every rank in the same sweep
         const unsigned long long wish = (unsigned long long)p.red_i[2];
@@ -237,30 +234,50 @@ __global__ void __launch_bounds__(256) finalize_sweep_kernel(FinalParams p)
             p.gctl[GC_CALM] = (double)p.red_i[1] <= p.V_total / 16.0;
             if (wish & 0xffffull) p.gctl[GC_REGROUP] = 1;
         }
-        (void)stale0; (void)used; (void)orphans;
         p.scal[2] = ll; p.scal[3] = lp;
         if (p.it >= 0) {
             if (p.ll_store) p.ll_store[p.it] = ll;
             if (p.lp_store) p.lp_store[p.it] = lp;
             if (p.nchange_store) p.nchange_store[p.it] = (double)p.red_i[1];
         }
-        upd = (p.it < 0) || (lp > lp_star);
-        if (upd) { p.scal[0] = lp; p.scal[1] = (double)(p.it < 0 ? 0 : p.it); }
-        *p.flag = upd;
+        *upd = (p.it < 0) || (lp > e.lp_star);
+        if (*upd) { p.scal[0] = lp; p.scal[1] = (double)(p.it < 0 ? 0 : p.it); }
+        *p.flag = *upd;
     }
     __syncthreads();
-    const bool u = upd != 0;
-    for (int i = threadIdx.x; i < nG; i += 256) {
-        const double x = p.gamma[i];
-        if (p.it >= 0 && p.gamma_store) p.gamma_store[(size_t)p.it * nG + i] = x;
-        if (u && p.star_mode == 0) p.gamma_star[i] = x;
+    const bool u = *upd != 0;
+    if (t < 256) {
+        for (int i = t; i < nG; i += 256) {
+            const double x = p.gamma[i];
+            if (p.it >= 0 && p.gamma_store) p.gamma_store[(size_t)p.it * nG + i] = x;
+            if (u && p.star_mode == 0) p.gamma_star[i] = x;
+        }
+        if (t < 16) {
+            const double x = p.eta[t];
+            if (p.it >= 0 && p.eta_store) p.eta_store[(size_t)p.it * 16 + t] = x;
+            if (u && p.star_mode == 0) p.eta_star[t] = x;
+            if (p.eta_commit) p.eta_commit[t] = x;
+        }
     }
-    if (threadIdx.x < 16) {
-        const double x = p.eta[threadIdx.x];
-        if (p.it >= 0 && p.eta_store) p.eta_store[(size_t)p.it * 16 + threadIdx.x] = x;
-        if (u && p.star_mode == 0) p.eta_star[threadIdx.x] = x;
-        if (p.eta_commit) p.eta_commit[threadIdx.x] = x;
-    }
+}
+
+__global__ void __launch_bounds__(256) finalize_sweep_kernel(FinalParams p)
+{
+    // The log-priors and the bookkeeping words read below were written at least two grids ago (gamma, eta_new: the draw
+    // kernel; lp_star: the previous finalize) -- the grid right before this one is the log-likelihood pass or the exchange,
+    // which write red_i only.  So everything but red_i is formed before pdl_enter(), under the tail of that grid (PDL_EARLY,
+    // common.cuh).
+#if !PDL_EARLY
+    pdl_enter();
+#endif
+    KPROF_SCOPE(KP_FIN);
+    __shared__ double sh[256];
+    __shared__ int upd;
+    const FinalEarly e = finalize_early(p, sh);
+#if PDL_EARLY
+    pdl_enter();
+#endif
+    finalize_late(p, e, &upd);
 }
 
 __global__ void copy_tau_if_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t n,

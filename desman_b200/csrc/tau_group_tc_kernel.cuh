@@ -61,6 +61,9 @@ struct TauGroupTcParams {
     unsigned long long *tier_counts;
     float *dbg;                // [V][3G] the sums D (log2 units) of every screened site, or nullptr (validation only)
     int early;                 // 1: control words, items and image are at least two grids old (see the kernel's prologue)
+    // sharded chain: the MAP snapshot tau_star <- tau of the previous sweep, if its bookkeeping (two grids ago) raised the flag;
+    // tau is not touched by this kernel, only by the list kernels after it
+    const uint8_t *star_src; uint8_t *star_dst; size_t star_n; const int *star_flag;
 };
 
 struct TcRec { int slot, count, img0; unsigned int code_lo, code_hi; int pad[3]; };
@@ -295,6 +298,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) tau_group_tc_kernel(TauGroupTcP
     // Only gamma / eta (the draw kernel's output) and the MT19937 words need the wait: table builders and epilogue.
     if (!p.early) pdl_enter();
     KPROF_SCOPE(KP_TGM);
+    if (p.star_flag && *p.star_flag) {
+        const size_t n16 = p.star_n / 16, i0 = (size_t)blockIdx.x * TC_THREADS + tid, st = (size_t)gridDim.x * TC_THREADS;
+        const uint4 *s4 = reinterpret_cast<const uint4 *>(p.star_src);
+        uint4 *d4 = reinterpret_cast<uint4 *>(p.star_dst);
+        for (size_t i = i0; i < n16; i += st) d4[i] = s4[i];
+        for (size_t i = n16 * 16 + i0; i < p.star_n; i += st) p.star_dst[i] = p.star_src[i];
+    }
     const int *gctl = p.grp.gctl;
     const int nitems = grp_active(gctl, 1) ? gctl[GC_NITEMS] : 0;
     if ((int)blockIdx.x >= nitems) {
