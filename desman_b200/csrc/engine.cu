@@ -2,6 +2,7 @@
 // the sweep drivers and the C-ABI declared in include/desman_b200.h.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <emmintrin.h>
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
@@ -154,6 +155,7 @@ struct desman_ctx {
     // pattern groups for the screening pass of the tau update (tau_group_kernel.cuh)
     int tau_group = 2;                       // 0: off, 1: on, 2: on iff the ~12*2^G biallelic patterns are <= V/2
     int tau_group_mma = 1;                   // 1: tensor-core form of the screening pass where it applies; 0: FFMA form
+    uint2 *pack16[2] = {nullptr, nullptr};   // device staging of a chunk of 4 x uint16 count cells (desman_set_counts)
     bool star_fold = false;                  // sharded chain: the next screening launch takes the MAP snapshot (tau_star <- tau if flag)
     int xch_fuse = 1;                        // exchange + bookkeeping of the previous sweep as one launch (peer-memory exchange only)
     int tau_open = 1;                        // 1: the work list of the screening pass is walked by tau_open_kernel (one CTA per site)
@@ -350,7 +352,8 @@ extern "C" int desman_ctx_destroy(desman_ctx *c)
     }
     if (c->xch_err) cudaFree(c->xch_err);
     if (c->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(c->comm);
-    for (void *q : {(void *)c->img, (void *)c->img_site, (void *)c->img_nsite, (void *)c->site_row, (void *)c->esum_store}) if (q) dfree(c, q);
+    for (void *q : {(void *)c->img, (void *)c->img_site, (void *)c->img_nsite, (void *)c->site_row, (void *)c->esum_store, (void *)c->pack16[0],
+                    (void *)c->pack16[1]}) if (q) dfree(c, q);
     void *ptrs[] = {c->counts, c->tau, c->tau_star, c->gamma, c->eta, c->eta_new, c->gamma_star, c->eta_star, c->stats,
                     c->red_base, c->agg_ctl, c->scal, c->flag, c->tau_cnt, c->tau_last, c->mt_state, c->words,
                     c->scratch, c->flush_buf, c->tiers, c->agg_keys, c->agg_code, c->agg_N, c->agg_ids, c->agg_nslots, c->agg_classM,
@@ -471,35 +474,70 @@ extern "C" int desman_set_counts(desman_ctx *c, const int64_t *variants, int64_t
     std::atomic<int> bad(0);
     std::atomic<long long> total(0), or_all(0);
     int buf = 0;
+    // Counts below 2^16 (the usual case) travel as 4 x uint16 per cell -- a quarter of the int64 tensor's bytes over PCIe and
+    // half the host-side writes -- and are widened to the canonical int32x4 cells by a kernel; a chunk that holds a larger
+    // count is simply packed again as int32x4.  The host pass is bound by memory traffic (205 MB of int64 to read at C3).
+    if (!c->pack16[0]) {
+        CU(dmalloc(c, &c->pack16[0], chunk_cells * sizeof(uint2)));
+        CU(dmalloc(c, &c->pack16[1], chunk_cells * sizeof(uint2)));
+    }
     for (size_t off = 0; off < ncell; off += chunk_cells, buf ^= 1) {
         const size_t n = (ncell - off < chunk_cells) ? ncell - off : chunk_cells;
         CU(cudaEventSynchronize(c->pin_ev[buf]));                       // previous copy out of this buffer finished
         int4 *dst = g_pin[buf];
         const int64_t *src = variants + off * 4;
         const int nt = host_threads(n);
-        auto work = [&](int t) {
+        std::atomic<long long> or_chunk(0), sum_chunk(0);
+        auto work = [&](int t, bool narrow) {
             const size_t lo = n * t / nt, hi = n * (t + 1) / nt;
             int64_t orv = 0, sum = 0, orc = 0;
-            for (size_t i = lo; i < hi; i++) {
-                const int64_t a = src[4 * i], b = src[4 * i + 1], d = src[4 * i + 2], e = src[4 * i + 3];
-                orc |= a | b | d | e;
-                orv |= a | b | d | e | (DESMAN_MAX_COUNT - a) | (DESMAN_MAX_COUNT - b) | (DESMAN_MAX_COUNT - d) | (DESMAN_MAX_COUNT - e);
-                sum += a + b + d + e;
-                dst[i] = make_int4((int)a, (int)b, (int)d, (int)e);
+            if (narrow) {
+                long long *d16 = reinterpret_cast<long long *>(dst);
+                for (size_t i = lo; i < hi; i++) {
+                    const int64_t a = src[4 * i], b = src[4 * i + 1], d = src[4 * i + 2], e = src[4 * i + 3];
+                    orc |= a | b | d | e;
+                    sum += a + b + d + e;
+                    // (streaming stores: the pinned buffer is written once and read by the DMA engine -- no read-for-ownership)
+                    _mm_stream_si64(d16 + i, (long long)(((uint64_t)a & 0xffffull) | (((uint64_t)b & 0xffffull) << 16) |
+                                                         (((uint64_t)d & 0xffffull) << 32) | (((uint64_t)e & 0xffffull) << 48)));
+                }
+                or_chunk |= orc;                                        // (accounted by the caller if the whole chunk is in range)
+                sum_chunk += sum;
+            } else {
+                for (size_t i = lo; i < hi; i++) {
+                    const int64_t a = src[4 * i], b = src[4 * i + 1], d = src[4 * i + 2], e = src[4 * i + 3];
+                    orc |= a | b | d | e;
+                    orv |= a | b | d | e | (DESMAN_MAX_COUNT - a) | (DESMAN_MAX_COUNT - b) | (DESMAN_MAX_COUNT - d) | (DESMAN_MAX_COUNT - e);
+                    sum += a + b + d + e;
+                    _mm_stream_si128(reinterpret_cast<__m128i *>(dst + i), _mm_set_epi32((int)e, (int)d, (int)b, (int)a));
+                }
+                total += sum;
+                or_all |= orc;
+                if (orv < 0) bad = 1;                                   // a negative count or one above the limit
             }
-            total += sum;
-            or_all |= orc;
-            if (orv < 0) bad = 1;                                       // a negative count or one above the limit
+            _mm_sfence();
         };
-        if (nt == 1) work(0);
-        else {
+        auto run = [&](bool narrow) {
+            if (nt == 1) { work(0, narrow); return; }
             std::vector<std::thread> th;
-            for (int t = 0; t < nt; t++) th.emplace_back(work, t);
+            for (int t = 0; t < nt; t++) th.emplace_back(work, t, narrow);
             for (auto &x : th) x.join();
+        };
+        run(true);
+        const long long oc = or_chunk.load();
+        if (oc >= 0 && oc < 65536) {
+            total += sum_chunk.load();
+            or_all |= oc;
+            CU(cudaMemcpyAsync(c->pack16[buf], dst, n * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaEventRecord(c->pin_ev[buf], c->stream));
+            widen_counts_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(c->pack16[buf], c->counts + off, n);
+        } else {                                                        // a count >= 2^16 (or a negative one): the wide form
+            run(false);
+            CU(cudaMemcpyAsync(c->counts + off, dst, n * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaEventRecord(c->pin_ev[buf], c->stream));
         }
-        CU(cudaMemcpyAsync(c->counts + off, dst, n * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
-        CU(cudaEventRecord(c->pin_ev[buf], c->stream));
     }
+    CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
     if (bad) { c->V = 0; return fail(DESMAN_EINVAL, "counts must be in [0, %d] per (v,s,base) cell", DESMAN_MAX_COUNT); }
     if (V != c->V || S != c->S) c->G = 0;  // state must be (re)set for a new shape

@@ -280,6 +280,15 @@ __global__ void __launch_bounds__(256) finalize_sweep_kernel(FinalParams p)
     finalize_late(p, e, &upd);
 }
 
+// count cells uploaded as 4 x uint16 -> the canonical int32x4 cells (desman_set_counts)
+__global__ void widen_counts_kernel(const uint2 *__restrict__ src, int4 *__restrict__ dst, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint2 w = src[i];
+        dst[i] = make_int4((int)(w.x & 0xffffu), (int)(w.x >> 16), (int)(w.y & 0xffffu), (int)(w.y >> 16));
+    }
+}
+
 __global__ void copy_tau_if_kernel(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, size_t n,
                                    const int *__restrict__ flag)
 {

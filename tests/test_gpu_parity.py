@@ -113,6 +113,30 @@ def test_tau_philox_bit_exact_vs_oracle(eng_mod, oracle_mod, V, S, G):
     e.close()
 
 
+@pytest.mark.parametrize("top", [65535, 65536, 70000, 2**24])
+def test_counts_upload_narrow_and_wide_cells(eng_mod, oracle_mod, top):
+    """desman_set_counts ships counts < 2^16 as 4 x uint16 per cell and widens them on the device; a chunk with a larger count
+    takes the int32x4 form: the tau step (which reads every cell) must equal the oracle's on both sides of the boundary."""
+    V, S, G = 48, 40, 4
+    p = synth_problem(V, S, G, depth=30.0, seed=5, ambiguous=True)
+    p["counts"][3, 7, 1] = top
+    p["counts"][V - 1, S - 1, 3] = min(top, 65535)
+    e = eng_mod.Engine(0, seed=9, rng_mode=eng_mod.RNG_PHILOX)
+    e.set_counts(p["counts"])
+    tau_o = onehot(p["tau0"])
+    e.set_state(tau_o, p["gamma0"], p["eta0"])
+    for k in range(2):
+        e.set_rng(9, sweep=k)
+        n_gpu = e.sample_tau()
+        n_cpu = oracle_mod.sample_tau_philox(tau_o, p["gamma0"], p["eta0"], p["counts"], 9, k)
+        assert n_gpu == n_cpu
+        assert np.array_equal(e.get_tau_index(), np.argmax(tau_o, 2).astype(np.uint8))
+    ll_gpu = e.loglik()
+    assert np.isclose(ll_gpu[0] if isinstance(ll_gpu, (tuple, list)) else ll_gpu,
+                      oracle_mod.loglik(tau_o, p["gamma0"], p["eta0"], p["counts"]), rtol=1e-10)
+    e.close()
+
+
 @pytest.mark.parametrize("mode", [0, 1])
 @pytest.mark.parametrize("V,S,G", SHAPES)
 def test_mu_stats_bit_exact_vs_oracle(eng_mod, oracle_mod, V, S, G, mode):

@@ -16,7 +16,7 @@ from desman_b200.synth import CHAIN_SEED, onehot, synth_counts  # noqa: E402
 
 p = synth_counts(100000, 64, 8)
 for rep in range(2):
-    hs = HaploSNP_Sampler(p["counts"], 8, RandomState(1), max_iter=20, seed=CHAIN_SEED)
+    hs = HaploSNP_Sampler(p["counts"], 8, RandomState(1), max_iter=int(sys.argv[1]) if len(sys.argv) > 1 else 20, seed=CHAIN_SEED)
     hs.tau, hs.gamma, hs.eta = onehot(p["tau0"]), p["gamma0"].copy(), p["eta0"].copy()
     t0 = time.perf_counter()
     if rep == 1:
@@ -26,4 +26,4 @@ for rep in range(2):
         pr.disable()
     print("update() wall %.1f ms (device %.1f ms)" % (1e3 * (time.perf_counter() - t0), hs._timing["elapsed_ms"]))
     hs.close()
-pstats.Stats(pr).sort_stats("cumulative").print_stats(14)
+pstats.Stats(pr).sort_stats("cumulative").print_stats(22)
