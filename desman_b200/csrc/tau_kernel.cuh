@@ -132,10 +132,11 @@ __device__ __noinline__ double tau_exact_logp_cand(const int4 *tile, const doubl
         }
         const double gg = gT[g * Sp + s];
         const double f0 = (double)(float)n.x, f1 = (double)(float)n.y, f2 = (double)(float)n.z, f3 = (double)(float)n.w;
-        if (n.x) L = fma(f0, log(fma(e[0], gg, b0)), L);
-        if (n.y) L = fma(f1, log(fma(e[1], gg, b1)), L);
-        if (n.z) L = fma(f2, log(fma(e[2], gg, b2)), L);
-        if (n.w) L = fma(f3, log(fma(e[3], gg, b3)), L);
+        // (branch-free: the four logs of a sample are independent and overlap; a zero count takes log(1) = 0 and
+        // fma(0, 0, L) == L, the value the skipped term leaves in tau_exact_logp)
+        const double l0 = log(n.x ? fma(e[0], gg, b0) : 1.0), l1 = log(n.y ? fma(e[1], gg, b1) : 1.0),
+                     l2 = log(n.z ? fma(e[2], gg, b2) : 1.0), l3 = log(n.w ? fma(e[3], gg, b3) : 1.0);
+        L = fma(f0, l0, L); L = fma(f1, l1, L); L = fma(f2, l2, L); L = fma(f3, l3, L);
     }
     return warp_sum(L);
 }

@@ -62,6 +62,18 @@ __global__ void __launch_bounds__(TAUO_WARPS * 32, 6) tau_open_kernel(TauParams 
     const float cancel0 = ccan / fmaxf(qmin, TAU_QMIN);
     const uint32_t fullG = (G >= 32) ? 0xffffffffu : ((1u << G) - 1u);
 #if PDL_EARLY
+    if (blockIdx.x == gridDim.x - 1) {
+        // One block (the last: it has a site only when the list is longer than the grid) walks the FP64 recompute of tier 3
+        // once on placeholder counts before its dependency wait.  The step is taken by one site in a few sweeps, always on
+        // instructions that nobody has touched since the L2 was last flushed: that site -- and with it the launch, and under
+        // sharding every rank -- waited ~8 us for code from HBM.  Here the lines are fetched under the tail of the screening pass.
+        for (int s = threadIdx.x; s < Sp; s += blockDim.x) tile[s] = make_int4(1, 1, 1, 1);
+        __syncthreads();
+        const double La = tau_exact_logp_cand(tile, gT, eta_s, 0ull, 0, S, Sp, G, lane, wib & 3);
+        double Lw[4] = {La, La - 1.0, La - 2.0, La - 3.0};
+        if (tau_exact_pick(Lw, 0.3) == 77) gmin_bits = 0u;                 // (never true: keeps the calls)
+        __syncthreads();
+    }
     pdl_enter();
 #endif
     KPROF_SCOPE(KP_TAUO);
