@@ -75,8 +75,9 @@ class Init_NMFT:
         finally:
             eng.close()
         self.tau, self.gamma, self.n_iter, self.div, self.div_trace = tau, gamma, it, div, trace
-        for i in range(0, it, 100):                                                   # :112-113 / :146-147
-            logging.info('NTF Iter %d, div = %f' % (i, trace[i]))
+        if fix_gamma != 2:
+            for i in range(0, it, 100):                                               # :112-113 / :146-147
+                logging.info('NTF Iter %d, div = %f' % (i, trace[i]))
 
     def factorize(self):
         """Init_NMFT.py:98-115"""
@@ -91,7 +92,41 @@ class Init_NMFT:
             self._run(True)
 
     def factorize_gamma(self):
-        raise NotImplementedError("factorize_gamma (Init_NMFT.py:117-132) has no caller in the reference")
+        """Init_NMFT.py:117-132: tau stays fixed (set by the caller), no random start, no eps clamp."""
+        for run in range(self.n_run):
+            self._run(2)
+            for i in range(0, self.n_iter, 100):                                      # :129-130
+                print(str(i) + "," + str(self.div_trace[i]))
+
+    # ------------------------------------------------------------------ single steps (the bodies of the reference's loops)
+    def _adjustment_input(self, X):
+        return np.maximum(X, np.finfo(self.tau.dtype).eps)                            # :93-97
+
+    def _step(self, mode, max_iter):
+        eng = Engine(self._device, seed=0)
+        try:
+            tau, gamma, it, div, _ = eng.nmft_factorize(self.snps, self.tau, np.ascontiguousarray(self.gamma), max_iter=max_iter,
+                                                        min_change=-1.0, fix_gamma=mode)
+        finally:
+            eng.close()
+        return tau, gamma, div
+
+    def div_objective(self):
+        """KL divergence of X from tau gamma with the factors as they are (:152-156)."""
+        return self._step(1, 0)[2]
+
+    def div_update(self):
+        """One multiplicative update of gamma, then tau (:158-181) -- followed by the eps clamp of _adjustment(), which the
+        reference's factorize() applies right after every div_update() (:107-108)."""
+        self.tau, self.gamma, self.div = self._step(0, 1)
+
+    def div_update_tau(self):
+        """One multiplicative update of tau with gamma fixed (:192-205)."""
+        self.tau, self.gamma, self.div = self._step(1, 1)
+
+    def div_update_gamma(self):
+        """One multiplicative update of gamma with tau fixed (:183-190)."""
+        self.tau, self.gamma, self.div = self._step(2, 1)
 
     # ------------------------------------------------------------------ results
     def get_gamma(self):

@@ -52,7 +52,7 @@ struct NmftParams {
     NmftState *st_in, *st_out;
     double *trace;
     int V, S, G;
-    int max_iter, fix_gamma;
+    int max_iter, fix_gamma;   // fix_gamma: 0 factorize() (both factors, eps clamps), 1 factorize_tau() (tau only), 2 factorize_gamma() (gamma only)
     double min_change;
 };
 
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) nmft_gamma_kernel(NmftParams p)
     const int lane = threadIdx.x & 31, gsub = threadIdx.x >> 5;       // 8 strain rows at a time
     const int s_local = lane >> 3, j = lane & 7;
     const int s = blockIdx.x * NMFT_GS + s_local;
-    if (!p.fix_gamma) {
+    if (p.fix_gamma != 1) {
         for (int g0 = 0; g0 < G; g0 += 8) {
             const int g = g0 + gsub;
             double newg = 0.0;
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(256) nmft_gamma_kernel(NmftParams p)
             for (int g = 0; g < G; g++) {
                 const double x = (G > 1) ? col[g][sl] / cs : 1.0;                         // :166
                 p.gamma[g * S + ss] = x;
-                p.gamma_adj[g * S + ss] = fmax(x, NMFT_EPS);                              // _adjustment :88-91
+                p.gamma_adj[g * S + ss] = p.fix_gamma ? x : fmax(x, NMFT_EPS);            // _adjustment :88-91 (factorize() only: :126 is commented out)
             }
         }
     }
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(256) nmft_gamma_kernel(NmftParams p)
 // Shared-memory rows are padded by 2 doubles so that lanes reading different rows at the same sample hit different banks.
 __global__ void __launch_bounds__(NMFT_WARPS * 32) nmft_tau_kernel(NmftParams p)
 {
-    if (p.st_out->done) return;
+    if (p.st_out->done || p.fix_gamma == 2) return;         // (factorize_gamma, Init_NMFT.py:117-132: tau stays)
     extern __shared__ double sm[];
     const int S = p.S, G = p.G, Sr = S + 2;
     double *gm = sm;                                   // [G][Sr] gamma'
@@ -395,7 +395,7 @@ static int nmft_factorize_impl(cudaStream_t stream, int sm_count, const int64_t 
     }
     cudaEventRecord(ev1, stream);
     NMFT_CU(cudaMemcpyAsync(hT.data(), dT, nT * 8, cudaMemcpyDeviceToHost, stream));
-    NMFT_CU(cudaMemcpyAsync(hG.data(), fix_gamma ? dG : dGa, nG * 8, cudaMemcpyDeviceToHost, stream));
+    NMFT_CU(cudaMemcpyAsync(hG.data(), fix_gamma == 1 ? dG : dGa, nG * 8, cudaMemcpyDeviceToHost, stream));
     if (div_trace && hst.iter > 0) NMFT_CU(cudaMemcpyAsync(div_trace, dTr, (size_t)hst.iter * 8, cudaMemcpyDeviceToHost, stream));
     NMFT_CU(cudaStreamSynchronize(stream));
     for (int64_t v = 0; v < V; v++)

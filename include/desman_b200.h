@@ -115,7 +115,9 @@ int desman_get_tau_sum_u32(desman_ctx *ctx, uint32_t *tau_sum /*V*G*4*/);   /* s
 
 /* NMFT initialiser (Init_NMFT.py).  snps int64 [V,S,4]; tau [4V,G] (rows v + a*V) and gamma [G,S] hold
  * the random initial factors on entry and the result on exit.  fix_gamma = 0: factorize (:98-115);
- * fix_gamma = 1: factorize_tau (:134-149).  div_trace (may be NULL) gets div after each iteration. */
+ * fix_gamma = 1: factorize_tau (:134-149); fix_gamma = 2: factorize_gamma (:117-132: tau stays, no eps clamps).  max_iter = 0
+ * evaluates div_objective (:152-156) of the factors as they are (with fix_gamma != 0); max_iter = 1 with min_change < 0 is one
+ * div_update / div_update_tau / div_update_gamma step (:158-205).  div_trace (may be NULL) gets div after each iteration. */
 int desman_nmft_factorize(desman_ctx *ctx, const int64_t *snps, int64_t V, int S, int G,
                           double *tau, double *gamma, int max_iter, double min_change, int fix_gamma,
                           int *n_iter_done, double *div_final, double *div_trace);

@@ -391,6 +391,37 @@ def make_assign_kat():
     np.savez_compressed(os.path.join(HERE, "assign_kat.npz"), **out)
 
 
+def make_nmft_steps_kat():
+    """Single steps of the UNMODIFIED Init_NMFT class (div_objective, div_update + _adjustment, div_update_tau,
+    div_update_gamma, factorize_gamma) on small problems: pins desman_b200.Init_NMFT's step methods."""
+    out = {}
+    for ci, (V, S, G, seed) in enumerate([(40, 12, 3, 7), (25, 40, 5, 11), (30, 9, 1, 3)]):
+        rng = np.random.default_rng(seed)
+        counts = synth_counts(rng, V, S, 30.0)
+        n = inmft.Init_NMFT(counts, G, RandomState(seed), max_iter=25)
+        n.random_initialize()
+        n._adjustment()
+        out[f"c{ci}_meta"] = np.array([V, S, G, seed], dtype=np.int64)
+        out[f"c{ci}_counts"] = counts.astype(np.int32)
+        out[f"c{ci}_tau0"] = n.tau.copy(); out[f"c{ci}_gamma0"] = n.gamma.copy()
+        out[f"c{ci}_div0"] = np.array(n.div_objective())
+        n.div_update(); n._adjustment()
+        out[f"c{ci}_tau1"] = n.tau.copy(); out[f"c{ci}_gamma1"] = n.gamma.copy(); out[f"c{ci}_div1"] = np.array(n.div_objective())
+        n.div_update_tau()
+        out[f"c{ci}_tau2"] = n.tau.copy(); out[f"c{ci}_div2"] = np.array(n.div_objective())
+        n.div_update_gamma()
+        out[f"c{ci}_gamma3"] = n.gamma.copy(); out[f"c{ci}_div3"] = np.array(n.div_objective())
+        buf = io.StringIO()
+        so, sys.stdout = sys.stdout, buf
+        try:
+            n.factorize_gamma()
+        finally:
+            sys.stdout = so
+        out[f"c{ci}_gamma4"] = n.gamma.copy(); out[f"c{ci}_div4"] = np.array(n.div_objective())
+    np.savez_compressed(os.path.join(HERE, "nmft_steps_kat.npz"), **out)
+    print("nmft_steps_kat.npz written")
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["kat", "loglik", "mu", "input", "i3"]
     oracle.build()
@@ -402,6 +433,8 @@ if __name__ == "__main__":
         make_mu_stats_ref()
     if "assign" in what:
         make_assign_kat()
+    if "nmft" in what:
+        make_nmft_steps_kat()
     if "input" in what:
         make_cog0015_input()
     if "i3" in what:

@@ -41,6 +41,37 @@ def test_nmft_matches_oracle(oracle_mod, V, S, G, fix):
     assert np.array_equal(a[clear], b[clear]) and clear.mean() > 0.9
 
 
+def test_nmft_single_steps_match_the_reference_class(capsys):
+    """div_objective / div_update (+ _adjustment) / div_update_tau / div_update_gamma / factorize_gamma of the UNMODIFIED
+    reference class (tests/golden/make_golden.py nmft) against the same methods of desman_b200.Init_NMFT."""
+    from numpy.random import RandomState
+
+    from desman_b200.Init_NMFT import Init_NMFT
+    z = np.load(os.path.join(GOLDEN, "nmft_steps_kat.npz"))
+    ci = 0
+    while f"c{ci}_meta" in z:
+        V, S, G, seed = (int(x) for x in z[f"c{ci}_meta"])
+        n = Init_NMFT(z[f"c{ci}_counts"].astype(np.int64), G, RandomState(seed), max_iter=25)
+        n.tau, n.gamma = z[f"c{ci}_tau0"].copy(), z[f"c{ci}_gamma0"].copy()
+        rt = dict(rtol=1e-9, atol=1e-300)
+        assert np.isclose(n.div_objective(), float(z[f"c{ci}_div0"]), rtol=1e-10)
+        n.div_update(); n._adjustment()
+        assert np.allclose(n.tau, z[f"c{ci}_tau1"], **rt) and np.allclose(n.gamma, z[f"c{ci}_gamma1"], **rt)
+        assert np.isclose(n.div_objective(), float(z[f"c{ci}_div1"]), rtol=1e-10)
+        n.div_update_tau()
+        assert np.allclose(n.tau, z[f"c{ci}_tau2"], **rt) and np.allclose(n.gamma, z[f"c{ci}_gamma1"], **rt)
+        assert np.isclose(n.div_objective(), float(z[f"c{ci}_div2"]), rtol=1e-10)
+        n.div_update_gamma()
+        assert np.allclose(n.gamma, z[f"c{ci}_gamma3"], **rt) and np.allclose(n.tau, z[f"c{ci}_tau2"], **rt)
+        assert np.isclose(n.div_objective(), float(z[f"c{ci}_div3"]), rtol=1e-10)
+        n.factorize_gamma()
+        assert capsys.readouterr().out.startswith("0,")                      # Init_NMFT.py:129-130 prints "iter,div"
+        assert np.allclose(n.gamma, z[f"c{ci}_gamma4"], rtol=1e-8, atol=1e-300) and np.allclose(n.tau, z[f"c{ci}_tau2"], **rt)
+        assert np.isclose(n.div_objective(), float(z[f"c{ci}_div4"]), rtol=1e-10)
+        ci += 1
+    assert ci == 3
+
+
 def test_nmft_class_reproduces_reference_on_cog0015():
     """Init_NMFT(...).factorize() with the reference's seed: the RandomState start, the 5000-iteration
     divergence trace, gamma and the discretised tau handed to the sampler all match the unmodified reference."""
