@@ -219,21 +219,34 @@ __global__ void __launch_bounds__(TAUO_WARPS * 32, 6) tau_open_kernel(TauParams 
 #ifdef KPROF
             const unsigned long long kq1 = gtimer();
 #endif
-            int k = 0;
-            for (int g = 0; g < G; g++) {
-                if (!((pending >> g) & 1u)) continue;
-                if ((k++ % TAUO_WARPS) != wib) continue;
-                int tier = 0;
-                const int t = step(code, g, from_screening, nlane, mlP, &tier);
-                if (lane == 0) {
-                    t_s[g] = t; t_s[32 + g] = tier;
-                    if (t >= 0 && t != code_get(code, g)) atomicMin(&first_flip, g);
-                }
-            }
+            // passes of TAUO_WARPS strains in ascending order; a flip found in one pass makes every later pass void (its strains
+            // come after the flip and go through the next round anyway), so the passes stop there
+            const int npend = __popc(pending);
+            uint32_t rest = pending;
 #ifdef KPROF
-            const unsigned long long kq2 = gtimer();
+            unsigned long long kq2 = kq1;
 #endif
-            __syncthreads();
+            for (int base = 0; base < npend; base += TAUO_WARPS) {
+                int g = -1;
+                for (int k = 0; k < TAUO_WARPS && rest; k++) {             // the k-th lowest pending strain of this pass
+                    const int gl = __ffs(rest) - 1;
+                    rest &= rest - 1u;
+                    if (k == wib) g = gl;
+                }
+                if (g >= 0) {
+                    int tier = 0;
+                    const int t = step(code, g, from_screening, nlane, mlP, &tier);
+                    if (lane == 0) {
+                        t_s[g] = t; t_s[32 + g] = tier;
+                        if (t >= 0 && t != code_get(code, g)) atomicMin(&first_flip, g);
+                    }
+                }
+#ifdef KPROF
+                kq2 = gtimer();
+#endif
+                __syncthreads();
+                if (first_flip < G) break;                                  // (uniform: read after the barrier)
+            }
 #ifdef KPROF
             const unsigned long long kq3 = gtimer();
             if (threadIdx.x == 0) { kp_q[0] += kq1 - kq0; kp_q[1] += kq2 - kq1; kp_q[2] += kq3 - kq2; }
