@@ -235,7 +235,9 @@ __global__ void __launch_bounds__(TAUO_WARPS * 32, 6) tau_open_kernel(TauParams 
                 }
                 if (g >= 0) {
                     int tier = 0;
-                    const int t = step(code, g, from_screening, nlane, mlP, &tier);
+                    // (after a flip, the steps the screening pass had left open skip the gap test as well: it failed on a margin of
+                    // tens of nats under the old pattern, and the brackets decide either way)
+                    const int t = step(code, g, from_screening || (screened && ((todo >> g) & 1u)), nlane, mlP, &tier);
                     if (lane == 0) {
                         t_s[g] = t; t_s[32 + g] = tier;
                         if (t >= 0 && t != code_get(code, g)) atomicMin(&first_flip, g);
