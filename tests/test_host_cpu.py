@@ -99,3 +99,25 @@ def test_bench_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["config"]["workload"] == bench.workload_name("c3", 100000, 64, 8)          # the string our arm prints too
     assert d["e2e"] == {"value": d["value"], "unit": "sweeps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0
+
+
+def test_batch_and_nmft_host_checks_need_no_device():
+    """Argument checks of the additions to the reference surfaces happen on the host, before any device call."""
+    import numpy as np
+    from numpy.random import RandomState
+
+    from desman_b200 import sampletau
+    from desman_b200.Init_NMFT import Init_NMFT
+    with pytest.raises(ValueError, match="at least one problem"):
+        sampletau.Batch([])
+    a, b = np.ones((3, 5, 4), dtype=np.int64), np.ones((2, 6, 4), dtype=np.int64)
+    with pytest.raises(ValueError, match="every problem must be"):
+        sampletau.Batch([a, b])
+    with pytest.raises(ValueError, match="dtype mismatch"):
+        sampletau.Batch([a.astype(np.int32)])
+    n = Init_NMFT(a, 2, RandomState(1))
+    x = np.array([[0.0, 1.0], [1e-300, 0.5]])
+    y = n._adjustment_input(x)                                   # Init_NMFT.py:93-97: floor at the machine epsilon, input untouched
+    assert np.array_equal(y, np.maximum(x, np.finfo(np.float64).eps)) and x[0, 0] == 0.0
+    n.random_initialize()                                        # host RNG in the reference's order: shapes of the factors
+    assert n.tau.shape == (12, 2) and n.gamma.shape == (2, 5) and np.allclose(n.gamma.sum(0), 1.0)
