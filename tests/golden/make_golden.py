@@ -391,6 +391,33 @@ def make_assign_kat():
     np.savez_compressed(os.path.join(HERE, "assign_kat.npz"), **out)
 
 
+def make_fix_tau_kat():
+    """storeHLogProb of the UNMODIFIED sampleTauFixTau (HaploSNP_Sampler.py:196-222): the normalised log-probabilities of the
+    step at strain H under the tau the call came in with -- a deterministic function of the inputs (the draws that follow come
+    from numpy's stream and are not pinned).  Pins oracle_sample_tau_fix_philox's logp."""
+    out = {}
+    for ci, (V, S, G, H, seed) in enumerate([(30, 12, 4, 0, 5), (24, 40, 6, 3, 9), (16, 9, 3, 2, 2), (12, 20, 5, 4, 7)]):
+        rng = np.random.default_rng(seed)
+        counts = synth_counts(rng, V, S, 40.0, zero_rows=1)
+        tau = np.zeros((V, G, 4), dtype=np.int64)
+        idx = rng.integers(0, 4, size=(V, G))
+        np.put_along_axis(tau, idx[:, :, None], 1, axis=2)
+        gamma = rng.dirichlet(np.ones(G), size=S)
+        eta = 0.95 * np.identity(4) + 0.0125 + 0.002 * rng.random((4, 4))
+        eta /= eta.sum(1)[:, None]
+        h = _bare_sampler(counts, G)
+        h.randomState = RandomState(seed)
+        work = tau.copy()
+        logp = h.sampleTauFixTau(work, H, gamma, eta)
+        out[f"c{ci}_meta"] = np.array([V, S, G, H, seed], dtype=np.int64)
+        out[f"c{ci}_counts"] = counts.astype(np.int32)
+        out[f"c{ci}_tau"] = idx.astype(np.uint8); out[f"c{ci}_gamma"] = gamma; out[f"c{ci}_eta"] = eta
+        out[f"c{ci}_logp"] = logp
+        assert np.array_equal(work[:, :H], tau[:, :H])                 # strains below H are pinned
+    np.savez_compressed(os.path.join(HERE, "fix_tau_kat.npz"), **out)
+    print("fix_tau_kat.npz written")
+
+
 def make_nmft_steps_kat():
     """Single steps of the UNMODIFIED Init_NMFT class (div_objective, div_update + _adjustment, div_update_tau,
     div_update_gamma, factorize_gamma) on small problems: pins desman_b200.Init_NMFT's step methods."""
@@ -435,6 +462,8 @@ if __name__ == "__main__":
         make_assign_kat()
     if "nmft" in what:
         make_nmft_steps_kat()
+    if "fixtau" in what:
+        make_fix_tau_kat()
     if "input" in what:
         make_cog0015_input()
     if "i3" in what:
