@@ -418,6 +418,35 @@ def make_fix_tau_kat():
     print("fix_tau_kat.npz written")
 
 
+def make_host_helpers_kat():
+    """Small host-side methods of the UNMODIFIED class that the mirror re-implements in numpy: normaliseLogProb (:186-194),
+    logMean (:526-540), tauDist (:137-147), baseProbabilityGivenTau (:129-134), updateTauIndices / mapTauState (:224-231)."""
+    rng = np.random.default_rng(77)
+    V, S, G = 9, 7, 6
+    counts = synth_counts(rng, V, S, 20.0)
+    h = _bare_sampler(counts, G)
+    h.tauMap = np.zeros((G, 4), dtype=np.int64)
+    for g in range(G):
+        for a in range(4):
+            h.tauMap[g, a] = a * (4 ** (G - g - 1))
+    idx = rng.integers(0, 4, size=(V, G))
+    tau = np.zeros((V, G, 4), dtype=np.int64)
+    np.put_along_axis(tau, idx[:, :, None], 1, axis=2)
+    h.tau = tau
+    h.tauIndices = np.zeros(V, dtype=np.int64)
+    h.updateTauIndices()
+    lv = [rng.normal(-50.0, 30.0, size=4) for _ in range(5)] + [np.array([-1e4, -1e4 - 1.0, -2e4, -1e4 - 0.5])]
+    ls = [rng.normal(-1e3, 5.0, size=n) for n in (3, 17, 50)]
+    gamma = rng.dirichlet(np.ones(G), size=S)
+    eta = 0.9 * np.identity(4) + 0.025
+    np.savez_compressed(os.path.join(HERE, "host_helpers_kat.npz"), tau=idx.astype(np.uint8), tauIndices=h.tauIndices,
+                        lv=np.array(lv), lv_out=np.array([h.normaliseLogProb(x) for x in lv]),
+                        ls0=ls[0], ls1=ls[1], ls2=ls[2], ls_out=np.array([h.logMean(x) for x in ls]),
+                        dist=np.array([h.tauDist(tau[i], tau[i + 1]) for i in range(V - 1)], dtype=np.int64),
+                        gamma=gamma, eta=eta, base_prob=np.array([h.baseProbabilityGivenTau(tau[i], gamma, eta) for i in range(V)]))
+    print("host_helpers_kat.npz written")
+
+
 def make_nmft_steps_kat():
     """Single steps of the UNMODIFIED Init_NMFT class (div_objective, div_update + _adjustment, div_update_tau,
     div_update_gamma, factorize_gamma) on small problems: pins desman_b200.Init_NMFT's step methods."""
@@ -464,6 +493,8 @@ if __name__ == "__main__":
         make_nmft_steps_kat()
     if "fixtau" in what:
         make_fix_tau_kat()
+    if "helpers" in what:
+        make_host_helpers_kat()
     if "input" in what:
         make_cog0015_input()
     if "i3" in what:

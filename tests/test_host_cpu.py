@@ -121,3 +121,28 @@ def test_batch_and_nmft_host_checks_need_no_device():
     assert np.array_equal(y, np.maximum(x, np.finfo(np.float64).eps)) and x[0, 0] == 0.0
     n.random_initialize()                                        # host RNG in the reference's order: shapes of the factors
     assert n.tau.shape == (12, 2) and n.gamma.shape == (2, 5) and np.allclose(n.gamma.sum(0), 1.0)
+
+
+def test_class_host_helpers_match_the_reference_class():
+    """The small numpy methods of the class mirror against golden vectors of the UNMODIFIED reference class
+    (tests/golden/make_golden.py helpers); the constructor and these methods need no device."""
+    import numpy as np
+    from numpy.random import RandomState
+
+    from conftest import golden, onehot
+    from desman_b200.HaploSNP_Sampler import HaploSNP_Sampler
+    z = golden("host_helpers_kat.npz")
+    tau = onehot(z["tau"])
+    V, G = tau.shape[0], tau.shape[1]
+    S = z["gamma"].shape[0]
+    hs = HaploSNP_Sampler(np.ones((V, S, 4), dtype=np.int64), G, RandomState(1))
+    hs.tau = tau
+    hs.updateTauIndices()
+    assert np.array_equal(np.asarray(hs.tauIndices), z["tauIndices"])            # :224-231: base-4 code, strain 0 most significant
+    for x, y in zip(z["lv"], z["lv_out"]):
+        assert np.allclose(hs.normaliseLogProb(x), y, rtol=1e-12, atol=1e-12)    # :186-194
+    for k in range(3):
+        assert np.isclose(hs.logMean(z["ls%d" % k]), z["ls_out"][k], rtol=1e-12)  # :526-540
+    assert [hs.tauDist(tau[i], tau[i + 1]) for i in range(V - 1)] == z["dist"].tolist()   # :137-147
+    for i in range(V):
+        assert np.allclose(hs.baseProbabilityGivenTau(tau[i], z["gamma"], z["eta"]), z["base_prob"][i], rtol=1e-12)   # :129-134
