@@ -447,6 +447,32 @@ def make_host_helpers_kat():
     print("host_helpers_kat.npz written")
 
 
+def make_degenerate_kat():
+    """calculateSND (:712-730), compSND (:747-770), variableTau (:732-745) and removeDegenerate (:771-832) of the UNMODIFIED
+    class (real constructor, G = 5) on a tau with duplicated haplotypes."""
+    rng = np.random.default_rng(31)
+    V, S, G = 14, 6, 5
+    counts = synth_counts(rng, V, S, 20.0)
+    h = hsnp.HaploSNP_Sampler(counts, G, RandomState(31), max_iter=2)
+    idx = rng.integers(0, 4, size=(V, G))
+    idx[:, 3] = idx[:, 0]                          # strain 3 == strain 0, strain 4 == strain 1: two merges
+    idx[:, 4] = idx[:, 1]
+    idx[5, :] = 2                                  # one site without variation
+    tau = np.zeros((V, G, 4), dtype=np.int64)
+    np.put_along_axis(tau, idx[:, :, None], 1, axis=2)
+    gamma = rng.dirichlet(np.ones(G), size=S)
+    h.tau = tau.copy(); h.gamma = gamma.copy()
+    other = np.zeros((V, 3, 4), dtype=np.int64)
+    np.put_along_axis(other, rng.integers(0, 4, size=(V, 3))[:, :, None], 1, axis=2)
+    out = dict(tau=idx.astype(np.uint8), gamma=gamma, other=np.argmax(other, 2).astype(np.uint8),
+               snd=h.calculateSND(h.tau), comp=h.compSND(h.tau, other), variable=h.variableTau(h.tau))
+    h.removeDegenerate()
+    out.update(G_after=np.array(h.G), tau_after=np.argmax(h.tau, 2).astype(np.uint8), gamma_after=h.gamma,
+               tauIndices_after=np.asarray(h.tauIndices), alpha_after=h.alpha, gamma_store_shape=np.array(h.gamma_store.shape))
+    np.savez_compressed(os.path.join(HERE, "degenerate_kat.npz"), **out)
+    print("degenerate_kat.npz written, G %d -> %d" % (G, h.G))
+
+
 def make_nmft_steps_kat():
     """Single steps of the UNMODIFIED Init_NMFT class (div_objective, div_update + _adjustment, div_update_tau,
     div_update_gamma, factorize_gamma) on small problems: pins desman_b200.Init_NMFT's step methods."""
@@ -495,6 +521,8 @@ if __name__ == "__main__":
         make_fix_tau_kat()
     if "helpers" in what:
         make_host_helpers_kat()
+    if "degenerate" in what:
+        make_degenerate_kat()
     if "input" in what:
         make_cog0015_input()
     if "i3" in what:

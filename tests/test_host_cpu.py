@@ -146,3 +146,28 @@ def test_class_host_helpers_match_the_reference_class():
     assert [hs.tauDist(tau[i], tau[i + 1]) for i in range(V - 1)] == z["dist"].tolist()   # :137-147
     for i in range(V):
         assert np.allclose(hs.baseProbabilityGivenTau(tau[i], z["gamma"], z["eta"]), z["base_prob"][i], rtol=1e-12)   # :129-134
+
+
+def test_snd_and_remove_degenerate_match_the_reference_class():
+    """calculateSND / compSND / variableTau / removeDegenerate of the mirror against golden vectors of the UNMODIFIED class
+    (tests/golden/make_golden.py degenerate): two pairs of identical haplotypes are merged and their gamma columns added."""
+    import numpy as np
+    from numpy.random import RandomState
+
+    from conftest import golden, onehot
+    from desman_b200.HaploSNP_Sampler import HaploSNP_Sampler
+    z = golden("degenerate_kat.npz")
+    tau, other = onehot(z["tau"]), onehot(z["other"])
+    V, G = tau.shape[0], tau.shape[1]
+    S = z["gamma"].shape[0]
+    hs = HaploSNP_Sampler(np.ones((V, S, 4), dtype=np.int64), G, RandomState(1), max_iter=2)
+    hs.tau, hs.gamma = tau.copy(), z["gamma"].copy()
+    assert np.array_equal(hs.calculateSND(hs.tau), z["snd"])                    # :712-730
+    assert np.array_equal(hs.compSND(hs.tau, other), z["comp"])                 # :747-770
+    assert np.array_equal(hs.variableTau(hs.tau), z["variable"])                # :732-745
+    hs.removeDegenerate()                                                       # :771-832
+    assert hs.G == int(z["G_after"]) == 3
+    assert np.array_equal(np.argmax(hs.tau, 2), z["tau_after"])
+    assert np.allclose(hs.gamma, z["gamma_after"], rtol=0, atol=0)
+    assert np.array_equal(np.asarray(hs.tauIndices), z["tauIndices_after"])
+    assert np.array_equal(hs.alpha, z["alpha_after"]) and tuple(hs.gamma_store.shape) == tuple(z["gamma_store_shape"])
